@@ -1,0 +1,169 @@
+/*
+ * qsae_b200.h -- C ABI of libqsae_b200.so: the B200 (sm_100a) forward hot path of
+ * ASSERT-KTH/QuantizedSAE (b_sae / baseline_sae / q_sae / t_sae).
+ *
+ * The reference has no FFI of its own: its boundary is the Python nn.Module API
+ * (src/quantized_sae/sae/*.py). Each entry point below replaces a group of eager ATen ops
+ * inside one reference forward; the citation says which. quantizedsae_b200/sae/*.py mirrors
+ * the nn.Module API on top of these calls (via ctypes, quantizedsae_b200/_lib.py) and
+ * INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only: device (or, where stated, host) pointers, sizes, a CUDA stream
+ *     handle passed as void* (cudaStream_t / CUstream; NULL = legacy default stream);
+ *   - every function returns 0 on success or a negative qsae_status; the message for the
+ *     calling thread is available from qsae_last_error();
+ *   - no hidden device allocation: scratch memory is caller-provided, its size comes from
+ *     the matching *_workspace_bytes() query;
+ *   - all launches are asynchronous on the given stream; nothing synchronises the device
+ *     except the *_host() pipeline entry, which returns after its last copy has landed;
+ *   - row-major everywhere; "bf16" buffers are raw uint16_t bit patterns.
+ */
+#ifndef QSAE_B200_H
+#define QSAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QSAE_ABI_VERSION 1
+
+typedef enum qsae_status {
+  QSAE_OK = 0,
+  QSAE_ERR_INVALID_ARGUMENT = -1,   /* bad shape / null pointer / unsupported size          */
+  QSAE_ERR_WORKSPACE_TOO_SMALL = -2,
+  QSAE_ERR_CUDA = -3,               /* a CUDA runtime / driver call failed                   */
+  QSAE_ERR_UNSUPPORTED_DEVICE = -4, /* not an sm_100 device                                  */
+  QSAE_ERR_K_OUT_OF_RANGE = -5      /* k > H (torch.topk raises RuntimeError here)           */
+} qsae_status;
+
+/* encoder epilogue applied before selection (reference: none for b_sae/baseline,
+ * ReLU for t_sae -- sae/binary.py:82-84, sae/baseline.py:8-10, sae/ternary.py:95-98) */
+typedef enum qsae_act { QSAE_ACT_NONE = 0, QSAE_ACT_RELU = 1 } qsae_act;
+
+int qsae_abi_version(void);
+const char* qsae_last_error(void);
+/* 0 if the current device is sm_100 (B200), QSAE_ERR_UNSUPPORTED_DEVICE otherwise */
+int qsae_check_device(void);
+
+/* ---------------------------------------------------------------------------------------
+ * One-time weight preparation (cached by the host modules per parameter version)
+ * ------------------------------------------------------------------------------------- */
+
+/* float32 -> bf16 (round to nearest even). Used for encoder.0.weight [H,D] and for x.
+ * Replaces nothing in the reference (which is fp32 throughout); it is the operand format of
+ * the tcgen05 encoder. n = number of elements. */
+int qsae_cast_f32_to_bf16(const float* src, uint16_t* dst, size_t n, void* stream);
+
+/* binary_decoder.quantized_int_weights() (sae/binary.py:49-58) fused with packing:
+ *   bit_i = sigmoid(logit) > 0.5 ; int_w = sum_i bit_i * c_i, c = [1,2,..,-2^(n-1)].
+ * logits [H, D*n_bits] (bit i of feature d at column d*n_bits+i, LSB first, sign bit last).
+ * n_bits <= 4: packed [H, D/2] bytes, feature 2j in the low nibble of byte j (two's complement)
+ * n_bits  > 4: packed [H, D] int8.
+ * stats (device, 2 doubles, optional, must be zeroed by the caller):
+ *   stats[0] += sum p(1-p)2^i  (numerator of polarize_loss, sae/binary.py:41-42)
+ *   stats[1]  = max |p - bit|  (how far the soft forward is from the hard dictionary)     */
+int qsae_pack_bitplanes(const float* logits, int H, int D, int n_bits, uint8_t* packed,
+                        double* stats, void* stream);
+
+/* binary_decoder.quantized_int_weights_continuous() (sae/binary.py:60-69), i.e. the soft
+ * effective weights of the reference forward (sae/binary.py:26-35): rows [H, D] float32. */
+int qsae_dequant_soft(const float* logits, int H, int D, int n_bits, float* rows, void* stream);
+
+/* [R, C] float32 -> [C, R] float32. baseline_sae keeps decoder.weight as [D, H]
+ * (sae/baseline.py:12); the sparse decoder gathers feature rows, so it needs [H, D]. */
+int qsae_transpose_f32(const float* src, int R, int C, float* dst, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Encoder + per-row top-k  (nn.Linear + Tensor.topk: sae/binary.py:92-94,
+ * sae/baseline.py:23-36, sae/ternary.py:102-114)
+ *
+ * z = x W^T + b on the tcgen05 tensor cores (bf16 operands, fp32 accumulate in TMEM); the
+ * per-row selection runs in the GEMM epilogue straight out of TMEM, so the dense [B,H]
+ * pre-activation never reaches HBM. Output is ordered by (value desc, index asc).
+ *
+ * exact = 0: values are the tensor-core results. They equal the fp32 reference up to fp32
+ *            accumulation order when x and W are bf16-representable (benchmark precondition).
+ * exact = 1: the bf16 pass selects k+QSAE_RESCORE_MARGIN candidates per row, which are
+ *            re-scored in fp32 from x_f32 / w_f32 and re-selected; flags[b] != 0 marks a row
+ *            whose selection could not be certified against bf16 rounding.
+ * Limits: D % 8 == 0, 8 <= D <= 512, 1 <= k <= QSAE_MAX_K, k <= H.
+ * ------------------------------------------------------------------------------------- */
+#define QSAE_MAX_K 224
+#define QSAE_RESCORE_MARGIN 16
+
+int qsae_encode_topk_workspace_bytes(int B, int H, int D, int k, size_t* bytes);
+
+int qsae_encode_topk(const float* x_f32,      /* [B, D] device                              */
+                     const uint16_t* w_bf16,   /* [H, D] from qsae_cast_f32_to_bf16          */
+                     const float* w_f32,       /* [H, D] original weights; may be NULL if !exact */
+                     const float* b_enc,       /* [H]                                        */
+                     int B, int H, int D, int k, int act, int exact,
+                     float* out_vals,          /* [B, k]                                     */
+                     int32_t* out_idx,         /* [B, k]                                     */
+                     int32_t* out_flags,       /* [B] or NULL                                */
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Exact fp32 CUDA-core encoder for a few rows: z[r, :] = x[rows[r], :] W^T + b (+act), dense
+ * [R, H] output. Fallback for rows flagged by qsae_encode_topk(exact=1) and GPU-side
+ * cross-check in the tests. Not a throughput path. */
+int qsae_encode_dense_f32(const float* x_f32, const int32_t* rows /* [R] or NULL = 0..R-1 */,
+                          int R, const float* w_f32, const float* b_enc, int H, int D, int act,
+                          float* z /* [R, H] */, void* stream);
+
+/* Diagnostic: the tensor-core encoder with its accumulator (+bias, +act) dumped densely to
+ * z [B, H] instead of being consumed by the selection. Same kernel, same pipeline; used by the
+ * tests to check the tcgen05 GEMM itself against an fp32 matmul. Workspace as for
+ * qsae_encode_topk. Not a product path (it writes the matrix the product path avoids). */
+int qsae_encode_dense_tc(const float* x_f32, const uint16_t* w_bf16, const float* b_enc, int B, int H,
+                         int D, int act, float* z, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* Per-row top-k of a dense [R, H] matrix, same ordering rule. out_* are [R, k]. */
+int qsae_topk_dense_workspace_bytes(int R, int H, int k, size_t* bytes);
+int qsae_topk_dense(const float* z, int R, int H, int k, float* out_vals, int32_t* out_idx,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Sparse decoders: recon[b,:] = scale * sum_j vals[b,j] * dict[idx[b,j], :] + bias
+ * (replace the dense latent.matmul(int_weights) of sae/binary.py:38 and the dense
+ * nn.Linear decode of sae/baseline.py:29). idx < 0 entries are skipped.
+ * ------------------------------------------------------------------------------------- */
+int qsae_decode_int4(const float* vals, const int32_t* idx, int B, int k,
+                     const uint8_t* packed /* [H, D/2] */, int H, int D, float scale,
+                     const float* bias /* [D] or NULL */, float* recon /* [B, D] */, void* stream);
+int qsae_decode_int8(const float* vals, const int32_t* idx, int B, int k,
+                     const int8_t* rows /* [H, D] */, int H, int D, float scale,
+                     const float* bias, float* recon, void* stream);
+int qsae_decode_rows_f32(const float* vals, const int32_t* idx, int B, int k,
+                         const float* rows /* [H, D] */, int H, int D, float scale,
+                         const float* bias, float* recon, void* stream);
+
+/* latent * mask (sae/binary.py:96-99) / zeros_like + scatter_ (sae/baseline.py:38-39):
+ * dense [B, H] float32 from the sparse form. Zero-fills `dense` first. */
+int qsae_densify(const float* vals, const int32_t* idx, int B, int k, int H, float* dense,
+                 void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * End-to-end b_sae forward on HOST buffers (the reference-facing call of bench.py's e2e leg):
+ * chunks the batch, overlaps H2D copy / kernels / D2H copy on internal streams, returns when
+ * the outputs are in host memory. Weights stay device-resident in a prepared handle.
+ * ------------------------------------------------------------------------------------- */
+typedef struct qsae_bsae_plan qsae_bsae_plan;
+
+int qsae_bsae_plan_create(const float* w_enc_f32_dev /* [H,D] */, const float* b_enc_dev /* [H] */,
+                          const float* dec_logits_dev /* [H, D*n_bits] */,
+                          const float* dec_bias_dev /* [D] */, int H, int D, int n_bits,
+                          float gamma, int k, int max_chunk_rows, qsae_bsae_plan** plan);
+void qsae_bsae_plan_destroy(qsae_bsae_plan* plan);
+/* x_host [B,D] float32 (pinned for full overlap); outputs: vals/idx [B,k], recon [B,D] on host */
+int qsae_bsae_forward_host(qsae_bsae_plan* plan, const float* x_host, int B, float* vals_host,
+                           int32_t* idx_host, float* recon_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QSAE_B200_H */

@@ -1,0 +1,268 @@
+"""ctypes binding of libqsae_b200.so (C ABI: include/qsae_b200.h).
+
+There is no fallback: if the library is missing it is built with nvcc, and if that fails, or a
+call returns a non-zero status, a QsaeError is raised. torch is used only to own device memory
+and to supply the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libqsae_b200.so"
+
+QSAE_MAX_K = 224
+QSAE_RESCORE_MARGIN = 16
+ACT_NONE, ACT_RELU = 0, 1
+
+# every symbol include/qsae_b200.h declares: name -> (restype, argtypes)
+_vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+SYMBOLS = {
+    "qsae_abi_version": (_i, []),
+    "qsae_last_error": (C.c_char_p, []),
+    "qsae_check_device": (_i, []),
+    "qsae_cast_f32_to_bf16": (_i, [_vp, _vp, _sz, _vp]),
+    "qsae_pack_bitplanes": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "qsae_dequant_soft": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "qsae_transpose_f32": (_i, [_vp, _i, _i, _vp, _vp]),
+    "qsae_encode_topk_workspace_bytes": (_i, [_i, _i, _i, _i, C.POINTER(_sz)]),
+    "qsae_encode_topk": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "qsae_encode_dense_tc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "qsae_encode_dense_f32": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "qsae_topk_dense_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
+    "qsae_topk_dense": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "qsae_decode_int4": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _f, _vp, _vp, _vp]),
+    "qsae_decode_int8": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _f, _vp, _vp, _vp]),
+    "qsae_decode_rows_f32": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _f, _vp, _vp, _vp]),
+    "qsae_densify": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "qsae_bsae_plan_create": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _i, C.POINTER(_vp)]),
+    "qsae_bsae_plan_destroy": (None, [_vp]),
+    "qsae_bsae_forward_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+}
+
+
+class QsaeError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"libqsae_b200 status {status}: {message}")
+        self.status = status
+
+
+_lib = None
+launch_count = 0  # kernels launched through this binding (bench.py reports it)
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    """dlopen the library and type every symbol; raises if it cannot be loaded."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        if not build_if_missing:
+            raise QsaeError(-100, f"{LIB_PATH} is missing (run python -m quantizedsae_b200.build)")
+        from . import build as _build
+
+        _build.build()
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    if lib.qsae_abi_version() != 1:
+        raise QsaeError(-101, "ABI version mismatch between _lib.py and libqsae_b200.so")
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        msg = load().qsae_last_error().decode(errors="replace")
+        if status == -5:
+            raise RuntimeError(msg)  # torch.topk raises RuntimeError for k > H as well
+        raise QsaeError(status, msg)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise QsaeError(-102, "libqsae_b200 kernels need CUDA tensors; there is no CPU path")
+        if t is not None and not t.is_contiguous():
+            raise QsaeError(-103, "libqsae_b200 kernels need contiguous tensors")
+
+
+# ------------------------------------------------------------------------------------------
+# thin typed wrappers (allocate outputs with torch, launch on torch's current stream)
+# ------------------------------------------------------------------------------------------
+
+def cast_bf16(src: torch.Tensor) -> torch.Tensor:
+    global launch_count
+    _need_cuda(src)
+    assert src.dtype == torch.float32
+    dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    check(load().qsae_cast_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()))
+    launch_count += 1
+    return dst
+
+
+def pack_bitplanes(logits: torch.Tensor, D: int, n_bits: int, want_stats: bool = True):
+    """-> (packed uint8 [H, D/2] or int8-as-uint8 [H, D], polarize_loss float|None, max_gap float|None)."""
+    global launch_count
+    _need_cuda(logits)
+    H = logits.shape[0]
+    assert logits.dtype == torch.float32 and logits.shape[1] == D * n_bits
+    cols = D // 2 if n_bits <= 4 else D
+    packed = torch.empty((H, cols), dtype=torch.uint8, device=logits.device)
+    stats = torch.zeros(2, dtype=torch.float64, device=logits.device) if want_stats else None
+    check(load().qsae_pack_bitplanes(logits.data_ptr(), H, D, n_bits, packed.data_ptr(), _ptr(stats), _stream()))
+    launch_count += 1
+    if not want_stats:
+        return packed, None, None
+    s = stats.cpu()
+    return packed, float(s[0]) / (H * D * n_bits), float(s[1])
+
+
+def dequant_soft(logits: torch.Tensor, D: int, n_bits: int) -> torch.Tensor:
+    global launch_count
+    _need_cuda(logits)
+    H = logits.shape[0]
+    rows = torch.empty((H, D), dtype=torch.float32, device=logits.device)
+    check(load().qsae_dequant_soft(logits.data_ptr(), H, D, n_bits, rows.data_ptr(), _stream()))
+    launch_count += 1
+    return rows
+
+
+def transpose(src: torch.Tensor) -> torch.Tensor:
+    global launch_count
+    _need_cuda(src)
+    R, Cc = src.shape
+    dst = torch.empty((Cc, R), dtype=torch.float32, device=src.device)
+    check(load().qsae_transpose_f32(src.data_ptr(), R, Cc, dst.data_ptr(), _stream()))
+    launch_count += 1
+    return dst
+
+
+def encode_topk_workspace_bytes(B: int, H: int, D: int, k: int) -> int:
+    n = _sz(0)
+    check(load().qsae_encode_topk_workspace_bytes(B, H, D, k, C.byref(n)))
+    return int(n.value)
+
+
+_ws_cache: dict = {}
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def encode_topk(x: torch.Tensor, w_bf16: torch.Tensor, w_f32: torch.Tensor | None, b_enc: torch.Tensor,
+                k: int, act: int = ACT_NONE, exact: bool = False, want_flags: bool = False):
+    """-> (vals [B,k] f32, idx [B,k] i32, flags [B] i32 | None)"""
+    global launch_count
+    _need_cuda(x, w_bf16, w_f32, b_enc)
+    B, D = x.shape
+    H = w_bf16.shape[0]
+    assert x.dtype == torch.float32 and w_bf16.dtype == torch.bfloat16 and b_enc.dtype == torch.float32
+    vals = torch.empty((B, k), dtype=torch.float32, device=x.device)
+    idx = torch.empty((B, k), dtype=torch.int32, device=x.device)
+    flags = torch.empty((B,), dtype=torch.int32, device=x.device) if want_flags else None
+    if B == 0:
+        return vals, idx, flags
+    nbytes = encode_topk_workspace_bytes(B, H, D, k)
+    ws = _workspace(x.device, nbytes)
+    check(load().qsae_encode_topk(x.data_ptr(), w_bf16.data_ptr(), _ptr(w_f32), b_enc.data_ptr(), B, H, D, k,
+                                  act, 1 if exact else 0, vals.data_ptr(), idx.data_ptr(), _ptr(flags),
+                                  ws.data_ptr(), ws.numel(), _stream()))
+    launch_count += 3
+    return vals, idx, flags
+
+
+def encode_dense_tc(x: torch.Tensor, w_bf16: torch.Tensor, b_enc: torch.Tensor, act: int = ACT_NONE) -> torch.Tensor:
+    """Diagnostic: dense z [B,H] straight from the tcgen05 encoder kernel."""
+    global launch_count
+    _need_cuda(x, w_bf16, b_enc)
+    B, D = x.shape
+    H = w_bf16.shape[0]
+    z = torch.empty((B, H), dtype=torch.float32, device=x.device)
+    ws = _workspace(x.device, encode_topk_workspace_bytes(B, H, D, 1))
+    check(load().qsae_encode_dense_tc(x.data_ptr(), w_bf16.data_ptr(), b_enc.data_ptr(), B, H, D, act,
+                                      z.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    launch_count += 2
+    return z
+
+
+def encode_dense(x: torch.Tensor, w_f32: torch.Tensor, b_enc: torch.Tensor | None, act: int = ACT_NONE,
+                 rows: torch.Tensor | None = None) -> torch.Tensor:
+    global launch_count
+    _need_cuda(x, w_f32, b_enc, rows)
+    R = x.shape[0] if rows is None else rows.numel()
+    H, D = w_f32.shape
+    z = torch.empty((R, H), dtype=torch.float32, device=x.device)
+    check(load().qsae_encode_dense_f32(x.data_ptr(), _ptr(rows), R, w_f32.data_ptr(), _ptr(b_enc), H, D, act,
+                                       z.data_ptr(), _stream()))
+    launch_count += 1
+    return z
+
+
+def topk_dense(z: torch.Tensor, k: int):
+    global launch_count
+    _need_cuda(z)
+    R, H = z.shape
+    vals = torch.empty((R, k), dtype=torch.float32, device=z.device)
+    idx = torch.empty((R, k), dtype=torch.int32, device=z.device)
+    if R == 0:
+        return vals, idx
+    n = _sz(0)
+    check(load().qsae_topk_dense_workspace_bytes(R, H, k, C.byref(n)))
+    ws = _workspace(z.device, int(n.value))
+    check(load().qsae_topk_dense(z.data_ptr(), R, H, k, vals.data_ptr(), idx.data_ptr(), ws.data_ptr(),
+                                 ws.numel(), _stream()))
+    launch_count += 2
+    return vals, idx
+
+
+def _decode(fn_name: str, vals, idx, dict_t, H, D, scale, bias):
+    global launch_count
+    _need_cuda(vals, idx, dict_t, bias)
+    B, k = vals.shape
+    recon = torch.empty((B, D), dtype=torch.float32, device=vals.device)
+    check(getattr(load(), fn_name)(vals.data_ptr(), idx.data_ptr(), B, k, dict_t.data_ptr(), H, D, float(scale),
+                                   _ptr(bias), recon.data_ptr(), _stream()))
+    launch_count += 1
+    return recon
+
+
+def decode_int4(vals, idx, packed, H, D, scale, bias):
+    return _decode("qsae_decode_int4", vals, idx, packed, H, D, scale, bias)
+
+
+def decode_int8(vals, idx, rows_i8, H, D, scale, bias):
+    return _decode("qsae_decode_int8", vals, idx, rows_i8, H, D, scale, bias)
+
+
+def decode_rows_f32(vals, idx, rows, H, D, scale, bias):
+    return _decode("qsae_decode_rows_f32", vals, idx, rows, H, D, scale, bias)
+
+
+def densify(vals: torch.Tensor, idx: torch.Tensor, H: int) -> torch.Tensor:
+    global launch_count
+    _need_cuda(vals, idx)
+    B, k = vals.shape
+    dense = torch.empty((B, H), dtype=torch.float32, device=vals.device)
+    check(load().qsae_densify(vals.data_ptr(), idx.data_ptr(), B, k, H, dense.data_ptr(), _stream()))
+    launch_count += 1
+    return dense

@@ -1,0 +1,370 @@
+// Fused encoder GEMM + per-row top-k candidate selection for sm_100a.
+//
+//   z[b, h] = sum_d x[b, d] * W[h, d] + bias[h]           (nn.Linear, sae/binary.py:82-84,92)
+//   per row b keep the k largest z[b, :]                   (Tensor.topk,  sae/binary.py:94)
+//
+// One CTA owns BM = 128 rows of x (kept resident in shared memory for the whole sweep) and
+// streams W through a TMA/mbarrier ring in tiles of BN = 256 latents x BK = 64. A single
+// thread issues tcgen05.mma (UMMA 128x256x16, bf16 in, fp32 accumulate) into one of two
+// 256-column TMEM accumulators; eight epilogue warps drain the other accumulator with
+// tcgen05.ld, add the bias and run a streaming threshold selection: thread (row, column-half)
+// keeps a running lower bound `thr` of the row's k-th largest value, appends the rare
+// survivors to a small per-row buffer in global memory (L2 resident) and, when a buffer runs
+// full, the warp compacts it cooperatively (bitwise radix bisection to the exact k-th key).
+// The dense [B, H] pre-activation is never written.
+//
+// The latent axis can be split over `n_splits` CTAs per row block (grid.x) to fill the 148 SMs
+// at small batch; every (split, column-half) is an independent sub-stream whose survivors are
+// merged by select_topk.cu.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "kernels.h"
+#include "ptx_sm100.cuh"
+#include "topk_common.cuh"
+
+namespace qsae {
+
+namespace {
+
+constexpr int BM = kEncBM;         // rows of x per CTA (UMMA M)
+constexpr int BN = kEncBN;         // latents per tile (UMMA N)
+constexpr int BK = 64;             // one 128-byte swizzle atom of bf16
+constexpr int UMMA_K = 16;
+constexpr int kStages = 3;         // W ring depth
+constexpr int kABytesPerChunk = BM * BK * 2;   // 16 KiB
+constexpr int kBBytesPerStage = BN * BK * 2;   // 32 KiB
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 128 + kEpiWarps * 32;  // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 bias
+constexpr int kTmemCols = 512;                  // 2 accumulators x 256 columns
+constexpr int CAP = kCandCap;
+
+struct SmemLayout {
+  uint32_t a_off, b_off, bias_off, bar_off, tmem_ptr_off, total;
+};
+__host__ __device__ inline SmemLayout smem_layout(int k_chunks) {
+  SmemLayout L;
+  L.a_off = 0;
+  L.b_off = L.a_off + k_chunks * kABytesPerChunk;
+  L.bias_off = L.b_off + kStages * kBBytesPerStage;
+  L.bar_off = L.bias_off + 2 * BN * 4;
+  L.tmem_ptr_off = L.bar_off + 8 * (1 + 2 * kStages + 6);
+  L.total = L.tmem_ptr_off + 16;
+  return L;
+}
+
+// Warp-cooperative compaction of the 32 per-row buffers owned by this warp's lanes: every buffer
+// holding more than k entries is reduced to its k largest and its owner's threshold is raised to
+// the k-th largest value (see warp_compact_row).
+__device__ __forceinline__ void compact_warp_buffers(uint2* buf, int& cnt, float& thr, int k,
+                                                     int lane) {
+  const unsigned full = 0xffffffffu;
+  __syncwarp();
+#pragma unroll 1
+  for (int r = 0; r < 32; ++r) {
+    const int n = __shfl_sync(full, cnt, r);
+    if (n <= k) continue;
+    const unsigned long long bp =
+        __shfl_sync(full, reinterpret_cast<unsigned long long>(buf), r);
+    float t;
+    const int out = warp_compact_row(reinterpret_cast<uint2*>(bp), n, k, lane, &t);
+    if (lane == r) {
+      cnt = out;
+      thr = t;
+    }
+  }
+  __syncwarp();
+}
+
+template <int K_CHUNKS>
+__global__ void __launch_bounds__(kThreads, 1)
+encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
+                   const __grid_constant__ CUtensorMap tmap_w, EncodeLaunch p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const SmemLayout L = smem_layout(K_CHUNKS);
+  uint8_t* a_smem = smem + L.a_off;
+  uint8_t* b_smem = smem + L.b_off;
+  float* bias_smem = reinterpret_cast<float*>(smem + L.bias_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* a_full = bars;
+  uint64_t* full = bars + 1;
+  uint64_t* empty = full + kStages;
+  uint64_t* tmem_full = empty + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* bias_full = tmem_empty + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L.tmem_ptr_off);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int split = blockIdx.x;
+  const int m0 = blockIdx.y * BM;
+  const int tile_begin = split * p.tiles_per_split;
+  const int tile_end = min(p.n_tiles, tile_begin + p.tiles_per_split);
+  const int n_my_tiles = max(0, tile_end - tile_begin);
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0u) {
+      printf("qsae: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
+    mbar_init(a_full, 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], kEpiWarps);
+      mbar_init(&bias_full[a], 1);
+    }
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer
+    if (lane == 0 && n_my_tiles > 0) {
+      tma_prefetch_desc(&tmap_x);
+      tma_prefetch_desc(&tmap_w);
+      mbar_arrive_expect_tx(a_full, K_CHUNKS * kABytesPerChunk);
+#pragma unroll
+      for (int kc = 0; kc < K_CHUNKS; ++kc)
+        tma_load_2d(a_smem + kc * kABytesPerChunk, &tmap_x, a_full, kc * BK, m0, kPolicyEvictFirst);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < n_my_tiles; ++t) {
+        const int n0 = (tile_begin + t) * BN;
+#pragma unroll 1
+        for (int kc = 0; kc < K_CHUNKS; ++kc) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full[stage], kBBytesPerStage);
+          tma_load_2d(b_smem + stage * kBBytesPerStage, &tmap_w, &full[stage], kc * BK, n0,
+                      kPolicyEvictLast);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- MMA issuer
+    if (lane == 0 && n_my_tiles > 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
+      const uint64_t a_desc0 = umma_desc_kmajor_sw128(smem_u32(a_smem));
+      const uint64_t b_desc0 = umma_desc_kmajor_sw128(smem_u32(b_smem));
+      mbar_wait(a_full, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < n_my_tiles; ++t) {
+        const int acc = t & 1;
+        mbar_wait(&tmem_empty[acc], ((t >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+#pragma unroll 1
+        for (int kc = 0; kc < K_CHUNKS; ++kc) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((kc * kABytesPerChunk) >> 4);
+          const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((stage * kBBytesPerStage) >> 4);
+#pragma unroll
+          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+            // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the
+            // (address >> 4) field of the descriptor
+            umma_f16_ss(d_tmem, a_desc + ks * 2, b_desc + ks * 2, idesc, (kc | ks) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (kc == K_CHUNKS - 1) umma_commit(&tmem_full[acc]);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------- bias tile loader
+    for (int t = 0; t < n_my_tiles; ++t) {
+      const int acc = t & 1;
+      mbar_wait(&tmem_empty[acc], ((t >> 1) & 1) ^ 1u);
+      const int n0 = (tile_begin + t) * BN;
+#pragma unroll
+      for (int i = 0; i < BN / 32; ++i) {
+        const int c = i * 32 + lane;
+        bias_smem[acc * BN + c] = (n0 + c < p.H) ? __ldg(p.bias + n0 + c) : 0.f;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bias_full[acc]);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------- epilogue / selection
+    const int e = warp - 4;
+    const int quad = e & 3;       // TMEM lanes 32*quad .. +31 (hardware: warp_id % 4)
+    const int half = e >> 2;      // columns [half*128, half*128+128) of the tile
+    const int row = m0 + quad * 32 + lane;
+    const bool row_ok = row < p.B;
+    const int nsub = p.n_splits * 2;
+    const int sub = split * 2 + half;
+    uint2* buf = reinterpret_cast<uint2*>(p.cand) +
+                 (static_cast<size_t>(row_ok ? row : 0) * nsub + sub) * CAP;
+    int cnt = 0;
+    float thr = row_ok ? -INFINITY : INFINITY;
+    const int k = p.k_sel;
+    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+
+    for (int t = 0; t < n_my_tiles; ++t) {
+      const int acc = t & 1;
+      const uint32_t ph = (t >> 1) & 1;
+      mbar_wait(&tmem_full[acc], ph);
+      mbar_wait(&bias_full[acc], ph);
+      tc_fence_after();
+      const int n_tile = (tile_begin + t) * BN + half * 128;
+      const float4* bias4 = reinterpret_cast<const float4*>(bias_smem + acc * BN + half * 128);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(lane_taddr + acc * BN + half * 128 + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n_tile + c * 32;
+        float v[32];
+        float vmax = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = bias4[c * 8 + j];
+          v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
+          v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
+          v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (col0 + 32 > p.H) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j >= p.H) v[j] = -INFINITY;
+        }
+        if (p.debug_z != nullptr && row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.H) p.debug_z[static_cast<size_t>(row) * p.H + col0 + j] = v[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) vmax = fmaxf(vmax, v[j]);
+        if (vmax > thr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (v[j] > thr) {
+              buf[cnt] = make_uint2(__float_as_uint(v[j]), static_cast<uint32_t>(col0 + j));
+              ++cnt;
+            }
+          }
+        }
+        if (__any_sync(0xffffffffu, cnt > CAP - 32)) compact_warp_buffers(buf, cnt, thr, k, lane);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+    // leave at most k survivors per sub-stream for the merge kernel
+    if (__any_sync(0xffffffffu, cnt > k)) compact_warp_buffers(buf, cnt, thr, k, lane);
+    if (row_ok) p.cand_cnt[static_cast<size_t>(row) * nsub + sub] = cnt;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) !=
+          cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+// bf16 row-major [rows, cols] -> 2D tensor map with a {64 x box_rows} box, 128-byte swizzle
+bool make_tmap_bf16(CUtensorMap* map, const void* base, int rows, int cols, int box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int K_CHUNKS>
+cudaError_t launch_k(const CUtensorMap& tx, const CUtensorMap& tw, const EncodeLaunch& p,
+                     cudaStream_t stream) {
+  const SmemLayout L = smem_layout(K_CHUNKS);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(encode_topk_kernel<K_CHUNKS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid(p.n_splits, (p.B + BM - 1) / BM);
+  encode_topk_kernel<K_CHUNKS><<<grid, kThreads, L.total, stream>>>(tx, tw, p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+int encode_pick_splits(int B, int H, int num_sms) {
+  const int m_tiles = (B + BM - 1) / BM;
+  const int n_tiles = (H + BN - 1) / BN;
+  int best_s = 1;
+  double best = -1.0;
+  for (int s = 1; s <= kMaxSplits && s <= n_tiles; s *= 2) {
+    const long units = static_cast<long>(m_tiles) * s;
+    const long waves = (units + num_sms - 1) / num_sms;
+    const int tps = (n_tiles + s - 1) / s;
+    // fraction of SM-time doing useful tiles: wave fill x split balance
+    const double eff = (static_cast<double>(units) / (waves * num_sms)) *
+                       (static_cast<double>(n_tiles) / (static_cast<double>(tps) * s));
+    if (eff > best * 1.03) { best = eff; best_s = s; }
+  }
+  return best_s;
+}
+
+const char* encode_topk_launch(const uint16_t* x_bf16, const uint16_t* w_bf16, EncodeLaunch p,
+                               cudaStream_t stream) {
+  CUtensorMap tx, tw;
+  if (!make_tmap_bf16(&tx, x_bf16, p.B, p.D, BM)) return "cuTensorMapEncodeTiled(x) failed";
+  if (!make_tmap_bf16(&tw, w_bf16, p.H, p.D, BN)) return "cuTensorMapEncodeTiled(W) failed";
+  const int kc = (p.D + BK - 1) / BK;
+  cudaError_t e;
+  switch (kc) {
+    case 1: e = launch_k<1>(tx, tw, p, stream); break;
+    case 2: e = launch_k<2>(tx, tw, p, stream); break;
+    case 3: e = launch_k<3>(tx, tw, p, stream); break;
+    case 4: e = launch_k<4>(tx, tw, p, stream); break;
+    case 5: e = launch_k<5>(tx, tw, p, stream); break;
+    case 6: e = launch_k<6>(tx, tw, p, stream); break;
+    case 7: e = launch_k<7>(tx, tw, p, stream); break;
+    case 8: e = launch_k<8>(tx, tw, p, stream); break;
+    default: return "D must be <= 512";
+  }
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+}  // namespace qsae

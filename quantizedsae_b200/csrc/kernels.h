@@ -1,0 +1,78 @@
+// Internal declarations shared by the .cu files behind the C ABI (include/qsae_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace qsae {
+
+constexpr int kEncBM = 128;     // rows of x per CTA
+constexpr int kEncBN = 256;     // latents per accumulator tile
+constexpr int kCandCap = 256;   // capacity of one (row, sub-stream) survivor buffer
+constexpr int kMaxSplits = 16;  // max CTAs sharing one row block along the latent axis
+constexpr int kMaxK = 224;      // == QSAE_MAX_K; survivors after compaction + one 32-wide chunk fit kCandCap
+
+struct EncodeLaunch {
+  int B, H, D;
+  int k_sel;            // survivors kept per sub-stream (k, or k + rescore margin)
+  int n_splits;         // grid.x
+  int tiles_per_split;  // in units of kEncBN latents
+  int n_tiles;          // ceil(H / kEncBN)
+  int act;              // 0 none, 1 relu
+  const float* bias;    // [H]
+  void* cand;           // [B][n_splits*2][kCandCap] {float bits, int32 column}
+  int* cand_cnt;        // [B][n_splits*2]
+  float* debug_z;       // optional dense [B, H] dump of the accumulator (+bias, act); diagnostics only
+};
+
+// encode_topk_sm100.cu
+int encode_pick_splits(int B, int H, int num_sms);
+const char* encode_topk_launch(const uint16_t* x_bf16, const uint16_t* w_bf16, EncodeLaunch p,
+                               cudaStream_t stream);
+
+// select_topk.cu
+struct SelectLaunch {
+  int B, H, D, k_sel, k_out, nsub, act, exact;
+  const void* cand;       // as above
+  const int* cand_cnt;
+  const float* x_f32;     // [B, D]   (exact only)
+  const float* w_f32;     // [H, D]   (exact only)
+  const float* bias;      // [H]      (exact only)
+  float* out_vals;        // [B, k_out]
+  int32_t* out_idx;       // [B, k_out]
+  int32_t* out_flags;     // [B] or null
+};
+const char* select_topk_launch(const SelectLaunch& p, cudaStream_t stream);
+// candidates from a dense [R, H] matrix (one sub-stream per row), same buffer format
+const char* dense_candidates_launch(const float* z, int R, int H, int k, void* cand, int* cand_cnt,
+                                    cudaStream_t stream);
+
+// pack.cu
+const char* cast_bf16_launch(const float* src, uint16_t* dst, size_t n, cudaStream_t stream);
+const char* pack_bitplanes_launch(const float* logits, int H, int D, int n_bits, uint8_t* packed,
+                                  double* stats, cudaStream_t stream);
+const char* dequant_soft_launch(const float* logits, int H, int D, int n_bits, float* rows,
+                                cudaStream_t stream);
+const char* transpose_launch(const float* src, int R, int C, float* dst, cudaStream_t stream);
+
+// decode.cu
+const char* decode_int4_launch(const float* vals, const int32_t* idx, int B, int k,
+                               const uint8_t* packed, int H, int D, float scale, const float* bias,
+                               float* recon, cudaStream_t stream);
+const char* decode_int8_launch(const float* vals, const int32_t* idx, int B, int k,
+                               const int8_t* rows, int H, int D, float scale, const float* bias,
+                               float* recon, cudaStream_t stream);
+const char* decode_f32_launch(const float* vals, const int32_t* idx, int B, int k, const float* rows,
+                              int H, int D, float scale, const float* bias, float* recon,
+                              cudaStream_t stream);
+const char* densify_launch(const float* vals, const int32_t* idx, int B, int k, int H, float* dense,
+                           cudaStream_t stream);
+
+// encode_dense.cu
+const char* encode_dense_launch(const float* x, const int32_t* rows, int R, const float* w,
+                                const float* bias, int H, int D, int act, float* z,
+                                cudaStream_t stream);
+
+inline const char* cuda_err(cudaError_t e) { return e == cudaSuccess ? nullptr : cudaGetErrorString(e); }
+
+}  // namespace qsae

@@ -1,0 +1,168 @@
+// One-time weight preparation kernels (all HBM-bound streaming passes):
+//   fp32 -> bf16 cast, bit-plane logits -> packed two's-complement dictionary (+ polarize stats),
+//   soft (sigmoid) dequantisation, fp32 transpose.
+// Compiled WITHOUT fast-math: the logistic must be the literal 1 / (1 + expf(-w)) that
+// torch evaluates (sae/binary.py:26,52) so the strict 0.5 threshold lands identically.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace qsae {
+
+namespace {
+
+__device__ __forceinline__ float logistic(float w) { return 1.0f / (1.0f + expf(-w)); }
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, size_t n) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t n4 = n / 4;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+    __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&lo);
+    o.y = *reinterpret_cast<uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(dst)[i] = o;
+  }
+  for (size_t i = n4 * 4 + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    __nv_bfloat16 b = __float2bfloat16_rn(src[i]);
+    dst[i] = *reinterpret_cast<uint16_t*>(&b);
+  }
+}
+
+// One thread per output feature (h, d): reads its n_bits logits, emits the integer.
+// Threads of a warp read consecutive features, i.e. a contiguous 32*n_bits*4-byte span.
+template <bool kNibble>
+__global__ void pack_bitplanes_kernel(const float* __restrict__ logits, int H, int D, int n_bits,
+                                      uint8_t* __restrict__ packed, double* stats) {
+  const size_t total = static_cast<size_t>(H) * D;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  double pol = 0.0;
+  float gap = 0.f;
+  // the trip count is warp-uniform (decided on the warp's first feature) because of the shuffle
+  for (size_t f0 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+       f0 - (threadIdx.x & 31) < total; f0 += stride) {
+    const bool in = f0 < total;
+    int value = 0;
+    if (in) {
+      const float* lp = logits + f0 * n_bits;
+      float polf = 0.f;
+      for (int i = 0; i < n_bits; ++i) {
+        const float p = logistic(lp[i]);
+        const int bit = p > 0.5f ? 1 : 0;
+        const int w = 1 << i;
+        value += (i == n_bits - 1) ? -bit * w : bit * w;
+        polf += p * (1.0f - p) * static_cast<float>(w);
+        gap = fmaxf(gap, fabsf(p - static_cast<float>(bit)));
+      }
+      pol += static_cast<double>(polf);
+    }
+    if (kNibble) {
+      // features 2j (low nibble) and 2j+1 (high nibble) sit in adjacent lanes; D is even
+      const int nib = value & 0xF;
+      const int other = __shfl_down_sync(0xffffffffu, nib, 1);
+      if (in && (f0 & 1) == 0) packed[f0 >> 1] = static_cast<uint8_t>(nib | (other << 4));
+    } else {
+      if (in) packed[f0] = static_cast<uint8_t>(static_cast<int8_t>(value));
+    }
+  }
+  if (stats != nullptr) {
+    // block reduce, one atomic pair per block
+    __shared__ double s_pol[32];
+    __shared__ float s_gap[32];
+    for (int o = 16; o > 0; o >>= 1) {
+      pol += __shfl_xor_sync(0xffffffffu, pol, o);
+      gap = fmaxf(gap, __shfl_xor_sync(0xffffffffu, gap, o));
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s_pol[warp] = pol; s_gap[warp] = gap; }
+    __syncthreads();
+    if (warp == 0) {
+      const int nw = blockDim.x >> 5;
+      pol = lane < nw ? s_pol[lane] : 0.0;
+      gap = lane < nw ? s_gap[lane] : 0.f;
+      for (int o = 16; o > 0; o >>= 1) {
+        pol += __shfl_xor_sync(0xffffffffu, pol, o);
+        gap = fmaxf(gap, __shfl_xor_sync(0xffffffffu, gap, o));
+      }
+      if (lane == 0) {
+        atomicAdd(&stats[0], pol);
+        // non-negative doubles order like their bit patterns
+        atomicMax(reinterpret_cast<unsigned long long*>(&stats[1]),
+                  static_cast<unsigned long long>(__double_as_longlong(static_cast<double>(gap))));
+      }
+    }
+  }
+}
+
+__global__ void dequant_soft_kernel(const float* __restrict__ logits, size_t total, int n_bits,
+                                    float* __restrict__ rows) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t f = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; f < total; f += stride) {
+    const float* lp = logits + f * n_bits;
+    float acc = 0.f;
+    for (int i = 0; i < n_bits; ++i) {
+      const float c = static_cast<float>(1 << i);
+      // separate multiply and add (no FMA contraction): matches (p * c).sum(-1) in fp32
+      acc = __fadd_rn(acc, __fmul_rn(logistic(lp[i]), (i == n_bits - 1) ? -c : c));
+    }
+    rows[f] = acc;
+  }
+}
+
+__global__ void transpose_kernel(const float* __restrict__ src, int R, int C, float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? src[static_cast<size_t>(r) * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < C) dst[static_cast<size_t>(c) * R + r] = tile[threadIdx.x][i];
+  }
+}
+
+int grid_for(size_t n, int block, int cap = 148 * 16) {
+  size_t g = (n + block - 1) / block;
+  if (g > static_cast<size_t>(cap)) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace
+
+const char* cast_bf16_launch(const float* src, uint16_t* dst, size_t n, cudaStream_t stream) {
+  cast_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, stream>>>(src, dst, n);
+  return cuda_err(cudaGetLastError());
+}
+
+const char* pack_bitplanes_launch(const float* logits, int H, int D, int n_bits, uint8_t* packed,
+                                  double* stats, cudaStream_t stream) {
+  const size_t total = static_cast<size_t>(H) * D;
+  const int grid = grid_for(total, 256);
+  if (n_bits <= 4)
+    pack_bitplanes_kernel<true><<<grid, 256, 0, stream>>>(logits, H, D, n_bits, packed, stats);
+  else
+    pack_bitplanes_kernel<false><<<grid, 256, 0, stream>>>(logits, H, D, n_bits, packed, stats);
+  return cuda_err(cudaGetLastError());
+}
+
+const char* dequant_soft_launch(const float* logits, int H, int D, int n_bits, float* rows,
+                                cudaStream_t stream) {
+  const size_t total = static_cast<size_t>(H) * D;
+  dequant_soft_kernel<<<grid_for(total, 256), 256, 0, stream>>>(logits, total, n_bits, rows);
+  return cuda_err(cudaGetLastError());
+}
+
+const char* transpose_launch(const float* src, int R, int C, float* dst, cudaStream_t stream) {
+  dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+  transpose_kernel<<<grid, block, 0, stream>>>(src, R, C, dst);
+  return cuda_err(cudaGetLastError());
+}
+
+}  // namespace qsae

@@ -1,0 +1,380 @@
+// C ABI (include/qsae_b200.h): argument validation, workspace carving, launch sequencing and
+// the host-buffer pipeline. No torch types, no exceptions across the boundary.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/qsae_b200.h"
+#include "kernels.h"
+
+using namespace qsae;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int launch_status(const char* what, const char* err) {
+  if (err == nullptr) return QSAE_OK;
+  return fail(QSAE_ERR_CUDA, "%s: %s", what, err);
+}
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+struct EncodePlan {
+  int n_splits, nsub, n_tiles, tiles_per_split, k_sel;
+  size_t x_off, cand_off, cnt_off, total;
+};
+
+int plan_encode(int B, int H, int D, int k, int exact, EncodePlan* pl) {
+  if (B <= 0 || H <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "B and H must be positive (B=%d H=%d)", B, H);
+  if (D < 8 || D > 512 || (D % 8) != 0)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "D must be a multiple of 8 in [8, 512], got %d", D);
+  if (k < 1) return fail(QSAE_ERR_INVALID_ARGUMENT, "k must be >= 1, got %d", k);
+  if (k > H) return fail(QSAE_ERR_K_OUT_OF_RANGE, "selected index k out of range (k=%d > H=%d)", k, H);
+  if (k > kMaxK) return fail(QSAE_ERR_INVALID_ARGUMENT, "k=%d exceeds QSAE_MAX_K=%d", k, kMaxK);
+  int k_sel = k;
+  if (exact) {
+    k_sel = k + QSAE_RESCORE_MARGIN;
+    if (k_sel > kMaxK) k_sel = kMaxK;
+    if (k_sel > H) k_sel = H;
+  }
+  pl->k_sel = k_sel;
+  pl->n_tiles = (H + kEncBN - 1) / kEncBN;
+  pl->n_splits = encode_pick_splits(B, H, num_sms());
+  pl->tiles_per_split = (pl->n_tiles + pl->n_splits - 1) / pl->n_splits;
+  pl->nsub = pl->n_splits * 2;
+  pl->x_off = 0;
+  pl->cand_off = align_up(static_cast<size_t>(B) * D * 2, 1024);
+  pl->cnt_off = pl->cand_off + static_cast<size_t>(B) * pl->nsub * kCandCap * 8;
+  pl->total = align_up(pl->cnt_off + static_cast<size_t>(B) * pl->nsub * 4, 256);
+  return QSAE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qsae_abi_version(void) { return QSAE_ABI_VERSION; }
+const char* qsae_last_error(void) { return g_err; }
+
+int qsae_check_device(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(QSAE_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10) return fail(QSAE_ERR_UNSUPPORTED_DEVICE, "need an sm_100 device, found sm_%d%d", major, minor);
+  return QSAE_OK;
+}
+
+int qsae_cast_f32_to_bf16(const float* src, uint16_t* dst, size_t n, void* stream) {
+  if (!src || !dst) return fail(QSAE_ERR_INVALID_ARGUMENT, "cast: null pointer");
+  if (n == 0) return QSAE_OK;
+  return launch_status("cast_f32_to_bf16", cast_bf16_launch(src, dst, n, S(stream)));
+}
+
+int qsae_pack_bitplanes(const float* logits, int H, int D, int n_bits, uint8_t* packed, double* stats,
+                        void* stream) {
+  if (!logits || !packed) return fail(QSAE_ERR_INVALID_ARGUMENT, "pack_bitplanes: null pointer");
+  if (H <= 0 || D <= 0 || n_bits < 1 || n_bits > 8)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "pack_bitplanes: need H,D > 0 and 1 <= n_bits <= 8");
+  if (n_bits <= 4 && (D % 2) != 0)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "pack_bitplanes: nibble packing needs an even D");
+  return launch_status("pack_bitplanes", pack_bitplanes_launch(logits, H, D, n_bits, packed, stats, S(stream)));
+}
+
+int qsae_dequant_soft(const float* logits, int H, int D, int n_bits, float* rows, void* stream) {
+  if (!logits || !rows) return fail(QSAE_ERR_INVALID_ARGUMENT, "dequant_soft: null pointer");
+  if (H <= 0 || D <= 0 || n_bits < 1 || n_bits > 30)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "dequant_soft: bad shape");
+  return launch_status("dequant_soft", dequant_soft_launch(logits, H, D, n_bits, rows, S(stream)));
+}
+
+int qsae_transpose_f32(const float* src, int R, int C, float* dst, void* stream) {
+  if (!src || !dst || R <= 0 || C <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "transpose: bad argument");
+  return launch_status("transpose", transpose_launch(src, R, C, dst, S(stream)));
+}
+
+int qsae_encode_topk_workspace_bytes(int B, int H, int D, int k, size_t* bytes) {
+  if (!bytes) return fail(QSAE_ERR_INVALID_ARGUMENT, "workspace query: null pointer");
+  EncodePlan pl;
+  // size for the exact variant (k + margin survivors): it is the larger of the two
+  int rc = plan_encode(B, H, D, k, 1, &pl);
+  if (rc != QSAE_OK) return rc;
+  *bytes = pl.total;
+  return QSAE_OK;
+}
+
+int qsae_encode_topk(const float* x_f32, const uint16_t* w_bf16, const float* w_f32, const float* b_enc,
+                     int B, int H, int D, int k, int act, int exact, float* out_vals, int32_t* out_idx,
+                     int32_t* out_flags, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B == 0) return QSAE_OK;
+  if (!x_f32 || !w_bf16 || !b_enc || !out_vals || !out_idx || !workspace)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "encode_topk: null pointer");
+  if (exact && !w_f32) return fail(QSAE_ERR_INVALID_ARGUMENT, "encode_topk: exact mode needs w_f32");
+  if (act != QSAE_ACT_NONE && act != QSAE_ACT_RELU)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "encode_topk: unknown activation %d", act);
+  EncodePlan pl;
+  int rc = plan_encode(B, H, D, k, exact, &pl);
+  if (rc != QSAE_OK) return rc;
+  if (workspace_bytes < pl.total)
+    return fail(QSAE_ERR_WORKSPACE_TOO_SMALL, "encode_topk: workspace %zu < %zu bytes", workspace_bytes, pl.total);
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0 || (reinterpret_cast<uintptr_t>(w_bf16) & 15) != 0)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "encode_topk: workspace must be 256-byte and w_bf16 16-byte aligned");
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  uint16_t* x_bf16 = reinterpret_cast<uint16_t*>(ws + pl.x_off);
+  cudaStream_t st = S(stream);
+
+  rc = launch_status("cast x", cast_bf16_launch(x_f32, x_bf16, static_cast<size_t>(B) * D, st));
+  if (rc != QSAE_OK) return rc;
+
+  EncodeLaunch el;
+  el.B = B; el.H = H; el.D = D; el.k_sel = pl.k_sel;
+  el.n_splits = pl.n_splits; el.tiles_per_split = pl.tiles_per_split; el.n_tiles = pl.n_tiles;
+  el.act = act; el.bias = b_enc; el.debug_z = nullptr;
+  el.cand = ws + pl.cand_off;
+  el.cand_cnt = reinterpret_cast<int*>(ws + pl.cnt_off);
+  rc = launch_status("encode_topk kernel", encode_topk_launch(x_bf16, w_bf16, el, st));
+  if (rc != QSAE_OK) return rc;
+
+  SelectLaunch sl;
+  sl.B = B; sl.H = H; sl.D = D; sl.k_sel = pl.k_sel; sl.k_out = k; sl.nsub = pl.nsub;
+  sl.act = act; sl.exact = exact;
+  sl.cand = el.cand; sl.cand_cnt = el.cand_cnt;
+  sl.x_f32 = x_f32; sl.w_f32 = w_f32; sl.bias = b_enc;
+  sl.out_vals = out_vals; sl.out_idx = out_idx; sl.out_flags = out_flags;
+  return launch_status("select_topk kernel", select_topk_launch(sl, st));
+}
+
+int qsae_encode_dense_tc(const float* x_f32, const uint16_t* w_bf16, const float* b_enc, int B, int H, int D,
+                         int act, float* z, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B == 0) return QSAE_OK;
+  if (!x_f32 || !w_bf16 || !b_enc || !z || !workspace) return fail(QSAE_ERR_INVALID_ARGUMENT, "encode_dense_tc: null pointer");
+  EncodePlan pl;
+  int rc = plan_encode(B, H, D, 1, 0, &pl);
+  if (rc != QSAE_OK) return rc;
+  if (workspace_bytes < pl.total) return fail(QSAE_ERR_WORKSPACE_TOO_SMALL, "encode_dense_tc: workspace %zu < %zu", workspace_bytes, pl.total);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  uint16_t* x_bf16 = reinterpret_cast<uint16_t*>(ws + pl.x_off);
+  rc = launch_status("cast x", cast_bf16_launch(x_f32, x_bf16, static_cast<size_t>(B) * D, S(stream)));
+  if (rc != QSAE_OK) return rc;
+  EncodeLaunch el;
+  el.B = B; el.H = H; el.D = D; el.k_sel = 1;
+  el.n_splits = pl.n_splits; el.tiles_per_split = pl.tiles_per_split; el.n_tiles = pl.n_tiles;
+  el.act = act; el.bias = b_enc; el.debug_z = z;
+  el.cand = ws + pl.cand_off;
+  el.cand_cnt = reinterpret_cast<int*>(ws + pl.cnt_off);
+  return launch_status("encode_topk kernel (dense dump)", encode_topk_launch(x_bf16, w_bf16, el, S(stream)));
+}
+
+int qsae_encode_dense_f32(const float* x_f32, const int32_t* rows, int R, const float* w_f32,
+                          const float* b_enc, int H, int D, int act, float* z, void* stream) {
+  if (R == 0) return QSAE_OK;
+  if (!x_f32 || !w_f32 || !z || R < 0 || H <= 0 || D <= 0)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "encode_dense: bad argument");
+  return launch_status("encode_dense", encode_dense_launch(x_f32, rows, R, w_f32, b_enc, H, D, act, z, S(stream)));
+}
+
+int qsae_topk_dense_workspace_bytes(int R, int H, int k, size_t* bytes) {
+  if (!bytes || R < 0 || H <= 0 || k < 1) return fail(QSAE_ERR_INVALID_ARGUMENT, "topk_dense workspace: bad argument");
+  *bytes = align_up(static_cast<size_t>(R) * kCandCap * 8 + static_cast<size_t>(R) * 4, 256);
+  return QSAE_OK;
+}
+
+int qsae_topk_dense(const float* z, int R, int H, int k, float* out_vals, int32_t* out_idx,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  if (R == 0) return QSAE_OK;
+  if (!z || !out_vals || !out_idx || !workspace) return fail(QSAE_ERR_INVALID_ARGUMENT, "topk_dense: null pointer");
+  if (k < 1) return fail(QSAE_ERR_INVALID_ARGUMENT, "k must be >= 1, got %d", k);
+  if (k > H) return fail(QSAE_ERR_K_OUT_OF_RANGE, "selected index k out of range (k=%d > H=%d)", k, H);
+  if (k > kMaxK) return fail(QSAE_ERR_INVALID_ARGUMENT, "k=%d exceeds QSAE_MAX_K=%d", k, kMaxK);
+  size_t need = 0;
+  qsae_topk_dense_workspace_bytes(R, H, k, &need);
+  if (workspace_bytes < need) return fail(QSAE_ERR_WORKSPACE_TOO_SMALL, "topk_dense: workspace %zu < %zu", workspace_bytes, need);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  void* cand = ws;
+  int* cnt = reinterpret_cast<int*>(ws + static_cast<size_t>(R) * kCandCap * 8);
+  int rc = launch_status("dense_candidates", dense_candidates_launch(z, R, H, k, cand, cnt, S(stream)));
+  if (rc != QSAE_OK) return rc;
+  SelectLaunch sl;
+  memset(&sl, 0, sizeof(sl));
+  sl.B = R; sl.H = H; sl.D = 0; sl.k_sel = k; sl.k_out = k; sl.nsub = 1;
+  sl.cand = cand; sl.cand_cnt = cnt; sl.out_vals = out_vals; sl.out_idx = out_idx;
+  return launch_status("select_topk kernel", select_topk_launch(sl, S(stream)));
+}
+
+static int check_decode(const char* who, const float* vals, const int32_t* idx, const void* dict,
+                        float* recon, int B, int k, int H, int D, int d_mult) {
+  if (!vals || !idx || !dict || !recon) return fail(QSAE_ERR_INVALID_ARGUMENT, "%s: null pointer", who);
+  if (B < 0 || k < 0 || H <= 0 || D <= 0 || (D % d_mult) != 0 || D > 1024)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "%s: need D %% %d == 0, D <= 1024 (D=%d)", who, d_mult, D);
+  return QSAE_OK;
+}
+
+int qsae_decode_int4(const float* vals, const int32_t* idx, int B, int k, const uint8_t* packed, int H,
+                     int D, float scale, const float* bias, float* recon, void* stream) {
+  int rc = check_decode("decode_int4", vals, idx, packed, recon, B, k, H, D, 8);
+  if (rc != QSAE_OK || B == 0) return rc;
+  return launch_status("decode_int4", decode_int4_launch(vals, idx, B, k, packed, H, D, scale, bias, recon, S(stream)));
+}
+
+int qsae_decode_int8(const float* vals, const int32_t* idx, int B, int k, const int8_t* rows, int H,
+                     int D, float scale, const float* bias, float* recon, void* stream) {
+  int rc = check_decode("decode_int8", vals, idx, rows, recon, B, k, H, D, 4);
+  if (rc != QSAE_OK || B == 0) return rc;
+  return launch_status("decode_int8", decode_int8_launch(vals, idx, B, k, rows, H, D, scale, bias, recon, S(stream)));
+}
+
+int qsae_decode_rows_f32(const float* vals, const int32_t* idx, int B, int k, const float* rows, int H,
+                         int D, float scale, const float* bias, float* recon, void* stream) {
+  int rc = check_decode("decode_rows_f32", vals, idx, rows, recon, B, k, H, D, 4);
+  if (rc != QSAE_OK || B == 0) return rc;
+  return launch_status("decode_rows_f32", decode_f32_launch(vals, idx, B, k, rows, H, D, scale, bias, recon, S(stream)));
+}
+
+int qsae_densify(const float* vals, const int32_t* idx, int B, int k, int H, float* dense, void* stream) {
+  if (B == 0) return QSAE_OK;
+  if (!vals || !idx || !dense || B < 0 || k < 0 || H <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "densify: bad argument");
+  return launch_status("densify", densify_launch(vals, idx, B, k, H, dense, S(stream)));
+}
+
+// --------------------------------------------------------------------------------------------
+// host-buffer pipeline
+// --------------------------------------------------------------------------------------------
+struct qsae_bsae_plan {
+  int H, D, n_bits, k, chunk;
+  float qstep;
+  const float* w_f32;
+  const float* b_enc;
+  const float* dec_bias;
+  uint16_t* w_bf16;
+  uint8_t* packed;
+  static constexpr int kSlots = 3;
+  struct Slot {
+    cudaStream_t stream;
+    float* x;
+    void* ws;
+    size_t ws_bytes;
+    float* vals;
+    int32_t* idx;
+    float* recon;
+  } slot[kSlots];
+};
+
+void qsae_bsae_plan_destroy(qsae_bsae_plan* p) {
+  if (!p) return;
+  for (int s = 0; s < qsae_bsae_plan::kSlots; ++s) {
+    auto& sl = p->slot[s];
+    if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
+    cudaFree(sl.x); cudaFree(sl.ws); cudaFree(sl.vals); cudaFree(sl.idx); cudaFree(sl.recon);
+  }
+  cudaFree(p->w_bf16);
+  cudaFree(p->packed);
+  delete p;
+}
+
+int qsae_bsae_plan_create(const float* w_enc, const float* b_enc, const float* logits, const float* dec_bias,
+                          int H, int D, int n_bits, float gamma, int k, int max_chunk_rows,
+                          qsae_bsae_plan** out) {
+  if (!w_enc || !b_enc || !logits || !dec_bias || !out) return fail(QSAE_ERR_INVALID_ARGUMENT, "plan_create: null pointer");
+  if (max_chunk_rows <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "plan_create: max_chunk_rows must be positive");
+  if (n_bits < 1 || n_bits > 8) return fail(QSAE_ERR_INVALID_ARGUMENT, "plan_create: 1 <= n_bits <= 8");
+  size_t ws_bytes = 0;
+  int rc = qsae_encode_topk_workspace_bytes(max_chunk_rows, H, D, k, &ws_bytes);
+  if (rc != QSAE_OK) return rc;
+  qsae_bsae_plan* p = new (std::nothrow) qsae_bsae_plan();
+  if (!p) return fail(QSAE_ERR_CUDA, "plan_create: out of host memory");
+  memset(p, 0, sizeof(*p));
+  p->H = H; p->D = D; p->n_bits = n_bits; p->k = k; p->chunk = max_chunk_rows;
+  p->qstep = gamma / static_cast<float>(1 << (n_bits - 1));
+  p->w_f32 = w_enc; p->b_enc = b_enc; p->dec_bias = dec_bias;
+  const size_t packed_bytes = n_bits <= 4 ? static_cast<size_t>(H) * D / 2 : static_cast<size_t>(H) * D;
+  cudaError_t e = cudaMalloc(&p->w_bf16, static_cast<size_t>(H) * D * 2);
+  if (e == cudaSuccess) e = cudaMalloc(&p->packed, packed_bytes);
+  for (int s = 0; s < qsae_bsae_plan::kSlots && e == cudaSuccess; ++s) {
+    auto& sl = p->slot[s];
+    sl.ws_bytes = ws_bytes;
+    e = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&sl.x, static_cast<size_t>(max_chunk_rows) * D * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&sl.ws, ws_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&sl.vals, static_cast<size_t>(max_chunk_rows) * k * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&sl.idx, static_cast<size_t>(max_chunk_rows) * k * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&sl.recon, static_cast<size_t>(max_chunk_rows) * D * 4);
+  }
+  if (e != cudaSuccess) {
+    qsae_bsae_plan_destroy(p);
+    return fail(QSAE_ERR_CUDA, "plan_create: %s", cudaGetErrorString(e));
+  }
+  cudaStream_t st = p->slot[0].stream;
+  rc = qsae_cast_f32_to_bf16(w_enc, p->w_bf16, static_cast<size_t>(H) * D, st);
+  if (rc == QSAE_OK) rc = qsae_pack_bitplanes(logits, H, D, n_bits, p->packed, nullptr, st);
+  if (rc == QSAE_OK && (e = cudaStreamSynchronize(st)) != cudaSuccess)
+    rc = fail(QSAE_ERR_CUDA, "plan_create: %s", cudaGetErrorString(e));
+  if (rc != QSAE_OK) { qsae_bsae_plan_destroy(p); return rc; }
+  *out = p;
+  return QSAE_OK;
+}
+
+int qsae_bsae_forward_host(qsae_bsae_plan* p, const float* x_host, int B, float* vals_host,
+                           int32_t* idx_host, float* recon_host) {
+  if (!p || !x_host || !vals_host || !idx_host || !recon_host || B < 0)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "forward_host: bad argument");
+  int rc = QSAE_OK;
+  int c = 0;
+  for (int r0 = 0; r0 < B && rc == QSAE_OK; r0 += p->chunk, ++c) {
+    auto& sl = p->slot[c % qsae_bsae_plan::kSlots];
+    const int rows = (B - r0 < p->chunk) ? (B - r0) : p->chunk;
+    cudaStream_t st = sl.stream;  // stream order protects the slot's buffers from its previous use
+    cudaError_t e = cudaMemcpyAsync(sl.x, x_host + static_cast<size_t>(r0) * p->D,
+                                    static_cast<size_t>(rows) * p->D * 4, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { rc = fail(QSAE_ERR_CUDA, "forward_host H2D: %s", cudaGetErrorString(e)); break; }
+    rc = qsae_encode_topk(sl.x, p->w_bf16, p->w_f32, p->b_enc, rows, p->H, p->D, p->k, QSAE_ACT_NONE, 0,
+                          sl.vals, sl.idx, nullptr, sl.ws, sl.ws_bytes, st);
+    if (rc != QSAE_OK) break;
+    if (p->n_bits <= 4)
+      rc = qsae_decode_int4(sl.vals, sl.idx, rows, p->k, p->packed, p->H, p->D, p->qstep, p->dec_bias, sl.recon, st);
+    else
+      rc = qsae_decode_int8(sl.vals, sl.idx, rows, p->k, reinterpret_cast<const int8_t*>(p->packed), p->H, p->D,
+                            p->qstep, p->dec_bias, sl.recon, st);
+    if (rc != QSAE_OK) break;
+    e = cudaMemcpyAsync(vals_host + static_cast<size_t>(r0) * p->k, sl.vals, static_cast<size_t>(rows) * p->k * 4,
+                        cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(idx_host + static_cast<size_t>(r0) * p->k, sl.idx, static_cast<size_t>(rows) * p->k * 4,
+                          cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(recon_host + static_cast<size_t>(r0) * p->D, sl.recon, static_cast<size_t>(rows) * p->D * 4,
+                          cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) rc = fail(QSAE_ERR_CUDA, "forward_host D2H: %s", cudaGetErrorString(e));
+  }
+  for (int s = 0; s < qsae_bsae_plan::kSlots; ++s) {
+    cudaError_t e = cudaStreamSynchronize(p->slot[s].stream);
+    if (e != cudaSuccess && rc == QSAE_OK) rc = fail(QSAE_ERR_CUDA, "forward_host sync: %s", cudaGetErrorString(e));
+  }
+  return rc;
+}
+
+}  // extern "C"
