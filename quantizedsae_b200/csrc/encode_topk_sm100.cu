@@ -3,19 +3,25 @@
 //   z[b, h] = sum_d x[b, d] * W[h, d] + bias[h]           (nn.Linear, sae/binary.py:82-84,92)
 //   per row b keep the k largest z[b, :]                   (Tensor.topk,  sae/binary.py:94)
 //
-// One CTA owns BM = 128 rows of x (kept resident in shared memory for the whole sweep) and
-// streams W through a TMA/mbarrier ring in tiles of BN = 256 latents x BK = 64. A single
-// thread issues tcgen05.mma (UMMA 128x256x16, bf16 in, fp32 accumulate) into one of two
-// 256-column TMEM accumulators; eight epilogue warps drain the other accumulator with
-// tcgen05.ld, add the bias and run a streaming threshold selection: thread (row, column-half)
-// keeps a running lower bound `thr` of the row's k-th largest value, appends the rare
-// survivors to a small per-row buffer in global memory (L2 resident) and, when a buffer runs
-// full, the warp compacts it cooperatively (bitwise radix bisection to the exact k-th key).
-// The dense [B, H] pre-activation is never written.
+// One CTA owns BM = 128 rows of x (resident in shared memory for the whole sweep) and streams W
+// through a TMA/mbarrier ring in tiles of BN = 256 latents x BK = 64. One thread issues
+// tcgen05.mma (UMMA 128x256x16, bf16 in, fp32 accumulate) into one of two 256-column TMEM
+// accumulators while eight epilogue warps drain the other with tcgen05.ld. The dense [B, H]
+// pre-activation is never written.
+//
+// Selection in the epilogue. Thread (row, column-half) sees its row's values 32 columns at a
+// time, column j of every chunk forming "class" j. It keeps in registers the running largest
+// (or two largest) value of each class; with 32 classes x m values per class there are 32*m seen
+// values >= T = min_j (m-th largest of class j), so T is a lower bound of the row's k-th largest
+// for every k <= 32*m -- one FMNMX per element, no memory, no sorting. Values >= T (about 4k per
+// row survive in total) are appended to a per-(row, sub-stream) buffer in global memory; stores
+// are gated by a warp vote so they are only issued when a survivor exists. A buffer that runs
+// full is filtered in place against the current T (bit-serial bisection to the exact k-th value
+// is the fallback when filtering does not help, e.g. floods of equal values after ReLU).
+// select_topk.cu merges the sub-streams of a row, sharpened by max_s T_s.
 //
 // The latent axis can be split over `n_splits` CTAs per row block (grid.x) to fill the 148 SMs
-// at small batch; every (split, column-half) is an independent sub-stream whose survivors are
-// merged by select_topk.cu.
+// at small batch; every (split, column-half) is an independent sub-stream.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -39,43 +45,227 @@ constexpr int kBBytesPerStage = BN * BK * 2;   // 32 KiB
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + kEpiWarps * 32;  // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 bias
 constexpr int kTmemCols = 512;                  // 2 accumulators x 256 columns
-constexpr int CAP = kCandCap;
 
 struct SmemLayout {
-  uint32_t a_off, b_off, bias_off, bar_off, tmem_ptr_off, total;
+  uint32_t a_off, b_off, bias_off, share_off, bar_off, tmem_ptr_off, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(int k_chunks) {
   SmemLayout L;
   L.a_off = 0;
   L.b_off = L.a_off + k_chunks * kABytesPerChunk;
   L.bias_off = L.b_off + kStages * kBBytesPerStage;
-  L.bar_off = L.bias_off + 2 * BN * 4;
+  L.share_off = L.bias_off + 2 * BN * 4;         // partner thresholds, 2 x 128 x bf16
+  L.bar_off = L.share_off + 2 * BM * 2;
   L.tmem_ptr_off = L.bar_off + 8 * (1 + 2 * kStages + 6);
   L.total = L.tmem_ptr_off + 16;
   return L;
 }
 
-// Warp-cooperative compaction of the 32 per-row buffers owned by this warp's lanes: every buffer
-// holding more than k entries is reduced to its k largest and its owner's threshold is raised to
-// the k-th largest value (see warp_compact_row).
-__device__ __forceinline__ void compact_warp_buffers(uint2* buf, int& cnt, float& thr, int k,
-                                                     int lane) {
+// float -> bf16 bits rounded toward -inf (a lower bound stays a lower bound)
+__device__ __forceinline__ uint16_t bf16_floor_bits(float f) {
+  uint32_t u = __float_as_uint(f);
+  if (u & 0x80000000u) u += 0xFFFFu;  // negative: grow the magnitude
+  return static_cast<uint16_t>(u >> 16);
+}
+__device__ __forceinline__ float bf16_bits_to_float(uint16_t b) {
+  return __uint_as_float(static_cast<uint32_t>(b) << 16);
+}
+
+// smallest float strictly greater than f (f finite or -inf)
+__device__ __forceinline__ float next_above(float f) { return key_to_float(float_to_key(f) + 1u); }
+
+// Overflow handling for the 32 buffers owned by this warp's lanes (lane r owns `buf`, `cnt`, and
+// the inclusive survivor threshold `thr`). Every buffer more than half full is filtered in place
+// against its owner's threshold (insertion order preserved); if that leaves it nearly full it is
+// cut to its exact k largest and the threshold moves just above the k-th value (after an exact
+// cut, later values equal to the k-th lose on column order).
+static __device__ __noinline__ void relieve_warp_buffers(uint2* buf, int& cnt, float& thr,
+                                                         float& valid_bound, int k, int cap, int lane) {
   const unsigned full = 0xffffffffu;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  constexpr int BATCH = 8;
   __syncwarp();
 #pragma unroll 1
   for (int r = 0; r < 32; ++r) {
     const int n = __shfl_sync(full, cnt, r);
-    if (n <= k) continue;
-    const unsigned long long bp =
-        __shfl_sync(full, reinterpret_cast<unsigned long long>(buf), r);
-    float t;
-    const int out = warp_compact_row(reinterpret_cast<uint2*>(bp), n, k, lane, &t);
+    if (n <= (cap >> 1)) continue;
+    const float t_in = __shfl_sync(full, thr, r);
+    uint2* rb = reinterpret_cast<uint2*>(
+        __shfl_sync(full, reinterpret_cast<unsigned long long>(buf), r));
+    int out = 0;
+#pragma unroll 1
+    for (int base = 0; base < n; base += 32 * BATCH) {
+      uint2 t[BATCH];
+#pragma unroll
+      for (int i = 0; i < BATCH; ++i) {  // BATCH independent loads in flight
+        const int e = base + i * 32 + lane;
+        t[i] = (e < n) ? rb[e] : make_uint2(0u, 0u);
+      }
+#pragma unroll
+      for (int i = 0; i < BATCH; ++i) {  // writes land at or before the slots already loaded
+        const int e = base + i * 32 + lane;
+        const bool keep = (e < n) && (__uint_as_float(t[i].x) >= t_in);
+        const unsigned b = __ballot_sync(full, keep);
+        if (keep) rb[out + __popc(b & lt_mask)] = t[i];
+        out += __popc(b);
+      }
+    }
+    float t_out = t_in;
+    float kth = -INFINITY;
+    if (out > cap - 96 && out > k) {
+      __syncwarp();
+      out = warp_compact_row_generic(rb, out, k, lane, &kth);
+      t_out = fmaxf(t_in, next_above(kth));
+    }
     if (lane == r) {
       cnt = out;
-      thr = t;
+      thr = t_out;
+      valid_bound = fmaxf(valid_bound, kth);  // the k-th value itself stays an inclusive bound
     }
   }
   __syncwarp();
+}
+
+// v[j] for a per-lane dynamic j: 31 selects (registers cannot be indexed dynamically)
+__device__ __forceinline__ float pick32(const float (&v)[32], int j) {
+  float a[16], b[8], c[4], d[2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (j & 16) ? v[i + 16] : v[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (j & 8) ? a[i + 8] : a[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[i + 4] : b[i];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) d[i] = (j & 2) ? c[i + 2] : c[i];
+  return (j & 1) ? d[1] : d[0];
+}
+
+// MODE 0: no class bound (any k <= kMaxK; bisection only)      MODE 1: top-1 per class, k <= 32
+// MODE 2: top-2 per class, k <= 64       MODE 3: top-2 per class shared with the partner thread
+//                                                 handling the other column half, k <= 128
+template <int MODE>
+__device__ __forceinline__ void epilogue_loop(const EncodeLaunch& p, int n_my_tiles, int tile_begin,
+                                              int split, int m0, int e, int lane, uint32_t tmem_base,
+                                              const float* bias_smem, uint16_t* share,
+                                              uint64_t* tmem_full, uint64_t* tmem_empty,
+                                              uint64_t* bias_full) {
+  const unsigned full = 0xffffffffu;
+  const int quad = e & 3;       // TMEM lanes 32*quad .. +31 (hardware: warp_id % 4)
+  const int half = e >> 2;      // columns [half*128, half*128+128) of the tile
+  const int row_in_tile = quad * 32 + lane;
+  const int row = m0 + row_in_tile;
+  const bool row_ok = row < p.B;
+  const bool live = row_ok && p.debug_mode == 0;
+  const int nsub = p.n_splits * 2;
+  const int sub = split * 2 + half;
+  const int cap = p.cap;
+  const size_t slot = static_cast<size_t>(row_ok ? row : 0) * nsub + sub;
+  uint2* buf = reinterpret_cast<uint2*>(p.cand) + slot * cap;
+  int cnt = 0;
+  const int k = p.k_sel;
+  const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+
+  // a value survives iff v >= thr (inclusive; starts at the lowest finite float so that the
+  // -inf used to mask out-of-range columns never survives)
+  float thr = live ? -3.402823466e+38f : INFINITY;
+  float valid_bound = -INFINITY;  // inclusive lower bound of the k-th largest, reported to the merge
+  float top1[MODE >= 1 ? 32 : 1];
+  float top2[MODE >= 2 ? 32 : 1];
+  const float init = live ? -INFINITY : INFINITY;
+#pragma unroll
+  for (int j = 0; j < (MODE >= 1 ? 32 : 1); ++j) top1[j] = init;
+#pragma unroll
+  for (int j = 0; j < (MODE >= 2 ? 32 : 1); ++j) top2[j] = init;
+
+  for (int t = 0; t < n_my_tiles; ++t) {
+    const int acc = t & 1;
+    const uint32_t ph = (t >> 1) & 1;
+    mbar_wait(&tmem_full[acc], ph);
+    mbar_wait(&bias_full[acc], ph);
+    tc_fence_after();
+    const int n_tile = (tile_begin + t) * BN + half * 128;
+    const float4* bias4 = reinterpret_cast<const float4*>(bias_smem + acc * BN + half * 128);
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      if (p.debug_mode == 2) break;  // timing experiment: pipeline without the TMEM drain
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(lane_taddr + acc * BN + half * 128 + c * 32, r);
+      tmem_ld_wait();
+      const int col0 = n_tile + c * 32;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = bias4[c * 8 + j];
+        v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
+        v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+        v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
+        v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+      }
+      if (p.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (col0 + 32 > p.H) {  // last, partial tile only
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j >= p.H) v[j] = -INFINITY;
+      }
+      if (p.debug_z != nullptr && row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.H) p.debug_z[static_cast<size_t>(row) * p.H + col0 + j] = v[j];
+      }
+      if constexpr (MODE >= 1) {
+        // class maxima and the bound they imply
+        float bound;
+        if constexpr (MODE == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) top1[j] = fmaxf(top1[j], v[j]);
+          bound = top1[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) bound = fminf(bound, top1[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            top2[j] = fmaxf(top2[j], fminf(top1[j], v[j]));
+            top1[j] = fmaxf(top1[j], v[j]);
+          }
+          bound = top2[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) bound = fminf(bound, top2[j]);
+        }
+        if constexpr (MODE == 3) {
+          // exchange with the thread on the other column half of this row; a stale partner
+          // value is an older, lower bound and therefore still valid
+          share[half * BM + row_in_tile] = bf16_floor_bits(bound);
+          bound = fminf(bound, bf16_bits_to_float(share[(half ^ 1) * BM + row_in_tile]));
+        }
+        if (live) { thr = fmaxf(thr, bound); valid_bound = fmaxf(valid_bound, bound); }
+      }
+      // survivors: per-lane hit mask, then rounds in which every lane with a pending hit stores
+      // one entry. Scattered stores cost one LSU transaction per lane, so the number of store
+      // instructions per chunk (= max hits of any lane) is what matters, not the ALU work.
+      uint32_t hits = 0u;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) hits |= (v[j] >= thr) ? (1u << j) : 0u;
+      while (__any_sync(full, hits != 0u)) {
+        if (hits != 0u) {
+          const int j = __ffs(hits) - 1;
+          hits &= hits - 1u;
+          buf[cnt] = make_uint2(__float_as_uint(pick32(v, j)), static_cast<uint32_t>(col0 + j));
+          ++cnt;
+        }
+      }
+      if (__any_sync(full, cnt > cap - 32)) relieve_warp_buffers(buf, cnt, thr, valid_bound, k, cap, lane);
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+  }
+  if (row_ok) {
+    p.cand_cnt[slot] = cnt;
+    p.cand_thr[slot] = live ? valid_bound : -INFINITY;
+  }
 }
 
 template <int K_CHUNKS>
@@ -87,6 +277,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
   uint8_t* a_smem = smem + L.a_off;
   uint8_t* b_smem = smem + L.b_off;
   float* bias_smem = reinterpret_cast<float*>(smem + L.bias_off);
+  uint16_t* share = reinterpret_cast<uint16_t*>(smem + L.share_off);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* a_full = bars;
   uint64_t* full = bars + 1;
@@ -122,6 +313,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
     fence_mbar_init();
     fence_proxy_async_smem();
   }
+  if (threadIdx.x < 2 * BM) share[threadIdx.x] = 0xFF80u;  // bf16 -inf
   if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
@@ -200,77 +392,24 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
   } else if (warp >= 4) {
     // ------------------------------------------------------------- epilogue / selection
     const int e = warp - 4;
-    const int quad = e & 3;       // TMEM lanes 32*quad .. +31 (hardware: warp_id % 4)
-    const int half = e >> 2;      // columns [half*128, half*128+128) of the tile
-    const int row = m0 + quad * 32 + lane;
-    const bool row_ok = row < p.B;
-    const int nsub = p.n_splits * 2;
-    const int sub = split * 2 + half;
-    uint2* buf = reinterpret_cast<uint2*>(p.cand) +
-                 (static_cast<size_t>(row_ok ? row : 0) * nsub + sub) * CAP;
-    int cnt = 0;
-    float thr = row_ok ? -INFINITY : INFINITY;
-    const int k = p.k_sel;
-    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-
-    for (int t = 0; t < n_my_tiles; ++t) {
-      const int acc = t & 1;
-      const uint32_t ph = (t >> 1) & 1;
-      mbar_wait(&tmem_full[acc], ph);
-      mbar_wait(&bias_full[acc], ph);
-      tc_fence_after();
-      const int n_tile = (tile_begin + t) * BN + half * 128;
-      const float4* bias4 = reinterpret_cast<const float4*>(bias_smem + acc * BN + half * 128);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(lane_taddr + acc * BN + half * 128 + c * 32, r);
-        tmem_ld_wait();
-        const int col0 = n_tile + c * 32;
-        float v[32];
-        float vmax = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b = bias4[c * 8 + j];
-          v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
-          v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
-          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
-          v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
-        }
-        if (p.act == 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (col0 + 32 > p.H) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j >= p.H) v[j] = -INFINITY;
-        }
-        if (p.debug_z != nullptr && row_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.H) p.debug_z[static_cast<size_t>(row) * p.H + col0 + j] = v[j];
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) vmax = fmaxf(vmax, v[j]);
-        if (vmax > thr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (v[j] > thr) {
-              buf[cnt] = make_uint2(__float_as_uint(v[j]), static_cast<uint32_t>(col0 + j));
-              ++cnt;
-            }
-          }
-        }
-        if (__any_sync(0xffffffffu, cnt > CAP - 32)) compact_warp_buffers(buf, cnt, thr, k, lane);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    switch (p.mode) {
+      case 1:
+        epilogue_loop<1>(p, n_my_tiles, tile_begin, split, m0, e, lane, tmem_base, bias_smem, share,
+                         tmem_full, tmem_empty, bias_full);
+        break;
+      case 2:
+        epilogue_loop<2>(p, n_my_tiles, tile_begin, split, m0, e, lane, tmem_base, bias_smem, share,
+                         tmem_full, tmem_empty, bias_full);
+        break;
+      case 3:
+        epilogue_loop<3>(p, n_my_tiles, tile_begin, split, m0, e, lane, tmem_base, bias_smem, share,
+                         tmem_full, tmem_empty, bias_full);
+        break;
+      default:
+        epilogue_loop<0>(p, n_my_tiles, tile_begin, split, m0, e, lane, tmem_base, bias_smem, share,
+                         tmem_full, tmem_empty, bias_full);
+        break;
     }
-    // leave at most k survivors per sub-stream for the merge kernel
-    if (__any_sync(0xffffffffu, cnt > k)) compact_warp_buffers(buf, cnt, thr, k, lane);
-    if (row_ok) p.cand_cnt[static_cast<size_t>(row) * nsub + sub] = cnt;
   }
 
   tc_fence_before();
@@ -344,6 +483,14 @@ int encode_pick_splits(int B, int H, int num_sms) {
     if (eff > best * 1.03) { best = eff; best_s = s; }
   }
   return best_s;
+}
+
+void encode_pick_mode(int k_sel, int* mode, int* cap) {
+  *cap = kCandCapMax;
+  if (k_sel <= 32) *mode = 1;
+  else if (k_sel <= 64) *mode = 2;
+  else if (k_sel <= 128) *mode = 3;
+  else *mode = 0;
 }
 
 const char* encode_topk_launch(const uint16_t* x_bf16, const uint16_t* w_bf16, EncodeLaunch p,

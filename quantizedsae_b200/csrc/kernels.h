@@ -6,35 +6,42 @@
 
 namespace qsae {
 
-constexpr int kEncBM = 128;     // rows of x per CTA
-constexpr int kEncBN = 256;     // latents per accumulator tile
-constexpr int kCandCap = 256;   // capacity of one (row, sub-stream) survivor buffer
-constexpr int kMaxSplits = 16;  // max CTAs sharing one row block along the latent axis
-constexpr int kMaxK = 224;      // == QSAE_MAX_K; survivors after compaction + one 32-wide chunk fit kCandCap
+constexpr int kEncBM = 128;        // rows of x per CTA
+constexpr int kEncBN = 256;        // latents per accumulator tile
+constexpr int kCandCapMax = 1024;  // largest per-(row, sub-stream) survivor buffer
+constexpr int kDenseCap = 256;     // survivor buffer of the dense top-k kernel
+constexpr int kMaxSplits = 8;      // max CTAs sharing one row block along the latent axis
+constexpr int kMaxK = 224;         // == QSAE_MAX_K
 
 struct EncodeLaunch {
   int B, H, D;
-  int k_sel;            // survivors kept per sub-stream (k, or k + rescore margin)
+  int k_sel;            // survivors that must be retained per row (k, or k + rescore margin)
   int n_splits;         // grid.x
   int tiles_per_split;  // in units of kEncBN latents
   int n_tiles;          // ceil(H / kEncBN)
   int act;              // 0 none, 1 relu
+  int mode;             // epilogue bound: 0 bisection only, 1/2/3 class maxima (see .cu)
+  int cap;              // entries per survivor buffer
   const float* bias;    // [H]
-  void* cand;           // [B][n_splits*2][kCandCap] {float bits, int32 column}
+  void* cand;           // [B][n_splits*2][cap] {float bits, int32 column}
   int* cand_cnt;        // [B][n_splits*2]
+  float* cand_thr;      // [B][n_splits*2] inclusive lower bound of the row's k_sel-th largest value
+  int debug_mode;       // 0 normal; timing experiments: 1 no survivors, 2 no TMEM drain
   float* debug_z;       // optional dense [B, H] dump of the accumulator (+bias, act); diagnostics only
 };
 
 // encode_topk_sm100.cu
 int encode_pick_splits(int B, int H, int num_sms);
+void encode_pick_mode(int k_sel, int* mode, int* cap);
 const char* encode_topk_launch(const uint16_t* x_bf16, const uint16_t* w_bf16, EncodeLaunch p,
                                cudaStream_t stream);
 
 // select_topk.cu
 struct SelectLaunch {
-  int B, H, D, k_sel, k_out, nsub, act, exact;
+  int B, H, D, k_sel, k_out, nsub, cap, act, exact;
   const void* cand;       // as above
   const int* cand_cnt;
+  const float* cand_thr;  // may be null
   const float* x_f32;     // [B, D]   (exact only)
   const float* w_f32;     // [H, D]   (exact only)
   const float* bias;      // [H]      (exact only)
@@ -43,7 +50,7 @@ struct SelectLaunch {
   int32_t* out_flags;     // [B] or null
 };
 const char* select_topk_launch(const SelectLaunch& p, cudaStream_t stream);
-// candidates from a dense [R, H] matrix (one sub-stream per row), same buffer format
+// survivors from a dense [R, H] matrix (one sub-stream per row, buffers of kDenseCap entries)
 const char* dense_candidates_launch(const float* z, int R, int H, int k, void* cand, int* cand_cnt,
                                     cudaStream_t stream);
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -43,8 +44,8 @@ int num_sms() {
 }
 
 struct EncodePlan {
-  int n_splits, nsub, n_tiles, tiles_per_split, k_sel;
-  size_t x_off, cand_off, cnt_off, total;
+  int n_splits, nsub, n_tiles, tiles_per_split, k_sel, mode, cap;
+  size_t x_off, cand_off, cnt_off, thr_off, total;
 };
 
 int plan_encode(int B, int H, int D, int k, int exact, EncodePlan* pl) {
@@ -63,12 +64,18 @@ int plan_encode(int B, int H, int D, int k, int exact, EncodePlan* pl) {
   pl->k_sel = k_sel;
   pl->n_tiles = (H + kEncBN - 1) / kEncBN;
   pl->n_splits = encode_pick_splits(B, H, num_sms());
+  if (const char* ov = getenv("QSAE_ENCODE_SPLITS")) {  // tuning experiments only
+    const int s = atoi(ov);
+    if (s >= 1 && s <= kMaxSplits && s <= pl->n_tiles) pl->n_splits = s;
+  }
   pl->tiles_per_split = (pl->n_tiles + pl->n_splits - 1) / pl->n_splits;
   pl->nsub = pl->n_splits * 2;
   pl->x_off = 0;
   pl->cand_off = align_up(static_cast<size_t>(B) * D * 2, 1024);
-  pl->cnt_off = pl->cand_off + static_cast<size_t>(B) * pl->nsub * kCandCap * 8;
-  pl->total = align_up(pl->cnt_off + static_cast<size_t>(B) * pl->nsub * 4, 256);
+  encode_pick_mode(k_sel, &pl->mode, &pl->cap);
+  pl->cnt_off = pl->cand_off + static_cast<size_t>(B) * pl->nsub * pl->cap * 8;
+  pl->thr_off = pl->cnt_off + static_cast<size_t>(B) * pl->nsub * 4;
+  pl->total = align_up(pl->thr_off + static_cast<size_t>(B) * pl->nsub * 4, 256);
   return QSAE_OK;
 }
 
@@ -155,15 +162,18 @@ int qsae_encode_topk(const float* x_f32, const uint16_t* w_bf16, const float* w_
   el.B = B; el.H = H; el.D = D; el.k_sel = pl.k_sel;
   el.n_splits = pl.n_splits; el.tiles_per_split = pl.tiles_per_split; el.n_tiles = pl.n_tiles;
   el.act = act; el.bias = b_enc; el.debug_z = nullptr;
+  { const char* dm = getenv("QSAE_ENCODE_DEBUG_MODE"); el.debug_mode = dm ? atoi(dm) : 0; }
+  el.mode = pl.mode; el.cap = pl.cap;
   el.cand = ws + pl.cand_off;
   el.cand_cnt = reinterpret_cast<int*>(ws + pl.cnt_off);
+  el.cand_thr = reinterpret_cast<float*>(ws + pl.thr_off);
   rc = launch_status("encode_topk kernel", encode_topk_launch(x_bf16, w_bf16, el, st));
   if (rc != QSAE_OK) return rc;
 
   SelectLaunch sl;
-  sl.B = B; sl.H = H; sl.D = D; sl.k_sel = pl.k_sel; sl.k_out = k; sl.nsub = pl.nsub;
+  sl.B = B; sl.H = H; sl.D = D; sl.k_sel = pl.k_sel; sl.k_out = k; sl.nsub = pl.nsub; sl.cap = pl.cap;
   sl.act = act; sl.exact = exact;
-  sl.cand = el.cand; sl.cand_cnt = el.cand_cnt;
+  sl.cand = el.cand; sl.cand_cnt = el.cand_cnt; sl.cand_thr = el.cand_thr;
   sl.x_f32 = x_f32; sl.w_f32 = w_f32; sl.bias = b_enc;
   sl.out_vals = out_vals; sl.out_idx = out_idx; sl.out_flags = out_flags;
   return launch_status("select_topk kernel", select_topk_launch(sl, st));
@@ -184,9 +194,11 @@ int qsae_encode_dense_tc(const float* x_f32, const uint16_t* w_bf16, const float
   EncodeLaunch el;
   el.B = B; el.H = H; el.D = D; el.k_sel = 1;
   el.n_splits = pl.n_splits; el.tiles_per_split = pl.tiles_per_split; el.n_tiles = pl.n_tiles;
-  el.act = act; el.bias = b_enc; el.debug_z = z;
+  el.act = act; el.bias = b_enc; el.debug_z = z; el.debug_mode = 0;
+  el.mode = pl.mode; el.cap = pl.cap;
   el.cand = ws + pl.cand_off;
   el.cand_cnt = reinterpret_cast<int*>(ws + pl.cnt_off);
+  el.cand_thr = reinterpret_cast<float*>(ws + pl.thr_off);
   return launch_status("encode_topk kernel (dense dump)", encode_topk_launch(x_bf16, w_bf16, el, S(stream)));
 }
 
@@ -200,7 +212,7 @@ int qsae_encode_dense_f32(const float* x_f32, const int32_t* rows, int R, const 
 
 int qsae_topk_dense_workspace_bytes(int R, int H, int k, size_t* bytes) {
   if (!bytes || R < 0 || H <= 0 || k < 1) return fail(QSAE_ERR_INVALID_ARGUMENT, "topk_dense workspace: bad argument");
-  *bytes = align_up(static_cast<size_t>(R) * kCandCap * 8 + static_cast<size_t>(R) * 4, 256);
+  *bytes = align_up(static_cast<size_t>(R) * kDenseCap * 8 + static_cast<size_t>(R) * 4, 256);
   return QSAE_OK;
 }
 
@@ -216,12 +228,12 @@ int qsae_topk_dense(const float* z, int R, int H, int k, float* out_vals, int32_
   if (workspace_bytes < need) return fail(QSAE_ERR_WORKSPACE_TOO_SMALL, "topk_dense: workspace %zu < %zu", workspace_bytes, need);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   void* cand = ws;
-  int* cnt = reinterpret_cast<int*>(ws + static_cast<size_t>(R) * kCandCap * 8);
+  int* cnt = reinterpret_cast<int*>(ws + static_cast<size_t>(R) * kDenseCap * 8);
   int rc = launch_status("dense_candidates", dense_candidates_launch(z, R, H, k, cand, cnt, S(stream)));
   if (rc != QSAE_OK) return rc;
   SelectLaunch sl;
   memset(&sl, 0, sizeof(sl));
-  sl.B = R; sl.H = H; sl.D = 0; sl.k_sel = k; sl.k_out = k; sl.nsub = 1;
+  sl.B = R; sl.H = H; sl.D = 0; sl.k_sel = k; sl.k_out = k; sl.nsub = 1; sl.cap = kDenseCap;
   sl.cand = cand; sl.cand_cnt = cnt; sl.out_vals = out_vals; sl.out_idx = out_idx;
   return launch_status("select_topk kernel", select_topk_launch(sl, S(stream)));
 }

@@ -12,65 +12,104 @@ namespace qsae {
 
 namespace {
 
-constexpr int kSelWarps = 4;
+constexpr int kMaxSelWarps = 4;   // dense_candidates_kernel: rows per block
+constexpr int kSelThreads = 256;  // select_topk_kernel: one block per row
 
-// shared memory per warp: n_max gathered keys + ksort selected keys (+ ksort bf16 scores if exact)
-__global__ void __launch_bounds__(kSelWarps * 32)
+__device__ __forceinline__ void atomic_min_float_key(unsigned* addr, float v) { atomicMin(addr, float_to_key(v)); }
+__device__ __forceinline__ void atomic_max_float_key(unsigned* addr, float v) { atomicMax(addr, float_to_key(v)); }
+
+// One block per row. Warps gather the row's sub-streams in parallel (batched, coalesced loads,
+// filtered by the row-level bound), warp 0 picks the k_sel largest composite keys, all warps
+// re-score them in fp32 when asked to, then the block sorts and emits.
+// shared memory: n_max gathered keys + ksort selected keys.
+__global__ void __launch_bounds__(kSelThreads)
 select_topk_kernel(SelectLaunch p, int n_max, int ksort) {
   extern __shared__ __align__(16) uint8_t sel_smem[];
+  __shared__ int s_n, s_out;
+  __shared__ unsigned s_worst_key, s_dev_key;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * kSelWarps + warp;
-  if (row >= p.B) return;
+  const int nwarps = kSelThreads / 32;
+  const int row = blockIdx.x;
   const unsigned full = 0xffffffffu;
   const unsigned lt_mask = (1u << lane) - 1u;
-  uint64_t* keys = reinterpret_cast<uint64_t*>(sel_smem) + static_cast<size_t>(warp) * (n_max + ksort);
+  uint64_t* keys = reinterpret_cast<uint64_t*>(sel_smem);
   uint64_t* sel = keys + n_max;
 
-  // ---- gather
-  int n = 0;
+  if (threadIdx.x == 0) {
+    s_n = 0;
+    s_worst_key = 0xFFFFFFFFu;
+    s_dev_key = float_to_key(0.f);
+  }
+  // row-level bound: every sub-stream's bound is a lower bound of the row's k_sel-th value
+  float thr_row = -INFINITY;
+  if (p.cand_thr != nullptr)
+    for (int s = 0; s < p.nsub; ++s)
+      thr_row = fmaxf(thr_row, p.cand_thr[static_cast<size_t>(row) * p.nsub + s]);
+  __syncthreads();
+
+  // ---- gather survivors >= thr_row (order is irrelevant: the composite keys are unique)
   const uint2* cand = reinterpret_cast<const uint2*>(p.cand);
-  for (int s = 0; s < p.nsub; ++s) {
+  constexpr int BATCH = 8;
+  for (int s = warp; s < p.nsub; s += nwarps) {
     const size_t slot = static_cast<size_t>(row) * p.nsub + s;
-    const int c = min(p.cand_cnt[slot], kCandCap);
-    const uint2* src = cand + slot * kCandCap;
-    for (int e = lane; e < c; e += 32) {
-      const uint2 t = src[e];
-      keys[n + e] = make_sort_key(__uint_as_float(t.x), t.y);
+    const int c = min(p.cand_cnt[slot], p.cap);
+    const uint2* src = cand + slot * p.cap;
+    for (int base = 0; base < c; base += 32 * BATCH) {
+      uint2 t[BATCH];
+#pragma unroll
+      for (int i = 0; i < BATCH; ++i) {
+        const int e = base + i * 32 + lane;
+        t[i] = (e < c) ? src[e] : make_uint2(0u, 0u);
+      }
+#pragma unroll
+      for (int i = 0; i < BATCH; ++i) {
+        const int e = base + i * 32 + lane;
+        const bool keep = (e < c) && (__uint_as_float(t[i].x) >= thr_row);
+        const unsigned b = __ballot_sync(full, keep);
+        if (b != 0u) {
+          int pos = 0;
+          if (lane == 0) pos = atomicAdd(&s_n, __popc(b));
+          pos = __shfl_sync(full, pos, 0) + __popc(b & lt_mask);
+          if (keep) keys[pos] = make_sort_key(__uint_as_float(t[i].x), t[i].y);
+        }
+      }
     }
-    n += c;
   }
-  __syncwarp();
-
-  // ---- k_sel largest composite keys (unique, so the count lands on k_sel exactly)
+  __syncthreads();
+  const int n = s_n;
   const int k_sel = min(p.k_sel, n);
-  uint64_t T = 0ull;
-  if (n > k_sel) {
-#pragma unroll 1
-    for (int bit = 63; bit >= 0; --bit) {
-      const uint64_t probe = T | (1ull << bit);
-      int c = 0;
-      for (int e = lane; e < n; e += 32) c += (keys[e] >= probe) ? 1 : 0;
-      c = __reduce_add_sync(full, c);
-      if (c >= k_sel) T = probe;
-      if (c == k_sel) break;
-    }
-  }
-  int out = 0;
-  for (int base = 0; base < n; base += 32) {
-    const int e = base + lane;
-    const uint64_t key = (e < n) ? keys[e] : 0ull;
-    const bool keep = (e < n) && (key >= T);
-    const unsigned b = __ballot_sync(full, keep);
-    if (keep) sel[out + __popc(b & lt_mask)] = key;
-    out += __popc(b);
-  }
-  for (int e = out + lane; e < ksort; e += 32) sel[e] = 0ull;
-  __syncwarp();
 
-  // ---- optional exact fp32 re-scoring of the selected survivors
-  float worst_bf16 = INFINITY;  // weakest tensor-core score among the selected
-  float max_dev = 0.f;          // largest |fp32 - tensor-core| seen on this row
+  // ---- warp 0: the k_sel largest composite keys
+  if (warp == 0) {
+    uint64_t T = 0ull;
+    if (n > k_sel) {
+#pragma unroll 1
+      for (int bit = 63; bit >= 0; --bit) {
+        const uint64_t probe = T | (1ull << bit);
+        int c = 0;
+        for (int e = lane; e < n; e += 32) c += (keys[e] >= probe) ? 1 : 0;
+        c = __reduce_add_sync(full, c);
+        if (c >= k_sel) T = probe;
+        if (c == k_sel) break;
+      }
+    }
+    int out = 0;
+    for (int base = 0; base < n; base += 32) {
+      const int e = base + lane;
+      const uint64_t key = (e < n) ? keys[e] : 0ull;
+      const bool keep = (e < n) && (key >= T);
+      const unsigned b = __ballot_sync(full, keep);
+      if (keep) sel[out + __popc(b & lt_mask)] = key;
+      out += __popc(b);
+    }
+    for (int e = out + lane; e < ksort; e += 32) sel[e] = 0ull;
+    if (lane == 0) s_out = out;
+  }
+  __syncthreads();
+  const int out = s_out;
+
+  // ---- optional exact fp32 re-scoring, candidates spread over the warps
   if (p.exact) {
     const int D = p.D;
     float4 xr[4];
@@ -80,39 +119,55 @@ select_topk_kernel(SelectLaunch p, int n_max, int ksort) {
       xr[c] = (d < D) ? *reinterpret_cast<const float4*>(p.x_f32 + static_cast<size_t>(row) * D + d)
                       : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    float worst = INFINITY, dev = 0.f;
 #pragma unroll 1
-    for (int j = 0; j < out; ++j) {
-      const uint64_t key = sel[j];
-      const uint32_t col = sort_key_col(key);
-      const float* wrow = p.w_f32 + static_cast<size_t>(col) * D;
-      float acc = 0.f;
+    for (int j = warp * 2; j < out; j += nwarps * 2) {  // two candidates per trip
+      const bool has1 = (j + 1) < out;
+      const uint64_t key0 = sel[j];
+      const uint64_t key1 = has1 ? sel[j + 1] : key0;
+      const uint32_t col0 = sort_key_col(key0), col1 = sort_key_col(key1);
+      const float* w0 = p.w_f32 + static_cast<size_t>(col0) * D;
+      const float* w1 = p.w_f32 + static_cast<size_t>(col1) * D;
+      float a0 = 0.f, a1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const int d = c * 128 + lane * 4;
         if (d < D) {
-          const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + d));
-          acc = fmaf(xr[c].x, w.x, acc);
-          acc = fmaf(xr[c].y, w.y, acc);
-          acc = fmaf(xr[c].z, w.z, acc);
-          acc = fmaf(xr[c].w, w.w, acc);
+          const float4 u = __ldg(reinterpret_cast<const float4*>(w0 + d));
+          const float4 v = __ldg(reinterpret_cast<const float4*>(w1 + d));
+          a0 = fmaf(xr[c].x, u.x, a0); a0 = fmaf(xr[c].y, u.y, a0);
+          a0 = fmaf(xr[c].z, u.z, a0); a0 = fmaf(xr[c].w, u.w, a0);
+          a1 = fmaf(xr[c].x, v.x, a1); a1 = fmaf(xr[c].y, v.y, a1);
+          a1 = fmaf(xr[c].z, v.z, a1); a1 = fmaf(xr[c].w, v.w, a1);
         }
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(full, acc, o);
-      float s = acc + __ldg(p.bias + col);
-      if (p.act == 1) s = fmaxf(s, 0.f);
-      const float old = sort_key_value(key);
-      worst_bf16 = fminf(worst_bf16, old);
-      max_dev = fmaxf(max_dev, fabsf(s - old));
-      if (lane == 0) sel[j] = make_sort_key(s, col);
+      for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(full, a0, o);
+        a1 += __shfl_xor_sync(full, a1, o);
+      }
+      float s0 = a0 + __ldg(p.bias + col0);
+      float s1 = a1 + __ldg(p.bias + col1);
+      if (p.act == 1) { s0 = fmaxf(s0, 0.f); s1 = fmaxf(s1, 0.f); }
+      const float old0 = sort_key_value(key0), old1 = sort_key_value(key1);
+      worst = fminf(worst, fminf(old0, old1));
+      dev = fmaxf(dev, fmaxf(fabsf(s0 - old0), fabsf(s1 - old1)));
+      if (lane == 0) {
+        sel[j] = make_sort_key(s0, col0);
+        if (has1) sel[j + 1] = make_sort_key(s1, col1);
+      }
     }
-    __syncwarp();
+    if (lane == 0) {
+      atomic_min_float_key(&s_worst_key, worst);
+      atomic_max_float_key(&s_dev_key, dev);
+    }
   }
+  __syncthreads();
 
-  // ---- bitonic sort of sel[0, ksort) descending
+  // ---- block-wide bitonic sort of sel[0, ksort) descending
   for (int size = 2; size <= ksort; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = lane; t < (ksort >> 1); t += 32) {
+      for (int t = threadIdx.x; t < (ksort >> 1); t += kSelThreads) {
         const int pos = ((t / stride) * (stride << 1)) + (t % stride);
         const int partner = pos + stride;
         const bool desc = (pos & size) == 0;
@@ -122,23 +177,25 @@ select_topk_kernel(SelectLaunch p, int n_max, int ksort) {
           sel[partner] = a;
         }
       }
-      __syncwarp();
+      __syncthreads();
     }
   }
 
   // ---- emit
-  for (int j = lane; j < p.k_out; j += 32) {
+  for (int j = threadIdx.x; j < p.k_out; j += kSelThreads) {
     const uint64_t key = sel[j];
     const bool valid = j < out;
     p.out_vals[static_cast<size_t>(row) * p.k_out + j] = valid ? sort_key_value(key) : 0.f;
     p.out_idx[static_cast<size_t>(row) * p.k_out + j] = valid ? static_cast<int32_t>(sort_key_col(key)) : -1;
   }
-  if (p.out_flags != nullptr && lane == 0) {
+  if (p.out_flags != nullptr && threadIdx.x == 0) {
     int flag = 0;
     if (p.exact && n > k_sel && p.k_out <= out) {
       // every dropped candidate scored <= worst_bf16 on the tensor cores; the selection is
       // certified when even 4x the largest observed rounding deviation cannot lift one of
       // them over the exact k-th value
+      const float worst_bf16 = key_to_float(s_worst_key);
+      const float max_dev = key_to_float(s_dev_key);
       const float kth = sort_key_value(sel[p.k_out - 1]);
       if (!(worst_bf16 + 4.f * max_dev < kth)) flag = 1;
     }
@@ -146,36 +203,58 @@ select_topk_kernel(SelectLaunch p, int n_max, int ksort) {
   }
 }
 
-// Streaming survivors from a dense row: same threshold + compaction scheme as the fused
-// epilogue, one warp per row, lanes over 32 consecutive columns.
-__global__ void __launch_bounds__(kSelWarps * 32)
+// Streaming survivors from a dense row, one warp per row, lanes over 32 consecutive columns.
+// Lane l only ever sees columns == l (mod 32): with m = ceil(k/32) running maxima per lane there
+// are 32*m seen values >= min over lanes of the m-th largest, the same class bound as in the
+// fused epilogue (here m <= 7 covers kMaxK).
+constexpr int kDenseTop = (kMaxK + 31) / 32;
+
+__global__ void __launch_bounds__(kMaxSelWarps * 32)
 dense_candidates_kernel(const float* __restrict__ z, int R, int H, int k, uint2* cand, int* cand_cnt) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * kSelWarps + warp;
+  const int row = blockIdx.x * kMaxSelWarps + warp;
   if (row >= R) return;
   const unsigned full = 0xffffffffu;
   const unsigned lt_mask = (1u << lane) - 1u;
-  uint2* rb = cand + static_cast<size_t>(row) * kCandCap;
+  uint2* rb = cand + static_cast<size_t>(row) * kDenseCap;
   const float* zr = z + static_cast<size_t>(row) * H;
+  const int m = (k + 31) / 32;
+  float top[kDenseTop];
+#pragma unroll
+  for (int i = 0; i < kDenseTop; ++i) top[i] = -INFINITY;
   int cnt = 0;
-  float thr = -INFINITY;
+  float thr_ge = -INFINITY, thr_gt = -INFINITY;
   for (int base = 0; base < H; base += 32) {
     const int c = base + lane;
     const float v = (c < H) ? zr[c] : -INFINITY;
-    const bool keep = v > thr;
+    // insert v into this lane's sorted top-m (descending)
+    float carry = v;
+#pragma unroll
+    for (int i = 0; i < kDenseTop; ++i) {
+      if (i < m) {
+        const float hi = fmaxf(top[i], carry);
+        carry = fminf(top[i], carry);
+        top[i] = hi;
+      }
+    }
+    float mine = top[0];
+#pragma unroll
+    for (int i = 1; i < kDenseTop; ++i)
+      if (i < m) mine = top[i];
+    float bound = mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bound = fminf(bound, __shfl_xor_sync(full, bound, o));
+    thr_ge = fmaxf(thr_ge, bound);
+    const bool keep = (v >= thr_ge) && (v > thr_gt);
     const unsigned b = __ballot_sync(full, keep);
     if (keep) rb[cnt + __popc(b & lt_mask)] = make_uint2(__float_as_uint(v), static_cast<uint32_t>(c));
     cnt += __popc(b);
-    if (cnt > kCandCap - 32) {
+    if (cnt > kDenseCap - 32) {
       __syncwarp();
-      cnt = warp_compact_row(rb, cnt, k, lane, &thr);
+      cnt = warp_compact_row_generic(rb, cnt, k, lane, &thr_gt);
       __syncwarp();
     }
-  }
-  if (cnt > k) {
-    __syncwarp();
-    cnt = warp_compact_row(rb, cnt, k, lane, &thr);
   }
   if (lane == 0) cand_cnt[row] = cnt;
 }
@@ -190,26 +269,26 @@ int next_pow2(int v) {
 
 const char* select_topk_launch(const SelectLaunch& p, cudaStream_t stream) {
   const int ksort = next_pow2(p.k_sel < 2 ? 2 : p.k_sel);
-  const int n_max = p.nsub * (p.k_sel < kCandCap ? p.k_sel : kCandCap);
-  const size_t smem = static_cast<size_t>(kSelWarps) * (n_max + ksort) * sizeof(uint64_t);
-  if (smem > 200 * 1024) return "select_topk: too many survivors per row for shared memory";
-  static size_t smem_attr = 0;
-  if (smem > 48 * 1024 && smem > smem_attr) {
+  const int n_max = p.nsub * p.cap;
+  const size_t smem = static_cast<size_t>(n_max + ksort) * sizeof(uint64_t);
+  const size_t budget = 200 * 1024;
+  if (smem > budget) return "select_topk: too many survivors per row for shared memory";
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
     cudaError_t e = cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
+                                         static_cast<int>(budget));
     if (e != cudaSuccess) return cudaGetErrorString(e);
-    smem_attr = smem;
+    attr_set = true;
   }
-  const int blocks = (p.B + kSelWarps - 1) / kSelWarps;
-  select_topk_kernel<<<blocks, kSelWarps * 32, smem, stream>>>(p, n_max, ksort);
+  select_topk_kernel<<<p.B, kSelThreads, smem, stream>>>(p, n_max, ksort);
   return cuda_err(cudaGetLastError());
 }
 
 const char* dense_candidates_launch(const float* z, int R, int H, int k, void* cand, int* cand_cnt,
                                     cudaStream_t stream) {
-  const int blocks = (R + kSelWarps - 1) / kSelWarps;
-  dense_candidates_kernel<<<blocks, kSelWarps * 32, 0, stream>>>(z, R, H, k,
-                                                                 reinterpret_cast<uint2*>(cand), cand_cnt);
+  const int blocks = (R + kMaxSelWarps - 1) / kMaxSelWarps;
+  dense_candidates_kernel<<<blocks, kMaxSelWarps * 32, 0, stream>>>(z, R, H, k,
+                                                                    reinterpret_cast<uint2*>(cand), cand_cnt);
   return cuda_err(cudaGetLastError());
 }
 

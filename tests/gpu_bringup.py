@@ -64,7 +64,7 @@ def _():
         ref_pol = O.polarize_loss(inp["logits"], cfg["n_bits"])
         assert abs(pol - ref_pol) <= 1e-5 * max(1.0, abs(ref_pol)), (pol, ref_pol)
         soft = L.dequant_soft(T(inp["logits"]), cfg["D"], cfg["n_bits"]).cpu().numpy()
-        np.testing.assert_allclose(soft, O.dequant_soft(inp["logits"], cfg["n_bits"]), rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(soft, O.dequant_soft(inp["logits"], cfg["n_bits"]), rtol=1e-5, atol=2e-7 * 2 ** cfg["n_bits"])
         print("   ", name, "pol", pol, "gap", gap)
 
 
