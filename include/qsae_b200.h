@@ -97,6 +97,11 @@ int qsae_transpose_f32(const float* src, int R, int C, float* dst, void* stream)
 
 int qsae_encode_topk_workspace_bytes(int B, int H, int D, int k, size_t* bytes);
 
+/* Measurement hook: when both are non-NULL (cudaEvent_t), the calling thread's next
+ * qsae_encode_topk calls record them on their stream immediately before / after the fused
+ * encoder kernel, so a caller can time the dominant kernel alone. NULL, NULL switches it off. */
+int qsae_set_encode_kernel_events(void* start_event, void* stop_event);
+
 int qsae_encode_topk(const float* x_f32,      /* [B, D] device                              */
                      const uint16_t* w_bf16,   /* [H, D] from qsae_cast_f32_to_bf16          */
                      const float* w_f32,       /* [H, D] original weights; may be NULL if !exact */

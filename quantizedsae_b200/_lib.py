@@ -29,6 +29,7 @@ SYMBOLS = {
     "qsae_dequant_soft": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "qsae_transpose_f32": (_i, [_vp, _i, _i, _vp, _vp]),
     "qsae_encode_topk_workspace_bytes": (_i, [_i, _i, _i, _i, C.POINTER(_sz)]),
+    "qsae_set_encode_kernel_events": (_i, [_vp, _vp]),
     "qsae_encode_topk": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "qsae_encode_dense_tc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "qsae_encode_dense_f32": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),

@@ -16,6 +16,9 @@ using namespace qsae;
 namespace {
 
 thread_local char g_err[512] = "";
+// optional CUDA events recorded immediately around the fused encoder kernel (bench.py roofline)
+thread_local cudaEvent_t g_enc_ev_start = nullptr;
+thread_local cudaEvent_t g_enc_ev_stop = nullptr;
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -97,6 +100,12 @@ int qsae_check_device(void) {
   return QSAE_OK;
 }
 
+int qsae_set_encode_kernel_events(void* start_event, void* stop_event) {
+  g_enc_ev_start = reinterpret_cast<cudaEvent_t>(start_event);
+  g_enc_ev_stop = reinterpret_cast<cudaEvent_t>(stop_event);
+  return QSAE_OK;
+}
+
 int qsae_cast_f32_to_bf16(const float* src, uint16_t* dst, size_t n, void* stream) {
   if (!src || !dst) return fail(QSAE_ERR_INVALID_ARGUMENT, "cast: null pointer");
   if (n == 0) return QSAE_OK;
@@ -167,7 +176,9 @@ int qsae_encode_topk(const float* x_f32, const uint16_t* w_bf16, const float* w_
   el.cand = ws + pl.cand_off;
   el.cand_cnt = reinterpret_cast<int*>(ws + pl.cnt_off);
   el.cand_thr = reinterpret_cast<float*>(ws + pl.thr_off);
+  if (g_enc_ev_start) cudaEventRecord(g_enc_ev_start, st);
   rc = launch_status("encode_topk kernel", encode_topk_launch(x_bf16, w_bf16, el, st));
+  if (g_enc_ev_stop) cudaEventRecord(g_enc_ev_stop, st);
   if (rc != QSAE_OK) return rc;
 
   SelectLaunch sl;

@@ -1,0 +1,6 @@
+"""nn.Module mirror of the reference's `quantized_sae.sae` package (same class names)."""
+from .base import SparseAutoencoder
+from .baseline import BaselineSparseAutoencoder
+from .binary import BinarySAE, binary_decoder
+
+__all__ = ["SparseAutoencoder", "BaselineSparseAutoencoder", "BinarySAE", "binary_decoder"]

@@ -1,0 +1,352 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu). Every call goes through the C ABI
+(libqsae_b200.so via ctypes); results are checked against
+  * the committed outputs of the unmodified reference (tests/golden/*.npz), and
+  * the numpy oracle on seeded inputs, bit-exact for integer / index work.
+Tolerances (stated once):
+  dictionary integers, packed nibbles, top-k indices ........ bit exact
+  latent values (bf16-representable inputs or exact mode) .... |dv| <= 1e-5 * max(1, |v|)
+  reconstructions (fp32 accumulate) ........................... atol 1e-4 * rms(recon) + rtol 1e-4
+"""
+import numpy as np
+import pytest
+import torch
+
+import quantizedsae_b200 as Q
+from oracle import qsae_oracle as O
+from quantizedsae_b200 import _lib as L
+from tests.golden import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def T(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def assert_recon_close(got, ref):
+    rms = float(np.sqrt(np.mean(np.square(ref, dtype=np.float64)))) + 1e-30
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-4 * rms)
+
+
+def assert_vals_close(got, ref):
+    assert np.all(np.abs(got - ref) <= 1e-5 * np.maximum(1.0, np.abs(ref)))
+
+
+def test_device_and_library(cuda_device):
+    L.check(L.load().qsae_check_device())
+    assert torch.cuda.get_device_capability(0)[0] == 10
+
+
+# ------------------------------------------------------------------------------------------
+# weight preparation
+# ------------------------------------------------------------------------------------------
+def test_cast_bf16_bit_exact(cuda_device):
+    a = np.random.default_rng(0).standard_normal((1000, 77)).astype(np.float32)
+    a[0, :4] = [0.0, -0.0, 1e-40, 3.3895314e38]
+    got = L.cast_bf16(T(a, cuda_device)).float().cpu().numpy()
+    assert np.array_equal(got, cases.round_bf16(a))
+
+
+@pytest.mark.parametrize("name", list(cases.BSAE_CASES))
+def test_pack_bitplanes_matches_reference_int_weights(cuda_device, golden_dir, name):
+    cfg = cases.BSAE_CASES[name]
+    g = np.load(golden_dir / f"{name}.npz")
+    inp = cases.bsae_inputs(cfg)
+    packed, pol, gap = L.pack_bitplanes(T(inp["logits"], cuda_device), cfg["D"], cfg["n_bits"])
+    got = O.unpack_nibbles(packed.cpu().numpy()) if cfg["n_bits"] <= 4 else packed.cpu().numpy().view(np.int8)
+    assert np.array_equal(got, g["int_weights"])               # reference quantized_int_weights()
+    assert pol == pytest.approx(float(g["polarize"]), rel=1e-5, abs=1e-9)
+    assert (gap == 0.0) == cfg["polar"]
+    soft = L.dequant_soft(T(inp["logits"], cuda_device), cfg["D"], cfg["n_bits"]).cpu().numpy()
+    np.testing.assert_allclose(soft[:4], g["soft_weights_row0"], rtol=1e-5, atol=2e-7 * 2 ** cfg["n_bits"])
+
+
+def test_readme_known_answer_and_all_nibbles(cuda_device):
+    pat = np.array([[(v >> i) & 1 for i in range(4)] for v in range(16)], dtype=np.float32)
+    logits = np.where(pat.reshape(1, 64) > 0, 110.0, -110.0).astype(np.float32)
+    packed, pol, gap = L.pack_bitplanes(T(logits, cuda_device), 16, 4)
+    ints = O.unpack_nibbles(packed.cpu().numpy())[0]
+    assert ints.tolist() == [v if v < 8 else v - 16 for v in range(16)]
+    assert ints[0b0101 + 0] == 5 and ints[10] == -6             # README.md:100: bits [0,1,0,1] LSB-first -> -6
+    vals = T(np.ones((1, 1), np.float32), cuda_device)
+    idx = T(np.zeros((1, 1), np.int32), cuda_device)
+    recon = L.decode_int4(vals, idx, packed, 1, 16, 4.0 / 8, None).cpu().numpy()[0]
+    assert recon[10] == -3.0                                     # -6 * (4.0 / 8)
+    assert pol == 0.0 and gap == 0.0
+
+
+# ------------------------------------------------------------------------------------------
+# sparse decoders, densify
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,k,H,D", [(1, 1, 256, 8), (37, 4, 2048, 64), (130, 32, 4096, 512), (9, 65, 1024, 256)])
+def test_decoders_vs_oracle(cuda_device, B, k, H, D):
+    rng = np.random.default_rng(B * 7 + k)
+    iw = rng.integers(-8, 8, size=(H, D)).astype(np.int8)
+    vals = rng.standard_normal((B, k)).astype(np.float32)
+    idx = np.stack([rng.choice(H, k, replace=False) for _ in range(B)]).astype(np.int32)
+    idx[0, -1] = -1                                              # empty slot is skipped
+    bias = rng.standard_normal(D).astype(np.float32)
+    vz = vals.copy()
+    vz[0, -1] = 0
+    iz = np.where(idx < 0, 0, idx)
+    ref = O.decode_rows(vz, iz, iw.astype(np.float32), 0.5, bias)
+    dv, di = T(vals, cuda_device), T(idx, cuda_device)
+    assert_recon_close(L.decode_int4(dv, di, T(O.pack_nibbles(iw), cuda_device), H, D, 0.5, T(bias, cuda_device)).cpu().numpy(), ref)
+    assert_recon_close(L.decode_int8(dv, di, T(iw, cuda_device), H, D, 0.5, T(bias, cuda_device)).cpu().numpy(), ref)
+    rows = rng.standard_normal((H, D)).astype(np.float32)
+    ref = O.decode_rows(vz, iz, rows, 1.0, None)
+    assert_recon_close(L.decode_rows_f32(dv, di, T(rows, cuda_device), H, D, 1.0, None).cpu().numpy(), ref)
+    dense = L.densify(T(vz, cuda_device), T(iz, cuda_device), H).cpu().numpy()
+    assert np.array_equal(dense, O.densify(vz, iz, H))
+    assert np.array_equal(L.transpose(T(rows, cuda_device)).cpu().numpy(), rows.T)
+
+
+def test_decode_linearity_full_size(cuda_device):
+    """Size-independent property at the headline shape: decode(a*v1 + v2-rows) is linear in vals."""
+    H, D, B, k = 32768, 512, 4096, 32
+    g = torch.Generator(device=cuda_device).manual_seed(1)
+    packed = torch.randint(0, 256, (H, D // 2), dtype=torch.uint8, device=cuda_device, generator=g)
+    idx = torch.randint(0, H, (B, k), dtype=torch.int32, device=cuda_device, generator=g)
+    v1 = torch.randn((B, k), device=cuda_device, generator=g)
+    v2 = torch.randn((B, k), device=cuda_device, generator=g)
+    r1 = L.decode_int4(v1, idx, packed, H, D, 0.5, None)
+    r2 = L.decode_int4(v2, idx, packed, H, D, 0.5, None)
+    r12 = L.decode_int4(2.0 * v1 + v2, idx, packed, H, D, 0.5, None)
+    torch.testing.assert_close(r12, 2.0 * r1 + r2, rtol=1e-4, atol=1e-3)
+    # checksum against the oracle on a few rows
+    rows = [0, 1, 777, B - 1]
+    ref = O.decode_rows(v1[rows].cpu().numpy(), idx[rows].cpu().numpy(),
+                        O.unpack_nibbles(packed.cpu().numpy()).astype(np.float32), 0.5, None)
+    assert_recon_close(r1[rows].cpu().numpy(), ref)
+
+
+# ------------------------------------------------------------------------------------------
+# encoder + top-k
+# ------------------------------------------------------------------------------------------
+def _enc_case(B, H, D, seed, bf16=True):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((B, D)).astype(np.float32)
+    W = cases.xavier_uniform(rng, H, D)
+    if bf16:
+        x, W = cases.round_bf16(x), cases.round_bf16(W)
+    b = (0.01 * rng.standard_normal(H)).astype(np.float32)
+    return x, W, b
+
+
+@pytest.mark.parametrize("B,H,D", [(128, 256, 64), (200, 1024, 512), (77, 1000, 72), (1, 300, 8)])
+def test_tensor_core_gemm_vs_fp32(cuda_device, B, H, D):
+    x, W, b = _enc_case(B, H, D, 3)
+    z = L.encode_dense_tc(T(x, cuda_device), L.cast_bf16(T(W, cuda_device)), T(b, cuda_device)).cpu().numpy()
+    np.testing.assert_allclose(z, O.encode_pre(x, W, b), rtol=1e-5, atol=1e-5)
+    zr = L.encode_dense_tc(T(x, cuda_device), L.cast_bf16(T(W, cuda_device)), T(b, cuda_device), act=L.ACT_RELU).cpu().numpy()
+    np.testing.assert_allclose(zr, np.maximum(O.encode_pre(x, W, b), 0), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,H,D,k", [
+    (32, 2048, 64, 4), (48, 4096, 512, 8), (300, 8192, 256, 32), (130, 32768, 512, 65),
+    (1, 512, 512, 1), (129, 1000, 72, 33), (5, 300, 8, 150), (64, 4096, 512, 224), (17, 64, 64, 64)])
+def test_fused_topk_bit_exact_indices(cuda_device, B, H, D, k):
+    x, W, b = _enc_case(B, H, D, 100 + k)
+    vals, idx, _ = L.encode_topk(T(x, cuda_device), L.cast_bf16(T(W, cuda_device)), None, T(b, cuda_device), k)
+    rv, ri = O.topk_rows(O.encode_pre(x, W, b), k)
+    assert np.array_equal(idx.cpu().numpy(), ri)
+    assert_vals_close(vals.cpu().numpy(), rv)
+
+
+def test_fused_topk_exact_mode_fp32_inputs(cuda_device):
+    """Arbitrary fp32 operands: bf16 candidates + fp32 re-scoring must reproduce the fp32 oracle."""
+    B, H, D, k = 256, 32768, 512, 32
+    x, W, b = _enc_case(B, H, D, 5, bf16=False)
+    dx, dW, db = T(x, cuda_device), T(W, cuda_device), T(b, cuda_device)
+    vals, idx, flags = L.encode_topk(dx, L.cast_bf16(dW), dW, db, k, exact=True, want_flags=True)
+    rv, ri = O.topk_rows(O.encode_pre(x, W, b), k)
+    assert np.array_equal(idx.cpu().numpy(), ri)
+    assert_vals_close(vals.cpu().numpy(), rv)
+    assert int(flags.sum()) == 0                                  # every row certified
+    # and k = 65 (reference default at H = 32768)
+    vals, idx, flags = L.encode_topk(dx, L.cast_bf16(dW), dW, db, 65, exact=True, want_flags=True)
+    rv, ri = O.topk_rows(O.encode_pre(x, W, b), 65)
+    assert np.array_equal(idx.cpu().numpy(), ri)
+    assert int(flags.sum()) == 0
+
+
+def test_relu_and_tie_rule(cuda_device):
+    """ReLU floods the stream with equal zeros: survivors must follow (value desc, index asc)."""
+    B, H, D, k = 64, 4096, 64, 48
+    x, W, b = _enc_case(B, H, D, 9)
+    b = b - 0.6                                                   # most pre-activations negative
+    vals, idx, _ = L.encode_topk(T(x, cuda_device), L.cast_bf16(T(W, cuda_device)), None, T(b, cuda_device), k, act=L.ACT_RELU)
+    rv, ri = O.topk_rows(np.maximum(O.encode_pre(x, W, b), 0).astype(np.float32), k)
+    assert (rv == 0).any(), "case should contain ties at zero"
+    assert np.array_equal(idx.cpu().numpy(), ri)
+    z = np.zeros((3, 5000), dtype=np.float32)
+    z[:, 2500] = 1
+    _, i2 = L.topk_dense(T(z, cuda_device), 4)
+    assert i2.cpu().numpy().tolist() == [[2500, 0, 1, 2]] * 3
+
+
+def test_topk_dense_and_simt_encoder(cuda_device):
+    for (B, H, D, k) in [(20, 1000, 72, 5), (33, 4096, 512, 65), (5, 300, 8, 224)]:
+        x, W, b = _enc_case(B, H, D, 2, bf16=False)
+        z = L.encode_dense(T(x, cuda_device), T(W, cuda_device), T(b, cuda_device))
+        np.testing.assert_allclose(z.cpu().numpy(), O.encode_pre(x, W, b), rtol=1e-4, atol=1e-5)
+        vals, idx = L.topk_dense(z, k)
+        rv, ri = O.topk_rows(z.cpu().numpy(), k)
+        assert np.array_equal(idx.cpu().numpy(), ri) and np.array_equal(vals.cpu().numpy(), rv)
+
+
+def test_edge_cases(cuda_device):
+    x, W, b = _enc_case(4, 512, 64, 11)
+    dW = L.cast_bf16(T(W, cuda_device))
+    v, i, _ = L.encode_topk(T(x[:0], cuda_device), dW, None, T(b, cuda_device), 4)    # empty batch
+    assert v.shape == (0, 4) and i.shape == (0, 4)
+    with pytest.raises(RuntimeError, match="out of range"):                            # k > H like torch.topk
+        L.encode_topk(T(x, cuda_device), dW, None, T(b, cuda_device), 513)
+    with pytest.raises(L.QsaeError):
+        L.encode_topk(T(x, cuda_device), dW, None, T(b, cuda_device), 0)
+    with pytest.raises(L.QsaeError):                                                   # D not a multiple of 8
+        L.encode_topk(torch.zeros(4, 12, device=cuda_device), torch.zeros(16, 12, device=cuda_device).bfloat16(),
+                      None, torch.zeros(16, device=cuda_device), 2)
+
+
+def test_full_size_properties(cuda_device):
+    """Headline shape (B=4096, H=32768, D=512): oracle on a row sample + self-consistency."""
+    B, H, D, k = 4096, 32768, 512, 32
+    x, W, b = _enc_case(B, H, D, 21)
+    dx, dW, db = T(x, cuda_device), T(W, cuda_device), T(b, cuda_device)
+    vals, idx, _ = L.encode_topk(dx, L.cast_bf16(dW), None, db, k)
+    rows = np.r_[0:16, 2040:2056, B - 16:B]
+    rv, ri = O.topk_rows(O.encode_pre(x[rows], W, b), k)
+    assert np.array_equal(idx.cpu().numpy()[rows], ri)
+    assert_vals_close(vals.cpu().numpy()[rows], rv)
+    v = vals.cpu().numpy()
+    i = idx.cpu().numpy()
+    assert np.all(np.diff(v, axis=1) <= 0)                                             # sorted descending
+    assert all(len(set(r)) == k for r in i[::97])                                      # distinct indices
+    assert i.min() >= 0 and i.max() < H
+    # values agree with an independent CUDA-core fp32 evaluation of the same (row, index) pairs
+    z = L.encode_dense(dx, dW, db, rows=T(np.arange(0, B, 64, dtype=np.int32), cuda_device)).cpu().numpy()
+    sel = np.take_along_axis(z, i[::64].astype(np.int64), axis=1)
+    assert_vals_close(v[::64], sel)
+    assert_vals_close(v[::64, 0], z.max(1))                                            # row maximum is first
+    assert np.all(np.sort(z, axis=1)[:, -k] <= v[::64, -1] + 1e-5)                     # nothing larger was left out
+    # idempotence: densify -> dense top-k returns the same sparse form
+    d = L.densify(vals[:64], idx[:64], H)
+    v2, i2 = L.topk_dense(d, k)
+    assert torch.equal(i2, idx[:64]) and torch.equal(v2, vals[:64])
+
+
+# ------------------------------------------------------------------------------------------
+# modules vs the reference's own outputs
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(cases.BSAE_CASES))
+def test_bsae_module_matches_reference(cuda_device, golden_dir, name):
+    cfg = cases.BSAE_CASES[name]
+    g = np.load(golden_dir / f"{name}.npz")
+    inp = cases.bsae_inputs(cfg)
+    m = Q.BinarySAE(cfg["D"], cfg["H"], cfg["gamma"], cfg["n_bits"])
+    m.load_state_dict({"encoder.0.weight": torch.from_numpy(inp["We"]), "encoder.0.bias": torch.from_numpy(inp["be"]),
+                       "decoder.weight": torch.from_numpy(inp["logits"]), "decoder.bias": torch.from_numpy(inp["bd"])},
+                      strict=True)
+    m.to(cuda_device).eval()
+    with torch.no_grad():
+        latent, recon, pol = m(T(inp["x"], cuda_device))
+    assert latent.shape == (cfg["B"], cfg["H"]) and recon.shape == (cfg["B"], cfg["D"]) and pol.dim() == 0
+    vals, idx = cases.sparse_from_dense(latent.cpu().numpy())
+    assert np.array_equal(idx, g["latent_idx"])                   # bit-exact top-k index sets and order
+    assert_vals_close(vals, g["latent_vals"])
+    assert_recon_close(recon.cpu().numpy(), g["recon"])
+    assert float(pol) == pytest.approx(float(g["polarize"]), rel=1e-5, abs=1e-9)
+    assert m.decoder.resolved_mode() == ("int" if cfg["polar"] else "soft")
+    assert int(m.last_flags.sum()) == 0
+    assert np.array_equal(m.decoder.quantized_int_weights().cpu().numpy().astype(np.int8), g["int_weights"])
+    # sparse return form carries the same information
+    m.return_dense = False
+    with torch.no_grad():
+        sp, recon2, _ = m(T(inp["x"], cuda_device))
+    assert torch.equal(sp.to_dense(), latent) and torch.equal(recon2, recon)
+    # the standalone decoder accepts the dense latent the reference passes (sae/binary.py:101)
+    with torch.no_grad():
+        recon3, _ = m.decoder(latent, None)
+    assert_recon_close(recon3.cpu().numpy(), g["recon"])
+    # dense encode() agrees with the oracle pre-activations
+    with torch.no_grad():
+        z = m.encode(T(inp["x"], cuda_device)).cpu().numpy()
+    np.testing.assert_allclose(z, O.encode_pre(inp["x"], inp["We"], inp["be"]), rtol=1e-4, atol=1e-5)
+
+
+def test_bsae_forced_int_mode_is_the_hard_dictionary(cuda_device):
+    cfg = cases.BSAE_CASES["bsae_soft_d64_h2048"]
+    inp = cases.bsae_inputs(cfg)
+    m = Q.BinarySAE(cfg["D"], cfg["H"], cfg["gamma"], cfg["n_bits"]).to(cuda_device)
+    with torch.no_grad():
+        m.encoder[0].weight.copy_(T(inp["We"], cuda_device)); m.encoder[0].bias.copy_(T(inp["be"], cuda_device))
+        m.decoder.weight.copy_(T(inp["logits"], cuda_device)); m.decoder.bias.copy_(T(inp["bd"], cuda_device))
+    m.decoder.decode_mode = "int"
+    with torch.no_grad():
+        _, recon, _ = m(T(inp["x"], cuda_device))
+    k = O.bsae_k(cfg["H"])
+    _, _, ref, _ = O.bsae_forward(inp["x"], inp["We"], inp["be"], inp["logits"], inp["bd"],
+                                  n_bits=cfg["n_bits"], gamma=cfg["gamma"], k=k, mode="hard")
+    assert_recon_close(recon.cpu().numpy(), ref)
+    # cache invalidation: changing the logits in place must change the packed dictionary
+    with torch.no_grad():
+        m.decoder.weight.neg_()
+        _, recon_neg, _ = m(T(inp["x"], cuda_device))
+    _, _, ref_neg, _ = O.bsae_forward(inp["x"], inp["We"], inp["be"], -inp["logits"], inp["bd"],
+                                      n_bits=cfg["n_bits"], gamma=cfg["gamma"], k=k, mode="hard")
+    assert_recon_close(recon_neg.cpu().numpy(), ref_neg)
+
+
+@pytest.mark.parametrize("name", list(cases.BASELINE_CASES))
+def test_baseline_module_matches_reference(cuda_device, golden_dir, name):
+    cfg = cases.BASELINE_CASES[name]
+    g = np.load(golden_dir / f"{name}.npz")
+    inp = cases.baseline_inputs(cfg)
+    m = Q.BaselineSparseAutoencoder(cfg["D"], cfg["H"])
+    m.load_state_dict({"encoder.0.weight": torch.from_numpy(inp["We"]), "encoder.0.bias": torch.from_numpy(inp["be"]),
+                       "decoder.weight": torch.from_numpy(inp["Wd"]), "decoder.bias": torch.from_numpy(inp["bd"])},
+                      strict=True)
+    m.to(cuda_device).eval()
+    with torch.no_grad():
+        h, recon = m(T(inp["x"], cuda_device))
+    vals, idx = cases.sparse_from_dense(h.cpu().numpy())
+    assert np.array_equal(idx, g["latent_idx"])
+    assert_vals_close(vals, g["latent_vals"])
+    assert_recon_close(recon.cpu().numpy(), g["recon"])
+    with torch.no_grad():
+        z = T(O.encode_pre(inp["x"], inp["We"], inp["be"]), cuda_device)
+        assert torch.equal(m.apply_topk_activation(z) != 0, h != 0)
+
+
+def test_host_pipeline_entry(cuda_device):
+    """qsae_bsae_forward_host: host buffers in, host buffers out, chunked and overlapped."""
+    import ctypes as C
+
+    cfg = cases.BSAE_CASES["bsae_polar_d512_h4096"]
+    inp = cases.bsae_inputs(cfg)
+    k = O.bsae_k(cfg["H"])
+    lib = L.load()
+    dW, db = T(inp["We"], cuda_device), T(inp["be"], cuda_device)
+    dl, dbd = T(inp["logits"], cuda_device), T(inp["bd"], cuda_device)
+    plan = C.c_void_p()
+    L.check(lib.qsae_bsae_plan_create(dW.data_ptr(), db.data_ptr(), dl.data_ptr(), dbd.data_ptr(), cfg["H"], cfg["D"],
+                                      cfg["n_bits"], cfg["gamma"], k, 20, C.byref(plan)))
+    try:
+        B = cfg["B"]
+        x = torch.from_numpy(inp["x"]).pin_memory()
+        vals = torch.empty((B, k), dtype=torch.float32).pin_memory()
+        idx = torch.empty((B, k), dtype=torch.int32).pin_memory()
+        recon = torch.empty((B, cfg["D"]), dtype=torch.float32).pin_memory()
+        L.check(lib.qsae_bsae_forward_host(plan, x.data_ptr(), B, vals.data_ptr(), idx.data_ptr(), recon.data_ptr()))
+    finally:
+        lib.qsae_bsae_plan_destroy(plan)
+    rv, ri, rr, _ = O.bsae_forward(inp["x"], inp["We"], inp["be"], inp["logits"], inp["bd"],
+                                   n_bits=cfg["n_bits"], gamma=cfg["gamma"], k=k, mode="hard")
+    assert np.array_equal(idx.numpy(), ri)
+    assert_vals_close(vals.numpy(), rv)
+    assert_recon_close(recon.numpy(), rr)
+
+
+def test_native_library_was_used(cuda_device):
+    assert L._lib is not None and L.launch_count > 0

@@ -1,0 +1,144 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol the header declares,
+the host modules mirror the reference's constructors / attributes / state_dict layout, and the
+product path refuses to run without CUDA instead of falling back."""
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+import quantizedsae_b200 as Q
+from quantizedsae_b200 import _lib
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _header_functions():
+    text = (ROOT / "include" / "qsae_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(qsae_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()                      # builds with nvcc if missing; raises if it cannot
+    declared = _header_functions()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/qsae_b200.h but not exported"
+    assert set(declared) == set(_lib.SYMBOLS), "ctypes table and header disagree"
+    assert lib.qsae_abi_version() == 1
+
+
+def test_sass_is_blackwell_native():
+    """tcgen05 / TMA / TMEM loads must be present in the built library (no GPU needed)."""
+    import shutil
+    import subprocess
+
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(exe).exists():
+        pytest.skip("cuobjdump not available")
+    _lib.load()
+    sass = subprocess.run([exe, "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, f"{mnemonic} missing from libqsae_b200.so SASS"
+    assert "HMMA." not in sass.replace("UTCHMMA", ""), "legacy mma.sync path found"
+
+
+def test_argument_validation_without_gpu():
+    """Pure host-side validation paths of the C ABI (they return before touching a device)."""
+    import ctypes as C
+
+    lib = _lib.load()
+    n = C.c_size_t(0)
+    assert lib.qsae_encode_topk_workspace_bytes(128, 1024, 500, 8, C.byref(n)) == -1   # D % 8
+    assert b"multiple of 8" in lib.qsae_last_error()
+    assert lib.qsae_encode_topk_workspace_bytes(128, 1024, 1024, 8, C.byref(n)) == -1  # D > 512
+    assert lib.qsae_encode_topk_workspace_bytes(128, 16, 64, 32, C.byref(n)) == -5     # k > H
+    assert b"out of range" in lib.qsae_last_error()
+    assert lib.qsae_encode_topk_workspace_bytes(128, 4096, 64, 500, C.byref(n)) == -1  # k > MAX_K
+    assert lib.qsae_pack_bitplanes(None, 8, 8, 4, None, None, None) == -1
+    assert lib.qsae_decode_int4(None, None, 1, 1, None, 8, 8, 1.0, None, None, None) == -1
+    with pytest.raises(RuntimeError):
+        _lib.check(-5)
+    with pytest.raises(_lib.QsaeError):
+        _lib.check(-1)
+
+
+def test_bsae_constructor_attributes_and_state_dict():
+    m = Q.BinarySAE(64, 2048, 4.0, 4)                     # positional, like scripts/training/train.py:60-91
+    assert (m.input_dim, m.hidden_dim, m.n_bits, m.k) == (64, 2048, 4, 0.002)
+    assert isinstance(m.encoder, torch.nn.Sequential) and isinstance(m.encoder[0], torch.nn.Linear)
+    d = m.decoder
+    assert (d.in_features, d.out_features, d.n_bits, d.gamma, d.quantization_step) == (2048, 64, 4, 4.0, 0.5)
+    assert d.scale_factor == 16
+    sd = m.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {
+        "encoder.0.weight": (2048, 64), "encoder.0.bias": (2048,),
+        "decoder.weight": (2048, 256), "decoder.bias": (64,)}
+    assert all(v.dtype == torch.float32 for v in sd.values())
+    assert float(m.encoder[0].bias.abs().max()) == 0.0     # zeros_ init (sae/binary.py:87)
+    bound = (6.0 / (64 + 2048)) ** 0.5                      # xavier_uniform gain 1 (sae/binary.py:86)
+    assert float(m.encoder[0].weight.abs().max()) <= bound + 1e-6
+    m8 = Q.BinarySAE(32, 1024)                              # defaults gamma=4.0, n_bits=8
+    assert m8.n_bits == 8 and m8.decoder.quantization_step == 4.0 / 128
+
+
+def test_bsae_state_dict_matches_reference_fixture(golden_dir):
+    import numpy as np
+
+    g = np.load(golden_dir / "bsae_polar_d64_h2048.npz")
+    m = Q.BinarySAE(64, 2048, 4.0, 4)
+    assert sorted(m.state_dict().keys()) == g["state_keys"].tolist()
+    assert [str(tuple(v.shape)) for _, v in sorted(m.state_dict().items())] == g["state_shapes"].tolist()
+    g = np.load(golden_dir / "baseline_d64_h2048.npz")
+    b = Q.BaselineSparseAutoencoder(64, 2048)
+    assert sorted(b.state_dict().keys()) == g["state_keys"].tolist()
+    assert [str(tuple(v.shape)) for _, v in sorted(b.state_dict().items())] == g["state_shapes"].tolist()
+    assert b.topk == 32
+
+
+def test_state_dict_round_trip_strict():
+    a, b = Q.BinarySAE(64, 1024, 1.5, 4), Q.BinarySAE(64, 1024, 1.5, 4)
+    b.load_state_dict(a.state_dict(), strict=True)
+    for k, v in a.state_dict().items():
+        assert torch.equal(v, b.state_dict()[k])
+
+
+def test_base_class_contract():
+    s = Q.SparseAutoencoder(8, 16)
+    with pytest.raises(NotImplementedError):
+        s.encode(torch.zeros(1, 8))
+    with pytest.raises(NotImplementedError):
+        s.decode(torch.zeros(1, 16))
+
+
+def test_no_cpu_fallback():
+    m = Q.BinarySAE(64, 1024, 4.0, 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(4, 64))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Q.BaselineSparseAutoencoder(64, 1024)(torch.zeros(4, 64))
+    with pytest.raises(_lib.QsaeError):
+        _lib.cast_bf16(torch.zeros(8))
+
+
+def test_prepared_cache_invalidation():
+    from quantizedsae_b200.sae.base import PreparedCache, param_key
+
+    p = torch.nn.Parameter(torch.zeros(4))
+    cache, calls = PreparedCache(), []
+    make = lambda: calls.append(1) or len(calls)
+    assert cache.get("x", param_key(p), make) == 1
+    assert cache.get("x", param_key(p), make) == 1          # cached
+    with torch.no_grad():
+        p.add_(1.0)                                         # in-place update bumps _version
+    assert cache.get("x", param_key(p), make) == 2
+    p.data = torch.ones(4)                                  # load_state_dict / .to() style swap
+    assert cache.get("x", param_key(p), make) == 3
+
+
+def test_oracle_is_not_imported_by_the_product():
+    """The package must never reach into oracle/ (test infrastructure only)."""
+    for path in (ROOT / "quantizedsae_b200").rglob("*.py"):
+        text = path.read_text()
+        assert "oracle" not in re.sub(r"#.*", "", text).replace("no oracle", ""), path
