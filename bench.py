@@ -188,6 +188,7 @@ def run_b200(args, rank, world, local_rank):
 
     We, be, logits, bd = make_weights(torch, device)
     w_bf16 = L.cast_bf16(We)
+    sample = L.prepare_sample(w_bf16, be)
     packed, _, gap = L.pack_bitplanes(logits, D, N_BITS)
     assert gap == 0.0
     del logits
@@ -196,7 +197,7 @@ def run_b200(args, rank, world, local_rank):
 
     def step(i):
         x = xs[i % len(xs)]
-        vals, idx, _ = L.encode_topk(x, w_bf16, None, be, k)
+        vals, idx, _ = L.encode_topk(x, w_bf16, None, be, k, sample=sample)
         recon = L.decode_int4(vals, idx, packed, H, D, qstep, bd)
         return vals, idx, recon
 

@@ -87,15 +87,28 @@ int qsae_transpose_f32(const float* src, int R, int C, float* dst, void* stream)
  *
  * exact = 0: values are the tensor-core results. They equal the fp32 reference up to fp32
  *            accumulation order when x and W are bf16-representable (benchmark precondition).
+ * With a sampled dictionary (qsae_prepare_encoder_sample) the call first scores only the
+ * sampled rows and uses each row's m-th largest sample value as a prior threshold for the full
+ * sweep (m chosen so that it is too high with probability < 1e-7 per row); the merge verifies
+ * the threshold by counting survivors and a rescue kernel recomputes a failing row exactly, so
+ * the result is the exact top-k either way -- the prior only removes survivor traffic.
  * exact = 1: the bf16 pass selects k+QSAE_RESCORE_MARGIN candidates per row, which are
- *            re-scored in fp32 from x_f32 / w_f32 and re-selected; flags[b] != 0 marks a row
+ *            re-scored in fp32 from x_f32 / w_f32 and re-selected; flags[b] == 1 marks a row
  *            whose selection could not be certified against bf16 rounding.
  * Limits: D % 8 == 0, 8 <= D <= 512, 1 <= k <= QSAE_MAX_K, k <= H.
  * ------------------------------------------------------------------------------------- */
 #define QSAE_MAX_K 224
 #define QSAE_RESCORE_MARGIN 16
 
-int qsae_encode_topk_workspace_bytes(int B, int H, int D, int k, size_t* bytes);
+/* n_sample: rows of the sampled dictionary that will be passed to qsae_encode_topk (0 = none) */
+int qsae_encode_topk_workspace_bytes(int B, int H, int D, int k, int n_sample, size_t* bytes);
+
+/* Gather a stratified pseudo-random sample of n_sample dictionary rows (and their biases) for
+ * the prior-threshold pre-pass of qsae_encode_topk. One-time, per weight version.
+ * Recommended: n_sample = H / 32 rounded up to a multiple of 256, for H >= 8192. */
+int qsae_prepare_encoder_sample(const uint16_t* w_bf16, const float* b_enc, int H, int D, int n_sample,
+                                uint16_t* w_sample /* [n_sample, D] */, float* b_sample /* [n_sample] */,
+                                void* stream);
 
 /* Measurement hook: when both are non-NULL (cudaEvent_t), the calling thread's next
  * qsae_encode_topk calls record them on their stream immediately before / after the fused
@@ -106,6 +119,9 @@ int qsae_encode_topk(const float* x_f32,      /* [B, D] device                  
                      const uint16_t* w_bf16,   /* [H, D] from qsae_cast_f32_to_bf16          */
                      const float* w_f32,       /* [H, D] original weights; may be NULL if !exact */
                      const float* b_enc,       /* [H]                                        */
+                     const uint16_t* w_sample, /* [n_sample, D] or NULL: sampled rows of w_bf16 */
+                     const float* b_sample,    /* [n_sample] or NULL                          */
+                     int n_sample,             /* 0 = no prior-threshold pre-pass             */
                      int B, int H, int D, int k, int act, int exact,
                      float* out_vals,          /* [B, k]                                     */
                      int32_t* out_idx,         /* [B, k]                                     */

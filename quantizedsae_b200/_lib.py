@@ -28,9 +28,10 @@ SYMBOLS = {
     "qsae_pack_bitplanes": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "qsae_dequant_soft": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "qsae_transpose_f32": (_i, [_vp, _i, _i, _vp, _vp]),
-    "qsae_encode_topk_workspace_bytes": (_i, [_i, _i, _i, _i, C.POINTER(_sz)]),
+    "qsae_encode_topk_workspace_bytes": (_i, [_i, _i, _i, _i, _i, C.POINTER(_sz)]),
+    "qsae_prepare_encoder_sample": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "qsae_set_encode_kernel_events": (_i, [_vp, _vp]),
-    "qsae_encode_topk": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "qsae_encode_topk": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "qsae_encode_dense_tc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "qsae_encode_dense_f32": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "qsae_topk_dense_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
@@ -152,10 +153,31 @@ def transpose(src: torch.Tensor) -> torch.Tensor:
     return dst
 
 
-def encode_topk_workspace_bytes(B: int, H: int, D: int, k: int) -> int:
+def encode_topk_workspace_bytes(B: int, H: int, D: int, k: int, n_sample: int = 0) -> int:
     n = _sz(0)
-    check(load().qsae_encode_topk_workspace_bytes(B, H, D, k, C.byref(n)))
+    check(load().qsae_encode_topk_workspace_bytes(B, H, D, k, n_sample, C.byref(n)))
     return int(n.value)
+
+
+def default_sample_rows(H: int) -> int:
+    """Rows of the sampled dictionary used for the prior threshold (0 = do not sample)."""
+    return ((H // 32 + 255) // 256) * 256 if H >= 8192 else 0
+
+
+def prepare_sample(w_bf16: torch.Tensor, b_enc: torch.Tensor, n_sample: int | None = None):
+    """-> (w_sample [n,D] bf16, b_sample [n] f32) or None when the dictionary is too small."""
+    global launch_count
+    _need_cuda(w_bf16, b_enc)
+    H, D = w_bf16.shape
+    n = default_sample_rows(H) if n_sample is None else n_sample
+    if n <= 0:
+        return None
+    ws = torch.empty((n, D), dtype=torch.bfloat16, device=w_bf16.device)
+    bs = torch.empty((n,), dtype=torch.float32, device=w_bf16.device)
+    check(load().qsae_prepare_encoder_sample(w_bf16.data_ptr(), b_enc.data_ptr(), H, D, n, ws.data_ptr(),
+                                             bs.data_ptr(), _stream()))
+    launch_count += 1
+    return ws, bs
 
 
 _ws_cache: dict = {}
@@ -171,7 +193,7 @@ def _workspace(device, nbytes: int) -> torch.Tensor:
 
 
 def encode_topk(x: torch.Tensor, w_bf16: torch.Tensor, w_f32: torch.Tensor | None, b_enc: torch.Tensor,
-                k: int, act: int = ACT_NONE, exact: bool = False, want_flags: bool = False):
+                k: int, act: int = ACT_NONE, exact: bool = False, want_flags: bool = False, sample=None):
     """-> (vals [B,k] f32, idx [B,k] i32, flags [B] i32 | None)"""
     global launch_count
     _need_cuda(x, w_bf16, w_f32, b_enc)
@@ -183,12 +205,14 @@ def encode_topk(x: torch.Tensor, w_bf16: torch.Tensor, w_f32: torch.Tensor | Non
     flags = torch.empty((B,), dtype=torch.int32, device=x.device) if want_flags else None
     if B == 0:
         return vals, idx, flags
-    nbytes = encode_topk_workspace_bytes(B, H, D, k)
+    w_s, b_s = sample if sample is not None else (None, None)
+    n_s = 0 if w_s is None else w_s.shape[0]
+    nbytes = encode_topk_workspace_bytes(B, H, D, k, n_s)
     ws = _workspace(x.device, nbytes)
-    check(load().qsae_encode_topk(x.data_ptr(), w_bf16.data_ptr(), _ptr(w_f32), b_enc.data_ptr(), B, H, D, k,
-                                  act, 1 if exact else 0, vals.data_ptr(), idx.data_ptr(), _ptr(flags),
-                                  ws.data_ptr(), ws.numel(), _stream()))
-    launch_count += 3
+    check(load().qsae_encode_topk(x.data_ptr(), w_bf16.data_ptr(), _ptr(w_f32), b_enc.data_ptr(), _ptr(w_s),
+                                  _ptr(b_s), n_s, B, H, D, k, act, 1 if exact else 0, vals.data_ptr(),
+                                  idx.data_ptr(), _ptr(flags), ws.data_ptr(), ws.numel(), _stream()))
+    launch_count += 3 if n_s == 0 else 7
     return vals, idx, flags
 
 

@@ -143,6 +143,9 @@ __device__ __forceinline__ float pick32(const float (&v)[32], int j) {
 // MODE 0: no class bound (any k <= kMaxK; bisection only)      MODE 1: top-1 per class, k <= 32
 // MODE 2: top-2 per class, k <= 64       MODE 3: top-2 per class shared with the partner thread
 //                                                 handling the other column half, k <= 128
+// MODE 4: fixed prior threshold per row (p.prior), no class bookkeeping
+// MODE 5: no survivor buffers at all: every thread keeps the kTopM largest values of its
+//         sub-stream sorted in registers and writes them to p.top_out (sample pre-pass, m <= 16)
 template <int MODE>
 __device__ __forceinline__ void epilogue_loop(const EncodeLaunch& p, int n_my_tiles, int tile_begin,
                                               int split, int m0, int e, int lane, uint32_t tmem_base,
@@ -169,13 +172,25 @@ __device__ __forceinline__ void epilogue_loop(const EncodeLaunch& p, int n_my_ti
   // -inf used to mask out-of-range columns never survives)
   float thr = live ? -3.402823466e+38f : INFINITY;
   float valid_bound = -INFINITY;  // inclusive lower bound of the k-th largest, reported to the merge
-  float top1[MODE >= 1 ? 32 : 1];
-  float top2[MODE >= 2 ? 32 : 1];
+  float tm[MODE == 5 ? kTopM : 1];
+#pragma unroll
+  for (int i = 0; i < (MODE == 5 ? kTopM : 1); ++i) tm[i] = -INFINITY;
+  if (MODE == 4 && live) {
+    // prior threshold: the m-th largest pre-activation of a sample of this row's latents
+    // (itself one of the row's values). Tight, but only probably <= the k-th largest: the merge
+    // kernel verifies it by counting survivors and sends the rare failing row to the rescue path.
+    thr = fmaxf(thr, __ldg(p.prior + static_cast<size_t>(row) * p.prior_stride));
+    valid_bound = thr;
+  }
+  constexpr bool kClasses = (MODE >= 1 && MODE <= 3);
+  constexpr bool kTop2 = (MODE == 2 || MODE == 3);
+  float top1[kClasses ? 32 : 1];
+  float top2[kTop2 ? 32 : 1];
   const float init = live ? -INFINITY : INFINITY;
 #pragma unroll
-  for (int j = 0; j < (MODE >= 1 ? 32 : 1); ++j) top1[j] = init;
+  for (int j = 0; j < (kClasses ? 32 : 1); ++j) top1[j] = init;
 #pragma unroll
-  for (int j = 0; j < (MODE >= 2 ? 32 : 1); ++j) top2[j] = init;
+  for (int j = 0; j < (kTop2 ? 32 : 1); ++j) top2[j] = init;
 
   for (int t = 0; t < n_my_tiles; ++t) {
     const int acc = t & 1;
@@ -215,7 +230,7 @@ __device__ __forceinline__ void epilogue_loop(const EncodeLaunch& p, int n_my_ti
         for (int j = 0; j < 32; ++j)
           if (col0 + j < p.H) p.debug_z[static_cast<size_t>(row) * p.H + col0 + j] = v[j];
       }
-      if constexpr (MODE >= 1) {
+      if constexpr (kClasses) {
         // class maxima and the bound they imply
         float bound;
         if constexpr (MODE == 1) {
@@ -246,23 +261,55 @@ __device__ __forceinline__ void epilogue_loop(const EncodeLaunch& p, int n_my_ti
       // one entry. Scattered stores cost one LSU transaction per lane, so the number of store
       // instructions per chunk (= max hits of any lane) is what matters, not the ALU work.
       uint32_t hits = 0u;
+      if constexpr (MODE == 5) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) hits |= (v[j] >= thr) ? (1u << j) : 0u;
-      while (__any_sync(full, hits != 0u)) {
-        if (hits != 0u) {
-          const int j = __ffs(hits) - 1;
-          hits &= hits - 1u;
-          buf[cnt] = make_uint2(__float_as_uint(pick32(v, j)), static_cast<uint32_t>(col0 + j));
-          ++cnt;
+        for (int j = 0; j < 32; ++j) hits |= (v[j] > thr) ? (1u << j) : 0u;
+        while (__any_sync(full, hits != 0u)) {
+          if (hits != 0u) {
+            const int j = __ffs(hits) - 1;
+            hits &= hits - 1u;
+            float carry = pick32(v, j);
+#pragma unroll
+            for (int i = 0; i < kTopM; ++i) {  // sorted insertion, descending
+              const float hi = fmaxf(tm[i], carry);
+              carry = fminf(tm[i], carry);
+              tm[i] = hi;
+            }
+          }
         }
+        if (live) {  // new threshold: the current m-th largest (p.k_sel = m, warp-uniform)
+          float t = tm[0];
+#pragma unroll
+          for (int i = 1; i < kTopM; ++i)
+            if (i < k) t = tm[i];
+          thr = fmaxf(thr, t);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) hits |= (v[j] >= thr) ? (1u << j) : 0u;
+        while (__any_sync(full, hits != 0u)) {
+          if (hits != 0u) {
+            const int j = __ffs(hits) - 1;
+            hits &= hits - 1u;
+            buf[cnt] = make_uint2(__float_as_uint(pick32(v, j)), static_cast<uint32_t>(col0 + j));
+            ++cnt;
+          }
+        }
+        if (__any_sync(full, cnt > cap - 32)) relieve_warp_buffers(buf, cnt, thr, valid_bound, k, cap, lane);
       }
-      if (__any_sync(full, cnt > cap - 32)) relieve_warp_buffers(buf, cnt, thr, valid_bound, k, cap, lane);
     }
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
   }
-  if (row_ok) {
+  if constexpr (MODE == 5) {
+    if (row_ok) {
+      float4* dst = reinterpret_cast<float4*>(p.top_out + slot * kTopM);
+#pragma unroll
+      for (int i = 0; i < kTopM / 4; ++i)
+        dst[i] = make_float4(tm[4 * i], tm[4 * i + 1], tm[4 * i + 2], tm[4 * i + 3]);
+    }
+  } else if (row_ok) {
     p.cand_cnt[slot] = cnt;
     p.cand_thr[slot] = live ? valid_bound : -INFINITY;
   }
@@ -403,6 +450,14 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
         break;
       case 3:
         epilogue_loop<3>(p, n_my_tiles, tile_begin, split, m0, e, lane, tmem_base, bias_smem, share,
+                         tmem_full, tmem_empty, bias_full);
+        break;
+      case 4:
+        epilogue_loop<4>(p, n_my_tiles, tile_begin, split, m0, e, lane, tmem_base, bias_smem, share,
+                         tmem_full, tmem_empty, bias_full);
+        break;
+      case 5:
+        epilogue_loop<5>(p, n_my_tiles, tile_begin, split, m0, e, lane, tmem_base, bias_smem, share,
                          tmem_full, tmem_empty, bias_full);
         break;
       default:

@@ -12,6 +12,7 @@ constexpr int kCandCapMax = 1024;  // largest per-(row, sub-stream) survivor buf
 constexpr int kDenseCap = 256;     // survivor buffer of the dense top-k kernel
 constexpr int kMaxSplits = 8;      // max CTAs sharing one row block along the latent axis
 constexpr int kMaxK = 224;         // == QSAE_MAX_K
+constexpr int kTopM = 16;          // register-resident top list of the sample pre-pass (mode 5)
 
 struct EncodeLaunch {
   int B, H, D;
@@ -20,9 +21,12 @@ struct EncodeLaunch {
   int tiles_per_split;  // in units of kEncBN latents
   int n_tiles;          // ceil(H / kEncBN)
   int act;              // 0 none, 1 relu
-  int mode;             // epilogue bound: 0 bisection only, 1/2/3 class maxima (see .cu)
+  int mode;             // epilogue bound: 0 bisection only, 1/2/3 class maxima, 4 prior (see .cu)
   int cap;              // entries per survivor buffer
   const float* bias;    // [H]
+  const float* prior;   // mode 4: per-row threshold at prior[row * prior_stride]
+  int prior_stride;
+  float* top_out;       // mode 5: [B][n_splits*2][kTopM] sorted largest values of each sub-stream
   void* cand;           // [B][n_splits*2][cap] {float bits, int32 column}
   int* cand_cnt;        // [B][n_splits*2]
   float* cand_thr;      // [B][n_splits*2] inclusive lower bound of the row's k_sel-th largest value
@@ -48,8 +52,38 @@ struct SelectLaunch {
   float* out_vals;        // [B, k_out]
   int32_t* out_idx;       // [B, k_out]
   int32_t* out_flags;     // [B] or null
+  int* rescue_count;      // prior mode: rows whose prior threshold failed the count check ...
+  int32_t* rescue_rows;   // ... are appended here (capacity B) and their output left to the rescue kernel
 };
+
+// rescue.cu: exact per-row top-k for the rows listed by the merge kernel (persistent small grid,
+// returns immediately when the list is empty)
+struct RescueLaunch {
+  int B, H, D, k_sel, k_out, act, exact;
+  const uint16_t* x_bf16;  // [B, D]
+  const uint16_t* w_bf16;  // [H, D]
+  const float* x_f32;      // exact only
+  const float* w_f32;      // exact only
+  const float* bias;       // [H]
+  const int* rescue_count;
+  const int32_t* rescue_rows;
+  float* out_vals;
+  int32_t* out_idx;
+  int32_t* out_flags;      // may be null
+};
+const char* rescue_rows_launch(const RescueLaunch& p, int num_sms, cudaStream_t stream);
+
+// pack.cu: gather a stratified pseudo-random sample of dictionary rows (prior-threshold pre-pass)
+const char* sample_rows_launch(const uint16_t* w_bf16, const float* bias, int H, int D, int n_sample,
+                               uint16_t* w_sample, float* b_sample, cudaStream_t stream);
 const char* select_topk_launch(const SelectLaunch& p, cudaStream_t stream);
+// warp-per-row merge for small survivor counts (prior mode); rows with more than its staging
+// capacity go to ovf_rows/ovf_count and are finished by select_topk_list_launch
+const char* select_small_launch(const SelectLaunch& p, int* ovf_count, int32_t* ovf_rows, cudaStream_t stream);
+const char* select_topk_list_launch(const SelectLaunch& p, const int* count, const int32_t* rows, int num_sms,
+                                    cudaStream_t stream);
+// prior[row] = m-th largest of the row's nsub * kTopM pre-pass values
+const char* prior_from_top_launch(const float* top, int B, int nsub, int m, float* prior, cudaStream_t stream);
 // survivors from a dense [R, H] matrix (one sub-stream per row, buffers of kDenseCap entries)
 const char* dense_candidates_launch(const float* z, int R, int H, int k, void* cand, int* cand_cnt,
                                     cudaStream_t stream);

@@ -127,6 +127,27 @@ __global__ void transpose_kernel(const float* __restrict__ src, int R, int C, fl
   }
 }
 
+// Stratified pseudo-random sample of dictionary rows: sample i is drawn from the i-th of n_sample
+// equal slices of [0, H) at a hashed offset, so the sample is spread over the whole dictionary
+// without following any period the latent ordering may have.
+__host__ __device__ inline int sample_row_index(int i, int H, int n_sample) {
+  const long long lo = static_cast<long long>(i) * H / n_sample;
+  const long long hi = static_cast<long long>(i + 1) * H / n_sample;
+  uint32_t h = static_cast<uint32_t>(i) * 2654435761u;
+  h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+  const long long span = hi - lo > 0 ? hi - lo : 1;
+  return static_cast<int>(lo + static_cast<long long>(h % static_cast<uint32_t>(span)));
+}
+
+__global__ void sample_rows_kernel(const uint16_t* __restrict__ w, const float* __restrict__ bias, int H,
+                                   int D, int n_sample, uint16_t* __restrict__ ws, float* __restrict__ bs) {
+  const int i = blockIdx.x;
+  const int src = sample_row_index(i, H, n_sample);
+  for (int d = threadIdx.x; d < D; d += blockDim.x)
+    ws[static_cast<size_t>(i) * D + d] = w[static_cast<size_t>(src) * D + d];
+  if (threadIdx.x == 0) bs[i] = bias[src];
+}
+
 int grid_for(size_t n, int block, int cap = 148 * 16) {
   size_t g = (n + block - 1) / block;
   if (g > static_cast<size_t>(cap)) g = cap;
@@ -156,6 +177,12 @@ const char* dequant_soft_launch(const float* logits, int H, int D, int n_bits, f
                                 cudaStream_t stream) {
   const size_t total = static_cast<size_t>(H) * D;
   dequant_soft_kernel<<<grid_for(total, 256), 256, 0, stream>>>(logits, total, n_bits, rows);
+  return cuda_err(cudaGetLastError());
+}
+
+const char* sample_rows_launch(const uint16_t* w_bf16, const float* bias, int H, int D, int n_sample,
+                               uint16_t* w_sample, float* b_sample, cudaStream_t stream) {
+  sample_rows_kernel<<<n_sample, 128, 0, stream>>>(w_bf16, bias, H, D, n_sample, w_sample, b_sample);
   return cuda_err(cudaGetLastError());
 }
 

@@ -1,6 +1,7 @@
 // C ABI (include/qsae_b200.h): argument validation, workspace carving, launch sequencing and
 // the host-buffer pipeline. No torch types, no exceptions across the boundary.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -46,12 +47,73 @@ int num_sms() {
   return cached[dev];
 }
 
-struct EncodePlan {
-  int n_splits, nsub, n_tiles, tiles_per_split, k_sel, mode, cap;
-  size_t x_off, cand_off, cnt_off, thr_off, total;
+// One fused-kernel + merge stage over a dictionary of H rows.
+struct StagePlan {
+  int H, k_sel, n_splits, nsub, n_tiles, tiles_per_split, mode, cap;
+  size_t cand_off, cnt_off, thr_off, end;
 };
 
-int plan_encode(int B, int H, int D, int k, int exact, EncodePlan* pl) {
+enum StageKind { kStageClassBound = 0, kStagePriorMain = 1, kStageSamplePre = 2 };
+
+void plan_stage(int B, int H, int k_sel, StageKind kind, bool allow_split_override, size_t base, StagePlan* sp) {
+  sp->H = H;
+  sp->k_sel = k_sel;
+  sp->n_tiles = (H + kEncBN - 1) / kEncBN;
+  sp->n_splits = encode_pick_splits(B, H, num_sms());
+  if (allow_split_override) {
+    if (const char* ov = getenv("QSAE_ENCODE_SPLITS")) {  // tuning experiments only
+      const int s = atoi(ov);
+      if (s >= 1 && s <= kMaxSplits && s <= sp->n_tiles) sp->n_splits = s;
+    }
+  }
+  if (kind == kStageSamplePre && (B + kEncBM - 1) / kEncBM >= num_sms()) sp->n_splits = 1;  // enough row blocks
+  sp->tiles_per_split = (sp->n_tiles + sp->n_splits - 1) / sp->n_splits;
+  sp->nsub = sp->n_splits * 2;
+  if (kind == kStageSamplePre) {
+    sp->mode = 5;   // register-resident top list, no survivor buffers: cand region = the lists
+    sp->cap = 0;
+    sp->cand_off = align_up(base, 256);
+    sp->cnt_off = sp->thr_off = sp->cand_off;
+    sp->end = align_up(sp->cand_off + static_cast<size_t>(B) * sp->nsub * kTopM * 4, 256);
+    return;
+  }
+  if (kind == kStagePriorMain) {
+    sp->mode = 4;
+    sp->cap = 512;
+  } else {
+    encode_pick_mode(k_sel, &sp->mode, &sp->cap);
+    if (sp->tiles_per_split * (kEncBN / 2) <= 448) sp->cap = 512;  // a sub-stream this short cannot fill more
+  }
+  sp->cand_off = align_up(base, 256);
+  sp->cnt_off = sp->cand_off + static_cast<size_t>(B) * sp->nsub * sp->cap * 8;
+  sp->thr_off = sp->cnt_off + static_cast<size_t>(B) * sp->nsub * 4;
+  sp->end = align_up(sp->thr_off + static_cast<size_t>(B) * sp->nsub * 4, 256);
+}
+
+// Prior threshold = m-th largest pre-activation over a sample of n_sample of the H latents.
+// It is too high for a row exactly when >= m sampled latents fall inside the row's top
+// (k_sel - 1); that count is ~Binomial(k_sel - 1, n_sample / H). Pick the smallest m whose tail
+// probability is below 1e-7 per row (such rows are detected by count and rescued exactly).
+int choose_prior_rank(int k_sel, double r) {
+  const int n = k_sel - 1;
+  if (n <= 0) return 1;
+  double pmf = pow(1.0 - r, n), cdf = pmf;
+  for (int j = 1; j <= n; ++j) {
+    if (1.0 - cdf < 1e-7) return j;
+    pmf *= static_cast<double>(n - j + 1) / j * r / (1.0 - r);
+    cdf += pmf;
+  }
+  return n + 1;
+}
+
+struct EncodePlan {
+  int k_sel, m;
+  bool use_prior;
+  StagePlan main, pre;
+  size_t x_off, prior_off, counters_off, rescue_rows_off, ovf_rows_off, total;
+};
+
+int plan_encode(int B, int H, int D, int k, int exact, int n_sample, EncodePlan* pl) {
   if (B <= 0 || H <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "B and H must be positive (B=%d H=%d)", B, H);
   if (D < 8 || D > 512 || (D % 8) != 0)
     return fail(QSAE_ERR_INVALID_ARGUMENT, "D must be a multiple of 8 in [8, 512], got %d", D);
@@ -65,21 +127,41 @@ int plan_encode(int B, int H, int D, int k, int exact, EncodePlan* pl) {
     if (k_sel > H) k_sel = H;
   }
   pl->k_sel = k_sel;
-  pl->n_tiles = (H + kEncBN - 1) / kEncBN;
-  pl->n_splits = encode_pick_splits(B, H, num_sms());
-  if (const char* ov = getenv("QSAE_ENCODE_SPLITS")) {  // tuning experiments only
-    const int s = atoi(ov);
-    if (s >= 1 && s <= kMaxSplits && s <= pl->n_tiles) pl->n_splits = s;
+  pl->use_prior = false;
+  pl->m = 0;
+  if (n_sample >= 256 && H >= 8 * static_cast<long long>(n_sample)) {
+    const char* ov = getenv("QSAE_ENCODE_PRIOR");  // "0" switches the prior off (tuning experiments)
+    const int m = choose_prior_rank(k_sel, static_cast<double>(n_sample) / H);
+    if (!(ov && atoi(ov) == 0) && m <= kTopM && m <= n_sample) {
+      pl->use_prior = true;
+      pl->m = m;
+    }
   }
-  pl->tiles_per_split = (pl->n_tiles + pl->n_splits - 1) / pl->n_splits;
-  pl->nsub = pl->n_splits * 2;
   pl->x_off = 0;
-  pl->cand_off = align_up(static_cast<size_t>(B) * D * 2, 1024);
-  encode_pick_mode(k_sel, &pl->mode, &pl->cap);
-  pl->cnt_off = pl->cand_off + static_cast<size_t>(B) * pl->nsub * pl->cap * 8;
-  pl->thr_off = pl->cnt_off + static_cast<size_t>(B) * pl->nsub * 4;
-  pl->total = align_up(pl->thr_off + static_cast<size_t>(B) * pl->nsub * 4, 256);
+  size_t off = align_up(static_cast<size_t>(B) * D * 2, 1024);
+  plan_stage(B, H, k_sel, pl->use_prior ? kStagePriorMain : kStageClassBound, true, off, &pl->main);
+  off = pl->main.end;
+  if (pl->use_prior) {
+    pl->prior_off = off; off = align_up(off + static_cast<size_t>(B) * 4, 256);
+    pl->counters_off = off; off += 256;
+    pl->rescue_rows_off = off; off = align_up(off + static_cast<size_t>(B) * 4, 256);
+    pl->ovf_rows_off = off; off = align_up(off + static_cast<size_t>(B) * 4, 256);
+    plan_stage(B, n_sample, pl->m, kStageSamplePre, false, off, &pl->pre);
+    off = pl->pre.end;
+  }
+  pl->total = off;
   return QSAE_OK;
+}
+
+void fill_encode_launch(EncodeLaunch* el, const StagePlan& sp, int B, int D, int act, const float* bias,
+                        uint8_t* ws) {
+  memset(el, 0, sizeof(*el));
+  el->B = B; el->H = sp.H; el->D = D; el->k_sel = sp.k_sel;
+  el->n_splits = sp.n_splits; el->tiles_per_split = sp.tiles_per_split; el->n_tiles = sp.n_tiles;
+  el->act = act; el->mode = sp.mode; el->cap = sp.cap; el->bias = bias;
+  el->cand = ws + sp.cand_off;
+  el->cand_cnt = reinterpret_cast<int*>(ws + sp.cnt_off);
+  el->cand_thr = reinterpret_cast<float*>(ws + sp.thr_off);
 }
 
 }  // namespace
@@ -134,17 +216,30 @@ int qsae_transpose_f32(const float* src, int R, int C, float* dst, void* stream)
   return launch_status("transpose", transpose_launch(src, R, C, dst, S(stream)));
 }
 
-int qsae_encode_topk_workspace_bytes(int B, int H, int D, int k, size_t* bytes) {
+int qsae_encode_topk_workspace_bytes(int B, int H, int D, int k, int n_sample, size_t* bytes) {
   if (!bytes) return fail(QSAE_ERR_INVALID_ARGUMENT, "workspace query: null pointer");
-  EncodePlan pl;
-  // size for the exact variant (k + margin survivors): it is the larger of the two
-  int rc = plan_encode(B, H, D, k, 1, &pl);
-  if (rc != QSAE_OK) return rc;
-  *bytes = pl.total;
+  size_t need = 0;
+  for (int exact = 0; exact < 2; ++exact) {
+    for (int pass = 0; pass < 2; ++pass) {  // with and without the sampled prior
+      EncodePlan pl;
+      int rc = plan_encode(B, H, D, k, exact, pass ? n_sample : 0, &pl);
+      if (rc != QSAE_OK) return rc;
+      if (pl.total > need) need = pl.total;
+    }
+  }
+  *bytes = need;
   return QSAE_OK;
 }
 
+int qsae_prepare_encoder_sample(const uint16_t* w_bf16, const float* b_enc, int H, int D, int n_sample,
+                                uint16_t* w_sample, float* b_sample, void* stream) {
+  if (!w_bf16 || !b_enc || !w_sample || !b_sample) return fail(QSAE_ERR_INVALID_ARGUMENT, "prepare_encoder_sample: null pointer");
+  if (n_sample < 1 || n_sample > H || D < 1) return fail(QSAE_ERR_INVALID_ARGUMENT, "prepare_encoder_sample: need 1 <= n_sample <= H");
+  return launch_status("sample_rows", sample_rows_launch(w_bf16, b_enc, H, D, n_sample, w_sample, b_sample, S(stream)));
+}
+
 int qsae_encode_topk(const float* x_f32, const uint16_t* w_bf16, const float* w_f32, const float* b_enc,
+                     const uint16_t* w_sample, const float* b_sample, int n_sample,
                      int B, int H, int D, int k, int act, int exact, float* out_vals, int32_t* out_idx,
                      int32_t* out_flags, void* workspace, size_t workspace_bytes, void* stream) {
   if (B == 0) return QSAE_OK;
@@ -153,8 +248,9 @@ int qsae_encode_topk(const float* x_f32, const uint16_t* w_bf16, const float* w_
   if (exact && !w_f32) return fail(QSAE_ERR_INVALID_ARGUMENT, "encode_topk: exact mode needs w_f32");
   if (act != QSAE_ACT_NONE && act != QSAE_ACT_RELU)
     return fail(QSAE_ERR_INVALID_ARGUMENT, "encode_topk: unknown activation %d", act);
+  if (!w_sample || !b_sample) n_sample = 0;
   EncodePlan pl;
-  int rc = plan_encode(B, H, D, k, exact, &pl);
+  int rc = plan_encode(B, H, D, k, exact, n_sample, &pl);
   if (rc != QSAE_OK) return rc;
   if (workspace_bytes < pl.total)
     return fail(QSAE_ERR_WORKSPACE_TOO_SMALL, "encode_topk: workspace %zu < %zu bytes", workspace_bytes, pl.total);
@@ -163,31 +259,76 @@ int qsae_encode_topk(const float* x_f32, const uint16_t* w_bf16, const float* w_
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   uint16_t* x_bf16 = reinterpret_cast<uint16_t*>(ws + pl.x_off);
   cudaStream_t st = S(stream);
+  int debug_mode = 0;
+  if (const char* dm = getenv("QSAE_ENCODE_DEBUG_MODE")) debug_mode = atoi(dm);
 
   rc = launch_status("cast x", cast_bf16_launch(x_f32, x_bf16, static_cast<size_t>(B) * D, st));
   if (rc != QSAE_OK) return rc;
 
+  if (!pl.use_prior) {
+    // ---- class-bound path: one sweep, block-per-row merge
+    EncodeLaunch el;
+    fill_encode_launch(&el, pl.main, B, D, act, b_enc, ws);
+    el.debug_mode = debug_mode;
+    if (g_enc_ev_start) cudaEventRecord(g_enc_ev_start, st);
+    rc = launch_status("encode_topk kernel", encode_topk_launch(x_bf16, w_bf16, el, st));
+    if (g_enc_ev_stop) cudaEventRecord(g_enc_ev_stop, st);
+    if (rc != QSAE_OK) return rc;
+    SelectLaunch sl;
+    memset(&sl, 0, sizeof(sl));
+    sl.B = B; sl.H = H; sl.D = D; sl.k_sel = pl.k_sel; sl.k_out = k; sl.nsub = pl.main.nsub; sl.cap = pl.main.cap;
+    sl.act = act; sl.exact = exact;
+    sl.cand = el.cand; sl.cand_cnt = el.cand_cnt; sl.cand_thr = el.cand_thr;
+    sl.x_f32 = x_f32; sl.w_f32 = w_f32; sl.bias = b_enc;
+    sl.out_vals = out_vals; sl.out_idx = out_idx; sl.out_flags = out_flags;
+    return launch_status("select_topk kernel", select_topk_launch(sl, st));
+  }
+
+  // ---- prior-threshold path
+  float* prior = reinterpret_cast<float*>(ws + pl.prior_off);
+  int* counters = reinterpret_cast<int*>(ws + pl.counters_off);   // [0] rescue rows, [1] merge overflow rows
+  int32_t* rescue_rows = reinterpret_cast<int32_t*>(ws + pl.rescue_rows_off);
+  int32_t* ovf_rows = reinterpret_cast<int32_t*>(ws + pl.ovf_rows_off);
+  cudaError_t ce = cudaMemsetAsync(counters, 0, 2 * sizeof(int), st);
+  if (ce != cudaSuccess) return fail(QSAE_ERR_CUDA, "encode_topk: %s", cudaGetErrorString(ce));
+  // 1. pre-pass: the fused kernel over the sampled dictionary rows, top list kept in registers
+  EncodeLaunch pe;
+  fill_encode_launch(&pe, pl.pre, B, D, act, b_sample, ws);
+  pe.top_out = reinterpret_cast<float*>(ws + pl.pre.cand_off);
+  rc = launch_status("encode_topk kernel (sample pre-pass)", encode_topk_launch(x_bf16, w_sample, pe, st));
+  if (rc != QSAE_OK) return rc;
+  rc = launch_status("prior kernel", prior_from_top_launch(pe.top_out, B, pl.pre.nsub, pl.m, prior, st));
+  if (rc != QSAE_OK) return rc;
+  // 2. full sweep against the prior
   EncodeLaunch el;
-  el.B = B; el.H = H; el.D = D; el.k_sel = pl.k_sel;
-  el.n_splits = pl.n_splits; el.tiles_per_split = pl.tiles_per_split; el.n_tiles = pl.n_tiles;
-  el.act = act; el.bias = b_enc; el.debug_z = nullptr;
-  { const char* dm = getenv("QSAE_ENCODE_DEBUG_MODE"); el.debug_mode = dm ? atoi(dm) : 0; }
-  el.mode = pl.mode; el.cap = pl.cap;
-  el.cand = ws + pl.cand_off;
-  el.cand_cnt = reinterpret_cast<int*>(ws + pl.cnt_off);
-  el.cand_thr = reinterpret_cast<float*>(ws + pl.thr_off);
+  fill_encode_launch(&el, pl.main, B, D, act, b_enc, ws);
+  el.debug_mode = debug_mode;
+  el.prior = prior; el.prior_stride = 1;
   if (g_enc_ev_start) cudaEventRecord(g_enc_ev_start, st);
   rc = launch_status("encode_topk kernel", encode_topk_launch(x_bf16, w_bf16, el, st));
   if (g_enc_ev_stop) cudaEventRecord(g_enc_ev_stop, st);
   if (rc != QSAE_OK) return rc;
-
+  // 3. merge (warp per row; rows with too many survivors go through the block kernel)
   SelectLaunch sl;
-  sl.B = B; sl.H = H; sl.D = D; sl.k_sel = pl.k_sel; sl.k_out = k; sl.nsub = pl.nsub; sl.cap = pl.cap;
+  memset(&sl, 0, sizeof(sl));
+  sl.B = B; sl.H = H; sl.D = D; sl.k_sel = pl.k_sel; sl.k_out = k; sl.nsub = pl.main.nsub; sl.cap = pl.main.cap;
   sl.act = act; sl.exact = exact;
   sl.cand = el.cand; sl.cand_cnt = el.cand_cnt; sl.cand_thr = el.cand_thr;
   sl.x_f32 = x_f32; sl.w_f32 = w_f32; sl.bias = b_enc;
   sl.out_vals = out_vals; sl.out_idx = out_idx; sl.out_flags = out_flags;
-  return launch_status("select_topk kernel", select_topk_launch(sl, st));
+  sl.rescue_count = counters; sl.rescue_rows = rescue_rows;
+  rc = launch_status("select_small kernel", select_small_launch(sl, counters + 1, ovf_rows, st));
+  if (rc != QSAE_OK) return rc;
+  rc = launch_status("select_topk list kernel", select_topk_list_launch(sl, counters + 1, ovf_rows, num_sms(), st));
+  if (rc != QSAE_OK) return rc;
+  // 4. rows whose prior failed the count check: exact recomputation
+  RescueLaunch rl;
+  memset(&rl, 0, sizeof(rl));
+  rl.B = B; rl.H = H; rl.D = D; rl.k_sel = pl.k_sel; rl.k_out = k; rl.act = act; rl.exact = exact;
+  rl.x_bf16 = x_bf16; rl.w_bf16 = w_bf16; rl.x_f32 = x_f32; rl.w_f32 = w_f32; rl.bias = b_enc;
+  rl.rescue_count = counters; rl.rescue_rows = rescue_rows;
+  rl.out_vals = out_vals; rl.out_idx = out_idx; rl.out_flags = out_flags;
+  return launch_status("rescue kernel", rescue_rows_launch(rl, num_sms(), st));
 }
 
 int qsae_encode_dense_tc(const float* x_f32, const uint16_t* w_bf16, const float* b_enc, int B, int H, int D,
@@ -195,7 +336,7 @@ int qsae_encode_dense_tc(const float* x_f32, const uint16_t* w_bf16, const float
   if (B == 0) return QSAE_OK;
   if (!x_f32 || !w_bf16 || !b_enc || !z || !workspace) return fail(QSAE_ERR_INVALID_ARGUMENT, "encode_dense_tc: null pointer");
   EncodePlan pl;
-  int rc = plan_encode(B, H, D, 1, 0, &pl);
+  int rc = plan_encode(B, H, D, 1, 0, 0, &pl);
   if (rc != QSAE_OK) return rc;
   if (workspace_bytes < pl.total) return fail(QSAE_ERR_WORKSPACE_TOO_SMALL, "encode_dense_tc: workspace %zu < %zu", workspace_bytes, pl.total);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
@@ -203,13 +344,8 @@ int qsae_encode_dense_tc(const float* x_f32, const uint16_t* w_bf16, const float
   rc = launch_status("cast x", cast_bf16_launch(x_f32, x_bf16, static_cast<size_t>(B) * D, S(stream)));
   if (rc != QSAE_OK) return rc;
   EncodeLaunch el;
-  el.B = B; el.H = H; el.D = D; el.k_sel = 1;
-  el.n_splits = pl.n_splits; el.tiles_per_split = pl.tiles_per_split; el.n_tiles = pl.n_tiles;
-  el.act = act; el.bias = b_enc; el.debug_z = z; el.debug_mode = 0;
-  el.mode = pl.mode; el.cap = pl.cap;
-  el.cand = ws + pl.cand_off;
-  el.cand_cnt = reinterpret_cast<int*>(ws + pl.cnt_off);
-  el.cand_thr = reinterpret_cast<float*>(ws + pl.thr_off);
+  fill_encode_launch(&el, pl.main, B, D, act, b_enc, ws);
+  el.debug_z = z;
   return launch_status("encode_topk kernel (dense dump)", encode_topk_launch(x_bf16, w_bf16, el, S(stream)));
 }
 
@@ -295,6 +431,9 @@ struct qsae_bsae_plan {
   const float* dec_bias;
   uint16_t* w_bf16;
   uint8_t* packed;
+  uint16_t* w_sample;
+  float* b_sample;
+  int n_sample;
   static constexpr int kSlots = 3;
   struct Slot {
     cudaStream_t stream;
@@ -316,6 +455,8 @@ void qsae_bsae_plan_destroy(qsae_bsae_plan* p) {
   }
   cudaFree(p->w_bf16);
   cudaFree(p->packed);
+  cudaFree(p->w_sample);
+  cudaFree(p->b_sample);
   delete p;
 }
 
@@ -326,7 +467,8 @@ int qsae_bsae_plan_create(const float* w_enc, const float* b_enc, const float* l
   if (max_chunk_rows <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "plan_create: max_chunk_rows must be positive");
   if (n_bits < 1 || n_bits > 8) return fail(QSAE_ERR_INVALID_ARGUMENT, "plan_create: 1 <= n_bits <= 8");
   size_t ws_bytes = 0;
-  int rc = qsae_encode_topk_workspace_bytes(max_chunk_rows, H, D, k, &ws_bytes);
+  const int n_sample = (H >= 8192) ? ((H / 32 + 255) / 256) * 256 : 0;
+  int rc = qsae_encode_topk_workspace_bytes(max_chunk_rows, H, D, k, n_sample, &ws_bytes);
   if (rc != QSAE_OK) return rc;
   qsae_bsae_plan* p = new (std::nothrow) qsae_bsae_plan();
   if (!p) return fail(QSAE_ERR_CUDA, "plan_create: out of host memory");
@@ -335,8 +477,11 @@ int qsae_bsae_plan_create(const float* w_enc, const float* b_enc, const float* l
   p->qstep = gamma / static_cast<float>(1 << (n_bits - 1));
   p->w_f32 = w_enc; p->b_enc = b_enc; p->dec_bias = dec_bias;
   const size_t packed_bytes = n_bits <= 4 ? static_cast<size_t>(H) * D / 2 : static_cast<size_t>(H) * D;
+  p->n_sample = n_sample;
   cudaError_t e = cudaMalloc(&p->w_bf16, static_cast<size_t>(H) * D * 2);
   if (e == cudaSuccess) e = cudaMalloc(&p->packed, packed_bytes);
+  if (e == cudaSuccess && n_sample > 0) e = cudaMalloc(&p->w_sample, static_cast<size_t>(n_sample) * D * 2);
+  if (e == cudaSuccess && n_sample > 0) e = cudaMalloc(&p->b_sample, static_cast<size_t>(n_sample) * 4);
   for (int s = 0; s < qsae_bsae_plan::kSlots && e == cudaSuccess; ++s) {
     auto& sl = p->slot[s];
     sl.ws_bytes = ws_bytes;
@@ -354,6 +499,8 @@ int qsae_bsae_plan_create(const float* w_enc, const float* b_enc, const float* l
   cudaStream_t st = p->slot[0].stream;
   rc = qsae_cast_f32_to_bf16(w_enc, p->w_bf16, static_cast<size_t>(H) * D, st);
   if (rc == QSAE_OK) rc = qsae_pack_bitplanes(logits, H, D, n_bits, p->packed, nullptr, st);
+  if (rc == QSAE_OK && n_sample > 0)
+    rc = qsae_prepare_encoder_sample(p->w_bf16, b_enc, H, D, n_sample, p->w_sample, p->b_sample, st);
   if (rc == QSAE_OK && (e = cudaStreamSynchronize(st)) != cudaSuccess)
     rc = fail(QSAE_ERR_CUDA, "plan_create: %s", cudaGetErrorString(e));
   if (rc != QSAE_OK) { qsae_bsae_plan_destroy(p); return rc; }
@@ -374,8 +521,8 @@ int qsae_bsae_forward_host(qsae_bsae_plan* p, const float* x_host, int B, float*
     cudaError_t e = cudaMemcpyAsync(sl.x, x_host + static_cast<size_t>(r0) * p->D,
                                     static_cast<size_t>(rows) * p->D * 4, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) { rc = fail(QSAE_ERR_CUDA, "forward_host H2D: %s", cudaGetErrorString(e)); break; }
-    rc = qsae_encode_topk(sl.x, p->w_bf16, p->w_f32, p->b_enc, rows, p->H, p->D, p->k, QSAE_ACT_NONE, 0,
-                          sl.vals, sl.idx, nullptr, sl.ws, sl.ws_bytes, st);
+    rc = qsae_encode_topk(sl.x, p->w_bf16, p->w_f32, p->b_enc, p->w_sample, p->b_sample, p->n_sample, rows, p->H,
+                          p->D, p->k, QSAE_ACT_NONE, 0, sl.vals, sl.idx, nullptr, sl.ws, sl.ws_bytes, st);
     if (rc != QSAE_OK) break;
     if (p->n_bits <= 4)
       rc = qsae_decode_int4(sl.vals, sl.idx, rows, p->k, p->packed, p->H, p->D, p->qstep, p->dec_bias, sl.recon, st);

@@ -22,15 +22,13 @@ __device__ __forceinline__ void atomic_max_float_key(unsigned* addr, float v) { 
 // filtered by the row-level bound), warp 0 picks the k_sel largest composite keys, all warps
 // re-score them in fp32 when asked to, then the block sorts and emits.
 // shared memory: n_max gathered keys + ksort selected keys.
-__global__ void __launch_bounds__(kSelThreads)
-select_topk_kernel(SelectLaunch p, int n_max, int ksort) {
-  extern __shared__ __align__(16) uint8_t sel_smem[];
+__device__ __forceinline__ void select_row_block(const SelectLaunch& p, int row, int n_max, int ksort,
+                                                 uint8_t* sel_smem) {
   __shared__ int s_n, s_out;
   __shared__ unsigned s_worst_key, s_dev_key;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nwarps = kSelThreads / 32;
-  const int row = blockIdx.x;
   const unsigned full = 0xffffffffu;
   const unsigned lt_mask = (1u << lane) - 1u;
   uint64_t* keys = reinterpret_cast<uint64_t*>(sel_smem);
@@ -79,6 +77,16 @@ select_topk_kernel(SelectLaunch p, int n_max, int ksort) {
   __syncthreads();
   const int n = s_n;
   const int k_sel = min(p.k_sel, n);
+
+  // ---- prior mode: the threshold was only probably valid. Fewer than k_sel survivors means it
+  //      was too high for this row: hand the row to the exact rescue kernel.
+  if (p.rescue_count != nullptr && n < p.k_sel) {
+    if (threadIdx.x == 0) {
+      p.rescue_rows[atomicAdd(p.rescue_count, 1)] = row;
+      if (p.out_flags != nullptr) p.out_flags[row] = 2;
+    }
+    return;
+  }
 
   // ---- warp 0: the k_sel largest composite keys
   if (warp == 0) {
@@ -203,6 +211,238 @@ select_topk_kernel(SelectLaunch p, int n_max, int ksort) {
   }
 }
 
+__global__ void __launch_bounds__(kSelThreads)
+select_topk_kernel(SelectLaunch p, int n_max, int ksort) {
+  extern __shared__ __align__(16) uint8_t sel_smem[];
+  select_row_block(p, blockIdx.x, n_max, ksort, sel_smem);
+}
+
+// the same merge for an explicit (device-side) list of rows: persistent small grid
+__global__ void __launch_bounds__(kSelThreads)
+select_topk_list_kernel(SelectLaunch p, int n_max, int ksort, const int* count, const int32_t* rows) {
+  extern __shared__ __align__(16) uint8_t sel_smem[];
+  const int n = min(*count, p.B);
+  for (int li = blockIdx.x; li < n; li += gridDim.x) {
+    select_row_block(p, rows[li], n_max, ksort, sel_smem);
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp-per-row merge for the prior-threshold path, where a row has only a few hundred survivors:
+// gather into a per-warp staging area, keep the composite keys in registers, bisect there.
+// No block-level synchronisation at all. Rows that do not fit the staging area are listed for
+// the block-per-row kernel above.
+// ------------------------------------------------------------------------------------------
+constexpr int kSmallWarps = 4;
+constexpr int kSmallCap = 1024;             // staged survivors per row
+
+// the k_sel largest of the n staged composite keys -> sel[0, k_sel) (unordered); R keys per lane
+template <int R>
+__device__ __forceinline__ int small_select(uint64_t* stage, int n, int k_sel, int lane) {
+  const unsigned full = 0xffffffffu;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  uint64_t key[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) key[i] = (lane + 32 * i < n) ? stage[lane + 32 * i] : 0ull;
+  __syncwarp();
+  uint64_t T = 0ull;
+  if (n > k_sel) {
+#pragma unroll 1
+    for (int bit = 63; bit >= 0; --bit) {
+      const uint64_t probe = T | (1ull << bit);
+      int c = 0;
+#pragma unroll
+      for (int i = 0; i < R; ++i) c += (key[i] >= probe) ? 1 : 0;
+      c = __reduce_add_sync(full, c);
+      if (c >= k_sel) T = probe;
+      if (c == k_sel) break;
+    }
+  }
+  int out = 0;  // the staging area is free again: the keys live in registers
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const bool keep = (lane + 32 * i < n) && (key[i] >= T);
+    const unsigned b = __ballot_sync(full, keep);
+    if (keep) stage[out + __popc(b & lt_mask)] = key[i];
+    out += __popc(b);
+  }
+  return out;
+}
+
+__global__ void __launch_bounds__(kSmallWarps * 32)
+select_small_kernel(SelectLaunch p, int ksort, int* ovf_count, int32_t* ovf_rows) {
+  __shared__ uint64_t stage_all[kSmallWarps][kSmallCap];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kSmallWarps + warp;
+  if (row >= p.B) return;
+  const unsigned full = 0xffffffffu;
+  uint64_t* stage = stage_all[warp];
+
+  // ---- counts and offsets of the row's sub-streams (nsub <= 32)
+  const size_t slot0 = static_cast<size_t>(row) * p.nsub;
+  const int my_c = (lane < p.nsub) ? min(p.cand_cnt[slot0 + lane], p.cap) : 0;
+  int incl = my_c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(full, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int n = __shfl_sync(full, incl, 31);
+  if (n > kSmallCap) {
+    if (lane == 0) ovf_rows[atomicAdd(ovf_count, 1)] = row;
+    return;
+  }
+  if (p.rescue_count != nullptr && n < p.k_sel) {  // prior threshold too high for this row
+    if (lane == 0) {
+      p.rescue_rows[atomicAdd(p.rescue_count, 1)] = row;
+      if (p.out_flags != nullptr) p.out_flags[row] = 2;
+    }
+    return;
+  }
+  // ---- gather (every survivor already passed the row's threshold in the sweep)
+  const uint2* cand = reinterpret_cast<const uint2*>(p.cand);
+  for (int s = 0; s < p.nsub; ++s) {
+    const int c = __shfl_sync(full, my_c, s);
+    const int off = __shfl_sync(full, incl, s) - c;
+    const uint2* src = cand + (slot0 + s) * p.cap;
+#pragma unroll 4
+    for (int e = lane; e < c; e += 32) {
+      const uint2 t = src[e];
+      stage[off + e] = make_sort_key(__uint_as_float(t.x), t.y);
+    }
+  }
+  __syncwarp();
+
+  // ---- k_sel largest composite keys (unique): bisection in registers, depth chosen by n
+  const int k_sel = min(p.k_sel, n);
+  int out;
+  if (n <= 256) out = small_select<8>(stage, n, k_sel, lane);
+  else if (n <= 512) out = small_select<16>(stage, n, k_sel, lane);
+  else out = small_select<32>(stage, n, k_sel, lane);
+  uint64_t* sel = stage;
+  for (int e = out + lane; e < ksort; e += 32) sel[e] = 0ull;
+  __syncwarp();
+
+  // ---- optional exact fp32 re-scoring
+  float worst_bf16 = INFINITY, max_dev = 0.f;
+  if (p.exact) {
+    const int D = p.D;
+    float4 xr[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int d = c * 128 + lane * 4;
+      xr[c] = (d < D) ? *reinterpret_cast<const float4*>(p.x_f32 + static_cast<size_t>(row) * D + d)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll 1
+    for (int j = 0; j < out; j += 2) {
+      const bool has1 = (j + 1) < out;
+      const uint64_t key0 = sel[j];
+      const uint64_t key1 = has1 ? sel[j + 1] : key0;
+      const uint32_t col0 = sort_key_col(key0), col1 = sort_key_col(key1);
+      const float* w0 = p.w_f32 + static_cast<size_t>(col0) * D;
+      const float* w1 = p.w_f32 + static_cast<size_t>(col1) * D;
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int d = c * 128 + lane * 4;
+        if (d < D) {
+          const float4 u = __ldg(reinterpret_cast<const float4*>(w0 + d));
+          const float4 v = __ldg(reinterpret_cast<const float4*>(w1 + d));
+          a0 = fmaf(xr[c].x, u.x, a0); a0 = fmaf(xr[c].y, u.y, a0);
+          a0 = fmaf(xr[c].z, u.z, a0); a0 = fmaf(xr[c].w, u.w, a0);
+          a1 = fmaf(xr[c].x, v.x, a1); a1 = fmaf(xr[c].y, v.y, a1);
+          a1 = fmaf(xr[c].z, v.z, a1); a1 = fmaf(xr[c].w, v.w, a1);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(full, a0, o);
+        a1 += __shfl_xor_sync(full, a1, o);
+      }
+      float s0 = a0 + __ldg(p.bias + col0);
+      float s1 = a1 + __ldg(p.bias + col1);
+      if (p.act == 1) { s0 = fmaxf(s0, 0.f); s1 = fmaxf(s1, 0.f); }
+      const float old0 = sort_key_value(key0), old1 = sort_key_value(key1);
+      worst_bf16 = fminf(worst_bf16, fminf(old0, old1));
+      max_dev = fmaxf(max_dev, fmaxf(fabsf(s0 - old0), fabsf(s1 - old1)));
+      __syncwarp();
+      if (lane == 0) {
+        sel[j] = make_sort_key(s0, col0);
+        if (has1) sel[j + 1] = make_sort_key(s1, col1);
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- bitonic sort of sel[0, ksort) descending, one warp
+  for (int size = 2; size <= ksort; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = lane; t < (ksort >> 1); t += 32) {
+        const int pos = ((t / stride) * (stride << 1)) + (t % stride);
+        const int partner = pos + stride;
+        const bool desc = (pos & size) == 0;
+        const uint64_t a = sel[pos], b = sel[partner];
+        if ((a < b) == desc) {
+          sel[pos] = b;
+          sel[partner] = a;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  for (int j = lane; j < p.k_out; j += 32) {
+    const uint64_t kk = sel[j];
+    const bool valid = j < out;
+    p.out_vals[static_cast<size_t>(row) * p.k_out + j] = valid ? sort_key_value(kk) : 0.f;
+    p.out_idx[static_cast<size_t>(row) * p.k_out + j] = valid ? static_cast<int32_t>(sort_key_col(kk)) : -1;
+  }
+  if (p.out_flags != nullptr && lane == 0) {
+    int flag = 0;
+    if (p.exact && n > k_sel && p.k_out <= out) {
+      const float kth = sort_key_value(sel[p.k_out - 1]);
+      if (!(worst_bf16 + 4.f * max_dev < kth)) flag = 1;
+    }
+    p.out_flags[row] = flag;
+  }
+}
+
+// prior[row] = m-th largest of the row's n = nsub * kTopM pre-pass values (n <= 512, P = values
+// per lane). Each lane ranks its own values against everybody's by broadcast -- no dependent
+// chain: the m-th largest is the value with exactly m - 1 entries ahead of it in
+// (value desc, slot asc) order.
+template <int P>
+__global__ void __launch_bounds__(256)
+prior_from_top_kernel(const float* __restrict__ top, int B, int n, int m, float* __restrict__ prior) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= B) return;
+  const unsigned full = 0xffffffffu;
+  const float* src = top + static_cast<size_t>(row) * n;
+  uint64_t key[P];
+  int rank[P];
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    const int slot = lane + 32 * i;
+    key[i] = (slot < n) ? make_sort_key(src[slot], static_cast<uint32_t>(slot)) : 0ull;
+    rank[i] = 0;
+  }
+#pragma unroll
+  for (int i2 = 0; i2 < P; ++i2) {
+#pragma unroll 8
+    for (int l2 = 0; l2 < 32; ++l2) {
+      const uint64_t other = __shfl_sync(full, key[i2], l2);
+#pragma unroll
+      for (int i = 0; i < P; ++i) rank[i] += (other > key[i]) ? 1 : 0;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < P; ++i)
+    if (key[i] != 0ull && rank[i] == m - 1) prior[row] = sort_key_value(key[i]);
+}
+
 // Streaming survivors from a dense row, one warp per row, lanes over 32 consecutive columns.
 // Lane l only ever sees columns == l (mod 32): with m = ceil(k/32) running maxima per lane there
 // are 32*m seen values >= min over lanes of the m-th largest, the same class bound as in the
@@ -281,6 +521,45 @@ const char* select_topk_launch(const SelectLaunch& p, cudaStream_t stream) {
     attr_set = true;
   }
   select_topk_kernel<<<p.B, kSelThreads, smem, stream>>>(p, n_max, ksort);
+  return cuda_err(cudaGetLastError());
+}
+
+const char* select_small_launch(const SelectLaunch& p, int* ovf_count, int32_t* ovf_rows, cudaStream_t stream) {
+  if (p.nsub > 32) return "select_small: at most 32 sub-streams per row";
+  const int ksort = next_pow2(p.k_sel < 2 ? 2 : p.k_sel);
+  if (ksort > kSmallCap) return "select_small: k too large";
+  const int blocks = (p.B + kSmallWarps - 1) / kSmallWarps;
+  select_small_kernel<<<blocks, kSmallWarps * 32, 0, stream>>>(p, ksort, ovf_count, ovf_rows);
+  return cuda_err(cudaGetLastError());
+}
+
+const char* select_topk_list_launch(const SelectLaunch& p, const int* count, const int32_t* rows, int num_sms,
+                                    cudaStream_t stream) {
+  const int ksort = next_pow2(p.k_sel < 2 ? 2 : p.k_sel);
+  const int n_max = p.nsub * p.cap;
+  const size_t smem = static_cast<size_t>(n_max + ksort) * sizeof(uint64_t);
+  const size_t budget = 200 * 1024;
+  if (smem > budget) return "select_topk: too many survivors per row for shared memory";
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(select_topk_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(budget));
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    attr_set = true;
+  }
+  select_topk_list_kernel<<<num_sms, kSelThreads, smem, stream>>>(p, n_max, ksort, count, rows);
+  return cuda_err(cudaGetLastError());
+}
+
+const char* prior_from_top_launch(const float* top, int B, int nsub, int m, float* prior, cudaStream_t stream) {
+  const int n = nsub * kTopM;
+  const int blocks = (B + 7) / 8;
+  if (n <= 32) prior_from_top_kernel<1><<<blocks, 256, 0, stream>>>(top, B, n, m, prior);
+  else if (n <= 64) prior_from_top_kernel<2><<<blocks, 256, 0, stream>>>(top, B, n, m, prior);
+  else if (n <= 128) prior_from_top_kernel<4><<<blocks, 256, 0, stream>>>(top, B, n, m, prior);
+  else if (n <= 256) prior_from_top_kernel<8><<<blocks, 256, 0, stream>>>(top, B, n, m, prior);
+  else if (n <= 512) prior_from_top_kernel<16><<<blocks, 256, 0, stream>>>(top, B, n, m, prior);
+  else return "prior_from_top: too many sub-streams";
   return cuda_err(cudaGetLastError());
 }
 

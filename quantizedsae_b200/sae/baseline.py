@@ -32,6 +32,12 @@ class BaselineSparseAutoencoder(nn.Module):
         w = self.encoder[0].weight
         return self._prep.get("w_bf16", param_key(w), lambda: _lib.cast_bf16(w.detach().contiguous()))
 
+    def _sample(self):
+        """Sampled dictionary rows for the prior-threshold pre-pass (None for small dictionaries)."""
+        lin = self.encoder[0]
+        return self._prep.get("sample", param_key(lin.weight, lin.bias),
+                              lambda: _lib.prepare_sample(self._w_bf16(), lin.bias.detach()))
+
     def _dec_rows(self):
         w = self.decoder.weight                     # [D, H]: feature vectors are columns
         return self._prep.get("dec_rows", param_key(w), lambda: _lib.transpose(w.detach().contiguous()))
@@ -42,7 +48,7 @@ class BaselineSparseAutoencoder(nn.Module):
         w32 = lin.weight.detach().contiguous()
         vals, idx, flags = _lib.encode_topk(x, self._w_bf16(), w32 if self.exact else None,
                                             lin.bias.detach(), int(self.topk), _lib.ACT_NONE,
-                                            self.exact, want_flags=self.exact)
+                                            self.exact, want_flags=self.exact, sample=self._sample())
         self.last_flags = flags
         return SparseLatents(vals, idx, (x.shape[0], self.hidden_dim))
 

@@ -149,6 +149,12 @@ class BinarySAE(SparseAutoencoder):
         w = self.encoder[0].weight
         return self._prep.get("w_bf16", param_key(w), lambda: _lib.cast_bf16(w.detach().contiguous()))
 
+    def _sample(self):
+        """Sampled dictionary rows for the prior-threshold pre-pass (None for small dictionaries)."""
+        lin = self.encoder[0]
+        return self._prep.get("sample", param_key(lin.weight, lin.bias),
+                              lambda: _lib.prepare_sample(self._w_bf16(), lin.bias.detach()))
+
     def encode(self, x):
         """Dense pre-activations [B, H] (sae/base.py:16-19). Exact fp32 CUDA-core kernel; the
         throughput path is forward()/encode_topk(), which never builds this matrix."""
@@ -163,7 +169,7 @@ class BinarySAE(SparseAutoencoder):
         w32 = lin.weight.detach().contiguous()
         vals, idx, flags = _lib.encode_topk(x, self._w_bf16(), w32 if self.exact else None,
                                             lin.bias.detach(), k, _lib.ACT_NONE, self.exact,
-                                            want_flags=self.exact)
+                                            want_flags=self.exact, sample=self._sample())
         self.last_flags = flags
         return SparseLatents(vals, idx, (x.shape[0], self.hidden_dim))
 

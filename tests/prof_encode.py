@@ -14,13 +14,14 @@ x = torch.randn((B, D), device=dev, generator=g).bfloat16().float()
 W = ((torch.rand((H, D), device=dev, generator=g) * 2 - 1) * (6.0 / (H + D)) ** 0.5).bfloat16().float()
 b = torch.zeros(H, device=dev)
 Wb = L.cast_bf16(W)
+sample = L.prepare_sample(Wb, b) if os.environ.get('QSAE_NO_SAMPLE') is None else None
 for _ in range(3):
-    L.encode_topk(x, Wb, None, b, k)
+    L.encode_topk(x, Wb, None, b, k, sample=sample)
 torch.cuda.synchronize()
 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 s.record()
 for _ in range(iters):
-    L.encode_topk(x, Wb, None, b, k)
+    L.encode_topk(x, Wb, None, b, k, sample=sample)
 e.record()
 torch.cuda.synchronize()
 t = s.elapsed_time(e) / iters

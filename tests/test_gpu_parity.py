@@ -362,3 +362,48 @@ def test_host_pipeline_entry(cuda_device):
 
 def test_native_library_was_used(cuda_device):
     assert L._lib is not None and L.launch_count > 0
+
+
+# ------------------------------------------------------------------------------------------
+# prior threshold (sampled-latent pre-pass), count verification and the rescue kernel
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,exact", [(32, False), (65, False), (32, True), (65, True)])
+def test_prior_threshold_path_matches_oracle(cuda_device, k, exact):
+    B, H, D = 384, 32768, 512
+    x, W, b = _enc_case(B, H, D, 40 + k, bf16=not exact)
+    dx, dW, db = T(x, cuda_device), T(W, cuda_device), T(b, cuda_device)
+    wb = L.cast_bf16(dW)
+    sample = L.prepare_sample(wb, db)
+    assert sample is not None and sample[0].shape == (1024, D)
+    vals, idx, flags = L.encode_topk(dx, wb, dW if exact else None, db, k, exact=exact, want_flags=True, sample=sample)
+    assert_topk_matches(vals.cpu().numpy(), idx.cpu().numpy(), O.encode_pre(x, W, b), k)
+    assert int((flags != 0).sum()) == 0
+    # identical to the path without the prior
+    v0, i0, _ = L.encode_topk(dx, wb, dW if exact else None, db, k, exact=exact)
+    assert torch.equal(i0, idx) and torch.equal(v0, vals)
+
+
+def test_prior_failure_is_rescued_exactly(cuda_device):
+    """Force the prior to fail: the sampled rows carry a huge bias that the real rows do not have,
+    so every row's prior threshold is far above its true top-k and the count check must route
+    all rows through the rescue kernel -- which has to reproduce the exact result."""
+    B, H, D, k = 70, 16384, 256, 32
+    x, W, b = _enc_case(B, H, D, 77)
+    dx, dW, db = T(x, cuda_device), T(W, cuda_device), T(b, cuda_device)
+    wb = L.cast_bf16(dW)
+    ws, bs = L.prepare_sample(wb, db, 512)
+    for exact in (False, True):
+        vals, idx, flags = L.encode_topk(dx, wb, dW if exact else None, db, k, exact=exact, want_flags=True,
+                                         sample=(ws, bs + 100.0))
+        assert_topk_matches(vals.cpu().numpy(), idx.cpu().numpy(), O.encode_pre(x, W, b), k)
+        assert int((flags != 0).sum()) == 0          # rescued rows are exact by construction
+
+
+def test_sample_rows_are_a_stratified_subset(cuda_device):
+    H, D, n = 32768, 64, 1024
+    W = torch.arange(H, device=cuda_device, dtype=torch.float32)[:, None].expand(H, D).contiguous()
+    b = torch.arange(H, device=cuda_device, dtype=torch.float32)
+    ws, bs = L.prepare_sample(L.cast_bf16(W), b, n)
+    rows = bs.cpu().numpy().astype(np.int64)
+    assert len(set(rows.tolist())) == n
+    assert np.all(rows // (H // n) == np.arange(n))   # one row from each of the n equal slices

@@ -50,12 +50,13 @@ def test_argument_validation_without_gpu():
 
     lib = _lib.load()
     n = C.c_size_t(0)
-    assert lib.qsae_encode_topk_workspace_bytes(128, 1024, 500, 8, C.byref(n)) == -1   # D % 8
+    assert lib.qsae_encode_topk_workspace_bytes(128, 1024, 500, 8, 0, C.byref(n)) == -1   # D % 8
     assert b"multiple of 8" in lib.qsae_last_error()
-    assert lib.qsae_encode_topk_workspace_bytes(128, 1024, 1024, 8, C.byref(n)) == -1  # D > 512
-    assert lib.qsae_encode_topk_workspace_bytes(128, 16, 64, 32, C.byref(n)) == -5     # k > H
+    assert lib.qsae_encode_topk_workspace_bytes(128, 1024, 1024, 8, 0, C.byref(n)) == -1  # D > 512
+    assert lib.qsae_encode_topk_workspace_bytes(128, 16, 64, 32, 0, C.byref(n)) == -5     # k > H
     assert b"out of range" in lib.qsae_last_error()
-    assert lib.qsae_encode_topk_workspace_bytes(128, 4096, 64, 500, C.byref(n)) == -1  # k > MAX_K
+    assert lib.qsae_encode_topk_workspace_bytes(128, 4096, 64, 500, 0, C.byref(n)) == -1  # k > MAX_K
+    assert lib.qsae_encode_topk_workspace_bytes(4096, 32768, 512, 32, 1024, C.byref(n)) == 0 and n.value > 0
     assert lib.qsae_pack_bitplanes(None, 8, 8, 4, None, None, None) == -1
     assert lib.qsae_decode_int4(None, None, 1, 1, None, 8, 8, 1.0, None, None, None) == -1
     with pytest.raises(RuntimeError):
