@@ -163,6 +163,47 @@ int qsae_decode_rows_f32(const float* vals, const int32_t* idx, int B, int k,
                          const float* rows /* [H, D] */, int H, int D, float scale,
                          const float* bias, float* recon, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * q_sae: QuantizedMatryoshkaDecoder (sae/quantized_matryoshka.py:47-143)
+ * ------------------------------------------------------------------------------------- */
+/* weight / weight_mirror [H, D] fp32 -> T = sign(sigmoid(w) >= 0.5) + sign(sigmoid(w_m) >= 0.5) in
+ * {-2, 0, +2}, packed 2 bits per entry ([H, D/16] uint32: bit0 non-zero, bit1 negative), and
+ * scale[h] = level_factor[level(h)] / (||T[h,:]||_2 + 1e-8)   (:67-91).
+ * level_start: device int[n_levels + 1] (first latent of each level, then H);
+ * level_factor: device float[n_levels] = 2^(n_bits - i - 2) * quant_step. D % 16 == 0. */
+int qsae_pack_matryoshka(const float* weight, const float* weight_mirror, int H, int D,
+                         const int* level_start, const float* level_factor, int n_levels,
+                         uint32_t* packed, float* scale, void* stream);
+
+int qsae_matryoshka_workspace_bytes(int B, int H, int D, size_t* bytes);
+
+/* QuantizedMatryoshkaSAE.forward (:217-220): encoder (Linear + Sigmoid, active <=> sigmoid(z) > 0.5)
+ * fused with the collection of each row's active latents, then the sparse level decoder:
+ * result[i, b, :] = bias + sum_{h active, level(h) <= i} scale[h] * T[h, :]     (cumulative, :121-129)
+ * level_count[i]  = number of active latents of level i over the batch (latent_group[i] * B).
+ * *overflow is set to 1 when a row had more active latents than the sparse path holds
+ * (1024 per sub-stream); the result is then incomplete and the caller must use a dense path. */
+int qsae_matryoshka_forward(const float* x_f32, const uint16_t* w_bf16,
+                            const float* w_f32 /* [H,D] or NULL: exact fp32 activity decisions */,
+                            const float* w_norm_max /* device scalar from qsae_max_row_norm; exact only */,
+                            const float* b_enc, const uint32_t* packed, const float* scale,
+                            const int* level_start, int n_levels, const float* dec_bias /* [D] or NULL */,
+                            int B, int H, int D, float* result /* [n_levels, B, D] */,
+                            unsigned long long* level_count /* [n_levels] */, int* overflow,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* max_h ||w[h,:]||_2 -> *out (device float). With w_f32 given, qsae_matryoshka_forward lowers each
+ * row's sweep threshold by the bound 2^-8 ||x_b|| max_h||w_h|| on |z_bf16 - z_fp32| and decides
+ * activity from an fp32 re-scoring, so the active set equals the fp32 reference's for any input. */
+int qsae_max_row_norm(const float* w_f32, int H, int D, float* out, void* stream);
+
+/* The level decoder alone, for callers that already hold the active latents:
+ * lists [B, cap, 2] int32 (second component = latent index), counts [B]. */
+int qsae_decode_matryoshka_lists(const int32_t* lists, const int32_t* counts, int cap, int B,
+                                 const uint32_t* packed, const float* scale, const int* level_start,
+                                 int n_levels, int H, int D, const float* dec_bias, float* result,
+                                 unsigned long long* level_count, void* stream);
+
 /* latent * mask (sae/binary.py:96-99) / zeros_like + scatter_ (sae/baseline.py:38-39):
  * dense [B, H] float32 from the sparse form. Zero-fills `dense` first. */
 int qsae_densify(const float* vals, const int32_t* idx, int B, int k, int H, float* dense,

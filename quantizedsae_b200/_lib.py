@@ -39,6 +39,11 @@ SYMBOLS = {
     "qsae_decode_int4": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _f, _vp, _vp, _vp]),
     "qsae_decode_int8": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _f, _vp, _vp, _vp]),
     "qsae_decode_rows_f32": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _f, _vp, _vp, _vp]),
+    "qsae_pack_matryoshka": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "qsae_matryoshka_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
+    "qsae_matryoshka_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "qsae_max_row_norm": (_i, [_vp, _i, _i, _vp, _vp]),
+    "qsae_decode_matryoshka_lists": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "qsae_densify": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "qsae_bsae_plan_create": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _i, C.POINTER(_vp)]),
     "qsae_bsae_plan_destroy": (None, [_vp]),
@@ -291,3 +296,63 @@ def densify(vals: torch.Tensor, idx: torch.Tensor, H: int) -> torch.Tensor:
     check(load().qsae_densify(vals.data_ptr(), idx.data_ptr(), B, k, H, dense.data_ptr(), _stream()))
     launch_count += 1
     return dense
+
+
+def pack_matryoshka(weight: torch.Tensor, weight_mirror: torch.Tensor, level_start: torch.Tensor,
+                    level_factor: torch.Tensor):
+    """-> (packed [H, D/16] int32 (2-bit codes), scale [H] f32)"""
+    global launch_count
+    _need_cuda(weight, weight_mirror, level_start, level_factor)
+    H, D = weight.shape
+    packed = torch.empty((H, D // 16), dtype=torch.int32, device=weight.device)
+    scale = torch.empty((H,), dtype=torch.float32, device=weight.device)
+    check(load().qsae_pack_matryoshka(weight.data_ptr(), weight_mirror.data_ptr(), H, D, level_start.data_ptr(),
+                                      level_factor.data_ptr(), level_factor.numel(), packed.data_ptr(),
+                                      scale.data_ptr(), _stream()))
+    launch_count += 1
+    return packed, scale
+
+
+def max_row_norm(w_f32: torch.Tensor) -> torch.Tensor:
+    global launch_count
+    _need_cuda(w_f32)
+    out = torch.zeros(1, dtype=torch.float32, device=w_f32.device)
+    check(load().qsae_max_row_norm(w_f32.data_ptr(), w_f32.shape[0], w_f32.shape[1], out.data_ptr(), _stream()))
+    launch_count += 1
+    return out
+
+
+def decode_matryoshka_lists(lists, counts, cap, packed, scale, level_start, n_levels, H, D, dec_bias):
+    global launch_count
+    _need_cuda(lists, counts, packed, scale, level_start, dec_bias)
+    B = counts.shape[0]
+    result = torch.empty((n_levels, B, D), dtype=torch.float32, device=lists.device)
+    level_count = torch.zeros((n_levels,), dtype=torch.int64, device=lists.device)
+    check(load().qsae_decode_matryoshka_lists(lists.data_ptr(), counts.data_ptr(), cap, B, packed.data_ptr(),
+                                              scale.data_ptr(), level_start.data_ptr(), n_levels, H, D, _ptr(dec_bias),
+                                              result.data_ptr(), level_count.data_ptr(), _stream()))
+    launch_count += 1
+    return result, level_count
+
+
+def matryoshka_forward(x, w_bf16, b_enc, packed, scale, level_start, n_levels, dec_bias, w_f32=None, w_norm_max=None):
+    """-> (result [n_levels, B, D] f32, level_count [n_levels] int64, overflow [1] int32)"""
+    global launch_count
+    _need_cuda(x, w_bf16, b_enc, packed, scale, level_start, dec_bias)
+    B, D = x.shape
+    H = w_bf16.shape[0]
+    result = torch.empty((n_levels, B, D), dtype=torch.float32, device=x.device)
+    counts = torch.empty((n_levels,), dtype=torch.int64, device=x.device)
+    overflow = torch.empty((1,), dtype=torch.int32, device=x.device)
+    if B == 0:
+        return result, counts.zero_(), overflow.zero_()
+    n = _sz(0)
+    check(load().qsae_matryoshka_workspace_bytes(B, H, D, C.byref(n)))
+    ws = _workspace(x.device, int(n.value))
+    check(load().qsae_matryoshka_forward(x.data_ptr(), w_bf16.data_ptr(), _ptr(w_f32), _ptr(w_norm_max),
+                                         b_enc.data_ptr(), packed.data_ptr(),
+                                         scale.data_ptr(), level_start.data_ptr(), n_levels, _ptr(dec_bias), B, H, D,
+                                         result.data_ptr(), counts.data_ptr(), overflow.data_ptr(), ws.data_ptr(),
+                                         ws.numel(), _stream()))
+    launch_count += 3
+    return result, counts, overflow

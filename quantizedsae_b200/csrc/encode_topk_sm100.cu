@@ -295,7 +295,18 @@ __device__ __forceinline__ void epilogue_loop(const EncodeLaunch& p, int n_my_ti
             ++cnt;
           }
         }
-        if (__any_sync(full, cnt > cap - 32)) relieve_warp_buffers(buf, cnt, thr, valid_bound, k, cap, lane);
+        if (__any_sync(full, cnt > cap - 32)) {
+          if (MODE == 4 && k <= 0) {
+            // threshold-only use (q_sae: every value above the threshold is wanted): a full
+            // buffer cannot be cut, so stop collecting and report the overflow
+            if (cnt > cap - 32) {
+              thr = INFINITY;
+              if (p.overflow != nullptr) atomicExch(p.overflow, 1);
+            }
+          } else {
+            relieve_warp_buffers(buf, cnt, thr, valid_bound, k, cap, lane);
+          }
+        }
       }
     }
     tc_fence_before();

@@ -26,6 +26,7 @@ struct EncodeLaunch {
   const float* bias;    // [H]
   const float* prior;   // mode 4: per-row threshold at prior[row * prior_stride]
   int prior_stride;
+  int* overflow;        // mode 4 with k_sel <= 0 (threshold only): set to 1 when a buffer filled up
   float* top_out;       // mode 5: [B][n_splits*2][kTopM] sorted largest values of each sub-stream
   void* cand;           // [B][n_splits*2][cap] {float bits, int32 column}
   int* cand_cnt;        // [B][n_splits*2]
@@ -108,6 +109,19 @@ const char* decode_f32_launch(const float* vals, const int32_t* idx, int B, int 
                               cudaStream_t stream);
 const char* densify_launch(const float* vals, const int32_t* idx, int B, int k, int H, float* dense,
                            cudaStream_t stream);
+
+// matryoshka.cu
+const char* pack_matryoshka_launch(const float* w, const float* wm, int H, int D, const int* level_start,
+                                   const float* level_factor, int n_levels, uint32_t* packed, float* scale,
+                                   cudaStream_t stream);
+const char* decode_matryoshka_launch(const void* cand, const int* cand_cnt, int nsub, int cap, int B,
+                                     const uint32_t* packed, const float* scale, const int* level_start,
+                                     int n_levels, int H, int D, const float* bias, float* result,
+                                     unsigned long long* level_count, const float* x_f32, const float* w_f32,
+                                     const float* b_enc, float thr_value, int exact, cudaStream_t stream);
+const char* max_row_norm_launch(const float* w, int H, int D, float* out, cudaStream_t stream);
+const char* row_threshold_launch(const float* x, int B, int D, const float* wmax, float thr_value, float* thr,
+                                 cudaStream_t stream);
 
 // encode_dense.cu
 const char* encode_dense_launch(const float* x, const int32_t* rows, int R, const float* w,

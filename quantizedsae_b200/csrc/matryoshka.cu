@@ -1,0 +1,220 @@
+// q_sae (QuantizedMatryoshkaDecoder, sae/quantized_matryoshka.py:47-143) on a packed dictionary.
+//
+// Reference per level i (latent rows [start_i, start_i + size_i)):
+//   S = +1 where sigmoid(w) >= 0.5 else -1, for weight and weight_mirror          (:67-80)
+//   T = S + S_mirror in {-2, 0, +2}
+//   scale[h] = 2^(n_bits - i - 2) * quant_step / (||T[h,:]||_2 + 1e-8)            (:82-91)
+//   a[b,h]  = latent[b,h] > 0.5 (latent = sigmoid(z), i.e. z > 0)                 (:99)
+//   recon  += (scale * a) @ T ; + bias once at level 0 ; result[i] = recon         (:121-129)
+//   latent_group[i] = mean_b sum_{h in level i} a[b,h]                             (:127)
+//
+// Packed form: 2 bits per entry (bit0 = non-zero, bit1 = negative; value = +-2), 16 entries per
+// 32-bit word, [H, D/16] words (128 B per row at D = 512) + one fp32 scale per row.
+// The decoder consumes the encoder's survivor lists directly (the active latents of a row, any
+// order): warp per token, level accumulators in shared memory, cumulative outputs.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace qsae {
+
+namespace {
+
+__device__ __forceinline__ float logistic(float w) { return 1.0f / (1.0f + expf(-w)); }
+
+// one warp per dictionary row; lane handles 16 consecutive features per trip
+__global__ void __launch_bounds__(256)
+pack_matryoshka_kernel(const float* __restrict__ w, const float* __restrict__ wm, int H, int D,
+                       const int* __restrict__ level_start, const float* __restrict__ level_factor,
+                       int n_levels, uint32_t* __restrict__ packed, float* __restrict__ scale) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x * 8 + warp;
+  if (h >= H) return;
+  const int words = D >> 4;
+  int nnz = 0;
+  for (int wd = lane; wd < words; wd += 32) {
+    uint32_t bits = 0u;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const size_t o = static_cast<size_t>(h) * D + wd * 16 + q;
+      const int s = (logistic(w[o]) >= 0.5f) ? 1 : -1;
+      const int sm = (logistic(wm[o]) >= 0.5f) ? 1 : -1;
+      const int t = s + sm;                     // -2, 0, +2
+      const uint32_t code = (t != 0 ? 1u : 0u) | (t < 0 ? 2u : 0u);
+      bits |= code << (2 * q);
+      nnz += (t != 0);
+    }
+    packed[static_cast<size_t>(h) * words + wd] = bits;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nnz += __shfl_xor_sync(0xffffffffu, nnz, o);
+  if (lane == 0) {
+    int lvl = 0;
+    while (lvl + 1 < n_levels && h >= level_start[lvl + 1]) ++lvl;
+    const float norm = sqrtf(static_cast<float>(4 * nnz));  // ||T||_2, T entries are +-2
+    scale[h] = level_factor[lvl] / (norm + 1e-8f);
+  }
+}
+
+// max_h ||w[h,:]||_2 (for the rounding-error band of the bf16 activity test), non-negative float max
+__global__ void __launch_bounds__(256)
+max_row_norm_kernel(const float* __restrict__ w, int H, int D, float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x * 8 + warp;
+  if (h >= H) return;
+  float s = 0.f;
+  for (int d = lane; d < D; d += 32) { const float v = w[static_cast<size_t>(h) * D + d]; s = fmaf(v, v, s); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) atomicMax(reinterpret_cast<unsigned*>(out), __float_as_uint(sqrtf(s)));
+}
+
+// thr[b] = thr_value - band_b, band_b = 2^-8 ||x_b||_2 max_h||w_h||_2 (+1 %): an upper bound of
+// |z_bf16 - z_fp32| (each operand carries <= 2^-9 relative rounding error), so every latent that
+// is active in fp32 survives the tensor-core sweep and is then decided exactly by re-scoring
+__global__ void __launch_bounds__(256)
+row_threshold_kernel(const float* __restrict__ x, int B, int D, const float* __restrict__ wmax, float thr_value,
+                     float* __restrict__ thr) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + warp;
+  if (b >= B) return;
+  float s = 0.f;
+  for (int d = lane; d < D; d += 32) { const float v = x[static_cast<size_t>(b) * D + d]; s = fmaf(v, v, s); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) thr[b] = thr_value - (1.01f * 0.00390625f * sqrtf(s) * (*wmax) + 1e-6f);
+}
+
+constexpr int kMatWarps = 4;
+
+// warp per token. acc[level][d] lives in shared memory (lane-private columns, no conflicts).
+__global__ void __launch_bounds__(kMatWarps * 32)
+decode_matryoshka_kernel(const uint2* __restrict__ cand, const int* __restrict__ cand_cnt, int nsub,
+                         int cap, int B, const uint32_t* __restrict__ packed,
+                         const float* __restrict__ scale, const int* __restrict__ level_start,
+                         int n_levels, int H, int D, const float* __restrict__ bias,
+                         float* __restrict__ result /* [n_levels, B, D] */,
+                         unsigned long long* __restrict__ level_count /* [n_levels] */,
+                         const float* __restrict__ x_f32, const float* __restrict__ w_f32,
+                         const float* __restrict__ b_enc, float thr_value, int exact) {
+  extern __shared__ float acc_smem[];  // [kMatWarps][n_levels][D]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kMatWarps + warp;
+  if (row >= B) return;
+  const unsigned full = 0xffffffffu;
+  float* acc = acc_smem + static_cast<size_t>(warp) * n_levels * D;
+  for (int i = lane; i < n_levels * D; i += 32) acc[i] = 0.f;
+  __syncwarp();
+  const int words = D >> 4;
+  int my_counts = 0;  // lane l counts level l (n_levels <= 32)
+  float4 xr[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int d = c * 128 + lane * 4;
+    xr[c] = (exact && d < D) ? *reinterpret_cast<const float4*>(x_f32 + static_cast<size_t>(row) * D + d)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int s = 0; s < nsub; ++s) {
+    const size_t slot = static_cast<size_t>(row) * nsub + s;
+    const int c = min(cand_cnt[slot], cap);
+    const uint2* src = cand + slot * cap;
+    for (int base = 0; base < c; base += 32) {
+      const int e = base + lane;
+      const int my_col = (e < c) ? static_cast<int>(src[e].y) : -1;
+      const int m = min(32, c - base);
+      for (int j = 0; j < m; ++j) {
+        const int col = __shfl_sync(full, my_col, j);
+        if (col < 0 || col >= H) continue;
+        if (exact) {  // the sweep kept a rounding-error band below the threshold: decide in fp32
+          const float* wrow = w_f32 + static_cast<size_t>(col) * D;
+          float a0 = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int d = c * 128 + lane * 4;
+            if (d < D) {
+              const float4 u = __ldg(reinterpret_cast<const float4*>(wrow + d));
+              a0 = fmaf(xr[c].x, u.x, a0); a0 = fmaf(xr[c].y, u.y, a0);
+              a0 = fmaf(xr[c].z, u.z, a0); a0 = fmaf(xr[c].w, u.w, a0);
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) a0 += __shfl_xor_sync(full, a0, o);
+          if (!(a0 + __ldg(b_enc + col) >= thr_value)) continue;
+        }
+        int lvl = 0;
+        while (lvl + 1 < n_levels && col >= level_start[lvl + 1]) ++lvl;
+        if (lane == lvl) ++my_counts;
+        const float sc = __ldg(scale + col);
+        const uint32_t* trow = packed + static_cast<size_t>(col) * words;
+        float* a = acc + static_cast<size_t>(lvl) * D;
+        for (int wd = lane; wd < words; wd += 32) {
+          const uint32_t bits = __ldg(trow + wd);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const uint32_t code = (bits >> (2 * q)) & 3u;
+            // +-2 * scale, or 0
+            const float t = (code & 1u) ? ((code & 2u) ? -2.f : 2.f) : 0.f;
+            a[wd * 16 + q] = fmaf(sc, t, a[wd * 16 + q]);
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  // cumulative outputs: result[i] = bias + sum_{l <= i} acc[l]
+  for (int d = lane; d < D; d += 32) {
+    float run = bias ? bias[d] : 0.f;
+    for (int l = 0; l < n_levels; ++l) {
+      run += acc[static_cast<size_t>(l) * D + d];
+      result[(static_cast<size_t>(l) * B + row) * D + d] = run;
+    }
+  }
+  if (lane < n_levels && my_counts > 0) atomicAdd(&level_count[lane], static_cast<unsigned long long>(my_counts));
+}
+
+}  // namespace
+
+const char* pack_matryoshka_launch(const float* w, const float* wm, int H, int D, const int* level_start,
+                                   const float* level_factor, int n_levels, uint32_t* packed, float* scale,
+                                   cudaStream_t stream) {
+  pack_matryoshka_kernel<<<(H + 7) / 8, 256, 0, stream>>>(w, wm, H, D, level_start, level_factor, n_levels,
+                                                          packed, scale);
+  return cuda_err(cudaGetLastError());
+}
+
+const char* max_row_norm_launch(const float* w, int H, int D, float* out, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float), stream);
+  if (e != cudaSuccess) return cudaGetErrorString(e);
+  max_row_norm_kernel<<<(H + 7) / 8, 256, 0, stream>>>(w, H, D, out);
+  return cuda_err(cudaGetLastError());
+}
+
+const char* row_threshold_launch(const float* x, int B, int D, const float* wmax, float thr_value, float* thr,
+                                 cudaStream_t stream) {
+  row_threshold_kernel<<<(B + 7) / 8, 256, 0, stream>>>(x, B, D, wmax, thr_value, thr);
+  return cuda_err(cudaGetLastError());
+}
+
+const char* decode_matryoshka_launch(const void* cand, const int* cand_cnt, int nsub, int cap, int B,
+                                     const uint32_t* packed, const float* scale, const int* level_start,
+                                     int n_levels, int H, int D, const float* bias, float* result,
+                                     unsigned long long* level_count, const float* x_f32, const float* w_f32,
+                                     const float* b_enc, float thr_value, int exact, cudaStream_t stream) {
+  const size_t smem = static_cast<size_t>(kMatWarps) * n_levels * D * sizeof(float);
+  if (smem > 200 * 1024) return "decode_matryoshka: n_levels * D too large for shared memory";
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(decode_matryoshka_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    attr = smem;
+  }
+  decode_matryoshka_kernel<<<(B + kMatWarps - 1) / kMatWarps, kMatWarps * 32, smem, stream>>>(
+      reinterpret_cast<const uint2*>(cand), cand_cnt, nsub, cap, B, packed, scale, level_start, n_levels, H, D,
+      bias, result, level_count, x_f32, w_f32, b_enc, thr_value, exact);
+  return cuda_err(cudaGetLastError());
+}
+
+}  // namespace qsae

@@ -349,6 +349,109 @@ int qsae_encode_dense_tc(const float* x_f32, const uint16_t* w_bf16, const float
   return launch_status("encode_topk kernel (dense dump)", encode_topk_launch(x_bf16, w_bf16, el, S(stream)));
 }
 
+// ---------------------------------------------------------------------------------------------
+// q_sae
+// ---------------------------------------------------------------------------------------------
+int qsae_pack_matryoshka(const float* weight, const float* weight_mirror, int H, int D, const int* level_start,
+                         const float* level_factor, int n_levels, uint32_t* packed, float* scale, void* stream) {
+  if (!weight || !weight_mirror || !level_start || !level_factor || !packed || !scale)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "pack_matryoshka: null pointer");
+  if (H <= 0 || D <= 0 || (D % 16) != 0 || n_levels < 1 || n_levels > 32)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "pack_matryoshka: need D %% 16 == 0 and 1 <= n_levels <= 32");
+  return launch_status("pack_matryoshka", pack_matryoshka_launch(weight, weight_mirror, H, D, level_start, level_factor,
+                                                                 n_levels, packed, scale, S(stream)));
+}
+
+namespace {
+struct MatPlan { StagePlan st; size_t x_off, prior_off, total; };
+constexpr float kActiveThreshold = 8.940697e-08f;  // sigmoid(z) > 0.5 in fp32 <=> z >= 1.5 * 2^-24
+int plan_matryoshka(int B, int H, int D, MatPlan* mp) {
+  if (B <= 0 || H <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "B and H must be positive");
+  if (D < 16 || D > 512 || (D % 16) != 0)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka: D must be a multiple of 16 in [16, 512], got %d", D);
+  mp->x_off = 0;
+  mp->prior_off = align_up(static_cast<size_t>(B) * D * 2, 1024);
+  plan_stage(B, H, 0, kStagePriorMain, false, mp->prior_off + align_up(static_cast<size_t>(B) * 4, 256), &mp->st);
+  mp->st.cap = kCandCapMax;  // every active latent is kept: largest buffers
+  mp->st.cnt_off = mp->st.cand_off + static_cast<size_t>(B) * mp->st.nsub * mp->st.cap * 8;
+  mp->st.thr_off = mp->st.cnt_off + static_cast<size_t>(B) * mp->st.nsub * 4;
+  mp->st.end = align_up(mp->st.thr_off + static_cast<size_t>(B) * mp->st.nsub * 4, 256);
+  mp->total = mp->st.end;
+  return QSAE_OK;
+}
+}  // namespace
+
+int qsae_matryoshka_workspace_bytes(int B, int H, int D, size_t* bytes) {
+  if (!bytes) return fail(QSAE_ERR_INVALID_ARGUMENT, "workspace query: null pointer");
+  MatPlan mp;
+  int rc = plan_matryoshka(B, H, D, &mp);
+  if (rc != QSAE_OK) return rc;
+  *bytes = mp.total;
+  return QSAE_OK;
+}
+
+int qsae_max_row_norm(const float* w_f32, int H, int D, float* out, void* stream) {
+  if (!w_f32 || !out || H <= 0 || D <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "max_row_norm: bad argument");
+  return launch_status("max_row_norm", max_row_norm_launch(w_f32, H, D, out, S(stream)));
+}
+
+int qsae_decode_matryoshka_lists(const int32_t* lists, const int32_t* counts, int cap, int B, const uint32_t* packed,
+                                 const float* scale, const int* level_start, int n_levels, int H, int D,
+                                 const float* dec_bias, float* result, unsigned long long* level_count, void* stream) {
+  if (B == 0) return QSAE_OK;
+  if (!lists || !counts || !packed || !scale || !level_start || !result || !level_count)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "decode_matryoshka_lists: null pointer");
+  if (n_levels < 1 || n_levels > 32 || (D % 16) != 0 || D > 512 || cap < 1)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "decode_matryoshka_lists: bad shape");
+  cudaError_t ce = cudaMemsetAsync(level_count, 0, static_cast<size_t>(n_levels) * sizeof(unsigned long long), S(stream));
+  if (ce != cudaSuccess) return fail(QSAE_ERR_CUDA, "decode_matryoshka_lists: %s", cudaGetErrorString(ce));
+  return launch_status("decode_matryoshka", decode_matryoshka_launch(lists, counts, 1, cap, B, packed, scale, level_start,
+                                                                     n_levels, H, D, dec_bias, result, level_count,
+                                                                     nullptr, nullptr, nullptr, 0.f, 0, S(stream)));
+}
+
+int qsae_matryoshka_forward(const float* x_f32, const uint16_t* w_bf16, const float* w_f32, const float* w_norm_max,
+                            const float* b_enc, const uint32_t* packed,
+                            const float* scale, const int* level_start, int n_levels, const float* dec_bias,
+                            int B, int H, int D, float* result, unsigned long long* level_count, int* overflow,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  if (B == 0) return QSAE_OK;
+  if (!x_f32 || !w_bf16 || !b_enc || !packed || !scale || !level_start || !result || !level_count || !overflow || !workspace)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_forward: null pointer");
+  if (n_levels < 1 || n_levels > 32) return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_forward: 1 <= n_levels <= 32");
+  const int exact = (w_f32 != nullptr) ? 1 : 0;
+  if (exact && !w_norm_max) return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_forward: exact mode needs w_norm_max");
+  MatPlan mp;
+  int rc = plan_matryoshka(B, H, D, &mp);
+  if (rc != QSAE_OK) return rc;
+  if (workspace_bytes < mp.total)
+    return fail(QSAE_ERR_WORKSPACE_TOO_SMALL, "matryoshka_forward: workspace %zu < %zu bytes", workspace_bytes, mp.total);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  uint16_t* x_bf16 = reinterpret_cast<uint16_t*>(ws + mp.x_off);
+  float* thr = reinterpret_cast<float*>(ws + mp.prior_off);
+  cudaStream_t st = S(stream);
+  cudaError_t ce = cudaMemsetAsync(level_count, 0, static_cast<size_t>(n_levels) * sizeof(unsigned long long), st);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(overflow, 0, sizeof(int), st);
+  if (ce == cudaSuccess && !exact) ce = cudaMemcpyAsync(thr, &kActiveThreshold, sizeof(float), cudaMemcpyHostToDevice, st);
+  if (ce != cudaSuccess) return fail(QSAE_ERR_CUDA, "matryoshka_forward: %s", cudaGetErrorString(ce));
+  if (exact) {
+    rc = launch_status("row_threshold", row_threshold_launch(x_f32, B, D, w_norm_max, kActiveThreshold, thr, st));
+    if (rc != QSAE_OK) return rc;
+  }
+  rc = launch_status("cast x", cast_bf16_launch(x_f32, x_bf16, static_cast<size_t>(B) * D, st));
+  if (rc != QSAE_OK) return rc;
+  EncodeLaunch el;
+  fill_encode_launch(&el, mp.st, B, D, QSAE_ACT_NONE, b_enc, ws);
+  el.prior = thr; el.prior_stride = exact ? 1 : 0;   // per-row band, or one constant threshold
+  el.overflow = overflow;
+  rc = launch_status("encode kernel (threshold)", encode_topk_launch(x_bf16, w_bf16, el, st));
+  if (rc != QSAE_OK) return rc;
+  return launch_status("decode_matryoshka", decode_matryoshka_launch(el.cand, el.cand_cnt, mp.st.nsub, mp.st.cap, B, packed,
+                                                                     scale, level_start, n_levels, H, D, dec_bias, result,
+                                                                     level_count, x_f32, w_f32, b_enc, kActiveThreshold,
+                                                                     exact, st));
+}
+
 int qsae_encode_dense_f32(const float* x_f32, const int32_t* rows, int R, const float* w_f32,
                           const float* b_enc, int H, int D, int act, float* z, void* stream) {
   if (R == 0) return QSAE_OK;

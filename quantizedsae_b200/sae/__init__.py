@@ -2,5 +2,7 @@
 from .base import SparseAutoencoder
 from .baseline import BaselineSparseAutoencoder
 from .binary import BinarySAE, binary_decoder
+from .quantized_matryoshka import QuantizedMatryoshkaDecoder, QuantizedMatryoshkaSAE
 
-__all__ = ["SparseAutoencoder", "BaselineSparseAutoencoder", "BinarySAE", "binary_decoder"]
+__all__ = ["SparseAutoencoder", "BaselineSparseAutoencoder", "BinarySAE", "binary_decoder",
+           "QuantizedMatryoshkaDecoder", "QuantizedMatryoshkaSAE"]

@@ -1,0 +1,145 @@
+"""q_sae: QuantizedMatryoshkaSAE / QuantizedMatryoshkaDecoder (sae/quantized_matryoshka.py) on
+libqsae_b200.so.
+
+forward(x) -> (latent_group: list[n_bits] of 0-d tensors, result: list[n_bits] of [B, D])   (:143)
+
+Reference: sigmoid encoder, activity = sigmoid(z) > 0.5 (`top_k` is stored and never used, :204),
+per level a dense `(scale * a) @ (S + S_mirror)` with host syncs (:85). Here: the tcgen05 encoder
+collects each row's active latents in its epilogue (threshold mode) and a sparse decoder sums the
+packed {-2,0,+2} rows per level, emitting the cumulative reconstructions in one pass.
+Rows with more active latents than the sparse path holds (1024 per sub-stream) raise: the dense
+decode GEMM for un-trained (50 % active) models is not built yet.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from .base import PreparedCache, SparseAutoencoder, param_key, require_cuda_input
+
+
+def nested_sizes(in_features: int, n_bits: int) -> list:
+    """Level sizes: base pattern [1, 1, 2, 4, ...] scaled to in_features with int() truncation,
+    remainder folded into the last level (sae/quantized_matryoshka.py:25-38)."""
+    sizes = [1 if i < 2 else 2 ** (i - 1) for i in range(n_bits)]
+    total = sum(sizes)
+    if total != in_features:
+        f = in_features / total
+        sizes = [max(1, int(s * f)) for s in sizes]
+        sizes[-1] = in_features - sum(sizes[:-1])
+    return sizes
+
+
+class QuantizedMatryoshkaDecoder(nn.Module):
+    def __init__(self, in_features, out_features, abs_range=4, n_bits=8, top_k=None, joint_gradient=False,
+                 allow_bias=True):
+        super().__init__()
+        self._ctx = [None] * n_bits            # training-only stash in the reference (:131-141); unused here
+        self.joint_gradient = joint_gradient
+        self.in_features = in_features
+        self.out_features = out_features
+        self.n_bits = n_bits
+        self.abs_range = abs_range
+        self.quant_step = abs_range / (2 ** (n_bits - 1))
+        self.top_k = top_k
+        self.allow_bias = allow_bias
+        self.nested_dictionary_size = nested_sizes(in_features, n_bits)
+        self.weight = nn.Parameter(torch.empty(in_features, out_features))
+        self.weight_mirror = nn.Parameter(torch.empty(in_features, out_features))
+        self.bias = nn.Parameter(torch.zeros(out_features))
+        nn.init.xavier_uniform_(self.weight)
+        nn.init.xavier_uniform_(self.weight_mirror)
+        self._prep = PreparedCache()
+
+    # ---- prepared dictionary ---------------------------------------------------------------
+    def _levels(self):
+        dev = self.weight.device
+
+        def make():
+            starts = [0]
+            for s in self.nested_dictionary_size:
+                starts.append(starts[-1] + s)
+            factors = [2 ** (self.n_bits - i - 2) * self.quant_step for i in range(self.n_bits)]
+            return (torch.tensor(starts, dtype=torch.int32, device=dev),
+                    torch.tensor(factors, dtype=torch.float32, device=dev))
+
+        return self._prep.get("levels", (str(dev), self.n_bits, self.in_features, self.quant_step), make)
+
+    def _packed(self):
+        if not self.weight.is_cuda:
+            raise RuntimeError("QuantizedMatryoshkaDecoder runs only on CUDA (no CPU fallback)")
+        ls, lf = self._levels()
+        return self._prep.get(
+            "packed", param_key(self.weight, self.weight_mirror),
+            lambda: _lib.pack_matryoshka(self.weight.detach().contiguous(), self.weight_mirror.detach().contiguous(),
+                                         ls, lf))
+
+    def _finish(self, result, counts, overflow, B):
+        if int(overflow.item()) != 0:
+            raise RuntimeError("q_sae: a row has more active latents than the sparse decoder holds "
+                               "(1024 per sub-stream); the dense decode path is not built yet")
+        groups = counts.to(torch.float32) / float(max(B, 1))
+        return [groups[i] for i in range(self.n_bits)], [result[i] for i in range(self.n_bits)]
+
+    def forward(self, latent):
+        """Reference signature: dense latent [B, H] (sigmoid outputs) -> (latent_group, result)."""
+        if not latent.is_cuda:
+            raise RuntimeError("QuantizedMatryoshkaDecoder runs only on CUDA (no CPU fallback)")
+        active = latent > 0.5                                           # (:99)
+        B, H = active.shape
+        cnt = active.sum(1).to(torch.int32)
+        cap = max(1, int(cnt.max().item()))
+        order = torch.argsort(active.to(torch.uint8), dim=1, descending=True, stable=True)[:, :cap]
+        lists = torch.zeros((B, cap, 2), dtype=torch.int32, device=latent.device)
+        lists[:, :, 1] = order.to(torch.int32)
+        packed, scale = self._packed()
+        ls, _ = self._levels()
+        result, counts = _lib.decode_matryoshka_lists(lists, cnt.contiguous(), cap, packed, scale, ls, self.n_bits,
+                                                      H, self.out_features,
+                                                      self.bias.detach() if self.allow_bias else None)
+        return self._finish(result, counts, torch.zeros(1, dtype=torch.int32), B)
+
+
+class QuantizedMatryoshkaSAE(SparseAutoencoder):
+    def __init__(self, input_dim, hidden_dim, top_k, abs_range=4, n_bits=8, allow_bias=True):
+        super().__init__(input_dim, hidden_dim)
+        self.n_bits = n_bits
+        self.abs_range = abs_range
+        self.input_dim = input_dim
+        self.hidden_dim = hidden_dim
+        self.allow_bias = allow_bias
+        self.top_k = top_k
+        self.encoder = nn.Sequential(nn.Linear(input_dim, hidden_dim), nn.Sigmoid())
+        nn.init.xavier_uniform_(self.encoder[0].weight, gain=1)
+        nn.init.zeros_(self.encoder[0].bias)
+        self.decoder = QuantizedMatryoshkaDecoder(hidden_dim, input_dim, abs_range=abs_range, n_bits=n_bits,
+                                                  top_k=self.top_k, allow_bias=self.allow_bias)
+        self.exact = True                    # decide activity from an fp32 re-scoring (any fp32 weights)
+        self._prep = PreparedCache()
+
+    def _w_bf16(self):
+        w = self.encoder[0].weight
+        return self._prep.get("w_bf16", param_key(w), lambda: _lib.cast_bf16(w.detach().contiguous()))
+
+    def _w_norm_max(self):
+        w = self.encoder[0].weight
+        return self._prep.get("w_norm", param_key(w), lambda: _lib.max_row_norm(w.detach().contiguous()))
+
+    def encode(self, x):
+        """Dense sigmoid latents [B, H] (sae/base.py:16-19); exact fp32 CUDA-core pre-activations."""
+        x = require_cuda_input(x, self)
+        lin = self.encoder[0]
+        return torch.sigmoid(_lib.encode_dense(x, lin.weight.detach().contiguous(), lin.bias.detach()))
+
+    def forward(self, x):
+        x = require_cuda_input(x, self)
+        lin = self.encoder[0]
+        packed, scale = self.decoder._packed()
+        ls, _ = self.decoder._levels()
+        result, counts, overflow = _lib.matryoshka_forward(
+            x, self._w_bf16(), lin.bias.detach(), packed, scale, ls, self.n_bits,
+            self.decoder.bias.detach() if self.allow_bias else None,
+            w_f32=lin.weight.detach().contiguous() if self.exact else None,
+            w_norm_max=self._w_norm_max() if self.exact else None)
+        return self.decoder._finish(result, counts, overflow, x.shape[0])

@@ -407,3 +407,58 @@ def test_sample_rows_are_a_stratified_subset(cuda_device):
     rows = bs.cpu().numpy().astype(np.int64)
     assert len(set(rows.tolist())) == n
     assert np.all(rows // (H // n) == np.arange(n))   # one row from each of the n equal slices
+
+
+# ------------------------------------------------------------------------------------------
+# q_sae (Quantized Matryoshka) vs the reference's own outputs
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(cases.QSAE_CASES))
+def test_qsae_module_matches_reference(cuda_device, golden_dir, name):
+    cfg = cases.QSAE_CASES[name]
+    g = np.load(golden_dir / f"{name}.npz")
+    inp = cases.qsae_inputs(cfg)
+    m = Q.QuantizedMatryoshkaSAE(cfg["D"], cfg["H"], 32, cfg["abs_range"], cfg["n_bits"], cfg["allow_bias"])
+    m.load_state_dict({"encoder.0.weight": torch.from_numpy(inp["We"]), "encoder.0.bias": torch.from_numpy(inp["be"]),
+                       "decoder.weight": torch.from_numpy(inp["W"]), "decoder.weight_mirror": torch.from_numpy(inp["Wm"]),
+                       "decoder.bias": torch.from_numpy(inp["bd"])}, strict=True)
+    m.to(cuda_device).eval()
+    assert m.decoder.nested_dictionary_size == g["level_sizes"].tolist()
+    with torch.no_grad():
+        groups, result = m(T(inp["x"], cuda_device))
+    assert len(groups) == cfg["n_bits"] == len(result) and groups[0].dim() == 0
+    np.testing.assert_allclose(np.array([float(v) for v in groups]), g["latent_group"], rtol=1e-6, atol=1e-6)
+    for i in range(cfg["n_bits"]):
+        assert_recon_close(result[i].cpu().numpy(), g["result"][i])
+    # packed dictionary: bit exact against the oracle's T and scale
+    packed, scale = m.decoder._packed()
+    Tref, sref, _, _ = O.qsae_dictionary(inp["W"], inp["Wm"], n_bits=cfg["n_bits"], abs_range=cfg["abs_range"])
+    codes = packed.cpu().numpy().view(np.uint32)
+    ent = ((codes[:, :, None] >> (2 * np.arange(16, dtype=np.uint32))) & 3).reshape(cfg["H"], -1)
+    Tgot = np.where(ent & 1, np.where(ent & 2, -2, 2), 0).astype(np.int8)
+    assert np.array_equal(Tgot, Tref)
+    np.testing.assert_allclose(scale.cpu().numpy(), sref, rtol=2e-7, atol=0)
+    # the decoder alone, fed the dense sigmoid latents the reference passes (:219)
+    with torch.no_grad():
+        g2, r2 = m.decoder(m.encode(T(inp["x"], cuda_device)))
+    for i in range(cfg["n_bits"]):
+        assert_recon_close(r2[i].cpu().numpy(), g["result"][i])
+    np.testing.assert_allclose(np.array([float(v) for v in g2]), g["latent_group"], rtol=1e-6, atol=1e-6)
+
+
+def test_qsae_headline_shape_vs_oracle(cuda_device):
+    """512 -> 32768, n_bits = 4, encoder bias -0.543 (mean L0 ~ 34)."""
+    cfg = dict(D=512, H=32768, n_bits=4, abs_range=4.0, B=96, enc_bias=-0.543, bf16=False, allow_bias=True, seed=91)
+    inp = cases.qsae_inputs(cfg)
+    m = Q.QuantizedMatryoshkaSAE(cfg["D"], cfg["H"], 32, cfg["abs_range"], cfg["n_bits"], True)
+    m.load_state_dict({"encoder.0.weight": torch.from_numpy(inp["We"]), "encoder.0.bias": torch.from_numpy(inp["be"]),
+                       "decoder.weight": torch.from_numpy(inp["W"]), "decoder.weight_mirror": torch.from_numpy(inp["Wm"]),
+                       "decoder.bias": torch.from_numpy(inp["bd"])}, strict=True)
+    m.to(cuda_device).eval()
+    with torch.no_grad():
+        groups, result = m(T(inp["x"], cuda_device))
+    rg, rr, act = O.qsae_forward(inp["x"], inp["We"], inp["be"], inp["W"], inp["Wm"], inp["bd"],
+                                 n_bits=4, abs_range=4.0, allow_bias=True)
+    assert 20 < act.sum(1).mean() < 50
+    np.testing.assert_allclose(np.array([float(v) for v in groups]), rg, rtol=1e-6, atol=1e-6)
+    for i in range(4):
+        assert_recon_close(result[i].cpu().numpy(), rr[i])

@@ -98,6 +98,21 @@ def test_bsae_state_dict_matches_reference_fixture(golden_dir):
     assert b.topk == 32
 
 
+def test_qsae_constructor_and_state_dict(golden_dir):
+    import numpy as np
+
+    g = np.load(golden_dir / "qsae_d64_h2048.npz")
+    m = Q.QuantizedMatryoshkaSAE(64, 2048, 32, 4.0, 4)      # (input_dim, hidden_dim, top_k, abs_range, n_bits)
+    assert sorted(m.state_dict().keys()) == g["state_keys"].tolist()
+    assert [str(tuple(v.shape)) for _, v in sorted(m.state_dict().items())] == g["state_shapes"].tolist()
+    assert m.decoder.nested_dictionary_size == g["level_sizes"].tolist() == [256, 256, 512, 1024]
+    assert (m.top_k, m.abs_range, m.n_bits, m.allow_bias, m.decoder.quant_step) == (32, 4.0, 4, True, 0.5)
+    assert isinstance(m.encoder[1], torch.nn.Sigmoid)
+    assert Q.QuantizedMatryoshkaSAE(512, 32768, 32, 4, 4).decoder.nested_dictionary_size == [4096, 4096, 8192, 16384]
+    d = Q.QuantizedMatryoshkaDecoder(1024, 64)               # defaults abs_range=4, n_bits=8
+    assert d.n_bits == 8 and d.quant_step == 4 / 128 and sum(d.nested_dictionary_size) == 1024
+
+
 def test_state_dict_round_trip_strict():
     a, b = Q.BinarySAE(64, 1024, 1.5, 4), Q.BinarySAE(64, 1024, 1.5, 4)
     b.load_state_dict(a.state_dict(), strict=True)
