@@ -204,6 +204,42 @@ int qsae_decode_matryoshka_lists(const int32_t* lists, const int32_t* counts, in
                                  int n_levels, int H, int D, const float* dec_bias, float* result,
                                  unsigned long long* level_count, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * t_sae: TernarySparseAutoencoder / STEWeights (sae/ternary.py:41-52, :116-122)
+ *   h = relu(x W^T + b)  -- DENSE [B, H], returned to the caller (no top-k in the reference forward)
+ *   recon = h T^T,  T = sign(Wd) * (|Wd| >= 0.5),  Wd = decoder.weight [D, H], no decoder bias
+ * Two chained tensor-core GEMMs; the second takes h as bf16 hi (+ lo) and the exact ternary T.
+ * ------------------------------------------------------------------------------------- */
+/* STEWeights hard weights (sae/ternary.py:46-49). t_bf16 [D, H] (B operand of qsae_decode_dense /
+ * qsae_tsae_forward) and/or t_rows [H, D] int8 (gather layout for qsae_decode_int8); either may be NULL. */
+int qsae_pack_ternary(const float* w /* [D, H] */, int D, int H, float threshold, uint16_t* t_bf16,
+                      int8_t* t_rows, void* stream);
+
+/* hi = bf16(src), lo = bf16(src - hi) (lo may be NULL): hi + lo carries 16 mantissa bits of src. */
+int qsae_split_bf16(const float* src, uint16_t* hi, uint16_t* lo, size_t n, void* stream);
+
+/* out[B, N] = (a_hi (+ a_lo))[B, K] * b_t[N, K]^T (+ bias): the dense F.linear(h, hard_weights) of
+ * sae/ternary.py:52 on the tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM, split-K
+ * with a fixed-order reduction: deterministic). K % 8 == 0, N % 4 == 0, N <= 512. */
+int qsae_decode_dense_workspace_bytes(int B, int K, int N, size_t* bytes);
+int qsae_decode_dense(const uint16_t* a_hi /* [B, K] */, const uint16_t* a_lo /* [B, K] or NULL */,
+                      const uint16_t* b_t /* [N, K] */, int B, int K, int N, const float* bias /* [N] or NULL */,
+                      float* out /* [B, N] */, void* workspace, size_t workspace_bytes, void* stream);
+
+/* TernarySparseAutoencoder.forward (sae/ternary.py:116-122).
+ * exact = 0: h from the tcgen05 encoder (bf16 operands: equals the fp32 reference up to accumulation
+ *            order when x and W are bf16-representable), written as fp32 (h_out) and bf16 by TMA stores
+ *            from the GEMM epilogue; recon from one pass over bf16(h) (relative error <= 2^-9 per term).
+ * exact = 1: h from the fp32 CUDA-core encoder (any fp32 operands; not a throughput path), recon from
+ *            two accumulating passes over the hi/lo split of h (2^-17 per term).
+ * H % 8 == 0, D % 8 == 0, 8 <= D <= 512. */
+int qsae_tsae_workspace_bytes(int B, int H, int D, int exact, size_t* bytes);
+int qsae_tsae_forward(const float* x_f32, const uint16_t* w_bf16 /* [H, D], exact = 0 */,
+                      const float* w_f32 /* [H, D], exact = 1 */, const float* b_enc,
+                      const uint16_t* t_bf16 /* [D, H] from qsae_pack_ternary */, int B, int H, int D, int exact,
+                      float* h_out /* [B, H] */, float* recon /* [B, D] */, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 /* latent * mask (sae/binary.py:96-99) / zeros_like + scatter_ (sae/baseline.py:38-39):
  * dense [B, H] float32 from the sparse form. Zero-fills `dense` first. */
 int qsae_densify(const float* vals, const int32_t* idx, int B, int k, int H, float* dense,

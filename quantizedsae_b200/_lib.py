@@ -44,6 +44,12 @@ SYMBOLS = {
     "qsae_matryoshka_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "qsae_max_row_norm": (_i, [_vp, _i, _i, _vp, _vp]),
     "qsae_decode_matryoshka_lists": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "qsae_pack_ternary": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp]),
+    "qsae_split_bf16": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "qsae_decode_dense_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
+    "qsae_decode_dense": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "qsae_tsae_workspace_bytes": (_i, [_i, _i, _i, _i, C.POINTER(_sz)]),
+    "qsae_tsae_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "qsae_densify": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "qsae_bsae_plan_create": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _i, C.POINTER(_vp)]),
     "qsae_bsae_plan_destroy": (None, [_vp]),
@@ -356,3 +362,67 @@ def matryoshka_forward(x, w_bf16, b_enc, packed, scale, level_start, n_levels, d
                                          ws.numel(), _stream()))
     launch_count += 3
     return result, counts, overflow
+
+
+def pack_ternary(w: torch.Tensor, threshold: float = 0.5, want_bf16: bool = True, want_rows: bool = False):
+    """decoder.weight [D, H] -> (T bf16 [D, H] | None, T int8 rows [H, D] | None), T = sign(w) * (|w| >= thr)."""
+    global launch_count
+    _need_cuda(w)
+    D, H = w.shape
+    assert w.dtype == torch.float32
+    t_bf16 = torch.empty((D, H), dtype=torch.bfloat16, device=w.device) if want_bf16 else None
+    t_rows = torch.empty((H, D), dtype=torch.int8, device=w.device) if want_rows else None
+    check(load().qsae_pack_ternary(w.data_ptr(), D, H, float(threshold), _ptr(t_bf16), _ptr(t_rows), _stream()))
+    launch_count += 1
+    return t_bf16, t_rows
+
+
+def split_bf16(src: torch.Tensor, want_lo: bool = True):
+    global launch_count
+    _need_cuda(src)
+    assert src.dtype == torch.float32
+    hi = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    lo = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device) if want_lo else None
+    check(load().qsae_split_bf16(src.data_ptr(), hi.data_ptr(), _ptr(lo), src.numel(), _stream()))
+    launch_count += 1
+    return hi, lo
+
+
+def decode_dense(a_hi: torch.Tensor, a_lo: torch.Tensor | None, b_t: torch.Tensor, bias: torch.Tensor | None = None):
+    """out [B, N] = (a_hi (+ a_lo)) [B, K] @ b_t [N, K]^T (+ bias); bf16 operands, fp32 result."""
+    global launch_count
+    _need_cuda(a_hi, a_lo, b_t, bias)
+    B, K = a_hi.shape
+    N = b_t.shape[0]
+    assert a_hi.dtype == torch.bfloat16 and b_t.dtype == torch.bfloat16 and b_t.shape[1] == K
+    out = torch.empty((B, N), dtype=torch.float32, device=a_hi.device)
+    if B == 0:
+        return out
+    n = _sz(0)
+    check(load().qsae_decode_dense_workspace_bytes(B, K, N, C.byref(n)))
+    ws = _workspace(a_hi.device, int(n.value))
+    check(load().qsae_decode_dense(a_hi.data_ptr(), _ptr(a_lo), b_t.data_ptr(), B, K, N, _ptr(bias), out.data_ptr(),
+                                   ws.data_ptr(), ws.numel(), _stream()))
+    launch_count += 2
+    return out
+
+
+def tsae_forward(x: torch.Tensor, w_bf16: torch.Tensor | None, w_f32: torch.Tensor | None, b_enc: torch.Tensor,
+                 t_bf16: torch.Tensor, exact: bool):
+    """-> (h [B, H] f32 dense ReLU latents, recon [B, D] f32)"""
+    global launch_count
+    _need_cuda(x, w_bf16, w_f32, b_enc, t_bf16)
+    B, D = x.shape
+    H = t_bf16.shape[1]
+    h = torch.empty((B, H), dtype=torch.float32, device=x.device)
+    recon = torch.empty((B, D), dtype=torch.float32, device=x.device)
+    if B == 0:
+        return h, recon
+    n = _sz(0)
+    check(load().qsae_tsae_workspace_bytes(B, H, D, 1 if exact else 0, C.byref(n)))
+    ws = _workspace(x.device, int(n.value))
+    check(load().qsae_tsae_forward(x.data_ptr(), _ptr(w_bf16), _ptr(w_f32), b_enc.data_ptr(), t_bf16.data_ptr(), B, H, D,
+                                   1 if exact else 0, h.data_ptr(), recon.data_ptr(), ws.data_ptr(), ws.numel(),
+                                   _stream()))
+    launch_count += 4
+    return h, recon

@@ -23,6 +23,7 @@
 // The latent axis can be split over `n_splits` CTAs per row block (grid.x) to fill the 148 SMs
 // at small batch; every (split, column-half) is an independent sub-stream.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -39,7 +40,9 @@ constexpr int BM = kEncBM;         // rows of x per CTA (UMMA M)
 constexpr int BN = kEncBN;         // latents per tile (UMMA N)
 constexpr int BK = 64;             // one 128-byte swizzle atom of bf16
 constexpr int UMMA_K = 16;
-constexpr int kStages = 3;         // W ring depth
+constexpr int kStagesSparse = 3;   // W ring depth, selection epilogues
+constexpr int kStagesDense = 2;    // W ring depth when the epilogue needs a store staging area
+constexpr int kStageBytesPerWarp = 4096;  // dense epilogue: one 32 x 32 fp32 tile per epilogue warp
 constexpr int kABytesPerChunk = BM * BK * 2;   // 16 KiB
 constexpr int kBBytesPerStage = BN * BK * 2;   // 32 KiB
 constexpr int kEpiWarps = 8;
@@ -47,16 +50,19 @@ constexpr int kThreads = 128 + kEpiWarps * 32;  // warps: 0 TMA, 1 MMA, 2 TMEM a
 constexpr int kTmemCols = 512;                  // 2 accumulators x 256 columns
 
 struct SmemLayout {
-  uint32_t a_off, b_off, bias_off, share_off, bar_off, tmem_ptr_off, total;
+  uint32_t a_off, b_off, staging_off, bias_off, share_off, bar_off, tmem_ptr_off, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int k_chunks) {
+__host__ __device__ constexpr int ring_stages(bool dense) { return dense ? kStagesDense : kStagesSparse; }
+__host__ __device__ inline SmemLayout smem_layout(int k_chunks, bool dense) {
   SmemLayout L;
+  const int stages = ring_stages(dense);
   L.a_off = 0;
   L.b_off = L.a_off + k_chunks * kABytesPerChunk;
-  L.bias_off = L.b_off + kStages * kBBytesPerStage;
+  L.staging_off = L.b_off + stages * kBBytesPerStage;   // 1024-byte aligned (swizzled TMA store source)
+  L.bias_off = L.staging_off + (dense ? kEpiWarps * kStageBytesPerWarp : 0);
   L.share_off = L.bias_off + 2 * BN * 4;         // partner thresholds, 2 x 128 x bf16
   L.bar_off = L.share_off + 2 * BM * 2;
-  L.tmem_ptr_off = L.bar_off + 8 * (1 + 2 * kStages + 6);
+  L.tmem_ptr_off = L.bar_off + 8 * (1 + 2 * stages + 6);
   L.total = L.tmem_ptr_off + 16;
   return L;
 }
@@ -326,12 +332,129 @@ __device__ __forceinline__ void epilogue_loop(const EncodeLaunch& p, int n_my_ti
   }
 }
 
-template <int K_CHUNKS>
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+
+// Dense epilogue (t_sae: the reference returns the dense ReLU latents, sae/ternary.py:116-122).
+// Each epilogue warp turns its 32 rows x 32 columns of the accumulator into
+//   h fp32                 (p.dense_flags & 1)   the module's first return value
+//   h_hi = bf16(h)         (p.dense_flags & 2)   A operand of the decoder GEMM
+//   h_lo = bf16(h - h_hi)  (p.dense_flags & 4)   second A operand (h_hi + h_lo carries 16 mantissa bits)
+// staged in shared memory in the TMA swizzle pattern (bank-conflict-free 16-byte stores, lane = row)
+// and written with cp.async.bulk.tensor stores, which clip rows >= B and columns >= H.
+__device__ __forceinline__ void epilogue_dense(const EncodeLaunch& p, const CUtensorMap* t_f32,
+                                               const CUtensorMap* t_hi, const CUtensorMap* t_lo,
+                                               int n_my_tiles, int tile_begin, int m0, int e, int lane,
+                                               uint32_t tmem_base, const float* bias_smem, uint8_t* staging,
+                                               uint64_t* tmem_full, uint64_t* tmem_empty, uint64_t* bias_full) {
+  const int quad = e & 3;
+  const int half = e >> 2;
+  const int row0 = m0 + quad * 32;
+  const bool warp_live = row0 < p.B;
+  uint8_t* st = staging + e * kStageBytesPerWarp;
+  const uint32_t st_addr = smem_u32(st);
+  const uint32_t f32_row = st_addr + lane * 128;
+  const uint32_t sw128 = static_cast<uint32_t>(lane & 7) << 4;         // SWIZZLE_128B: chunk ^= row % 8
+  const uint32_t b16_row = st_addr + lane * 64;
+  const uint32_t sw64 = static_cast<uint32_t>((lane >> 1) & 3) << 4;   // SWIZZLE_64B: chunk ^= (row / 2) % 4
+  const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+  const int flags = p.dense_flags;
+
+  for (int t = 0; t < n_my_tiles; ++t) {
+    const int acc = t & 1;
+    const uint32_t ph = (t >> 1) & 1;
+    mbar_wait(&tmem_full[acc], ph);
+    mbar_wait(&bias_full[acc], ph);
+    tc_fence_after();
+    const int n_tile = (tile_begin + t) * BN + half * 128;
+    const float4* bias4 = reinterpret_cast<const float4*>(bias_smem + acc * BN + half * 128);
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(lane_taddr + acc * BN + half * 128 + c * 32, r);
+      tmem_ld_wait();
+      const int col0 = n_tile + c * 32;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = bias4[c * 8 + j];
+        v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
+        v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+        v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
+        v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+      }
+      if (p.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (!warp_live || col0 >= p.H) continue;  // warp-uniform
+      if (flags & 1) {
+        if (lane == 0) tma_store_wait_read();   // the previous store has left the staging tile
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          st_shared_v4(f32_row + ((static_cast<uint32_t>(q) << 4) ^ sw128), __float_as_uint(v[4 * q]),
+                       __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]), __float_as_uint(v[4 * q + 3]));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(t_f32, st, col0, row0);
+          tma_store_commit();
+        }
+      }
+      if (flags & 6) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = v[2 * j], b = v[2 * j + 1];
+          hi[j] = pack_bf16x2(a, b);
+          const float ah = __uint_as_float(hi[j] << 16), bh = __uint_as_float(hi[j] & 0xFFFF0000u);
+          lo[j] = pack_bf16x2(a - ah, b - bh);
+        }
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          st_shared_v4(b16_row + ((static_cast<uint32_t>(q) << 4) ^ sw64), hi[4 * q], hi[4 * q + 1], hi[4 * q + 2],
+                       hi[4 * q + 3]);
+        if (flags & 4) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            st_shared_v4(b16_row + 2048 + ((static_cast<uint32_t>(q) << 4) ^ sw64), lo[4 * q], lo[4 * q + 1],
+                         lo[4 * q + 2], lo[4 * q + 3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (flags & 2) tma_store_2d(t_hi, st, col0, row0);
+          if (flags & 4) tma_store_2d(t_lo, st + 2048, col0, row0);
+          tma_store_commit();
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+  }
+  if (lane == 0) tma_store_wait_all();
+  __syncwarp();
+}
+
+template <int K_CHUNKS, bool DENSE>
 __global__ void __launch_bounds__(kThreads, 1)
 encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
-                   const __grid_constant__ CUtensorMap tmap_w, EncodeLaunch p) {
+                   const __grid_constant__ CUtensorMap tmap_w,
+                   const __grid_constant__ CUtensorMap tmap_o32,
+                   const __grid_constant__ CUtensorMap tmap_ohi,
+                   const __grid_constant__ CUtensorMap tmap_olo, EncodeLaunch p) {
+  constexpr int kStages = ring_stages(DENSE);
   extern __shared__ __align__(1024) uint8_t smem[];
-  const SmemLayout L = smem_layout(K_CHUNKS);
+  const SmemLayout L = smem_layout(K_CHUNKS, DENSE);
   uint8_t* a_smem = smem + L.a_off;
   uint8_t* b_smem = smem + L.b_off;
   float* bias_smem = reinterpret_cast<float*>(smem + L.bias_off);
@@ -450,6 +573,10 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
   } else if (warp >= 4) {
     // ------------------------------------------------------------- epilogue / selection
     const int e = warp - 4;
+    if constexpr (DENSE) {
+      epilogue_dense(p, &tmap_o32, &tmap_ohi, &tmap_olo, n_my_tiles, tile_begin, m0, e, lane, tmem_base, bias_smem,
+                     smem + L.staging_off, tmem_full, tmem_empty, bias_full);
+    } else
     switch (p.mode) {
       case 1:
         epilogue_loop<1>(p, n_my_tiles, tile_begin, split, m0, e, lane, tmem_base, bias_smem, share,
@@ -502,34 +629,58 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
-// bf16 row-major [rows, cols] -> 2D tensor map with a {64 x box_rows} box, 128-byte swizzle
-bool make_tmap_bf16(CUtensorMap* map, const void* base, int rows, int cols, int box_rows) {
+// row-major [rows, cols] -> 2D tensor map with a {box_cols x box_rows} box
+bool make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* base, int rows, int cols,
+                  int box_cols, int box_rows, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return false;
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * elem_bytes};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(map, dtype, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
+// bf16 operand tile: {64 x box_rows} box, 128-byte swizzle
+bool make_tmap_bf16(CUtensorMap* map, const void* base, int rows, int cols, int box_rows) {
+  return make_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, BK, box_rows,
+                      CU_TENSOR_MAP_SWIZZLE_128B);
+}
 
-template <int K_CHUNKS>
-cudaError_t launch_k(const CUtensorMap& tx, const CUtensorMap& tw, const EncodeLaunch& p,
-                     cudaStream_t stream) {
-  const SmemLayout L = smem_layout(K_CHUNKS);
+template <int K_CHUNKS, bool DENSE>
+cudaError_t launch_k(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& o32, const CUtensorMap& ohi,
+                     const CUtensorMap& olo, const EncodeLaunch& p, cudaStream_t stream) {
+  const SmemLayout L = smem_layout(K_CHUNKS, DENSE);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(encode_topk_kernel<K_CHUNKS>,
+    cudaError_t e = cudaFuncSetAttribute(encode_topk_kernel<K_CHUNKS, DENSE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   dim3 grid(p.n_splits, (p.B + BM - 1) / BM);
-  encode_topk_kernel<K_CHUNKS><<<grid, kThreads, L.total, stream>>>(tx, tw, p);
+  encode_topk_kernel<K_CHUNKS, DENSE><<<grid, kThreads, L.total, stream>>>(tx, tw, o32, ohi, olo, p);
   return cudaGetLastError();
+}
+
+template <bool DENSE>
+const char* launch_any(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& o32, const CUtensorMap& ohi,
+                       const CUtensorMap& olo, const EncodeLaunch& p, cudaStream_t stream) {
+  const int kc = (p.D + BK - 1) / BK;
+  cudaError_t e;
+  switch (kc) {
+    case 1: e = launch_k<1, DENSE>(tx, tw, o32, ohi, olo, p, stream); break;
+    case 2: e = launch_k<2, DENSE>(tx, tw, o32, ohi, olo, p, stream); break;
+    case 3: e = launch_k<3, DENSE>(tx, tw, o32, ohi, olo, p, stream); break;
+    case 4: e = launch_k<4, DENSE>(tx, tw, o32, ohi, olo, p, stream); break;
+    case 5: e = launch_k<5, DENSE>(tx, tw, o32, ohi, olo, p, stream); break;
+    case 6: e = launch_k<6, DENSE>(tx, tw, o32, ohi, olo, p, stream); break;
+    case 7: e = launch_k<7, DENSE>(tx, tw, o32, ohi, olo, p, stream); break;
+    case 8: e = launch_k<8, DENSE>(tx, tw, o32, ohi, olo, p, stream); break;
+    default: return "D must be <= 512";
+  }
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
 }  // namespace
@@ -564,20 +715,29 @@ const char* encode_topk_launch(const uint16_t* x_bf16, const uint16_t* w_bf16, E
   CUtensorMap tx, tw;
   if (!make_tmap_bf16(&tx, x_bf16, p.B, p.D, BM)) return "cuTensorMapEncodeTiled(x) failed";
   if (!make_tmap_bf16(&tw, w_bf16, p.H, p.D, BN)) return "cuTensorMapEncodeTiled(W) failed";
-  const int kc = (p.D + BK - 1) / BK;
-  cudaError_t e;
-  switch (kc) {
-    case 1: e = launch_k<1>(tx, tw, p, stream); break;
-    case 2: e = launch_k<2>(tx, tw, p, stream); break;
-    case 3: e = launch_k<3>(tx, tw, p, stream); break;
-    case 4: e = launch_k<4>(tx, tw, p, stream); break;
-    case 5: e = launch_k<5>(tx, tw, p, stream); break;
-    case 6: e = launch_k<6>(tx, tw, p, stream); break;
-    case 7: e = launch_k<7>(tx, tw, p, stream); break;
-    case 8: e = launch_k<8>(tx, tw, p, stream); break;
-    default: return "D must be <= 512";
-  }
-  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+  p.dense_flags = 0;
+  return launch_any<false>(tx, tw, tx, tx, tx, p, stream);
+}
+
+const char* encode_dense_tc_launch(const uint16_t* x_bf16, const uint16_t* w_bf16, EncodeLaunch p, float* out_f32,
+                                   uint16_t* out_hi, uint16_t* out_lo, cudaStream_t stream) {
+  if ((p.H % 8) != 0) return "dense tensor-core encoder needs H % 8 == 0";
+  CUtensorMap tx, tw, o32, ohi, olo;
+  if (!make_tmap_bf16(&tx, x_bf16, p.B, p.D, BM)) return "cuTensorMapEncodeTiled(x) failed";
+  if (!make_tmap_bf16(&tw, w_bf16, p.H, p.D, BN)) return "cuTensorMapEncodeTiled(W) failed";
+  o32 = ohi = olo = tx;
+  p.dense_flags = (out_f32 ? 1 : 0) | (out_hi ? 2 : 0) | (out_lo ? 4 : 0);
+  if (p.dense_flags == 0) return "dense encoder: no output requested";
+  if (out_f32 && !make_tmap_2d(&o32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out_f32, p.B, p.H, 32, 32,
+                               CU_TENSOR_MAP_SWIZZLE_128B))
+    return "cuTensorMapEncodeTiled(h fp32) failed";
+  if (out_hi && !make_tmap_2d(&ohi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out_hi, p.B, p.H, 32, 32,
+                              CU_TENSOR_MAP_SWIZZLE_64B))
+    return "cuTensorMapEncodeTiled(h hi) failed";
+  if (out_lo && !make_tmap_2d(&olo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out_lo, p.B, p.H, 32, 32,
+                              CU_TENSOR_MAP_SWIZZLE_64B))
+    return "cuTensorMapEncodeTiled(h lo) failed";
+  return launch_any<true>(tx, tw, o32, ohi, olo, p, stream);
 }
 
 }  // namespace qsae

@@ -31,6 +31,7 @@ struct EncodeLaunch {
   void* cand;           // [B][n_splits*2][cap] {float bits, int32 column}
   int* cand_cnt;        // [B][n_splits*2]
   float* cand_thr;      // [B][n_splits*2] inclusive lower bound of the row's k_sel-th largest value
+  int dense_flags;      // dense epilogue outputs: 1 fp32, 2 bf16 hi, 4 bf16 lo (set by the launcher)
   int debug_mode;       // 0 normal; timing experiments: 1 no survivors, 2 no TMEM drain
   float* debug_z;       // optional dense [B, H] dump of the accumulator (+bias, act); diagnostics only
 };
@@ -40,6 +41,16 @@ int encode_pick_splits(int B, int H, int num_sms);
 void encode_pick_mode(int k_sel, int* mode, int* cap);
 const char* encode_topk_launch(const uint16_t* x_bf16, const uint16_t* w_bf16, EncodeLaunch p,
                                cudaStream_t stream);
+
+// dense epilogue variant (t_sae): h = act(x W^T + b) as fp32 and/or bf16 hi (+ lo) [B, H], TMA stores
+const char* encode_dense_tc_launch(const uint16_t* x_bf16, const uint16_t* w_bf16, EncodeLaunch p, float* out_f32,
+                                   uint16_t* out_hi, uint16_t* out_lo, cudaStream_t stream);
+
+// dense_decode_sm100.cu: out[B, N] = (a_hi (+ a_lo))[B, K] * b_t[N, K]^T (+ bias), bf16 in, fp32 accumulate
+int dense_decode_pick_splits(int B, int K, int num_sms);
+size_t dense_decode_workspace_bytes(int B, int K, int N, int num_sms);
+const char* dense_decode_launch(const uint16_t* a_hi, const uint16_t* a_lo, const uint16_t* b_t, int B, int K, int N,
+                                const float* bias, float* out, void* workspace, int num_sms, cudaStream_t stream);
 
 // select_topk.cu
 struct SelectLaunch {
@@ -96,6 +107,11 @@ const char* pack_bitplanes_launch(const float* logits, int H, int D, int n_bits,
 const char* dequant_soft_launch(const float* logits, int H, int D, int n_bits, float* rows,
                                 cudaStream_t stream);
 const char* transpose_launch(const float* src, int R, int C, float* dst, cudaStream_t stream);
+// src -> hi = bf16(src), lo = bf16(src - hi) (lo may be null)
+const char* split_bf16_launch(const float* src, uint16_t* hi, uint16_t* lo, size_t n, cudaStream_t stream);
+// t_sae decoder.weight [D, H] -> sign(w) * (|w| >= threshold): bf16 [D, H] and/or int8 rows [H, D]
+const char* pack_ternary_launch(const float* w, int D, int H, float threshold, uint16_t* t_bf16, int8_t* t_rows,
+                                cudaStream_t stream);
 
 // decode.cu
 const char* decode_int4_launch(const float* vals, const int32_t* idx, int B, int k,

@@ -113,6 +113,63 @@ __global__ void dequant_soft_kernel(const float* __restrict__ logits, size_t tot
   }
 }
 
+// hi = bf16(v), lo = bf16(v - hi): hi + lo carries 16 mantissa bits of v
+__global__ void split_bf16_kernel(const float* __restrict__ src, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                  size_t n) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t n4 = n / 4;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&h0);
+    o.y = *reinterpret_cast<const uint32_t*>(&h1);
+    reinterpret_cast<uint2*>(hi)[i] = o;
+    if (lo != nullptr) {
+      const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+      const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y);
+      const __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+      o.x = *reinterpret_cast<const uint32_t*>(&l0);
+      o.y = *reinterpret_cast<const uint32_t*>(&l1);
+      reinterpret_cast<uint2*>(lo)[i] = o;
+    }
+  }
+  for (size_t i = n4 * 4 + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(src[i]);
+    hi[i] = *reinterpret_cast<const uint16_t*>(&h);
+    if (lo != nullptr) {
+      const __nv_bfloat16 l = __float2bfloat16_rn(src[i] - __bfloat162float(h));
+      lo[i] = *reinterpret_cast<const uint16_t*>(&l);
+    }
+  }
+}
+
+// STEWeights hard weights (sae/ternary.py:46-49): sign(w) * (|w| >= threshold) in {-1, 0, +1}.
+// 32 x 32 tiles of w [D, H]: bf16 in place ([D, H], K-major B operand of the decoder GEMM) and
+// transposed int8 rows ([H, D], gather layout of the sparse decoder).
+__global__ void pack_ternary_kernel(const float* __restrict__ w, int D, int H, float threshold,
+                                    uint16_t* __restrict__ t_bf16, int8_t* __restrict__ t_rows) {
+  __shared__ int8_t tile[32][33];
+  const int h0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int d = d0 + i, h = h0 + threadIdx.x;
+    int8_t t = 0;
+    if (d < D && h < H) {
+      const float v = w[static_cast<size_t>(d) * H + h];
+      t = (fabsf(v) >= threshold) ? (v > 0.f ? 1 : (v < 0.f ? -1 : 0)) : 0;
+      if (t_bf16 != nullptr)
+        t_bf16[static_cast<size_t>(d) * H + h] = t == 0 ? 0x0000u : (t > 0 ? 0x3F80u : 0xBF80u);
+    }
+    tile[i][threadIdx.x] = t;
+  }
+  if (t_rows == nullptr) return;
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int h = h0 + i, d = d0 + threadIdx.x;
+    if (h < H && d < D) t_rows[static_cast<size_t>(h) * D + d] = tile[threadIdx.x][i];
+  }
+}
+
 __global__ void transpose_kernel(const float* __restrict__ src, int R, int C, float* __restrict__ dst) {
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -183,6 +240,18 @@ const char* dequant_soft_launch(const float* logits, int H, int D, int n_bits, f
 const char* sample_rows_launch(const uint16_t* w_bf16, const float* bias, int H, int D, int n_sample,
                                uint16_t* w_sample, float* b_sample, cudaStream_t stream) {
   sample_rows_kernel<<<n_sample, 128, 0, stream>>>(w_bf16, bias, H, D, n_sample, w_sample, b_sample);
+  return cuda_err(cudaGetLastError());
+}
+
+const char* split_bf16_launch(const float* src, uint16_t* hi, uint16_t* lo, size_t n, cudaStream_t stream) {
+  split_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, stream>>>(src, hi, lo, n);
+  return cuda_err(cudaGetLastError());
+}
+
+const char* pack_ternary_launch(const float* w, int D, int H, float threshold, uint16_t* t_bf16, int8_t* t_rows,
+                                cudaStream_t stream) {
+  dim3 grid((H + 31) / 32, (D + 31) / 32), block(32, 8);
+  pack_ternary_kernel<<<grid, block, 0, stream>>>(w, D, H, threshold, t_bf16, t_rows);
   return cuda_err(cudaGetLastError());
 }
 

@@ -109,6 +109,20 @@ __device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const void* de
       "l"(desc), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "l"(cache_policy)
       : "memory");
 }
+// 2D tiled store shared::cta -> global (bulk async-group completion). Rows / columns of the box
+// that fall outside the tensor are clipped by the hardware.
+__device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(desc),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk stores of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// ... and have completed entirely (writes performed)
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // L2 cache policies (createpolicy encodings used by CUTLASS' TMA::CacheHintSm90)
 constexpr uint64_t kPolicyEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kPolicyEvictFirst = 0x12F0000000000000ull;

@@ -452,6 +452,120 @@ int qsae_matryoshka_forward(const float* x_f32, const uint16_t* w_bf16, const fl
                                                                      exact, st));
 }
 
+// ---------------------------------------------------------------------------------------------
+// t_sae
+// ---------------------------------------------------------------------------------------------
+int qsae_split_bf16(const float* src, uint16_t* hi, uint16_t* lo, size_t n, void* stream) {
+  if (!src || !hi) return fail(QSAE_ERR_INVALID_ARGUMENT, "split_bf16: null pointer");
+  if (n == 0) return QSAE_OK;
+  return launch_status("split_bf16", split_bf16_launch(src, hi, lo, n, S(stream)));
+}
+
+int qsae_pack_ternary(const float* w, int D, int H, float threshold, uint16_t* t_bf16, int8_t* t_rows, void* stream) {
+  if (!w || (!t_bf16 && !t_rows)) return fail(QSAE_ERR_INVALID_ARGUMENT, "pack_ternary: null pointer");
+  if (D <= 0 || H <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "pack_ternary: bad shape");
+  return launch_status("pack_ternary", pack_ternary_launch(w, D, H, threshold, t_bf16, t_rows, S(stream)));
+}
+
+static int check_dense_decode(const char* who, int B, int K, int N) {
+  if (B < 0 || K <= 0 || N <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "%s: bad shape", who);
+  if ((K % 8) != 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "%s: the contraction length must be a multiple of 8, got %d", who, K);
+  if ((N % 4) != 0 || N > 512) return fail(QSAE_ERR_INVALID_ARGUMENT, "%s: output width must be a multiple of 4, <= 512, got %d", who, N);
+  return QSAE_OK;
+}
+
+int qsae_decode_dense_workspace_bytes(int B, int K, int N, size_t* bytes) {
+  if (!bytes) return fail(QSAE_ERR_INVALID_ARGUMENT, "workspace query: null pointer");
+  int rc = check_dense_decode("decode_dense", B, K, N);
+  if (rc != QSAE_OK) return rc;
+  *bytes = align_up(dense_decode_workspace_bytes(B > 0 ? B : 1, K, N, num_sms()), 256);
+  return QSAE_OK;
+}
+
+int qsae_decode_dense(const uint16_t* a_hi, const uint16_t* a_lo, const uint16_t* b_t, int B, int K, int N,
+                      const float* bias, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_dense_decode("decode_dense", B, K, N);
+  if (rc != QSAE_OK || B == 0) return rc;
+  if (!a_hi || !b_t || !out || !workspace) return fail(QSAE_ERR_INVALID_ARGUMENT, "decode_dense: null pointer");
+  if ((reinterpret_cast<uintptr_t>(a_hi) & 15) || (reinterpret_cast<uintptr_t>(a_lo) & 15) ||
+      (reinterpret_cast<uintptr_t>(b_t) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 15))
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "decode_dense: operands must be 16-byte aligned");
+  const size_t need = dense_decode_workspace_bytes(B, K, N, num_sms());
+  if (workspace_bytes < need) return fail(QSAE_ERR_WORKSPACE_TOO_SMALL, "decode_dense: workspace %zu < %zu bytes", workspace_bytes, need);
+  if (g_enc_ev_start) cudaEventRecord(g_enc_ev_start, S(stream));
+  rc = launch_status("dense_decode", dense_decode_launch(a_hi, a_lo, b_t, B, K, N, bias, out, workspace, num_sms(), S(stream)));
+  if (g_enc_ev_stop) cudaEventRecord(g_enc_ev_stop, S(stream));
+  return rc;
+}
+
+namespace {
+struct TsaePlan { size_t x_off, hi_off, lo_off, dec_off, total; };
+int plan_tsae(int B, int H, int D, int exact, TsaePlan* tp) {
+  if (B <= 0 || H <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "B and H must be positive (B=%d H=%d)", B, H);
+  if (D < 8 || D > 512 || (D % 8) != 0)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "D must be a multiple of 8 in [8, 512], got %d", D);
+  if ((H % 8) != 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "t_sae: hidden_dim must be a multiple of 8, got %d", H);
+  tp->x_off = 0;
+  tp->hi_off = align_up(static_cast<size_t>(B) * D * 2, 1024);
+  tp->lo_off = align_up(tp->hi_off + static_cast<size_t>(B) * H * 2, 1024);
+  tp->dec_off = exact ? align_up(tp->lo_off + static_cast<size_t>(B) * H * 2, 1024) : tp->lo_off;
+  tp->total = align_up(tp->dec_off + dense_decode_workspace_bytes(B, H, D, num_sms()), 256);
+  return QSAE_OK;
+}
+}  // namespace
+
+int qsae_tsae_workspace_bytes(int B, int H, int D, int exact, size_t* bytes) {
+  if (!bytes) return fail(QSAE_ERR_INVALID_ARGUMENT, "workspace query: null pointer");
+  TsaePlan tp;
+  int rc = plan_tsae(B, H, D, exact, &tp);
+  if (rc != QSAE_OK) return rc;
+  *bytes = tp.total;
+  return QSAE_OK;
+}
+
+int qsae_tsae_forward(const float* x_f32, const uint16_t* w_bf16, const float* w_f32, const float* b_enc,
+                      const uint16_t* t_bf16, int B, int H, int D, int exact, float* h_out, float* recon,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  if (B == 0) return QSAE_OK;
+  if (!x_f32 || !b_enc || !t_bf16 || !h_out || !recon || !workspace)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "tsae_forward: null pointer");
+  if (exact ? !w_f32 : !w_bf16) return fail(QSAE_ERR_INVALID_ARGUMENT, "tsae_forward: missing encoder weights for this mode");
+  TsaePlan tp;
+  int rc = plan_tsae(B, H, D, exact, &tp);
+  if (rc != QSAE_OK) return rc;
+  if (workspace_bytes < tp.total)
+    return fail(QSAE_ERR_WORKSPACE_TOO_SMALL, "tsae_forward: workspace %zu < %zu bytes", workspace_bytes, tp.total);
+  if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0 || (reinterpret_cast<uintptr_t>(h_out) & 15) != 0)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "tsae_forward: workspace must be 1024-byte and h_out 16-byte aligned");
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  uint16_t* x_bf16 = reinterpret_cast<uint16_t*>(ws + tp.x_off);
+  uint16_t* h_hi = reinterpret_cast<uint16_t*>(ws + tp.hi_off);
+  uint16_t* h_lo = exact ? reinterpret_cast<uint16_t*>(ws + tp.lo_off) : nullptr;
+  cudaStream_t st = S(stream);
+  if (exact) {
+    // fp32 CUDA-core encoder (any fp32 operands), then the 16-bit hi/lo split of h
+    rc = launch_status("encode_dense", encode_dense_launch(x_f32, nullptr, B, w_f32, b_enc, H, D, QSAE_ACT_RELU, h_out, st));
+    if (rc != QSAE_OK) return rc;
+    rc = launch_status("split_bf16", split_bf16_launch(h_out, h_hi, h_lo, static_cast<size_t>(B) * H, st));
+    if (rc != QSAE_OK) return rc;
+  } else {
+    rc = launch_status("cast x", cast_bf16_launch(x_f32, x_bf16, static_cast<size_t>(B) * D, st));
+    if (rc != QSAE_OK) return rc;
+    EncodeLaunch el;
+    memset(&el, 0, sizeof(el));
+    el.B = B; el.H = H; el.D = D; el.act = QSAE_ACT_RELU; el.bias = b_enc;
+    el.n_tiles = (H + kEncBN - 1) / kEncBN;
+    el.n_splits = encode_pick_splits(B, H, num_sms());
+    el.tiles_per_split = (el.n_tiles + el.n_splits - 1) / el.n_splits;
+    if (g_enc_ev_start) cudaEventRecord(g_enc_ev_start, st);
+    rc = launch_status("encode kernel (dense)", encode_dense_tc_launch(x_bf16, w_bf16, el, h_out, h_hi, nullptr, st));
+    if (g_enc_ev_stop) cudaEventRecord(g_enc_ev_stop, st);
+    if (rc != QSAE_OK) return rc;
+  }
+  return launch_status("dense_decode", dense_decode_launch(h_hi, h_lo, t_bf16, B, H, D, nullptr, recon, ws + tp.dec_off,
+                                                           num_sms(), st));
+}
+
 int qsae_encode_dense_f32(const float* x_f32, const int32_t* rows, int R, const float* w_f32,
                           const float* b_enc, int H, int D, int act, float* z, void* stream) {
   if (R == 0) return QSAE_OK;

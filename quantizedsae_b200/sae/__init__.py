@@ -3,6 +3,7 @@ from .base import SparseAutoencoder
 from .baseline import BaselineSparseAutoencoder
 from .binary import BinarySAE, binary_decoder
 from .quantized_matryoshka import QuantizedMatryoshkaDecoder, QuantizedMatryoshkaSAE
+from .ternary import STEWeights, TernarySparseAutoencoder
 
 __all__ = ["SparseAutoencoder", "BaselineSparseAutoencoder", "BinarySAE", "binary_decoder",
-           "QuantizedMatryoshkaDecoder", "QuantizedMatryoshkaSAE"]
+           "QuantizedMatryoshkaDecoder", "QuantizedMatryoshkaSAE", "STEWeights", "TernarySparseAutoencoder"]

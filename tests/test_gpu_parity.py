@@ -462,3 +462,142 @@ def test_qsae_headline_shape_vs_oracle(cuda_device):
     np.testing.assert_allclose(np.array([float(v) for v in groups]), rg, rtol=1e-6, atol=1e-6)
     for i in range(4):
         assert_recon_close(result[i].cpu().numpy(), rr[i])
+
+
+# ------------------------------------------------------------------------------------------
+# t_sae (ternary): dense ReLU latents + dense ternary decoder GEMM
+#   h (exact mode or bf16-representable inputs) ........ |dh| <= 1e-5 * max(1, |h|)
+#   recon, exact mode (hi/lo two-pass decoder) ......... atol 1e-4 * rms + rtol 1e-4
+#   recon, fast mode (one bf16 pass over h) ............ atol 8e-3 * rms + rtol 8e-3
+# ------------------------------------------------------------------------------------------
+def assert_recon_close_bf16(got, ref):
+    rms = float(np.sqrt(np.mean(np.square(ref, dtype=np.float64)))) + 1e-30
+    np.testing.assert_allclose(got, ref, rtol=8e-3, atol=8e-3 * rms)
+
+
+def test_pack_ternary_bit_exact(cuda_device):
+    rng = np.random.default_rng(5)
+    D, H = 70, 1000
+    w = (0.4824 * rng.standard_normal((D, H))).astype(np.float32)
+    w[0, :8] = [0.5, -0.5, np.nextafter(np.float32(0.5), np.float32(0)), -np.nextafter(np.float32(0.5), np.float32(0)),
+                0.0, -0.0, 3.0, -3.0]
+    t_bf16, t_rows = L.pack_ternary(T(w, cuda_device), 0.5, want_bf16=True, want_rows=True)
+    ref = O.ternarize(w)
+    assert np.array_equal(t_bf16.float().cpu().numpy().astype(np.int8), ref)
+    assert np.array_equal(t_rows.cpu().numpy(), ref.T)
+    assert ref[0, :8].tolist() == [1, -1, 0, 0, 0, 0, 1, -1]
+
+
+@pytest.mark.parametrize("B,K,N", [(128, 1024, 512), (200, 4096, 64), (77, 1000, 256), (1, 72, 8), (300, 2048, 384)])
+def test_decode_dense_vs_fp64(cuda_device, B, K, N):
+    rng = np.random.default_rng(B + K + N)
+    a = np.maximum(rng.standard_normal((B, K)), 0).astype(np.float32)
+    t = O.ternarize((0.4824 * rng.standard_normal((N, K))).astype(np.float32))
+    bias = rng.standard_normal(N).astype(np.float32)
+    ref = a.astype(np.float64) @ t.T.astype(np.float64) + bias
+    hi, lo = L.split_bf16(T(a, cuda_device))
+    tb = T(t.astype(np.float32), cuda_device).bfloat16().contiguous()
+    # hi + lo reproduces a to 2^-17
+    rec = hi.float().cpu().numpy().astype(np.float64) + lo.float().cpu().numpy()
+    assert np.all(np.abs(rec - a) <= 2.0 ** -16 * np.abs(a) + 1e-38)
+    two = L.decode_dense(hi, lo, tb, T(bias, cuda_device)).cpu().numpy()
+    assert_recon_close(two, ref.astype(np.float32))
+    one = L.decode_dense(hi, None, tb, T(bias, cuda_device)).cpu().numpy()
+    assert_recon_close_bf16(one, ref.astype(np.float32))
+    # the single pass is exact for the operand it was given: compare against bf16(a) in fp64
+    ref_hi = hi.float().cpu().numpy().astype(np.float64) @ t.T.astype(np.float64) + bias
+    assert_recon_close(one, ref_hi.astype(np.float32))
+
+
+@pytest.mark.parametrize("B,H,D", [(128, 256, 64), (200, 1000, 512), (77, 2056, 72), (1, 304, 8), (300, 4096, 512)])
+def test_dense_encoder_tma_store_epilogue(cuda_device, B, H, D):
+    """fast t_sae path: h = relu(x W^T + b) written by TMA stores as fp32 (+ bf16 for the decoder)."""
+    xn, Wn, bn = _enc_case(B, H, D, seed=B + H)
+    inp = dict(x=xn, We=Wn, be=bn)
+    rng = np.random.default_rng(3)
+    wd = (0.4824 * rng.standard_normal((D, H))).astype(np.float32)
+    We, be, x = (T(inp[k], cuda_device) for k in ("We", "be", "x"))
+    t_bf16, _ = L.pack_ternary(T(wd, cuda_device))
+    h, recon = L.tsae_forward(x, L.cast_bf16(We), None, be, t_bf16, exact=False)
+    torch.cuda.synchronize()
+    h_ref, r_ref = O.tsae_forward(inp["x"], inp["We"], inp["be"], wd)
+    assert_vals_close(h.cpu().numpy(), h_ref)
+    assert_recon_close_bf16(recon.cpu().numpy(), r_ref)
+    # the decoder consumed bf16(h) of the h this kernel produced: recompute exactly that
+    hb = h.bfloat16().float().cpu().numpy().astype(np.float64)
+    assert_recon_close(recon.cpu().numpy(), (hb @ O.ternarize(wd).T.astype(np.float64)).astype(np.float32))
+
+
+@pytest.mark.parametrize("name", list(cases.TSAE_CASES))
+def test_tsae_module_matches_reference(cuda_device, golden_dir, name):
+    cfg = cases.TSAE_CASES[name]
+    g = np.load(golden_dir / f"{name}.npz")
+    inp = cases.tsae_inputs(cfg)
+    m = Q.TernarySparseAutoencoder(cfg["D"], cfg["H"])
+    assert sorted(m.state_dict().keys()) == g["state_keys"].tolist()
+    sd = m.state_dict()
+    sd.update({"encoder.0.weight": torch.from_numpy(inp["We"]), "encoder.0.bias": torch.from_numpy(inp["be"]),
+               "decoder.weight": torch.from_numpy(inp["Wd"])})
+    m.load_state_dict(sd, strict=True)
+    m.to(cuda_device).eval()
+    assert m.topk == int(cfg["H"] * 0.002) and m.decoder.threshold == 0.5
+    with torch.no_grad():
+        h, recon = m(T(inp["x"], cuda_device))                       # exact mode (default)
+    assert tuple(h.shape) == (cfg["B"], cfg["H"]) and tuple(recon.shape) == (cfg["B"], cfg["D"])
+    assert_vals_close(h.cpu().numpy(), g["h"])
+    assert_recon_close(recon.cpu().numpy(), g["recon"])
+    assert sorted(m.state_dict().keys()) == g["state_keys_after_forward"].tolist()
+    assert np.array_equal(m.decoder.hard_weights().cpu().numpy().astype(np.int8), O.ternarize(inp["Wd"]))
+    # decoder alone on the dense latents, as callers of STEWeights use it
+    with torch.no_grad():
+        r2 = m.decoder(T(g["h"], cuda_device))
+    assert_recon_close(r2.cpu().numpy(), g["recon"])
+    if cfg["bf16"]:
+        m.exact = False
+        with torch.no_grad():
+            h3, r3 = m(T(inp["x"], cuda_device))
+        assert_vals_close(h3.cpu().numpy(), g["h"])
+        assert_recon_close_bf16(r3.cpu().numpy(), g["recon"])
+
+
+def test_tsae_topk_mode_vs_oracle(cuda_device):
+    cfg = dict(D=512, H=8192, B=64, bf16=True, seed=77)
+    inp = cases.tsae_inputs(cfg)
+    m = Q.TernarySparseAutoencoder(cfg["D"], cfg["H"])
+    sd = m.state_dict()
+    sd.update({"encoder.0.weight": torch.from_numpy(inp["We"]), "encoder.0.bias": torch.from_numpy(inp["be"]),
+               "decoder.weight": torch.from_numpy(inp["Wd"])})
+    m.load_state_dict(sd, strict=True)
+    m.to(cuda_device).eval()
+    h_ref, _ = O.tsae_forward(inp["x"], inp["We"], inp["be"], inp["Wd"])
+    with torch.no_grad():
+        lat, recon = m.forward_topk(T(inp["x"], cuda_device))
+        dense = m.apply_topk_activation(T(h_ref, cuda_device))
+    assert_topk_matches(lat.values.cpu().numpy(), lat.indices.cpu().numpy(), h_ref, m.topk)
+    rv, ri = O.tsae_topk_activation(h_ref, m.topk)
+    ref_recon = O.decode_rows(rv, ri, np.ascontiguousarray(O.ternarize(inp["Wd"]).T.astype(np.float32)), 1.0, None)
+    assert_recon_close(recon.cpu().numpy(), ref_recon)
+    assert np.array_equal(dense.cpu().numpy(), O.densify(rv, ri, cfg["H"]))
+
+
+def test_tsae_full_size_properties(cuda_device):
+    """4096 x 32768 x 512 (BASELINE config 3 per GPU): spot rows against the fp32 CUDA-core encoder,
+    fast decoder against the exact two-pass decoder, and linearity of the decoder."""
+    B, H, D = 4096, 32768, 512
+    g = torch.Generator(device=cuda_device).manual_seed(3)
+    We = ((torch.rand((H, D), device=cuda_device, generator=g) * 2 - 1) * (6.0 / (H + D)) ** 0.5).bfloat16().float()
+    be = 0.01 * torch.randn(H, device=cuda_device, generator=g)
+    Wd = 0.4824 * torch.randn((D, H), device=cuda_device, generator=g)
+    x = torch.randn((B, D), device=cuda_device, generator=g).bfloat16().float()
+    t_bf16, _ = L.pack_ternary(Wd)
+    h, recon = L.tsae_forward(x, L.cast_bf16(We), None, be, t_bf16, exact=False)
+    rows = torch.tensor([0, 1, 127, 128, 2047, 4095], dtype=torch.int32, device=cuda_device)
+    z = L.encode_dense(x, We, be, L.ACT_RELU, rows=rows)
+    assert_vals_close(h[rows.long()].cpu().numpy(), z.cpu().numpy())
+    assert float(h.min()) >= 0.0 and 0.4 < float((h > 0).float().mean()) < 0.6
+    hi, lo = L.split_bf16(h)
+    exact = L.decode_dense(hi, lo, t_bf16)
+    assert_recon_close_bf16(recon.cpu().numpy(), exact.cpu().numpy())
+    assert torch.equal(L.decode_dense(hi, None, t_bf16), recon)          # deterministic, same operand
+    ref64 = (h[:64].double() @ t_bf16.double().T).float()
+    assert_recon_close(exact[:64].cpu().numpy(), ref64.cpu().numpy())

@@ -57,6 +57,9 @@ def test_argument_validation_without_gpu():
     assert b"out of range" in lib.qsae_last_error()
     assert lib.qsae_encode_topk_workspace_bytes(128, 4096, 64, 500, 0, C.byref(n)) == -1  # k > MAX_K
     assert lib.qsae_encode_topk_workspace_bytes(4096, 32768, 512, 32, 1024, C.byref(n)) == 0 and n.value > 0
+    assert lib.qsae_tsae_workspace_bytes(128, 1004, 64, 0, C.byref(n)) == -1             # H % 8
+    assert lib.qsae_tsae_workspace_bytes(4096, 32768, 512, 1, C.byref(n)) == 0 and n.value > 2 * 4096 * 32768 * 2
+    assert lib.qsae_decode_dense_workspace_bytes(128, 1024, 514, C.byref(n)) == -1       # N % 4
     assert lib.qsae_pack_bitplanes(None, 8, 8, 4, None, None, None) == -1
     assert lib.qsae_decode_int4(None, None, 1, 1, None, 8, 8, 1.0, None, None, None) == -1
     with pytest.raises(RuntimeError):
@@ -111,6 +114,20 @@ def test_qsae_constructor_and_state_dict(golden_dir):
     assert Q.QuantizedMatryoshkaSAE(512, 32768, 32, 4, 4).decoder.nested_dictionary_size == [4096, 4096, 8192, 16384]
     d = Q.QuantizedMatryoshkaDecoder(1024, 64)               # defaults abs_range=4, n_bits=8
     assert d.n_bits == 8 and d.quant_step == 4 / 128 and sum(d.nested_dictionary_size) == 1024
+
+
+def test_tsae_constructor_and_state_dict(golden_dir):
+    import numpy as np
+
+    g = np.load(golden_dir / "tsae_d64_h2048.npz")
+    m = Q.TernarySparseAutoencoder(64, 2048)
+    assert sorted(m.state_dict().keys()) == g["state_keys"].tolist()
+    assert [str(tuple(m.state_dict()[k].shape)) for k in sorted(m.state_dict())] == g["state_shapes"].tolist()
+    assert m.topk == 4 and m.decoder.threshold == 0.5
+    assert isinstance(m.encoder[1], torch.nn.ReLU) and tuple(m.decoder.weight.shape) == (64, 2048)
+    assert float(m.decoder.mask.min()) == 1.0 and m.decoder.input_activations is None
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(4, 64))
 
 
 def test_state_dict_round_trip_strict():
