@@ -240,6 +240,38 @@ int qsae_tsae_forward(const float* x_f32, const uint16_t* w_bf16 /* [H, D], exac
                       float* h_out /* [B, H] */, float* recon /* [B, D] */, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Dictionary-sharded b_sae (2^20-latent dictionaries over G GPUs). Shard g owns the
+ * latents [g * shard_latents, (g + 1) * shard_latents) of nn.Linear / binary_decoder
+ * (sae/binary.py:82-84, :24-38); x is replicated. Per forward:
+ *   qsae_encode_topk on the shard          -> local top-k (values, shard-local indices)
+ *   qsae_pack_candidates + all-gather      -> [G][B][k] {value, local index} entries on every rank
+ *   qsae_merge_candidates                  -> global top-k (value desc, global index asc), identical on
+ *                                             every rank: Tensor.topk over the full dictionary (:94)
+ *   qsae_decode_int4_range                 -> partial reconstruction from the winners this shard owns
+ *   reduce-scatter(sum) of the partials    -> rows of latent.matmul(int_weights) (:38)
+ * The two collectives are issued by the host side (NCCL via torch.distributed); these entry points
+ * are the compute steps between them.
+ * ------------------------------------------------------------------------------------- */
+/* (vals, idx)[n] -> n interleaved {float32 bits, int32 index} 8-byte entries (one all-gather operand) */
+int qsae_pack_candidates(const float* vals, const int32_t* idx, size_t n, void* out, void* stream);
+
+int qsae_merge_candidates_workspace_bytes(int B, size_t* bytes);
+/* cand_all: [n_shards][B][k_in] entries, shard-local indices; entry (s, b, j) stands for the global
+ * latent s * shard_latents + index. out_*: [B, k_out], k_out <= n_shards * k_in, k_out <= QSAE_MAX_K. */
+int qsae_merge_candidates(const void* cand_all, int n_shards, int B, int k_in, int shard_latents, int k_out,
+                          float* out_vals, int32_t* out_idx, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* qsae_decode_int4 / qsae_decode_int8 restricted to the latents [idx_begin, idx_begin + shard_latents)
+ * held in `packed_shard` / `rows_shard` (global indices in idx; others are skipped). */
+int qsae_decode_int4_range(const float* vals, const int32_t* idx, int B, int k, const uint8_t* packed_shard,
+                           int shard_latents, int idx_begin, int D, float scale, const float* bias,
+                           float* recon, void* stream);
+int qsae_decode_int8_range(const float* vals, const int32_t* idx, int B, int k, const int8_t* rows_shard,
+                           int shard_latents, int idx_begin, int D, float scale, const float* bias,
+                           float* recon, void* stream);
+
 /* latent * mask (sae/binary.py:96-99) / zeros_like + scatter_ (sae/baseline.py:38-39):
  * dense [B, H] float32 from the sparse form. Zero-fills `dense` first. */
 int qsae_densify(const float* vals, const int32_t* idx, int B, int k, int H, float* dense,

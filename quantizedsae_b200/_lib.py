@@ -50,6 +50,11 @@ SYMBOLS = {
     "qsae_decode_dense": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "qsae_tsae_workspace_bytes": (_i, [_i, _i, _i, _i, C.POINTER(_sz)]),
     "qsae_tsae_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "qsae_pack_candidates": (_i, [_vp, _vp, _sz, _vp, _vp]),
+    "qsae_merge_candidates_workspace_bytes": (_i, [_i, C.POINTER(_sz)]),
+    "qsae_merge_candidates": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "qsae_decode_int4_range": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "qsae_decode_int8_range": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
     "qsae_densify": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "qsae_bsae_plan_create": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _i, C.POINTER(_vp)]),
     "qsae_bsae_plan_destroy": (None, [_vp]),
@@ -426,3 +431,45 @@ def tsae_forward(x: torch.Tensor, w_bf16: torch.Tensor | None, w_f32: torch.Tens
                                    _stream()))
     launch_count += 4
     return h, recon
+
+
+def pack_candidates(vals: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """(vals, idx) [B, k] -> [B, k, 2] int32 entries {float bits, index}: one all-gather operand."""
+    global launch_count
+    _need_cuda(vals, idx)
+    out = torch.empty(tuple(vals.shape) + (2,), dtype=torch.int32, device=vals.device)
+    check(load().qsae_pack_candidates(vals.data_ptr(), idx.data_ptr(), vals.numel(), out.data_ptr(), _stream()))
+    launch_count += 1
+    return out
+
+
+def merge_candidates(cand_all: torch.Tensor, shard_latents: int, k_out: int):
+    """cand_all [G, B, k_in, 2] int32 (gathered pack_candidates outputs) -> global (vals, idx) [B, k_out]."""
+    global launch_count
+    _need_cuda(cand_all)
+    G, B, k_in, two = cand_all.shape
+    assert two == 2 and cand_all.dtype == torch.int32
+    vals = torch.empty((B, k_out), dtype=torch.float32, device=cand_all.device)
+    idx = torch.empty((B, k_out), dtype=torch.int32, device=cand_all.device)
+    if B == 0:
+        return vals, idx
+    n = _sz(0)
+    check(load().qsae_merge_candidates_workspace_bytes(B, C.byref(n)))
+    ws = _workspace(cand_all.device, int(n.value))
+    check(load().qsae_merge_candidates(cand_all.data_ptr(), G, B, k_in, shard_latents, k_out, vals.data_ptr(),
+                                       idx.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    launch_count += 2
+    return vals, idx
+
+
+def decode_range(vals, idx, dict_shard, shard_latents: int, idx_begin: int, D: int, scale: float, bias, n_bits: int):
+    """Partial reconstruction from the winners inside [idx_begin, idx_begin + shard_latents)."""
+    global launch_count
+    _need_cuda(vals, idx, dict_shard, bias)
+    B, k = vals.shape
+    recon = torch.empty((B, D), dtype=torch.float32, device=vals.device)
+    fn = load().qsae_decode_int4_range if n_bits <= 4 else load().qsae_decode_int8_range
+    check(fn(vals.data_ptr(), idx.data_ptr(), B, k, dict_shard.data_ptr(), shard_latents, idx_begin, D, float(scale),
+             _ptr(bias), recon.data_ptr(), _stream()))
+    launch_count += 1
+    return recon

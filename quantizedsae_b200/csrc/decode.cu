@@ -27,7 +27,7 @@ template <int NCH>
 __global__ void __launch_bounds__(kDecWarps * 32)
 decode_int4_kernel(const float* __restrict__ vals, const int32_t* __restrict__ idx, int B, int k,
                    const uint32_t* __restrict__ packed, int H, int D, float scale,
-                   const float* __restrict__ bias, float* __restrict__ recon) {
+                   const float* __restrict__ bias, float* __restrict__ recon, int idx_offset) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * kDecWarps + warp;
   if (row >= B) return;
@@ -42,7 +42,8 @@ decode_int4_kernel(const float* __restrict__ vals, const int32_t* __restrict__ i
   for (int base = 0; base < k; base += 32) {
     const int e = base + lane;
     const float my_v = (e < k) ? vals[static_cast<size_t>(row) * k + e] : 0.f;
-    const int my_i = (e < k) ? idx[static_cast<size_t>(row) * k + e] : -1;
+    // dictionary shards: only entries inside [idx_offset, idx_offset + H) belong to this dictionary
+    const int my_i = (e < k) ? idx[static_cast<size_t>(row) * k + e] - idx_offset : -1;
     const int m = min(32, k - base);
 #pragma unroll 4
     for (int j = 0; j < m; ++j) {
@@ -80,7 +81,7 @@ template <typename T, int NCH>
 __global__ void __launch_bounds__(kDecWarps * 32)
 decode_rows_kernel(const float* __restrict__ vals, const int32_t* __restrict__ idx, int B, int k,
                    const T* __restrict__ rows, int H, int D, float scale,
-                   const float* __restrict__ bias, float* __restrict__ recon) {
+                   const float* __restrict__ bias, float* __restrict__ recon, int idx_offset) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * kDecWarps + warp;
   if (row >= B) return;
@@ -92,7 +93,8 @@ decode_rows_kernel(const float* __restrict__ vals, const int32_t* __restrict__ i
   for (int base = 0; base < k; base += 32) {
     const int e = base + lane;
     const float my_v = (e < k) ? vals[static_cast<size_t>(row) * k + e] : 0.f;
-    const int my_i = (e < k) ? idx[static_cast<size_t>(row) * k + e] : -1;
+    // dictionary shards: only entries inside [idx_offset, idx_offset + H) belong to this dictionary
+    const int my_i = (e < k) ? idx[static_cast<size_t>(row) * k + e] - idx_offset : -1;
     const int m = min(32, k - base);
 #pragma unroll 4
     for (int j = 0; j < m; ++j) {
@@ -141,19 +143,34 @@ __global__ void scatter_kernel(const float* __restrict__ vals, const int32_t* __
   }
 }
 
+__global__ void pack_candidates_kernel(const float* __restrict__ vals, const int32_t* __restrict__ idx, size_t n,
+                                       uint2* __restrict__ out) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += stride)
+    out[e] = make_uint2(__float_as_uint(vals[e]), static_cast<uint32_t>(idx[e]));
+}
+
 }  // namespace
+
+const char* pack_candidates_launch(const float* vals, const int32_t* idx, size_t n, void* out, cudaStream_t stream) {
+  if (n == 0) return nullptr;
+  size_t g = (n + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  pack_candidates_kernel<<<static_cast<int>(g), 256, 0, stream>>>(vals, idx, n, reinterpret_cast<uint2*>(out));
+  return cuda_err(cudaGetLastError());
+}
 
 const char* decode_int4_launch(const float* vals, const int32_t* idx, int B, int k,
                                const uint8_t* packed, int H, int D, float scale, const float* bias,
-                               float* recon, cudaStream_t stream) {
+                               float* recon, int idx_offset, cudaStream_t stream) {
   const int blocks = (B + kDecWarps - 1) / kDecWarps;
   const uint32_t* p32 = reinterpret_cast<const uint32_t*>(packed);
   if (D <= 256)
-    decode_int4_kernel<1><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, p32, H, D, scale, bias, recon);
+    decode_int4_kernel<1><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, p32, H, D, scale, bias, recon, idx_offset);
   else if (D <= 512)
-    decode_int4_kernel<2><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, p32, H, D, scale, bias, recon);
+    decode_int4_kernel<2><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, p32, H, D, scale, bias, recon, idx_offset);
   else if (D <= 1024)
-    decode_int4_kernel<4><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, p32, H, D, scale, bias, recon);
+    decode_int4_kernel<4><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, p32, H, D, scale, bias, recon, idx_offset);
   else
     return "decode_int4: D must be <= 1024";
   return cuda_err(cudaGetLastError());
@@ -162,16 +179,16 @@ const char* decode_int4_launch(const float* vals, const int32_t* idx, int B, int
 template <typename T>
 static const char* decode_rows_dispatch(const float* vals, const int32_t* idx, int B, int k,
                                         const T* rows, int H, int D, float scale, const float* bias,
-                                        float* recon, cudaStream_t stream) {
+                                        float* recon, int idx_offset, cudaStream_t stream) {
   const int blocks = (B + kDecWarps - 1) / kDecWarps;
   if (D <= 128)
-    decode_rows_kernel<T, 1><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, rows, H, D, scale, bias, recon);
+    decode_rows_kernel<T, 1><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, rows, H, D, scale, bias, recon, idx_offset);
   else if (D <= 256)
-    decode_rows_kernel<T, 2><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, rows, H, D, scale, bias, recon);
+    decode_rows_kernel<T, 2><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, rows, H, D, scale, bias, recon, idx_offset);
   else if (D <= 512)
-    decode_rows_kernel<T, 4><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, rows, H, D, scale, bias, recon);
+    decode_rows_kernel<T, 4><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, rows, H, D, scale, bias, recon, idx_offset);
   else if (D <= 1024)
-    decode_rows_kernel<T, 8><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, rows, H, D, scale, bias, recon);
+    decode_rows_kernel<T, 8><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, rows, H, D, scale, bias, recon, idx_offset);
   else
     return "decode_rows: D must be <= 1024";
   return cuda_err(cudaGetLastError());
@@ -179,14 +196,14 @@ static const char* decode_rows_dispatch(const float* vals, const int32_t* idx, i
 
 const char* decode_int8_launch(const float* vals, const int32_t* idx, int B, int k,
                                const int8_t* rows, int H, int D, float scale, const float* bias,
-                               float* recon, cudaStream_t stream) {
-  return decode_rows_dispatch<int8_t>(vals, idx, B, k, rows, H, D, scale, bias, recon, stream);
+                               float* recon, int idx_offset, cudaStream_t stream) {
+  return decode_rows_dispatch<int8_t>(vals, idx, B, k, rows, H, D, scale, bias, recon, idx_offset, stream);
 }
 
 const char* decode_f32_launch(const float* vals, const int32_t* idx, int B, int k, const float* rows,
-                              int H, int D, float scale, const float* bias, float* recon,
+                              int H, int D, float scale, const float* bias, float* recon, int idx_offset,
                               cudaStream_t stream) {
-  return decode_rows_dispatch<float>(vals, idx, B, k, rows, H, D, scale, bias, recon, stream);
+  return decode_rows_dispatch<float>(vals, idx, B, k, rows, H, D, scale, bias, recon, idx_offset, stream);
 }
 
 const char* densify_launch(const float* vals, const int32_t* idx, int B, int k, int H, float* dense,

@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 #include "ptx_sm100.cuh"
@@ -42,7 +43,7 @@ constexpr int BK = 64;             // one 128-byte swizzle atom of bf16
 constexpr int UMMA_K = 16;
 constexpr int kStagesSparse = 3;   // W ring depth, selection epilogues
 constexpr int kStagesDense = 2;    // W ring depth when the epilogue needs a store staging area
-constexpr int kStageBytesPerWarp = 4096;  // dense epilogue: one 32 x 32 fp32 tile per epilogue warp
+constexpr int kStageBytesPerWarp = 4096;  // dense epilogue: two 32-row x 64-byte store staging tiles per warp
 constexpr int kABytesPerChunk = BM * BK * 2;   // 16 KiB
 constexpr int kBBytesPerStage = BN * BK * 2;   // 32 KiB
 constexpr int kEpiWarps = 8;
@@ -345,8 +346,34 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 //   h fp32                 (p.dense_flags & 1)   the module's first return value
 //   h_hi = bf16(h)         (p.dense_flags & 2)   A operand of the decoder GEMM
 //   h_lo = bf16(h - h_hi)  (p.dense_flags & 4)   second A operand (h_hi + h_lo carries 16 mantissa bits)
-// staged in shared memory in the TMA swizzle pattern (bank-conflict-free 16-byte stores, lane = row)
-// and written with cp.async.bulk.tensor stores, which clip rows >= B and columns >= H.
+// Every output leaves through cp.async.bulk.tensor stores (which clip rows >= B and columns >= H)
+// from 2 KiB staging tiles of 32 rows x 64 bytes, written in the SWIZZLE_64B pattern so the
+// lane-per-row 16-byte shared stores are bank-conflict free. A warp alternates between two staging
+// tiles: before refilling one it only waits for the store issued two groups earlier
+// (wait_group.read 1), so staging, TMA reads and the next TMEM drain overlap.
+struct DenseStager {
+  uint32_t row_addr[2];   // this lane's 64-byte row in staging tile 0 / 1
+  const uint8_t* tile[2];
+  uint32_t sw64;          // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) % 4
+  int buf;
+  int lane;
+  __device__ __forceinline__ void put(const CUtensorMap* tmap, const uint32_t (&w)[16], int col, int row) {
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      st_shared_v4(row_addr[buf] + ((static_cast<uint32_t>(q) << 4) ^ sw64), w[4 * q], w[4 * q + 1], w[4 * q + 2],
+                   w[4 * q + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmap, tile[buf], col, row);
+      tma_store_commit();
+    }
+    buf ^= 1;
+  }
+};
+
 __device__ __forceinline__ void epilogue_dense(const EncodeLaunch& p, const CUtensorMap* t_f32,
                                                const CUtensorMap* t_hi, const CUtensorMap* t_lo,
                                                int n_my_tiles, int tile_begin, int m0, int e, int lane,
@@ -357,11 +384,14 @@ __device__ __forceinline__ void epilogue_dense(const EncodeLaunch& p, const CUte
   const int row0 = m0 + quad * 32;
   const bool warp_live = row0 < p.B;
   uint8_t* st = staging + e * kStageBytesPerWarp;
-  const uint32_t st_addr = smem_u32(st);
-  const uint32_t f32_row = st_addr + lane * 128;
-  const uint32_t sw128 = static_cast<uint32_t>(lane & 7) << 4;         // SWIZZLE_128B: chunk ^= row % 8
-  const uint32_t b16_row = st_addr + lane * 64;
-  const uint32_t sw64 = static_cast<uint32_t>((lane >> 1) & 3) << 4;   // SWIZZLE_64B: chunk ^= (row / 2) % 4
+  DenseStager stg;
+  stg.tile[0] = st;
+  stg.tile[1] = st + 2048;
+  stg.row_addr[0] = smem_u32(st) + lane * 64;
+  stg.row_addr[1] = stg.row_addr[0] + 2048;
+  stg.sw64 = static_cast<uint32_t>((lane >> 1) & 3) << 4;
+  stg.buf = 0;
+  stg.lane = lane;
   const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
   const int flags = p.dense_flags;
 
@@ -379,62 +409,41 @@ __device__ __forceinline__ void epilogue_dense(const EncodeLaunch& p, const CUte
       tmem_ld_32x32b_x32(lane_taddr + acc * BN + half * 128 + c * 32, r);
       tmem_ld_wait();
       const int col0 = n_tile + c * 32;
-      float v[32];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 b = bias4[c * 8 + j];
-        v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
-        v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
-        v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
-        v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+        r[4 * j + 0] = __float_as_uint(__uint_as_float(r[4 * j + 0]) + b.x);
+        r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + b.y);
+        r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + b.z);
+        r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + b.w);
       }
       if (p.act == 1) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]), 0.f));
       }
       if (!warp_live || col0 >= p.H) continue;  // warp-uniform
       if (flags & 1) {
-        if (lane == 0) tma_store_wait_read();   // the previous store has left the staging tile
-        __syncwarp();
+        uint32_t w[16];
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          st_shared_v4(f32_row + ((static_cast<uint32_t>(q) << 4) ^ sw128), __float_as_uint(v[4 * q]),
-                       __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]), __float_as_uint(v[4 * q + 3]));
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(t_f32, st, col0, row0);
-          tma_store_commit();
+        for (int j = 0; j < 16; ++j) w[j] = r[j];
+        stg.put(t_f32, w, col0, row0);
+        if (col0 + 16 < p.H) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) w[j] = r[16 + j];
+          stg.put(t_f32, w, col0 + 16, row0);
         }
       }
       if (flags & 6) {
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float a = v[2 * j], b = v[2 * j + 1];
+          const float a = __uint_as_float(r[2 * j]), b = __uint_as_float(r[2 * j + 1]);
           hi[j] = pack_bf16x2(a, b);
           const float ah = __uint_as_float(hi[j] << 16), bh = __uint_as_float(hi[j] & 0xFFFF0000u);
           lo[j] = pack_bf16x2(a - ah, b - bh);
         }
-        if (lane == 0) tma_store_wait_read();
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          st_shared_v4(b16_row + ((static_cast<uint32_t>(q) << 4) ^ sw64), hi[4 * q], hi[4 * q + 1], hi[4 * q + 2],
-                       hi[4 * q + 3]);
-        if (flags & 4) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            st_shared_v4(b16_row + 2048 + ((static_cast<uint32_t>(q) << 4) ^ sw64), lo[4 * q], lo[4 * q + 1],
-                         lo[4 * q + 2], lo[4 * q + 3]);
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          if (flags & 2) tma_store_2d(t_hi, st, col0, row0);
-          if (flags & 4) tma_store_2d(t_lo, st + 2048, col0, row0);
-          tma_store_commit();
-        }
+        if (flags & 2) stg.put(t_hi, hi, col0, row0);
+        if (flags & 4) stg.put(t_lo, lo, col0, row0);
       }
     }
     tc_fence_before();
@@ -728,8 +737,9 @@ const char* encode_dense_tc_launch(const uint16_t* x_bf16, const uint16_t* w_bf1
   o32 = ohi = olo = tx;
   p.dense_flags = (out_f32 ? 1 : 0) | (out_hi ? 2 : 0) | (out_lo ? 4 : 0);
   if (p.dense_flags == 0) return "dense encoder: no output requested";
-  if (out_f32 && !make_tmap_2d(&o32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out_f32, p.B, p.H, 32, 32,
-                               CU_TENSOR_MAP_SWIZZLE_128B))
+  if (const char* m = getenv("QSAE_DENSE_FLAGS_MASK")) p.dense_flags &= atoi(m);  // timing experiments only
+  if (out_f32 && !make_tmap_2d(&o32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out_f32, p.B, p.H, 16, 32,
+                               CU_TENSOR_MAP_SWIZZLE_64B))
     return "cuTensorMapEncodeTiled(h fp32) failed";
   if (out_hi && !make_tmap_2d(&ohi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out_hi, p.B, p.H, 32, 32,
                               CU_TENSOR_MAP_SWIZZLE_64B))

@@ -66,6 +66,10 @@ struct SelectLaunch {
   int32_t* out_flags;     // [B] or null
   int* rescue_count;      // prior mode: rows whose prior threshold failed the count check ...
   int32_t* rescue_rows;   // ... are appended here (capacity B) and their output left to the rescue kernel
+  // Layout of the survivor lists: list (row, s) starts at entry (row * row_stride + s * sub_stride) * cap.
+  // 0 / 0 = the fused encoder's layout [B][nsub][cap]. Gathered per-shard candidates are [nsub][B][cap].
+  long long row_stride, sub_stride;
+  int sub_col_offset;     // column of an entry of list s is stored_col + s * sub_col_offset (dictionary shards)
 };
 
 // rescue.cu: exact per-row top-k for the rows listed by the merge kernel (persistent small grid,
@@ -114,15 +118,18 @@ const char* pack_ternary_launch(const float* w, int D, int H, float threshold, u
                                 cudaStream_t stream);
 
 // decode.cu
+// idx_offset: the dictionary holds latents [idx_offset, idx_offset + H); other entries are skipped
 const char* decode_int4_launch(const float* vals, const int32_t* idx, int B, int k,
                                const uint8_t* packed, int H, int D, float scale, const float* bias,
-                               float* recon, cudaStream_t stream);
+                               float* recon, int idx_offset, cudaStream_t stream);
 const char* decode_int8_launch(const float* vals, const int32_t* idx, int B, int k,
                                const int8_t* rows, int H, int D, float scale, const float* bias,
-                               float* recon, cudaStream_t stream);
+                               float* recon, int idx_offset, cudaStream_t stream);
 const char* decode_f32_launch(const float* vals, const int32_t* idx, int B, int k, const float* rows,
-                              int H, int D, float scale, const float* bias, float* recon,
+                              int H, int D, float scale, const float* bias, float* recon, int idx_offset,
                               cudaStream_t stream);
+// (vals, idx) [n] -> interleaved {float bits, column} entries, the survivor-list format of the merge kernels
+const char* pack_candidates_launch(const float* vals, const int32_t* idx, size_t n, void* out, cudaStream_t stream);
 const char* densify_launch(const float* vals, const int32_t* idx, int B, int k, int H, float* dense,
                            cudaStream_t stream);
 

@@ -614,21 +614,82 @@ int qsae_decode_int4(const float* vals, const int32_t* idx, int B, int k, const 
                      int D, float scale, const float* bias, float* recon, void* stream) {
   int rc = check_decode("decode_int4", vals, idx, packed, recon, B, k, H, D, 8);
   if (rc != QSAE_OK || B == 0) return rc;
-  return launch_status("decode_int4", decode_int4_launch(vals, idx, B, k, packed, H, D, scale, bias, recon, S(stream)));
+  return launch_status("decode_int4", decode_int4_launch(vals, idx, B, k, packed, H, D, scale, bias, recon, 0, S(stream)));
 }
 
 int qsae_decode_int8(const float* vals, const int32_t* idx, int B, int k, const int8_t* rows, int H,
                      int D, float scale, const float* bias, float* recon, void* stream) {
   int rc = check_decode("decode_int8", vals, idx, rows, recon, B, k, H, D, 4);
   if (rc != QSAE_OK || B == 0) return rc;
-  return launch_status("decode_int8", decode_int8_launch(vals, idx, B, k, rows, H, D, scale, bias, recon, S(stream)));
+  return launch_status("decode_int8", decode_int8_launch(vals, idx, B, k, rows, H, D, scale, bias, recon, 0, S(stream)));
 }
 
 int qsae_decode_rows_f32(const float* vals, const int32_t* idx, int B, int k, const float* rows, int H,
                          int D, float scale, const float* bias, float* recon, void* stream) {
   int rc = check_decode("decode_rows_f32", vals, idx, rows, recon, B, k, H, D, 4);
   if (rc != QSAE_OK || B == 0) return rc;
-  return launch_status("decode_rows_f32", decode_f32_launch(vals, idx, B, k, rows, H, D, scale, bias, recon, S(stream)));
+  return launch_status("decode_rows_f32", decode_f32_launch(vals, idx, B, k, rows, H, D, scale, bias, recon, 0, S(stream)));
+}
+
+// ---------------------------------------------------------------------------------------------
+// dictionary-sharded b_sae: merge of gathered per-shard candidates, range-restricted decode
+// ---------------------------------------------------------------------------------------------
+int qsae_pack_candidates(const float* vals, const int32_t* idx, size_t n, void* out, void* stream) {
+  if (n == 0) return QSAE_OK;
+  if (!vals || !idx || !out) return fail(QSAE_ERR_INVALID_ARGUMENT, "pack_candidates: null pointer");
+  return launch_status("pack_candidates", pack_candidates_launch(vals, idx, n, out, S(stream)));
+}
+
+int qsae_merge_candidates_workspace_bytes(int B, size_t* bytes) {
+  if (!bytes || B < 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "merge_candidates workspace: bad argument");
+  *bytes = align_up(256 + static_cast<size_t>(B > 0 ? B : 1) * 4, 256);
+  return QSAE_OK;
+}
+
+int qsae_merge_candidates(const void* cand_all, int n_shards, int B, int k_in, int shard_latents, int k_out,
+                          float* out_vals, int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B == 0) return QSAE_OK;
+  if (!cand_all || !out_vals || !out_idx || !workspace) return fail(QSAE_ERR_INVALID_ARGUMENT, "merge_candidates: null pointer");
+  if (n_shards < 1 || n_shards > 32 || k_in < 1 || k_out < 1 || shard_latents < 1)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "merge_candidates: need 1 <= n_shards <= 32, k_in, k_out >= 1");
+  if (k_out > kMaxK) return fail(QSAE_ERR_INVALID_ARGUMENT, "k=%d exceeds QSAE_MAX_K=%d", k_out, kMaxK);
+  if (static_cast<long long>(n_shards) * k_in < k_out)
+    return fail(QSAE_ERR_K_OUT_OF_RANGE, "selected index k out of range (k=%d > %d candidates)", k_out, n_shards * k_in);
+  size_t need = 0;
+  qsae_merge_candidates_workspace_bytes(B, &need);
+  if (workspace_bytes < need) return fail(QSAE_ERR_WORKSPACE_TOO_SMALL, "merge_candidates: workspace %zu < %zu", workspace_bytes, need);
+  cudaStream_t st = S(stream);
+  int* counters = static_cast<int*>(workspace);
+  int32_t* ovf_rows = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(workspace) + 256);
+  cudaError_t ce = cudaMemsetAsync(counters, 0, 2 * sizeof(int), st);
+  if (ce != cudaSuccess) return fail(QSAE_ERR_CUDA, "merge_candidates: %s", cudaGetErrorString(ce));
+  SelectLaunch sl;
+  memset(&sl, 0, sizeof(sl));
+  sl.B = B; sl.H = n_shards * shard_latents; sl.k_sel = k_out; sl.k_out = k_out; sl.nsub = n_shards; sl.cap = k_in;
+  sl.cand = cand_all;                 // [n_shards][B][k_in] entries, every list full
+  sl.row_stride = 1; sl.sub_stride = B; sl.sub_col_offset = shard_latents;
+  sl.out_vals = out_vals; sl.out_idx = out_idx;
+  int rc = launch_status("select_small kernel", select_small_launch(sl, counters + 1, ovf_rows, st));
+  if (rc != QSAE_OK) return rc;
+  return launch_status("select_topk list kernel", select_topk_list_launch(sl, counters + 1, ovf_rows, num_sms(), st));
+}
+
+int qsae_decode_int4_range(const float* vals, const int32_t* idx, int B, int k, const uint8_t* packed_shard,
+                           int shard_latents, int idx_begin, int D, float scale, const float* bias, float* recon,
+                           void* stream) {
+  int rc = check_decode("decode_int4_range", vals, idx, packed_shard, recon, B, k, shard_latents, D, 8);
+  if (rc != QSAE_OK || B == 0) return rc;
+  return launch_status("decode_int4", decode_int4_launch(vals, idx, B, k, packed_shard, shard_latents, D, scale, bias, recon,
+                                                         idx_begin, S(stream)));
+}
+
+int qsae_decode_int8_range(const float* vals, const int32_t* idx, int B, int k, const int8_t* rows_shard,
+                           int shard_latents, int idx_begin, int D, float scale, const float* bias, float* recon,
+                           void* stream) {
+  int rc = check_decode("decode_int8_range", vals, idx, rows_shard, recon, B, k, shard_latents, D, 4);
+  if (rc != QSAE_OK || B == 0) return rc;
+  return launch_status("decode_int8", decode_int8_launch(vals, idx, B, k, rows_shard, shard_latents, D, scale, bias, recon,
+                                                         idx_begin, S(stream)));
 }
 
 int qsae_densify(const float* vals, const int32_t* idx, int B, int k, int H, float* dense, void* stream) {

@@ -15,6 +15,16 @@ namespace {
 constexpr int kMaxSelWarps = 4;   // dense_candidates_kernel: rows per block
 constexpr int kSelThreads = 256;  // select_topk_kernel: one block per row
 
+// index of survivor list (row, s); cand_cnt == nullptr means every list holds exactly `cap` entries
+__device__ __forceinline__ size_t list_slot(const SelectLaunch& p, int row, int s) {
+  const long long rs = p.row_stride ? p.row_stride : p.nsub;
+  const long long ss = p.sub_stride ? p.sub_stride : 1;
+  return static_cast<size_t>(row * rs + s * ss);
+}
+__device__ __forceinline__ int list_count(const SelectLaunch& p, size_t slot) {
+  return p.cand_cnt ? min(p.cand_cnt[slot], p.cap) : p.cap;
+}
+
 __device__ __forceinline__ void atomic_min_float_key(unsigned* addr, float v) { atomicMin(addr, float_to_key(v)); }
 __device__ __forceinline__ void atomic_max_float_key(unsigned* addr, float v) { atomicMax(addr, float_to_key(v)); }
 
@@ -43,16 +53,17 @@ __device__ __forceinline__ void select_row_block(const SelectLaunch& p, int row,
   float thr_row = -INFINITY;
   if (p.cand_thr != nullptr)
     for (int s = 0; s < p.nsub; ++s)
-      thr_row = fmaxf(thr_row, p.cand_thr[static_cast<size_t>(row) * p.nsub + s]);
+      thr_row = fmaxf(thr_row, p.cand_thr[list_slot(p, row, s)]);
   __syncthreads();
 
   // ---- gather survivors >= thr_row (order is irrelevant: the composite keys are unique)
   const uint2* cand = reinterpret_cast<const uint2*>(p.cand);
   constexpr int BATCH = 8;
   for (int s = warp; s < p.nsub; s += nwarps) {
-    const size_t slot = static_cast<size_t>(row) * p.nsub + s;
-    const int c = min(p.cand_cnt[slot], p.cap);
+    const size_t slot = list_slot(p, row, s);
+    const int c = list_count(p, slot);
     const uint2* src = cand + slot * p.cap;
+    const uint32_t col_add = static_cast<uint32_t>(s) * static_cast<uint32_t>(p.sub_col_offset);
     for (int base = 0; base < c; base += 32 * BATCH) {
       uint2 t[BATCH];
 #pragma unroll
@@ -69,7 +80,7 @@ __device__ __forceinline__ void select_row_block(const SelectLaunch& p, int row,
           int pos = 0;
           if (lane == 0) pos = atomicAdd(&s_n, __popc(b));
           pos = __shfl_sync(full, pos, 0) + __popc(b & lt_mask);
-          if (keep) keys[pos] = make_sort_key(__uint_as_float(t[i].x), t[i].y);
+          if (keep) keys[pos] = make_sort_key(__uint_as_float(t[i].x), t[i].y + col_add);
         }
       }
     }
@@ -281,8 +292,7 @@ select_small_kernel(SelectLaunch p, int ksort, int* ovf_count, int32_t* ovf_rows
   uint64_t* stage = stage_all[warp];
 
   // ---- counts and offsets of the row's sub-streams (nsub <= 32)
-  const size_t slot0 = static_cast<size_t>(row) * p.nsub;
-  const int my_c = (lane < p.nsub) ? min(p.cand_cnt[slot0 + lane], p.cap) : 0;
+  const int my_c = (lane < p.nsub) ? list_count(p, list_slot(p, row, lane)) : 0;
   int incl = my_c;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -306,11 +316,12 @@ select_small_kernel(SelectLaunch p, int ksort, int* ovf_count, int32_t* ovf_rows
   for (int s = 0; s < p.nsub; ++s) {
     const int c = __shfl_sync(full, my_c, s);
     const int off = __shfl_sync(full, incl, s) - c;
-    const uint2* src = cand + (slot0 + s) * p.cap;
+    const uint2* src = cand + list_slot(p, row, s) * p.cap;
+    const uint32_t col_add = static_cast<uint32_t>(s) * static_cast<uint32_t>(p.sub_col_offset);
 #pragma unroll 4
     for (int e = lane; e < c; e += 32) {
       const uint2 t = src[e];
-      stage[off + e] = make_sort_key(__uint_as_float(t.x), t.y);
+      stage[off + e] = make_sort_key(__uint_as_float(t.x), t.y + col_add);
     }
   }
   __syncwarp();

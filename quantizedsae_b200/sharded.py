@@ -1,0 +1,230 @@
+"""Dictionary-sharded b_sae for 2^20-latent dictionaries (BASELINE config 5).
+
+The reference BinarySAE (sae/binary.py:73-103) keeps the whole dictionary in one process. Here rank
+g of G owns the latents [g*H/G, (g+1)*H/G): its slice of encoder.0.weight / bias and of the bit-plane
+logits decoder.weight; decoder.bias and the input batch x are replicated. One forward is
+
+    local fused encoder + top-k over the shard  (tcgen05 kernel, shard-local indices)
+    all-gather of the (value, index) candidates  -> [G, B, k] on every rank            (collective 1)
+    merge to the global top-k, (value desc, global index asc): identical on every rank
+    sparse decode of the winners this shard owns -> partial reconstruction [B, D]
+    reduce-scatter(sum) of the partials          -> this rank's B/G rows of the result (collective 2)
+
+which equals the reference forward on the concatenated dictionary: topk over all H latents
+(:94) and latent.matmul(int_weights) (:38) split by rows of int_weights.
+
+The collectives go through torch.distributed (NCCL over NVLink on the B200 box; gloo in the CPU
+tests). The compute steps are injected as `ops`: `CudaShardOps` (libqsae_b200.so, the product) is the
+default; the CPU tests pass a numpy implementation to exercise the choreography under gloo. There is
+no CPU fallback in the product: CudaShardOps raises on non-CUDA tensors.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .sae.base import PreparedCache, param_key
+from .sparse import SparseLatents
+
+
+@dataclass(frozen=True)
+class ShardPlan:
+    """Pure host-side partition arithmetic (covered by the CPU tests)."""
+    hidden_dim: int
+    world_size: int
+    rank: int
+
+    def __post_init__(self):
+        if self.world_size < 1 or not (0 <= self.rank < self.world_size):
+            raise ValueError(f"bad rank {self.rank} / world size {self.world_size}")
+        if self.hidden_dim % self.world_size != 0:
+            raise ValueError(f"hidden_dim {self.hidden_dim} is not divisible by the world size {self.world_size}")
+
+    @property
+    def shard_latents(self) -> int:
+        return self.hidden_dim // self.world_size
+
+    @property
+    def latent_begin(self) -> int:
+        return self.rank * self.shard_latents
+
+    def latent_range(self, rank: int | None = None) -> tuple:
+        r = self.rank if rank is None else rank
+        return r * self.shard_latents, (r + 1) * self.shard_latents
+
+    def k_local(self, k: int) -> int:
+        """Candidates each shard contributes: its own top-min(k, shard size) contains every global winner it owns."""
+        return min(k, self.shard_latents)
+
+    def padded_batch(self, batch: int) -> int:
+        """reduce-scatter needs equal row blocks: the batch is padded to a multiple of the world size."""
+        return -(-batch // self.world_size) * self.world_size
+
+    def row_range(self, batch: int, rank: int | None = None) -> tuple:
+        """Rows of the (unpadded) batch whose reconstruction lands on `rank` after the reduce-scatter."""
+        r = self.rank if rank is None else rank
+        per = self.padded_batch(batch) // self.world_size
+        return min(batch, r * per), min(batch, (r + 1) * per)
+
+    def shard_state_dict(self, full: dict, n_bits: int) -> dict:
+        """Slice a full BinarySAE state_dict (sae/binary.py layout) down to this rank's shard."""
+        a, b = self.latent_range()
+        return {"encoder.0.weight": full["encoder.0.weight"][a:b].clone(),
+                "encoder.0.bias": full["encoder.0.bias"][a:b].clone(),
+                "decoder.weight": full["decoder.weight"][a:b].clone(),
+                "decoder.bias": full["decoder.bias"].clone()}
+
+
+class CudaShardOps:
+    """The compute steps on libqsae_b200.so."""
+
+    def __init__(self, module: "DictionaryShardedBinarySAE"):
+        self.m = module
+        self._prep = PreparedCache()
+
+    def _w_bf16(self):
+        w = self.m.encoder[0].weight
+        return self._prep.get("w_bf16", param_key(w), lambda: _lib.cast_bf16(w.detach().contiguous()))
+
+    def _sample(self):
+        lin = self.m.encoder[0]
+        return self._prep.get("sample", param_key(lin.weight, lin.bias),
+                              lambda: _lib.prepare_sample(self._w_bf16(), lin.bias.detach()))
+
+    def _packed(self):
+        w = self.m.decoder_weight
+        if not w.is_cuda:
+            raise RuntimeError("DictionaryShardedBinarySAE runs only on CUDA (no CPU fallback)")
+        return self._prep.get("packed", param_key(w),
+                              lambda: _lib.pack_bitplanes(w.detach(), self.m.input_dim, self.m.n_bits))
+
+    def local_candidates(self, x: torch.Tensor, k_local: int) -> torch.Tensor:
+        """-> [B, k_local, 2] int32 entries {value bits, shard-local index}"""
+        if not x.is_cuda:
+            raise RuntimeError("DictionaryShardedBinarySAE runs only on CUDA (no CPU fallback)")
+        lin = self.m.encoder[0]
+        w32 = lin.weight.detach().contiguous()
+        vals, idx, _ = _lib.encode_topk(x, self._w_bf16(), w32 if self.m.exact else None, lin.bias.detach(), k_local,
+                                        _lib.ACT_NONE, self.m.exact, sample=self._sample())
+        return _lib.pack_candidates(vals, idx)
+
+    def merge(self, cand_all: torch.Tensor, shard_latents: int, k: int):
+        return _lib.merge_candidates(cand_all, shard_latents, k)
+
+    def decode_partial(self, vals, idx, plan: ShardPlan, with_bias: bool) -> torch.Tensor:
+        packed, _, gap = self._packed()
+        if gap > self.m.polar_tol:
+            raise RuntimeError("dictionary-sharded b_sae serves the packed (polarised / hard) dictionary only; "
+                               f"max |sigmoid(w) - bit| = {gap:.3g} on this shard")
+        return _lib.decode_range(vals, idx, packed, plan.shard_latents, plan.latent_begin, self.m.input_dim,
+                                 self.m.quantization_step, self.m.decoder_bias.detach() if with_bias else None,
+                                 self.m.n_bits)
+
+    def polarize_numerator(self) -> float:
+        """sum over the shard of p (1 - p) 2^i (sae/binary.py:41-42 before the mean)."""
+        w = self.m.decoder_weight
+        return self._packed()[1] * w.numel()
+
+
+class DictionaryShardedBinarySAE(nn.Module):
+    """Rank-local shard of BinarySAE(input_dim, hidden_dim, gamma, n_bits) (sae/binary.py:73).
+
+    state_dict keys are the reference's, with the latent axis sliced: encoder.0.weight [H/G, D],
+    encoder.0.bias [H/G], decoder.weight [H/G, D*n_bits], decoder.bias [D] (replicated).
+    forward(x) -> (SparseLatents over all H latents, recon rows owned by this rank [B/G, D] or the
+    gathered [B, D] when `gather_output`, polarize_loss)."""
+
+    def __init__(self, input_dim, hidden_dim, gamma=4.0, n_bits=8, *, rank=None, world_size=None,
+                 process_group=None, ops=None):
+        super().__init__()
+        import torch.distributed as dist
+
+        self._dist = dist
+        self.group = process_group
+        if world_size is None:
+            world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        if rank is None:
+            rank = dist.get_rank(process_group) if dist.is_initialized() else 0
+        self.plan = ShardPlan(hidden_dim, world_size, rank)
+        self.input_dim, self.hidden_dim, self.n_bits, self.gamma = input_dim, hidden_dim, n_bits, gamma
+        self.quantization_step = gamma / (2 ** (n_bits - 1))
+        self.k = 0.002
+        hs = self.plan.shard_latents
+        self.encoder = nn.Sequential(nn.Linear(input_dim, hs))
+        self.decoder = nn.Module()
+        self.decoder.weight = nn.Parameter(torch.empty(hs, input_dim * n_bits))
+        self.decoder.bias = nn.Parameter(torch.zeros(input_dim))
+        nn.init.xavier_uniform_(self.encoder[0].weight, gain=1)
+        nn.init.zeros_(self.encoder[0].bias)
+        nn.init.kaiming_normal_(self.decoder.weight)
+        self.exact = True
+        self.gather_output = False
+        self.polar_tol = 1e-6
+        # ops=False defers the choice (tests install their own backend after construction)
+        self.ops = CudaShardOps(self) if ops is None else (ops or None)
+
+    @property
+    def decoder_weight(self):
+        return self.decoder.weight
+
+    @property
+    def decoder_bias(self):
+        return self.decoder.bias
+
+    def top_k(self) -> int:
+        return int(self.hidden_dim * self.k)          # over the FULL dictionary, as sae/binary.py:94
+
+    # ---- collectives (world size 1 degenerates to local views) -------------------------------
+    def _all_gather(self, t: torch.Tensor) -> torch.Tensor:
+        G = self.plan.world_size
+        if G == 1:
+            return t.unsqueeze(0)
+        out = torch.empty((G * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        self._dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        return out.view((G,) + tuple(t.shape))
+
+    def _reduce_scatter_rows(self, partial: torch.Tensor) -> torch.Tensor:
+        G = self.plan.world_size
+        if G == 1:
+            return partial
+        B, D = partial.shape
+        Bp = self.plan.padded_batch(B)
+        if Bp != B:
+            partial = torch.cat([partial, partial.new_zeros((Bp - B, D))], 0)
+        out = torch.empty((Bp // G, D), dtype=partial.dtype, device=partial.device)
+        self._dist.reduce_scatter_tensor(out, partial.contiguous(), op=self._dist.ReduceOp.SUM, group=self.group)
+        a, b = self.plan.row_range(B)
+        return out[: b - a]
+
+    def polarize_loss(self, like: torch.Tensor) -> torch.Tensor:
+        num = torch.tensor([self.ops.polarize_numerator()], dtype=torch.float64, device=like.device)
+        if self.plan.world_size > 1:
+            self._dist.all_reduce(num, group=self.group)
+        total = self.hidden_dim * self.input_dim * self.n_bits
+        return (num[0] / total).to(torch.float32)
+
+    # ---- forward ------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor):
+        if x.dim() != 2 or x.shape[1] != self.input_dim:
+            raise RuntimeError(f"expected a [batch, {self.input_dim}] matrix, got shape {tuple(x.shape)}")
+        x = x.contiguous().float()
+        k = self.top_k()
+        if k > self.hidden_dim:
+            raise RuntimeError(f"selected index k out of range (k={k} > H={self.hidden_dim})")
+        plan = self.plan
+        cand = self.ops.local_candidates(x, plan.k_local(k))                  # [B, k_loc, 2]
+        cand_all = self._all_gather(cand)                                     # [G, B, k_loc, 2]
+        vals, idx = self.ops.merge(cand_all, plan.shard_latents, k)           # global top-k, same on all ranks
+        partial = self.ops.decode_partial(vals, idx, plan, with_bias=(plan.rank == 0))
+        rows = self._reduce_scatter_rows(partial)
+        if self.gather_output and plan.world_size > 1:
+            B = x.shape[0]
+            per = plan.padded_batch(B) // plan.world_size
+            if rows.shape[0] != per:
+                rows = torch.cat([rows, rows.new_zeros((per - rows.shape[0], rows.shape[1]))], 0)
+            rows = self._all_gather(rows).reshape(-1, rows.shape[1])[:B]
+        latents = SparseLatents(vals, idx, (x.shape[0], self.hidden_dim))
+        return latents, rows, self.polarize_loss(x)

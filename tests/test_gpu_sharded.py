@@ -1,0 +1,126 @@
+"""GPU parity of the dictionary-sharded b_sae (C ABI: qsae_pack_candidates, qsae_merge_candidates,
+qsae_decode_int4_range). On one GPU the G shards are evaluated one after the other and the gathered
+candidate tensor is assembled by hand (the collectives are covered by tests/test_sharded_gloo.py and,
+when the box has >= 2 GPUs, by the NCCL test below). Indices bit-exact, values 1e-5, recon 1e-4."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import qsae_oracle as O
+from quantizedsae_b200 import _lib as L
+from quantizedsae_b200.sharded import DictionaryShardedBinarySAE, ShardPlan
+from tests.sharded_common import full_state_dict, sharded_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _recon_close(got, ref):
+    rms = float(np.sqrt(np.mean(np.square(ref, dtype=np.float64)))) + 1e-30
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-4 * rms)
+
+
+@pytest.mark.parametrize("G,D,H,B,k", [(4, 64, 2048, 37, 4), (8, 512, 16384, 130, 32), (2, 256, 8192, 64, 65),
+                                       (8, 64, 4096, 20, 200), (8, 512, 65536, 96, 128)])
+def test_virtual_shards_match_full_dictionary(cuda_device, G, D, H, B, k):
+    cfg, inp = sharded_case(D=D, H=H, B=B, seed=G + k)
+    dev = cuda_device
+    x = torch.from_numpy(inp["x"]).to(dev)
+    bd = torch.from_numpy(inp["bd"]).to(dev)
+    qstep = cfg["gamma"] / 2 ** (cfg["n_bits"] - 1)
+    cands, packs = [], []
+    for g in range(G):
+        plan = ShardPlan(H, G, g)
+        a, b = plan.latent_range()
+        We = torch.from_numpy(inp["We"][a:b]).to(dev)
+        be = torch.from_numpy(inp["be"][a:b]).to(dev)
+        kl = plan.k_local(k)
+        w_bf16 = L.cast_bf16(We)
+        vals, idx, _ = L.encode_topk(x, w_bf16, None, be, kl, sample=L.prepare_sample(w_bf16, be))
+        assert int(idx.min()) >= 0 and int(idx.max()) < plan.shard_latents          # shard-local indices
+        cands.append(L.pack_candidates(vals, idx))
+        packs.append(L.pack_bitplanes(torch.from_numpy(inp["logits"][a:b]).to(dev), D, cfg["n_bits"])[0])
+    cand_all = torch.stack(cands, 0).contiguous()                                    # what the all-gather delivers
+    gv, gi = L.merge_candidates(cand_all, H // G, k)
+    rv, ri, rr, _ = O.bsae_forward(inp["x"], inp["We"], inp["be"], inp["logits"], inp["bd"], n_bits=cfg["n_bits"],
+                                   gamma=cfg["gamma"], k=k, mode="hard")
+    assert np.array_equal(gi.cpu().numpy(), ri)
+    assert np.all(np.abs(gv.cpu().numpy() - rv) <= 1e-5 * np.maximum(1.0, np.abs(rv)))
+    total = torch.zeros((B, D), device=dev)
+    for g in range(G):
+        part = L.decode_range(gv, gi, packs[g], H // G, g * (H // G), D, qstep, bd if g == 0 else None, cfg["n_bits"])
+        total += part                                                                # stands in for the reduce-scatter
+    _recon_close(total.cpu().numpy(), rr)
+    # ownership: the partial of shard g only depends on winners inside its range
+    g = G - 1
+    masked = torch.where((gi >= g * (H // G)) & (gi < (g + 1) * (H // G)), gi, torch.full_like(gi, -1))
+    p1 = L.decode_range(gv, masked, packs[g], H // G, g * (H // G), D, qstep, None, cfg["n_bits"])
+    p2 = L.decode_range(gv, gi, packs[g], H // G, g * (H // G), D, qstep, None, cfg["n_bits"])
+    assert torch.equal(p1, p2)
+
+
+def test_world_size_one_module_equals_bsae(cuda_device):
+    cfg, inp = sharded_case(D=64, H=4096, B=50)
+    m = DictionaryShardedBinarySAE(cfg["D"], cfg["H"], cfg["gamma"], cfg["n_bits"], rank=0, world_size=1)
+    m.load_state_dict(full_state_dict(inp), strict=True)
+    m.to(cuda_device).eval()
+    with torch.no_grad():
+        lat, rows, pol = m(torch.from_numpy(inp["x"]).to(cuda_device))
+    k = int(cfg["H"] * 0.002)
+    rv, ri, rr, rp = O.bsae_forward(inp["x"], inp["We"], inp["be"], inp["logits"], inp["bd"], n_bits=cfg["n_bits"],
+                                    gamma=cfg["gamma"], k=k, mode="hard")
+    assert np.array_equal(lat.indices.cpu().numpy(), ri)
+    _recon_close(rows.cpu().numpy(), rr)
+    assert float(pol) == rp == 0.0
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _nccl_worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        cfg, inp = sharded_case(D=512, H=32768, B=203, seed=5)
+        m = DictionaryShardedBinarySAE(cfg["D"], cfg["H"], cfg["gamma"], cfg["n_bits"])
+        m.load_state_dict(m.plan.shard_state_dict(full_state_dict(inp), cfg["n_bits"]), strict=True)
+        m.to(dev).eval()
+        m.k = 2 ** -10
+        with torch.no_grad():
+            lat, rows, pol = m(torch.from_numpy(inp["x"]).to(dev))
+        torch.cuda.synchronize()
+        out[rank] = (lat.values.cpu().numpy(), lat.indices.cpu().numpy(), rows.cpu().numpy(), float(pol),
+                     m.plan.row_range(cfg["B"]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_dictionary_sharded_forward_under_nccl(cuda_device):
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus N)")
+    import torch.multiprocessing as mp
+
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_nccl_worker, args=(world, port, out), nprocs=world, join=True)
+        res = {r: out[r] for r in range(world)}
+    cfg, inp = sharded_case(D=512, H=32768, B=203, seed=5)
+    rv, ri, rr, rp = O.bsae_forward(inp["x"], inp["We"], inp["be"], inp["logits"], inp["bd"], n_bits=cfg["n_bits"],
+                                    gamma=cfg["gamma"], k=32, mode="hard")
+    for r in range(world):
+        v, i, rows, pol, (a, b) = res[r]
+        assert np.array_equal(i, ri)
+        assert np.all(np.abs(v - rv) <= 1e-5 * np.maximum(1.0, np.abs(rv)))
+        _recon_close(rows, rr[a:b])
+        assert pol == rp
