@@ -44,6 +44,10 @@ def parse():
     ap.add_argument("--k", type=int, default=32, help="latents kept per row (model.k = k / 32768)")
     ap.add_argument("--cpu-batch", type=int, default=4096, help="rows per step of the CPU arm / cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", default="batch-sharded", choices=["batch-sharded", "dict-sharded"],
+                    help="dict-sharded: BASELINE config 5, b_sae 512->2^20 with the dictionary split over the GPUs "
+                         "(NCCL all-gather of top-k candidates + reduce-scatter of partial reconstructions)")
+    ap.add_argument("--hidden", type=int, default=2 ** 20, help="dictionary size of the dict-sharded variant")
     return ap.parse_args()
 
 
@@ -303,6 +307,86 @@ def run_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_dict_sharded(args, rank, world, local_rank):
+    """BASELINE config 5: one 2^20-latent dictionary split over the ranks; x replicated; strong scaling."""
+    import torch
+
+    from quantizedsae_b200 import _lib as L
+    from quantizedsae_b200.sharded import DictionaryShardedBinarySAE
+
+    dist = None
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=device)
+    L.check(L.load().qsae_check_device())
+    Hh, B, k = args.hidden, min(args.batch, 4096) if args.batch == 65536 else args.batch, args.k
+    with torch.device(device):
+        m = DictionaryShardedBinarySAE(D, Hh, GAMMA, N_BITS, rank=rank, world_size=world)
+    g = torch.Generator(device=device).manual_seed(100 + rank)
+    with torch.no_grad():
+        m.encoder[0].weight.copy_(m.encoder[0].weight.bfloat16().float())
+        hs = m.plan.shard_latents
+        for a in range(0, hs, 65536):          # polarised logits, generated in slices
+            b = min(hs, a + 65536)
+            m.decoder.weight[a:b] = torch.where(torch.rand((b - a, D * N_BITS), device=device, generator=g) < 0.5, 110.0, -110.0)
+        m.decoder.bias.copy_(torch.randn(D, device=device, generator=torch.Generator(device=device).manual_seed(7)))
+    m.eval()
+    m.exact = False
+    m.k = k / Hh
+    gx = torch.Generator(device=device).manual_seed(1000)     # the same x on every rank (replicated input)
+    xs = [torch.randn((B, D), device=device, generator=gx).bfloat16().float() for _ in range(3)]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(max(3, args.warmup)):
+            m(xs[i % 3])
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        launches0 = L.launch_count
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(args.steps):
+            lat, rows, _ = m(xs[i % 3])
+        ev1.record()
+        barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = L.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([elapsed_ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t[0])
+    if rank == 0:
+        peaks = load_peaks()
+        flops_per_gpu = 2.0 * B * (Hh // world) * D
+        ms = elapsed_ms / args.steps
+        print(json.dumps({
+            "metric": f"b_sae 512->{Hh} 4-bit dictionary-sharded fwd tokens/s", "value": B * args.steps / (elapsed_ms * 1e-3),
+            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"b_sae input_dim=512 hidden_dim={Hh} n_bits=4 gamma=4.0 k={k} forward, batch {B} "
+                                   f"replicated, dictionary split over {world} GPU(s)",
+                       "l2": f"encoder shard {(Hh // world) * D * 2 / 1e6:.0f} MB bf16 per GPU streams from HBM every step (> 126 MB L2 when > 1); 3 rotating inputs",
+                       "parallelism": f"dictionary-sharded x{world}: NCCL all-gather of [B,k] candidates, reduce-scatter of [B,512] partials"},
+            "roofline": {"bound": "tensor", "kernel": "encode_topk_kernel<8> over the local shard", "achieved": flops_per_gpu / (ms * 1e-3) / 1e12,
+                         "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": flops_per_gpu / (ms * 1e-3) / 1e12 / peaks["tflops"],
+                         "traffic": None, "note": "whole step time used (upper bound on kernel time): fraction is a lower bound",
+                         "peak_source": peaks["source"]},
+            "gpu_launches": launches, "clocks": clocks}), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -316,8 +400,12 @@ def main():
         port = os.environ.get("MASTER_PORT", "29531")
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", port, __file__, "--gpus", str(args.gpus),
-               "--steps", str(args.steps), "--warmup", str(args.warmup), "--batch", str(args.batch), "--k", str(args.k)]
+               "--steps", str(args.steps), "--warmup", str(args.warmup), "--batch", str(args.batch), "--k", str(args.k),
+               "--variant", args.variant, "--hidden", str(args.hidden)]
         raise SystemExit(subprocess.call(cmd))
+    if args.variant == "dict-sharded":
+        run_dict_sharded(args, rank, world, local_rank)
+        return
     run_b200(args, rank, world, local_rank)
 
 

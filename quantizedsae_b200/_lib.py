@@ -228,7 +228,7 @@ def encode_topk(x: torch.Tensor, w_bf16: torch.Tensor, w_f32: torch.Tensor | Non
     check(load().qsae_encode_topk(x.data_ptr(), w_bf16.data_ptr(), _ptr(w_f32), b_enc.data_ptr(), _ptr(w_s),
                                   _ptr(b_s), n_s, B, H, D, k, act, 1 if exact else 0, vals.data_ptr(),
                                   idx.data_ptr(), _ptr(flags), ws.data_ptr(), ws.numel(), _stream()))
-    launch_count += 3 if n_s == 0 else 7
+    launch_count += 3 if n_s == 0 else 8
     return vals, idx, flags
 
 

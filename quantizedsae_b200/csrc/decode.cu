@@ -4,7 +4,8 @@
 // sae/baseline.py:29): only the k selected dictionary rows are touched. One warp per token row;
 // the 32 lanes read one dictionary row as a single contiguous, vectorised request (int4: 4 B per
 // lane = 128 B per 256 features; fp32: 16 B per lane = 512 B per 128 features), so every gather
-// is fully coalesced. Memory-bound by construction: the figure of merit is achieved GB/s.
+// is fully coalesced. The packed dictionaries are L2 resident at H = 32768; see DESIGN.md for the
+// measured bound of each variant.
 // Also: densify (sparse -> dense [B, H], sae/binary.py:96-99).
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -17,13 +18,19 @@ namespace {
 
 constexpr int kDecWarps = 4;
 
-// sign-extended nibble j (0..7) of a 32-bit word
-__device__ __forceinline__ float nibble_f(uint32_t w, int j) {
-  return static_cast<float>(static_cast<int32_t>(w << (28 - 4 * j)) >> 28);
-}
-
 // NCH = number of 256-feature chunks a lane accumulates (D <= 256 * NCH)
-template <int NCH>
+//
+// Exact integer accumulation. The kernel is bound by instruction issue, not by memory (the packed
+// dictionary is L2 resident), and int -> float conversion of every nibble was half of the issue slots.
+// Instead the row's k values are converted ONCE to fixed point, v_j = round(v_j * 2^S) with S chosen
+// from max_j |v_j| so that sum_j 15 |v_j| 2^S < 2^30, and every dictionary nibble contributes one
+// integer multiply-add: acc[d] += u'_jd * vfix_j with u' = w + 8 in [0, 15] (w ^ 8 on the two's
+// complement nibble). The bias of 8 leaves with one correction per row, acc[d] - 8 sum_j vfix_j, and a
+// single int -> float conversion per output feature follows. The sum is exact in integers (order
+// independent, deterministic); the only rounding is that of v_j to >= 18 fractional bits of max|v|.
+// WPL = 32-bit words (8 features each) per lane, read as one vector load: lane l owns the features
+// [8 WPL l, 8 WPL (l + 1)) -- D <= 256 WPL. FULL: D == 256 WPL exactly, no per-word guards.
+template <int WPL, bool FULL>
 __global__ void __launch_bounds__(kDecWarps * 32)
 decode_int4_kernel(const float* __restrict__ vals, const int32_t* __restrict__ idx, int B, int k,
                    const uint32_t* __restrict__ packed, int H, int D, float scale,
@@ -33,42 +40,92 @@ decode_int4_kernel(const float* __restrict__ vals, const int32_t* __restrict__ i
   if (row >= B) return;
   const unsigned full = 0xffffffffu;
   const int words_per_row = D >> 3;
-  float acc[NCH][8];
+  const int w0 = lane * WPL;                      // first word of this lane
+  const float* vrow = vals + static_cast<size_t>(row) * k;
+  const int32_t* irow = idx + static_cast<size_t>(row) * k;
+
+  // ---- scale of the row: max |v| over the entries that belong to this dictionary
+  float amax = 0.f;
+  bool bad = false;
+  for (int e = lane; e < k; e += 32) {
+    const int i = irow[e] - idx_offset;   // dictionary shards: only [idx_offset, idx_offset + H) is ours
+    if (i >= 0 && i < H) {
+      const float v = vrow[e];
+      bad |= !(fabsf(v) <= 3.0e38f);      // NaN or infinity
+      amax = fmaxf(amax, fabsf(v));
+    }
+  }
 #pragma unroll
-  for (int c = 0; c < NCH; ++c)
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(full, amax, o));
+  bad = __any_sync(full, bad);
+  int klog = 0;
+  while ((1 << klog) < k) ++klog;
+  const int e2 = max(static_cast<int>((__float_as_uint(amax) >> 23) & 0xFF) - 127, -100);  // amax < 2^(e2 + 1)
+  const int S = min(26 - klog - 1 - e2, 120);                                              // |v| 2^S < 2^(26 - klog)
+  const float to_fixed = __uint_as_float(static_cast<uint32_t>(S + 127) << 23);
+  const float from_fixed = __uint_as_float(static_cast<uint32_t>(127 - S) << 23);
+
+  int acc[WPL][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
+  for (int c = 0; c < WPL; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[c][j] = 0;
+  int vsum = 0;
 
   for (int base = 0; base < k; base += 32) {
     const int e = base + lane;
-    const float my_v = (e < k) ? vals[static_cast<size_t>(row) * k + e] : 0.f;
-    // dictionary shards: only entries inside [idx_offset, idx_offset + H) belong to this dictionary
-    const int my_i = (e < k) ? idx[static_cast<size_t>(row) * k + e] - idx_offset : -1;
+    int my_i = (e < k) ? irow[e] - idx_offset : -1;
+    const bool mine = my_i >= 0 && my_i < H;
+    // entries outside this dictionary contribute nothing: value 0, row 0
+    const int my_f = mine ? __float2int_rn(vrow[e] * to_fixed) : 0;
+    my_i = mine ? my_i : 0;
     const int m = min(32, k - base);
 #pragma unroll 4
     for (int j = 0; j < m; ++j) {
-      const float v = __shfl_sync(full, my_v, j);
+      const int vf = __shfl_sync(full, my_f, j);
       const int i = __shfl_sync(full, my_i, j);
-      if (i < 0 || i >= H) continue;  // warp-uniform
-      const uint32_t* drow = packed + static_cast<size_t>(i) * words_per_row;
+      vsum += vf;
+      const uint32_t* drow = packed + static_cast<size_t>(i) * words_per_row + w0;
+      uint32_t word[WPL];
+      if constexpr (FULL) {
+        if constexpr (WPL == 1) {
+          word[0] = __ldg(drow);
+        } else if constexpr (WPL == 2) {
+          const uint2 t = __ldg(reinterpret_cast<const uint2*>(drow));
+          word[0] = t.x; word[1] = t.y;
+        } else {
+          const uint4 t = __ldg(reinterpret_cast<const uint4*>(drow));
+          word[0] = t.x; word[1] = t.y; word[2] = t.z; word[3] = t.w;
+        }
+      } else {
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int w = c * 32 + lane;
-        if (w < words_per_row) {
-          const uint32_t bits = __ldg(drow + w);
+        for (int c = 0; c < WPL; ++c) word[c] = (w0 + c < words_per_row) ? __ldg(drow + c) : 0x88888888u;
+      }
 #pragma unroll
-          for (int q = 0; q < 8; ++q) acc[c][q] = fmaf(v, nibble_f(bits, q), acc[c][q]);
+      for (int c = 0; c < WPL; ++c) {
+        const uint32_t bits = word[c] ^ 0x88888888u;               // biased nibbles u' = w + 8
+        const uint32_t lo = bits & 0x0F0F0F0Fu;                     // features 0, 2, 4, 6 as bytes
+        const uint32_t hi = (bits >> 4) & 0x0F0F0F0Fu;              // features 1, 3, 5, 7
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          acc[c][2 * q] += static_cast<int>(__byte_perm(lo, 0u, 0x4440u + q)) * vf;
+          acc[c][2 * q + 1] += static_cast<int>(__byte_perm(hi, 0u, 0x4440u + q)) * vf;
         }
       }
     }
   }
+  const int corr = 8 * vsum;
+  const float qnan = __uint_as_float(0x7FC00000u);
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const int d = (c * 32 + lane) * 8;
-    if (d < D) {
+  for (int c = 0; c < WPL; ++c) {
+    const int d = (w0 + c) * 8;
+    if (FULL || d < D) {
       float o[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) o[q] = scale * acc[c][q] + (bias ? __ldg(bias + d + q) : 0.f);
+      for (int q = 0; q < 8; ++q) {
+        const float sum = static_cast<float>(acc[c][q] - corr) * from_fixed;
+        o[q] = bad ? qnan : (scale * sum + (bias ? __ldg(bias + d + q) : 0.f));
+      }
       float4* dst = reinterpret_cast<float4*>(recon + static_cast<size_t>(row) * D + d);
       dst[0] = make_float4(o[0], o[1], o[2], o[3]);
       dst[1] = make_float4(o[4], o[5], o[6], o[7]);
@@ -165,14 +222,17 @@ const char* decode_int4_launch(const float* vals, const int32_t* idx, int B, int
                                float* recon, int idx_offset, cudaStream_t stream) {
   const int blocks = (B + kDecWarps - 1) / kDecWarps;
   const uint32_t* p32 = reinterpret_cast<const uint32_t*>(packed);
-  if (D <= 256)
-    decode_int4_kernel<1><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, p32, H, D, scale, bias, recon, idx_offset);
-  else if (D <= 512)
-    decode_int4_kernel<2><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, p32, H, D, scale, bias, recon, idx_offset);
-  else if (D <= 1024)
-    decode_int4_kernel<4><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, p32, H, D, scale, bias, recon, idx_offset);
-  else
-    return "decode_int4: D must be <= 1024";
+#define QSAE_DEC4(WPL, FULL) \
+  decode_int4_kernel<WPL, FULL><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, p32, H, D, scale, bias, recon, idx_offset)
+  const bool aligned = (reinterpret_cast<uintptr_t>(packed) & 15) == 0;
+  if (D == 256) QSAE_DEC4(1, true);
+  else if (D == 512 && aligned) QSAE_DEC4(2, true);
+  else if (D == 1024 && aligned) QSAE_DEC4(4, true);
+  else if (D <= 256) QSAE_DEC4(1, false);
+  else if (D <= 512) QSAE_DEC4(2, false);
+  else if (D <= 1024) QSAE_DEC4(4, false);
+  else return "decode_int4: D must be <= 1024";
+#undef QSAE_DEC4
   return cuda_err(cudaGetLastError());
 }
 

@@ -93,9 +93,12 @@ const char* rescue_rows_launch(const RescueLaunch& p, int num_sms, cudaStream_t 
 const char* sample_rows_launch(const uint16_t* w_bf16, const float* bias, int H, int D, int n_sample,
                                uint16_t* w_sample, float* b_sample, cudaStream_t stream);
 const char* select_topk_launch(const SelectLaunch& p, cudaStream_t stream);
-// warp-per-row merge for small survivor counts (prior mode); rows with more than its staging
-// capacity go to ovf_rows/ovf_count and are finished by select_topk_list_launch
-const char* select_small_launch(const SelectLaunch& p, int* ovf_count, int32_t* ovf_rows, cudaStream_t stream);
+// warp-per-row merge for small survivor counts (prior mode / gathered shard candidates). tier = keys per
+// lane (8 / 16 / 32: rows with up to 256 / 512 / 1024 survivors); rows that do not fit are appended to
+// ovf_rows / ovf_count for the next tier. rows == nullptr: every row of the batch; else the device-side list
+// rows[0, *count) on a persistent grid.
+const char* select_small_launch(const SelectLaunch& p, int tier, const int* count, const int32_t* rows, int num_sms,
+                                int* ovf_count, int32_t* ovf_rows, cudaStream_t stream);
 const char* select_topk_list_launch(const SelectLaunch& p, const int* count, const int32_t* rows, int num_sms,
                                     cudaStream_t stream);
 // prior[row] = m-th largest of the row's nsub * kTopM pre-pass values

@@ -110,7 +110,7 @@ struct EncodePlan {
   int k_sel, m;
   bool use_prior;
   StagePlan main, pre;
-  size_t x_off, prior_off, counters_off, rescue_rows_off, ovf_rows_off, total;
+  size_t x_off, prior_off, counters_off, rescue_rows_off, ovf_rows_off, ovf2_rows_off, total;
 };
 
 int plan_encode(int B, int H, int D, int k, int exact, int n_sample, EncodePlan* pl) {
@@ -146,6 +146,7 @@ int plan_encode(int B, int H, int D, int k, int exact, int n_sample, EncodePlan*
     pl->counters_off = off; off += 256;
     pl->rescue_rows_off = off; off = align_up(off + static_cast<size_t>(B) * 4, 256);
     pl->ovf_rows_off = off; off = align_up(off + static_cast<size_t>(B) * 4, 256);
+    pl->ovf2_rows_off = off; off = align_up(off + static_cast<size_t>(B) * 4, 256);
     plan_stage(B, n_sample, pl->m, kStageSamplePre, false, off, &pl->pre);
     off = pl->pre.end;
   }
@@ -286,10 +287,11 @@ int qsae_encode_topk(const float* x_f32, const uint16_t* w_bf16, const float* w_
 
   // ---- prior-threshold path
   float* prior = reinterpret_cast<float*>(ws + pl.prior_off);
-  int* counters = reinterpret_cast<int*>(ws + pl.counters_off);   // [0] rescue rows, [1] merge overflow rows
+  int* counters = reinterpret_cast<int*>(ws + pl.counters_off);   // [0] rescue rows, [1] / [2] merge overflow rows (tier 1 / 2)
   int32_t* rescue_rows = reinterpret_cast<int32_t*>(ws + pl.rescue_rows_off);
   int32_t* ovf_rows = reinterpret_cast<int32_t*>(ws + pl.ovf_rows_off);
-  cudaError_t ce = cudaMemsetAsync(counters, 0, 2 * sizeof(int), st);
+  int32_t* ovf2_rows = reinterpret_cast<int32_t*>(ws + pl.ovf2_rows_off);
+  cudaError_t ce = cudaMemsetAsync(counters, 0, 4 * sizeof(int), st);
   if (ce != cudaSuccess) return fail(QSAE_ERR_CUDA, "encode_topk: %s", cudaGetErrorString(ce));
   // 1. pre-pass: the fused kernel over the sampled dictionary rows, top list kept in registers
   EncodeLaunch pe;
@@ -317,9 +319,13 @@ int qsae_encode_topk(const float* x_f32, const uint16_t* w_bf16, const float* w_
   sl.x_f32 = x_f32; sl.w_f32 = w_f32; sl.bias = b_enc;
   sl.out_vals = out_vals; sl.out_idx = out_idx; sl.out_flags = out_flags;
   sl.rescue_count = counters; sl.rescue_rows = rescue_rows;
-  rc = launch_status("select_small kernel", select_small_launch(sl, counters + 1, ovf_rows, st));
+  //    tier 1: rows with <= 512 survivors (the expected count is ~32 m); tier 2: <= 1024; then block per row
+  rc = launch_status("select_small kernel", select_small_launch(sl, 16, nullptr, nullptr, num_sms(), counters + 1, ovf_rows, st));
   if (rc != QSAE_OK) return rc;
-  rc = launch_status("select_topk list kernel", select_topk_list_launch(sl, counters + 1, ovf_rows, num_sms(), st));
+  rc = launch_status("select_small kernel (tier 2)",
+                     select_small_launch(sl, 32, counters + 1, ovf_rows, num_sms(), counters + 2, ovf2_rows, st));
+  if (rc != QSAE_OK) return rc;
+  rc = launch_status("select_topk list kernel", select_topk_list_launch(sl, counters + 2, ovf2_rows, num_sms(), st));
   if (rc != QSAE_OK) return rc;
   // 4. rows whose prior failed the count check: exact recomputation
   RescueLaunch rl;
@@ -669,9 +675,11 @@ int qsae_merge_candidates(const void* cand_all, int n_shards, int B, int k_in, i
   sl.cand = cand_all;                 // [n_shards][B][k_in] entries, every list full
   sl.row_stride = 1; sl.sub_stride = B; sl.sub_col_offset = shard_latents;
   sl.out_vals = out_vals; sl.out_idx = out_idx;
-  int rc = launch_status("select_small kernel", select_small_launch(sl, counters + 1, ovf_rows, st));
-  if (rc != QSAE_OK) return rc;
-  return launch_status("select_topk list kernel", select_topk_list_launch(sl, counters + 1, ovf_rows, num_sms(), st));
+  // every row has exactly n_shards * k_in candidates: pick the tier that holds them
+  const long long n_cand = static_cast<long long>(n_shards) * k_in;
+  if (n_cand > 1024) return launch_status("select_topk kernel", select_topk_launch(sl, st));
+  const int tier = n_cand <= 256 ? 8 : (n_cand <= 512 ? 16 : 32);
+  return launch_status("select_small kernel", select_small_launch(sl, tier, nullptr, nullptr, num_sms(), counters + 1, ovf_rows, st));
 }
 
 int qsae_decode_int4_range(const float* vals, const int32_t* idx, int B, int k, const uint8_t* packed_shard,

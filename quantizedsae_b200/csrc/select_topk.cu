@@ -246,34 +246,82 @@ select_topk_list_kernel(SelectLaunch p, int n_max, int ksort, const int* count, 
 // the block-per-row kernel above.
 // ------------------------------------------------------------------------------------------
 constexpr int kSmallWarps = 4;
-constexpr int kSmallCap = 1024;             // staged survivors per row
 
-// the k_sel largest of the n staged composite keys -> sel[0, k_sel) (unordered); R keys per lane
+// the k_sel largest of the n staged composite keys -> sel[0, k_sel) (unordered); R keys per lane.
+// Bisection on the 32-bit value keys only, starting below the bits all survivors share (they come
+// from a narrow tail of the row's distribution) and stopping as soon as a probe isolates exactly
+// k_sel entries: ~10-15 rounds of R compares instead of 64 rounds over 64-bit keys. Ties at the k-th
+// value (rare) are resolved by a second bisection over the column halves of the tied keys.
 template <int R>
 __device__ __forceinline__ int small_select(uint64_t* stage, int n, int k_sel, int lane) {
   const unsigned full = 0xffffffffu;
   const unsigned lt_mask = (1u << lane) - 1u;
   uint64_t key[R];
+  uint32_t vk[R];
 #pragma unroll
-  for (int i = 0; i < R; ++i) key[i] = (lane + 32 * i < n) ? stage[lane + 32 * i] : 0ull;
+  for (int i = 0; i < R; ++i) {
+    key[i] = (lane + 32 * i < n) ? stage[lane + 32 * i] : 0ull;
+    vk[i] = static_cast<uint32_t>(key[i] >> 32);
+  }
   __syncwarp();
-  uint64_t T = 0ull;
+  uint32_t T = 0u;        // keep: vk > T, or vk == T and low half >= L
+  uint32_t L = 0u;
+  bool strict_only = false;
   if (n > k_sel) {
-#pragma unroll 1
-    for (int bit = 63; bit >= 0; --bit) {
-      const uint64_t probe = T | (1ull << bit);
-      int c = 0;
+    uint32_t a = 0xFFFFFFFFu, o = 0u;
 #pragma unroll
-      for (int i = 0; i < R; ++i) c += (key[i] >= probe) ? 1 : 0;
-      c = __reduce_add_sync(full, c);
-      if (c >= k_sel) T = probe;
-      if (c == k_sel) break;
+    for (int i = 0; i < R; ++i) {
+      if (lane + 32 * i < n) { a &= vk[i]; o |= vk[i]; }
     }
+    a = __reduce_and_sync(full, a);
+    o = __reduce_or_sync(full, o);
+    const uint32_t diff = a ^ o;
+    int c_ge = n;         // count(vk >= T) for the current T
+    T = a;                // all shared leading bits; the differing bits start cleared
+    if (diff != 0u) {
+      const int top = 31 - __clz(diff);
+      T = a & ~((2u << top) - 1u);
+#pragma unroll 1
+      for (int bit = top; bit >= 0; --bit) {
+        const uint32_t probe = T | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < R; ++i) c += (vk[i] >= probe) ? 1 : 0;   // padding keys are 0 < probe
+        c = __reduce_add_sync(full, c);
+        if (c >= k_sel) { T = probe; c_ge = c; }
+        if (c == k_sel) break;
+      }
+    }
+    if (c_ge > k_sel) {
+      // T is the k-th largest value and several entries carry it: keep every vk > T and the
+      // (k_sel - count(vk > T)) tied entries with the largest low halves (lowest columns)
+      int c_gt = 0;
+#pragma unroll
+      for (int i = 0; i < R; ++i) c_gt += (vk[i] > T) ? 1 : 0;
+      c_gt = __reduce_add_sync(full, c_gt);
+      const int need = k_sel - c_gt;
+#pragma unroll 1
+      for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t probe = L | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < R; ++i) c += (vk[i] == T && static_cast<uint32_t>(key[i]) >= probe) ? 1 : 0;
+        c = __reduce_add_sync(full, c);
+        if (c >= need) L = probe;
+        if (c == need) break;
+      }
+    } else {
+      strict_only = true;  // vk >= T is exactly the k_sel largest
+    }
+  } else {
+    strict_only = true;    // keep everything
   }
   int out = 0;  // the staging area is free again: the keys live in registers
 #pragma unroll
   for (int i = 0; i < R; ++i) {
-    const bool keep = (lane + 32 * i < n) && (key[i] >= T);
+    const bool valid = lane + 32 * i < n;
+    const bool keep = valid && (strict_only ? (vk[i] >= T)
+                                            : (vk[i] > T || (vk[i] == T && static_cast<uint32_t>(key[i]) >= L)));
     const unsigned b = __ballot_sync(full, keep);
     if (keep) stage[out + __popc(b & lt_mask)] = key[i];
     out += __popc(b);
@@ -281,16 +329,76 @@ __device__ __forceinline__ int small_select(uint64_t* stage, int n, int k_sel, i
   return out;
 }
 
-__global__ void __launch_bounds__(kSmallWarps * 32)
-select_small_kernel(SelectLaunch p, int ksort, int* ovf_count, int32_t* ovf_rows) {
-  __shared__ uint64_t stage_all[kSmallWarps][kSmallCap];
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * kSmallWarps + warp;
-  if (row >= p.B) return;
+// Bitonic sort (descending) of 32 * P composite keys held P per lane, element e = j * 32 + lane:
+// strides below 32 exchange through shuffles, larger strides are register moves.
+template <int P>
+__device__ __forceinline__ void warp_bitonic_desc(uint64_t (&k)[P], int lane) {
   const unsigned full = 0xffffffffu;
-  uint64_t* stage = stage_all[warp];
+#pragma unroll
+  for (int size = 2; size <= 32 * P; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= 32) {
+        const int js = stride >> 5;
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+          if ((j & js) == 0) {
+            const bool desc = ((j * 32) & size) == 0;   // size >= 64 here: depends on j only
+            const uint64_t a = k[j], b = k[j | js];
+            const bool swap = (a < b) == desc;
+            k[j] = swap ? b : a;
+            k[j | js] = swap ? a : b;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+          const bool desc = (((j * 32) | lane) & size) == 0;
+          const bool lower = (lane & stride) == 0;
+          const uint64_t mine = k[j];
+          const uint64_t other = __shfl_xor_sync(full, mine, stride);
+          const bool mine_big = mine > other;
+          const bool take_max = (lower == desc);
+          k[j] = (take_max == mine_big) ? mine : other;
+        }
+      }
+    }
+  }
+}
 
+template <int P>
+__device__ __forceinline__ void sort_and_emit(const SelectLaunch& p, int row, const uint64_t* sel, int out, int n,
+                                              int k_sel, float worst_bf16, float max_dev, int lane) {
+  uint64_t k[P];
+#pragma unroll
+  for (int j = 0; j < P; ++j) k[j] = sel[j * 32 + lane];
+  warp_bitonic_desc<P>(k, lane);
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const int e = j * 32 + lane;
+    if (e < p.k_out) {
+      const bool valid = e < out;
+      p.out_vals[static_cast<size_t>(row) * p.k_out + e] = valid ? sort_key_value(k[j]) : 0.f;
+      p.out_idx[static_cast<size_t>(row) * p.k_out + e] = valid ? static_cast<int32_t>(sort_key_col(k[j])) : -1;
+    }
+    if (p.out_flags != nullptr && e == p.k_out - 1) {
+      int flag = 0;
+      if (p.exact && n > k_sel && p.k_out <= out) {
+        // every dropped candidate scored <= worst_bf16 on the tensor cores; certified when even 4x the
+        // largest observed rounding deviation cannot lift one of them over the exact k-th value
+        const float kth = sort_key_value(k[j]);
+        if (!(worst_bf16 + 4.f * max_dev < kth)) flag = 1;
+      }
+      p.out_flags[row] = flag;
+    }
+  }
+}
+
+// One row: gather -> select -> (re-score) -> sort -> emit. R = survivor keys per lane (capacity 32 * R).
+template <int R>
+__device__ __forceinline__ void small_row(const SelectLaunch& p, int row, int ksort, uint64_t* stage, int* ovf_count,
+                                          int32_t* ovf_rows, int lane) {
+  const unsigned full = 0xffffffffu;
   // ---- counts and offsets of the row's sub-streams (nsub <= 32)
   const int my_c = (lane < p.nsub) ? list_count(p, list_slot(p, row, lane)) : 0;
   int incl = my_c;
@@ -300,7 +408,7 @@ select_small_kernel(SelectLaunch p, int ksort, int* ovf_count, int32_t* ovf_rows
     if (lane >= o) incl += t;
   }
   const int n = __shfl_sync(full, incl, 31);
-  if (n > kSmallCap) {
+  if (n > 32 * R) {   // next tier
     if (lane == 0) ovf_rows[atomicAdd(ovf_count, 1)] = row;
     return;
   }
@@ -326,12 +434,8 @@ select_small_kernel(SelectLaunch p, int ksort, int* ovf_count, int32_t* ovf_rows
   }
   __syncwarp();
 
-  // ---- k_sel largest composite keys (unique): bisection in registers, depth chosen by n
   const int k_sel = min(p.k_sel, n);
-  int out;
-  if (n <= 256) out = small_select<8>(stage, n, k_sel, lane);
-  else if (n <= 512) out = small_select<16>(stage, n, k_sel, lane);
-  else out = small_select<32>(stage, n, k_sel, lane);
+  const int out = small_select<R>(stage, n, k_sel, lane);
   uint64_t* sel = stage;
   for (int e = out + lane; e < ksort; e += 32) sel[e] = 0ull;
   __syncwarp();
@@ -388,35 +492,29 @@ select_small_kernel(SelectLaunch p, int ksort, int* ovf_count, int32_t* ovf_rows
     __syncwarp();
   }
 
-  // ---- bitonic sort of sel[0, ksort) descending, one warp
-  for (int size = 2; size <= ksort; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = lane; t < (ksort >> 1); t += 32) {
-        const int pos = ((t / stride) * (stride << 1)) + (t % stride);
-        const int partner = pos + stride;
-        const bool desc = (pos & size) == 0;
-        const uint64_t a = sel[pos], b = sel[partner];
-        if ((a < b) == desc) {
-          sel[pos] = b;
-          sel[partner] = a;
-        }
-      }
-      __syncwarp();
-    }
-  }
-  for (int j = lane; j < p.k_out; j += 32) {
-    const uint64_t kk = sel[j];
-    const bool valid = j < out;
-    p.out_vals[static_cast<size_t>(row) * p.k_out + j] = valid ? sort_key_value(kk) : 0.f;
-    p.out_idx[static_cast<size_t>(row) * p.k_out + j] = valid ? static_cast<int32_t>(sort_key_col(kk)) : -1;
-  }
-  if (p.out_flags != nullptr && lane == 0) {
-    int flag = 0;
-    if (p.exact && n > k_sel && p.k_out <= out) {
-      const float kth = sort_key_value(sel[p.k_out - 1]);
-      if (!(worst_bf16 + 4.f * max_dev < kth)) flag = 1;
-    }
-    p.out_flags[row] = flag;
+  // ---- sort in registers and emit (value desc, column asc)
+  if (ksort <= 32) sort_and_emit<1>(p, row, sel, out, n, k_sel, worst_bf16, max_dev, lane);
+  else if (ksort <= 64) sort_and_emit<2>(p, row, sel, out, n, k_sel, worst_bf16, max_dev, lane);
+  else if (ksort <= 128) sort_and_emit<4>(p, row, sel, out, n, k_sel, worst_bf16, max_dev, lane);
+  else sort_and_emit<8>(p, row, sel, out, n, k_sel, worst_bf16, max_dev, lane);
+  __syncwarp();
+}
+
+// rows == nullptr: one warp per row of the batch; otherwise a persistent grid over rows[0, *count)
+template <int R>
+__global__ void __launch_bounds__(kSmallWarps * 32)
+select_small_kernel(SelectLaunch p, int ksort, const int* count, const int32_t* rows, int* ovf_count,
+                    int32_t* ovf_rows) {
+  __shared__ uint64_t stage_all[kSmallWarps][32 * R];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (rows == nullptr) {
+    const int row = blockIdx.x * kSmallWarps + warp;
+    if (row < p.B) small_row<R>(p, row, ksort, stage_all[warp], ovf_count, ovf_rows, lane);
+  } else {
+    const int n_list = min(*count, p.B);
+    for (int li = blockIdx.x * kSmallWarps + warp; li < n_list; li += gridDim.x * kSmallWarps)
+      small_row<R>(p, rows[li], ksort, stage_all[warp], ovf_count, ovf_rows, lane);
   }
 }
 
@@ -535,12 +633,18 @@ const char* select_topk_launch(const SelectLaunch& p, cudaStream_t stream) {
   return cuda_err(cudaGetLastError());
 }
 
-const char* select_small_launch(const SelectLaunch& p, int* ovf_count, int32_t* ovf_rows, cudaStream_t stream) {
+const char* select_small_launch(const SelectLaunch& p, int tier, const int* count, const int32_t* rows, int num_sms,
+                                int* ovf_count, int32_t* ovf_rows, cudaStream_t stream) {
   if (p.nsub > 32) return "select_small: at most 32 sub-streams per row";
-  const int ksort = next_pow2(p.k_sel < 2 ? 2 : p.k_sel);
-  if (ksort > kSmallCap) return "select_small: k too large";
-  const int blocks = (p.B + kSmallWarps - 1) / kSmallWarps;
-  select_small_kernel<<<blocks, kSmallWarps * 32, 0, stream>>>(p, ksort, ovf_count, ovf_rows);
+  const int ksort = next_pow2(p.k_sel < 32 ? 32 : p.k_sel);
+  if (ksort > 256) return "select_small: k too large";
+  const int blocks = rows ? num_sms * 4 : (p.B + kSmallWarps - 1) / kSmallWarps;
+  switch (tier) {
+    case 8: select_small_kernel<8><<<blocks, kSmallWarps * 32, 0, stream>>>(p, ksort, count, rows, ovf_count, ovf_rows); break;
+    case 16: select_small_kernel<16><<<blocks, kSmallWarps * 32, 0, stream>>>(p, ksort, count, rows, ovf_count, ovf_rows); break;
+    case 32: select_small_kernel<32><<<blocks, kSmallWarps * 32, 0, stream>>>(p, ksort, count, rows, ovf_count, ovf_rows); break;
+    default: return "select_small: tier must be 8, 16 or 32 keys per lane";
+  }
   return cuda_err(cudaGetLastError());
 }
 

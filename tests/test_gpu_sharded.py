@@ -124,3 +124,23 @@ def test_dictionary_sharded_forward_under_nccl(cuda_device):
         assert np.all(np.abs(v - rv) <= 1e-5 * np.maximum(1.0, np.abs(rv)))
         _recon_close(rows, rr[a:b])
         assert pol == rp
+
+
+@pytest.mark.parametrize("G,B,kin,kout", [(8, 33, 32, 32), (4, 17, 65, 65), (8, 9, 128, 100), (2, 5, 7, 9), (8, 6, 224, 224)])
+def test_merge_candidates_tie_rule(cuda_device, G, B, kin, kout):
+    """Heavily tied candidate values: the merge must order by (value desc, global index asc) exactly."""
+    rng = np.random.default_rng(G * 1000 + kin)
+    shard = 4096
+    vals = rng.integers(0, 4, size=(G, B, kin)).astype(np.float32)       # only 4 distinct values
+    vals[:, 0] = 1.0                                                      # a row where everything ties
+    idx = np.stack([np.stack([rng.choice(shard, kin, replace=False) for _ in range(B)]) for _ in range(G)]).astype(np.int32)
+    cand = np.empty((G, B, kin, 2), dtype=np.int32)
+    cand[..., 0] = vals.view(np.int32)
+    cand[..., 1] = idx
+    gv, gi = L.merge_candidates(torch.from_numpy(cand).to(cuda_device), shard, kout)
+    gidx = idx.astype(np.int64) + (np.arange(G) * shard)[:, None, None]
+    v = vals.transpose(1, 0, 2).reshape(B, -1)
+    i = gidx.transpose(1, 0, 2).reshape(B, -1)
+    order = np.lexsort((i, -v.astype(np.float64)), axis=1)[:, :kout]
+    assert np.array_equal(gi.cpu().numpy(), np.take_along_axis(i, order, 1))
+    assert np.array_equal(gv.cpu().numpy(), np.take_along_axis(v, order, 1))
