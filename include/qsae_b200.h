@@ -192,6 +192,23 @@ int qsae_matryoshka_forward(const float* x_f32, const uint16_t* w_bf16,
                             unsigned long long* level_count /* [n_levels] */, int* overflow,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* Dense path of the same forward, for any activity level (the sparse path reports *overflow when a row
+ * has more active latents than its survivor lists hold -- e.g. an untrained model, ~50 % active):
+ * dense pre-activations, A = (sigmoid(z) > 0.5) * scale as bf16 hi + lo, and one tcgen05 GEMM per level
+ * over that level's range of the latent axis with T^T [D, H] in bf16, outputs accumulated level by level.
+ * w_f32 given: pre-activations on fp32 CUDA cores (exact for any fp32 operands); else w_bf16 on the
+ * tensor cores. level_start is needed on the device (counts) and on the host (GEMM ranges);
+ * boundaries and H must be multiples of 8. */
+int qsae_unpack_matryoshka_t(const uint32_t* packed /* [H, D/16] */, int H, int D, uint16_t* t_bf16 /* [D, H] */,
+                             void* stream);
+int qsae_matryoshka_dense_workspace_bytes(int B, int H, int D, size_t* bytes);
+int qsae_matryoshka_forward_dense(const float* x_f32, const uint16_t* w_bf16, const float* w_f32, const float* b_enc,
+                                  const uint16_t* t_bf16, const float* scale, const int* level_start_dev,
+                                  const int* level_start_host, int n_levels, const float* dec_bias, int B, int H,
+                                  int D, float* result /* [n_levels, B, D] */,
+                                  unsigned long long* level_count /* [n_levels] */, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+
 /* max_h ||w[h,:]||_2 -> *out (device float). With w_f32 given, qsae_matryoshka_forward lowers each
  * row's sweep threshold by the bound 2^-8 ||x_b|| max_h||w_h|| on |z_bf16 - z_fp32| and decides
  * activity from an fp32 re-scoring, so the active set equals the fp32 reference's for any input. */

@@ -43,6 +43,10 @@ SYMBOLS = {
     "qsae_matryoshka_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
     "qsae_matryoshka_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "qsae_max_row_norm": (_i, [_vp, _i, _i, _vp, _vp]),
+    "qsae_unpack_matryoshka_t": (_i, [_vp, _i, _i, _vp, _vp]),
+    "qsae_matryoshka_dense_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
+    "qsae_matryoshka_forward_dense": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i), _i, _vp, _i, _i, _i, _vp, _vp,
+                                           _vp, _sz, _vp]),
     "qsae_decode_matryoshka_lists": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "qsae_pack_ternary": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp]),
     "qsae_split_bf16": (_i, [_vp, _vp, _vp, _sz, _vp]),
@@ -473,3 +477,37 @@ def decode_range(vals, idx, dict_shard, shard_latents: int, idx_begin: int, D: i
              _ptr(bias), recon.data_ptr(), _stream()))
     launch_count += 1
     return recon
+
+
+def unpack_matryoshka_t(packed: torch.Tensor, D: int) -> torch.Tensor:
+    """packed 2-bit codes [H, D/16] -> T^T bf16 [D, H] (entries -2, 0, +2)."""
+    global launch_count
+    _need_cuda(packed)
+    H = packed.shape[0]
+    t = torch.empty((D, H), dtype=torch.bfloat16, device=packed.device)
+    check(load().qsae_unpack_matryoshka_t(packed.data_ptr(), H, D, t.data_ptr(), _stream()))
+    launch_count += 1
+    return t
+
+
+def matryoshka_forward_dense(x, w_bf16, w_f32, b_enc, t_bf16, scale, level_start_dev, level_start_host, dec_bias):
+    """Dense q_sae forward -> (result [n_levels, B, D] f32, level_count [n_levels] int64)."""
+    global launch_count
+    _need_cuda(x, w_bf16, w_f32, b_enc, t_bf16, scale, level_start_dev, dec_bias)
+    B, D = x.shape
+    H = t_bf16.shape[1]
+    n_levels = len(level_start_host) - 1
+    result = torch.empty((n_levels, B, D), dtype=torch.float32, device=x.device)
+    counts = torch.zeros((n_levels,), dtype=torch.int64, device=x.device)
+    if B == 0:
+        return result, counts
+    n = _sz(0)
+    check(load().qsae_matryoshka_dense_workspace_bytes(B, H, D, C.byref(n)))
+    ws = _workspace(x.device, int(n.value))
+    starts = (_i * (n_levels + 1))(*[int(v) for v in level_start_host])
+    check(load().qsae_matryoshka_forward_dense(x.data_ptr(), _ptr(w_bf16), _ptr(w_f32), b_enc.data_ptr(), t_bf16.data_ptr(),
+                                               scale.data_ptr(), level_start_dev.data_ptr(), starts, n_levels,
+                                               _ptr(dec_bias), B, H, D, result.data_ptr(), counts.data_ptr(),
+                                               ws.data_ptr(), ws.numel(), _stream()))
+    launch_count += 3 + 2 * n_levels
+    return result, counts

@@ -157,7 +157,8 @@ dense_decode_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
 }
 
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int splits, size_t n,
-                                       const float* __restrict__ bias, int N, float* __restrict__ out) {
+                                       const float* __restrict__ bias, const float* __restrict__ prev, int N,
+                                       float* __restrict__ out) {
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n / 4; i += stride) {
     float4 acc = reinterpret_cast<const float4*>(partial)[i];
@@ -169,6 +170,10 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int sp
       const int d = static_cast<int>((i * 4) % N);
       acc.x += bias[d]; acc.y += bias[d + 1]; acc.z += bias[d + 2]; acc.w += bias[d + 3];
     }
+    if (prev != nullptr) {   // cumulative outputs (q_sae levels): out = prev + this range
+      const float4 q = reinterpret_cast<const float4*>(prev)[i];
+      acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+    }
     reinterpret_cast<float4*>(out)[i] = acc;
   }
 }
@@ -177,7 +182,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-bool make_tmap(CUtensorMap* map, const void* base, int rows, int cols, int box_rows) {
+bool make_tmap(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows) {
   static EncodeTiledFn enc = nullptr;
   if (!enc) {
     void* ptr = nullptr;
@@ -188,7 +193,7 @@ bool make_tmap(CUtensorMap* map, const void* base, int rows, int cols, int box_r
     enc = reinterpret_cast<EncodeTiledFn>(ptr);
   }
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};   // row pitch in bytes (a K sub-range keeps the full pitch)
   cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
@@ -236,13 +241,15 @@ size_t dense_decode_workspace_bytes(int B, int K, int N, int num_sms) {
   return static_cast<size_t>(dense_decode_pick_splits(B, K, num_sms)) * B * N * sizeof(float);
 }
 
-const char* dense_decode_launch(const uint16_t* a_hi, const uint16_t* a_lo, const uint16_t* b_t, int B, int K, int N,
-                                const float* bias, float* out, void* workspace, int num_sms, cudaStream_t stream) {
+const char* dense_decode_launch(const uint16_t* a_hi, const uint16_t* a_lo, int lda, const uint16_t* b_t, int ldb, int B,
+                                int K, int N, const float* bias, const float* prev, float* out, void* workspace,
+                                int num_sms, cudaStream_t stream) {
   if (N > 512 || (N % 4) != 0) return "dense_decode: N must be a multiple of 4, <= 512";
+  if ((lda % 8) != 0 || (ldb % 8) != 0) return "dense_decode: row pitches must be multiples of 8 elements";
   CUtensorMap ta0, ta1, tb;
-  if (!make_tmap(&ta0, a_hi, B, K, BM)) return "cuTensorMapEncodeTiled(A) failed";
-  if (!make_tmap(&ta1, a_lo ? a_lo : a_hi, B, K, BM)) return "cuTensorMapEncodeTiled(A lo) failed";
-  if (!make_tmap(&tb, b_t, N, K, BN)) return "cuTensorMapEncodeTiled(B) failed";
+  if (!make_tmap(&ta0, a_hi, B, K, lda, BM)) return "cuTensorMapEncodeTiled(A) failed";
+  if (!make_tmap(&ta1, a_lo ? a_lo : a_hi, B, K, lda, BM)) return "cuTensorMapEncodeTiled(A lo) failed";
+  if (!make_tmap(&tb, b_t, N, K, ldb, BN)) return "cuTensorMapEncodeTiled(B) failed";
   DecodeLaunch p;
   p.B = B; p.K = K; p.N = N;
   p.k_chunks = (K + BK - 1) / BK;
@@ -256,7 +263,7 @@ const char* dense_decode_launch(const uint16_t* a_hi, const uint16_t* a_lo, cons
   size_t g = (n / 4 + 255) / 256;
   if (g > 148 * 8) g = 148 * 8;
   if (g < 1) g = 1;
-  reduce_partials_kernel<<<static_cast<int>(g), 256, 0, stream>>>(p.partial, splits, n, bias, N, out);
+  reduce_partials_kernel<<<static_cast<int>(g), 256, 0, stream>>>(p.partial, splits, n, bias, prev, N, out);
   return cuda_err(cudaGetLastError());
 }
 

@@ -49,8 +49,11 @@ const char* encode_dense_tc_launch(const uint16_t* x_bf16, const uint16_t* w_bf1
 // dense_decode_sm100.cu: out[B, N] = (a_hi (+ a_lo))[B, K] * b_t[N, K]^T (+ bias), bf16 in, fp32 accumulate
 int dense_decode_pick_splits(int B, int K, int num_sms);
 size_t dense_decode_workspace_bytes(int B, int K, int N, int num_sms);
-const char* dense_decode_launch(const uint16_t* a_hi, const uint16_t* a_lo, const uint16_t* b_t, int B, int K, int N,
-                                const float* bias, float* out, void* workspace, int num_sms, cudaStream_t stream);
+// lda / ldb: row pitches in elements (a K sub-range of a wider matrix keeps the full pitch);
+// prev: optional [B, N] added to the result (cumulative per-level outputs)
+const char* dense_decode_launch(const uint16_t* a_hi, const uint16_t* a_lo, int lda, const uint16_t* b_t, int ldb, int B,
+                                int K, int N, const float* bias, const float* prev, float* out, void* workspace,
+                                int num_sms, cudaStream_t stream);
 
 // select_topk.cu
 struct SelectLaunch {
@@ -145,6 +148,12 @@ const char* decode_matryoshka_launch(const void* cand, const int* cand_cnt, int 
                                      int n_levels, int H, int D, const float* bias, float* result,
                                      unsigned long long* level_count, const float* x_f32, const float* w_f32,
                                      const float* b_enc, float thr_value, int exact, cudaStream_t stream);
+// packed 2-bit codes [H, D/16] -> T^T as bf16 [D, H] with entries {-2, 0, +2} (B operand of the dense level GEMMs)
+const char* unpack_matryoshka_t_launch(const uint32_t* packed, int H, int D, uint16_t* t_bf16, cudaStream_t stream);
+// z [B, H] -> a = (z >= thr) * scale[h] split into bf16 hi / lo [B, H]; level_count[l] += active entries of level l
+const char* matryoshka_dense_operand_launch(const float* z, int B, int H, const float* scale, float thr,
+                                            const int* level_start, int n_levels, uint16_t* a_hi, uint16_t* a_lo,
+                                            unsigned long long* level_count, cudaStream_t stream);
 const char* max_row_norm_launch(const float* w, int H, int D, float* out, cudaStream_t stream);
 const char* row_threshold_launch(const float* x, int B, int D, const float* wmax, float thr_value, float* thr,
                                  cudaStream_t stream);

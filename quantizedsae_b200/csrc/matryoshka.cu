@@ -12,6 +12,7 @@
 // 32-bit word, [H, D/16] words (128 B per row at D = 512) + one fp32 scale per row.
 // The decoder consumes the encoder's survivor lists directly (the active latents of a row, any
 // order): warp per token, level accumulators in shared memory, cumulative outputs.
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -85,6 +86,60 @@ row_threshold_kernel(const float* __restrict__ x, int B, int D, const float* __r
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) thr[b] = thr_value - (1.01f * 0.00390625f * sqrtf(s) * (*wmax) + 1e-6f);
+}
+
+// ---- dense fallback (rows with more active latents than the survivor lists hold, e.g. an untrained
+// model with ~50 % activity): the level sums become tensor-core GEMMs over K ranges of H.
+
+// packed codes [H, D/16] -> T^T bf16 [D, H]; 32 x 32 tiles through shared memory, coalesced both ways
+__global__ void unpack_matryoshka_t_kernel(const uint32_t* __restrict__ packed, int H, int D,
+                                           uint16_t* __restrict__ t_bf16) {
+  __shared__ uint16_t tile[32][33];
+  const int h0 = blockIdx.x * 32, d0 = blockIdx.y * 32;   // D % 16 == 0: a tile covers two code words per row
+  const int words = D >> 4;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int h = h0 + i, d = d0 + threadIdx.x;
+    uint16_t v = 0;
+    if (h < H && d < D) {
+      const uint32_t code = (packed[static_cast<size_t>(h) * words + (d >> 4)] >> (2 * (d & 15))) & 3u;
+      v = (code & 1u) ? ((code & 2u) ? 0xC000u : 0x4000u) : 0u;   // -2.0 / +2.0 / 0 in bf16
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int d = d0 + i, h = h0 + threadIdx.x;
+    if (d < D && h < H) t_bf16[static_cast<size_t>(d) * H + h] = tile[threadIdx.x][i];
+  }
+}
+
+// a[b, h] = (z[b, h] >= thr) ? scale[h] : 0, as bf16 hi + lo (hi + lo = scale to 2^-17); per-level activity counts
+__global__ void __launch_bounds__(256)
+matryoshka_dense_operand_kernel(const float* __restrict__ z, int B, int H, const float* __restrict__ scale, float thr,
+                                const int* __restrict__ level_start, int n_levels, uint16_t* __restrict__ a_hi,
+                                uint16_t* __restrict__ a_lo, unsigned long long* __restrict__ level_count) {
+  __shared__ unsigned s_cnt[32];
+  if (threadIdx.x < 32) s_cnt[threadIdx.x] = 0u;
+  __syncthreads();
+  const size_t total = static_cast<size_t>(B) * H;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int h = static_cast<int>(e % H);
+    const bool active = z[e] >= thr;
+    const float a = active ? scale[h] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(a);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(a - __bfloat162float(hi));
+    a_hi[e] = *reinterpret_cast<const uint16_t*>(&hi);
+    a_lo[e] = *reinterpret_cast<const uint16_t*>(&lo);
+    if (active) {
+      int lvl = 0;
+      while (lvl + 1 < n_levels && h >= level_start[lvl + 1]) ++lvl;
+      atomicAdd(&s_cnt[lvl], 1u);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < n_levels && s_cnt[threadIdx.x] != 0u)
+    atomicAdd(&level_count[threadIdx.x], static_cast<unsigned long long>(s_cnt[threadIdx.x]));
 }
 
 constexpr int kMatWarps = 4;
@@ -181,6 +236,22 @@ const char* pack_matryoshka_launch(const float* w, const float* wm, int H, int D
                                    cudaStream_t stream) {
   pack_matryoshka_kernel<<<(H + 7) / 8, 256, 0, stream>>>(w, wm, H, D, level_start, level_factor, n_levels,
                                                           packed, scale);
+  return cuda_err(cudaGetLastError());
+}
+
+const char* unpack_matryoshka_t_launch(const uint32_t* packed, int H, int D, uint16_t* t_bf16, cudaStream_t stream) {
+  dim3 grid((H + 31) / 32, (D + 31) / 32), block(32, 8);
+  unpack_matryoshka_t_kernel<<<grid, block, 0, stream>>>(packed, H, D, t_bf16);
+  return cuda_err(cudaGetLastError());
+}
+
+const char* matryoshka_dense_operand_launch(const float* z, int B, int H, const float* scale, float thr,
+                                            const int* level_start, int n_levels, uint16_t* a_hi, uint16_t* a_lo,
+                                            unsigned long long* level_count, cudaStream_t stream) {
+  size_t g = (static_cast<size_t>(B) * H + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  matryoshka_dense_operand_kernel<<<static_cast<int>(g), 256, 0, stream>>>(z, B, H, scale, thr, level_start, n_levels,
+                                                                           a_hi, a_lo, level_count);
   return cuda_err(cudaGetLastError());
 }
 

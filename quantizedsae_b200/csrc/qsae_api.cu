@@ -499,7 +499,7 @@ int qsae_decode_dense(const uint16_t* a_hi, const uint16_t* a_lo, const uint16_t
   const size_t need = dense_decode_workspace_bytes(B, K, N, num_sms());
   if (workspace_bytes < need) return fail(QSAE_ERR_WORKSPACE_TOO_SMALL, "decode_dense: workspace %zu < %zu bytes", workspace_bytes, need);
   if (g_enc_ev_start) cudaEventRecord(g_enc_ev_start, S(stream));
-  rc = launch_status("dense_decode", dense_decode_launch(a_hi, a_lo, b_t, B, K, N, bias, out, workspace, num_sms(), S(stream)));
+  rc = launch_status("dense_decode", dense_decode_launch(a_hi, a_lo, K, b_t, K, B, K, N, bias, nullptr, out, workspace, num_sms(), S(stream)));
   if (g_enc_ev_stop) cudaEventRecord(g_enc_ev_stop, S(stream));
   return rc;
 }
@@ -568,8 +568,107 @@ int qsae_tsae_forward(const float* x_f32, const uint16_t* w_bf16, const float* w
     if (g_enc_ev_stop) cudaEventRecord(g_enc_ev_stop, st);
     if (rc != QSAE_OK) return rc;
   }
-  return launch_status("dense_decode", dense_decode_launch(h_hi, h_lo, t_bf16, B, H, D, nullptr, recon, ws + tp.dec_off,
-                                                           num_sms(), st));
+  return launch_status("dense_decode", dense_decode_launch(h_hi, h_lo, H, t_bf16, H, B, H, D, nullptr, nullptr, recon,
+                                                           ws + tp.dec_off, num_sms(), st));
+}
+
+// ---- q_sae dense fallback: any activity level (an untrained model is ~50 % active), level sums as GEMMs
+int qsae_unpack_matryoshka_t(const uint32_t* packed, int H, int D, uint16_t* t_bf16, void* stream) {
+  if (!packed || !t_bf16 || H <= 0 || D <= 0 || (D % 16) != 0)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "unpack_matryoshka_t: bad argument");
+  return launch_status("unpack_matryoshka_t", unpack_matryoshka_t_launch(packed, H, D, t_bf16, S(stream)));
+}
+
+namespace {
+struct MatDensePlan { size_t x_off, z_off, hi_off, lo_off, dec_off, total; };
+int plan_matryoshka_dense(int B, int H, int D, MatDensePlan* mp) {
+  if (B <= 0 || H <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "B and H must be positive");
+  if (D < 16 || D > 512 || (D % 16) != 0)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka: D must be a multiple of 16 in [16, 512], got %d", D);
+  if ((H % 8) != 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka dense path: hidden_dim must be a multiple of 8, got %d", H);
+  const size_t bh = static_cast<size_t>(B) * H;
+  mp->x_off = 0;
+  mp->z_off = align_up(static_cast<size_t>(B) * D * 2, 1024);
+  mp->hi_off = align_up(mp->z_off + bh * 4, 1024);
+  mp->lo_off = align_up(mp->hi_off + bh * 2, 1024);
+  mp->dec_off = align_up(mp->lo_off + bh * 2, 1024);
+  mp->total = align_up(mp->dec_off + 16 * static_cast<size_t>(B) * D * sizeof(float), 256);   // up to 16 K splits
+  return QSAE_OK;
+}
+}  // namespace
+
+int qsae_matryoshka_dense_workspace_bytes(int B, int H, int D, size_t* bytes) {
+  if (!bytes) return fail(QSAE_ERR_INVALID_ARGUMENT, "workspace query: null pointer");
+  MatDensePlan mp;
+  int rc = plan_matryoshka_dense(B, H, D, &mp);
+  if (rc != QSAE_OK) return rc;
+  *bytes = mp.total;
+  return QSAE_OK;
+}
+
+int qsae_matryoshka_forward_dense(const float* x_f32, const uint16_t* w_bf16, const float* w_f32, const float* b_enc,
+                                  const uint16_t* t_bf16, const float* scale, const int* level_start_dev,
+                                  const int* level_start_host, int n_levels, const float* dec_bias, int B, int H, int D,
+                                  float* result, unsigned long long* level_count, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  if (B == 0) return QSAE_OK;
+  if (!x_f32 || !b_enc || !t_bf16 || !scale || !level_start_dev || !level_start_host || !result || !level_count || !workspace)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_forward_dense: null pointer");
+  if (!w_bf16 && !w_f32) return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_forward_dense: no encoder weights");
+  if (n_levels < 1 || n_levels > 32) return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_forward_dense: 1 <= n_levels <= 32");
+  for (int i = 0; i <= n_levels; ++i) {
+    if ((level_start_host[i] % 8) != 0 || (i > 0 && level_start_host[i] <= level_start_host[i - 1]))
+      return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka dense path: level boundaries must be increasing multiples of 8");
+  }
+  if (level_start_host[0] != 0 || level_start_host[n_levels] != H)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka dense path: levels must cover [0, H)");
+  MatDensePlan mp;
+  int rc = plan_matryoshka_dense(B, H, D, &mp);
+  if (rc != QSAE_OK) return rc;
+  if (workspace_bytes < mp.total)
+    return fail(QSAE_ERR_WORKSPACE_TOO_SMALL, "matryoshka_forward_dense: workspace %zu < %zu bytes", workspace_bytes, mp.total);
+  if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_forward_dense: workspace must be 1024-byte aligned");
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  uint16_t* x_bf16 = reinterpret_cast<uint16_t*>(ws + mp.x_off);
+  float* z = reinterpret_cast<float*>(ws + mp.z_off);
+  uint16_t* a_hi = reinterpret_cast<uint16_t*>(ws + mp.hi_off);
+  uint16_t* a_lo = reinterpret_cast<uint16_t*>(ws + mp.lo_off);
+  cudaStream_t st = S(stream);
+  cudaError_t ce = cudaMemsetAsync(level_count, 0, static_cast<size_t>(n_levels) * sizeof(unsigned long long), st);
+  if (ce != cudaSuccess) return fail(QSAE_ERR_CUDA, "matryoshka_forward_dense: %s", cudaGetErrorString(ce));
+  // 1. dense pre-activations: fp32 CUDA cores when the original weights are given (exact for any fp32
+  //    operands), else the tcgen05 encoder with its TMA-store epilogue
+  if (w_f32) {
+    rc = launch_status("encode_dense", encode_dense_launch(x_f32, nullptr, B, w_f32, b_enc, H, D, QSAE_ACT_NONE, z, st));
+  } else {
+    rc = launch_status("cast x", cast_bf16_launch(x_f32, x_bf16, static_cast<size_t>(B) * D, st));
+    if (rc != QSAE_OK) return rc;
+    EncodeLaunch el;
+    memset(&el, 0, sizeof(el));
+    el.B = B; el.H = H; el.D = D; el.act = QSAE_ACT_NONE; el.bias = b_enc;
+    el.n_tiles = (H + kEncBN - 1) / kEncBN;
+    el.n_splits = encode_pick_splits(B, H, num_sms());
+    el.tiles_per_split = (el.n_tiles + el.n_splits - 1) / el.n_splits;
+    rc = launch_status("encode kernel (dense)", encode_dense_tc_launch(x_bf16, w_bf16, el, z, nullptr, nullptr, st));
+  }
+  if (rc != QSAE_OK) return rc;
+  // 2. A = active * scale, split into bf16 hi / lo; activity counts per level
+  rc = launch_status("matryoshka_dense_operand",
+                     matryoshka_dense_operand_launch(z, B, H, scale, kActiveThreshold, level_start_dev, n_levels, a_hi, a_lo,
+                                                     level_count, st));
+  if (rc != QSAE_OK) return rc;
+  // 3. one GEMM per level over its K range, outputs accumulated level by level (:121-129)
+  const size_t bd = static_cast<size_t>(B) * D;
+  for (int i = 0; i < n_levels; ++i) {
+    const int k0 = level_start_host[i], kn = level_start_host[i + 1] - k0;
+    rc = launch_status("dense_decode (level)",
+                       dense_decode_launch(a_hi + k0, a_lo + k0, H, t_bf16 + k0, H, B, kn, D, i == 0 ? dec_bias : nullptr,
+                                           i == 0 ? nullptr : result + (i - 1) * bd, result + i * bd, ws + mp.dec_off,
+                                           num_sms(), st));
+    if (rc != QSAE_OK) return rc;
+  }
+  return QSAE_OK;
 }
 
 int qsae_encode_dense_f32(const float* x_f32, const int32_t* rows, int R, const float* w_f32,

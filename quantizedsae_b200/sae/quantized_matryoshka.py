@@ -7,8 +7,10 @@ Reference: sigmoid encoder, activity = sigmoid(z) > 0.5 (`top_k` is stored and n
 per level a dense `(scale * a) @ (S + S_mirror)` with host syncs (:85). Here: the tcgen05 encoder
 collects each row's active latents in its epilogue (threshold mode) and a sparse decoder sums the
 packed {-2,0,+2} rows per level, emitting the cumulative reconstructions in one pass.
-Rows with more active latents than the sparse path holds (1024 per sub-stream) raise: the dense
-decode GEMM for un-trained (50 % active) models is not built yet.
+When a row has more active latents than the survivor lists hold (1024 per sub-stream, e.g. an
+untrained model with ~50 % activity) the forward is redone on the dense path: dense pre-activations,
+A = active * scale as bf16 hi + lo and one tcgen05 GEMM per level (qsae_matryoshka_forward_dense).
+`dense_mode`: "auto" (default: sparse first, dense on overflow), "always", "never" (raise on overflow).
 """
 from __future__ import annotations
 
@@ -75,10 +77,21 @@ class QuantizedMatryoshkaDecoder(nn.Module):
             lambda: _lib.pack_matryoshka(self.weight.detach().contiguous(), self.weight_mirror.detach().contiguous(),
                                          ls, lf))
 
+    def _t_bf16(self):
+        """T^T [D, H] bf16 for the dense level GEMMs (cached per weight version)."""
+        return self._prep.get("t_bf16", param_key(self.weight, self.weight_mirror),
+                              lambda: _lib.unpack_matryoshka_t(self._packed()[0], self.out_features))
+
+    def _level_starts_host(self):
+        starts = [0]
+        for s in self.nested_dictionary_size:
+            starts.append(starts[-1] + s)
+        return starts
+
     def _finish(self, result, counts, overflow, B):
-        if int(overflow.item()) != 0:
+        if overflow is not None and int(overflow.item()) != 0:
             raise RuntimeError("q_sae: a row has more active latents than the sparse decoder holds "
-                               "(1024 per sub-stream); the dense decode path is not built yet")
+                               "(1024 per sub-stream) and dense_mode is 'never'")
         groups = counts.to(torch.float32) / float(max(B, 1))
         return [groups[i] for i in range(self.n_bits)], [result[i] for i in range(self.n_bits)]
 
@@ -116,6 +129,8 @@ class QuantizedMatryoshkaSAE(SparseAutoencoder):
         self.decoder = QuantizedMatryoshkaDecoder(hidden_dim, input_dim, abs_range=abs_range, n_bits=n_bits,
                                                   top_k=self.top_k, allow_bias=self.allow_bias)
         self.exact = True                    # decide activity from an fp32 re-scoring (any fp32 weights)
+        self.dense_mode = "auto"             # "auto" | "always" | "never"
+        self.last_path = None                # "sparse" / "dense": which path produced the last forward
         self._prep = PreparedCache()
 
     def _w_bf16(self):
@@ -132,8 +147,22 @@ class QuantizedMatryoshkaSAE(SparseAutoencoder):
         lin = self.encoder[0]
         return torch.sigmoid(_lib.encode_dense(x, lin.weight.detach().contiguous(), lin.bias.detach()))
 
+    def _forward_dense(self, x):
+        lin = self.encoder[0]
+        dec = self.decoder
+        _, scale = dec._packed()
+        ls, _ = dec._levels()
+        result, counts = _lib.matryoshka_forward_dense(
+            x, None if self.exact else self._w_bf16(), lin.weight.detach().contiguous() if self.exact else None,
+            lin.bias.detach(), dec._t_bf16(), scale, ls, dec._level_starts_host(),
+            dec.bias.detach() if self.allow_bias else None)
+        self.last_path = "dense"
+        return dec._finish(result, counts, None, x.shape[0])
+
     def forward(self, x):
         x = require_cuda_input(x, self)
+        if self.dense_mode == "always":
+            return self._forward_dense(x)
         lin = self.encoder[0]
         packed, scale = self.decoder._packed()
         ls, _ = self.decoder._levels()
@@ -142,4 +171,7 @@ class QuantizedMatryoshkaSAE(SparseAutoencoder):
             self.decoder.bias.detach() if self.allow_bias else None,
             w_f32=lin.weight.detach().contiguous() if self.exact else None,
             w_norm_max=self._w_norm_max() if self.exact else None)
+        if self.dense_mode == "auto" and int(overflow.item()) != 0:
+            return self._forward_dense(x)
+        self.last_path = "sparse"
         return self.decoder._finish(result, counts, overflow, x.shape[0])

@@ -601,3 +601,55 @@ def test_tsae_full_size_properties(cuda_device):
     assert torch.equal(L.decode_dense(hi, None, t_bf16), recon)          # deterministic, same operand
     ref64 = (h[:64].double() @ t_bf16.double().T).float()
     assert_recon_close(exact[:64].cpu().numpy(), ref64.cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------
+# q_sae dense path (any activity level): level sums as tcgen05 GEMMs
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(cases.QSAE_CASES))
+@pytest.mark.parametrize("exact", [True, False])
+def test_qsae_dense_path_matches_reference(cuda_device, golden_dir, name, exact):
+    cfg = cases.QSAE_CASES[name]
+    if not exact and not cfg["bf16"]:
+        pytest.skip("the tensor-core encoder needs bf16-representable inputs for sign-exact activity")
+    g = np.load(golden_dir / f"{name}.npz")
+    inp = cases.qsae_inputs(cfg)
+    m = Q.QuantizedMatryoshkaSAE(cfg["D"], cfg["H"], 32, cfg["abs_range"], cfg["n_bits"], cfg["allow_bias"])
+    m.load_state_dict({"encoder.0.weight": torch.from_numpy(inp["We"]), "encoder.0.bias": torch.from_numpy(inp["be"]),
+                       "decoder.weight": torch.from_numpy(inp["W"]), "decoder.weight_mirror": torch.from_numpy(inp["Wm"]),
+                       "decoder.bias": torch.from_numpy(inp["bd"])}, strict=True)
+    m.to(cuda_device).eval()
+    m.dense_mode, m.exact = "always", exact
+    with torch.no_grad():
+        groups, result = m(T(inp["x"], cuda_device))
+    assert m.last_path == "dense"
+    np.testing.assert_allclose(np.array([float(v) for v in groups]), g["latent_group"], rtol=1e-6, atol=1e-6)
+    for i in range(cfg["n_bits"]):
+        assert_recon_close(result[i].cpu().numpy(), g["result"][i])
+    # T^T operand: bit exact against the oracle dictionary
+    Tref, _, _, _ = O.qsae_dictionary(inp["W"], inp["Wm"], n_bits=cfg["n_bits"], abs_range=cfg["abs_range"])
+    assert np.array_equal(m.decoder._t_bf16().float().cpu().numpy().astype(np.int8), Tref.T)
+
+
+def test_qsae_untrained_model_falls_back_to_dense(cuda_device):
+    """Random init, zero encoder bias: ~50 % of 32768 latents active per row (dense case).
+    The sparse path overflows its survivor lists and the forward is redone on the dense path."""
+    cfg = dict(D=512, H=32768, n_bits=4, abs_range=4.0, B=160, enc_bias=0.0, bf16=False, allow_bias=True, seed=92)
+    inp = cases.qsae_inputs(cfg)
+    m = Q.QuantizedMatryoshkaSAE(cfg["D"], cfg["H"], 32, cfg["abs_range"], cfg["n_bits"], True)
+    m.load_state_dict({"encoder.0.weight": torch.from_numpy(inp["We"]), "encoder.0.bias": torch.from_numpy(inp["be"]),
+                       "decoder.weight": torch.from_numpy(inp["W"]), "decoder.weight_mirror": torch.from_numpy(inp["Wm"]),
+                       "decoder.bias": torch.from_numpy(inp["bd"])}, strict=True)
+    m.to(cuda_device).eval()
+    with torch.no_grad():
+        groups, result = m(T(inp["x"], cuda_device))
+    assert m.last_path == "dense"
+    rg, rr, act = O.qsae_forward(inp["x"], inp["We"], inp["be"], inp["W"], inp["Wm"], inp["bd"],
+                                 n_bits=4, abs_range=4.0, allow_bias=True)
+    assert 15000 < act.sum(1).mean() < 18000
+    np.testing.assert_allclose(np.array([float(v) for v in groups]), rg, rtol=1e-6, atol=1e-6)
+    for i in range(4):
+        assert_recon_close(result[i].cpu().numpy(), rr[i])
+    m.dense_mode = "never"
+    with pytest.raises(RuntimeError, match="more active latents"):
+        m(T(inp["x"], cuda_device))
