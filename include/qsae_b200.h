@@ -216,10 +216,12 @@ int qsae_max_row_norm(const float* w_f32, int H, int D, float* out, void* stream
 
 /* The level decoder alone, for callers that already hold the active latents:
  * lists [B, cap, 2] int32 (second component = latent index), counts [B]. */
+int qsae_decode_matryoshka_lists_workspace_bytes(size_t* bytes);
 int qsae_decode_matryoshka_lists(const int32_t* lists, const int32_t* counts, int cap, int B,
                                  const uint32_t* packed, const float* scale, const int* level_start,
                                  int n_levels, int H, int D, const float* dec_bias, float* result,
-                                 unsigned long long* level_count, void* stream);
+                                 unsigned long long* level_count, void* workspace, size_t workspace_bytes,
+                                 void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * t_sae: TernarySparseAutoencoder / STEWeights (sae/ternary.py:41-52, :116-122)

@@ -47,7 +47,8 @@ SYMBOLS = {
     "qsae_matryoshka_dense_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
     "qsae_matryoshka_forward_dense": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i), _i, _vp, _i, _i, _i, _vp, _vp,
                                            _vp, _sz, _vp]),
-    "qsae_decode_matryoshka_lists": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "qsae_decode_matryoshka_lists_workspace_bytes": (_i, [C.POINTER(_sz)]),
+    "qsae_decode_matryoshka_lists": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "qsae_pack_ternary": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp]),
     "qsae_split_bf16": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "qsae_decode_dense_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
@@ -343,10 +344,14 @@ def decode_matryoshka_lists(lists, counts, cap, packed, scale, level_start, n_le
     B = counts.shape[0]
     result = torch.empty((n_levels, B, D), dtype=torch.float32, device=lists.device)
     level_count = torch.zeros((n_levels,), dtype=torch.int64, device=lists.device)
+    n = _sz(0)
+    check(load().qsae_decode_matryoshka_lists_workspace_bytes(C.byref(n)))
+    ws = _workspace(lists.device, int(n.value))
     check(load().qsae_decode_matryoshka_lists(lists.data_ptr(), counts.data_ptr(), cap, B, packed.data_ptr(),
                                               scale.data_ptr(), level_start.data_ptr(), n_levels, H, D, _ptr(dec_bias),
-                                              result.data_ptr(), level_count.data_ptr(), _stream()))
-    launch_count += 1
+                                              result.data_ptr(), level_count.data_ptr(), ws.data_ptr(), ws.numel(),
+                                              _stream()))
+    launch_count += 2
     return result, level_count
 
 
@@ -369,7 +374,7 @@ def matryoshka_forward(x, w_bf16, b_enc, packed, scale, level_start, n_levels, d
                                          scale.data_ptr(), level_start.data_ptr(), n_levels, _ptr(dec_bias), B, H, D,
                                          result.data_ptr(), counts.data_ptr(), overflow.data_ptr(), ws.data_ptr(),
                                          ws.numel(), _stream()))
-    launch_count += 3
+    launch_count += 4
     return result, counts, overflow
 
 

@@ -147,13 +147,17 @@ const char* decode_matryoshka_launch(const void* cand, const int* cand_cnt, int 
                                      const uint32_t* packed, const float* scale, const int* level_start,
                                      int n_levels, int H, int D, const float* bias, float* result,
                                      unsigned long long* level_count, const float* x_f32, const float* w_f32,
-                                     const float* b_enc, float thr_value, int exact, cudaStream_t stream);
+                                     const float* b_enc, float thr_value, int exact, void* scratch, int num_sms,
+                                     cudaStream_t stream);
+// scratch of decode_matryoshka_launch (per-warp activity counts before the final sum)
+size_t decode_matryoshka_scratch_bytes(int num_sms);
 // packed 2-bit codes [H, D/16] -> T^T as bf16 [D, H] with entries {-2, 0, +2} (B operand of the dense level GEMMs)
 const char* unpack_matryoshka_t_launch(const uint32_t* packed, int H, int D, uint16_t* t_bf16, cudaStream_t stream);
 // z [B, H] -> a = (z >= thr) * scale[h] split into bf16 hi / lo [B, H]; level_count[l] += active entries of level l
 const char* matryoshka_dense_operand_launch(const float* z, int B, int H, const float* scale, float thr,
                                             const int* level_start, int n_levels, uint16_t* a_hi, uint16_t* a_lo,
-                                            unsigned long long* level_count, cudaStream_t stream);
+                                            unsigned long long* level_count, void* scratch, cudaStream_t stream);
+size_t matryoshka_dense_operand_scratch_bytes();
 const char* max_row_norm_launch(const float* w, int H, int D, float* out, cudaStream_t stream);
 const char* row_threshold_launch(const float* x, int B, int D, const float* wmax, float thr_value, float* thr,
                                  cudaStream_t stream);

@@ -369,7 +369,7 @@ int qsae_pack_matryoshka(const float* weight, const float* weight_mirror, int H,
 }
 
 namespace {
-struct MatPlan { StagePlan st; size_t x_off, prior_off, total; };
+struct MatPlan { StagePlan st; size_t x_off, prior_off, scratch_off, total; };
 constexpr float kActiveThreshold = 8.940697e-08f;  // sigmoid(z) > 0.5 in fp32 <=> z >= 1.5 * 2^-24
 int plan_matryoshka(int B, int H, int D, MatPlan* mp) {
   if (B <= 0 || H <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "B and H must be positive");
@@ -382,7 +382,8 @@ int plan_matryoshka(int B, int H, int D, MatPlan* mp) {
   mp->st.cnt_off = mp->st.cand_off + static_cast<size_t>(B) * mp->st.nsub * mp->st.cap * 8;
   mp->st.thr_off = mp->st.cnt_off + static_cast<size_t>(B) * mp->st.nsub * 4;
   mp->st.end = align_up(mp->st.thr_off + static_cast<size_t>(B) * mp->st.nsub * 4, 256);
-  mp->total = mp->st.end;
+  mp->scratch_off = mp->st.end;
+  mp->total = align_up(mp->scratch_off + decode_matryoshka_scratch_bytes(num_sms()), 256);
   return QSAE_OK;
 }
 }  // namespace
@@ -401,19 +402,29 @@ int qsae_max_row_norm(const float* w_f32, int H, int D, float* out, void* stream
   return launch_status("max_row_norm", max_row_norm_launch(w_f32, H, D, out, S(stream)));
 }
 
+int qsae_decode_matryoshka_lists_workspace_bytes(size_t* bytes) {
+  if (!bytes) return fail(QSAE_ERR_INVALID_ARGUMENT, "workspace query: null pointer");
+  *bytes = align_up(decode_matryoshka_scratch_bytes(num_sms()), 256);
+  return QSAE_OK;
+}
+
 int qsae_decode_matryoshka_lists(const int32_t* lists, const int32_t* counts, int cap, int B, const uint32_t* packed,
                                  const float* scale, const int* level_start, int n_levels, int H, int D,
-                                 const float* dec_bias, float* result, unsigned long long* level_count, void* stream) {
+                                 const float* dec_bias, float* result, unsigned long long* level_count,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
   if (B == 0) return QSAE_OK;
-  if (!lists || !counts || !packed || !scale || !level_start || !result || !level_count)
+  if (!lists || !counts || !packed || !scale || !level_start || !result || !level_count || !workspace)
     return fail(QSAE_ERR_INVALID_ARGUMENT, "decode_matryoshka_lists: null pointer");
-  if (n_levels < 1 || n_levels > 32 || (D % 16) != 0 || D > 512 || cap < 1)
-    return fail(QSAE_ERR_INVALID_ARGUMENT, "decode_matryoshka_lists: bad shape");
+  if (n_levels < 1 || n_levels > 8 || (D % 16) != 0 || D > 512 || cap < 1)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "decode_matryoshka_lists: need 1 <= n_levels <= 8, D %% 16 == 0, D <= 512");
+  if (workspace_bytes < decode_matryoshka_scratch_bytes(num_sms()))
+    return fail(QSAE_ERR_WORKSPACE_TOO_SMALL, "decode_matryoshka_lists: workspace too small");
   cudaError_t ce = cudaMemsetAsync(level_count, 0, static_cast<size_t>(n_levels) * sizeof(unsigned long long), S(stream));
   if (ce != cudaSuccess) return fail(QSAE_ERR_CUDA, "decode_matryoshka_lists: %s", cudaGetErrorString(ce));
   return launch_status("decode_matryoshka", decode_matryoshka_launch(lists, counts, 1, cap, B, packed, scale, level_start,
                                                                      n_levels, H, D, dec_bias, result, level_count,
-                                                                     nullptr, nullptr, nullptr, 0.f, 0, S(stream)));
+                                                                     nullptr, nullptr, nullptr, 0.f, 0, workspace, num_sms(),
+                                                                     S(stream)));
 }
 
 int qsae_matryoshka_forward(const float* x_f32, const uint16_t* w_bf16, const float* w_f32, const float* w_norm_max,
@@ -424,7 +435,7 @@ int qsae_matryoshka_forward(const float* x_f32, const uint16_t* w_bf16, const fl
   if (B == 0) return QSAE_OK;
   if (!x_f32 || !w_bf16 || !b_enc || !packed || !scale || !level_start || !result || !level_count || !overflow || !workspace)
     return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_forward: null pointer");
-  if (n_levels < 1 || n_levels > 32) return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_forward: 1 <= n_levels <= 32");
+  if (n_levels < 1 || n_levels > 8) return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_forward: 1 <= n_levels <= 8");
   const int exact = (w_f32 != nullptr) ? 1 : 0;
   if (exact && !w_norm_max) return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_forward: exact mode needs w_norm_max");
   MatPlan mp;
@@ -455,7 +466,7 @@ int qsae_matryoshka_forward(const float* x_f32, const uint16_t* w_bf16, const fl
   return launch_status("decode_matryoshka", decode_matryoshka_launch(el.cand, el.cand_cnt, mp.st.nsub, mp.st.cap, B, packed,
                                                                      scale, level_start, n_levels, H, D, dec_bias, result,
                                                                      level_count, x_f32, w_f32, b_enc, kActiveThreshold,
-                                                                     exact, st));
+                                                                     exact, ws + mp.scratch_off, num_sms(), st));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -580,7 +591,7 @@ int qsae_unpack_matryoshka_t(const uint32_t* packed, int H, int D, uint16_t* t_b
 }
 
 namespace {
-struct MatDensePlan { size_t x_off, z_off, hi_off, lo_off, dec_off, total; };
+struct MatDensePlan { size_t x_off, z_off, hi_off, lo_off, cnt_off, dec_off, total; };
 int plan_matryoshka_dense(int B, int H, int D, MatDensePlan* mp) {
   if (B <= 0 || H <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "B and H must be positive");
   if (D < 16 || D > 512 || (D % 16) != 0)
@@ -591,7 +602,8 @@ int plan_matryoshka_dense(int B, int H, int D, MatDensePlan* mp) {
   mp->z_off = align_up(static_cast<size_t>(B) * D * 2, 1024);
   mp->hi_off = align_up(mp->z_off + bh * 4, 1024);
   mp->lo_off = align_up(mp->hi_off + bh * 2, 1024);
-  mp->dec_off = align_up(mp->lo_off + bh * 2, 1024);
+  mp->cnt_off = align_up(mp->lo_off + bh * 2, 1024);
+  mp->dec_off = align_up(mp->cnt_off + matryoshka_dense_operand_scratch_bytes(), 1024);
   mp->total = align_up(mp->dec_off + 16 * static_cast<size_t>(B) * D * sizeof(float), 256);   // up to 16 K splits
   return QSAE_OK;
 }
@@ -656,7 +668,7 @@ int qsae_matryoshka_forward_dense(const float* x_f32, const uint16_t* w_bf16, co
   // 2. A = active * scale, split into bf16 hi / lo; activity counts per level
   rc = launch_status("matryoshka_dense_operand",
                      matryoshka_dense_operand_launch(z, B, H, scale, kActiveThreshold, level_start_dev, n_levels, a_hi, a_lo,
-                                                     level_count, st));
+                                                     level_count, ws + mp.cnt_off, st));
   if (rc != QSAE_OK) return rc;
   // 3. one GEMM per level over its K range, outputs accumulated level by level (:121-129)
   const size_t bd = static_cast<size_t>(B) * D;
