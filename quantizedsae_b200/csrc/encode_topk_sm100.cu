@@ -454,10 +454,16 @@ __device__ __forceinline__ void epilogue_dense(const EncodeLaunch& p, const CUte
   __syncwarp();
 }
 
-template <int K_CHUNKS, bool DENSE>
+// MCAST: launched as clusters of two CTAs along the row-block axis. The pair sweeps the same W
+// tiles in lockstep; each CTA fetches half of every 256 x 64 stage (128 latents) and TMA-multicasts
+// it into both CTAs' rings, so the pair reads W from L2 once instead of twice. The kernel streams W
+// at the L2 slice throughput limit (~6300 B/clk chip-wide), which makes this the lever for the
+// variants that also push their outputs through L2 (dense epilogue).
+template <int K_CHUNKS, bool DENSE, bool MCAST>
 __global__ void __launch_bounds__(kThreads, 1)
 encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
                    const __grid_constant__ CUtensorMap tmap_w,
+                   const __grid_constant__ CUtensorMap tmap_wh,
                    const __grid_constant__ CUtensorMap tmap_o32,
                    const __grid_constant__ CUtensorMap tmap_ohi,
                    const __grid_constant__ CUtensorMap tmap_olo, EncodeLaunch p) {
@@ -484,6 +490,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
   const int tile_begin = split * p.tiles_per_split;
   const int tile_end = min(p.n_tiles, tile_begin + p.tiles_per_split);
   const int n_my_tiles = max(0, tile_end - tile_begin);
+  const uint32_t cta_rank = MCAST ? cluster_ctarank() : 0u;
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0u) {
@@ -493,7 +500,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
     mbar_init(a_full, 1);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], MCAST ? 2 : 1);   // multicast: both CTAs' MMAs must have released the stage
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -507,6 +514,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
   if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
+  if constexpr (MCAST) cluster_sync_all();   // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -527,8 +535,14 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
         for (int kc = 0; kc < K_CHUNKS; ++kc) {
           mbar_wait(&empty[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full[stage], kBBytesPerStage);
-          tma_load_2d(b_smem + stage * kBBytesPerStage, &tmap_w, &full[stage], kc * BK, n0,
-                      kPolicyEvictLast);
+          if constexpr (MCAST) {
+            // my half of the stage lands in both CTAs; the other half arrives from the peer
+            tma_load_2d_mcast(b_smem + stage * kBBytesPerStage + cta_rank * (kBBytesPerStage / 2), &tmap_wh,
+                              &full[stage], kc * BK, n0 + static_cast<int>(cta_rank) * (BN / 2), 0x3, kPolicyEvictLast);
+          } else {
+            tma_load_2d(b_smem + stage * kBBytesPerStage, &tmap_w, &full[stage], kc * BK, n0,
+                        kPolicyEvictLast);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -559,7 +573,8 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
             // (address >> 4) field of the descriptor
             umma_f16_ss(d_tmem, a_desc + ks * 2, b_desc + ks * 2, idesc, (kc | ks) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);
+          if constexpr (MCAST) umma_commit_mcast(&empty[stage], 0x3);
+          else umma_commit(&empty[stage]);
           if (kc == K_CHUNKS - 1) umma_commit(&tmem_full[acc]);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -616,6 +631,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (MCAST) cluster_sync_all();   // no CTA leaves while its peer may still write into it
   tc_fence_after();
   if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
 }
@@ -657,39 +673,67 @@ bool make_tmap_bf16(CUtensorMap* map, const void* base, int rows, int cols, int 
                       CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int K_CHUNKS, bool DENSE>
-cudaError_t launch_k(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& o32, const CUtensorMap& ohi,
-                     const CUtensorMap& olo, const EncodeLaunch& p, cudaStream_t stream) {
+template <int K_CHUNKS, bool DENSE, bool MCAST>
+cudaError_t launch_k(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& twh, const CUtensorMap& o32,
+                     const CUtensorMap& ohi, const CUtensorMap& olo, const EncodeLaunch& p, cudaStream_t stream) {
   const SmemLayout L = smem_layout(K_CHUNKS, DENSE);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(encode_topk_kernel<K_CHUNKS, DENSE>,
+    cudaError_t e = cudaFuncSetAttribute(encode_topk_kernel<K_CHUNKS, DENSE, MCAST>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   dim3 grid(p.n_splits, (p.B + BM - 1) / BM);
-  encode_topk_kernel<K_CHUNKS, DENSE><<<grid, kThreads, L.total, stream>>>(tx, tw, o32, ohi, olo, p);
-  return cudaGetLastError();
+  if constexpr (MCAST) {
+    grid.y = (grid.y + 1) / 2 * 2;   // whole clusters; the padding CTA sweeps zero rows and writes nothing
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = L.total;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1;
+    at[0].val.clusterDim.y = 2;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, encode_topk_kernel<K_CHUNKS, DENSE, MCAST>, tx, tw, twh, o32, ohi, olo, p);
+  } else {
+    encode_topk_kernel<K_CHUNKS, DENSE, MCAST><<<grid, kThreads, L.total, stream>>>(tx, tw, twh, o32, ohi, olo, p);
+    return cudaGetLastError();
+  }
 }
 
 template <bool DENSE>
-const char* launch_any(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& o32, const CUtensorMap& ohi,
-                       const CUtensorMap& olo, const EncodeLaunch& p, cudaStream_t stream) {
+const char* launch_any(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& twh, const CUtensorMap& o32,
+                       const CUtensorMap& ohi, const CUtensorMap& olo, const EncodeLaunch& p, cudaStream_t stream) {
   const int kc = (p.D + BK - 1) / BK;
   cudaError_t e;
   switch (kc) {
-    case 1: e = launch_k<1, DENSE>(tx, tw, o32, ohi, olo, p, stream); break;
-    case 2: e = launch_k<2, DENSE>(tx, tw, o32, ohi, olo, p, stream); break;
-    case 3: e = launch_k<3, DENSE>(tx, tw, o32, ohi, olo, p, stream); break;
-    case 4: e = launch_k<4, DENSE>(tx, tw, o32, ohi, olo, p, stream); break;
-    case 5: e = launch_k<5, DENSE>(tx, tw, o32, ohi, olo, p, stream); break;
-    case 6: e = launch_k<6, DENSE>(tx, tw, o32, ohi, olo, p, stream); break;
-    case 7: e = launch_k<7, DENSE>(tx, tw, o32, ohi, olo, p, stream); break;
-    case 8: e = launch_k<8, DENSE>(tx, tw, o32, ohi, olo, p, stream); break;
+    case 1: e = launch_k<1, DENSE, false>(tx, tw, twh, o32, ohi, olo, p, stream); break;
+    case 2: e = launch_k<2, DENSE, false>(tx, tw, twh, o32, ohi, olo, p, stream); break;
+    case 3: e = launch_k<3, DENSE, false>(tx, tw, twh, o32, ohi, olo, p, stream); break;
+    case 4: e = launch_k<4, DENSE, false>(tx, tw, twh, o32, ohi, olo, p, stream); break;
+    case 5: e = launch_k<5, DENSE, false>(tx, tw, twh, o32, ohi, olo, p, stream); break;
+    case 6: e = launch_k<6, DENSE, false>(tx, tw, twh, o32, ohi, olo, p, stream); break;
+    case 7: e = launch_k<7, DENSE, false>(tx, tw, twh, o32, ohi, olo, p, stream); break;
+    case 8:   // the headline width: the multicast pair variant exists here
+      e = p.mcast ? launch_k<8, DENSE, true>(tx, tw, twh, o32, ohi, olo, p, stream)
+                  : launch_k<8, DENSE, false>(tx, tw, twh, o32, ohi, olo, p, stream);
+      break;
     default: return "D must be <= 512";
   }
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+// Multicast pairs need two row blocks per cluster. Measured on B200 (B = 65536, k = 32): -2 % on the whole
+// selection call, nothing on the dense-epilogue variant and +1 % at B = 4096 (the L2 already merges the
+// two CTAs' requests for the same W lines most of the time), so it is on only for large sparse sweeps.
+bool want_mcast(const EncodeLaunch& p, bool dflt) {
+  if (const char* m = getenv("QSAE_ENCODE_MCAST")) dflt = atoi(m) != 0;   // tests and tuning experiments
+  return dflt && p.D > 448 && p.B > BM;
 }
 
 }  // namespace
@@ -725,7 +769,10 @@ const char* encode_topk_launch(const uint16_t* x_bf16, const uint16_t* w_bf16, E
   if (!make_tmap_bf16(&tx, x_bf16, p.B, p.D, BM)) return "cuTensorMapEncodeTiled(x) failed";
   if (!make_tmap_bf16(&tw, w_bf16, p.H, p.D, BN)) return "cuTensorMapEncodeTiled(W) failed";
   p.dense_flags = 0;
-  return launch_any<false>(tx, tw, tx, tx, tx, p, stream);
+  p.mcast = want_mcast(p, p.B >= 16384) ? 1 : 0;
+  CUtensorMap twh = tw;
+  if (p.mcast && !make_tmap_bf16(&twh, w_bf16, p.H, p.D, BN / 2)) return "cuTensorMapEncodeTiled(W half) failed";
+  return launch_any<false>(tx, tw, twh, tx, tx, tx, p, stream);
 }
 
 const char* encode_dense_tc_launch(const uint16_t* x_bf16, const uint16_t* w_bf16, EncodeLaunch p, float* out_f32,
@@ -747,7 +794,10 @@ const char* encode_dense_tc_launch(const uint16_t* x_bf16, const uint16_t* w_bf1
   if (out_lo && !make_tmap_2d(&olo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out_lo, p.B, p.H, 32, 32,
                               CU_TENSOR_MAP_SWIZZLE_64B))
     return "cuTensorMapEncodeTiled(h lo) failed";
-  return launch_any<true>(tx, tw, o32, ohi, olo, p, stream);
+  p.mcast = want_mcast(p, false) ? 1 : 0;
+  CUtensorMap twh = tw;
+  if (p.mcast && !make_tmap_bf16(&twh, w_bf16, p.H, p.D, BN / 2)) return "cuTensorMapEncodeTiled(W half) failed";
+  return launch_any<true>(tx, tw, twh, o32, ohi, olo, p, stream);
 }
 
 }  // namespace qsae
