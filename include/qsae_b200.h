@@ -209,6 +209,11 @@ int qsae_matryoshka_forward_dense(const float* x_f32, const uint16_t* w_bf16, co
                                   unsigned long long* level_count /* [n_levels] */, void* workspace,
                                   size_t workspace_bytes, void* stream);
 
+/* rq_sae (ResidualQuantizedSAE.forward, sae/residual_quantized.py:53-69): a cascade of one-bit q_saes, each
+ * run with qsae_matryoshka_forward (n_levels = 1) on the residual of the previous stage;
+ * this is the step between stages (:67): out = (residual - recon) * 2. out may alias residual. */
+int qsae_residual_update(const float* residual, const float* recon, size_t n, float* out, void* stream);
+
 /* max_h ||w[h,:]||_2 -> *out (device float). With w_f32 given, qsae_matryoshka_forward lowers each
  * row's sweep threshold by the bound 2^-8 ||x_b|| max_h||w_h|| on |z_bf16 - z_fp32| and decides
  * activity from an fp32 re-scoring, so the active set equals the fp32 reference's for any input. */

@@ -271,6 +271,20 @@ def qsae_forward(x, We, be, W, Wm, bd, *, n_bits: int, abs_range: float, allow_b
     return groups.astype(F32), result.astype(F32), act
 
 
+def rqsae_forward(x, stages, *, abs_range: float):
+    """ResidualQuantizedSAE.forward (sae/residual_quantized.py:53-69): stage t is a one-bit
+    QuantizedMatryoshkaSAE on the residual r_t (bias only in stage 0, :46); r_{t+1} = 2 (r_t - recon_t).
+    ``stages``: list of (We, be, W, Wm, bd). Returns (latent_group [T], recon [T, B, D])."""
+    r = x.astype(F32)
+    groups, recons = [], []
+    for t, (We, be, W, Wm, bd) in enumerate(stages):
+        g, res, _ = qsae_forward(r, We, be, W, Wm, bd, n_bits=1, abs_range=abs_range, allow_bias=(t == 0))
+        groups.append(g[-1])
+        recons.append(res[-1])
+        r = ((r - res[-1]) * F32(2)).astype(F32)
+    return np.array(groups, dtype=F32), np.stack(recons).astype(F32)
+
+
 # --------------------------------------------------------------------------------------
 # dense float32 port of BinarySAE.forward, op-for-op (CPU baseline timing only)
 # --------------------------------------------------------------------------------------

@@ -5,9 +5,9 @@ return structure); all arithmetic runs in libqsae_b200.so (hand-written CUDA beh
 include/qsae_b200.h). Importing this package does not need a GPU; running a forward does.
 """
 from .sae import (BaselineSparseAutoencoder, BinarySAE, QuantizedMatryoshkaDecoder, QuantizedMatryoshkaSAE,
-                  SparseAutoencoder, STEWeights, TernarySparseAutoencoder, binary_decoder)
+                  ResidualQuantizedSAE, SparseAutoencoder, STEWeights, TernarySparseAutoencoder, binary_decoder)
 from .sparse import SparseLatents
 
 __version__ = "0.1.0"
 __all__ = ["BaselineSparseAutoencoder", "BinarySAE", "SparseAutoencoder", "binary_decoder", "SparseLatents",
-           "QuantizedMatryoshkaDecoder", "QuantizedMatryoshkaSAE", "STEWeights", "TernarySparseAutoencoder"]
+           "QuantizedMatryoshkaDecoder", "QuantizedMatryoshkaSAE", "STEWeights", "TernarySparseAutoencoder", "ResidualQuantizedSAE"]

@@ -43,6 +43,7 @@ SYMBOLS = {
     "qsae_matryoshka_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
     "qsae_matryoshka_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "qsae_max_row_norm": (_i, [_vp, _i, _i, _vp, _vp]),
+    "qsae_residual_update": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "qsae_unpack_matryoshka_t": (_i, [_vp, _i, _i, _vp, _vp]),
     "qsae_matryoshka_dense_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
     "qsae_matryoshka_forward_dense": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i), _i, _vp, _i, _i, _i, _vp, _vp,
@@ -516,3 +517,13 @@ def matryoshka_forward_dense(x, w_bf16, w_f32, b_enc, t_bf16, scale, level_start
                                                ws.data_ptr(), ws.numel(), _stream()))
     launch_count += 3 + 2 * n_levels
     return result, counts
+
+
+def residual_update(residual: torch.Tensor, recon: torch.Tensor) -> torch.Tensor:
+    """(residual - recon) * 2 (sae/residual_quantized.py:67)."""
+    global launch_count
+    _need_cuda(residual, recon)
+    out = torch.empty_like(residual)
+    check(load().qsae_residual_update(residual.data_ptr(), recon.data_ptr(), residual.numel(), out.data_ptr(), _stream()))
+    launch_count += 1
+    return out

@@ -118,6 +118,8 @@ const char* pack_bitplanes_launch(const float* logits, int H, int D, int n_bits,
 const char* dequant_soft_launch(const float* logits, int H, int D, int n_bits, float* rows,
                                 cudaStream_t stream);
 const char* transpose_launch(const float* src, int R, int C, float* dst, cudaStream_t stream);
+// out = (r - recon) * 2 (rq_sae residual step)
+const char* residual_update_launch(const float* r, const float* recon, size_t n, float* out, cudaStream_t stream);
 // src -> hi = bf16(src), lo = bf16(src - hi) (lo may be null)
 const char* split_bf16_launch(const float* src, uint16_t* hi, uint16_t* lo, size_t n, cudaStream_t stream);
 // t_sae decoder.weight [D, H] -> sign(w) * (|w| >= threshold): bf16 [D, H] and/or int8 rows [H, D]

@@ -170,6 +170,19 @@ __global__ void pack_ternary_kernel(const float* __restrict__ w, int D, int H, f
   }
 }
 
+// rq_sae residual step (sae/residual_quantized.py:67): out = (r - recon) * 2
+__global__ void residual_update_kernel(const float* __restrict__ r, const float* __restrict__ recon, size_t n,
+                                       float* __restrict__ out) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t n4 = n / 4;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = reinterpret_cast<const float4*>(r)[i], b = reinterpret_cast<const float4*>(recon)[i];
+    reinterpret_cast<float4*>(out)[i] = make_float4((a.x - b.x) * 2.f, (a.y - b.y) * 2.f, (a.z - b.z) * 2.f, (a.w - b.w) * 2.f);
+  }
+  for (size_t i = n4 * 4 + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = (r[i] - recon[i]) * 2.f;
+}
+
 __global__ void transpose_kernel(const float* __restrict__ src, int R, int C, float* __restrict__ dst) {
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -240,6 +253,11 @@ const char* dequant_soft_launch(const float* logits, int H, int D, int n_bits, f
 const char* sample_rows_launch(const uint16_t* w_bf16, const float* bias, int H, int D, int n_sample,
                                uint16_t* w_sample, float* b_sample, cudaStream_t stream) {
   sample_rows_kernel<<<n_sample, 128, 0, stream>>>(w_bf16, bias, H, D, n_sample, w_sample, b_sample);
+  return cuda_err(cudaGetLastError());
+}
+
+const char* residual_update_launch(const float* r, const float* recon, size_t n, float* out, cudaStream_t stream) {
+  residual_update_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, stream>>>(r, recon, n, out);
   return cuda_err(cudaGetLastError());
 }
 

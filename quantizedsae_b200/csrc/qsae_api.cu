@@ -683,6 +683,14 @@ int qsae_matryoshka_forward_dense(const float* x_f32, const uint16_t* w_bf16, co
   return QSAE_OK;
 }
 
+int qsae_residual_update(const float* residual, const float* recon, size_t n, float* out, void* stream) {
+  if (n == 0) return QSAE_OK;
+  if (!residual || !recon || !out) return fail(QSAE_ERR_INVALID_ARGUMENT, "residual_update: null pointer");
+  if ((reinterpret_cast<uintptr_t>(residual) | reinterpret_cast<uintptr_t>(recon) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "residual_update: buffers must be 16-byte aligned");
+  return launch_status("residual_update", residual_update_launch(residual, recon, n, out, S(stream)));
+}
+
 int qsae_encode_dense_f32(const float* x_f32, const int32_t* rows, int R, const float* w_f32,
                           const float* b_enc, int H, int D, int act, float* z, void* stream) {
   if (R == 0) return QSAE_OK;

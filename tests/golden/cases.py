@@ -59,6 +59,13 @@ QSAE_CASES = {
 }
 
 
+# rq_sae (next row): cascade of n_bits one-bit q_saes on doubled residuals
+RQSAE_CASES = {
+    "rqsae_d64_h2048":  dict(D=64,  H=2048, n_bits=4, abs_range=4.0, B=32, enc_bias=-0.3, seed=51),
+    "rqsae_d512_h4096": dict(D=512, H=4096, n_bits=3, abs_range=2.0, B=24, enc_bias=-0.5, seed=52),
+}
+
+
 def bsae_inputs(cfg: dict) -> dict:
     """Synthetic weights/inputs shaped like SURVEY.md 8(d) config 1 (scaled down)."""
     rng = np.random.default_rng(cfg["seed"])
@@ -115,6 +122,37 @@ def qsae_inputs(cfg: dict) -> dict:
     if cfg["bf16"]:
         We, x = round_bf16(We), round_bf16(x)
     return dict(x=x, We=We, be=be, W=W, Wm=Wm, bd=bd)
+
+
+def rqsae_inputs(cfg: dict) -> dict:
+    """Per-stage weights of ResidualQuantizedSAE (sae/residual_quantized.py:13-49): stage i is a
+    QuantizedMatryoshkaSAE(input_dim, sizes[i], n_bits=1)."""
+    rng = np.random.default_rng(cfg["seed"])
+    D, H, B, nb = cfg["D"], cfg["H"], cfg["B"], cfg["n_bits"]
+    sizes = [1 if i < 2 else 2 ** (i - 1) for i in range(nb)]
+    f = H / sum(sizes)
+    if sum(sizes) != H:
+        sizes = [max(1, int(s * f)) for s in sizes]
+        sizes[-1] = H - sum(sizes[:-1])
+    out = dict(x=rng.standard_normal((B, D)).astype(F32))
+    for i, hs in enumerate(sizes):
+        out[f"We{i}"] = xavier_uniform(rng, hs, D)
+        out[f"be{i}"] = (cfg["enc_bias"] + 0.01 * rng.standard_normal(hs)).astype(F32)
+        out[f"W{i}"] = away_from_zero(xavier_uniform(rng, hs, D))
+        out[f"Wm{i}"] = away_from_zero(xavier_uniform(rng, hs, D))
+        out[f"bd{i}"] = rng.standard_normal(D).astype(F32)
+    return out
+
+
+def rqsae_state_dict(inp: dict, n_bits: int) -> dict:
+    sd = {}
+    for i in range(n_bits):
+        sd[f"saes.{i}.encoder.0.weight"] = inp[f"We{i}"]
+        sd[f"saes.{i}.encoder.0.bias"] = inp[f"be{i}"]
+        sd[f"saes.{i}.decoder.weight"] = inp[f"W{i}"]
+        sd[f"saes.{i}.decoder.weight_mirror"] = inp[f"Wm{i}"]
+        sd[f"saes.{i}.decoder.bias"] = inp[f"bd{i}"]
+    return sd
 
 
 def checksum(arrays: dict) -> str:

@@ -118,6 +118,23 @@ def make_qsae(ref, name, cfg):
     )
 
 
+def make_rqsae(ref, name, cfg):
+    inp = cases.rqsae_inputs(cfg)
+    m = ref.ResidualQuantizedSAE(cfg["D"], cfg["H"], 32, cfg["abs_range"], cfg["n_bits"])
+    m.load_state_dict({k: T(v) for k, v in cases.rqsae_state_dict(inp, cfg["n_bits"]).items()}, strict=True)
+    m.eval()
+    with torch.no_grad():
+        groups, recons = m(T(inp["x"]))
+    np.savez_compressed(
+        OUT / f"{name}.npz", input_sha=cases.checksum(inp),
+        latent_group=np.array([g.item() for g in groups], dtype=np.float64),
+        recon=np.stack([_np(r) for r in recons]),
+        stage_sizes=np.array(m.sae_hidden_dims),
+        state_keys=np.array(sorted(m.state_dict().keys())),
+        state_shapes=np.array([str(tuple(v.shape)) for _, v in sorted(m.state_dict().items())]),
+    )
+
+
 def make_misc(ref):
     """Known answers that are not tied to a seeded case."""
     # README.md:100 -- MSB-first [1,0,1,0] == storage order (LSB-first) [0,1,0,1] -> -6 -> -3.0
@@ -148,6 +165,12 @@ def make_misc(ref):
 def main():
     torch.manual_seed(0)
     ref = ref_shim.load()
+    if "--only-rqsae" in sys.argv:       # added after the first fixture set was committed
+        for name, cfg in cases.RQSAE_CASES.items():
+            make_rqsae(ref, name, cfg)
+        return
+    for name, cfg in cases.RQSAE_CASES.items():
+        make_rqsae(ref, name, cfg)
     for name, cfg in cases.BSAE_CASES.items():
         make_bsae(ref, name, cfg)
     for name, cfg in cases.BASELINE_CASES.items():

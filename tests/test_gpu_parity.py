@@ -673,3 +673,25 @@ def test_multicast_pair_variant_is_bit_identical(cuda_device, monkeypatch, mcast
     v0, i0, _ = L.encode_topk(dx, wb, None, db, k, sample=L.prepare_sample(wb, db))
     h0, r0 = L.tsae_forward(dx, wb, None, db, t_bf16, exact=False)
     assert torch.equal(vals, v0) and torch.equal(idx, i0) and torch.equal(h, h0) and torch.equal(recon, r0)
+
+
+# ------------------------------------------------------------------------------------------
+# rq_sae (residual cascade of one-bit q_saes) vs the reference's own outputs
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(cases.RQSAE_CASES))
+def test_rqsae_module_matches_reference(cuda_device, golden_dir, name):
+    cfg = cases.RQSAE_CASES[name]
+    g = np.load(golden_dir / f"{name}.npz")
+    inp = cases.rqsae_inputs(cfg)
+    m = Q.ResidualQuantizedSAE(cfg["D"], cfg["H"], 32, cfg["abs_range"], cfg["n_bits"])
+    assert m.sae_hidden_dims == g["stage_sizes"].tolist()
+    assert sorted(m.state_dict().keys()) == g["state_keys"].tolist()
+    assert [str(tuple(v.shape)) for _, v in sorted(m.state_dict().items())] == g["state_shapes"].tolist()
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in cases.rqsae_state_dict(inp, cfg["n_bits"]).items()}, strict=True)
+    m.to(cuda_device).eval()
+    with torch.no_grad():
+        groups, recons = m(T(inp["x"], cuda_device))
+    assert len(groups) == len(recons) == cfg["n_bits"]
+    np.testing.assert_allclose(np.array([float(v) for v in groups]), g["latent_group"], rtol=1e-6, atol=1e-6)
+    for t in range(cfg["n_bits"]):
+        assert_recon_close(recons[t].cpu().numpy(), g["recon"][t])

@@ -150,3 +150,18 @@ def test_topk_tie_rule():
     assert O.topk_rows(z, 4)[1].tolist() == [[512, 0, 1, 2]]
     with pytest.raises(RuntimeError):
         O.topk_rows(z, 2048)
+
+
+@pytest.mark.parametrize("name", list(cases.RQSAE_CASES))
+def test_rqsae_matches_reference(golden_dir, name):
+    cfg = cases.RQSAE_CASES[name]
+    g = np.load(golden_dir / f"{name}.npz")
+    inp = cases.rqsae_inputs(cfg)
+    assert cases.checksum(inp) == str(g["input_sha"])
+    stages = [(inp[f"We{i}"], inp[f"be{i}"], inp[f"W{i}"], inp[f"Wm{i}"], inp[f"bd{i}"]) for i in range(cfg["n_bits"])]
+    groups, recons = O.rqsae_forward(inp["x"], stages, abs_range=cfg["abs_range"])
+    assert O.matryoshka_level_sizes(cfg["H"], cfg["n_bits"]) == g["stage_sizes"].tolist()
+    np.testing.assert_allclose(groups, g["latent_group"], rtol=1e-6, atol=1e-6)
+    for t in range(cfg["n_bits"]):
+        rms = float(np.sqrt(np.mean(g["recon"][t].astype(np.float64) ** 2)))
+        np.testing.assert_allclose(recons[t], g["recon"][t], rtol=2e-5, atol=2e-5 * rms)
