@@ -695,3 +695,27 @@ def test_rqsae_module_matches_reference(cuda_device, golden_dir, name):
     np.testing.assert_allclose(np.array([float(v) for v in groups]), g["latent_group"], rtol=1e-6, atol=1e-6)
     for t in range(cfg["n_bits"]):
         assert_recon_close(recons[t].cpu().numpy(), g["recon"][t])
+
+
+def test_inference_wrapper_on_gpu(cuda_device, golden_dir, tmp_path):
+    """load_sae -> SAEWrapper on the B200 modules: output dictionaries of inference/framework.py:76-111 and
+    the b_sae dictionary export (:114-124) against the reference fixture."""
+    from quantizedsae_b200 import inference as I
+
+    name = "bsae_polar_d64_h2048"
+    cfg, g = cases.BSAE_CASES[name], np.load(golden_dir / f"{name}.npz")
+    inp = cases.bsae_inputs(cfg)
+    torch.save({"encoder.0.weight": torch.from_numpy(inp["We"]), "encoder.0.bias": torch.from_numpy(inp["be"]),
+                "decoder.weight": torch.from_numpy(inp["logits"]), "decoder.bias": torch.from_numpy(inp["bd"])},
+               tmp_path / "b.pth")
+    w = I.load_sae("b_sae", device=cuda_device, checkpoint_path=tmp_path / "b.pth", input_dim=cfg["D"], hidden_dim=cfg["H"],
+                   gamma=cfg["gamma"], n_bits=cfg["n_bits"])
+    out = w([torch.from_numpy(inp["x"])])                       # DataLoader-style 1-list, host tensor
+    assert set(out) == {"latent", "reconstruction", "aux"} and "polarize_loss" in out["aux"]
+    assert_recon_close(out["reconstruction"].cpu().numpy(), g["recon"])
+    assert tuple(out["latent"].shape) == (cfg["B"], cfg["H"])
+    d = w.decoder_dictionary()
+    ref = O.dequant_hard(inp["logits"], cfg["n_bits"]).astype(np.float32) * (cfg["gamma"] / 2 ** (cfg["n_bits"] - 1))
+    assert np.array_equal(d["weight"].numpy(), ref) and not d["weight"].is_cuda
+    recs = list(w.reconstruct_loader([torch.from_numpy(inp["x"][:8]), torch.from_numpy(inp["x"][8:])]))
+    assert_recon_close(torch.cat(recs).cpu().numpy(), g["recon"])

@@ -175,3 +175,47 @@ def test_oracle_is_not_imported_by_the_product():
     for path in (ROOT / "quantizedsae_b200").rglob("*.py"):
         text = path.read_text()
         assert "oracle" not in re.sub(r"#.*", "", text).replace("no oracle", ""), path
+
+
+def test_inference_registry_mirrors_the_reference(tmp_path):
+    """Registry keys / kwargs of inference/framework.py:165-220, checkpoint restore, key remap."""
+    from quantizedsae_b200 import inference as I
+    from quantizedsae_b200.inference.framework import remap_eleuther_keys
+
+    assert {"b_sae", "q_sae", "rq_sae", "baseline_sae"} <= set(I.SAE_REGISTRY)
+    assert I.SAE_REGISTRY["b_sae"].kwargs == {"input_dim": 512, "hidden_dim": 32768, "gamma": 1.5, "n_bits": 4}
+    assert I.SAE_REGISTRY["q_sae"].kwargs == {"input_dim": 512, "hidden_dim": 32768, "top_k": 32, "abs_range": 1.5,
+                                              "n_bits": 4, "allow_bias": True}
+    assert I.SAE_REGISTRY["rq_sae"].kwargs["n_bits"] == 4 and I.SAE_REGISTRY["baseline_sae"].kwargs["hidden_dim"] == 32768
+    assert I.available_saes(tmp_path)["b_sae"] == tmp_path / "Trained_SAEs" / "b_sae_32768_4_bits.pth"
+    with pytest.raises(KeyError):
+        I.load_sae("nope")
+    with pytest.raises(FileNotFoundError):
+        I.load_sae("b_sae", checkpoint_root=tmp_path, device="cpu")
+    # checkpoint round trip on a small configuration (kwargs overridden, device cpu: weights only)
+    src = Q.BinarySAE(64, 1024, 1.5, 4)
+    torch.save(src.state_dict(), tmp_path / "b.pth")
+    w = I.load_sae("b_sae", device="cpu", checkpoint_path=tmp_path / "b.pth", input_dim=64, hidden_dim=1024)
+    assert isinstance(w.model, Q.BinarySAE) and not w.model.training
+    assert torch.equal(w.model.decoder.weight, src.decoder.weight)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        w(torch.zeros(2, 64))
+    with pytest.raises(ValueError):
+        w([])
+    with pytest.raises(TypeError):
+        w("x")
+    # EleutherAI safetensors layout -> baseline_sae layout (:253-271)
+    from safetensors.torch import save_file
+
+    e = {"encoder.weight": torch.randn(128, 16), "encoder.bias": torch.randn(128), "W_dec": torch.randn(128, 16),
+         "b_dec": torch.randn(16)}
+    save_file(e, str(tmp_path / "sae.safetensors"))
+    wb = I.load_sae("baseline_sae", device="cpu", checkpoint_path=tmp_path / "sae.safetensors", input_dim=16, hidden_dim=128)
+    assert torch.equal(wb.model.decoder.weight, e["W_dec"].t()) and torch.equal(wb.model.encoder[0].weight, e["encoder.weight"])
+    d = wb.decoder_dictionary()
+    assert set(d) == {"weight", "bias"} and tuple(d["weight"].shape) == (16, 128)
+    assert remap_eleuther_keys({"encoder.0.weight": 1}) == {"encoder.0.weight": 1}
+    rq = Q.ResidualQuantizedSAE(16, 64, 32, 1.5, 3)
+    torch.save({"state_dict": rq.state_dict()}, tmp_path / "rq.pth")     # wrapped checkpoints are unwrapped
+    wr = I.load_sae("rq_sae", device="cpu", checkpoint_path=tmp_path / "rq.pth", input_dim=16, hidden_dim=64, n_bits=3)
+    assert set(wr.decoder_dictionary()) >= {"level_0_weight", "level_2_effective_weight", "level_0_bias"}
