@@ -43,27 +43,41 @@ constexpr int BK = 64;             // one 128-byte swizzle atom of bf16
 constexpr int UMMA_K = 16;
 constexpr int kStagesSparse = 3;   // W ring depth, selection epilogues
 constexpr int kStagesDense = 2;    // W ring depth when the epilogue needs a store staging area
-constexpr int kStageBytesPerWarp = 4096;  // dense epilogue: two 32-row x 64-byte store staging tiles per warp
+// Defaults from B200 measurements: the dense epilogue gains 17 % from cta_group::2
+// pairs (3-stage ring next to the staging area, half the W bytes per SM); the selection epilogues lose
+// 5 % with pairs (the leader's MMA waits for the slower of two epilogues) and gain 2 % from multicast
+// at large batch.
+constexpr int kDefaultClusterDense = 2;
+// dense epilogue: one XOR-swizzled transposition tile per warp, 32 rows of 128 bytes (pairs) or 64 bytes
+__host__ __device__ constexpr int dense_stage_bytes(bool wide) { return wide ? 32 * 128 : 32 * 64; }
 constexpr int kABytesPerChunk = BM * BK * 2;   // 16 KiB
 constexpr int kBBytesPerStage = BN * BK * 2;   // 32 KiB
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 128 + kEpiWarps * 32;  // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 bias
+// warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 bias, 4.. epilogue (8 warps, 128 columns of a tile each).
+// Measured for the dense epilogue: 16 warps of 64 columns are not faster (237 vs 227 us at B = 4096);
+// the store phase is bound by the SM's store path to L2 (~25 B/clk per SM), not by
+// the latency of an epilogue warp.
+__host__ __device__ constexpr int epi_warps(bool dense) { return 8; }
+__host__ __device__ constexpr int cta_threads(bool dense) { return 128 + epi_warps(dense) * 32; }
 constexpr int kTmemCols = 512;                  // 2 accumulators x 256 columns
 
 struct SmemLayout {
   uint32_t a_off, b_off, staging_off, bias_off, share_off, bar_off, tmem_ptr_off, total;
 };
-__host__ __device__ constexpr int ring_stages(bool dense) { return dense ? kStagesDense : kStagesSparse; }
-__host__ __device__ inline SmemLayout smem_layout(int k_chunks, bool dense) {
+// pair (cta_group::2): a CTA keeps only its half of every W stage (16 KiB), which pays for deeper rings
+__host__ __device__ constexpr int ring_stages(bool dense, bool pair) {
+  return pair ? (dense ? 3 : 4) : (dense ? kStagesDense : kStagesSparse);
+}
+__host__ __device__ constexpr int stage_bytes(bool pair) { return pair ? kBBytesPerStage / 2 : kBBytesPerStage; }
+__host__ __device__ inline SmemLayout smem_layout(int k_chunks, bool dense, bool pair) {
   SmemLayout L;
-  const int stages = ring_stages(dense);
+  const int stages = ring_stages(dense, pair);
   L.a_off = 0;
   L.b_off = L.a_off + k_chunks * kABytesPerChunk;
-  L.staging_off = L.b_off + stages * kBBytesPerStage;   // 1024-byte aligned (swizzled TMA store source)
-  L.bias_off = L.staging_off + (dense ? kEpiWarps * kStageBytesPerWarp : 0);
+  L.staging_off = L.b_off + stages * stage_bytes(pair);   // 1024-byte aligned (swizzled TMA store source)
+  L.bias_off = L.staging_off + (dense ? epi_warps(true) * dense_stage_bytes(pair) : 0);
   L.share_off = L.bias_off + 2 * BN * 4;         // partner thresholds, 2 x 128 x bf16
   L.bar_off = L.share_off + 2 * BM * 2;
-  L.tmem_ptr_off = L.bar_off + 8 * (1 + 2 * stages + 6);
+  L.tmem_ptr_off = L.bar_off + 8 * (1 + 2 * stages + 8);
   L.total = L.tmem_ptr_off + 16;
   return L;
 }
@@ -158,7 +172,7 @@ __device__ __forceinline__ void epilogue_loop(const EncodeLaunch& p, int n_my_ti
                                               int split, int m0, int e, int lane, uint32_t tmem_base,
                                               const float* bias_smem, uint16_t* share,
                                               uint64_t* tmem_full, uint64_t* tmem_empty,
-                                              uint64_t* bias_full) {
+                                              uint64_t* bias_full, uint64_t* pair_empty) {
   const unsigned full = 0xffffffffu;
   const int quad = e & 3;       // TMEM lanes 32*quad .. +31 (hardware: warp_id % 4)
   const int half = e >> 2;      // columns [half*128, half*128+128) of the tile
@@ -318,7 +332,10 @@ __device__ __forceinline__ void epilogue_loop(const EncodeLaunch& p, int n_my_ti
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    if (lane == 0) {
+      mbar_arrive(&tmem_empty[acc]);
+      if (pair_empty != nullptr) mbar_arrive_cluster(&pair_empty[acc], 0);   // the leader's MMA thread waits for both CTAs
+    }
   }
   if constexpr (MODE == 5) {
     if (row_ok) {
@@ -341,59 +358,44 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&t);
 }
 
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
 // Dense epilogue (t_sae: the reference returns the dense ReLU latents, sae/ternary.py:116-122).
 // Each epilogue warp turns its 32 rows x 32 columns of the accumulator into
 //   h fp32                 (p.dense_flags & 1)   the module's first return value
 //   h_hi = bf16(h)         (p.dense_flags & 2)   A operand of the decoder GEMM
 //   h_lo = bf16(h - h_hi)  (p.dense_flags & 4)   second A operand (h_hi + h_lo carries 16 mantissa bits)
-// Every output leaves through cp.async.bulk.tensor stores (which clip rows >= B and columns >= H)
-// from 2 KiB staging tiles of 32 rows x 64 bytes, written in the SWIZZLE_64B pattern so the
-// lane-per-row 16-byte shared stores are bank-conflict free. A warp alternates between two staging
-// tiles: before refilling one it only waits for the store issued two groups earlier
-// (wait_group.read 1), so staging, TMA reads and the next TMEM drain overlap.
-struct DenseStager {
-  uint32_t row_addr[2];   // this lane's 64-byte row in staging tile 0 / 1
-  const uint8_t* tile[2];
-  uint32_t sw64;          // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) % 4
-  int buf;
-  int lane;
-  __device__ __forceinline__ void put(const CUtensorMap* tmap, const uint32_t (&w)[16], int col, int row) {
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-    __syncwarp();
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      st_shared_v4(row_addr[buf] + ((static_cast<uint32_t>(q) << 4) ^ sw64), w[4 * q], w[4 * q + 1], w[4 * q + 2],
-                   w[4 * q + 3]);
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      tma_store_2d(tmap, tile[buf], col, row);
-      tma_store_commit();
-    }
-    buf ^= 1;
-  }
-};
-
-__device__ __forceinline__ void epilogue_dense(const EncodeLaunch& p, const CUtensorMap* t_f32,
-                                               const CUtensorMap* t_hi, const CUtensorMap* t_lo,
-                                               int n_my_tiles, int tile_begin, int m0, int e, int lane,
-                                               uint32_t tmem_base, const float* bias_smem, uint8_t* staging,
-                                               uint64_t* tmem_full, uint64_t* tmem_empty, uint64_t* bias_full) {
-  const int quad = e & 3;
-  const int half = e >> 2;
+// The accumulator arrives one row per lane; an XOR-swizzled shared-memory tile (16-byte chunk c of
+// row r at c ^ (r % 8) for 128-byte rows, c ^ ((r / 2) % 4) for 64-byte rows: conflict-free both for the
+// lane-per-row writes and for the row-contiguous reads) turns that into 16-byte global stores in which
+// every warp instruction writes whole 128-byte (fp32) or 64-byte (bf16) row segments. The L1 data pipe
+// is the resource to spare here: it also feeds the UMMA operand reads (ncu: 73 % busy, half of it bank
+// conflicts, with a padded-row layout). (A first version issued cp.async.bulk.tensor stores from a swizzled staging tile; the TMA
+// engine handled its 64-byte-wide boxes at ~16 B/clk per SM and the store time added to the sweep
+// instead of hiding behind it: 225 us vs 110 us with the stores masked off at B = 4096.)
+// WIDE: 36-word fp32 staging rows (32 columns at a time); otherwise the fp32 tile goes through the
+// 20-word bf16 layout in two 16-column halves (the single-CTA variant has no shared memory to spare).
+template <bool WIDE>
+__device__ __forceinline__ void epilogue_dense(const EncodeLaunch& p, int n_my_tiles, int tile_begin, int m0, int e,
+                                               int lane, uint32_t tmem_base, const float* bias_smem, uint8_t* staging,
+                                               uint64_t* tmem_full, uint64_t* tmem_empty, uint64_t* bias_full,
+                                               uint64_t* pair_empty) {
+  constexpr int kColsPerWarp = BN / (epi_warps(true) / 4);   // 128
+  const int quad = e & 3;          // TMEM lanes 32*quad .. +31 (hardware: warp_id % 4)
+  const int cgrp = e >> 2;         // columns [cgrp * 128, +128) of the tile
   const int row0 = m0 + quad * 32;
   const bool warp_live = row0 < p.B;
-  uint8_t* st = staging + e * kStageBytesPerWarp;
-  DenseStager stg;
-  stg.tile[0] = st;
-  stg.tile[1] = st + 2048;
-  stg.row_addr[0] = smem_u32(st) + lane * 64;
-  stg.row_addr[1] = stg.row_addr[0] + 2048;
-  stg.sw64 = static_cast<uint32_t>((lane >> 1) & 3) << 4;
-  stg.buf = 0;
-  stg.lane = lane;
+  const uint32_t st = smem_u32(staging + e * dense_stage_bytes(WIDE));
   const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
   const int flags = p.dense_flags;
+  const size_t H = static_cast<size_t>(p.H);
+  // read-back roles: fp32 -- 8 lanes per row, 4 rows per instruction; bf16 -- 4 lanes per row, 8 rows
+  const int f_row = lane >> 3, f_col = (lane & 7) * 4;
+  const int h_row = lane >> 2, h_col = (lane & 3) * 8;
 
   for (int t = 0; t < n_my_tiles; ++t) {
     const int acc = t & 1;
@@ -401,12 +403,12 @@ __device__ __forceinline__ void epilogue_dense(const EncodeLaunch& p, const CUte
     mbar_wait(&tmem_full[acc], ph);
     mbar_wait(&bias_full[acc], ph);
     tc_fence_after();
-    const int n_tile = (tile_begin + t) * BN + half * 128;
-    const float4* bias4 = reinterpret_cast<const float4*>(bias_smem + acc * BN + half * 128);
+    const int n_tile = (tile_begin + t) * BN + cgrp * kColsPerWarp;
+    const float4* bias4 = reinterpret_cast<const float4*>(bias_smem + acc * BN + cgrp * kColsPerWarp);
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < kColsPerWarp / 32; ++c) {
       uint32_t r[32];
-      tmem_ld_32x32b_x32(lane_taddr + acc * BN + half * 128 + c * 32, r);
+      tmem_ld_32x32b_x32(lane_taddr + acc * BN + cgrp * kColsPerWarp + c * 32, r);
       tmem_ld_wait();
       const int col0 = n_tile + c * 32;
 #pragma unroll
@@ -423,53 +425,110 @@ __device__ __forceinline__ void epilogue_dense(const EncodeLaunch& p, const CUte
       }
       if (!warp_live || col0 >= p.H) continue;  // warp-uniform
       if (flags & 1) {
-        uint32_t w[16];
+        if constexpr (WIDE) {
+          __syncwarp();                            // the previous tile's readers are done
 #pragma unroll
-        for (int j = 0; j < 16; ++j) w[j] = r[j];
-        stg.put(t_f32, w, col0, row0);
-        if (col0 + 16 < p.H) {
+          for (int q = 0; q < 8; ++q)
+            st_shared_v4(st + lane * 128 + ((q ^ (lane & 7)) << 4), r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+          __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) w[j] = r[16 + j];
-          stg.put(t_f32, w, col0 + 16, row0);
+          for (int j = 0; j < 8; ++j) {
+            const int rr = 4 * j + f_row;
+            const uint4 v = ld_shared_v4(st + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+            if (row0 + rr < p.B && col0 + f_col < p.H)
+              *reinterpret_cast<uint4*>(p.out_f32 + static_cast<size_t>(row0 + rr) * H + col0 + f_col) = v;
+          }
+        } else {
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {         // 16 columns at a time through the 80-byte-row layout
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              st_shared_v4(st + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4), r[16 * hf + 4 * q], r[16 * hf + 4 * q + 1],
+                           r[16 * hf + 4 * q + 2], r[16 * hf + 4 * q + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int rr = 8 * j + h_row;
+              const int cc = col0 + 16 * hf + (lane & 3) * 4;
+              const uint4 v = ld_shared_v4(st + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4));
+              if (row0 + rr < p.B && cc < p.H)
+                *reinterpret_cast<uint4*>(p.out_f32 + static_cast<size_t>(row0 + rr) * H + cc) = v;
+            }
+          }
         }
       }
       if (flags & 6) {
-        uint32_t hi[16], lo[16];
+        uint32_t hi[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float a = __uint_as_float(r[2 * j]), b = __uint_as_float(r[2 * j + 1]);
-          hi[j] = pack_bf16x2(a, b);
-          const float ah = __uint_as_float(hi[j] << 16), bh = __uint_as_float(hi[j] & 0xFFFF0000u);
-          lo[j] = pack_bf16x2(a - ah, b - bh);
+        for (int j = 0; j < 16; ++j) hi[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+        if (flags & 2) {
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            st_shared_v4(st + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4), hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int rr = 8 * j + h_row;
+            const uint4 v = ld_shared_v4(st + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4));
+            if (row0 + rr < p.B && col0 + h_col < p.H)
+              *reinterpret_cast<uint4*>(p.out_hi + static_cast<size_t>(row0 + rr) * H + col0 + h_col) = v;
+          }
         }
-        if (flags & 2) stg.put(t_hi, hi, col0, row0);
-        if (flags & 4) stg.put(t_lo, lo, col0, row0);
+        if (flags & 4) {
+          uint32_t lo[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a = __uint_as_float(r[2 * j]), b = __uint_as_float(r[2 * j + 1]);
+            const float ah = __uint_as_float(hi[j] << 16), bh = __uint_as_float(hi[j] & 0xFFFF0000u);
+            lo[j] = pack_bf16x2(a - ah, b - bh);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            st_shared_v4(st + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4), lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int rr = 8 * j + h_row;
+            const uint4 v = ld_shared_v4(st + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4));
+            if (row0 + rr < p.B && col0 + h_col < p.H)
+              *reinterpret_cast<uint4*>(p.out_lo + static_cast<size_t>(row0 + rr) * H + col0 + h_col) = v;
+          }
+        }
       }
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    if (lane == 0) {
+      mbar_arrive(&tmem_empty[acc]);
+      if (pair_empty != nullptr) mbar_arrive_cluster(&pair_empty[acc], 0);
+    }
   }
-  if (lane == 0) tma_store_wait_all();
-  __syncwarp();
 }
 
-// MCAST: launched as clusters of two CTAs along the row-block axis. The pair sweeps the same W
-// tiles in lockstep; each CTA fetches half of every 256 x 64 stage (128 latents) and TMA-multicasts
-// it into both CTAs' rings, so the pair reads W from L2 once instead of twice. The kernel streams W
-// at the L2 slice throughput limit (~6300 B/clk chip-wide), which makes this the lever for the
-// variants that also push their outputs through L2 (dense epilogue).
-template <int K_CHUNKS, bool DENSE, bool MCAST>
-__global__ void __launch_bounds__(kThreads, 1)
+// CL = 0: one CTA per 128 rows.
+// CL = 1 (multicast): clusters of two CTAs along the row-block axis sweep the same W tiles in
+//   lockstep; each CTA fetches half of every 256 x 64 stage (128 latents) and TMA-multicasts it into
+//   both CTAs' rings, so the pair reads W from L2 once instead of twice. MMAs stay per CTA.
+// CL = 2 (pair, cta_group::2): the two CTAs execute ONE tcgen05.mma of M = 256. Each keeps its own
+//   128 rows of x and only ITS half of every W stage (16 KiB instead of 32), the leader (rank 0)
+//   issues the MMAs and commits, every TMA load credits the leader's barriers, both epilogues drain
+//   their own 128 accumulator rows from their own TMEM. Halves the W bytes per SM (L2 -> SM traffic
+//   and shared-memory reads) and frees 16 KiB per stage: 4-stage ring for the selection epilogues,
+//   3 stages next to the store staging area for the dense epilogue.
+template <int K_CHUNKS, bool DENSE, int CL>
+__global__ void __launch_bounds__(cta_threads(DENSE), 1)
 encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
                    const __grid_constant__ CUtensorMap tmap_w,
-                   const __grid_constant__ CUtensorMap tmap_wh,
-                   const __grid_constant__ CUtensorMap tmap_o32,
-                   const __grid_constant__ CUtensorMap tmap_ohi,
-                   const __grid_constant__ CUtensorMap tmap_olo, EncodeLaunch p) {
-  constexpr int kStages = ring_stages(DENSE);
+                   const __grid_constant__ CUtensorMap tmap_wh, EncodeLaunch p) {
+  constexpr bool MCAST = CL == 1;
+  constexpr bool PAIR = CL == 2;
+  constexpr int kStages = ring_stages(DENSE, PAIR);
+  constexpr int kStageBytes = stage_bytes(PAIR);
   extern __shared__ __align__(1024) uint8_t smem[];
-  const SmemLayout L = smem_layout(K_CHUNKS, DENSE);
+  const SmemLayout L = smem_layout(K_CHUNKS, DENSE, PAIR);
   uint8_t* a_smem = smem + L.a_off;
   uint8_t* b_smem = smem + L.b_off;
   float* bias_smem = reinterpret_cast<float*>(smem + L.bias_off);
@@ -481,16 +540,19 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
   uint64_t* tmem_full = empty + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* bias_full = tmem_empty + 2;
+  uint64_t* pair_empty = bias_full + 2;     // leader only: both CTAs' epilogues released accumulator a
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L.tmem_ptr_off);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int split = blockIdx.x;
-  const int m0 = blockIdx.y * BM;
+  // cluster variants pair two row blocks along grid.x (CTA pairs must be adjacent in x)
+  const int split = (CL != 0) ? blockIdx.y : blockIdx.x;
+  const int m0 = ((CL != 0) ? blockIdx.x : blockIdx.y) * BM;
   const int tile_begin = split * p.tiles_per_split;
   const int tile_end = min(p.n_tiles, tile_begin + p.tiles_per_split);
   const int n_my_tiles = max(0, tile_end - tile_begin);
-  const uint32_t cta_rank = MCAST ? cluster_ctarank() : 0u;
+  const uint32_t cta_rank = (CL != 0) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0u;
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0u) {
@@ -504,17 +566,21 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], kEpiWarps);
+      mbar_init(&tmem_empty[a], epi_warps(DENSE));
       mbar_init(&bias_full[a], 1);
+      mbar_init(&pair_empty[a], 2 * epi_warps(DENSE));
     }
     fence_mbar_init();
     fence_proxy_async_smem();
   }
   if (threadIdx.x < 2 * BM) share[threadIdx.x] = 0xFF80u;  // bf16 -inf
-  if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr);
+  if (warp == 2) {
+    if constexpr (PAIR) tmem_alloc_pair<kTmemCols>(tmem_ptr);
+    else tmem_alloc<kTmemCols>(tmem_ptr);
+  }
   tc_fence_before();
   __syncthreads();
-  if constexpr (MCAST) cluster_sync_all();   // the peer's barriers exist before anything signals them
+  if constexpr (CL != 0) cluster_sync_all();   // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -522,11 +588,20 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
     // ------------------------------------------------------------- TMA producer
     if (lane == 0 && n_my_tiles > 0) {
       tma_prefetch_desc(&tmap_x);
-      tma_prefetch_desc(&tmap_w);
-      mbar_arrive_expect_tx(a_full, K_CHUNKS * kABytesPerChunk);
+      tma_prefetch_desc(PAIR || MCAST ? &tmap_wh : &tmap_w);
+      if constexpr (PAIR) {
+        // both x tiles and both halves of every W stage are credited to the leader's barriers
+        const uint32_t a_full_leader = mapa_u32(smem_u32(a_full), 0);
+        if (leader) mbar_arrive_expect_tx(a_full, 2 * K_CHUNKS * kABytesPerChunk);
 #pragma unroll
-      for (int kc = 0; kc < K_CHUNKS; ++kc)
-        tma_load_2d(a_smem + kc * kABytesPerChunk, &tmap_x, a_full, kc * BK, m0, kPolicyEvictFirst);
+        for (int kc = 0; kc < K_CHUNKS; ++kc)
+          tma_load_2d_pair(a_smem + kc * kABytesPerChunk, &tmap_x, a_full_leader, kc * BK, m0, kPolicyEvictFirst);
+      } else {
+        mbar_arrive_expect_tx(a_full, K_CHUNKS * kABytesPerChunk);
+#pragma unroll
+        for (int kc = 0; kc < K_CHUNKS; ++kc)
+          tma_load_2d(a_smem + kc * kABytesPerChunk, &tmap_x, a_full, kc * BK, m0, kPolicyEvictFirst);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < n_my_tiles; ++t) {
@@ -534,12 +609,17 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
 #pragma unroll 1
         for (int kc = 0; kc < K_CHUNKS; ++kc) {
           mbar_wait(&empty[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full[stage], kBBytesPerStage);
-          if constexpr (MCAST) {
+          if constexpr (PAIR) {
+            if (leader) mbar_arrive_expect_tx(&full[stage], kBBytesPerStage);   // 16 KiB from each CTA
+            tma_load_2d_pair(b_smem + stage * kStageBytes, &tmap_wh, mapa_u32(smem_u32(&full[stage]), 0), kc * BK,
+                             n0 + static_cast<int>(cta_rank) * (BN / 2), kPolicyEvictLast);
+          } else if constexpr (MCAST) {
+            mbar_arrive_expect_tx(&full[stage], kBBytesPerStage);
             // my half of the stage lands in both CTAs; the other half arrives from the peer
             tma_load_2d_mcast(b_smem + stage * kBBytesPerStage + cta_rank * (kBBytesPerStage / 2), &tmap_wh,
                               &full[stage], kc * BK, n0 + static_cast<int>(cta_rank) * (BN / 2), 0x3, kPolicyEvictLast);
           } else {
+            mbar_arrive_expect_tx(&full[stage], kBBytesPerStage);
             tma_load_2d(b_smem + stage * kBBytesPerStage, &tmap_w, &full[stage], kc * BK, n0,
                         kPolicyEvictLast);
           }
@@ -548,9 +628,9 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------- MMA issuer
-    if (lane == 0 && n_my_tiles > 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
+    // ------------------------------------------------------------- MMA issuer (pair: the leader only)
+    if (lane == 0 && n_my_tiles > 0 && (!PAIR || leader)) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(PAIR ? 2 * BM : BM, BN);
       const uint64_t a_desc0 = umma_desc_kmajor_sw128(smem_u32(a_smem));
       const uint64_t b_desc0 = umma_desc_kmajor_sw128(smem_u32(b_smem));
       mbar_wait(a_full, 0);
@@ -558,7 +638,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
       uint32_t phase = 0;
       for (int t = 0; t < n_my_tiles; ++t) {
         const int acc = t & 1;
-        mbar_wait(&tmem_empty[acc], ((t >> 1) & 1) ^ 1u);
+        mbar_wait(PAIR ? &pair_empty[acc] : &tmem_empty[acc], ((t >> 1) & 1) ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
 #pragma unroll 1
@@ -566,16 +646,22 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((kc * kABytesPerChunk) >> 4);
-          const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((stage * kBBytesPerStage) >> 4);
+          const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((stage * kStageBytes) >> 4);
 #pragma unroll
           for (int ks = 0; ks < BK / UMMA_K; ++ks) {
             // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the
             // (address >> 4) field of the descriptor
-            umma_f16_ss(d_tmem, a_desc + ks * 2, b_desc + ks * 2, idesc, (kc | ks) != 0 ? 1u : 0u);
+            if constexpr (PAIR) umma_f16_ss_pair(d_tmem, a_desc + ks * 2, b_desc + ks * 2, idesc, (kc | ks) != 0 ? 1u : 0u);
+            else umma_f16_ss(d_tmem, a_desc + ks * 2, b_desc + ks * 2, idesc, (kc | ks) != 0 ? 1u : 0u);
           }
-          if constexpr (MCAST) umma_commit_mcast(&empty[stage], 0x3);
-          else umma_commit(&empty[stage]);
-          if (kc == K_CHUNKS - 1) umma_commit(&tmem_full[acc]);
+          if constexpr (PAIR) {
+            umma_commit_pair(&empty[stage], 0x3);
+            if (kc == K_CHUNKS - 1) umma_commit_pair(&tmem_full[acc], 0x3);
+          } else {
+            if constexpr (MCAST) umma_commit_mcast(&empty[stage], 0x3);
+            else umma_commit(&empty[stage]);
+            if (kc == K_CHUNKS - 1) umma_commit(&tmem_full[acc]);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -597,43 +683,47 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
   } else if (warp >= 4) {
     // ------------------------------------------------------------- epilogue / selection
     const int e = warp - 4;
+    uint64_t* pe = PAIR ? pair_empty : nullptr;
     if constexpr (DENSE) {
-      epilogue_dense(p, &tmap_o32, &tmap_ohi, &tmap_olo, n_my_tiles, tile_begin, m0, e, lane, tmem_base, bias_smem,
-                     smem + L.staging_off, tmem_full, tmem_empty, bias_full);
+      epilogue_dense<PAIR>(p, n_my_tiles, tile_begin, m0, e, lane, tmem_base, bias_smem, smem + L.staging_off,
+                           tmem_full, tmem_empty, bias_full, pe);
     } else
     switch (p.mode) {
       case 1:
         epilogue_loop<1>(p, n_my_tiles, tile_begin, split, m0, e, lane, tmem_base, bias_smem, share,
-                         tmem_full, tmem_empty, bias_full);
+                         tmem_full, tmem_empty, bias_full, pe);
         break;
       case 2:
         epilogue_loop<2>(p, n_my_tiles, tile_begin, split, m0, e, lane, tmem_base, bias_smem, share,
-                         tmem_full, tmem_empty, bias_full);
+                         tmem_full, tmem_empty, bias_full, pe);
         break;
       case 3:
         epilogue_loop<3>(p, n_my_tiles, tile_begin, split, m0, e, lane, tmem_base, bias_smem, share,
-                         tmem_full, tmem_empty, bias_full);
+                         tmem_full, tmem_empty, bias_full, pe);
         break;
       case 4:
         epilogue_loop<4>(p, n_my_tiles, tile_begin, split, m0, e, lane, tmem_base, bias_smem, share,
-                         tmem_full, tmem_empty, bias_full);
+                         tmem_full, tmem_empty, bias_full, pe);
         break;
       case 5:
         epilogue_loop<5>(p, n_my_tiles, tile_begin, split, m0, e, lane, tmem_base, bias_smem, share,
-                         tmem_full, tmem_empty, bias_full);
+                         tmem_full, tmem_empty, bias_full, pe);
         break;
       default:
         epilogue_loop<0>(p, n_my_tiles, tile_begin, split, m0, e, lane, tmem_base, bias_smem, share,
-                         tmem_full, tmem_empty, bias_full);
+                         tmem_full, tmem_empty, bias_full, pe);
         break;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if constexpr (MCAST) cluster_sync_all();   // no CTA leaves while its peer may still write into it
+  if constexpr (CL != 0) cluster_sync_all();   // no CTA leaves while its peer may still write into it
   tc_fence_after();
-  if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
+  if (warp == 2) {
+    if constexpr (PAIR) tmem_dealloc_pair<kTmemCols>(tmem_base);
+    else tmem_dealloc<kTmemCols>(tmem_base);
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -673,67 +763,69 @@ bool make_tmap_bf16(CUtensorMap* map, const void* base, int rows, int cols, int 
                       CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int K_CHUNKS, bool DENSE, bool MCAST>
-cudaError_t launch_k(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& twh, const CUtensorMap& o32,
-                     const CUtensorMap& ohi, const CUtensorMap& olo, const EncodeLaunch& p, cudaStream_t stream) {
-  const SmemLayout L = smem_layout(K_CHUNKS, DENSE);
+template <int K_CHUNKS, bool DENSE, int CL>
+cudaError_t launch_k(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& twh, const EncodeLaunch& p,
+                     cudaStream_t stream) {
+  const SmemLayout L = smem_layout(K_CHUNKS, DENSE, CL == 2);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(encode_topk_kernel<K_CHUNKS, DENSE, MCAST>,
+    cudaError_t e = cudaFuncSetAttribute(encode_topk_kernel<K_CHUNKS, DENSE, CL>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   dim3 grid(p.n_splits, (p.B + BM - 1) / BM);
-  if constexpr (MCAST) {
-    grid.y = (grid.y + 1) / 2 * 2;   // whole clusters; the padding CTA sweeps zero rows and writes nothing
+  if constexpr (CL != 0) {
+    // whole clusters along x; the padding CTA sweeps zero rows and writes nothing
+    grid = dim3(((p.B + BM - 1) / BM + 1) / 2 * 2, p.n_splits);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(cta_threads(DENSE));
     cfg.dynamicSmemBytes = L.total;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 1;
-    at[0].val.clusterDim.y = 2;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, encode_topk_kernel<K_CHUNKS, DENSE, MCAST>, tx, tw, twh, o32, ohi, olo, p);
+    return cudaLaunchKernelEx(&cfg, encode_topk_kernel<K_CHUNKS, DENSE, CL>, tx, tw, twh, p);
   } else {
-    encode_topk_kernel<K_CHUNKS, DENSE, MCAST><<<grid, kThreads, L.total, stream>>>(tx, tw, twh, o32, ohi, olo, p);
+    encode_topk_kernel<K_CHUNKS, DENSE, CL><<<grid, cta_threads(DENSE), L.total, stream>>>(tx, tw, twh, p);
     return cudaGetLastError();
   }
 }
 
 template <bool DENSE>
-const char* launch_any(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& twh, const CUtensorMap& o32,
-                       const CUtensorMap& ohi, const CUtensorMap& olo, const EncodeLaunch& p, cudaStream_t stream) {
+const char* launch_any(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& twh, const EncodeLaunch& p,
+                       cudaStream_t stream) {
   const int kc = (p.D + BK - 1) / BK;
   cudaError_t e;
   switch (kc) {
-    case 1: e = launch_k<1, DENSE, false>(tx, tw, twh, o32, ohi, olo, p, stream); break;
-    case 2: e = launch_k<2, DENSE, false>(tx, tw, twh, o32, ohi, olo, p, stream); break;
-    case 3: e = launch_k<3, DENSE, false>(tx, tw, twh, o32, ohi, olo, p, stream); break;
-    case 4: e = launch_k<4, DENSE, false>(tx, tw, twh, o32, ohi, olo, p, stream); break;
-    case 5: e = launch_k<5, DENSE, false>(tx, tw, twh, o32, ohi, olo, p, stream); break;
-    case 6: e = launch_k<6, DENSE, false>(tx, tw, twh, o32, ohi, olo, p, stream); break;
-    case 7: e = launch_k<7, DENSE, false>(tx, tw, twh, o32, ohi, olo, p, stream); break;
-    case 8:   // the headline width: the multicast pair variant exists here
-      e = p.mcast ? launch_k<8, DENSE, true>(tx, tw, twh, o32, ohi, olo, p, stream)
-                  : launch_k<8, DENSE, false>(tx, tw, twh, o32, ohi, olo, p, stream);
+    case 1: e = launch_k<1, DENSE, 0>(tx, tw, twh, p, stream); break;
+    case 2: e = launch_k<2, DENSE, 0>(tx, tw, twh, p, stream); break;
+    case 3: e = launch_k<3, DENSE, 0>(tx, tw, twh, p, stream); break;
+    case 4: e = launch_k<4, DENSE, 0>(tx, tw, twh, p, stream); break;
+    case 5: e = launch_k<5, DENSE, 0>(tx, tw, twh, p, stream); break;
+    case 6: e = launch_k<6, DENSE, 0>(tx, tw, twh, p, stream); break;
+    case 7: e = launch_k<7, DENSE, 0>(tx, tw, twh, p, stream); break;
+    case 8:   // the headline width: the cluster variants exist here
+      if (p.cluster == 2) e = launch_k<8, DENSE, 2>(tx, tw, twh, p, stream);
+      else if (p.cluster == 1) e = launch_k<8, DENSE, 1>(tx, tw, twh, p, stream);
+      else e = launch_k<8, DENSE, 0>(tx, tw, twh, p, stream);
       break;
     default: return "D must be <= 512";
   }
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
-// Multicast pairs need two row blocks per cluster. Measured on B200 (B = 65536, k = 32): -2 % on the whole
-// selection call, nothing on the dense-epilogue variant and +1 % at B = 4096 (the L2 already merges the
-// two CTAs' requests for the same W lines most of the time), so it is on only for large sparse sweeps.
-bool want_mcast(const EncodeLaunch& p, bool dflt) {
-  if (const char* m = getenv("QSAE_ENCODE_MCAST")) dflt = atoi(m) != 0;   // tests and tuning experiments
-  return dflt && p.D > 448 && p.B > BM;
+// Cluster variant of a launch: 0 single CTA, 1 multicast pair, 2 cta_group::2 pair. Pairs need two row
+// blocks. QSAE_ENCODE_CLUSTER overrides the default (tests and tuning experiments).
+int pick_cluster(const EncodeLaunch& p, int dflt) {
+  if (const char* m = getenv("QSAE_ENCODE_CLUSTER")) dflt = atoi(m);
+  if (dflt < 0 || dflt > 2 || p.D <= 448 || p.B <= BM) return 0;
+  return dflt;
 }
 
 }  // namespace
@@ -769,35 +861,28 @@ const char* encode_topk_launch(const uint16_t* x_bf16, const uint16_t* w_bf16, E
   if (!make_tmap_bf16(&tx, x_bf16, p.B, p.D, BM)) return "cuTensorMapEncodeTiled(x) failed";
   if (!make_tmap_bf16(&tw, w_bf16, p.H, p.D, BN)) return "cuTensorMapEncodeTiled(W) failed";
   p.dense_flags = 0;
-  p.mcast = want_mcast(p, p.B >= 16384) ? 1 : 0;
+  p.cluster = pick_cluster(p, p.B >= 16384 ? 1 : 0);
   CUtensorMap twh = tw;
-  if (p.mcast && !make_tmap_bf16(&twh, w_bf16, p.H, p.D, BN / 2)) return "cuTensorMapEncodeTiled(W half) failed";
-  return launch_any<false>(tx, tw, twh, tx, tx, tx, p, stream);
+  if (p.cluster && !make_tmap_bf16(&twh, w_bf16, p.H, p.D, BN / 2)) return "cuTensorMapEncodeTiled(W half) failed";
+  return launch_any<false>(tx, tw, twh, p, stream);
 }
 
 const char* encode_dense_tc_launch(const uint16_t* x_bf16, const uint16_t* w_bf16, EncodeLaunch p, float* out_f32,
                                    uint16_t* out_hi, uint16_t* out_lo, cudaStream_t stream) {
   if ((p.H % 8) != 0) return "dense tensor-core encoder needs H % 8 == 0";
-  CUtensorMap tx, tw, o32, ohi, olo;
+  if ((reinterpret_cast<uintptr_t>(out_f32) | reinterpret_cast<uintptr_t>(out_hi) | reinterpret_cast<uintptr_t>(out_lo)) & 15)
+    return "dense tensor-core encoder: outputs must be 16-byte aligned";
+  CUtensorMap tx, tw;
   if (!make_tmap_bf16(&tx, x_bf16, p.B, p.D, BM)) return "cuTensorMapEncodeTiled(x) failed";
   if (!make_tmap_bf16(&tw, w_bf16, p.H, p.D, BN)) return "cuTensorMapEncodeTiled(W) failed";
-  o32 = ohi = olo = tx;
+  p.out_f32 = out_f32; p.out_hi = out_hi; p.out_lo = out_lo;
   p.dense_flags = (out_f32 ? 1 : 0) | (out_hi ? 2 : 0) | (out_lo ? 4 : 0);
   if (p.dense_flags == 0) return "dense encoder: no output requested";
   if (const char* m = getenv("QSAE_DENSE_FLAGS_MASK")) p.dense_flags &= atoi(m);  // timing experiments only
-  if (out_f32 && !make_tmap_2d(&o32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out_f32, p.B, p.H, 16, 32,
-                               CU_TENSOR_MAP_SWIZZLE_64B))
-    return "cuTensorMapEncodeTiled(h fp32) failed";
-  if (out_hi && !make_tmap_2d(&ohi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out_hi, p.B, p.H, 32, 32,
-                              CU_TENSOR_MAP_SWIZZLE_64B))
-    return "cuTensorMapEncodeTiled(h hi) failed";
-  if (out_lo && !make_tmap_2d(&olo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out_lo, p.B, p.H, 32, 32,
-                              CU_TENSOR_MAP_SWIZZLE_64B))
-    return "cuTensorMapEncodeTiled(h lo) failed";
-  p.mcast = want_mcast(p, false) ? 1 : 0;
+  p.cluster = pick_cluster(p, kDefaultClusterDense);
   CUtensorMap twh = tw;
-  if (p.mcast && !make_tmap_bf16(&twh, w_bf16, p.H, p.D, BN / 2)) return "cuTensorMapEncodeTiled(W half) failed";
-  return launch_any<true>(tx, tw, twh, o32, ohi, olo, p, stream);
+  if (p.cluster && !make_tmap_bf16(&twh, w_bf16, p.H, p.D, BN / 2)) return "cuTensorMapEncodeTiled(W half) failed";
+  return launch_any<true>(tx, tw, twh, p, stream);
 }
 
 }  // namespace qsae

@@ -31,8 +31,11 @@ struct EncodeLaunch {
   void* cand;           // [B][n_splits*2][cap] {float bits, int32 column}
   int* cand_cnt;        // [B][n_splits*2]
   float* cand_thr;      // [B][n_splits*2] inclusive lower bound of the row's k_sel-th largest value
-  int mcast;            // 1: clusters of two row blocks sharing every W stage by TMA multicast (set by the launcher)
+  int cluster;          // 0 single CTA, 1 TMA-multicast pair, 2 cta_group::2 pair (set by the launcher)
   int dense_flags;      // dense epilogue outputs: 1 fp32, 2 bf16 hi, 4 bf16 lo (set by the launcher)
+  float* out_f32;       // dense epilogue: [B, H] row-major outputs (set by the launcher)
+  uint16_t* out_hi;
+  uint16_t* out_lo;
   int debug_mode;       // 0 normal; timing experiments: 1 no survivors, 2 no TMEM drain
   float* debug_z;       // optional dense [B, H] dump of the accumulator (+bias, act); diagnostics only
 };

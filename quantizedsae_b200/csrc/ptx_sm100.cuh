@@ -191,6 +191,57 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---------------------------------------------------------------- tcgen05, CTA pairs (cta_group::2)
+// Two CTAs of a cluster (ranks 2i, 2i+1, same TPC) execute one MMA of M = 256: each holds its own
+// 128 rows of A and half of the N columns of B in shared memory at identical offsets, each receives
+// its 128 accumulator rows in its own TMEM. Only the leader (even rank) issues MMA and commit.
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result) {   // one warp in EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this offset in every CTA of cta_mask when the pair's MMAs complete
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+// shared::cluster address of `local_addr` (a shared::cta address of this CTA) in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+// TMA load issued by either CTA of a pair; the completion bytes are credited to `bar_cluster_addr`,
+// which may live in the peer CTA (the leader's "stage full" barrier)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* desc, uint32_t bar_cluster_addr,
+                                                 int32_t c0, int32_t c1, uint64_t cache_policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(desc), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(cache_policy)
+      : "memory");
+}
+
 // K-major, 128-byte swizzled operand tile: rows of 128 B (64 bf16), 8-row atoms of 1024 B.
 //   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused with swizzle, 1) |
 //   [32,46) SBO >> 4 = 1024 >> 4 | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)

@@ -655,21 +655,22 @@ def test_qsae_untrained_model_falls_back_to_dense(cuda_device):
         m(T(inp["x"], cuda_device))
 
 
-@pytest.mark.parametrize("mcast", ["0", "1"])
-def test_multicast_pair_variant_is_bit_identical(cuda_device, monkeypatch, mcast):
-    """The cluster-of-two TMA-multicast variant of the encoder (sparse and dense epilogues) must give
-    the same bits as the single-CTA variant; odd numbers of row blocks exercise the padding CTA."""
+@pytest.mark.parametrize("mcast", ["1", "2"])
+def test_cluster_variants_are_bit_identical(cuda_device, monkeypatch, mcast):
+    """The cluster-of-two variants of the encoder -- 1: TMA multicast of the W stages, 2: cta_group::2
+    MMA pairs -- with the sparse and the dense epilogue must give the same bits as the single-CTA
+    variant; odd numbers of row blocks exercise the padding CTA."""
     B, H, D, k = 300, 8192, 512, 32
     x, W, b = _enc_case(B, H, D, 55)
     dx, dW, db = T(x, cuda_device), T(W, cuda_device), T(b, cuda_device)
     wb = L.cast_bf16(dW)
-    monkeypatch.setenv("QSAE_ENCODE_MCAST", mcast)
+    monkeypatch.setenv("QSAE_ENCODE_CLUSTER", mcast)
     vals, idx, _ = L.encode_topk(dx, wb, None, db, k, sample=L.prepare_sample(wb, db))
     assert_topk_matches(vals.cpu().numpy(), idx.cpu().numpy(), O.encode_pre(x, W, b), k)
     wd = (0.4824 * np.random.default_rng(1).standard_normal((D, H))).astype(np.float32)
     t_bf16, _ = L.pack_ternary(T(wd, cuda_device))
     h, recon = L.tsae_forward(dx, wb, None, db, t_bf16, exact=False)
-    monkeypatch.setenv("QSAE_ENCODE_MCAST", "0")
+    monkeypatch.setenv("QSAE_ENCODE_CLUSTER", "0")
     v0, i0, _ = L.encode_topk(dx, wb, None, db, k, sample=L.prepare_sample(wb, db))
     h0, r0 = L.tsae_forward(dx, wb, None, db, t_bf16, exact=False)
     assert torch.equal(vals, v0) and torch.equal(idx, i0) and torch.equal(h, h0) and torch.equal(recon, r0)
