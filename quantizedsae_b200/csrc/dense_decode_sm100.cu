@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 #include "ptx_sm100.cuh"
@@ -26,10 +27,15 @@ constexpr int kABytes = BM * BK * 2;   // 16 KiB
 constexpr int kBBytes = BN * BK * 2;   // 32 KiB per N tile
 constexpr int kThreads = 256;          // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue
 
-template <int N_TILES>
+// PAIR (cta_group::2): two CTAs (256 rows) execute one MMA; each keeps its own A tile and HALF of
+// every B (= T) tile -- 128 of the 256 output columns of each N tile -- so a stage is 48 KiB instead
+// of 80 KiB: four stages instead of two, and 40 % less operand traffic per flop (the single-CTA
+// kernel pulls 80 KB per 1024 MMA cycles, above the L2 slice throughput of the part).
+template <int N_TILES, bool PAIR>
 struct Cfg {
-  static constexpr int kStageBytes = kABytes + N_TILES * kBBytes;
-  static constexpr int kStages = (N_TILES == 1) ? 4 : 2;
+  static constexpr int kBTileBytes = PAIR ? kBBytes / 2 : kBBytes;
+  static constexpr int kStageBytes = kABytes + N_TILES * kBTileBytes;
+  static constexpr int kStages = PAIR ? 4 : ((N_TILES == 1) ? 4 : 2);
   static constexpr int kTmemCols = N_TILES * BN;  // 256 or 512
   static constexpr int kBarOff = kStages * kStageBytes;
   static constexpr int kSmem = kBarOff + 8 * (2 * kStages + 1) + 16;
@@ -43,11 +49,11 @@ struct DecodeLaunch {
   float* partial;        // [splits][B][N]
 };
 
-template <int N_TILES>
+template <int N_TILES, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 dense_decode_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
                     const __grid_constant__ CUtensorMap tmap_b, DecodeLaunch p) {
-  using C = Cfg<N_TILES>;
+  using C = Cfg<N_TILES, PAIR>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBarOff);
   uint64_t* full = bars;
@@ -56,8 +62,11 @@ dense_decode_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int split = blockIdx.x;
-  const int m0 = blockIdx.y * BM;
+  // pairs sit next to each other along grid.x (two row blocks); otherwise x = K split, y = row block
+  const int split = PAIR ? blockIdx.y : blockIdx.x;
+  const int m0 = (PAIR ? blockIdx.x : blockIdx.y) * BM;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0u;
   const int kc_begin = split * p.chunks_per_split;
   const int kc_end = min(p.k_chunks, kc_begin + p.chunks_per_split);
   const int n_chunks = max(0, kc_end - kc_begin) * p.n_passes;
@@ -75,9 +84,13 @@ dense_decode_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
     fence_mbar_init();
     fence_proxy_async_smem();
   }
-  if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_ptr);
+  if (warp == 2) {
+    if constexpr (PAIR) tmem_alloc_pair<C::kTmemCols>(tmem_ptr);
+    else tmem_alloc<C::kTmemCols>(tmem_ptr);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -93,18 +106,29 @@ dense_decode_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
         for (int kc = kc_begin; kc < kc_end; ++kc) {
           mbar_wait(&empty[stage], phase ^ 1u);
           uint8_t* st = smem + stage * C::kStageBytes;
-          mbar_arrive_expect_tx(&full[stage], C::kStageBytes);
-          tma_load_2d(st, ta, &full[stage], kc * BK, m0, kPolicyEvictFirst);
+          if constexpr (PAIR) {
+            // both CTAs' loads are credited to the leader's barrier (2 x 48 KiB per stage)
+            const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), 0);
+            if (leader) mbar_arrive_expect_tx(&full[stage], 2 * C::kStageBytes);
+            tma_load_2d_pair(st, ta, full_leader, kc * BK, m0, kPolicyEvictFirst);
 #pragma unroll
-          for (int nt = 0; nt < N_TILES; ++nt)
-            tma_load_2d(st + kABytes + nt * kBBytes, &tmap_b, &full[stage], kc * BK, nt * BN, kPolicyEvictLast);
+            for (int nt = 0; nt < N_TILES; ++nt)
+              tma_load_2d_pair(st + kABytes + nt * C::kBTileBytes, &tmap_b, full_leader, kc * BK,
+                               nt * BN + static_cast<int>(cta_rank) * (BN / 2), kPolicyEvictLast);
+          } else {
+            mbar_arrive_expect_tx(&full[stage], C::kStageBytes);
+            tma_load_2d(st, ta, &full[stage], kc * BK, m0, kPolicyEvictFirst);
+#pragma unroll
+            for (int nt = 0; nt < N_TILES; ++nt)
+              tma_load_2d(st + kABytes + nt * kBBytes, &tmap_b, &full[stage], kc * BK, nt * BN, kPolicyEvictLast);
+          }
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && n_chunks > 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
+    if (lane == 0 && n_chunks > 0 && (!PAIR || leader)) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(PAIR ? 2 * BM : BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < n_chunks; ++i) {
@@ -114,13 +138,22 @@ dense_decode_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
         const uint64_t a_desc = umma_desc_kmajor_sw128(st);
 #pragma unroll
         for (int nt = 0; nt < N_TILES; ++nt) {
-          const uint64_t b_desc = umma_desc_kmajor_sw128(st + kABytes + nt * kBBytes);
+          const uint64_t b_desc = umma_desc_kmajor_sw128(st + kABytes + nt * C::kBTileBytes);
 #pragma unroll
-          for (int ks = 0; ks < BK / UMMA_K; ++ks)
-            umma_f16_ss(tmem_base + nt * BN, a_desc + ks * 2, b_desc + ks * 2, idesc, (i | ks) != 0 ? 1u : 0u);
+          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+            if constexpr (PAIR)
+              umma_f16_ss_pair(tmem_base + nt * BN, a_desc + ks * 2, b_desc + ks * 2, idesc, (i | ks) != 0 ? 1u : 0u);
+            else
+              umma_f16_ss(tmem_base + nt * BN, a_desc + ks * 2, b_desc + ks * 2, idesc, (i | ks) != 0 ? 1u : 0u);
+          }
         }
-        umma_commit(&empty[stage]);
-        if (i == n_chunks - 1) umma_commit(acc_full);
+        if constexpr (PAIR) {
+          umma_commit_pair(&empty[stage], 0x3);
+          if (i == n_chunks - 1) umma_commit_pair(acc_full, 0x3);
+        } else {
+          umma_commit(&empty[stage]);
+          if (i == n_chunks - 1) umma_commit(acc_full);
+        }
         if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -152,8 +185,12 @@ dense_decode_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_co
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();
   tc_fence_after();
-  if (warp == 2) tmem_dealloc<C::kTmemCols>(tmem_base);
+  if (warp == 2) {
+    if constexpr (PAIR) tmem_dealloc_pair<C::kTmemCols>(tmem_base);
+    else tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
 }
 
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int splits, size_t n,
@@ -201,20 +238,37 @@ bool make_tmap(CUtensorMap* map, const void* base, int rows, int cols, int ld, i
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int N_TILES>
+template <int N_TILES, bool PAIR>
 cudaError_t launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const DecodeLaunch& p,
                    int splits, cudaStream_t stream) {
-  using C = Cfg<N_TILES>;
+  using C = Cfg<N_TILES, PAIR>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(dense_decode_kernel<N_TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(dense_decode_kernel<N_TILES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::kSmem);
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  dim3 grid(splits, (p.B + BM - 1) / BM);
-  dense_decode_kernel<N_TILES><<<grid, kThreads, C::kSmem, stream>>>(a0, a1, b, p);
-  return cudaGetLastError();
+  const int m_tiles = (p.B + BM - 1) / BM;
+  if constexpr (PAIR) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((m_tiles + 1) / 2 * 2, splits);   // whole pairs along x; a padding CTA multiplies zero rows
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::kSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, dense_decode_kernel<N_TILES, PAIR>, a0, a1, b, p);
+  } else {
+    dim3 grid(splits, m_tiles);
+    dense_decode_kernel<N_TILES, PAIR><<<grid, kThreads, C::kSmem, stream>>>(a0, a1, b, p);
+    return cudaGetLastError();
+  }
 }
 
 }  // namespace
@@ -249,7 +303,10 @@ const char* dense_decode_launch(const uint16_t* a_hi, const uint16_t* a_lo, int 
   CUtensorMap ta0, ta1, tb;
   if (!make_tmap(&ta0, a_hi, B, K, lda, BM)) return "cuTensorMapEncodeTiled(A) failed";
   if (!make_tmap(&ta1, a_lo ? a_lo : a_hi, B, K, lda, BM)) return "cuTensorMapEncodeTiled(A lo) failed";
-  if (!make_tmap(&tb, b_t, N, K, ldb, BN)) return "cuTensorMapEncodeTiled(B) failed";
+  // CTA pairs need two row blocks; QSAE_DECODE_PAIR=0/1 overrides (tests and tuning experiments)
+  bool pair = B > BM;
+  if (const char* m = getenv("QSAE_DECODE_PAIR")) pair = pair && atoi(m) != 0;
+  if (!make_tmap(&tb, b_t, N, K, ldb, pair ? BN / 2 : BN)) return "cuTensorMapEncodeTiled(B) failed";
   DecodeLaunch p;
   p.B = B; p.K = K; p.N = N;
   p.k_chunks = (K + BK - 1) / BK;
@@ -257,7 +314,9 @@ const char* dense_decode_launch(const uint16_t* a_hi, const uint16_t* a_lo, int 
   p.chunks_per_split = (p.k_chunks + splits - 1) / splits;
   p.n_passes = a_lo ? 2 : 1;
   p.partial = static_cast<float*>(workspace);
-  cudaError_t e = (N <= 256) ? launch<1>(ta0, ta1, tb, p, splits, stream) : launch<2>(ta0, ta1, tb, p, splits, stream);
+  cudaError_t e;
+  if (pair) e = (N <= 256) ? launch<1, true>(ta0, ta1, tb, p, splits, stream) : launch<2, true>(ta0, ta1, tb, p, splits, stream);
+  else e = (N <= 256) ? launch<1, false>(ta0, ta1, tb, p, splits, stream) : launch<2, false>(ta0, ta1, tb, p, splits, stream);
   if (e != cudaSuccess) return cudaGetErrorString(e);
   const size_t n = static_cast<size_t>(B) * N;
   size_t g = (n / 4 + 255) / 256;

@@ -720,3 +720,18 @@ def test_inference_wrapper_on_gpu(cuda_device, golden_dir, tmp_path):
     assert np.array_equal(d["weight"].numpy(), ref) and not d["weight"].is_cuda
     recs = list(w.reconstruct_loader([torch.from_numpy(inp["x"][:8]), torch.from_numpy(inp["x"][8:])]))
     assert_recon_close(torch.cat(recs).cpu().numpy(), g["recon"])
+
+
+@pytest.mark.parametrize("B,K,N", [(300, 4096, 512), (129, 1000, 64), (1024, 8192, 384)])
+def test_decoder_gemm_pair_variant_is_bit_identical(cuda_device, monkeypatch, B, K, N):
+    """cta_group::2 pairs (default for more than one row block) against the single-CTA kernel."""
+    rng = np.random.default_rng(B)
+    a = np.maximum(rng.standard_normal((B, K)), 0).astype(np.float32)
+    t = O.ternarize((0.4824 * rng.standard_normal((N, K))).astype(np.float32))
+    hi, lo = L.split_bf16(T(a, cuda_device))
+    tb = T(t.astype(np.float32), cuda_device).bfloat16().contiguous()
+    monkeypatch.setenv("QSAE_DECODE_PAIR", "1")
+    one, two = L.decode_dense(hi, None, tb), L.decode_dense(hi, lo, tb)
+    monkeypatch.setenv("QSAE_DECODE_PAIR", "0")
+    assert torch.equal(one, L.decode_dense(hi, None, tb)) and torch.equal(two, L.decode_dense(hi, lo, tb))
+    assert_recon_close(two.cpu().numpy(), (a.astype(np.float64) @ t.T.astype(np.float64)).astype(np.float32))
