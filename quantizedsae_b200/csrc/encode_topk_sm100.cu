@@ -65,7 +65,7 @@ struct SmemLayout {
 };
 // pair (cta_group::2): a CTA keeps only its half of every W stage (16 KiB), which pays for deeper rings
 __host__ __device__ constexpr int ring_stages(bool dense, bool pair) {
-  return pair ? (dense ? 3 : 4) : (dense ? kStagesDense : kStagesSparse);
+  return pair ? 4 : (dense ? kStagesDense : kStagesSparse);
 }
 __host__ __device__ constexpr int stage_bytes(bool pair) { return pair ? kBBytesPerStage / 2 : kBBytesPerStage; }
 __host__ __device__ inline SmemLayout smem_layout(int k_chunks, bool dense, bool pair) {
