@@ -163,6 +163,7 @@ class DictionaryShardedBinarySAE(nn.Module):
         self.exact = True
         self.gather_output = False
         self.polar_tol = 1e-6
+        self._pol_cache = None
         # ops=False defers the choice (tests install their own backend after construction)
         self.ops = CudaShardOps(self) if ops is None else (ops or None)
 
@@ -200,11 +201,16 @@ class DictionaryShardedBinarySAE(nn.Module):
         return out[: b - a]
 
     def polarize_loss(self, like: torch.Tensor) -> torch.Tensor:
-        num = torch.tensor([self.ops.polarize_numerator()], dtype=torch.float64, device=like.device)
-        if self.plan.world_size > 1:
-            self._dist.all_reduce(num, group=self.group)
-        total = self.hidden_dim * self.input_dim * self.n_bits
-        return (num[0] / total).to(torch.float32)
+        """mean over the FULL dictionary of p (1 - p) 2^i (sae/binary.py:41-42): weight-only, so the
+        all-reduce of the per-shard numerators runs once per weight version, not per forward."""
+        key = param_key(self.decoder.weight) + (str(like.device),)
+        if self._pol_cache is None or self._pol_cache[0] != key:
+            num = torch.tensor([self.ops.polarize_numerator()], dtype=torch.float64, device=like.device)
+            if self.plan.world_size > 1:
+                self._dist.all_reduce(num, group=self.group)
+            total = self.hidden_dim * self.input_dim * self.n_bits
+            self._pol_cache = (key, (num[0] / total).to(torch.float32))
+        return self._pol_cache[1]
 
     # ---- forward ------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor):
