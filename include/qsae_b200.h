@@ -196,13 +196,14 @@ int qsae_matryoshka_forward(const float* x_f32, const uint16_t* w_bf16,
  * has more active latents than its survivor lists hold -- e.g. an untrained model, ~50 % active):
  * dense pre-activations, A = (sigmoid(z) > 0.5) * scale as bf16 hi + lo, and one tcgen05 GEMM per level
  * over that level's range of the latent axis with T^T [D, H] in bf16, outputs accumulated level by level.
- * w_f32 given: pre-activations on fp32 CUDA cores (exact for any fp32 operands); else w_bf16 on the
- * tensor cores. level_start is needed on the device (counts) and on the host (GEMM ranges);
+ * w_mid / w_lo given (qsae_split_bf16x3 of the encoder weight): fp32-accurate pre-activations through the
+ * split passes described at qsae_tsae_forward; else one bf16 pass. level_start is needed on the device (counts) and on the host (GEMM ranges);
  * boundaries and H must be multiples of 8. */
 int qsae_unpack_matryoshka_t(const uint32_t* packed /* [H, D/16] */, int H, int D, uint16_t* t_bf16 /* [D, H] */,
                              void* stream);
 int qsae_matryoshka_dense_workspace_bytes(int B, int H, int D, size_t* bytes);
-int qsae_matryoshka_forward_dense(const float* x_f32, const uint16_t* w_bf16, const float* w_f32, const float* b_enc,
+int qsae_matryoshka_forward_dense(const float* x_f32, const uint16_t* w_hi, const uint16_t* w_mid, const uint16_t* w_lo,
+                                  const float* b_enc,
                                   const uint16_t* t_bf16, const float* scale, const int* level_start_dev,
                                   const int* level_start_host, int n_levels, const float* dec_bias, int B, int H,
                                   int D, float* result /* [n_levels, B, D] */,
@@ -241,6 +242,9 @@ int qsae_pack_ternary(const float* w /* [D, H] */, int D, int H, float threshold
 
 /* hi = bf16(src), lo = bf16(src - hi) (lo may be NULL): hi + lo carries 16 mantissa bits of src. */
 int qsae_split_bf16(const float* src, uint16_t* hi, uint16_t* lo, size_t n, void* stream);
+/* hi + mid + lo == src exactly (8 + 8 + 8 mantissa bits). The exact modes of the dense encoder take the
+ * encoder weight in this form (one-time, cached per weight version); mid / lo may be NULL. */
+int qsae_split_bf16x3(const float* src, uint16_t* hi, uint16_t* mid, uint16_t* lo, size_t n, void* stream);
 
 /* out[B, N] = (a_hi (+ a_lo))[B, K] * b_t[N, K]^T (+ bias): the dense F.linear(h, hard_weights) of
  * sae/ternary.py:52 on the tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM, split-K
@@ -254,12 +258,15 @@ int qsae_decode_dense(const uint16_t* a_hi /* [B, K] */, const uint16_t* a_lo /*
  * exact = 0: h from the tcgen05 encoder (bf16 operands: equals the fp32 reference up to accumulation
  *            order when x and W are bf16-representable), written as fp32 (h_out) and bf16 by TMA stores
  *            from the GEMM epilogue; recon from one pass over bf16(h) (relative error <= 2^-9 per term).
- * exact = 1: h from the fp32 CUDA-core encoder (any fp32 operands; not a throughput path), recon from
- *            two accumulating passes over the hi/lo split of h (2^-17 per term).
+ * exact = 1: any fp32 operands. x and W are split exactly into three bf16 parts each and the six partial
+ *            products above 2^-24 are accumulated on the tensor cores in three launches of the dense
+ *            encoder (xh (wh + wm + wl); += xm (wh + wm); act(+ xl wh + b)); recon from two accumulating
+ *            passes over the hi/lo split of h (2^-17 per term).
  * H % 8 == 0, D % 8 == 0, 8 <= D <= 512. */
 int qsae_tsae_workspace_bytes(int B, int H, int D, int exact, size_t* bytes);
-int qsae_tsae_forward(const float* x_f32, const uint16_t* w_bf16 /* [H, D], exact = 0 */,
-                      const float* w_f32 /* [H, D], exact = 1 */, const float* b_enc,
+int qsae_tsae_forward(const float* x_f32, const uint16_t* w_hi /* [H, D]: bf16(W) */,
+                      const uint16_t* w_mid, const uint16_t* w_lo /* [H, D] from qsae_split_bf16x3; exact = 1 */,
+                      const float* b_enc,
                       const uint16_t* t_bf16 /* [D, H] from qsae_pack_ternary */, int B, int H, int D, int exact,
                       float* h_out /* [B, H] */, float* recon /* [B, D] */, void* workspace,
                       size_t workspace_bytes, void* stream);

@@ -46,8 +46,8 @@ SYMBOLS = {
     "qsae_residual_update": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "qsae_unpack_matryoshka_t": (_i, [_vp, _i, _i, _vp, _vp]),
     "qsae_matryoshka_dense_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
-    "qsae_matryoshka_forward_dense": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i), _i, _vp, _i, _i, _i, _vp, _vp,
-                                           _vp, _sz, _vp]),
+    "qsae_matryoshka_forward_dense": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i), _i, _vp, _i, _i, _i, _vp,
+                                           _vp, _vp, _sz, _vp]),
     "qsae_decode_matryoshka_lists_workspace_bytes": (_i, [C.POINTER(_sz)]),
     "qsae_decode_matryoshka_lists": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "qsae_pack_ternary": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp]),
@@ -55,7 +55,8 @@ SYMBOLS = {
     "qsae_decode_dense_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
     "qsae_decode_dense": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "qsae_tsae_workspace_bytes": (_i, [_i, _i, _i, _i, C.POINTER(_sz)]),
-    "qsae_tsae_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "qsae_split_bf16x3": (_i, [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "qsae_tsae_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "qsae_pack_candidates": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "qsae_merge_candidates_workspace_bytes": (_i, [_i, C.POINTER(_sz)]),
     "qsae_merge_candidates": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
@@ -422,11 +423,25 @@ def decode_dense(a_hi: torch.Tensor, a_lo: torch.Tensor | None, b_t: torch.Tenso
     return out
 
 
-def tsae_forward(x: torch.Tensor, w_bf16: torch.Tensor | None, w_f32: torch.Tensor | None, b_enc: torch.Tensor,
-                 t_bf16: torch.Tensor, exact: bool):
-    """-> (h [B, H] f32 dense ReLU latents, recon [B, D] f32)"""
+def split_bf16x3(src: torch.Tensor):
+    """-> (hi, mid, lo) bf16 tensors with hi + mid + lo == src exactly."""
     global launch_count
-    _need_cuda(x, w_bf16, w_f32, b_enc, t_bf16)
+    _need_cuda(src)
+    assert src.dtype == torch.float32
+    parts = tuple(torch.empty(src.shape, dtype=torch.bfloat16, device=src.device) for _ in range(3))
+    check(load().qsae_split_bf16x3(src.data_ptr(), parts[0].data_ptr(), parts[1].data_ptr(), parts[2].data_ptr(),
+                                   src.numel(), _stream()))
+    launch_count += 1
+    return parts
+
+
+def tsae_forward(x: torch.Tensor, w_parts, b_enc: torch.Tensor, t_bf16: torch.Tensor, exact: bool):
+    """w_parts: (bf16(W),) for the fast mode or split_bf16x3(W) for the exact mode.
+    -> (h [B, H] f32 dense ReLU latents, recon [B, D] f32)"""
+    global launch_count
+    w_hi = w_parts[0]
+    w_mid, w_lo = (w_parts[1], w_parts[2]) if exact else (None, None)
+    _need_cuda(x, w_hi, w_mid, w_lo, b_enc, t_bf16)
     B, D = x.shape
     H = t_bf16.shape[1]
     h = torch.empty((B, H), dtype=torch.float32, device=x.device)
@@ -436,10 +451,10 @@ def tsae_forward(x: torch.Tensor, w_bf16: torch.Tensor | None, w_f32: torch.Tens
     n = _sz(0)
     check(load().qsae_tsae_workspace_bytes(B, H, D, 1 if exact else 0, C.byref(n)))
     ws = _workspace(x.device, int(n.value))
-    check(load().qsae_tsae_forward(x.data_ptr(), _ptr(w_bf16), _ptr(w_f32), b_enc.data_ptr(), t_bf16.data_ptr(), B, H, D,
-                                   1 if exact else 0, h.data_ptr(), recon.data_ptr(), ws.data_ptr(), ws.numel(),
-                                   _stream()))
-    launch_count += 4
+    check(load().qsae_tsae_forward(x.data_ptr(), w_hi.data_ptr(), _ptr(w_mid), _ptr(w_lo), b_enc.data_ptr(),
+                                   t_bf16.data_ptr(), B, H, D, 1 if exact else 0, h.data_ptr(), recon.data_ptr(),
+                                   ws.data_ptr(), ws.numel(), _stream()))
+    launch_count += 6 if exact else 4
     return h, recon
 
 
@@ -496,10 +511,13 @@ def unpack_matryoshka_t(packed: torch.Tensor, D: int) -> torch.Tensor:
     return t
 
 
-def matryoshka_forward_dense(x, w_bf16, w_f32, b_enc, t_bf16, scale, level_start_dev, level_start_host, dec_bias):
-    """Dense q_sae forward -> (result [n_levels, B, D] f32, level_count [n_levels] int64)."""
+def matryoshka_forward_dense(x, w_parts, b_enc, t_bf16, scale, level_start_dev, level_start_host, dec_bias):
+    """Dense q_sae forward -> (result [n_levels, B, D] f32, level_count [n_levels] int64).
+    w_parts: (bf16(W),) or split_bf16x3(W) for fp32-accurate activity decisions."""
     global launch_count
-    _need_cuda(x, w_bf16, w_f32, b_enc, t_bf16, scale, level_start_dev, dec_bias)
+    w_hi = w_parts[0]
+    w_mid, w_lo = (w_parts[1], w_parts[2]) if len(w_parts) == 3 else (None, None)
+    _need_cuda(x, w_hi, w_mid, w_lo, b_enc, t_bf16, scale, level_start_dev, dec_bias)
     B, D = x.shape
     H = t_bf16.shape[1]
     n_levels = len(level_start_host) - 1
@@ -511,7 +529,8 @@ def matryoshka_forward_dense(x, w_bf16, w_f32, b_enc, t_bf16, scale, level_start
     check(load().qsae_matryoshka_dense_workspace_bytes(B, H, D, C.byref(n)))
     ws = _workspace(x.device, int(n.value))
     starts = (_i * (n_levels + 1))(*[int(v) for v in level_start_host])
-    check(load().qsae_matryoshka_forward_dense(x.data_ptr(), _ptr(w_bf16), _ptr(w_f32), b_enc.data_ptr(), t_bf16.data_ptr(),
+    check(load().qsae_matryoshka_forward_dense(x.data_ptr(), w_hi.data_ptr(), _ptr(w_mid), _ptr(w_lo), b_enc.data_ptr(),
+                                               t_bf16.data_ptr(),
                                                scale.data_ptr(), level_start_dev.data_ptr(), starts, n_levels,
                                                _ptr(dec_bias), B, H, D, result.data_ptr(), counts.data_ptr(),
                                                ws.data_ptr(), ws.numel(), _stream()))

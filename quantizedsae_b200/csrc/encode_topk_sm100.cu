@@ -419,11 +419,69 @@ __device__ __forceinline__ void epilogue_dense(const EncodeLaunch& p, int n_my_t
         r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + b.z);
         r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + b.w);
       }
-      if (p.act == 1) {
+      if (p.act == 1 && p.accum_mode == 0) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]), 0.f));
       }
       if (!warp_live || col0 >= p.H) continue;  // warp-uniform
+      if (p.accum_mode != 0) {
+        // Split-operand passes (exact fp32 encoder): r holds this pass's raw partial products (the
+        // launcher passes no bias for these passes; the final pass adds p.accum_bias here).
+        //   1: out = acc            2: out = out + acc            3: out = act(out + acc + bias), + bf16 hi / lo
+        // The transformation runs in the row-contiguous read-back layout, where `out` is read coalesced.
+        auto finish = [&](int rr, int cc, const uint4 u) {
+          if (row0 + rr >= p.B || cc >= p.H) return;
+          const size_t off = static_cast<size_t>(row0 + rr) * H + cc;
+          float4 v = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+          if (p.accum_mode >= 2) {
+            const float4 o = *reinterpret_cast<const float4*>(p.out_f32 + off);
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+          }
+          if (p.accum_mode == 3) {
+            const float4 b = *reinterpret_cast<const float4*>(p.accum_bias + cc);
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            if (p.act == 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            if (flags & 6) {
+              const uint32_t h0 = pack_bf16x2(v.x, v.y), h1 = pack_bf16x2(v.z, v.w);
+              if (flags & 2) *reinterpret_cast<uint2*>(p.out_hi + off) = make_uint2(h0, h1);
+              if (flags & 4) {
+                const uint32_t l0 = pack_bf16x2(v.x - __uint_as_float(h0 << 16), v.y - __uint_as_float(h0 & 0xFFFF0000u));
+                const uint32_t l1 = pack_bf16x2(v.z - __uint_as_float(h1 << 16), v.w - __uint_as_float(h1 & 0xFFFF0000u));
+                *reinterpret_cast<uint2*>(p.out_lo + off) = make_uint2(l0, l1);
+              }
+            }
+          }
+          *reinterpret_cast<float4*>(p.out_f32 + off) = v;
+        };
+        if constexpr (WIDE) {
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            st_shared_v4(st + lane * 128 + ((q ^ (lane & 7)) << 4), r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int rr = 4 * j + f_row;
+            finish(rr, col0 + f_col, ld_shared_v4(st + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4)));
+          }
+        } else {
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              st_shared_v4(st + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4), r[16 * hf + 4 * q], r[16 * hf + 4 * q + 1],
+                           r[16 * hf + 4 * q + 2], r[16 * hf + 4 * q + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int rr = 8 * j + h_row;
+              finish(rr, col0 + 16 * hf + (lane & 3) * 4, ld_shared_v4(st + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4)));
+            }
+          }
+        }
+        continue;
+      }
       if (flags & 1) {
         if constexpr (WIDE) {
           __syncwarp();                            // the previous tile's readers are done
@@ -521,8 +579,9 @@ __device__ __forceinline__ void epilogue_dense(const EncodeLaunch& p, int n_my_t
 template <int K_CHUNKS, bool DENSE, int CL>
 __global__ void __launch_bounds__(cta_threads(DENSE), 1)
 encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
-                   const __grid_constant__ CUtensorMap tmap_w,
-                   const __grid_constant__ CUtensorMap tmap_wh, EncodeLaunch p) {
+                   const __grid_constant__ CUtensorMap tmap_b0,
+                   const __grid_constant__ CUtensorMap tmap_b1,
+                   const __grid_constant__ CUtensorMap tmap_b2, EncodeLaunch p) {
   constexpr bool MCAST = CL == 1;
   constexpr bool PAIR = CL == 2;
   constexpr int kStages = ring_stages(DENSE, PAIR);
@@ -553,6 +612,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
   const int n_my_tiles = max(0, tile_end - tile_begin);
   const uint32_t cta_rank = (CL != 0) ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0u;
+  const int k_iters = (p.k_parts > 1 ? p.k_parts : 1) * K_CHUNKS;
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0u) {
@@ -588,7 +648,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
     // ------------------------------------------------------------- TMA producer
     if (lane == 0 && n_my_tiles > 0) {
       tma_prefetch_desc(&tmap_x);
-      tma_prefetch_desc(PAIR || MCAST ? &tmap_wh : &tmap_w);
+      tma_prefetch_desc(&tmap_b0);
       if constexpr (PAIR) {
         // both x tiles and both halves of every W stage are credited to the leader's barriers
         const uint32_t a_full_leader = mapa_u32(smem_u32(a_full), 0);
@@ -606,22 +666,24 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
       uint32_t phase = 0;
       for (int t = 0; t < n_my_tiles; ++t) {
         const int n0 = (tile_begin + t) * BN;
+        // p.k_parts B operands (bf16 parts of W) are contracted against the same resident x tile
 #pragma unroll 1
-        for (int kc = 0; kc < K_CHUNKS; ++kc) {
+        for (int it = 0; it < k_iters; ++it) {
+          const int part = it / K_CHUNKS, kc = it - part * K_CHUNKS;
+          const CUtensorMap* tb = part == 0 ? &tmap_b0 : (part == 1 ? &tmap_b1 : &tmap_b2);
           mbar_wait(&empty[stage], phase ^ 1u);
           if constexpr (PAIR) {
             if (leader) mbar_arrive_expect_tx(&full[stage], kBBytesPerStage);   // 16 KiB from each CTA
-            tma_load_2d_pair(b_smem + stage * kStageBytes, &tmap_wh, mapa_u32(smem_u32(&full[stage]), 0), kc * BK,
+            tma_load_2d_pair(b_smem + stage * kStageBytes, tb, mapa_u32(smem_u32(&full[stage]), 0), kc * BK,
                              n0 + static_cast<int>(cta_rank) * (BN / 2), kPolicyEvictLast);
           } else if constexpr (MCAST) {
             mbar_arrive_expect_tx(&full[stage], kBBytesPerStage);
             // my half of the stage lands in both CTAs; the other half arrives from the peer
-            tma_load_2d_mcast(b_smem + stage * kBBytesPerStage + cta_rank * (kBBytesPerStage / 2), &tmap_wh,
+            tma_load_2d_mcast(b_smem + stage * kBBytesPerStage + cta_rank * (kBBytesPerStage / 2), tb,
                               &full[stage], kc * BK, n0 + static_cast<int>(cta_rank) * (BN / 2), 0x3, kPolicyEvictLast);
           } else {
             mbar_arrive_expect_tx(&full[stage], kBBytesPerStage);
-            tma_load_2d(b_smem + stage * kBBytesPerStage, &tmap_w, &full[stage], kc * BK, n0,
-                        kPolicyEvictLast);
+            tma_load_2d(b_smem + stage * kBBytesPerStage, tb, &full[stage], kc * BK, n0, kPolicyEvictLast);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -642,7 +704,8 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
 #pragma unroll 1
-        for (int kc = 0; kc < K_CHUNKS; ++kc) {
+        for (int it = 0; it < k_iters; ++it) {
+          const int kc = it % K_CHUNKS;      // every part of W meets the same x chunks
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((kc * kABytesPerChunk) >> 4);
@@ -651,16 +714,16 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
           for (int ks = 0; ks < BK / UMMA_K; ++ks) {
             // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the
             // (address >> 4) field of the descriptor
-            if constexpr (PAIR) umma_f16_ss_pair(d_tmem, a_desc + ks * 2, b_desc + ks * 2, idesc, (kc | ks) != 0 ? 1u : 0u);
-            else umma_f16_ss(d_tmem, a_desc + ks * 2, b_desc + ks * 2, idesc, (kc | ks) != 0 ? 1u : 0u);
+            if constexpr (PAIR) umma_f16_ss_pair(d_tmem, a_desc + ks * 2, b_desc + ks * 2, idesc, (it | ks) != 0 ? 1u : 0u);
+            else umma_f16_ss(d_tmem, a_desc + ks * 2, b_desc + ks * 2, idesc, (it | ks) != 0 ? 1u : 0u);
           }
           if constexpr (PAIR) {
             umma_commit_pair(&empty[stage], 0x3);
-            if (kc == K_CHUNKS - 1) umma_commit_pair(&tmem_full[acc], 0x3);
+            if (it == k_iters - 1) umma_commit_pair(&tmem_full[acc], 0x3);
           } else {
             if constexpr (MCAST) umma_commit_mcast(&empty[stage], 0x3);
             else umma_commit(&empty[stage]);
-            if (kc == K_CHUNKS - 1) umma_commit(&tmem_full[acc]);
+            if (it == k_iters - 1) umma_commit(&tmem_full[acc]);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -675,7 +738,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
 #pragma unroll
       for (int i = 0; i < BN / 32; ++i) {
         const int c = i * 32 + lane;
-        bias_smem[acc * BN + c] = (n0 + c < p.H) ? __ldg(p.bias + n0 + c) : 0.f;
+        bias_smem[acc * BN + c] = (p.bias != nullptr && n0 + c < p.H) ? __ldg(p.bias + n0 + c) : 0.f;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bias_full[acc]);
@@ -763,9 +826,10 @@ bool make_tmap_bf16(CUtensorMap* map, const void* base, int rows, int cols, int 
                       CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+struct BMaps { CUtensorMap m[3]; };   // the (up to three) bf16 parts of W, boxed for the chosen cluster variant
+
 template <int K_CHUNKS, bool DENSE, int CL>
-cudaError_t launch_k(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& twh, const EncodeLaunch& p,
-                     cudaStream_t stream) {
+cudaError_t launch_k(const CUtensorMap& tx, const BMaps& b, const EncodeLaunch& p, cudaStream_t stream) {
   const SmemLayout L = smem_layout(K_CHUNKS, DENSE, CL == 2);
   static bool attr_set = false;
   if (!attr_set) {
@@ -790,30 +854,29 @@ cudaError_t launch_k(const CUtensorMap& tx, const CUtensorMap& tw, const CUtenso
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, encode_topk_kernel<K_CHUNKS, DENSE, CL>, tx, tw, twh, p);
+    return cudaLaunchKernelEx(&cfg, encode_topk_kernel<K_CHUNKS, DENSE, CL>, tx, b.m[0], b.m[1], b.m[2], p);
   } else {
-    encode_topk_kernel<K_CHUNKS, DENSE, CL><<<grid, cta_threads(DENSE), L.total, stream>>>(tx, tw, twh, p);
+    encode_topk_kernel<K_CHUNKS, DENSE, CL><<<grid, cta_threads(DENSE), L.total, stream>>>(tx, b.m[0], b.m[1], b.m[2], p);
     return cudaGetLastError();
   }
 }
 
 template <bool DENSE>
-const char* launch_any(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& twh, const EncodeLaunch& p,
-                       cudaStream_t stream) {
+const char* launch_any(const CUtensorMap& tx, const BMaps& b, const EncodeLaunch& p, cudaStream_t stream) {
   const int kc = (p.D + BK - 1) / BK;
   cudaError_t e;
   switch (kc) {
-    case 1: e = launch_k<1, DENSE, 0>(tx, tw, twh, p, stream); break;
-    case 2: e = launch_k<2, DENSE, 0>(tx, tw, twh, p, stream); break;
-    case 3: e = launch_k<3, DENSE, 0>(tx, tw, twh, p, stream); break;
-    case 4: e = launch_k<4, DENSE, 0>(tx, tw, twh, p, stream); break;
-    case 5: e = launch_k<5, DENSE, 0>(tx, tw, twh, p, stream); break;
-    case 6: e = launch_k<6, DENSE, 0>(tx, tw, twh, p, stream); break;
-    case 7: e = launch_k<7, DENSE, 0>(tx, tw, twh, p, stream); break;
+    case 1: e = launch_k<1, DENSE, 0>(tx, b, p, stream); break;
+    case 2: e = launch_k<2, DENSE, 0>(tx, b, p, stream); break;
+    case 3: e = launch_k<3, DENSE, 0>(tx, b, p, stream); break;
+    case 4: e = launch_k<4, DENSE, 0>(tx, b, p, stream); break;
+    case 5: e = launch_k<5, DENSE, 0>(tx, b, p, stream); break;
+    case 6: e = launch_k<6, DENSE, 0>(tx, b, p, stream); break;
+    case 7: e = launch_k<7, DENSE, 0>(tx, b, p, stream); break;
     case 8:   // the headline width: the cluster variants exist here
-      if (p.cluster == 2) e = launch_k<8, DENSE, 2>(tx, tw, twh, p, stream);
-      else if (p.cluster == 1) e = launch_k<8, DENSE, 1>(tx, tw, twh, p, stream);
-      else e = launch_k<8, DENSE, 0>(tx, tw, twh, p, stream);
+      if (p.cluster == 2) e = launch_k<8, DENSE, 2>(tx, b, p, stream);
+      else if (p.cluster == 1) e = launch_k<8, DENSE, 1>(tx, b, p, stream);
+      else e = launch_k<8, DENSE, 0>(tx, b, p, stream);
       break;
     default: return "D must be <= 512";
   }
@@ -855,34 +918,47 @@ void encode_pick_mode(int k_sel, int* mode, int* cap) {
   else *mode = 0;
 }
 
-const char* encode_topk_launch(const uint16_t* x_bf16, const uint16_t* w_bf16, EncodeLaunch p,
-                               cudaStream_t stream) {
-  CUtensorMap tx, tw;
-  if (!make_tmap_bf16(&tx, x_bf16, p.B, p.D, BM)) return "cuTensorMapEncodeTiled(x) failed";
-  if (!make_tmap_bf16(&tw, w_bf16, p.H, p.D, BN)) return "cuTensorMapEncodeTiled(W) failed";
-  p.dense_flags = 0;
-  p.cluster = pick_cluster(p, p.B >= 16384 ? 1 : 0);
-  CUtensorMap twh = tw;
-  if (p.cluster && !make_tmap_bf16(&twh, w_bf16, p.H, p.D, BN / 2)) return "cuTensorMapEncodeTiled(W half) failed";
-  return launch_any<false>(tx, tw, twh, p, stream);
+// tensor maps of the W parts with the box the cluster variant loads (256 latents, or 128 per CTA of a pair)
+const char* make_b_maps(BMaps* bm, const uint16_t* const* parts, int n_parts, const EncodeLaunch& p) {
+  const int box = p.cluster ? BN / 2 : BN;
+  for (int i = 0; i < 3; ++i) {
+    const uint16_t* w = parts[i < n_parts ? i : 0];
+    if (!make_tmap_bf16(&bm->m[i], w, p.H, p.D, box)) return "cuTensorMapEncodeTiled(W) failed";
+  }
+  return nullptr;
 }
 
-const char* encode_dense_tc_launch(const uint16_t* x_bf16, const uint16_t* w_bf16, EncodeLaunch p, float* out_f32,
-                                   uint16_t* out_hi, uint16_t* out_lo, cudaStream_t stream) {
+const char* encode_topk_launch(const uint16_t* x_bf16, const uint16_t* w_bf16, EncodeLaunch p,
+                               cudaStream_t stream) {
+  CUtensorMap tx;
+  if (!make_tmap_bf16(&tx, x_bf16, p.B, p.D, BM)) return "cuTensorMapEncodeTiled(x) failed";
+  p.dense_flags = 0;
+  p.k_parts = 1;
+  p.accum_mode = 0;
+  p.cluster = pick_cluster(p, p.B >= 16384 ? 1 : 0);
+  BMaps bm;
+  if (const char* err = make_b_maps(&bm, &w_bf16, 1, p)) return err;
+  return launch_any<false>(tx, bm, p, stream);
+}
+
+const char* encode_dense_tc_launch(const uint16_t* x_bf16, const uint16_t* const* w_parts, int n_parts, EncodeLaunch p,
+                                   float* out_f32, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t stream) {
   if ((p.H % 8) != 0) return "dense tensor-core encoder needs H % 8 == 0";
+  if (n_parts < 1 || n_parts > 3) return "dense tensor-core encoder: 1 to 3 parts of W";
   if ((reinterpret_cast<uintptr_t>(out_f32) | reinterpret_cast<uintptr_t>(out_hi) | reinterpret_cast<uintptr_t>(out_lo)) & 15)
     return "dense tensor-core encoder: outputs must be 16-byte aligned";
-  CUtensorMap tx, tw;
+  if (p.accum_mode != 0 && !out_f32) return "dense encoder: accumulating passes need the fp32 output";
+  CUtensorMap tx;
   if (!make_tmap_bf16(&tx, x_bf16, p.B, p.D, BM)) return "cuTensorMapEncodeTiled(x) failed";
-  if (!make_tmap_bf16(&tw, w_bf16, p.H, p.D, BN)) return "cuTensorMapEncodeTiled(W) failed";
   p.out_f32 = out_f32; p.out_hi = out_hi; p.out_lo = out_lo;
+  p.k_parts = n_parts;
   p.dense_flags = (out_f32 ? 1 : 0) | (out_hi ? 2 : 0) | (out_lo ? 4 : 0);
   if (p.dense_flags == 0) return "dense encoder: no output requested";
   if (const char* m = getenv("QSAE_DENSE_FLAGS_MASK")) p.dense_flags &= atoi(m);  // timing experiments only
   p.cluster = pick_cluster(p, kDefaultClusterDense);
-  CUtensorMap twh = tw;
-  if (p.cluster && !make_tmap_bf16(&twh, w_bf16, p.H, p.D, BN / 2)) return "cuTensorMapEncodeTiled(W half) failed";
-  return launch_any<true>(tx, tw, twh, p, stream);
+  BMaps bm;
+  if (const char* err = make_b_maps(&bm, w_parts, n_parts, p)) return err;
+  return launch_any<true>(tx, bm, p, stream);
 }
 
 }  // namespace qsae

@@ -33,6 +33,9 @@ struct EncodeLaunch {
   float* cand_thr;      // [B][n_splits*2] inclusive lower bound of the row's k_sel-th largest value
   int cluster;          // 0 single CTA, 1 TMA-multicast pair, 2 cta_group::2 pair (set by the launcher)
   int dense_flags;      // dense epilogue outputs: 1 fp32, 2 bf16 hi, 4 bf16 lo (set by the launcher)
+  int k_parts;          // 1..3 bf16 parts of W contracted against the same x tile (set by the launcher)
+  int accum_mode;       // dense epilogue, split-operand passes: 0 off, 1 out = acc, 2 out += acc, 3 out = act(out + acc + bias)
+  const float* accum_bias;  // [H], added by the final accumulating pass
   float* out_f32;       // dense epilogue: [B, H] row-major outputs (set by the launcher)
   uint16_t* out_hi;
   uint16_t* out_lo;
@@ -47,8 +50,12 @@ const char* encode_topk_launch(const uint16_t* x_bf16, const uint16_t* w_bf16, E
                                cudaStream_t stream);
 
 // dense epilogue variant (t_sae): h = act(x W^T + b) as fp32 and/or bf16 hi (+ lo) [B, H], TMA stores
-const char* encode_dense_tc_launch(const uint16_t* x_bf16, const uint16_t* w_bf16, EncodeLaunch p, float* out_f32,
-                                   uint16_t* out_hi, uint16_t* out_lo, cudaStream_t stream);
+// w_parts: 1..3 bf16 matrices [H, D] whose sum is W (hi, mid, lo of a split fp32 matrix): all are contracted
+// against x into the same accumulator. p.accum_mode selects plain / accumulating output (see EncodeLaunch).
+const char* encode_dense_tc_launch(const uint16_t* x_bf16, const uint16_t* const* w_parts, int n_parts, EncodeLaunch p,
+                                   float* out_f32, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t stream);
+// src -> three bf16 parts with hi + mid + lo == src exactly (24 mantissa bits); mid / lo may be null
+const char* split_bf16x3_launch(const float* src, uint16_t* hi, uint16_t* mid, uint16_t* lo, size_t n, cudaStream_t stream);
 
 // dense_decode_sm100.cu: out[B, N] = (a_hi (+ a_lo))[B, K] * b_t[N, K]^T (+ bias), bf16 in, fp32 accumulate
 int dense_decode_pick_splits(int B, int K, int num_sms);

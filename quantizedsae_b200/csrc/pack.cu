@@ -144,6 +144,24 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, uint16_t* __res
   }
 }
 
+// hi = bf16(v), mid = bf16(v - hi), lo = bf16(v - hi - mid): the three parts sum to v exactly
+// (8 + 8 + 8 mantissa bits; both subtractions are exact in fp32)
+__global__ void split_bf16x3_kernel(const float* __restrict__ src, uint16_t* __restrict__ hi, uint16_t* __restrict__ mid,
+                                    uint16_t* __restrict__ lo, size_t n) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = src[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(m);
+    const __nv_bfloat16 l = __float2bfloat16_rn(r2);
+    hi[i] = *reinterpret_cast<const uint16_t*>(&h);
+    if (mid != nullptr) mid[i] = *reinterpret_cast<const uint16_t*>(&m);
+    if (lo != nullptr) lo[i] = *reinterpret_cast<const uint16_t*>(&l);
+  }
+}
+
 // STEWeights hard weights (sae/ternary.py:46-49): sign(w) * (|w| >= threshold) in {-1, 0, +1}.
 // 32 x 32 tiles of w [D, H]: bf16 in place ([D, H], K-major B operand of the decoder GEMM) and
 // transposed int8 rows ([H, D], gather layout of the sparse decoder).
@@ -258,6 +276,11 @@ const char* sample_rows_launch(const uint16_t* w_bf16, const float* bias, int H,
 
 const char* residual_update_launch(const float* r, const float* recon, size_t n, float* out, cudaStream_t stream) {
   residual_update_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, stream>>>(r, recon, n, out);
+  return cuda_err(cudaGetLastError());
+}
+
+const char* split_bf16x3_launch(const float* src, uint16_t* hi, uint16_t* mid, uint16_t* lo, size_t n, cudaStream_t stream) {
+  split_bf16x3_kernel<<<grid_for(n, 256), 256, 0, stream>>>(src, hi, mid, lo, n);
   return cuda_err(cudaGetLastError());
 }
 

@@ -516,6 +516,60 @@ int qsae_decode_dense(const uint16_t* a_hi, const uint16_t* a_lo, const uint16_t
 }
 
 namespace {
+// Dense pre-activations (+ activation) on the tensor cores.
+//   w_mid == w_lo == nullptr: one pass over bf16(x) and w_hi (fast mode).
+//   otherwise: fp32-accurate product through 8 + 8 + 8-bit operand splits, x = xh + xm + xl and
+//   W = wh + wm + wl (both exact), keeping the six partial products above 2^-24:
+//     pass 1: xh * (wh + wm + wl) -> out      pass 2: out += xm * (wh + wm)
+//     pass 3: out = act(out + xl * wh + bias), bf16 hi (+ lo) of the result written alongside.
+//   Each pass is one launch of the dense encoder kernel (the x tile is resident in shared memory, the W
+//   parts stream through the ring into the same TMEM accumulator).
+// x_parts: workspace for the bf16 part(s) of x, 3 * align_up(B * D * 2, 1024) bytes in split mode.
+int dense_encode_tc(const float* x_f32, const uint16_t* w_hi, const uint16_t* w_mid, const uint16_t* w_lo,
+                    const float* b_enc, int B, int H, int D, int act, uint8_t* x_parts, float* out_f32, uint16_t* out_hi,
+                    uint16_t* out_lo, cudaStream_t st) {
+  EncodeLaunch el;
+  memset(&el, 0, sizeof(el));
+  el.B = B; el.H = H; el.D = D; el.act = act; el.bias = b_enc;
+  el.n_tiles = (H + kEncBN - 1) / kEncBN;
+  el.n_splits = encode_pick_splits(B, H, num_sms());
+  el.tiles_per_split = (el.n_tiles + el.n_splits - 1) / el.n_splits;
+  const size_t xn = static_cast<size_t>(B) * D;
+  const size_t xstride = align_up(xn * 2, 1024);
+  uint16_t* xh = reinterpret_cast<uint16_t*>(x_parts);
+  if (!w_mid || !w_lo) {
+    int rc = launch_status("cast x", cast_bf16_launch(x_f32, xh, xn, st));
+    if (rc != QSAE_OK) return rc;
+    const uint16_t* parts[1] = {w_hi};
+    if (g_enc_ev_start) cudaEventRecord(g_enc_ev_start, st);
+    rc = launch_status("encode kernel (dense)", encode_dense_tc_launch(xh, parts, 1, el, out_f32, out_hi, out_lo, st));
+    if (g_enc_ev_stop) cudaEventRecord(g_enc_ev_stop, st);
+    return rc;
+  }
+  uint16_t* xm = reinterpret_cast<uint16_t*>(x_parts + xstride);
+  uint16_t* xl = reinterpret_cast<uint16_t*>(x_parts + 2 * xstride);
+  int rc = launch_status("split x", split_bf16x3_launch(x_f32, xh, xm, xl, xn, st));
+  if (rc != QSAE_OK) return rc;
+  el.bias = nullptr;            // the kernel's bias loader treats a null bias as zeros; the final pass adds b_enc
+  el.accum_bias = b_enc;
+  const uint16_t* p1[3] = {w_hi, w_mid, w_lo};
+  const uint16_t* p2[2] = {w_hi, w_mid};
+  const uint16_t* p3[1] = {w_hi};
+  if (g_enc_ev_start) cudaEventRecord(g_enc_ev_start, st);
+  el.accum_mode = 1;
+  rc = launch_status("encode kernel (dense, xh)", encode_dense_tc_launch(xh, p1, 3, el, out_f32, nullptr, nullptr, st));
+  if (rc != QSAE_OK) return rc;
+  el.accum_mode = 2;
+  rc = launch_status("encode kernel (dense, xm)", encode_dense_tc_launch(xm, p2, 2, el, out_f32, nullptr, nullptr, st));
+  if (rc != QSAE_OK) return rc;
+  el.accum_mode = 3;
+  rc = launch_status("encode kernel (dense, xl)", encode_dense_tc_launch(xl, p3, 1, el, out_f32, out_hi, out_lo, st));
+  if (g_enc_ev_stop) cudaEventRecord(g_enc_ev_stop, st);
+  return rc;
+}
+}  // namespace
+
+namespace {
 struct TsaePlan { size_t x_off, hi_off, lo_off, dec_off, total; };
 int plan_tsae(int B, int H, int D, int exact, TsaePlan* tp) {
   if (B <= 0 || H <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "B and H must be positive (B=%d H=%d)", B, H);
@@ -523,7 +577,7 @@ int plan_tsae(int B, int H, int D, int exact, TsaePlan* tp) {
     return fail(QSAE_ERR_INVALID_ARGUMENT, "D must be a multiple of 8 in [8, 512], got %d", D);
   if ((H % 8) != 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "t_sae: hidden_dim must be a multiple of 8, got %d", H);
   tp->x_off = 0;
-  tp->hi_off = align_up(static_cast<size_t>(B) * D * 2, 1024);
+  tp->hi_off = (exact ? 3 : 1) * align_up(static_cast<size_t>(B) * D * 2, 1024);
   tp->lo_off = align_up(tp->hi_off + static_cast<size_t>(B) * H * 2, 1024);
   tp->dec_off = exact ? align_up(tp->lo_off + static_cast<size_t>(B) * H * 2, 1024) : tp->lo_off;
   tp->total = align_up(tp->dec_off + dense_decode_workspace_bytes(B, H, D, num_sms()), 256);
@@ -540,13 +594,19 @@ int qsae_tsae_workspace_bytes(int B, int H, int D, int exact, size_t* bytes) {
   return QSAE_OK;
 }
 
-int qsae_tsae_forward(const float* x_f32, const uint16_t* w_bf16, const float* w_f32, const float* b_enc,
-                      const uint16_t* t_bf16, int B, int H, int D, int exact, float* h_out, float* recon,
-                      void* workspace, size_t workspace_bytes, void* stream) {
+int qsae_split_bf16x3(const float* src, uint16_t* hi, uint16_t* mid, uint16_t* lo, size_t n, void* stream) {
+  if (!src || !hi) return fail(QSAE_ERR_INVALID_ARGUMENT, "split_bf16x3: null pointer");
+  if (n == 0) return QSAE_OK;
+  return launch_status("split_bf16x3", split_bf16x3_launch(src, hi, mid, lo, n, S(stream)));
+}
+
+int qsae_tsae_forward(const float* x_f32, const uint16_t* w_hi, const uint16_t* w_mid, const uint16_t* w_lo,
+                      const float* b_enc, const uint16_t* t_bf16, int B, int H, int D, int exact, float* h_out,
+                      float* recon, void* workspace, size_t workspace_bytes, void* stream) {
   if (B == 0) return QSAE_OK;
-  if (!x_f32 || !b_enc || !t_bf16 || !h_out || !recon || !workspace)
+  if (!x_f32 || !w_hi || !b_enc || !t_bf16 || !h_out || !recon || !workspace)
     return fail(QSAE_ERR_INVALID_ARGUMENT, "tsae_forward: null pointer");
-  if (exact ? !w_f32 : !w_bf16) return fail(QSAE_ERR_INVALID_ARGUMENT, "tsae_forward: missing encoder weights for this mode");
+  if (exact && (!w_mid || !w_lo)) return fail(QSAE_ERR_INVALID_ARGUMENT, "tsae_forward: exact mode needs the three parts of W");
   TsaePlan tp;
   int rc = plan_tsae(B, H, D, exact, &tp);
   if (rc != QSAE_OK) return rc;
@@ -555,30 +615,12 @@ int qsae_tsae_forward(const float* x_f32, const uint16_t* w_bf16, const float* w
   if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0 || (reinterpret_cast<uintptr_t>(h_out) & 15) != 0)
     return fail(QSAE_ERR_INVALID_ARGUMENT, "tsae_forward: workspace must be 1024-byte and h_out 16-byte aligned");
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  uint16_t* x_bf16 = reinterpret_cast<uint16_t*>(ws + tp.x_off);
   uint16_t* h_hi = reinterpret_cast<uint16_t*>(ws + tp.hi_off);
   uint16_t* h_lo = exact ? reinterpret_cast<uint16_t*>(ws + tp.lo_off) : nullptr;
   cudaStream_t st = S(stream);
-  if (exact) {
-    // fp32 CUDA-core encoder (any fp32 operands), then the 16-bit hi/lo split of h
-    rc = launch_status("encode_dense", encode_dense_launch(x_f32, nullptr, B, w_f32, b_enc, H, D, QSAE_ACT_RELU, h_out, st));
-    if (rc != QSAE_OK) return rc;
-    rc = launch_status("split_bf16", split_bf16_launch(h_out, h_hi, h_lo, static_cast<size_t>(B) * H, st));
-    if (rc != QSAE_OK) return rc;
-  } else {
-    rc = launch_status("cast x", cast_bf16_launch(x_f32, x_bf16, static_cast<size_t>(B) * D, st));
-    if (rc != QSAE_OK) return rc;
-    EncodeLaunch el;
-    memset(&el, 0, sizeof(el));
-    el.B = B; el.H = H; el.D = D; el.act = QSAE_ACT_RELU; el.bias = b_enc;
-    el.n_tiles = (H + kEncBN - 1) / kEncBN;
-    el.n_splits = encode_pick_splits(B, H, num_sms());
-    el.tiles_per_split = (el.n_tiles + el.n_splits - 1) / el.n_splits;
-    if (g_enc_ev_start) cudaEventRecord(g_enc_ev_start, st);
-    rc = launch_status("encode kernel (dense)", encode_dense_tc_launch(x_bf16, w_bf16, el, h_out, h_hi, nullptr, st));
-    if (g_enc_ev_stop) cudaEventRecord(g_enc_ev_stop, st);
-    if (rc != QSAE_OK) return rc;
-  }
+  rc = dense_encode_tc(x_f32, w_hi, exact ? w_mid : nullptr, exact ? w_lo : nullptr, b_enc, B, H, D, QSAE_ACT_RELU,
+                       ws + tp.x_off, h_out, h_hi, h_lo, st);
+  if (rc != QSAE_OK) return rc;
   return launch_status("dense_decode", dense_decode_launch(h_hi, h_lo, H, t_bf16, H, B, H, D, nullptr, nullptr, recon,
                                                            ws + tp.dec_off, num_sms(), st));
 }
@@ -599,7 +641,7 @@ int plan_matryoshka_dense(int B, int H, int D, MatDensePlan* mp) {
   if ((H % 8) != 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka dense path: hidden_dim must be a multiple of 8, got %d", H);
   const size_t bh = static_cast<size_t>(B) * H;
   mp->x_off = 0;
-  mp->z_off = align_up(static_cast<size_t>(B) * D * 2, 1024);
+  mp->z_off = 3 * align_up(static_cast<size_t>(B) * D * 2, 1024);   // room for the three bf16 parts of x
   mp->hi_off = align_up(mp->z_off + bh * 4, 1024);
   mp->lo_off = align_up(mp->hi_off + bh * 2, 1024);
   mp->cnt_off = align_up(mp->lo_off + bh * 2, 1024);
@@ -618,7 +660,8 @@ int qsae_matryoshka_dense_workspace_bytes(int B, int H, int D, size_t* bytes) {
   return QSAE_OK;
 }
 
-int qsae_matryoshka_forward_dense(const float* x_f32, const uint16_t* w_bf16, const float* w_f32, const float* b_enc,
+int qsae_matryoshka_forward_dense(const float* x_f32, const uint16_t* w_hi, const uint16_t* w_mid, const uint16_t* w_lo,
+                                  const float* b_enc,
                                   const uint16_t* t_bf16, const float* scale, const int* level_start_dev,
                                   const int* level_start_host, int n_levels, const float* dec_bias, int B, int H, int D,
                                   float* result, unsigned long long* level_count, void* workspace,
@@ -626,7 +669,7 @@ int qsae_matryoshka_forward_dense(const float* x_f32, const uint16_t* w_bf16, co
   if (B == 0) return QSAE_OK;
   if (!x_f32 || !b_enc || !t_bf16 || !scale || !level_start_dev || !level_start_host || !result || !level_count || !workspace)
     return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_forward_dense: null pointer");
-  if (!w_bf16 && !w_f32) return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_forward_dense: no encoder weights");
+  if (!w_hi) return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_forward_dense: no encoder weights");
   if (n_levels < 1 || n_levels > 32) return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_forward_dense: 1 <= n_levels <= 32");
   for (int i = 0; i <= n_levels; ++i) {
     if ((level_start_host[i] % 8) != 0 || (i > 0 && level_start_host[i] <= level_start_host[i - 1]))
@@ -642,28 +685,15 @@ int qsae_matryoshka_forward_dense(const float* x_f32, const uint16_t* w_bf16, co
   if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0)
     return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_forward_dense: workspace must be 1024-byte aligned");
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  uint16_t* x_bf16 = reinterpret_cast<uint16_t*>(ws + mp.x_off);
   float* z = reinterpret_cast<float*>(ws + mp.z_off);
   uint16_t* a_hi = reinterpret_cast<uint16_t*>(ws + mp.hi_off);
   uint16_t* a_lo = reinterpret_cast<uint16_t*>(ws + mp.lo_off);
   cudaStream_t st = S(stream);
   cudaError_t ce = cudaMemsetAsync(level_count, 0, static_cast<size_t>(n_levels) * sizeof(unsigned long long), st);
   if (ce != cudaSuccess) return fail(QSAE_ERR_CUDA, "matryoshka_forward_dense: %s", cudaGetErrorString(ce));
-  // 1. dense pre-activations: fp32 CUDA cores when the original weights are given (exact for any fp32
-  //    operands), else the tcgen05 encoder with its TMA-store epilogue
-  if (w_f32) {
-    rc = launch_status("encode_dense", encode_dense_launch(x_f32, nullptr, B, w_f32, b_enc, H, D, QSAE_ACT_NONE, z, st));
-  } else {
-    rc = launch_status("cast x", cast_bf16_launch(x_f32, x_bf16, static_cast<size_t>(B) * D, st));
-    if (rc != QSAE_OK) return rc;
-    EncodeLaunch el;
-    memset(&el, 0, sizeof(el));
-    el.B = B; el.H = H; el.D = D; el.act = QSAE_ACT_NONE; el.bias = b_enc;
-    el.n_tiles = (H + kEncBN - 1) / kEncBN;
-    el.n_splits = encode_pick_splits(B, H, num_sms());
-    el.tiles_per_split = (el.n_tiles + el.n_splits - 1) / el.n_splits;
-    rc = launch_status("encode kernel (dense)", encode_dense_tc_launch(x_bf16, w_bf16, el, z, nullptr, nullptr, st));
-  }
+  // 1. dense pre-activations on the tensor cores: one bf16 pass, or the fp32-accurate split passes when
+  //    the mid / lo parts of W are given (exact activity decisions for any fp32 operands)
+  rc = dense_encode_tc(x_f32, w_hi, w_mid, w_lo, b_enc, B, H, D, QSAE_ACT_NONE, ws + mp.x_off, z, nullptr, nullptr, st);
   if (rc != QSAE_OK) return rc;
   // 2. A = active * scale, split into bf16 hi / lo; activity counts per level
   rc = launch_status("matryoshka_dense_operand",

@@ -137,6 +137,11 @@ class QuantizedMatryoshkaSAE(SparseAutoencoder):
         w = self.encoder[0].weight
         return self._prep.get("w_bf16", param_key(w), lambda: _lib.cast_bf16(w.detach().contiguous()))
 
+    def _w_parts(self):
+        """(hi, mid, lo) bf16 parts of encoder.0.weight (dense path, exact mode)."""
+        w = self.encoder[0].weight
+        return self._prep.get("w_parts", param_key(w), lambda: _lib.split_bf16x3(w.detach().contiguous()))
+
     def _w_norm_max(self):
         w = self.encoder[0].weight
         return self._prep.get("w_norm", param_key(w), lambda: _lib.max_row_norm(w.detach().contiguous()))
@@ -152,9 +157,9 @@ class QuantizedMatryoshkaSAE(SparseAutoencoder):
         dec = self.decoder
         _, scale = dec._packed()
         ls, _ = dec._levels()
+        w_parts = self._w_parts() if self.exact else (self._w_bf16(),)
         result, counts = _lib.matryoshka_forward_dense(
-            x, None if self.exact else self._w_bf16(), lin.weight.detach().contiguous() if self.exact else None,
-            lin.bias.detach(), dec._t_bf16(), scale, ls, dec._level_starts_host(),
+            x, w_parts, lin.bias.detach(), dec._t_bf16(), scale, ls, dec._level_starts_host(),
             dec.bias.detach() if self.allow_bias else None)
         self.last_path = "dense"
         return dec._finish(result, counts, None, x.shape[0])

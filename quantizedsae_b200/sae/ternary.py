@@ -11,9 +11,11 @@ does not enter the forward value). So t_sae is two chained dense GEMMs:
   * decoder: a second tcgen05 GEMM over K = hidden_dim with the exact-ternary bf16 matrix, split-K
     with a fixed-order reduction.
 `exact` (default True, as for the other modules) reproduces the fp32 reference for arbitrary fp32
-weights/inputs: h from the fp32 CUDA-core encoder and a two-pass hi/lo decoder; exact = False is the
-throughput path, exact when x and encoder.0.weight are bf16-representable (the benchmark's stated
-precondition) up to fp32 accumulation order and bf16 rounding of h in the decoder.
+weights/inputs, still on the tensor cores: x and encoder.0.weight are split exactly into three bf16
+parts each and the six partial products above 2^-24 are accumulated in three launches of the encoder;
+the decoder runs two passes over the hi/lo split of h. exact = False is the throughput path, exact
+when x and encoder.0.weight are bf16-representable (the benchmark's stated precondition) up to fp32
+accumulation order and bf16 rounding of h in the decoder.
 
 The dormant sparse mode `apply_topk_activation` (:102-114) is available on dense inputs and, opt-in,
 as `forward_topk(x)`: fused encoder + top-k (ReLU epilogue) and an int8 ternary row gather.
@@ -81,6 +83,11 @@ class TernarySparseAutoencoder(nn.Module):
         w = self.encoder[0].weight
         return self._prep.get("w_bf16", param_key(w), lambda: _lib.cast_bf16(w.detach().contiguous()))
 
+    def _w_parts(self):
+        """(hi, mid, lo) bf16 parts of encoder.0.weight, hi + mid + lo == W exactly."""
+        w = self.encoder[0].weight
+        return self._prep.get("w_parts", param_key(w), lambda: _lib.split_bf16x3(w.detach().contiguous()))
+
     def _sample(self):
         lin = self.encoder[0]
         return self._prep.get("sample", param_key(lin.weight, lin.bias),
@@ -112,8 +119,8 @@ class TernarySparseAutoencoder(nn.Module):
         lin = self.encoder[0]
         t_bf16 = self.decoder._ternary()[0]
         if self.exact:
-            h, recon = _lib.tsae_forward(x, None, lin.weight.detach().contiguous(), lin.bias.detach(), t_bf16, True)
+            h, recon = _lib.tsae_forward(x, self._w_parts(), lin.bias.detach(), t_bf16, True)
         else:
-            h, recon = _lib.tsae_forward(x, self._w_bf16(), None, lin.bias.detach(), t_bf16, False)
+            h, recon = _lib.tsae_forward(x, (self._w_bf16(),), lin.bias.detach(), t_bf16, False)
         self.decoder.input_activations = h        # the reference's forward hook (sae/ternary.py:21-22)
         return h, recon

@@ -17,10 +17,10 @@ We = ((torch.rand((H, D), device=dev, generator=g) * 2 - 1) * (6.0 / (H + D)) **
 be = torch.zeros(H, device=dev)
 Wd = 0.4824 * torch.randn((D, H), device=dev, generator=g)
 xs = [torch.randn((B, D), device=dev, generator=g).bfloat16().float() for _ in range(3)]
-w_bf16 = L.cast_bf16(We)
+w_parts = L.split_bf16x3(We) if exact else (L.cast_bf16(We),)
 t_bf16, _ = L.pack_ternary(Wd)
 for i in range(3):
-    h, r = L.tsae_forward(xs[i % 3], w_bf16, We, be, t_bf16, exact)
+    h, r = L.tsae_forward(xs[i % 3], w_parts, be, t_bf16, exact)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -28,7 +28,7 @@ k0.record(); k1.record()
 L.check(L.load().qsae_set_encode_kernel_events(k0.cuda_event, k1.cuda_event))
 e0.record()
 for i in range(iters):
-    h, r = L.tsae_forward(xs[i % 3], w_bf16, We, be, t_bf16, exact)
+    h, r = L.tsae_forward(xs[i % 3], w_parts, be, t_bf16, exact)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / iters

@@ -518,7 +518,7 @@ def test_dense_encoder_tma_store_epilogue(cuda_device, B, H, D):
     wd = (0.4824 * rng.standard_normal((D, H))).astype(np.float32)
     We, be, x = (T(inp[k], cuda_device) for k in ("We", "be", "x"))
     t_bf16, _ = L.pack_ternary(T(wd, cuda_device))
-    h, recon = L.tsae_forward(x, L.cast_bf16(We), None, be, t_bf16, exact=False)
+    h, recon = L.tsae_forward(x, (L.cast_bf16(We),), be, t_bf16, exact=False)
     torch.cuda.synchronize()
     h_ref, r_ref = O.tsae_forward(inp["x"], inp["We"], inp["be"], wd)
     assert_vals_close(h.cpu().numpy(), h_ref)
@@ -590,7 +590,7 @@ def test_tsae_full_size_properties(cuda_device):
     Wd = 0.4824 * torch.randn((D, H), device=cuda_device, generator=g)
     x = torch.randn((B, D), device=cuda_device, generator=g).bfloat16().float()
     t_bf16, _ = L.pack_ternary(Wd)
-    h, recon = L.tsae_forward(x, L.cast_bf16(We), None, be, t_bf16, exact=False)
+    h, recon = L.tsae_forward(x, (L.cast_bf16(We),), be, t_bf16, exact=False)
     rows = torch.tensor([0, 1, 127, 128, 2047, 4095], dtype=torch.int32, device=cuda_device)
     z = L.encode_dense(x, We, be, L.ACT_RELU, rows=rows)
     assert_vals_close(h[rows.long()].cpu().numpy(), z.cpu().numpy())
@@ -669,10 +669,10 @@ def test_cluster_variants_are_bit_identical(cuda_device, monkeypatch, mcast):
     assert_topk_matches(vals.cpu().numpy(), idx.cpu().numpy(), O.encode_pre(x, W, b), k)
     wd = (0.4824 * np.random.default_rng(1).standard_normal((D, H))).astype(np.float32)
     t_bf16, _ = L.pack_ternary(T(wd, cuda_device))
-    h, recon = L.tsae_forward(dx, wb, None, db, t_bf16, exact=False)
+    h, recon = L.tsae_forward(dx, (wb,), db, t_bf16, exact=False)
     monkeypatch.setenv("QSAE_ENCODE_CLUSTER", "0")
     v0, i0, _ = L.encode_topk(dx, wb, None, db, k, sample=L.prepare_sample(wb, db))
-    h0, r0 = L.tsae_forward(dx, wb, None, db, t_bf16, exact=False)
+    h0, r0 = L.tsae_forward(dx, (wb,), db, t_bf16, exact=False)
     assert torch.equal(vals, v0) and torch.equal(idx, i0) and torch.equal(h, h0) and torch.equal(recon, r0)
 
 
@@ -735,3 +735,25 @@ def test_decoder_gemm_pair_variant_is_bit_identical(cuda_device, monkeypatch, B,
     monkeypatch.setenv("QSAE_DECODE_PAIR", "0")
     assert torch.equal(one, L.decode_dense(hi, None, tb)) and torch.equal(two, L.decode_dense(hi, lo, tb))
     assert_recon_close(two.cpu().numpy(), (a.astype(np.float64) @ t.T.astype(np.float64)).astype(np.float32))
+
+
+@pytest.mark.parametrize("B,H,D", [(24, 4096, 512), (300, 8192, 512), (130, 1000, 72), (512, 32768, 512)])
+def test_exact_dense_encoder_split_passes(cuda_device, B, H, D):
+    """fp32-accurate dense encoder on the tensor cores (3 x 3 bf16 operand split, three accumulating
+    launches; single-CTA variant for small shapes, cta_group::2 pairs for D = 512 and B > 128):
+    arbitrary fp32 x and W, h within 1e-5 * max(1, |h|) of the fp64 value; split parts sum exactly."""
+    x, W, b = _enc_case(B, H, D, seed=B + D, bf16=False)
+    rng = np.random.default_rng(9)
+    wd = (0.4824 * rng.standard_normal((D, H))).astype(np.float32)
+    dW = T(W, cuda_device)
+    parts = L.split_bf16x3(dW)
+    total = parts[0].double() + parts[1].double() + parts[2].double()
+    assert torch.equal(total.float(), dW) and torch.equal(total, dW.double())
+    t_bf16, _ = L.pack_ternary(T(wd, cuda_device))
+    h, recon = L.tsae_forward(T(x, cuda_device), parts, T(b, cuda_device), t_bf16, exact=True)
+    h64 = np.maximum(x.astype(np.float64) @ W.astype(np.float64).T + b, 0)
+    got = h.cpu().numpy()
+    assert np.all(np.abs(got - h64) <= 1e-5 * np.maximum(1.0, np.abs(h64)))
+    # tighter: the split passes are as good as an fp32 matmul (products exact, fp32 accumulation)
+    assert np.max(np.abs(got - h64)) <= 4e-6 * max(1.0, np.max(np.abs(h64)))
+    assert_recon_close(recon.cpu().numpy(), (h64 @ O.ternarize(wd).T.astype(np.float64)).astype(np.float32))
