@@ -502,7 +502,7 @@ __device__ __forceinline__ void small_row(const SelectLaunch& p, int row, int ks
 
 // rows == nullptr: one warp per row of the batch; otherwise a persistent grid over rows[0, *count)
 template <int R>
-__global__ void __launch_bounds__(kSmallWarps * 32)
+__global__ void __launch_bounds__(kSmallWarps * 32, R <= 16 ? 8 : 1)
 select_small_kernel(SelectLaunch p, int ksort, const int* count, const int32_t* rows, int* ovf_count,
                     int32_t* ovf_rows) {
   __shared__ uint64_t stage_all[kSmallWarps][32 * R];
