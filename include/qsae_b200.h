@@ -95,9 +95,17 @@ int qsae_transpose_f32(const float* src, int R, int C, float* dst, void* stream)
  * exact = 1: the bf16 pass selects k+QSAE_RESCORE_MARGIN candidates per row, which are
  *            re-scored in fp32 from x_f32 / w_f32 and re-selected; flags[b] == 1 marks a row
  *            whose selection could not be certified against bf16 rounding.
- * Limits: D % 8 == 0, 8 <= D <= 512, 1 <= k <= QSAE_MAX_K, k <= H.
+ * Limits: D % 8 == 0, 8 <= D <= 512, 1 <= k <= QSAE_MAX_K_LARGE, k <= H.
+ * k <= QSAE_MAX_K runs on the warp-level selection kernels (the b_sae / baseline defaults: 65 and 32
+ * at H = 32768). Larger k -- the reference default k = int(0.002 H) = 2097 at H = 2^20, or 262 per
+ * shard of an 8-way dictionary split (sae/binary.py:94) -- takes the block-level path: ordered top-m
+ * of the sampled rows (m <= QSAE_MAX_K) as the row threshold, a threshold-only sweep (no in-kernel cut),
+ * a block-per-row radix select over the ~m H / n_sample survivors, and an exact dense recomputation of
+ * any row whose survivor count check fails. Without a usable sample the call falls back to dense
+ * pre-activations in row chunks + a dense radix select (small dictionaries only; not a throughput path).
  * ------------------------------------------------------------------------------------- */
 #define QSAE_MAX_K 224
+#define QSAE_MAX_K_LARGE 4096
 #define QSAE_RESCORE_MARGIN 16
 
 /* n_sample: rows of the sampled dictionary that will be passed to qsae_encode_topk (0 = none) */
@@ -289,7 +297,7 @@ int qsae_pack_candidates(const float* vals, const int32_t* idx, size_t n, void* 
 
 int qsae_merge_candidates_workspace_bytes(int B, size_t* bytes);
 /* cand_all: [n_shards][B][k_in] entries, shard-local indices; entry (s, b, j) stands for the global
- * latent s * shard_latents + index. out_*: [B, k_out], k_out <= n_shards * k_in, k_out <= QSAE_MAX_K. */
+ * latent s * shard_latents + index. out_*: [B, k_out], k_out <= n_shards * k_in, k_out <= QSAE_MAX_K_LARGE. */
 int qsae_merge_candidates(const void* cand_all, int n_shards, int B, int k_in, int shard_latents, int k_out,
                           float* out_vals, int32_t* out_idx, void* workspace, size_t workspace_bytes,
                           void* stream);

@@ -15,6 +15,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libqsae_b200.so"
 
 QSAE_MAX_K = 224
+QSAE_MAX_K_LARGE = 4096
 QSAE_RESCORE_MARGIN = 16
 ACT_NONE, ACT_RELU = 0, 1
 

@@ -11,7 +11,9 @@ constexpr int kEncBN = 256;        // latents per accumulator tile
 constexpr int kCandCapMax = 1024;  // largest per-(row, sub-stream) survivor buffer
 constexpr int kDenseCap = 256;     // survivor buffer of the dense top-k kernel
 constexpr int kMaxSplits = 8;      // max CTAs sharing one row block along the latent axis
-constexpr int kMaxK = 224;         // == QSAE_MAX_K
+constexpr int kMaxK = 224;         // == QSAE_MAX_K: largest k of the warp-level selection paths
+constexpr int kMaxKLarge = 4096;   // == QSAE_MAX_K_LARGE: largest k of the block-level (radix select) paths
+constexpr size_t kSelectSmemBudget = 200 * 1024;   // shared memory of the block-per-row select kernels
 constexpr int kTopM = 16;          // register-resident top list of the sample pre-pass (mode 5)
 
 struct EncodeLaunch {
@@ -107,6 +109,12 @@ const char* rescue_rows_launch(const RescueLaunch& p, int num_sms, cudaStream_t 
 const char* sample_rows_launch(const uint16_t* w_bf16, const float* bias, int H, int D, int n_sample,
                                uint16_t* w_sample, float* b_sample, cudaStream_t stream);
 const char* select_topk_launch(const SelectLaunch& p, cudaStream_t stream);
+// ordered top-k of every row of a dense [R, H] matrix, any k <= kMaxKLarge (block-level radix select)
+const char* select_dense_launch(const float* z, int R, int H, int k, int num_sms, float* out_vals, int32_t* out_idx,
+                                cudaStream_t stream);
+// large-k counterpart of rescue_rows_launch (k_out <= kMaxKLarge); scratch: rescue_large_scratch_bytes
+size_t rescue_large_scratch_bytes(int H, int num_sms);
+const char* rescue_large_launch(const RescueLaunch& p, void* scratch, int num_sms, cudaStream_t stream);
 // warp-per-row merge for small survivor counts (prior mode / gathered shard candidates). tier = keys per
 // lane (8 / 16 / 32: rows with up to 256 / 512 / 1024 survivors); rows that do not fit are appended to
 // ovf_rows / ovf_count for the next tier. rows == nullptr: every row of the batch; else the device-side list

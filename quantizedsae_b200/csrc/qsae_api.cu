@@ -119,7 +119,7 @@ int plan_encode(int B, int H, int D, int k, int exact, int n_sample, EncodePlan*
     return fail(QSAE_ERR_INVALID_ARGUMENT, "D must be a multiple of 8 in [8, 512], got %d", D);
   if (k < 1) return fail(QSAE_ERR_INVALID_ARGUMENT, "k must be >= 1, got %d", k);
   if (k > H) return fail(QSAE_ERR_K_OUT_OF_RANGE, "selected index k out of range (k=%d > H=%d)", k, H);
-  if (k > kMaxK) return fail(QSAE_ERR_INVALID_ARGUMENT, "k=%d exceeds QSAE_MAX_K=%d", k, kMaxK);
+  if (k > kMaxK) return fail(QSAE_ERR_INVALID_ARGUMENT, "k=%d exceeds QSAE_MAX_K=%d on the warp-level path", k, kMaxK);
   int k_sel = k;
   if (exact) {
     k_sel = k + QSAE_RESCORE_MARGIN;
@@ -163,6 +163,185 @@ void fill_encode_launch(EncodeLaunch* el, const StagePlan& sp, int B, int D, int
   el->cand = ws + sp.cand_off;
   el->cand_cnt = reinterpret_cast<int*>(ws + sp.cnt_off);
   el->cand_thr = reinterpret_cast<float*>(ws + sp.thr_off);
+}
+
+
+int next_pow2_host(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// ---- k > QSAE_MAX_K (e.g. the reference default k = int(0.002 H) = 2097 at H = 2^20, sae/binary.py:94) -----------
+// Prior path: top-m over the sampled dictionary rows (class-bound sweep + block merge, m <= QSAE_MAX_K) gives the
+// row's threshold; the full sweep keeps everything above it (threshold-only mode, no in-kernel cut); the block-level
+// merge radix-selects k_sel of the ~m H / n_sample survivors; rows whose count check fails (or whose lists filled up)
+// are recomputed exactly. Dense path (no usable sample): dense pre-activations in row chunks + dense radix select.
+struct LargePlan {
+  int k_sel, m, chunk_rows;
+  bool use_prior;
+  StagePlan main, pre, dense;
+  size_t x_off, counters_off, rescue_rows_off, pre_vals_off, pre_idx_off, scratch_off, z_off, total;
+};
+
+int plan_encode_large(int B, int H, int D, int k, int exact, int n_sample, LargePlan* lp) {
+  if (B <= 0 || H <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "B and H must be positive (B=%d H=%d)", B, H);
+  if (D < 8 || D > 512 || (D % 8) != 0)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "D must be a multiple of 8 in [8, 512], got %d", D);
+  if (k > H) return fail(QSAE_ERR_K_OUT_OF_RANGE, "selected index k out of range (k=%d > H=%d)", k, H);
+  if (k > kMaxKLarge) return fail(QSAE_ERR_INVALID_ARGUMENT, "k=%d exceeds QSAE_MAX_K_LARGE=%d", k, kMaxKLarge);
+  // re-scoring margin: the density of pre-activations around the k-th largest grows with k, so the number of
+  // candidates inside the bf16 rounding band does too (k / 4 covers 4 x the band on Gaussian-like rows)
+  int k_sel = exact ? k + (k / 4 > QSAE_RESCORE_MARGIN ? k / 4 : QSAE_RESCORE_MARGIN) : k;
+  if (k_sel > H) k_sel = H;
+  lp->k_sel = k_sel;
+  lp->use_prior = false;
+  lp->m = 0;
+  lp->chunk_rows = 0;
+  const int ksort = next_pow2_host(k_sel);
+  lp->x_off = 0;
+  size_t off = align_up(static_cast<size_t>(B) * D * 2, 1024);
+  if (n_sample >= 256 && H >= 8 * static_cast<long long>(n_sample)) {
+    const double r = static_cast<double>(n_sample) / H;
+    const int m = choose_prior_rank(k_sel, r);
+    if (m <= kMaxK && m <= n_sample) {
+      plan_stage(B, H, 0, kStagePriorMain, true, off, &lp->main);
+      // expected survivors ~ m / r per row; buffers for twice that, bounded by the merge kernel's shared memory
+      const long long want = static_cast<long long>(2.0 * m / r) + 64;
+      int cap = next_pow2_host(static_cast<int>((want + lp->main.nsub - 1) / lp->main.nsub));
+      if (cap < 256) cap = 256;
+      while (cap > 256 && (static_cast<size_t>(lp->main.nsub) * cap + ksort) * 8 > kSelectSmemBudget) cap >>= 1;
+      if ((static_cast<size_t>(lp->main.nsub) * cap + ksort) * 8 <= kSelectSmemBudget &&
+          static_cast<long long>(lp->main.nsub) * (cap - 32) >= k_sel) {
+        lp->use_prior = true;
+        lp->m = m;
+        lp->main.cap = cap;
+        lp->main.cnt_off = lp->main.cand_off + static_cast<size_t>(B) * lp->main.nsub * cap * 8;
+        lp->main.thr_off = lp->main.cnt_off + static_cast<size_t>(B) * lp->main.nsub * 4;
+        lp->main.end = align_up(lp->main.thr_off + static_cast<size_t>(B) * lp->main.nsub * 4, 256);
+      }
+    }
+  }
+  if (lp->use_prior) {
+    off = lp->main.end;
+    lp->counters_off = off; off += 256;
+    lp->rescue_rows_off = off; off = align_up(off + static_cast<size_t>(B) * 4, 256);
+    lp->pre_vals_off = off; off = align_up(off + static_cast<size_t>(B) * lp->m * 4, 256);
+    lp->pre_idx_off = off; off = align_up(off + static_cast<size_t>(B) * lp->m * 4, 256);
+    lp->scratch_off = off; off = align_up(off + rescue_large_scratch_bytes(H, num_sms()), 256);
+    plan_stage(B, n_sample, lp->m, kStageClassBound, false, off, &lp->pre);
+    off = lp->pre.end;
+  } else {
+    // dense pre-activations in row chunks of at most ~1 GB
+    long long rows = (1ll << 30) / (static_cast<long long>(H) * 4);
+    rows = rows / kEncBM * kEncBM;
+    if (rows < kEncBM) rows = kEncBM;
+    if (rows > B) rows = B;
+    lp->chunk_rows = static_cast<int>(rows);
+    lp->z_off = off; off = align_up(off + static_cast<size_t>(rows) * H * 4, 256);
+    plan_stage(static_cast<int>(rows), H, 1, kStageClassBound, false, off, &lp->dense);
+    off = lp->dense.end;
+  }
+  lp->total = off;
+  return QSAE_OK;
+}
+
+int encode_topk_large(const float* x_f32, const uint16_t* w_bf16, const float* w_f32, const float* b_enc,
+                      const uint16_t* w_sample, const float* b_sample, int n_sample, int B, int H, int D, int k, int act,
+                      int exact, float* out_vals, int32_t* out_idx, int32_t* out_flags, void* workspace,
+                      size_t workspace_bytes, cudaStream_t st) {
+  LargePlan lp;
+  int rc = plan_encode_large(B, H, D, k, exact, n_sample, &lp);
+  if (rc != QSAE_OK) return rc;
+  if (workspace_bytes < lp.total)
+    return fail(QSAE_ERR_WORKSPACE_TOO_SMALL, "encode_topk: workspace %zu < %zu bytes", workspace_bytes, lp.total);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  uint16_t* x_bf16 = reinterpret_cast<uint16_t*>(ws + lp.x_off);
+
+  if (!lp.use_prior) {
+    // ---- dense path
+    if (!exact) {
+      rc = launch_status("cast x", cast_bf16_launch(x_f32, x_bf16, static_cast<size_t>(B) * D, st));
+      if (rc != QSAE_OK) return rc;
+    }
+    float* z = reinterpret_cast<float*>(ws + lp.z_off);
+    for (int r0 = 0; r0 < B; r0 += lp.chunk_rows) {
+      const int rows = (B - r0 < lp.chunk_rows) ? (B - r0) : lp.chunk_rows;
+      if (exact) {
+        rc = launch_status("encode_dense", encode_dense_launch(x_f32 + static_cast<size_t>(r0) * D, nullptr, rows, w_f32,
+                                                               b_enc, H, D, act, z, st));
+      } else {
+        EncodeLaunch el;
+        fill_encode_launch(&el, lp.dense, rows, D, act, b_enc, ws);   // the chunk's split plan, possibly fewer rows
+        el.debug_z = z;
+        rc = launch_status("encode_topk kernel (dense dump)",
+                           encode_topk_launch(x_bf16 + static_cast<size_t>(r0) * D, w_bf16, el, st));
+      }
+      if (rc != QSAE_OK) return rc;
+      rc = launch_status("select_dense", select_dense_launch(z, rows, H, k, num_sms(), out_vals + static_cast<size_t>(r0) * k,
+                                                             out_idx + static_cast<size_t>(r0) * k, st));
+      if (rc != QSAE_OK) return rc;
+    }
+    if (out_flags != nullptr) {
+      cudaError_t ce = cudaMemsetAsync(out_flags, 0, static_cast<size_t>(B) * 4, st);
+      if (ce != cudaSuccess) return fail(QSAE_ERR_CUDA, "encode_topk: %s", cudaGetErrorString(ce));
+    }
+    return QSAE_OK;
+  }
+
+  // ---- prior path
+  int* counters = reinterpret_cast<int*>(ws + lp.counters_off);   // [0] rescue rows, [1] sweep overflow flag
+  int32_t* rescue_rows = reinterpret_cast<int32_t*>(ws + lp.rescue_rows_off);
+  float* pre_vals = reinterpret_cast<float*>(ws + lp.pre_vals_off);
+  int32_t* pre_idx = reinterpret_cast<int32_t*>(ws + lp.pre_idx_off);
+  cudaError_t ce = cudaMemsetAsync(counters, 0, 4 * sizeof(int), st);
+  if (ce != cudaSuccess) return fail(QSAE_ERR_CUDA, "encode_topk: %s", cudaGetErrorString(ce));
+  rc = launch_status("cast x", cast_bf16_launch(x_f32, x_bf16, static_cast<size_t>(B) * D, st));
+  if (rc != QSAE_OK) return rc;
+  // 1. ordered top-m over the sampled rows (tensor-core values: the same arithmetic as the full sweep)
+  {
+    EncodeLaunch pe;
+    fill_encode_launch(&pe, lp.pre, B, D, act, b_sample, ws);
+    rc = launch_status("encode_topk kernel (sample top-m)", encode_topk_launch(x_bf16, w_sample, pe, st));
+    if (rc != QSAE_OK) return rc;
+    SelectLaunch sl;
+    memset(&sl, 0, sizeof(sl));
+    sl.B = B; sl.H = n_sample; sl.D = D; sl.k_sel = lp.m; sl.k_out = lp.m; sl.nsub = lp.pre.nsub; sl.cap = lp.pre.cap;
+    sl.act = act;
+    sl.cand = pe.cand; sl.cand_cnt = pe.cand_cnt; sl.cand_thr = pe.cand_thr;
+    sl.out_vals = pre_vals; sl.out_idx = pre_idx;
+    rc = launch_status("select_topk kernel (sample top-m)", select_topk_launch(sl, st));
+    if (rc != QSAE_OK) return rc;
+  }
+  // 2. full sweep, everything >= the row's m-th largest sample value
+  EncodeLaunch el;
+  fill_encode_launch(&el, lp.main, B, D, act, b_enc, ws);
+  el.k_sel = 0;
+  el.prior = pre_vals + (lp.m - 1); el.prior_stride = lp.m;
+  el.overflow = counters + 1;
+  if (g_enc_ev_start) cudaEventRecord(g_enc_ev_start, st);
+  rc = launch_status("encode_topk kernel", encode_topk_launch(x_bf16, w_bf16, el, st));
+  if (g_enc_ev_stop) cudaEventRecord(g_enc_ev_stop, st);
+  if (rc != QSAE_OK) return rc;
+  // 3. block-per-row merge (radix select), count check
+  SelectLaunch sl;
+  memset(&sl, 0, sizeof(sl));
+  sl.B = B; sl.H = H; sl.D = D; sl.k_sel = lp.k_sel; sl.k_out = k; sl.nsub = lp.main.nsub; sl.cap = lp.main.cap;
+  sl.act = act; sl.exact = exact;
+  sl.cand = el.cand; sl.cand_cnt = el.cand_cnt; sl.cand_thr = el.cand_thr;
+  sl.x_f32 = x_f32; sl.w_f32 = w_f32; sl.bias = b_enc;
+  sl.out_vals = out_vals; sl.out_idx = out_idx; sl.out_flags = out_flags;
+  sl.rescue_count = counters; sl.rescue_rows = rescue_rows;
+  rc = launch_status("select_topk kernel", select_topk_launch(sl, st));
+  if (rc != QSAE_OK) return rc;
+  // 4. failed rows: exact recomputation
+  RescueLaunch rl;
+  memset(&rl, 0, sizeof(rl));
+  rl.B = B; rl.H = H; rl.D = D; rl.k_sel = lp.k_sel; rl.k_out = k; rl.act = act; rl.exact = exact;
+  rl.x_bf16 = x_bf16; rl.w_bf16 = w_bf16; rl.x_f32 = x_f32; rl.w_f32 = w_f32; rl.bias = b_enc;
+  rl.rescue_count = counters; rl.rescue_rows = rescue_rows;
+  rl.out_vals = out_vals; rl.out_idx = out_idx; rl.out_flags = out_flags;
+  return launch_status("rescue kernel (large k)", rescue_large_launch(rl, ws + lp.scratch_off, num_sms(), st));
 }
 
 }  // namespace
@@ -222,10 +401,19 @@ int qsae_encode_topk_workspace_bytes(int B, int H, int D, int k, int n_sample, s
   size_t need = 0;
   for (int exact = 0; exact < 2; ++exact) {
     for (int pass = 0; pass < 2; ++pass) {  // with and without the sampled prior
-      EncodePlan pl;
-      int rc = plan_encode(B, H, D, k, exact, pass ? n_sample : 0, &pl);
-      if (rc != QSAE_OK) return rc;
-      if (pl.total > need) need = pl.total;
+      size_t total = 0;
+      if (k > kMaxK) {
+        LargePlan lp;
+        int rc = plan_encode_large(B, H, D, k, exact, pass ? n_sample : 0, &lp);
+        if (rc != QSAE_OK) return rc;
+        total = lp.total;
+      } else {
+        EncodePlan pl;
+        int rc = plan_encode(B, H, D, k, exact, pass ? n_sample : 0, &pl);
+        if (rc != QSAE_OK) return rc;
+        total = pl.total;
+      }
+      if (total > need) need = total;
     }
   }
   *bytes = need;
@@ -250,13 +438,16 @@ int qsae_encode_topk(const float* x_f32, const uint16_t* w_bf16, const float* w_
   if (act != QSAE_ACT_NONE && act != QSAE_ACT_RELU)
     return fail(QSAE_ERR_INVALID_ARGUMENT, "encode_topk: unknown activation %d", act);
   if (!w_sample || !b_sample) n_sample = 0;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0 || (reinterpret_cast<uintptr_t>(w_bf16) & 15) != 0)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "encode_topk: workspace must be 256-byte and w_bf16 16-byte aligned");
+  if (k > kMaxK && k <= H)
+    return encode_topk_large(x_f32, w_bf16, w_f32, b_enc, w_sample, b_sample, n_sample, B, H, D, k, act, exact, out_vals,
+                             out_idx, out_flags, workspace, workspace_bytes, S(stream));
   EncodePlan pl;
   int rc = plan_encode(B, H, D, k, exact, n_sample, &pl);
   if (rc != QSAE_OK) return rc;
   if (workspace_bytes < pl.total)
     return fail(QSAE_ERR_WORKSPACE_TOO_SMALL, "encode_topk: workspace %zu < %zu bytes", workspace_bytes, pl.total);
-  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0 || (reinterpret_cast<uintptr_t>(w_bf16) & 15) != 0)
-    return fail(QSAE_ERR_INVALID_ARGUMENT, "encode_topk: workspace must be 256-byte and w_bf16 16-byte aligned");
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   uint16_t* x_bf16 = reinterpret_cast<uint16_t*>(ws + pl.x_off);
   cudaStream_t st = S(stream);
@@ -741,7 +932,9 @@ int qsae_topk_dense(const float* z, int R, int H, int k, float* out_vals, int32_
   if (!z || !out_vals || !out_idx || !workspace) return fail(QSAE_ERR_INVALID_ARGUMENT, "topk_dense: null pointer");
   if (k < 1) return fail(QSAE_ERR_INVALID_ARGUMENT, "k must be >= 1, got %d", k);
   if (k > H) return fail(QSAE_ERR_K_OUT_OF_RANGE, "selected index k out of range (k=%d > H=%d)", k, H);
-  if (k > kMaxK) return fail(QSAE_ERR_INVALID_ARGUMENT, "k=%d exceeds QSAE_MAX_K=%d", k, kMaxK);
+  if (k > kMaxKLarge) return fail(QSAE_ERR_INVALID_ARGUMENT, "k=%d exceeds QSAE_MAX_K_LARGE=%d", k, kMaxKLarge);
+  if (k > kMaxK)   // block-level radix select straight from the dense rows (no workspace)
+    return launch_status("select_dense", select_dense_launch(z, R, H, k, num_sms(), out_vals, out_idx, S(stream)));
   size_t need = 0;
   qsae_topk_dense_workspace_bytes(R, H, k, &need);
   if (workspace_bytes < need) return fail(QSAE_ERR_WORKSPACE_TOO_SMALL, "topk_dense: workspace %zu < %zu", workspace_bytes, need);
@@ -807,7 +1000,7 @@ int qsae_merge_candidates(const void* cand_all, int n_shards, int B, int k_in, i
   if (!cand_all || !out_vals || !out_idx || !workspace) return fail(QSAE_ERR_INVALID_ARGUMENT, "merge_candidates: null pointer");
   if (n_shards < 1 || n_shards > 32 || k_in < 1 || k_out < 1 || shard_latents < 1)
     return fail(QSAE_ERR_INVALID_ARGUMENT, "merge_candidates: need 1 <= n_shards <= 32, k_in, k_out >= 1");
-  if (k_out > kMaxK) return fail(QSAE_ERR_INVALID_ARGUMENT, "k=%d exceeds QSAE_MAX_K=%d", k_out, kMaxK);
+  if (k_out > kMaxKLarge) return fail(QSAE_ERR_INVALID_ARGUMENT, "k=%d exceeds QSAE_MAX_K_LARGE=%d", k_out, kMaxKLarge);
   if (static_cast<long long>(n_shards) * k_in < k_out)
     return fail(QSAE_ERR_K_OUT_OF_RANGE, "selected index k out of range (k=%d > %d candidates)", k_out, n_shards * k_in);
   size_t need = 0;
@@ -826,7 +1019,7 @@ int qsae_merge_candidates(const void* cand_all, int n_shards, int B, int k_in, i
   sl.out_vals = out_vals; sl.out_idx = out_idx;
   // every row has exactly n_shards * k_in candidates: pick the tier that holds them
   const long long n_cand = static_cast<long long>(n_shards) * k_in;
-  if (n_cand > 1024) return launch_status("select_topk kernel", select_topk_launch(sl, st));
+  if (n_cand > 1024 || k_out > kMaxK) return launch_status("select_topk kernel", select_topk_launch(sl, st));
   const int tier = n_cand <= 256 ? 8 : (n_cand <= 512 ? 16 : 32);
   return launch_status("select_small kernel", select_small_launch(sl, tier, nullptr, nullptr, num_sms(), counters + 1, ovf_rows, st));
 }

@@ -29,16 +29,19 @@ __device__ __forceinline__ void atomic_min_float_key(unsigned* addr, float v) { 
 __device__ __forceinline__ void atomic_max_float_key(unsigned* addr, float v) { atomicMax(addr, float_to_key(v)); }
 
 // One block per row. Warps gather the row's sub-streams in parallel (batched, coalesced loads,
-// filtered by the row-level bound), warp 0 picks the k_sel largest composite keys, all warps
-// re-score them in fp32 when asked to, then the block sorts and emits.
+// filtered by the row-level bound), the block radix-selects the k_sel largest composite keys, all
+// warps re-score them in fp32 when asked to, then the block sorts and emits. Any k_sel that fits
 // shared memory: n_max gathered keys + ksort selected keys.
+template <int THREADS>
 __device__ __forceinline__ void select_row_block(const SelectLaunch& p, int row, int n_max, int ksort,
                                                  uint8_t* sel_smem) {
-  __shared__ int s_n, s_out;
+  __shared__ int s_n, s_out, s_ovf;
+  __shared__ int s_hist[256];
+  __shared__ int s_ctl[4];
   __shared__ unsigned s_worst_key, s_dev_key;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int nwarps = kSelThreads / 32;
+  constexpr int nwarps = THREADS / 32;
   const unsigned full = 0xffffffffu;
   const unsigned lt_mask = (1u << lane) - 1u;
   uint64_t* keys = reinterpret_cast<uint64_t*>(sel_smem);
@@ -46,6 +49,8 @@ __device__ __forceinline__ void select_row_block(const SelectLaunch& p, int row,
 
   if (threadIdx.x == 0) {
     s_n = 0;
+    s_out = 0;
+    s_ovf = 0;
     s_worst_key = 0xFFFFFFFFu;
     s_dev_key = float_to_key(0.f);
   }
@@ -62,6 +67,8 @@ __device__ __forceinline__ void select_row_block(const SelectLaunch& p, int row,
   for (int s = warp; s < p.nsub; s += nwarps) {
     const size_t slot = list_slot(p, row, s);
     const int c = list_count(p, slot);
+    // a threshold-only sweep (no in-kernel cut) stops collecting when a list fills up
+    if (lane == 0 && p.cand_cnt != nullptr && p.cand_cnt[slot] > p.cap - 32) s_ovf = 1;
     const uint2* src = cand + slot * p.cap;
     const uint32_t col_add = static_cast<uint32_t>(s) * static_cast<uint32_t>(p.sub_col_offset);
     for (int base = 0; base < c; base += 32 * BATCH) {
@@ -90,8 +97,9 @@ __device__ __forceinline__ void select_row_block(const SelectLaunch& p, int row,
   const int k_sel = min(p.k_sel, n);
 
   // ---- prior mode: the threshold was only probably valid. Fewer than k_sel survivors means it
-  //      was too high for this row: hand the row to the exact rescue kernel.
-  if (p.rescue_count != nullptr && n < p.k_sel) {
+  //      was too high for this row, a full list that it was far too low: hand the row to the exact
+  //      rescue kernel.
+  if (p.rescue_count != nullptr && (n < p.k_sel || s_ovf != 0)) {
     if (threadIdx.x == 0) {
       p.rescue_rows[atomicAdd(p.rescue_count, 1)] = row;
       if (p.out_flags != nullptr) p.out_flags[row] = 2;
@@ -99,34 +107,24 @@ __device__ __forceinline__ void select_row_block(const SelectLaunch& p, int row,
     return;
   }
 
-  // ---- warp 0: the k_sel largest composite keys
-  if (warp == 0) {
-    uint64_t T = 0ull;
-    if (n > k_sel) {
-#pragma unroll 1
-      for (int bit = 63; bit >= 0; --bit) {
-        const uint64_t probe = T | (1ull << bit);
-        int c = 0;
-        for (int e = lane; e < n; e += 32) c += (keys[e] >= probe) ? 1 : 0;
-        c = __reduce_add_sync(full, c);
-        if (c >= k_sel) T = probe;
-        if (c == k_sel) break;
-      }
+  // ---- the k_sel largest composite keys -> sel[0, out)
+  const uint64_t T = block_radix_select([&](int e) { return keys[e]; }, n, k_sel, s_hist, s_ctl);
+  for (int base = 0; base < n; base += THREADS) {
+    const int e = base + threadIdx.x;
+    const uint64_t key = (e < n) ? keys[e] : 0ull;
+    const bool keep = (e < n) && (key >= T);
+    const unsigned b = __ballot_sync(full, keep);
+    if (b != 0u) {
+      int pos = 0;
+      if (lane == 0) pos = atomicAdd(&s_out, __popc(b));
+      pos = __shfl_sync(full, pos, 0) + __popc(b & lt_mask);
+      if (keep && pos < ksort) sel[pos] = key;
     }
-    int out = 0;
-    for (int base = 0; base < n; base += 32) {
-      const int e = base + lane;
-      const uint64_t key = (e < n) ? keys[e] : 0ull;
-      const bool keep = (e < n) && (key >= T);
-      const unsigned b = __ballot_sync(full, keep);
-      if (keep) sel[out + __popc(b & lt_mask)] = key;
-      out += __popc(b);
-    }
-    for (int e = out + lane; e < ksort; e += 32) sel[e] = 0ull;
-    if (lane == 0) s_out = out;
   }
   __syncthreads();
-  const int out = s_out;
+  const int out = min(s_out, ksort);
+  for (int e = out + threadIdx.x; e < ksort; e += THREADS) sel[e] = 0ull;
+  __syncthreads();
 
   // ---- optional exact fp32 re-scoring, candidates spread over the warps
   if (p.exact) {
@@ -183,31 +181,16 @@ __device__ __forceinline__ void select_row_block(const SelectLaunch& p, int row,
   }
   __syncthreads();
 
-  // ---- block-wide bitonic sort of sel[0, ksort) descending
-  for (int size = 2; size <= ksort; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = threadIdx.x; t < (ksort >> 1); t += kSelThreads) {
-        const int pos = ((t / stride) * (stride << 1)) + (t % stride);
-        const int partner = pos + stride;
-        const bool desc = (pos & size) == 0;
-        const uint64_t a = sel[pos], b = sel[partner];
-        if ((a < b) == desc) {
-          sel[pos] = b;
-          sel[partner] = a;
-        }
-      }
-      __syncthreads();
-    }
-  }
+  block_bitonic_desc(sel, ksort);
 
   // ---- emit
-  for (int j = threadIdx.x; j < p.k_out; j += kSelThreads) {
+  for (int j = threadIdx.x; j < p.k_out; j += THREADS) {
     const uint64_t key = sel[j];
     const bool valid = j < out;
     p.out_vals[static_cast<size_t>(row) * p.k_out + j] = valid ? sort_key_value(key) : 0.f;
     p.out_idx[static_cast<size_t>(row) * p.k_out + j] = valid ? static_cast<int32_t>(sort_key_col(key)) : -1;
   }
-  if (p.out_flags != nullptr && threadIdx.x == 0) {
+  if (threadIdx.x == 0) {
     int flag = 0;
     if (p.exact && n > k_sel && p.k_out <= out) {
       // every dropped candidate scored <= worst_bf16 on the tensor cores; the selection is
@@ -218,14 +201,17 @@ __device__ __forceinline__ void select_row_block(const SelectLaunch& p, int row,
       const float kth = sort_key_value(sel[p.k_out - 1]);
       if (!(worst_bf16 + 4.f * max_dev < kth)) flag = 1;
     }
-    p.out_flags[row] = flag;
+    // an uncertified row is recomputed exactly when a rescue pass follows (it then clears the flag)
+    if (flag != 0 && p.rescue_count != nullptr) p.rescue_rows[atomicAdd(p.rescue_count, 1)] = row;
+    if (p.out_flags != nullptr) p.out_flags[row] = flag;
   }
 }
 
-__global__ void __launch_bounds__(kSelThreads)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
 select_topk_kernel(SelectLaunch p, int n_max, int ksort) {
   extern __shared__ __align__(16) uint8_t sel_smem[];
-  select_row_block(p, blockIdx.x, n_max, ksort, sel_smem);
+  select_row_block<THREADS>(p, blockIdx.x, n_max, ksort, sel_smem);
 }
 
 // the same merge for an explicit (device-side) list of rows: persistent small grid
@@ -234,8 +220,135 @@ select_topk_list_kernel(SelectLaunch p, int n_max, int ksort, const int* count, 
   extern __shared__ __align__(16) uint8_t sel_smem[];
   const int n = min(*count, p.B);
   for (int li = blockIdx.x; li < n; li += gridDim.x) {
-    select_row_block(p, rows[li], n_max, ksort, sel_smem);
+    select_row_block<kSelThreads>(p, rows[li], n_max, ksort, sel_smem);
     __syncthreads();
+  }
+}
+
+// Top-k of one dense row z[0, H) (any k): radix select on the composite keys built on the fly, then
+// sort in shared memory. Leaves the ordered keys in sel[0, ksort) (zero padded); returns their count.
+template <int THREADS>
+__device__ __forceinline__ int dense_row_topk(const float* z, int H, int k, int ksort, uint64_t* sel, int* hist,
+                                              int* ctl, int* s_out) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  if (threadIdx.x == 0) *s_out = 0;
+  const uint64_t T = block_radix_select([&](int e) { return make_sort_key(z[e], static_cast<uint32_t>(e)); }, H, k,
+                                        hist, ctl);
+  __syncthreads();
+  for (int base = 0; base < H; base += THREADS) {
+    const int e = base + threadIdx.x;
+    const uint64_t key = (e < H) ? make_sort_key(z[e], static_cast<uint32_t>(e)) : 0ull;
+    const bool keep = (e < H) && (key >= T);
+    const unsigned b = __ballot_sync(full, keep);
+    if (b != 0u) {
+      int pos = 0;
+      if (lane == 0) pos = atomicAdd(s_out, __popc(b));
+      pos = __shfl_sync(full, pos, 0) + __popc(b & lt_mask);
+      if (keep && pos < ksort) sel[pos] = key;
+    }
+  }
+  __syncthreads();
+  const int out = min(*s_out, ksort);
+  for (int e = out + threadIdx.x; e < ksort; e += THREADS) sel[e] = 0ull;
+  __syncthreads();
+  block_bitonic_desc(sel, ksort);
+  return out;
+}
+
+__device__ __forceinline__ void emit_sorted(const uint64_t* sel, int out, int row, int k_out, float* out_vals,
+                                            int32_t* out_idx) {
+  for (int j = threadIdx.x; j < k_out; j += blockDim.x) {
+    const uint64_t key = sel[j];
+    const bool valid = j < out;
+    out_vals[static_cast<size_t>(row) * k_out + j] = valid ? sort_key_value(key) : 0.f;
+    out_idx[static_cast<size_t>(row) * k_out + j] = valid ? static_cast<int32_t>(sort_key_col(key)) : -1;
+  }
+}
+
+constexpr int kLargeThreads = 1024;
+
+// dense [R, H] matrix -> ordered top-k per row, any k (block per row)
+__global__ void __launch_bounds__(kLargeThreads)
+select_dense_kernel(const float* __restrict__ z, int R, int H, int k, int ksort, float* out_vals, int32_t* out_idx) {
+  extern __shared__ __align__(16) uint8_t sel_smem[];
+  __shared__ int s_hist[256];
+  __shared__ int s_ctl[4];
+  __shared__ int s_out;
+  uint64_t* sel = reinterpret_cast<uint64_t*>(sel_smem);
+  for (int row = blockIdx.x; row < R; row += gridDim.x) {
+    const int out = dense_row_topk<kLargeThreads>(z + static_cast<size_t>(row) * H, H, k, ksort, sel, s_hist, s_ctl, &s_out);
+    emit_sorted(sel, out, row, k, out_vals, out_idx);
+    __syncthreads();
+  }
+}
+
+// Exact recomputation of listed rows for any k (the large-k counterpart of rescue.cu): dense
+// pre-activations of the row into this block's scratch line (CUDA cores, same per-lane FMA order and
+// shuffle tree as the fp32 re-scoring), then the dense-row top-k above.
+__global__ void __launch_bounds__(kLargeThreads)
+rescue_large_kernel(RescueLaunch p, float* scratch, int ksort) {
+  extern __shared__ __align__(16) uint8_t sel_smem[];
+  __shared__ float4 xs[128];
+  __shared__ int s_hist[256];
+  __shared__ int s_ctl[4];
+  __shared__ int s_out;
+  uint64_t* sel = reinterpret_cast<uint64_t*>(sel_smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+  const int D = p.D, H = p.H;
+  const int count = min(*p.rescue_count, p.B);
+  float* zrow = scratch + static_cast<size_t>(blockIdx.x) * H;
+  for (int li = blockIdx.x; li < count; li += gridDim.x) {
+    const int row = p.rescue_rows[li];
+    __syncthreads();
+    for (int q = threadIdx.x; q < 128; q += kLargeThreads) {
+      const int d = q * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (d < D) {
+        if (p.exact) {
+          v = *reinterpret_cast<const float4*>(p.x_f32 + static_cast<size_t>(row) * D + d);
+        } else {
+          const uint2 u = *reinterpret_cast<const uint2*>(p.x_bf16 + static_cast<size_t>(row) * D + d);
+          v = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u),
+                          __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
+        }
+      }
+      xs[q] = v;
+    }
+    __syncthreads();
+    float4 xr[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) xr[c] = xs[c * 32 + lane];
+    for (int h = warp; h < H; h += kLargeThreads / 32) {
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int d = c * 128 + lane * 4;
+        if (d < D) {
+          float4 w;
+          if (p.exact) {
+            w = __ldg(reinterpret_cast<const float4*>(p.w_f32 + static_cast<size_t>(h) * D + d));
+          } else {
+            const uint2 u = __ldg(reinterpret_cast<const uint2*>(p.w_bf16 + static_cast<size_t>(h) * D + d));
+            w = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u),
+                            __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
+          }
+          acc = fmaf(xr[c].x, w.x, acc); acc = fmaf(xr[c].y, w.y, acc);
+          acc = fmaf(xr[c].z, w.z, acc); acc = fmaf(xr[c].w, w.w, acc);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(full, acc, o);
+      float s = acc + __ldg(p.bias + h);
+      if (p.act == 1) s = fmaxf(s, 0.f);
+      if (lane == 0) zrow[h] = s;
+    }
+    __syncthreads();
+    const int out = dense_row_topk<kLargeThreads>(zrow, H, p.k_out, ksort, sel, s_hist, s_ctl, &s_out);
+    emit_sorted(sel, out, row, p.k_out, p.out_vals, p.out_idx);
+    if (p.out_flags != nullptr && threadIdx.x == 0) p.out_flags[row] = 0;  // exact by construction
   }
 }
 
@@ -381,7 +494,7 @@ __device__ __forceinline__ void sort_and_emit(const SelectLaunch& p, int row, co
       p.out_vals[static_cast<size_t>(row) * p.k_out + e] = valid ? sort_key_value(k[j]) : 0.f;
       p.out_idx[static_cast<size_t>(row) * p.k_out + e] = valid ? static_cast<int32_t>(sort_key_col(k[j])) : -1;
     }
-    if (p.out_flags != nullptr && e == p.k_out - 1) {
+    if (e == p.k_out - 1) {
       int flag = 0;
       if (p.exact && n > k_sel && p.k_out <= out) {
         // every dropped candidate scored <= worst_bf16 on the tensor cores; certified when even 4x the
@@ -389,7 +502,9 @@ __device__ __forceinline__ void sort_and_emit(const SelectLaunch& p, int row, co
         const float kth = sort_key_value(k[j]);
         if (!(worst_bf16 + 4.f * max_dev < kth)) flag = 1;
       }
-      p.out_flags[row] = flag;
+      // an uncertified row is recomputed exactly when a rescue pass follows (it then clears the flag)
+      if (flag != 0 && p.rescue_count != nullptr) p.rescue_rows[atomicAdd(p.rescue_count, 1)] = row;
+      if (p.out_flags != nullptr) p.out_flags[row] = flag;
     }
   }
 }
@@ -620,16 +735,63 @@ const char* select_topk_launch(const SelectLaunch& p, cudaStream_t stream) {
   const int ksort = next_pow2(p.k_sel < 2 ? 2 : p.k_sel);
   const int n_max = p.nsub * p.cap;
   const size_t smem = static_cast<size_t>(n_max + ksort) * sizeof(uint64_t);
-  const size_t budget = 200 * 1024;
+  const size_t budget = kSelectSmemBudget;
   if (smem > budget) return "select_topk: too many survivors per row for shared memory";
+  const bool large = p.k_sel > kMaxK;   // long sorts: 32 warps per row
+  static bool attr_set[2] = {false, false};
+  if (smem > 48 * 1024 && !attr_set[large]) {
+    cudaError_t e = large ? cudaFuncSetAttribute(select_topk_kernel<kLargeThreads>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(budget))
+                          : cudaFuncSetAttribute(select_topk_kernel<kSelThreads>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(budget));
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    attr_set[large] = true;
+  }
+  if (large) select_topk_kernel<kLargeThreads><<<p.B, kLargeThreads, smem, stream>>>(p, n_max, ksort);
+  else select_topk_kernel<kSelThreads><<<p.B, kSelThreads, smem, stream>>>(p, n_max, ksort);
+  return cuda_err(cudaGetLastError());
+}
+
+const char* select_dense_launch(const float* z, int R, int H, int k, int num_sms, float* out_vals, int32_t* out_idx,
+                                cudaStream_t stream) {
+  const int ksort = next_pow2(k < 2 ? 2 : k);
+  const size_t smem = static_cast<size_t>(ksort) * sizeof(uint64_t);
+  if (smem > kSelectSmemBudget) return "select_dense: k too large for shared memory";
   static bool attr_set = false;
   if (smem > 48 * 1024 && !attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(budget));
+    cudaError_t e = cudaFuncSetAttribute(select_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(kSelectSmemBudget));
     if (e != cudaSuccess) return cudaGetErrorString(e);
     attr_set = true;
   }
-  select_topk_kernel<<<p.B, kSelThreads, smem, stream>>>(p, n_max, ksort);
+  const int blocks = R < num_sms * 2 ? R : num_sms * 2;
+  select_dense_kernel<<<blocks, kLargeThreads, smem, stream>>>(z, R, H, k, ksort, out_vals, out_idx);
+  return cuda_err(cudaGetLastError());
+}
+
+int rescue_large_blocks(int H, int num_sms) {
+  // one scratch line of H floats per block, at most 256 MB in total
+  long long b = (256ll << 20) / (static_cast<long long>(H) * 4);
+  if (b > num_sms) b = num_sms;
+  if (b < 8) b = 8;
+  return static_cast<int>(b);
+}
+size_t rescue_large_scratch_bytes(int H, int num_sms) {
+  return static_cast<size_t>(rescue_large_blocks(H, num_sms)) * H * sizeof(float);
+}
+
+const char* rescue_large_launch(const RescueLaunch& p, void* scratch, int num_sms, cudaStream_t stream) {
+  const int ksort = next_pow2(p.k_out < 2 ? 2 : p.k_out);
+  const size_t smem = static_cast<size_t>(ksort) * sizeof(uint64_t);
+  if (smem > kSelectSmemBudget) return "rescue_large: k too large for shared memory";
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(rescue_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(kSelectSmemBudget));
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    attr_set = true;
+  }
+  rescue_large_kernel<<<rescue_large_blocks(p.H, num_sms), kLargeThreads, smem, stream>>>(p, static_cast<float*>(scratch), ksort);
   return cuda_err(cudaGetLastError());
 }
 

@@ -88,7 +88,7 @@ class binary_decoder(nn.Module):
     def forward(self, latent, true_sum=None):
         """reference signature (latent, true_sum) -> (reconstruction, polarize_loss); the second
         argument is unused there too (sae/binary.py:24). `latent` may be SparseLatents or the
-        dense [B, H] matrix the reference passes (rows with at most QSAE_MAX_K non-zeros)."""
+        dense [B, H] matrix the reference passes (rows with at most QSAE_MAX_K_LARGE non-zeros)."""
         if not isinstance(latent, SparseLatents):
             latent = sparsify_dense(latent)
         return self.decode_sparse(latent), self.polarize_loss()
@@ -120,8 +120,8 @@ def sparsify_dense(latent: torch.Tensor) -> SparseLatents:
     latent = latent.contiguous().float()
     nnz = int((latent != 0).sum(1).max().item()) if latent.numel() else 0
     k = max(1, nnz)
-    if k > _lib.QSAE_MAX_K:
-        raise RuntimeError(f"dense latent with {nnz} non-zeros per row exceeds QSAE_MAX_K={_lib.QSAE_MAX_K}")
+    if k > _lib.QSAE_MAX_K_LARGE:
+        raise RuntimeError(f"dense latent with {nnz} non-zeros per row exceeds QSAE_MAX_K_LARGE={_lib.QSAE_MAX_K_LARGE}")
     _, idx = _lib.topk_dense(latent.abs(), k)
     vals = torch.gather(latent, 1, idx.long())
     idx = torch.where(vals != 0, idx, torch.full_like(idx, -1))

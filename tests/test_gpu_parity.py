@@ -35,7 +35,9 @@ def assert_vals_close(got, ref):
 def assert_topk_matches(gv, gi, z, k, eps=1e-6):
     """Index order must equal the oracle's (value desc, index asc) bit for bit, except where the
     oracle's own fp32 values are tied to within accumulation-order noise (|dz| <= eps * max(1,|z|)):
-    there any order / choice among the near-equal entries is accepted."""
+    there any order / choice among the near-equal entries is accepted. Near-ties must stay rare:
+    at most 2 % of the rows for k <= 224; for the large-k paths (thousands of adjacent order
+    statistics per row) at most 0.5 % of all (row, rank) positions."""
     rv, ri = O.topk_rows(z, k)
     bad_rows = np.nonzero((gi != ri).any(1))[0]
     for r in bad_rows:
@@ -43,7 +45,10 @@ def assert_topk_matches(gv, gi, z, k, eps=1e-6):
         got = z[r, gi[r].astype(np.int64)]
         assert np.all(np.abs(got - rv[r]) <= eps * np.maximum(1.0, np.abs(rv[r]))), \
             f"row {r}: differs from the oracle beyond a near-tie: {gi[r]} vs {ri[r]}"
-    assert len(bad_rows) <= max(1, gi.shape[0] // 50), f"{len(bad_rows)} rows rely on the near-tie rule"
+    if k <= 224:
+        assert len(bad_rows) <= max(1, gi.shape[0] // 50), f"{len(bad_rows)} rows rely on the near-tie rule"
+    else:
+        assert int((gi != ri).sum()) <= max(2, gi.size // 200), f"{int((gi != ri).sum())} positions rely on the near-tie rule"
     assert_vals_close(gv, np.take_along_axis(z, gi.astype(np.int64), axis=1))
 
 
@@ -397,6 +402,99 @@ def test_prior_failure_is_rescued_exactly(cuda_device):
                                          sample=(ws, bs + 100.0))
         assert_topk_matches(vals.cpu().numpy(), idx.cpu().numpy(), O.encode_pre(x, W, b), k)
         assert int((flags != 0).sum()) == 0          # rescued rows are exact by construction
+
+
+# ------------------------------------------------------------------------------------------
+# k > QSAE_MAX_K: block-level radix select (reference default k = int(0.002 H) = 2097 at H = 2^20)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,D,k,exact", [
+    (40, 16384, 256, 300, False),     # prior path, m ~ 27
+    (33, 65536, 128, 2097, False),    # prior path at the reference-default k of a 2^20 dictionary
+    (260, 32768, 512, 262, False),    # 2097 / 8 shards
+    (24, 32768, 512, 300, True),      # arbitrary fp32 operands: fp32 re-scoring of k + 16 candidates
+    (9, 2048, 64, 500, False),        # no sample: dense pre-activations + dense radix select
+    (7, 2048, 64, 500, True),
+    (5, 4096, 8, 4096, False),        # k == H
+])
+def test_large_k_topk_matches_oracle(cuda_device, B, H, D, k, exact):
+    x, W, b = _enc_case(B, H, D, 300 + k, bf16=not exact)
+    dx, dW, db = T(x, cuda_device), T(W, cuda_device), T(b, cuda_device)
+    wb = L.cast_bf16(dW)
+    sample = L.prepare_sample(wb, db)
+    assert (sample is not None) == (H >= 8192)
+    vals, idx, flags = L.encode_topk(dx, wb, dW if exact else None, db, k, exact=exact, want_flags=True, sample=sample)
+    assert_topk_matches(vals.cpu().numpy(), idx.cpu().numpy(), O.encode_pre(x, W, b), k)
+    assert int((flags != 0).sum()) == 0
+
+
+def test_large_k_relu_ties_and_failed_prior_are_rescued(cuda_device):
+    """(a) ReLU zeros flood every survivor list (threshold 0 keeps all H latents): the rows must go
+    through the exact dense recomputation and come back in (value desc, index asc) order, bit exact.
+    (b) A prior that is far too high (sampled rows carry a bias the real rows lack) fails the count
+    check on every row."""
+    B, H, D, k = 20, 16384, 64, 1000
+    x, W, b = _enc_case(B, H, D, 91)
+    b = b - 0.6
+    dx, dW, db = T(x, cuda_device), T(W, cuda_device), T(b, cuda_device)
+    wb = L.cast_bf16(dW)
+    sample = L.prepare_sample(wb, db)
+    vals, idx, _ = L.encode_topk(dx, wb, None, db, k, act=L.ACT_RELU, sample=sample)
+    zr = np.maximum(O.encode_pre(x, W, b), 0).astype(np.float32)
+    rv, ri = O.topk_rows(zr, k)
+    assert (rv == 0).any()
+    assert_topk_matches(vals.cpu().numpy(), idx.cpu().numpy(), zr, k)
+    zero = rv == 0
+    assert np.array_equal(idx.cpu().numpy()[zero], ri[zero])
+    ws, bs = sample
+    for exact in (False, True):
+        vals, idx, flags = L.encode_topk(dx, wb, dW if exact else None, db, 300, exact=exact, want_flags=True,
+                                         sample=(ws, bs + 100.0))
+        assert_topk_matches(vals.cpu().numpy(), idx.cpu().numpy(), O.encode_pre(x, W, b), 300)
+        assert int((flags != 0).sum()) == 0
+
+
+def test_large_k_dense_topk_and_decode(cuda_device):
+    """dense top-k with k > QSAE_MAX_K (apply_topk_activation / binary_decoder.forward on dense latents)
+    and the sparse decoders at the same k."""
+    rng = np.random.default_rng(12)
+    R, H, D, k = 11, 20000, 64, 700
+    z = rng.standard_normal((R, H)).astype(np.float32)
+    z[3] = np.round(z[3])                                               # heavy ties in one row
+    vals, idx = L.topk_dense(T(z, cuda_device), k)
+    rv, ri = O.topk_rows(z, k)
+    assert np.array_equal(idx.cpu().numpy(), ri) and np.array_equal(vals.cpu().numpy(), rv)
+    iw = rng.integers(-8, 8, size=(H, D)).astype(np.int8)
+    bias = rng.standard_normal(D).astype(np.float32)
+    ref = O.decode_rows(rv, ri, iw.astype(np.float32), 0.5, bias)
+    got = L.decode_int4(vals, idx, T(O.pack_nibbles(iw), cuda_device), H, D, 0.5, T(bias, cuda_device)).cpu().numpy()
+    assert_recon_close(got, ref)
+    got = L.decode_int8(vals, idx, T(iw, cuda_device), H, D, 0.5, T(bias, cuda_device)).cpu().numpy()
+    assert_recon_close(got, ref)
+
+
+def test_bsae_module_reference_default_k_large_dictionary(cuda_device):
+    """BinarySAE at H = 2^17 keeps int(0.002 H) = 262 latents per row (sae/binary.py:94): module forward
+    vs the oracle restatement (the reference itself is pinned at smaller H by the golden fixtures)."""
+    D, H, B, n_bits = 64, 2 ** 17, 48, 4
+    rng = np.random.default_rng(8)
+    x = cases.round_bf16(rng.standard_normal((B, D)).astype(np.float32))
+    We = cases.round_bf16(cases.xavier_uniform(rng, H, D))
+    be = np.zeros(H, np.float32)
+    logits = np.where(rng.random((H, D * n_bits)) < 0.5, 110.0, -110.0).astype(np.float32)
+    bd = rng.standard_normal(D).astype(np.float32)
+    m = Q.BinarySAE(D, H, 4.0, n_bits)
+    m.load_state_dict({"encoder.0.weight": torch.from_numpy(We), "encoder.0.bias": torch.from_numpy(be),
+                       "decoder.weight": torch.from_numpy(logits), "decoder.bias": torch.from_numpy(bd)}, strict=True)
+    m.to(cuda_device).eval()
+    m.return_dense = False
+    k = O.bsae_k(H)
+    assert k == 262
+    with torch.no_grad():
+        sp, recon, pol = m(T(x, cuda_device))
+    rv, ri, rr, rp = O.bsae_forward(x, We, be, logits, bd, n_bits=n_bits, gamma=4.0, k=k, mode="hard")
+    assert_topk_matches(sp.values.cpu().numpy(), sp.indices.cpu().numpy(), O.encode_pre(x, We, be), k)
+    assert_recon_close(recon.cpu().numpy(), rr)
+    assert float(pol) == pytest.approx(rp, abs=1e-9)
 
 
 def test_sample_rows_are_a_stratified_subset(cuda_device):

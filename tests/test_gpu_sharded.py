@@ -126,7 +126,8 @@ def test_dictionary_sharded_forward_under_nccl(cuda_device):
         assert pol == rp
 
 
-@pytest.mark.parametrize("G,B,kin,kout", [(8, 33, 32, 32), (4, 17, 65, 65), (8, 9, 128, 100), (2, 5, 7, 9), (8, 6, 224, 224)])
+@pytest.mark.parametrize("G,B,kin,kout", [(8, 33, 32, 32), (4, 17, 65, 65), (8, 9, 128, 100), (2, 5, 7, 9), (8, 6, 224, 224),
+                                          (8, 5, 263, 2097), (8, 3, 2097, 2097), (4, 4, 1000, 4000)])
 def test_merge_candidates_tie_rule(cuda_device, G, B, kin, kout):
     """Heavily tied candidate values: the merge must order by (value desc, global index asc) exactly."""
     rng = np.random.default_rng(G * 1000 + kin)

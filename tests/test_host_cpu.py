@@ -55,7 +55,10 @@ def test_argument_validation_without_gpu():
     assert lib.qsae_encode_topk_workspace_bytes(128, 1024, 1024, 8, 0, C.byref(n)) == -1  # D > 512
     assert lib.qsae_encode_topk_workspace_bytes(128, 16, 64, 32, 0, C.byref(n)) == -5     # k > H
     assert b"out of range" in lib.qsae_last_error()
-    assert lib.qsae_encode_topk_workspace_bytes(128, 4096, 64, 500, 0, C.byref(n)) == -1  # k > MAX_K
+    assert lib.qsae_encode_topk_workspace_bytes(128, 8192, 64, 5000, 0, C.byref(n)) == -1  # k > MAX_K_LARGE
+    assert b"QSAE_MAX_K_LARGE" in lib.qsae_last_error()
+    assert lib.qsae_encode_topk_workspace_bytes(128, 4096, 64, 500, 0, C.byref(n)) == 0 and n.value > 128 * 4096 * 4  # dense path
+    assert lib.qsae_encode_topk_workspace_bytes(4096, 131072, 512, 262, 4096, C.byref(n)) == 0 and n.value > 0       # prior path
     assert lib.qsae_encode_topk_workspace_bytes(4096, 32768, 512, 32, 1024, C.byref(n)) == 0 and n.value > 0
     assert lib.qsae_tsae_workspace_bytes(128, 1004, 64, 0, C.byref(n)) == -1             # H % 8
     assert lib.qsae_tsae_workspace_bytes(4096, 32768, 512, 1, C.byref(n)) == 0 and n.value > 2 * 4096 * 32768 * 2
