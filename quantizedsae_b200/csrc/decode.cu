@@ -80,8 +80,10 @@ decode_int4_kernel(const float* __restrict__ vals, const int32_t* __restrict__ i
     const int my_f = mine ? __float2int_rn(vrow[e] * to_fixed) : 0;
     my_i = mine ? my_i : 0;
     const int m = min(32, k - base);
+    const unsigned owned = __ballot_sync(full, mine);   // dictionary shards own ~1 / G of the winners: skip the rest
 #pragma unroll 4
     for (int j = 0; j < m; ++j) {
+      if (((owned >> j) & 1u) == 0u) continue;          // warp-uniform
       const int vf = __shfl_sync(full, my_f, j);
       const int i = __shfl_sync(full, my_i, j);
       vsum += vf;

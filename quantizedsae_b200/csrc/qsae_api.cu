@@ -206,9 +206,11 @@ int plan_encode_large(int B, int H, int D, int k, int exact, int n_sample, Large
     const int m = choose_prior_rank(k_sel, r);
     if (m <= kMaxK && m <= n_sample) {
       plan_stage(B, H, 0, kStagePriorMain, true, off, &lp->main);
-      // expected survivors ~ m / r per row; buffers for twice that, bounded by the merge kernel's shared memory
-      const long long want = static_cast<long long>(2.0 * m / r) + 64;
-      int cap = next_pow2_host(static_cast<int>((want + lp->main.nsub - 1) / lp->main.nsub));
+      // survivors of a row = rank of the m-th largest sample value in the full row: mean m / r, standard
+      // deviation ~ sqrt(m) / r (negative binomial); a list holds 1 / nsub of them (+ Poisson spread).
+      // Lists sized for mean + 7 sigma of both: a filled list costs an exact recomputation of the row.
+      const double per_list = (m + 7.0 * sqrt(static_cast<double>(m))) / r / lp->main.nsub;
+      int cap = next_pow2_host(static_cast<int>(per_list + 7.0 * sqrt(per_list)) + 64);
       if (cap < 256) cap = 256;
       while (cap > 256 && (static_cast<size_t>(lp->main.nsub) * cap + ksort) * 8 > kSelectSmemBudget) cap >>= 1;
       if ((static_cast<size_t>(lp->main.nsub) * cap + ksort) * 8 <= kSelectSmemBudget &&
@@ -334,6 +336,23 @@ int encode_topk_large(const float* x_f32, const uint16_t* w_bf16, const float* w
   sl.rescue_count = counters; sl.rescue_rows = rescue_rows;
   rc = launch_status("select_topk kernel", select_topk_launch(sl, st));
   if (rc != QSAE_OK) return rc;
+  if (getenv("QSAE_DEBUG_LARGE")) {   // diagnostics: survivor statistics of this call (synchronises)
+    cudaStreamSynchronize(st);
+    int h_counters[4];
+    cudaMemcpy(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost);
+    const size_t nl = static_cast<size_t>(B) * lp.main.nsub;
+    int* h_cnt = static_cast<int*>(malloc(nl * sizeof(int)));
+    cudaMemcpy(h_cnt, el.cand_cnt, nl * sizeof(int), cudaMemcpyDeviceToHost);
+    long long tot = 0; int mx = 0, row_min = 1 << 30, row_max = 0;
+    for (int r = 0; r < B; ++r) {
+      int rs = 0;
+      for (int s2 = 0; s2 < lp.main.nsub; ++s2) { const int c = h_cnt[static_cast<size_t>(r) * lp.main.nsub + s2]; rs += c; if (c > mx) mx = c; }
+      tot += rs; if (rs < row_min) row_min = rs; if (rs > row_max) row_max = rs;
+    }
+    fprintf(stderr, "[qsae large] k=%d k_sel=%d m=%d nsub=%d cap=%d: survivors/row mean %.1f min %d max %d, largest list %d; rescued rows %d, sweep overflow %d\n",
+            k, lp.k_sel, lp.m, lp.main.nsub, lp.main.cap, static_cast<double>(tot) / B, row_min, row_max, mx, h_counters[0], h_counters[1]);
+    free(h_cnt);
+  }
   // 4. failed rows: exact recomputation
   RescueLaunch rl;
   memset(&rl, 0, sizeof(rl));

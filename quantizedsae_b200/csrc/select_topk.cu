@@ -181,7 +181,8 @@ __device__ __forceinline__ void select_row_block(const SelectLaunch& p, int row,
   }
   __syncthreads();
 
-  block_bitonic_desc(sel, ksort);
+  if (ksort >= 2048) block_bitonic_desc_regs<8>(sel, ksort);
+  else block_bitonic_desc(sel, ksort);
 
   // ---- emit
   for (int j = threadIdx.x; j < p.k_out; j += THREADS) {
@@ -208,7 +209,7 @@ __device__ __forceinline__ void select_row_block(const SelectLaunch& p, int row,
 }
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 2 : 1)
 select_topk_kernel(SelectLaunch p, int n_max, int ksort) {
   extern __shared__ __align__(16) uint8_t sel_smem[];
   select_row_block<THREADS>(p, blockIdx.x, n_max, ksort, sel_smem);
@@ -253,7 +254,8 @@ __device__ __forceinline__ int dense_row_topk(const float* z, int H, int k, int 
   const int out = min(*s_out, ksort);
   for (int e = out + threadIdx.x; e < ksort; e += THREADS) sel[e] = 0ull;
   __syncthreads();
-  block_bitonic_desc(sel, ksort);
+  if (ksort >= 2048) block_bitonic_desc_regs<8>(sel, ksort);
+  else block_bitonic_desc(sel, ksort);
   return out;
 }
 
@@ -267,7 +269,8 @@ __device__ __forceinline__ void emit_sorted(const uint64_t* sel, int out, int ro
   }
 }
 
-constexpr int kLargeThreads = 1024;
+constexpr int kLargeThreads = 512;   // long sorts (ksort >= kLongSort): 16 warps, register-resident bitonic chunks
+constexpr int kLongSort = 2048;
 
 // dense [R, H] matrix -> ordered top-k per row, any k (block per row)
 __global__ void __launch_bounds__(kLargeThreads)
@@ -737,7 +740,7 @@ const char* select_topk_launch(const SelectLaunch& p, cudaStream_t stream) {
   const size_t smem = static_cast<size_t>(n_max + ksort) * sizeof(uint64_t);
   const size_t budget = kSelectSmemBudget;
   if (smem > budget) return "select_topk: too many survivors per row for shared memory";
-  const bool large = p.k_sel > kMaxK;   // long sorts: 32 warps per row
+  const bool large = ksort >= kLongSort;   // long sorts: 16 warps per row
   static bool attr_set[2] = {false, false};
   if (smem > 48 * 1024 && !attr_set[large]) {
     cudaError_t e = large ? cudaFuncSetAttribute(select_topk_kernel<kLargeThreads>,

@@ -68,19 +68,51 @@ __device__ __forceinline__ uint32_t sort_key_col(uint64_t k) {
 
 // Block-cooperative radix select over n distinct 64-bit composite keys, key_at(e) for e in [0, n):
 // returns T such that exactly min(k, n) keys satisfy key >= T. Most-significant-digit first, 8 bits
-// per pass, every pass one sweep of all threads over the keys (shared-memory histogram); stops as soon
-// as a digit bucket holds exactly the number of keys still wanted (distinct values: <= 4 passes over the
-// value half, the column half only breaks ties). Any k (the warp bisections handle k <= kMaxK only).
-// hist: 256 ints of shared memory; ctl: 3 ints. Must be called by every thread of the block.
+// per pass, every pass one sweep of all threads over the keys (shared-memory histogram). The first
+// sweep finds the leading bits all keys share (survivors of one row sit in a narrow value range: sign
+// and exponent are common) so that no pass piles every key onto one histogram bin; the select stops
+// as soon as a digit bucket holds exactly the number of keys still wanted (distinct values: <= 3-4
+// passes, the column half only breaks ties). Any k (the warp bisections handle k <= kMaxK only).
+// hist: 256 ints of shared memory; ctl: 4 ints. Must be called by every thread of the block.
 template <typename KeyAt>
 __device__ __forceinline__ uint64_t block_radix_select(KeyAt key_at, int n, int k, int* hist, int* ctl) {
   if (n <= k) return 0ull;
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  uint64_t prefix = 0ull, mask = 0ull;
+  // ---- shared leading bits: AND / OR of all keys
+  unsigned* u = reinterpret_cast<unsigned*>(hist);
+  if (threadIdx.x == 0) { u[0] = 0xFFFFFFFFu; u[1] = 0xFFFFFFFFu; u[2] = 0u; u[3] = 0u; }
+  __syncthreads();
+  {
+    uint64_t a = ~0ull, o = 0ull;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      const uint64_t key = key_at(e);
+      a &= key;
+      o |= key;
+    }
+    unsigned a_hi = static_cast<unsigned>(a >> 32), a_lo = static_cast<unsigned>(a);
+    unsigned o_hi = static_cast<unsigned>(o >> 32), o_lo = static_cast<unsigned>(o);
+    a_hi = __reduce_and_sync(full, a_hi); a_lo = __reduce_and_sync(full, a_lo);
+    o_hi = __reduce_or_sync(full, o_hi); o_lo = __reduce_or_sync(full, o_lo);
+    if (lane == 0) {
+      atomicAnd(&u[0], a_hi); atomicAnd(&u[1], a_lo);
+      atomicOr(&u[2], o_hi); atomicOr(&u[3], o_lo);
+    }
+  }
+  __syncthreads();
+  const uint64_t all_and = (static_cast<uint64_t>(u[0]) << 32) | u[1];
+  const uint64_t all_or = (static_cast<uint64_t>(u[2]) << 32) | u[3];
+  __syncthreads();   // hist is reused below
+  const uint64_t diff = all_and ^ all_or;   // != 0: n > k >= 1 distinct keys
+  const int top = 63 - __clzll(static_cast<long long>(diff));
+  int shift = top - 7;
+  if (shift < 0) shift = 0;
+  // bits above the first digit are common to all keys
+  uint64_t mask = (shift + 8 >= 64) ? 0ull : (~0ull << (shift + 8));
+  uint64_t prefix = all_and & mask;
   int need = k;
 #pragma unroll 1
-  for (int shift = 56; shift >= 0; shift -= 8) {
+  for (;;) {
     for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
     __syncthreads();
     for (int e = threadIdx.x; e < n; e += blockDim.x) {
@@ -121,17 +153,28 @@ __device__ __forceinline__ uint64_t block_radix_select(KeyAt key_at, int n, int 
     prefix |= static_cast<uint64_t>(bin) << shift;
     mask |= 0xFFull << shift;
     __syncthreads();   // ctl / hist are rewritten by the next pass
-    if (bucket == need) break;   // the whole bucket is wanted: the low bits of T stay zero
+    if (bucket == need || shift == 0) break;   // the whole bucket is wanted: the low bits of T stay zero
+    shift = shift >= 8 ? shift - 8 : 0;        // a last partial digit re-reads a few decided bits (harmless)
   }
   return prefix;
 }
 
 // Block-wide bitonic sort (descending) of sel[0, ksort), ksort a power of two, in shared memory.
+// Each warp owns a contiguous chunk of ksort / nwarps elements: every step whose exchange distance
+// stays inside a chunk runs warp-locally (__syncwarp), only the long strides synchronise the block
+// (ksort = 4096 on 32 warps: 15 block barriers instead of 78).
 __device__ __forceinline__ void block_bitonic_desc(uint64_t* sel, int ksort) {
+  const int nthreads = blockDim.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = nthreads >> 5;
+  int chunk = ksort / nwarps;              // elements per warp (power of two); < 64: plain block steps only
+  if (chunk < 64) chunk = 0;
+  const int half = ksort >> 1;
   for (int size = 2; size <= ksort; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = threadIdx.x; t < (ksort >> 1); t += blockDim.x) {
-        const int pos = ((t / stride) * (stride << 1)) + (t % stride);
+    int stride = size >> 1;
+    for (; stride > 0 && 2 * stride > chunk; stride >>= 1) {   // block-level steps
+      for (int t = threadIdx.x; t < half; t += nthreads) {
+        const int pos = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
         const int partner = pos + stride;
         const bool desc = (pos & size) == 0;
         const uint64_t a = sel[pos], b = sel[partner];
@@ -142,6 +185,113 @@ __device__ __forceinline__ void block_bitonic_desc(uint64_t* sel, int ksort) {
       }
       __syncthreads();
     }
+    if (stride > 0) {                                           // the remaining strides stay inside a warp's chunk
+      const int t0 = warp * (chunk >> 1);
+      for (; stride > 0; stride >>= 1) {
+        for (int tt = lane; tt < (chunk >> 1); tt += 32) {
+          const int t = t0 + tt;
+          const int pos = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+          const int partner = pos + stride;
+          const bool desc = (pos & size) == 0;
+          const uint64_t a = sel[pos], b = sel[partner];
+          if ((a < b) == desc) {
+            sel[pos] = b;
+            sel[partner] = a;
+          }
+        }
+        __syncwarp();
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---- register-resident variant for long sorts ------------------------------------------------------------
+// A warp holds a chunk of 32 P consecutive elements, P per lane (element j * 32 + lane of the chunk): strides
+// below 32 exchange through shuffles, strides 32 .. 16 P are register moves; only strides >= 32 P go through
+// shared memory with a block barrier (ksort = 4096, 16 warps, P = 8: 10 block-level steps out of 78).
+template <int P>
+__device__ __forceinline__ void warp_bitonic_step(uint64_t (&k)[P], int lane, int stride, bool desc_uniform, int size,
+                                                  bool use_uniform) {
+  const unsigned full = 0xffffffffu;
+  if (stride >= 32) {
+    const int js = stride >> 5;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      if ((j & js) == 0) {
+        const bool desc = use_uniform ? desc_uniform : (((j * 32) & size) == 0);
+        const uint64_t a = k[j], b = k[j | js];
+        const bool swap = (a < b) == desc;
+        k[j] = swap ? b : a;
+        k[j | js] = swap ? a : b;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const bool desc = use_uniform ? desc_uniform : ((((j * 32) | lane) & size) == 0);
+      const bool lower = (lane & stride) == 0;
+      const uint64_t mine = k[j];
+      const uint64_t other = __shfl_xor_sync(full, mine, stride);
+      const bool mine_big = mine > other;
+      const bool take_max = (lower == desc);
+      k[j] = (take_max == mine_big) ? mine : other;
+    }
+  }
+}
+
+template <int P>
+__device__ __forceinline__ void block_bitonic_desc_regs(uint64_t* sel, int ksort) {
+  constexpr int CH = 32 * P;
+  const int nthreads = blockDim.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = nthreads >> 5;
+  const int nchunks = ksort / CH;
+  const int half = ksort >> 1;
+  // ---- phase 1: every chunk fully sorted in registers, direction from its position (sizes 2 .. CH)
+  for (int c = warp; c < nchunks; c += nwarps) {
+    uint64_t k[P];
+    const int base = c * CH;
+#pragma unroll
+    for (int j = 0; j < P; ++j) k[j] = sel[base + j * 32 + lane];
+#pragma unroll
+    for (int size = 2; size <= CH; size <<= 1) {
+      const bool top = size == CH;
+      const bool desc_u = (base & size) == 0;
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) warp_bitonic_step<P>(k, lane, stride, desc_u, size, top);
+    }
+#pragma unroll
+    for (int j = 0; j < P; ++j) sel[base + j * 32 + lane] = k[j];
+  }
+  __syncthreads();
+  // ---- phase 2: sizes 2 CH .. ksort: long strides in shared memory, the tail of every merge in registers
+  for (int size = 2 * CH; size <= ksort; size <<= 1) {
+    for (int stride = size >> 1; stride >= CH; stride >>= 1) {
+      for (int t = threadIdx.x; t < half; t += nthreads) {
+        const int pos = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+        const int partner = pos + stride;
+        const bool desc = (pos & size) == 0;
+        const uint64_t a = sel[pos], b = sel[partner];
+        if ((a < b) == desc) {
+          sel[pos] = b;
+          sel[partner] = a;
+        }
+      }
+      __syncthreads();
+    }
+    for (int c = warp; c < nchunks; c += nwarps) {
+      uint64_t k[P];
+      const int base = c * CH;
+      const bool desc_u = (base & size) == 0;
+#pragma unroll
+      for (int j = 0; j < P; ++j) k[j] = sel[base + j * 32 + lane];
+#pragma unroll
+      for (int stride = CH >> 1; stride > 0; stride >>= 1) warp_bitonic_step<P>(k, lane, stride, desc_u, 0, true);
+#pragma unroll
+      for (int j = 0; j < P; ++j) sel[base + j * 32 + lane] = k[j];
+    }
+    __syncthreads();
   }
 }
 

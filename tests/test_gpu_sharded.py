@@ -61,6 +61,39 @@ def test_virtual_shards_match_full_dictionary(cuda_device, G, D, H, B, k):
     assert torch.equal(p1, p2)
 
 
+@pytest.mark.parametrize("G,D,H,B,k", [(8, 64, 131072, 24, 262), (4, 128, 65536, 10, 1000)])
+def test_virtual_shards_large_k(cuda_device, G, D, H, B, k):
+    """k > QSAE_MAX_K (int(0.002 H) = 262 at H = 2^17, 2097 at 2^20): every shard contributes its own
+    top-k through the block-level path, the merge radix-selects the global top-k of the G * k
+    candidates. Compared with the near-tie-aware rule (thousands of adjacent order statistics)."""
+    from tests.test_gpu_parity import assert_topk_matches
+
+    cfg, inp = sharded_case(D=D, H=H, B=B, seed=G + k)
+    dev = cuda_device
+    x = torch.from_numpy(inp["x"]).to(dev)
+    bd = torch.from_numpy(inp["bd"]).to(dev)
+    qstep = cfg["gamma"] / 2 ** (cfg["n_bits"] - 1)
+    cands, packs = [], []
+    for g in range(G):
+        plan = ShardPlan(H, G, g)
+        a, b = plan.latent_range()
+        We = torch.from_numpy(inp["We"][a:b]).to(dev)
+        be = torch.from_numpy(inp["be"][a:b]).to(dev)
+        w_bf16 = L.cast_bf16(We)
+        vals, idx, _ = L.encode_topk(x, w_bf16, None, be, plan.k_local(k), sample=L.prepare_sample(w_bf16, be))
+        cands.append(L.pack_candidates(vals, idx))
+        packs.append(L.pack_bitplanes(torch.from_numpy(inp["logits"][a:b]).to(dev), D, cfg["n_bits"])[0])
+    gv, gi = L.merge_candidates(torch.stack(cands, 0).contiguous(), H // G, k)
+    z = O.encode_pre(inp["x"], inp["We"], inp["be"])
+    assert_topk_matches(gv.cpu().numpy(), gi.cpu().numpy(), z, k)
+    total = torch.zeros((B, D), device=dev)
+    for g in range(G):
+        total += L.decode_range(gv, gi, packs[g], H // G, g * (H // G), D, qstep, bd if g == 0 else None, cfg["n_bits"])
+    ref = O.decode_rows(gv.cpu().numpy(), gi.cpu().numpy(), O.dequant_hard(inp["logits"], cfg["n_bits"]).astype(np.float32),
+                        qstep, inp["bd"])
+    _recon_close(total.cpu().numpy(), ref)
+
+
 def test_world_size_one_module_equals_bsae(cuda_device):
     cfg, inp = sharded_case(D=64, H=4096, B=50)
     m = DictionaryShardedBinarySAE(cfg["D"], cfg["H"], cfg["gamma"], cfg["n_bits"], rank=0, world_size=1)
@@ -82,7 +115,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _nccl_worker(rank, world, port, out):
+def _nccl_worker(rank, world, port, out, D, H, B, kfrac):
     import torch.distributed as dist
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -90,11 +123,11 @@ def _nccl_worker(rank, world, port, out):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        cfg, inp = sharded_case(D=512, H=32768, B=203, seed=5)
+        cfg, inp = sharded_case(D=D, H=H, B=B, seed=5)
         m = DictionaryShardedBinarySAE(cfg["D"], cfg["H"], cfg["gamma"], cfg["n_bits"])
         m.load_state_dict(m.plan.shard_state_dict(full_state_dict(inp), cfg["n_bits"]), strict=True)
         m.to(dev).eval()
-        m.k = 2 ** -10
+        m.k = kfrac
         with torch.no_grad():
             lat, rows, pol = m(torch.from_numpy(inp["x"]).to(dev))
         torch.cuda.synchronize()
@@ -104,26 +137,32 @@ def _nccl_worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_dictionary_sharded_forward_under_nccl(cuda_device):
+# k = 32 of 32768 latents; and the reference default fraction 0.002 on 2^17 latents (k = 262 > QSAE_MAX_K:
+# block-level selection on every shard, radix-select merge of G * 262 candidates)
+@pytest.mark.parametrize("D,H,B,kfrac", [(512, 32768, 203, 2 ** -10), (128, 131072, 61, 0.002)])
+def test_dictionary_sharded_forward_under_nccl(cuda_device, D, H, B, kfrac):
     world = min(torch.cuda.device_count(), 8)
     if world < 2:
         pytest.skip("needs >= 2 GPUs (gpurun --gpus N)")
     import torch.multiprocessing as mp
+    from tests.test_gpu_parity import assert_topk_matches
 
     port = _free_port()
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_nccl_worker, args=(world, port, out), nprocs=world, join=True)
+        mp.spawn(_nccl_worker, args=(world, port, out, D, H, B, kfrac), nprocs=world, join=True)
         res = {r: out[r] for r in range(world)}
-    cfg, inp = sharded_case(D=512, H=32768, B=203, seed=5)
-    rv, ri, rr, rp = O.bsae_forward(inp["x"], inp["We"], inp["be"], inp["logits"], inp["bd"], n_bits=cfg["n_bits"],
-                                    gamma=cfg["gamma"], k=32, mode="hard")
+    cfg, inp = sharded_case(D=D, H=H, B=B, seed=5)
+    k = int(H * kfrac)
+    z = O.encode_pre(inp["x"], inp["We"], inp["be"])
+    hard = O.dequant_hard(inp["logits"], cfg["n_bits"]).astype(np.float32)
+    qstep = cfg["gamma"] / 2 ** (cfg["n_bits"] - 1)
     for r in range(world):
         v, i, rows, pol, (a, b) = res[r]
-        assert np.array_equal(i, ri)
-        assert np.all(np.abs(v - rv) <= 1e-5 * np.maximum(1.0, np.abs(rv)))
-        _recon_close(rows, rr[a:b])
-        assert pol == rp
+        assert np.array_equal(i, res[0][1]) and np.array_equal(v, res[0][0])       # identical on every rank
+        assert_topk_matches(v, i, z, k)
+        _recon_close(rows, O.decode_rows(v, i, hard, qstep, inp["bd"])[a:b])
+        assert pol == 0.0
 
 
 @pytest.mark.parametrize("G,B,kin,kout", [(8, 33, 32, 32), (4, 17, 65, 65), (8, 9, 128, 100), (2, 5, 7, 9), (8, 6, 224, 224),
