@@ -30,6 +30,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 D, H, N_BITS, GAMMA = 512, 32768, 4, 4.0
+E2E_CHUNK = int(os.environ.get("QSAE_E2E_CHUNK", "8192"))   # largest row chunk of the host-buffer pipeline
 METRIC = "b_sae 512->32768 4-bit fwd tokens/s"
 UNIT = "tokens/s"
 
@@ -246,7 +247,7 @@ def run_b200(args, rank, world, local_rank):
     g = torch.Generator(device=device).manual_seed(5)
     logits2 = torch.where(torch.rand((H, D * N_BITS), device=device, generator=g) < 0.5, 110.0, -110.0).float()
     L.check(lib.qsae_bsae_plan_create(We.data_ptr(), be.data_ptr(), logits2.data_ptr(), bd.data_ptr(), H, D, N_BITS,
-                                      C.c_float(GAMMA), k, 8192, C.byref(plan)))
+                                      C.c_float(GAMMA), k, E2E_CHUNK, C.byref(plan)))
     del logits2
     try:
         hx = [x.cpu().pin_memory() for x in xs[:2]]

@@ -1081,7 +1081,7 @@ struct qsae_bsae_plan {
   uint16_t* w_sample;
   float* b_sample;
   int n_sample;
-  static constexpr int kSlots = 3;
+  static constexpr int kSlots = 4;
   struct Slot {
     cudaStream_t stream;
     float* x;
@@ -1161,13 +1161,28 @@ int qsae_bsae_forward_host(qsae_bsae_plan* p, const float* x_host, int B, float*
     return fail(QSAE_ERR_INVALID_ARGUMENT, "forward_host: bad argument");
   int rc = QSAE_OK;
   int c = 0;
-  for (int r0 = 0; r0 < B && rc == QSAE_OK; r0 += p->chunk, ++c) {
+  // Chunk schedule: the device -> host copy of the results is the longest leg (B * (8 k + 4 D) bytes over PCIe), and
+  // it cannot start before the first chunk has been copied in and computed. So the first chunks are small
+  // (2048 rows, doubling) to start the output stream early, the rest are as large as the plan allows because
+  // the kernels are more efficient on large batches (the compute leg must stay ahead of the copy-out leg).
+  int next_rows = p->chunk < 2048 ? p->chunk : 2048;
+  const bool trace = getenv("QSAE_DEBUG_PIPELINE") != nullptr;   // diagnostics: per-chunk event timeline on stderr
+  constexpr int kTraceMax = 64;
+  cudaEvent_t tev[kTraceMax][4];
+  int trows[kTraceMax];
+  if (trace) {
+    for (int i = 0; i < kTraceMax; ++i) for (int j = 0; j < 4; ++j) cudaEventCreate(&tev[i][j]);
+  }
+  for (int r0 = 0, rows = 0; r0 < B && rc == QSAE_OK; r0 += rows, ++c) {
     auto& sl = p->slot[c % qsae_bsae_plan::kSlots];
-    const int rows = (B - r0 < p->chunk) ? (B - r0) : p->chunk;
+    rows = (B - r0 < next_rows) ? (B - r0) : next_rows;
+    next_rows = (next_rows * 2 < p->chunk) ? next_rows * 2 : p->chunk;
+    if (trace && c < kTraceMax) { trows[c] = rows; cudaEventRecord(tev[c][0], sl.stream); }
     cudaStream_t st = sl.stream;  // stream order protects the slot's buffers from its previous use
     cudaError_t e = cudaMemcpyAsync(sl.x, x_host + static_cast<size_t>(r0) * p->D,
                                     static_cast<size_t>(rows) * p->D * 4, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) { rc = fail(QSAE_ERR_CUDA, "forward_host H2D: %s", cudaGetErrorString(e)); break; }
+    if (trace && c < kTraceMax) cudaEventRecord(tev[c][1], st);
     rc = qsae_encode_topk(sl.x, p->w_bf16, p->w_f32, p->b_enc, p->w_sample, p->b_sample, p->n_sample, rows, p->H,
                           p->D, p->k, QSAE_ACT_NONE, 0, sl.vals, sl.idx, nullptr, sl.ws, sl.ws_bytes, st);
     if (rc != QSAE_OK) break;
@@ -1177,6 +1192,7 @@ int qsae_bsae_forward_host(qsae_bsae_plan* p, const float* x_host, int B, float*
       rc = qsae_decode_int8(sl.vals, sl.idx, rows, p->k, reinterpret_cast<const int8_t*>(p->packed), p->H, p->D,
                             p->qstep, p->dec_bias, sl.recon, st);
     if (rc != QSAE_OK) break;
+    if (trace && c < kTraceMax) cudaEventRecord(tev[c][2], st);
     e = cudaMemcpyAsync(vals_host + static_cast<size_t>(r0) * p->k, sl.vals, static_cast<size_t>(rows) * p->k * 4,
                         cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess)
@@ -1186,10 +1202,21 @@ int qsae_bsae_forward_host(qsae_bsae_plan* p, const float* x_host, int B, float*
       e = cudaMemcpyAsync(recon_host + static_cast<size_t>(r0) * p->D, sl.recon, static_cast<size_t>(rows) * p->D * 4,
                           cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) rc = fail(QSAE_ERR_CUDA, "forward_host D2H: %s", cudaGetErrorString(e));
+    if (trace && c < kTraceMax) cudaEventRecord(tev[c][3], st);
   }
   for (int s = 0; s < qsae_bsae_plan::kSlots; ++s) {
     cudaError_t e = cudaStreamSynchronize(p->slot[s].stream);
     if (e != cudaSuccess && rc == QSAE_OK) rc = fail(QSAE_ERR_CUDA, "forward_host sync: %s", cudaGetErrorString(e));
+  }
+  if (trace) {
+    const int nc = c < kTraceMax ? c : kTraceMax;
+    for (int i = 0; i < nc && rc == QSAE_OK; ++i) {
+      float t[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int j = 0; j < 4; ++j) cudaEventElapsedTime(&t[j], tev[0][0], tev[i][j]);
+      fprintf(stderr, "[qsae pipeline] chunk %2d rows %6d: start %.3f  h2d done %.3f  compute done %.3f  d2h done %.3f ms\n", i,
+              trows[i], t[0], t[1], t[2], t[3]);
+    }
+    for (int i = 0; i < kTraceMax; ++i) for (int j = 0; j < 4; ++j) cudaEventDestroy(tev[i][j]);
   }
   return rc;
 }
