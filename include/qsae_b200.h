@@ -200,6 +200,33 @@ int qsae_matryoshka_forward(const float* x_f32, const uint16_t* w_bf16,
                             unsigned long long* level_count /* [n_levels] */, int* overflow,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same forward, additionally exporting each row's active latents for the analysis consumers
+ * (_activation_mask of scripts/analysis/dynamic_analysis.py:30-73 without the dense [B, H] mask):
+ * active_idx [B, active_cap] int32, unordered, empty slots = -1; active_cnt [B] = number of active latents of the
+ * row (entries beyond active_cap are counted but not stored). NULL active_idx = plain forward. */
+int qsae_matryoshka_forward_active(const float* x_f32, const uint16_t* w_bf16, const float* w_f32,
+                                   const float* w_norm_max, const float* b_enc, const uint32_t* packed,
+                                   const float* scale, const int* level_start, int n_levels, const float* dec_bias,
+                                   int B, int H, int D, float* result, unsigned long long* level_count, int* overflow,
+                                   int32_t* active_idx, int active_cap, int32_t* active_cnt, void* workspace,
+                                   size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Analysis consumers over sparse active lists (scripts/analysis/dynamic_analysis.py:317-440).
+ * idx [B, cap] int32: latent indices of a row, entries < 0 or >= H are empty; vals [B, cap] or NULL: when
+ * given, an entry is active iff its value is > 0 (b_sae / baseline: `latent > 0`, :44-50).
+ * qsae_activation_counts: counts[h] += rows in which h is active                (:341, mask.sum(0))
+ * qsae_coactivation:      cooc[i * H + j] += rows in which i and j are both active, i == j included
+ *                         (:344-345, mask^T mask as int32); cap <= 2048
+ * qsae_sq_error_accumulate: *out += sum (a - b)^2 in float64                     (:96-100)
+ * All three accumulate into caller-zeroed device buffers, so a data loader's batches add up.
+ * ------------------------------------------------------------------------------------- */
+int qsae_activation_counts(const int32_t* idx, const float* vals, int B, int cap, int H,
+                           unsigned long long* counts /* [H] */, void* stream);
+int qsae_coactivation(const int32_t* idx, const float* vals, int B, int cap, int H, int32_t* cooc /* [H, H] */,
+                      void* stream);
+int qsae_sq_error_accumulate(const float* a, const float* b, size_t n, double* out /* device scalar */, void* stream);
+
 /* Dense path of the same forward, for any activity level (the sparse path reports *overflow when a row
  * has more active latents than its survivor lists hold -- e.g. an untrained model, ~50 % active):
  * dense pre-activations, A = (sigmoid(z) > 0.5) * scale as bf16 hi + lo, and one tcgen05 GEMM per level

@@ -79,4 +79,25 @@ def load() -> types.SimpleNamespace:
         ResidualQuantizedSAE=getattr(rq, "ResidualQuantizedSAE", None) if rq else None,
     )
     _cache["ns"] = ns
+    _cache["mods"] = dict(binary=binary, baseline=baseline, qm=qm, rq=rq)
     return ns
+
+
+def load_analysis() -> types.SimpleNamespace:
+    """The reference's inference wrapper (src/quantized_sae/inference/framework.py) and analysis script
+    (scripts/analysis/dynamic_analysis.py), unmodified. Both import the pre-refactor module names
+    (`SAEs.binary_SAE`, `sae_inference_framework`, ...): those are aliased to the shim-loaded modules."""
+    ns = load()
+    if "analysis" in _cache:
+        return _cache["analysis"]
+    mods = _cache["mods"]
+    saes = sys.modules["SAEs"]
+    for alias, mod in (("baseline_SAE", mods["baseline"]), ("binary_SAE", mods["binary"]),
+                       ("residual_quantized_matryoshka_SAE", mods["rq"])):
+        sys.modules[f"SAEs.{alias}"] = mod
+        setattr(saes, alias, mod)
+    fw = _exec(REFERENCE_ROOT / "src" / "quantized_sae" / "inference" / "framework.py", "sae_inference_framework")
+    da = _exec(REFERENCE_ROOT / "scripts" / "analysis" / "dynamic_analysis.py", "_ref_dynamic_analysis")
+    out = types.SimpleNamespace(framework=fw, dynamic_analysis=da, classes=ns)
+    _cache["analysis"] = out
+    return out

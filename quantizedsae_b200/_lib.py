@@ -43,6 +43,11 @@ SYMBOLS = {
     "qsae_pack_matryoshka": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "qsae_matryoshka_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
     "qsae_matryoshka_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "qsae_matryoshka_forward_active": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp,
+                                            _vp, _i, _vp, _vp, _sz, _vp]),
+    "qsae_activation_counts": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "qsae_coactivation": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "qsae_sq_error_accumulate": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "qsae_max_row_norm": (_i, [_vp, _i, _i, _vp, _vp]),
     "qsae_residual_update": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "qsae_unpack_matryoshka_t": (_i, [_vp, _i, _i, _vp, _vp]),
@@ -358,8 +363,10 @@ def decode_matryoshka_lists(lists, counts, cap, packed, scale, level_start, n_le
     return result, level_count
 
 
-def matryoshka_forward(x, w_bf16, b_enc, packed, scale, level_start, n_levels, dec_bias, w_f32=None, w_norm_max=None):
-    """-> (result [n_levels, B, D] f32, level_count [n_levels] int64, overflow [1] int32)"""
+def matryoshka_forward(x, w_bf16, b_enc, packed, scale, level_start, n_levels, dec_bias, w_f32=None, w_norm_max=None,
+                       active_cap: int = 0):
+    """-> (result [n_levels, B, D] f32, level_count [n_levels] int64, overflow [1] int32)
+    active_cap > 0: additionally (active_idx [B, active_cap] int32 with -1 in empty slots, active_cnt [B] int32)."""
     global launch_count
     _need_cuda(x, w_bf16, b_enc, packed, scale, level_start, dec_bias)
     B, D = x.shape
@@ -367,18 +374,50 @@ def matryoshka_forward(x, w_bf16, b_enc, packed, scale, level_start, n_levels, d
     result = torch.empty((n_levels, B, D), dtype=torch.float32, device=x.device)
     counts = torch.empty((n_levels,), dtype=torch.int64, device=x.device)
     overflow = torch.empty((1,), dtype=torch.int32, device=x.device)
+    a_idx = torch.empty((B, active_cap), dtype=torch.int32, device=x.device) if active_cap > 0 else None
+    a_cnt = torch.zeros((B,), dtype=torch.int32, device=x.device) if active_cap > 0 else None
     if B == 0:
-        return result, counts.zero_(), overflow.zero_()
+        out = (result, counts.zero_(), overflow.zero_())
+        return out + (a_idx, a_cnt) if active_cap > 0 else out
     n = _sz(0)
     check(load().qsae_matryoshka_workspace_bytes(B, H, D, C.byref(n)))
     ws = _workspace(x.device, int(n.value))
-    check(load().qsae_matryoshka_forward(x.data_ptr(), w_bf16.data_ptr(), _ptr(w_f32), _ptr(w_norm_max),
-                                         b_enc.data_ptr(), packed.data_ptr(),
-                                         scale.data_ptr(), level_start.data_ptr(), n_levels, _ptr(dec_bias), B, H, D,
-                                         result.data_ptr(), counts.data_ptr(), overflow.data_ptr(), ws.data_ptr(),
-                                         ws.numel(), _stream()))
+    check(load().qsae_matryoshka_forward_active(x.data_ptr(), w_bf16.data_ptr(), _ptr(w_f32), _ptr(w_norm_max),
+                                                b_enc.data_ptr(), packed.data_ptr(), scale.data_ptr(),
+                                                level_start.data_ptr(), n_levels, _ptr(dec_bias), B, H, D,
+                                                result.data_ptr(), counts.data_ptr(), overflow.data_ptr(),
+                                                _ptr(a_idx), active_cap, _ptr(a_cnt), ws.data_ptr(), ws.numel(), _stream()))
     launch_count += 4
-    return result, counts, overflow
+    return (result, counts, overflow, a_idx, a_cnt) if active_cap > 0 else (result, counts, overflow)
+
+
+def activation_counts(idx: torch.Tensor, vals: torch.Tensor | None, counts: torch.Tensor) -> None:
+    """counts [H] int64 += rows in which each latent is active (idx [B, cap] int32, -1 = empty; vals: active iff > 0)."""
+    global launch_count
+    _need_cuda(idx, vals, counts)
+    assert idx.dtype == torch.int32 and counts.dtype == torch.int64 and idx.dim() == 2
+    B, cap = idx.shape
+    check(load().qsae_activation_counts(idx.data_ptr(), _ptr(vals), B, cap, counts.numel(), counts.data_ptr(), _stream()))
+    launch_count += 1
+
+
+def coactivation(idx: torch.Tensor, vals: torch.Tensor | None, cooc: torch.Tensor) -> None:
+    """cooc [H, H] int32 += A^T A of the boolean activity described by the lists."""
+    global launch_count
+    _need_cuda(idx, vals, cooc)
+    assert idx.dtype == torch.int32 and cooc.dtype == torch.int32 and cooc.dim() == 2 and cooc.shape[0] == cooc.shape[1]
+    B, cap = idx.shape
+    check(load().qsae_coactivation(idx.data_ptr(), _ptr(vals), B, cap, cooc.shape[0], cooc.data_ptr(), _stream()))
+    launch_count += 1
+
+
+def sq_error_accumulate(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> None:
+    """out (device float64 scalar) += sum (a - b)^2."""
+    global launch_count
+    _need_cuda(a, b, out)
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and out.dtype == torch.float64 and a.numel() == b.numel()
+    check(load().qsae_sq_error_accumulate(a.data_ptr(), b.data_ptr(), a.numel(), out.data_ptr(), _stream()))
+    launch_count += 1
 
 
 def pack_ternary(w: torch.Tensor, threshold: float = 0.5, want_bf16: bool = True, want_rows: bool = False):

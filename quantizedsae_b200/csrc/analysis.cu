@@ -1,0 +1,112 @@
+// Sparse-native analysis consumers (scripts/analysis/dynamic_analysis.py:317-440 of the reference).
+// The reference densifies the activity of every batch into a [B, H] boolean mask and forms the
+// co-activation counts as a dense [H, B] x [B, H] matrix product (141 TFLOP per 65536-token batch at
+// H = 32768) that it ships to the CPU chunk by chunk. Here the active sets stay sparse -- idx [B, cap] with
+// ~k entries per row -- and the [H, H] int32 matrix stays resident in HBM (4.3 GB at H = 32768):
+// k^2 atomic increments per token instead of H^2 multiply-adds per token.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace qsae {
+
+namespace {
+
+__device__ __forceinline__ bool entry_active(const int32_t* idx, const float* vals, size_t e, int H) {
+  const int i = idx[e];
+  return i >= 0 && i < H && (vals == nullptr || vals[e] > 0.f);
+}
+
+// activation_counts[h] += number of rows in which h is active (dynamic_analysis.py:341)
+__global__ void __launch_bounds__(256)
+activation_counts_kernel(const int32_t* __restrict__ idx, const float* __restrict__ vals, size_t total, int H,
+                         unsigned long long* __restrict__ counts) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride)
+    if (entry_active(idx, vals, e, H)) atomicAdd(&counts[idx[e]], 1ull);
+}
+
+// coactivation[i, j] += 1 for every ordered pair (i, j) of latents active in the same row, i == j included
+// (A^T A of the boolean activity matrix, dynamic_analysis.py:344-345). One warp per row: the row's active
+// latents are compacted into shared memory, then lane j of the warp increments C[a_i, a_j] for each i.
+constexpr int kCoWarps = 4;
+constexpr int kCoCap = 2048;   // active latents per row held in shared memory
+
+__global__ void __launch_bounds__(kCoWarps * 32)
+coactivation_kernel(const int32_t* __restrict__ idx, const float* __restrict__ vals, int B, int cap, int H,
+                    int32_t* __restrict__ cooc) {
+  __shared__ int act[kCoWarps][kCoCap];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  for (int row = blockIdx.x * kCoWarps + warp; row < B; row += gridDim.x * kCoWarps) {
+    int n = 0;
+    for (int base = 0; base < cap; base += 32) {
+      const int e = base + lane;
+      const bool a = e < cap && entry_active(idx, vals, static_cast<size_t>(row) * cap + e, H);
+      const unsigned b = __ballot_sync(full, a);
+      const int pos = n + __popc(b & lt_mask);
+      if (a && pos < kCoCap) act[warp][pos] = idx[static_cast<size_t>(row) * cap + e];
+      n += __popc(b);
+    }
+    n = min(n, kCoCap);   // the launcher rejects cap > kCoCap
+    __syncwarp();
+    for (int i = 0; i < n; ++i) {
+      int32_t* crow = cooc + static_cast<size_t>(act[warp][i]) * H;
+      for (int j = lane; j < n; j += 32) atomicAdd(&crow[act[warp][j]], 1);
+    }
+    __syncwarp();
+  }
+}
+
+// *out += sum (a - b)^2 in fp64 (dynamic_analysis.py:96-100: mean squared reconstruction error numerator)
+__global__ void __launch_bounds__(256)
+sq_error_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, double* __restrict__ out) {
+  __shared__ double s[256];
+  double acc = 0.0;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += stride) {
+    const double d = static_cast<double>(a[e]) - static_cast<double>(b[e]);
+    acc += d * d;
+  }
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(out, s[0]);
+}
+
+}  // namespace
+
+const char* activation_counts_launch(const int32_t* idx, const float* vals, int B, int cap, int H,
+                                     unsigned long long* counts, cudaStream_t stream) {
+  const size_t total = static_cast<size_t>(B) * cap;
+  if (total == 0) return nullptr;
+  size_t g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  activation_counts_kernel<<<static_cast<int>(g), 256, 0, stream>>>(idx, vals, total, H, counts);
+  return cuda_err(cudaGetLastError());
+}
+
+const char* coactivation_launch(const int32_t* idx, const float* vals, int B, int cap, int H, int32_t* cooc,
+                                cudaStream_t stream) {
+  if (cap > kCoCap) return "coactivation: more than 2048 list entries per row";
+  if (B == 0 || cap == 0) return nullptr;
+  int blocks = (B + kCoWarps - 1) / kCoWarps;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  coactivation_kernel<<<blocks, kCoWarps * 32, 0, stream>>>(idx, vals, B, cap, H, cooc);
+  return cuda_err(cudaGetLastError());
+}
+
+const char* sq_error_launch(const float* a, const float* b, size_t n, double* out, cudaStream_t stream) {
+  if (n == 0) return nullptr;
+  size_t g = (n + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  sq_error_kernel<<<static_cast<int>(g), 256, 0, stream>>>(a, b, n, out);
+  return cuda_err(cudaGetLastError());
+}
+
+}  // namespace qsae

@@ -169,7 +169,8 @@ const char* decode_matryoshka_launch(const void* cand, const int* cand_cnt, int 
                                      int n_levels, int H, int D, const float* bias, float* result,
                                      unsigned long long* level_count, const float* x_f32, const float* w_f32,
                                      const float* b_enc, float thr_value, int exact, void* scratch, int num_sms,
-                                     cudaStream_t stream);
+                                     cudaStream_t stream, int32_t* active_idx = nullptr, int active_cap = 0,
+                                     int* active_cnt = nullptr);
 // scratch of decode_matryoshka_launch (per-warp activity counts before the final sum)
 size_t decode_matryoshka_scratch_bytes(int num_sms);
 // packed 2-bit codes [H, D/16] -> T^T as bf16 [D, H] with entries {-2, 0, +2} (B operand of the dense level GEMMs)
@@ -182,6 +183,13 @@ size_t matryoshka_dense_operand_scratch_bytes();
 const char* max_row_norm_launch(const float* w, int H, int D, float* out, cudaStream_t stream);
 const char* row_threshold_launch(const float* x, int B, int D, const float* wmax, float thr_value, float* thr,
                                  cudaStream_t stream);
+
+// analysis.cu: statistics over sparse active lists idx [B, cap] (entry < 0 = empty; with vals: active iff value > 0)
+const char* activation_counts_launch(const int32_t* idx, const float* vals, int B, int cap, int H,
+                                     unsigned long long* counts, cudaStream_t stream);
+const char* coactivation_launch(const int32_t* idx, const float* vals, int B, int cap, int H, int32_t* cooc,
+                                cudaStream_t stream);
+const char* sq_error_launch(const float* a, const float* b, size_t n, double* out, cudaStream_t stream);
 
 // encode_dense.cu
 const char* encode_dense_launch(const float* x, const int32_t* rows, int R, const float* w,

@@ -158,7 +158,9 @@ decode_matryoshka_kernel(const uint2* __restrict__ cand, const int* __restrict__
                          float* __restrict__ result /* [n_levels, B, D] */,
                          unsigned* __restrict__ count_partial /* [gridDim.x * kMatWarps, NL] */,
                          const float* __restrict__ x_f32, const float* __restrict__ w_f32,
-                         const float* __restrict__ b_enc, float thr_value, int exact) {
+                         const float* __restrict__ b_enc, float thr_value, int exact,
+                         int32_t* __restrict__ active_idx /* [B, active_cap] or null */, int active_cap,
+                         int* __restrict__ active_cnt /* [B] */) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned full = 0xffffffffu;
   const int words = D >> 4;                 // <= 32: lane `l` owns word l (features 16 l .. 16 l + 15)
@@ -183,6 +185,7 @@ decode_matryoshka_kernel(const uint2* __restrict__ cand, const int* __restrict__
       xr[c] = (exact && d < D) ? *reinterpret_cast<const float4*>(x_f32 + static_cast<size_t>(row) * D + d)
                                : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    int n_act = 0;   // warp-uniform: active latents of this row (exported for the analysis consumers)
     for (int s = 0; s < nsub; ++s) {
       const size_t slot = static_cast<size_t>(row) * nsub + s;
       const int c = min(cand_cnt[slot], cap);
@@ -210,6 +213,10 @@ decode_matryoshka_kernel(const uint2* __restrict__ cand, const int* __restrict__
             for (int o = 16; o > 0; o >>= 1) a0 += __shfl_xor_sync(full, a0, o);
             if (!(a0 + __ldg(b_enc + col) >= thr_value)) continue;
           }
+          if (active_idx != nullptr) {
+            if (lane == 0 && n_act < active_cap) active_idx[static_cast<size_t>(row) * active_cap + n_act] = col;
+            ++n_act;
+          }
           int lvl = 0;
 #pragma unroll
           for (int l = 1; l < NL; ++l) lvl += (col >= lstart[l]) ? 1 : 0;
@@ -232,6 +239,7 @@ decode_matryoshka_kernel(const uint2* __restrict__ cand, const int* __restrict__
         }
       }
     }
+    if (active_idx != nullptr && lane == 0) active_cnt[row] = n_act;
     // cumulative outputs: result[i] = bias + sum_{l <= i} acc[l]
     if (has_word) {
       float run[16];
@@ -328,7 +336,7 @@ const char* decode_matryoshka_launch(const void* cand, const int* cand_cnt, int 
                                      int n_levels, int H, int D, const float* bias, float* result,
                                      unsigned long long* level_count, const float* x_f32, const float* w_f32,
                                      const float* b_enc, float thr_value, int exact, void* scratch, int num_sms,
-                                     cudaStream_t stream) {
+                                     cudaStream_t stream, int32_t* active_idx, int active_cap, int* active_cnt) {
   if (n_levels > 8) return "decode_matryoshka: at most 8 levels (n_bits <= 8)";
   if (D > 512 || (D % 16) != 0) return "decode_matryoshka: D must be a multiple of 16, <= 512";
   int blocks = (B + kMatWarps - 1) / kMatWarps;
@@ -337,7 +345,7 @@ const char* decode_matryoshka_launch(const void* cand, const int* cand_cnt, int 
   const uint2* c2 = reinterpret_cast<const uint2*>(cand);
 #define QSAE_MAT(NL) \
   decode_matryoshka_kernel<NL><<<blocks, kMatWarps * 32, 0, stream>>>(c2, cand_cnt, nsub, cap, B, packed, scale, level_start, \
-      n_levels, H, D, bias, result, partial, x_f32, w_f32, b_enc, thr_value, exact)
+      n_levels, H, D, bias, result, partial, x_f32, w_f32, b_enc, thr_value, exact, active_idx, active_cap, active_cnt)
   int nl;
   if (n_levels <= 1) { nl = 1; QSAE_MAT(1); }
   else if (n_levels <= 2) { nl = 2; QSAE_MAT(2); }

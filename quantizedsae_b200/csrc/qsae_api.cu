@@ -642,7 +642,20 @@ int qsae_matryoshka_forward(const float* x_f32, const uint16_t* w_bf16, const fl
                             const float* scale, const int* level_start, int n_levels, const float* dec_bias,
                             int B, int H, int D, float* result, unsigned long long* level_count, int* overflow,
                             void* workspace, size_t workspace_bytes, void* stream) {
+  return qsae_matryoshka_forward_active(x_f32, w_bf16, w_f32, w_norm_max, b_enc, packed, scale, level_start, n_levels,
+                                        dec_bias, B, H, D, result, level_count, overflow, nullptr, 0, nullptr, workspace,
+                                        workspace_bytes, stream);
+}
+
+int qsae_matryoshka_forward_active(const float* x_f32, const uint16_t* w_bf16, const float* w_f32,
+                                   const float* w_norm_max, const float* b_enc, const uint32_t* packed,
+                                   const float* scale, const int* level_start, int n_levels, const float* dec_bias,
+                                   int B, int H, int D, float* result, unsigned long long* level_count, int* overflow,
+                                   int32_t* active_idx, int active_cap, int32_t* active_cnt, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
   if (B == 0) return QSAE_OK;
+  if (active_idx != nullptr && (active_cap < 1 || active_cnt == nullptr))
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_forward: active list export needs active_cap >= 1 and active_cnt");
   if (!x_f32 || !w_bf16 || !b_enc || !packed || !scale || !level_start || !result || !level_count || !overflow || !workspace)
     return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_forward: null pointer");
   if (n_levels < 1 || n_levels > 8) return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_forward: 1 <= n_levels <= 8");
@@ -673,10 +686,40 @@ int qsae_matryoshka_forward(const float* x_f32, const uint16_t* w_bf16, const fl
   el.overflow = overflow;
   rc = launch_status("encode kernel (threshold)", encode_topk_launch(x_bf16, w_bf16, el, st));
   if (rc != QSAE_OK) return rc;
+  if (active_idx != nullptr) {   // empty slots read as -1
+    ce = cudaMemsetAsync(active_idx, 0xFF, static_cast<size_t>(B) * active_cap * sizeof(int32_t), st);
+    if (ce != cudaSuccess) return fail(QSAE_ERR_CUDA, "matryoshka_forward: %s", cudaGetErrorString(ce));
+  }
   return launch_status("decode_matryoshka", decode_matryoshka_launch(el.cand, el.cand_cnt, mp.st.nsub, mp.st.cap, B, packed,
                                                                      scale, level_start, n_levels, H, D, dec_bias, result,
                                                                      level_count, x_f32, w_f32, b_enc, kActiveThreshold,
-                                                                     exact, ws + mp.scratch_off, num_sms(), st));
+                                                                     exact, ws + mp.scratch_off, num_sms(), st, active_idx,
+                                                                     active_cap, active_cnt));
+}
+
+// ---------------------------------------------------------------------------------------------
+// analysis consumers over sparse active lists (scripts/analysis/dynamic_analysis.py)
+// ---------------------------------------------------------------------------------------------
+int qsae_activation_counts(const int32_t* idx, const float* vals, int B, int cap, int H, unsigned long long* counts,
+                           void* stream) {
+  if (B < 0 || cap < 0 || H <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "activation_counts: bad shape");
+  if (B == 0 || cap == 0) return QSAE_OK;
+  if (!idx || !counts) return fail(QSAE_ERR_INVALID_ARGUMENT, "activation_counts: null pointer");
+  return launch_status("activation_counts", activation_counts_launch(idx, vals, B, cap, H, counts, S(stream)));
+}
+
+int qsae_coactivation(const int32_t* idx, const float* vals, int B, int cap, int H, int32_t* cooc, void* stream) {
+  if (B < 0 || cap < 0 || H <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "coactivation: bad shape");
+  if (cap > 2048) return fail(QSAE_ERR_INVALID_ARGUMENT, "coactivation: at most 2048 list entries per row, got %d", cap);
+  if (B == 0 || cap == 0) return QSAE_OK;
+  if (!idx || !cooc) return fail(QSAE_ERR_INVALID_ARGUMENT, "coactivation: null pointer");
+  return launch_status("coactivation", coactivation_launch(idx, vals, B, cap, H, cooc, S(stream)));
+}
+
+int qsae_sq_error_accumulate(const float* a, const float* b, size_t n, double* out, void* stream) {
+  if (n == 0) return QSAE_OK;
+  if (!a || !b || !out) return fail(QSAE_ERR_INVALID_ARGUMENT, "sq_error: null pointer");
+  return launch_status("sq_error", sq_error_launch(a, b, n, out, S(stream)));
 }
 
 // ---------------------------------------------------------------------------------------------

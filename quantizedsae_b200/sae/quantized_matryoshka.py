@@ -164,6 +164,36 @@ class QuantizedMatryoshkaSAE(SparseAutoencoder):
         self.last_path = "dense"
         return dec._finish(result, counts, None, x.shape[0])
 
+    def forward_active(self, x, active_cap: int = 256):
+        """forward(x) plus each row's active latents in sparse form, for the analysis consumers
+        (scripts/analysis/dynamic_analysis.py:30-73 builds a dense [B, H] mask from a second encoder pass).
+        -> dict(latent_groups, reconstruction_levels, level_counts int64 [n_bits],
+                active_idx [B, cap] int32 (-1 = empty, unordered), active_cnt [B] int32).
+        Sparse path only: a model whose rows overflow the survivor lists (~50 % active, untrained) has no
+        sparse active form and raises."""
+        x = require_cuda_input(x, self)
+        lin = self.encoder[0]
+        packed, scale = self.decoder._packed()
+        ls, _ = self.decoder._levels()
+        cap = max(32, int(active_cap))
+        while True:
+            result, counts, overflow, a_idx, a_cnt = _lib.matryoshka_forward(
+                x, self._w_bf16(), lin.bias.detach(), packed, scale, ls, self.n_bits,
+                self.decoder.bias.detach() if self.allow_bias else None,
+                w_f32=lin.weight.detach().contiguous() if self.exact else None,
+                w_norm_max=self._w_norm_max() if self.exact else None, active_cap=cap)
+            if int(overflow.item()) != 0:
+                raise RuntimeError("q_sae: rows with more active latents than the sparse path holds have no sparse "
+                                   "active-list form (dense activity); use model.encode(x) > 0.5")
+            need = int(a_cnt.max().item()) if a_cnt.numel() else 0
+            if need <= cap:
+                break
+            cap = 1 << (need - 1).bit_length()
+        self.last_path = "sparse"
+        groups, levels = self.decoder._finish(result, counts, overflow, x.shape[0])
+        return {"latent_groups": groups, "reconstruction_levels": levels, "level_counts": counts,
+                "active_idx": a_idx, "active_cnt": a_cnt}
+
     def forward(self, x):
         x = require_cuda_input(x, self)
         if self.dense_mode == "always":
