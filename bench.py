@@ -8,7 +8,7 @@
 
 A "step" is one forward of the hot path over one batch of synthetic activations:
 x [B,512] fp32 (resident in HBM) -> bf16 cast -> fused tcgen05 encoder + top-k -> merge -> packed
-int4 sparse decode -> (values, indices) [B,k] + reconstruction [B,512]. Weights are pre-packed
+int4 sparse decode -> (values, indices) [B,k] + reconstruction [B,512] (one call: qsae_bsae_forward). Weights are pre-packed
 (one-time cost, not in the step). Rows are independent, so N GPUs shard the batch with
 replicated weights and no collective on the data path ("scaling": "weak").
 Prints ONE JSON line on rank 0.
@@ -202,8 +202,7 @@ def run_b200(args, rank, world, local_rank):
 
     def step(i):
         x = xs[i % len(xs)]
-        vals, idx, _ = L.encode_topk(x, w_bf16, None, be, k, sample=sample)
-        recon = L.decode_int4(vals, idx, packed, H, D, qstep, bd)
+        vals, idx, _, recon = L.bsae_forward(x, w_bf16, None, be, k, packed, N_BITS, qstep, bd, sample=sample)
         return vals, idx, recon
 
     def barrier():

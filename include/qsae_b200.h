@@ -136,6 +136,18 @@ int qsae_encode_topk(const float* x_f32,      /* [B, D] device                  
                      int32_t* out_flags,       /* [B] or NULL                                */
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* BinarySAE.forward on device buffers in one call (sae/binary.py:91-103): qsae_encode_topk followed by the sparse
+ * decode of the packed dictionary (qsae_pack_bitplanes; n_bits <= 4: nibbles, else int8 rows),
+ * recon = qstep * sum_j v_j dict[idx_j, :] + dec_bias. Same workspace as qsae_encode_topk.
+ * (Measured and rejected: decoding a row inside the merge warp that has just sorted it. The merged kernel took
+ * exactly the sum of the two, 325 us vs 154 + 171 us at B = 65536: the row phases of the resident warps do not
+ * interleave enough to hide the merge's list latency behind the decode's integer work.) */
+int qsae_bsae_forward(const float* x_f32, const uint16_t* w_bf16, const float* w_f32, const float* b_enc,
+                      const uint16_t* w_sample, const float* b_sample, int n_sample, int B, int H, int D, int k,
+                      int exact, const uint8_t* packed, int n_bits, float qstep, const float* dec_bias /* [D] or NULL */,
+                      float* out_vals /* [B, k] */, int32_t* out_idx /* [B, k] */, int32_t* out_flags /* [B] or NULL */,
+                      float* recon /* [B, D] */, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Exact fp32 CUDA-core encoder for a few rows: z[r, :] = x[rows[r], :] W^T + b (+act), dense
  * [R, H] output. Fallback for rows flagged by qsae_encode_topk(exact=1) and GPU-side
  * cross-check in the tests. Not a throughput path. */

@@ -33,6 +33,8 @@ SYMBOLS = {
     "qsae_prepare_encoder_sample": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "qsae_set_encode_kernel_events": (_i, [_vp, _vp]),
     "qsae_encode_topk": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "qsae_bsae_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp,
+                               _sz, _vp]),
     "qsae_encode_dense_tc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "qsae_encode_dense_f32": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "qsae_topk_dense_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
@@ -212,11 +214,17 @@ def prepare_sample(w_bf16: torch.Tensor, b_enc: torch.Tensor, n_sample: int | No
 _ws_cache: dict = {}
 
 
+_WS_ALIGN = 1024   # the TMA-fed kernels want 1024-byte aligned workspaces; torch's small-block pool gives 512
+
+
 def _workspace(device, nbytes: int) -> torch.Tensor:
+    """Per (device, stream) scratch buffer, grown on demand, 1024-byte aligned."""
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        raw = torch.empty(nbytes + _WS_ALIGN, dtype=torch.uint8, device=device)
+        off = (-raw.data_ptr()) % _WS_ALIGN
+        ws = raw[off:off + nbytes]
         _ws_cache[key] = ws
     return ws
 
@@ -243,6 +251,32 @@ def encode_topk(x: torch.Tensor, w_bf16: torch.Tensor, w_f32: torch.Tensor | Non
                                   idx.data_ptr(), _ptr(flags), ws.data_ptr(), ws.numel(), _stream()))
     launch_count += 3 if n_s == 0 else 8
     return vals, idx, flags
+
+
+def bsae_forward(x: torch.Tensor, w_bf16: torch.Tensor, w_f32: torch.Tensor | None, b_enc: torch.Tensor, k: int,
+                 packed: torch.Tensor, n_bits: int, qstep: float, dec_bias: torch.Tensor | None, exact: bool = False,
+                 want_flags: bool = False, sample=None):
+    """BinarySAE.forward on device buffers -> (vals [B,k], idx [B,k], flags | None, recon [B,D])."""
+    global launch_count
+    _need_cuda(x, w_bf16, w_f32, b_enc, packed, dec_bias)
+    B, D = x.shape
+    H = w_bf16.shape[0]
+    assert x.dtype == torch.float32 and w_bf16.dtype == torch.bfloat16 and b_enc.dtype == torch.float32
+    vals = torch.empty((B, k), dtype=torch.float32, device=x.device)
+    idx = torch.empty((B, k), dtype=torch.int32, device=x.device)
+    recon = torch.empty((B, D), dtype=torch.float32, device=x.device)
+    flags = torch.empty((B,), dtype=torch.int32, device=x.device) if want_flags else None
+    if B == 0:
+        return vals, idx, flags, recon
+    w_s, b_s = sample if sample is not None else (None, None)
+    n_s = 0 if w_s is None else w_s.shape[0]
+    ws = _workspace(x.device, encode_topk_workspace_bytes(B, H, D, k, n_s))
+    check(load().qsae_bsae_forward(x.data_ptr(), w_bf16.data_ptr(), _ptr(w_f32), b_enc.data_ptr(), _ptr(w_s), _ptr(b_s),
+                                   n_s, B, H, D, k, 1 if exact else 0, packed.data_ptr(), n_bits, float(qstep),
+                                   _ptr(dec_bias), vals.data_ptr(), idx.data_ptr(), _ptr(flags), recon.data_ptr(),
+                                   ws.data_ptr(), ws.numel(), _stream()))
+    launch_count += 4 if n_s == 0 else 10
+    return vals, idx, flags, recon
 
 
 def encode_dense_tc(x: torch.Tensor, w_bf16: torch.Tensor, b_enc: torch.Tensor, act: int = ACT_NONE) -> torch.Tensor:

@@ -30,7 +30,7 @@ constexpr int kDecWarps = 4;
 // independent, deterministic); the only rounding is that of v_j to >= 18 fractional bits of max|v|.
 // WPL = 32-bit words (8 features each) per lane, read as one vector load: lane l owns the features
 // [8 WPL l, 8 WPL (l + 1)) -- D <= 256 WPL. FULL: D == 256 WPL exactly, no per-word guards.
-template <int WPL, bool FULL>
+template <int WPL, bool FULL, bool RANGE>
 __global__ void __launch_bounds__(kDecWarps * 32)
 decode_int4_kernel(const float* __restrict__ vals, const int32_t* __restrict__ idx, int B, int k,
                    const uint32_t* __restrict__ packed, int H, int D, float scale,
@@ -80,10 +80,12 @@ decode_int4_kernel(const float* __restrict__ vals, const int32_t* __restrict__ i
     const int my_f = mine ? __float2int_rn(vrow[e] * to_fixed) : 0;
     my_i = mine ? my_i : 0;
     const int m = min(32, k - base);
-    const unsigned owned = __ballot_sync(full, mine);   // dictionary shards own ~1 / G of the winners: skip the rest
+    // dictionary shards own ~1 / G of the winners: skip the rest (warp-uniform test; RANGE is a template
+    // flag because the test costs the plain decoder 10 % of its issue slots)
+    const unsigned owned = RANGE ? __ballot_sync(full, mine) : 0xffffffffu;
 #pragma unroll 4
     for (int j = 0; j < m; ++j) {
-      if (((owned >> j) & 1u) == 0u) continue;          // warp-uniform
+      if (RANGE && ((owned >> j) & 1u) == 0u) continue;
       const int vf = __shfl_sync(full, my_f, j);
       const int i = __shfl_sync(full, my_i, j);
       vsum += vf;
@@ -221,11 +223,19 @@ const char* pack_candidates_launch(const float* vals, const int32_t* idx, size_t
 
 const char* decode_int4_launch(const float* vals, const int32_t* idx, int B, int k,
                                const uint8_t* packed, int H, int D, float scale, const float* bias,
-                               float* recon, int idx_offset, cudaStream_t stream) {
+                               float* recon, int idx_offset, cudaStream_t stream, bool skip_unowned) {
   const int blocks = (B + kDecWarps - 1) / kDecWarps;
   const uint32_t* p32 = reinterpret_cast<const uint32_t*>(packed);
-#define QSAE_DEC4(WPL, FULL) \
-  decode_int4_kernel<WPL, FULL><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, p32, H, D, scale, bias, recon, idx_offset)
+  const bool range = skip_unowned || idx_offset != 0;   // dictionary shards skip the winners other shards own
+#define QSAE_DEC4(WPL, FULL)                                                                                          \
+  do {                                                                                                                \
+    if (range)                                                                                                        \
+      decode_int4_kernel<WPL, FULL, true><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, p32, H, D, scale,   \
+                                                                                 bias, recon, idx_offset);            \
+    else                                                                                                              \
+      decode_int4_kernel<WPL, FULL, false><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, p32, H, D, scale,  \
+                                                                                  bias, recon, idx_offset);           \
+  } while (0)
   const bool aligned = (reinterpret_cast<uintptr_t>(packed) & 15) == 0;
   if (D == 256) QSAE_DEC4(1, true);
   else if (D == 512 && aligned) QSAE_DEC4(2, true);

@@ -148,7 +148,7 @@ const char* pack_ternary_launch(const float* w, int D, int H, float threshold, u
 // idx_offset: the dictionary holds latents [idx_offset, idx_offset + H); other entries are skipped
 const char* decode_int4_launch(const float* vals, const int32_t* idx, int B, int k,
                                const uint8_t* packed, int H, int D, float scale, const float* bias,
-                               float* recon, int idx_offset, cudaStream_t stream);
+                               float* recon, int idx_offset, cudaStream_t stream, bool skip_unowned = false);
 const char* decode_int8_launch(const float* vals, const int32_t* idx, int B, int k,
                                const int8_t* rows, int H, int D, float scale, const float* bias,
                                float* recon, int idx_offset, cudaStream_t stream);

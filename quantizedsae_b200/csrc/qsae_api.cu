@@ -446,7 +446,10 @@ int qsae_prepare_encoder_sample(const uint16_t* w_bf16, const float* b_enc, int 
   return launch_status("sample_rows", sample_rows_launch(w_bf16, b_enc, H, D, n_sample, w_sample, b_sample, S(stream)));
 }
 
-int qsae_encode_topk(const float* x_f32, const uint16_t* w_bf16, const float* w_f32, const float* b_enc,
+}  // extern "C"
+
+namespace {
+int encode_topk_impl(const float* x_f32, const uint16_t* w_bf16, const float* w_f32, const float* b_enc,
                      const uint16_t* w_sample, const float* b_sample, int n_sample,
                      int B, int H, int D, int k, int act, int exact, float* out_vals, int32_t* out_idx,
                      int32_t* out_flags, void* workspace, size_t workspace_bytes, void* stream) {
@@ -545,6 +548,33 @@ int qsae_encode_topk(const float* x_f32, const uint16_t* w_bf16, const float* w_
   rl.rescue_count = counters; rl.rescue_rows = rescue_rows;
   rl.out_vals = out_vals; rl.out_idx = out_idx; rl.out_flags = out_flags;
   return launch_status("rescue kernel", rescue_rows_launch(rl, num_sms(), st));
+}
+}  // namespace
+
+extern "C" {
+
+int qsae_encode_topk(const float* x_f32, const uint16_t* w_bf16, const float* w_f32, const float* b_enc,
+                     const uint16_t* w_sample, const float* b_sample, int n_sample,
+                     int B, int H, int D, int k, int act, int exact, float* out_vals, int32_t* out_idx,
+                     int32_t* out_flags, void* workspace, size_t workspace_bytes, void* stream) {
+  return encode_topk_impl(x_f32, w_bf16, w_f32, b_enc, w_sample, b_sample, n_sample, B, H, D, k, act, exact, out_vals,
+                          out_idx, out_flags, workspace, workspace_bytes, stream);
+}
+
+int qsae_bsae_forward(const float* x_f32, const uint16_t* w_bf16, const float* w_f32, const float* b_enc,
+                      const uint16_t* w_sample, const float* b_sample, int n_sample, int B, int H, int D, int k,
+                      int exact, const uint8_t* packed, int n_bits, float qstep, const float* dec_bias,
+                      float* out_vals, int32_t* out_idx, int32_t* out_flags, float* recon, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  if (B == 0) return QSAE_OK;
+  if (!packed || !recon) return fail(QSAE_ERR_INVALID_ARGUMENT, "bsae_forward: null pointer");
+  if (n_bits < 1 || n_bits > 8) return fail(QSAE_ERR_INVALID_ARGUMENT, "bsae_forward: 1 <= n_bits <= 8");
+  int rc = encode_topk_impl(x_f32, w_bf16, w_f32, b_enc, w_sample, b_sample, n_sample, B, H, D, k, QSAE_ACT_NONE, exact,
+                            out_vals, out_idx, out_flags, workspace, workspace_bytes, stream);
+  if (rc != QSAE_OK) return rc;
+  if (n_bits <= 4) return qsae_decode_int4(out_vals, out_idx, B, k, packed, H, D, qstep, dec_bias, recon, stream);
+  return qsae_decode_int8(out_vals, out_idx, B, k, reinterpret_cast<const int8_t*>(packed), H, D, qstep, dec_bias, recon,
+                          stream);
 }
 
 int qsae_encode_dense_tc(const float* x_f32, const uint16_t* w_bf16, const float* b_enc, int B, int H, int D,
@@ -1092,7 +1122,7 @@ int qsae_decode_int4_range(const float* vals, const int32_t* idx, int B, int k, 
   int rc = check_decode("decode_int4_range", vals, idx, packed_shard, recon, B, k, shard_latents, D, 8);
   if (rc != QSAE_OK || B == 0) return rc;
   return launch_status("decode_int4", decode_int4_launch(vals, idx, B, k, packed_shard, shard_latents, D, scale, bias, recon,
-                                                         idx_begin, S(stream)));
+                                                         idx_begin, S(stream), true));
 }
 
 int qsae_decode_int8_range(const float* vals, const int32_t* idx, int B, int k, const int8_t* rows_shard,
@@ -1226,14 +1256,9 @@ int qsae_bsae_forward_host(qsae_bsae_plan* p, const float* x_host, int B, float*
                                     static_cast<size_t>(rows) * p->D * 4, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) { rc = fail(QSAE_ERR_CUDA, "forward_host H2D: %s", cudaGetErrorString(e)); break; }
     if (trace && c < kTraceMax) cudaEventRecord(tev[c][1], st);
-    rc = qsae_encode_topk(sl.x, p->w_bf16, p->w_f32, p->b_enc, p->w_sample, p->b_sample, p->n_sample, rows, p->H,
-                          p->D, p->k, QSAE_ACT_NONE, 0, sl.vals, sl.idx, nullptr, sl.ws, sl.ws_bytes, st);
-    if (rc != QSAE_OK) break;
-    if (p->n_bits <= 4)
-      rc = qsae_decode_int4(sl.vals, sl.idx, rows, p->k, p->packed, p->H, p->D, p->qstep, p->dec_bias, sl.recon, st);
-    else
-      rc = qsae_decode_int8(sl.vals, sl.idx, rows, p->k, reinterpret_cast<const int8_t*>(p->packed), p->H, p->D,
-                            p->qstep, p->dec_bias, sl.recon, st);
+    rc = qsae_bsae_forward(sl.x, p->w_bf16, p->w_f32, p->b_enc, p->w_sample, p->b_sample, p->n_sample, rows, p->H, p->D,
+                           p->k, 0, p->packed, p->n_bits, p->qstep, p->dec_bias, sl.vals, sl.idx, nullptr, sl.recon, sl.ws,
+                           sl.ws_bytes, st);
     if (rc != QSAE_OK) break;
     if (trace && c < kTraceMax) cudaEventRecord(tev[c][2], st);
     e = cudaMemcpyAsync(vals_host + static_cast<size_t>(r0) * p->k, sl.vals, static_cast<size_t>(rows) * p->k * 4,

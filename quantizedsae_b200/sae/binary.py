@@ -174,7 +174,19 @@ class BinarySAE(SparseAutoencoder):
         return SparseLatents(vals, idx, (x.shape[0], self.hidden_dim))
 
     def forward(self, x):
-        latents = self.encode_topk(x)
-        recon = self.decoder.decode_sparse(latents)
+        if self.decoder.resolved_mode() == "int":
+            # packed dictionary: encoder + top-k + sparse decode behind one C-ABI call (qsae_bsae_forward)
+            x = require_cuda_input(x, self)
+            lin, dec = self.encoder[0], self.decoder
+            w32 = lin.weight.detach().contiguous()
+            vals, idx, flags, recon = _lib.bsae_forward(
+                x, self._w_bf16(), w32 if self.exact else None, lin.bias.detach(), int(self.hidden_dim * self.k),
+                dec._packed()[0], self.n_bits, dec.quantization_step, dec.bias.detach(), exact=self.exact,
+                want_flags=self.exact, sample=self._sample())
+            self.last_flags = flags
+            latents = SparseLatents(vals, idx, (x.shape[0], self.hidden_dim))
+        else:
+            latents = self.encode_topk(x)
+            recon = self.decoder.decode_sparse(latents)
         out_latent = latents.to_dense() if self.return_dense else latents
         return out_latent, recon, self.decoder.polarize_loss()

@@ -404,6 +404,41 @@ def test_prior_failure_is_rescued_exactly(cuda_device):
         assert int((flags != 0).sum()) == 0          # rescued rows are exact by construction
 
 
+@pytest.mark.parametrize("B,H,D,k,n_bits,exact", [
+    (1000, 32768, 512, 32, 4, False), (700, 32768, 512, 65, 4, False), (300, 32768, 512, 32, 4, True),
+    (513, 16384, 512, 200, 4, False),      # rows spill into the tier-2 / block-level merge kernels
+    (200, 16384, 256, 32, 4, False),
+    (150, 8192, 512, 16, 8, False),        # int8 dictionary
+    (90, 2048, 512, 8, 4, False),          # no sampled prior
+])
+def test_bsae_forward_entry_is_bit_identical_to_the_two_calls(cuda_device, B, H, D, k, n_bits, exact):
+    """qsae_bsae_forward (one call) vs qsae_encode_topk + qsae_decode_int4/int8."""
+    x, W, b = _enc_case(B, H, D, 500 + k, bf16=not exact)
+    rng = np.random.default_rng(k)
+    dx, dW, db = T(x, cuda_device), T(W, cuda_device), T(b, cuda_device)
+    wb = L.cast_bf16(dW)
+    sample = L.prepare_sample(wb, db)
+    bd = T(rng.standard_normal(D).astype(np.float32), cuda_device)
+    if n_bits <= 4:
+        packed = torch.randint(0, 256, (H, D // 2), dtype=torch.uint8, device=cuda_device)
+        dec = L.decode_int4
+    else:
+        packed = torch.randint(-128, 128, (H, D), dtype=torch.int8, device=cuda_device)
+        dec = L.decode_int8
+    v0, i0, f0 = L.encode_topk(dx, wb, dW if exact else None, db, k, exact=exact, want_flags=True, sample=sample)
+    r0 = dec(v0, i0, packed, H, D, 0.5, bd)
+    v1, i1, f1, r1 = L.bsae_forward(dx, wb, dW if exact else None, db, k, packed, n_bits, 0.5, bd, exact=exact,
+                                    want_flags=True, sample=sample)
+    assert torch.equal(i0, i1) and torch.equal(v0, v1) and torch.equal(f0, f1)
+    assert torch.equal(r0, r1)
+    if sample is not None:    # a failed prior sends every row through the rescue kernel + listed-rows decode
+        ws, bs = sample
+        v2, i2, _, r2 = L.bsae_forward(dx, wb, dW if exact else None, db, k, packed, n_bits, 0.5, bd, exact=exact,
+                                       sample=(ws, bs + 100.0))
+        assert_topk_matches(v2.cpu().numpy(), i2.cpu().numpy(), O.encode_pre(x, W, b), k)
+        assert torch.equal(dec(v2, i2, packed, H, D, 0.5, bd), r2)
+
+
 # ------------------------------------------------------------------------------------------
 # k > QSAE_MAX_K: block-level radix select (reference default k = int(0.002 H) = 2097 at H = 2^20)
 # ------------------------------------------------------------------------------------------
