@@ -336,10 +336,16 @@ int qsae_pack_candidates(const float* vals, const int32_t* idx, size_t n, void* 
 
 int qsae_merge_candidates_workspace_bytes(int B, size_t* bytes);
 /* cand_all: [n_shards][B][k_in] entries, shard-local indices; entry (s, b, j) stands for the global
- * latent s * shard_latents + index. out_*: [B, k_out], k_out <= n_shards * k_in, k_out <= QSAE_MAX_K_LARGE. */
+ * latent s * shard_latents + index. out_*: [B, k_out], k_out <= n_shards * k_in, k_out <= QSAE_MAX_K_LARGE.
+ * incomplete (device int32, or NULL): for TRUNCATED lists -- every shard sent only its k_in < k_out best
+ * candidates (a shard owns ~k_out / n_shards of the winners, so k_out / n_shards + 6 sigma is almost always
+ * enough and cuts the all-gather and the merge input by ~n_shards / 1.5). *incomplete is set to 1 when, for
+ * some row, ALL k_in entries of some shard were selected: that shard may hold further winners it did not send,
+ * and the caller must repeat the exchange with the shards' full candidate lists. 0 = the result is the exact
+ * global top-k. Every rank merges the same gathered tensor, so all ranks see the same flag. */
 int qsae_merge_candidates(const void* cand_all, int n_shards, int B, int k_in, int shard_latents, int k_out,
-                          float* out_vals, int32_t* out_idx, void* workspace, size_t workspace_bytes,
-                          void* stream);
+                          float* out_vals, int32_t* out_idx, int32_t* incomplete, void* workspace,
+                          size_t workspace_bytes, void* stream);
 
 /* qsae_decode_int4 / qsae_decode_int8 restricted to the latents [idx_begin, idx_begin + shard_latents)
  * held in `packed_shard` / `rows_shard` (global indices in idx; others are skipped). */

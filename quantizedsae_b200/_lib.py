@@ -67,7 +67,7 @@ SYMBOLS = {
     "qsae_tsae_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "qsae_pack_candidates": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "qsae_merge_candidates_workspace_bytes": (_i, [_i, C.POINTER(_sz)]),
-    "qsae_merge_candidates": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "qsae_merge_candidates": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "qsae_decode_int4_range": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
     "qsae_decode_int8_range": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
     "qsae_densify": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
@@ -542,23 +542,26 @@ def pack_candidates(vals: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def merge_candidates(cand_all: torch.Tensor, shard_latents: int, k_out: int):
-    """cand_all [G, B, k_in, 2] int32 (gathered pack_candidates outputs) -> global (vals, idx) [B, k_out]."""
+def merge_candidates(cand_all: torch.Tensor, shard_latents: int, k_out: int, truncated: bool = False):
+    """cand_all [G, B, k_in, 2] int32 (gathered pack_candidates outputs) -> global (vals, idx) [B, k_out].
+    truncated=True (the shards sent fewer candidates than they hold): -> (vals, idx, incomplete [1] int32);
+    incomplete != 0 means some shard's list was used up and the exchange must be repeated with full lists."""
     global launch_count
     _need_cuda(cand_all)
     G, B, k_in, two = cand_all.shape
     assert two == 2 and cand_all.dtype == torch.int32
     vals = torch.empty((B, k_out), dtype=torch.float32, device=cand_all.device)
     idx = torch.empty((B, k_out), dtype=torch.int32, device=cand_all.device)
+    flag = torch.zeros((1,), dtype=torch.int32, device=cand_all.device) if truncated else None
     if B == 0:
-        return vals, idx
+        return (vals, idx, flag) if truncated else (vals, idx)
     n = _sz(0)
     check(load().qsae_merge_candidates_workspace_bytes(B, C.byref(n)))
     ws = _workspace(cand_all.device, int(n.value))
     check(load().qsae_merge_candidates(cand_all.data_ptr(), G, B, k_in, shard_latents, k_out, vals.data_ptr(),
-                                       idx.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+                                       idx.data_ptr(), _ptr(flag), ws.data_ptr(), ws.numel(), _stream()))
     launch_count += 2
-    return vals, idx
+    return (vals, idx, flag) if truncated else (vals, idx)
 
 
 def decode_range(vals, idx, dict_shard, shard_latents: int, idx_begin: int, D: int, scale: float, bias, n_bits: int):

@@ -1087,7 +1087,8 @@ int qsae_merge_candidates_workspace_bytes(int B, size_t* bytes) {
 }
 
 int qsae_merge_candidates(const void* cand_all, int n_shards, int B, int k_in, int shard_latents, int k_out,
-                          float* out_vals, int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream) {
+                          float* out_vals, int32_t* out_idx, int32_t* incomplete, void* workspace, size_t workspace_bytes,
+                          void* stream) {
   if (B == 0) return QSAE_OK;
   if (!cand_all || !out_vals || !out_idx || !workspace) return fail(QSAE_ERR_INVALID_ARGUMENT, "merge_candidates: null pointer");
   if (n_shards < 1 || n_shards > 32 || k_in < 1 || k_out < 1 || shard_latents < 1)
@@ -1111,7 +1112,13 @@ int qsae_merge_candidates(const void* cand_all, int n_shards, int B, int k_in, i
   sl.out_vals = out_vals; sl.out_idx = out_idx;
   // every row has exactly n_shards * k_in candidates: pick the tier that holds them
   const long long n_cand = static_cast<long long>(n_shards) * k_in;
-  if (n_cand > 1024 || k_out > kMaxK) return launch_status("select_topk kernel", select_topk_launch(sl, st));
+  if (incomplete != nullptr) {   // truncated lists (k_in < the shards' full candidate count): completeness check
+    ce = cudaMemsetAsync(incomplete, 0, sizeof(int32_t), st);
+    if (ce != cudaSuccess) return fail(QSAE_ERR_CUDA, "merge_candidates: %s", cudaGetErrorString(ce));
+    sl.incomplete = incomplete;
+  }
+  if (n_cand > 1024 || k_out > kMaxK || incomplete != nullptr)
+    return launch_status("select_topk kernel", select_topk_launch(sl, st));
   const int tier = n_cand <= 256 ? 8 : (n_cand <= 512 ? 16 : 32);
   return launch_status("select_small kernel", select_small_launch(sl, tier, nullptr, nullptr, num_sms(), counters + 1, ovf_rows, st));
 }

@@ -37,6 +37,7 @@ template <int THREADS>
 __device__ __forceinline__ void select_row_block(const SelectLaunch& p, int row, int n_max, int ksort,
                                                  uint8_t* sel_smem) {
   __shared__ int s_n, s_out, s_ovf;
+  __shared__ unsigned long long s_listmin[32];   // smallest composite key of each list (incomplete-list check)
   __shared__ int s_hist[256];
   __shared__ int s_ctl[4];
   __shared__ unsigned s_worst_key, s_dev_key;
@@ -72,6 +73,7 @@ __device__ __forceinline__ void select_row_block(const SelectLaunch& p, int row,
     if (lane == 0 && p.cand_cnt != nullptr && p.cand_cnt[slot] > p.cap - 32) s_ovf = 1;
     const uint2* src = cand + slot * p.cap;
     const uint32_t col_add = static_cast<uint32_t>(s) * static_cast<uint32_t>(p.sub_col_offset);
+    uint64_t lmin = ~0ull;
     for (int base = 0; base < c; base += 32 * BATCH) {
       uint2 t[BATCH];
 #pragma unroll
@@ -88,9 +90,18 @@ __device__ __forceinline__ void select_row_block(const SelectLaunch& p, int row,
           int pos = 0;
           if (lane == 0) pos = atomicAdd(&s_n, __popc(b));
           pos = __shfl_sync(full, pos, 0) + __popc(b & lt_mask);
-          if (keep) keys[pos] = make_sort_key(__uint_as_float(t[i].x), t[i].y + col_add);
+          if (keep) {
+            const uint64_t key = make_sort_key(__uint_as_float(t[i].x), t[i].y + col_add);
+            keys[pos] = key;
+            lmin = min(lmin, key);
+          }
         }
       }
+    }
+    if (p.incomplete != nullptr && s < 32) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lmin = min(lmin, __shfl_xor_sync(full, lmin, o));
+      if (lane == 0) s_listmin[s] = lmin;
     }
   }
   __syncthreads();
@@ -125,6 +136,11 @@ __device__ __forceinline__ void select_row_block(const SelectLaunch& p, int row,
   __syncthreads();
   const int out = min(s_out, ksort);
   for (int e = out + threadIdx.x; e < ksort; e += THREADS) sel[e] = 0ull;
+  // truncated lists: a list whose every entry was selected may be hiding further winners (conservative: also
+  // fires when the list's last entry is exactly the k-th)
+  if (p.incomplete != nullptr && threadIdx.x < p.nsub && threadIdx.x < 32 && s_listmin[threadIdx.x] >= T &&
+      s_listmin[threadIdx.x] != ~0ull)
+    atomicExch(p.incomplete, 1);
   __syncthreads();
 
   // ---- optional exact fp32 re-scoring, candidates spread over the warps

@@ -6,6 +6,8 @@ logits decoder.weight; decoder.bias and the input batch x are replicated. One fo
 
     local fused encoder + top-k over the shard  (tcgen05 kernel, shard-local indices)
     all-gather of the (value, index) candidates  -> [G, B, k] on every rank            (collective 1)
+        (large k: k / G + 6 sigma candidates per shard first; the merge verifies that no shard ran out of
+         candidates and the exchange is repeated with the full k only then -- ShardPlan.k_send)
     merge to the global top-k, (value desc, global index asc): identical on every rank
     sparse decode of the winners this shard owns -> partial reconstruction [B, D]
     reduce-scatter(sum) of the partials          -> this rank's B/G rows of the result (collective 2)
@@ -20,6 +22,7 @@ no CPU fallback in the product: CudaShardOps raises on non-CUDA tensors.
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass
 
 import torch
@@ -58,6 +61,17 @@ class ShardPlan:
     def k_local(self, k: int) -> int:
         """Candidates each shard contributes: its own top-min(k, shard size) contains every global winner it owns."""
         return min(k, self.shard_latents)
+
+    def k_send(self, k: int, min_k: int = 256) -> int:
+        """Candidates a shard sends in the first exchange round. A shard owns ~k / G of a row's winners (latents are
+        not ordered by importance), so for large k its top k / G + 6 sqrt(k / G) + 16 almost always covers its share:
+        2097 -> 376 per shard at G = 8, which cuts the all-gather and the merge input 5.6x. The merge verifies it
+        (a shard whose whole list was selected may hold more) and the exchange is repeated with k_local on failure."""
+        kl = self.k_local(k)
+        if self.world_size == 1 or k < min_k:
+            return kl
+        share = k / self.world_size
+        return min(kl, int(math.ceil(share + 6.0 * math.sqrt(share) + 16)))
 
     def padded_batch(self, batch: int) -> int:
         """reduce-scatter needs equal row blocks: the batch is padded to a multiple of the world size."""
@@ -111,8 +125,8 @@ class CudaShardOps:
                                         _lib.ACT_NONE, self.m.exact, sample=self._sample())
         return _lib.pack_candidates(vals, idx)
 
-    def merge(self, cand_all: torch.Tensor, shard_latents: int, k: int):
-        return _lib.merge_candidates(cand_all, shard_latents, k)
+    def merge(self, cand_all: torch.Tensor, shard_latents: int, k: int, truncated: bool = False):
+        return _lib.merge_candidates(cand_all, shard_latents, k, truncated=truncated)
 
     def decode_partial(self, vals, idx, plan: ShardPlan, with_bias: bool) -> torch.Tensor:
         packed, _, gap = self._packed()
@@ -163,6 +177,8 @@ class DictionaryShardedBinarySAE(nn.Module):
         self.exact = True
         self.gather_output = False
         self.polar_tol = 1e-6
+        self.trim_min_k = 256                # k below this: every shard sends its full top-k (tiny anyway)
+        self.last_exchange = None            # "truncated" / "full": which candidate exchange produced the last forward
         self._pol_cache = None
         # ops=False defers the choice (tests install their own backend after construction)
         self.ops = CudaShardOps(self) if ops is None else (ops or None)
@@ -221,9 +237,21 @@ class DictionaryShardedBinarySAE(nn.Module):
         if k > self.hidden_dim:
             raise RuntimeError(f"selected index k out of range (k={k} > H={self.hidden_dim})")
         plan = self.plan
-        cand = self.ops.local_candidates(x, plan.k_local(k))                  # [B, k_loc, 2]
-        cand_all = self._all_gather(cand)                                     # [G, B, k_loc, 2]
-        vals, idx = self.ops.merge(cand_all, plan.shard_latents, k)           # global top-k, same on all ranks
+        k_loc, k_snd = plan.k_local(k), plan.k_send(k, self.trim_min_k)
+        self.last_exchange = "full"
+        vals = None
+        if k_snd < k_loc:
+            # round 1: truncated lists; every rank merges the same tensor and therefore sees the same verdict
+            cand_all = self._all_gather(self.ops.local_candidates(x, k_snd))  # [G, B, k_snd, 2]
+            vals, idx, incomplete = self.ops.merge(cand_all, plan.shard_latents, k, truncated=True)
+            if int(incomplete.item()) != 0:
+                vals = None                                                   # some shard ran out of candidates
+            else:
+                self.last_exchange = "truncated"
+        if vals is None:
+            cand = self.ops.local_candidates(x, k_loc)                        # [B, k_loc, 2]
+            cand_all = self._all_gather(cand)                                 # [G, B, k_loc, 2]
+            vals, idx = self.ops.merge(cand_all, plan.shard_latents, k)       # global top-k, same on all ranks
         partial = self.ops.decode_partial(vals, idx, plan, with_bias=(plan.rank == 0))
         rows = self._reduce_scatter_rows(partial)
         if self.gather_output and plan.world_size > 1:

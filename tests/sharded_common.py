@@ -34,7 +34,7 @@ class NumpyShardOps:
         out[..., 1] = idx
         return torch.from_numpy(out)
 
-    def merge(self, cand_all, shard_latents, k):
+    def merge(self, cand_all, shard_latents, k, truncated=False):
         c = cand_all.numpy()
         G, B, kin, _ = c.shape
         vals = np.ascontiguousarray(c[..., 0]).view(np.float32)                       # [G, B, kin]
@@ -42,8 +42,15 @@ class NumpyShardOps:
         v = vals.transpose(1, 0, 2).reshape(B, G * kin)
         i = gidx.transpose(1, 0, 2).reshape(B, G * kin)
         order = np.lexsort((i, -v.astype(np.float64)), axis=1)[:, :k]
-        return (torch.from_numpy(np.take_along_axis(v, order, 1).astype(np.float32)),
-                torch.from_numpy(np.take_along_axis(i, order, 1).astype(np.int32)))
+        out = (torch.from_numpy(np.take_along_axis(v, order, 1).astype(np.float32)),
+               torch.from_numpy(np.take_along_axis(i, order, 1).astype(np.int32)))
+        if not truncated:
+            return out
+        # incomplete: some shard had all of its kin entries selected (positions g * kin .. (g + 1) * kin - 1 of the row)
+        chosen = np.zeros((B, G * kin), dtype=bool)
+        np.put_along_axis(chosen, order, True, axis=1)
+        used_up = chosen.reshape(B, G, kin).all(axis=2).any()
+        return out + (torch.tensor([int(used_up)], dtype=torch.int32),)
 
     def decode_partial(self, vals, idx, plan, with_bias):
         rows = O.dequant_hard(self.m.decoder_weight.detach().numpy(), self.m.n_bits).astype(np.float32)

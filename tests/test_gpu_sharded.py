@@ -132,7 +132,7 @@ def _nccl_worker(rank, world, port, out, D, H, B, kfrac):
             lat, rows, pol = m(torch.from_numpy(inp["x"]).to(dev))
         torch.cuda.synchronize()
         out[rank] = (lat.values.cpu().numpy(), lat.indices.cpu().numpy(), rows.cpu().numpy(), float(pol),
-                     m.plan.row_range(cfg["B"]))
+                     m.plan.row_range(cfg["B"]), m.last_exchange)
     finally:
         dist.destroy_process_group()
 
@@ -158,11 +158,36 @@ def test_dictionary_sharded_forward_under_nccl(cuda_device, D, H, B, kfrac):
     hard = O.dequant_hard(inp["logits"], cfg["n_bits"]).astype(np.float32)
     qstep = cfg["gamma"] / 2 ** (cfg["n_bits"] - 1)
     for r in range(world):
-        v, i, rows, pol, (a, b) = res[r]
+        v, i, rows, pol, (a, b), exchange = res[r]
+        assert exchange == ("truncated" if k >= 256 else "full")
         assert np.array_equal(i, res[0][1]) and np.array_equal(v, res[0][0])       # identical on every rank
         assert_topk_matches(v, i, z, k)
         _recon_close(rows, O.decode_rows(v, i, hard, qstep, inp["bd"])[a:b])
         assert pol == 0.0
+
+
+def test_merge_candidates_truncated_lists(cuda_device):
+    """Shards that send only part of their candidates: the merge must report a list that was used up."""
+    rng = np.random.default_rng(4)
+    G, B, kin, kout, shard = 4, 6, 100, 300, 4096
+    vals = rng.standard_normal((G, B, kin)).astype(np.float32)
+    vals[0, 2] += 10.0                                          # row 2: shard 0's whole list wins
+    vals = -np.sort(-vals, axis=2)
+    idx = np.stack([np.stack([rng.choice(shard, kin, replace=False) for _ in range(B)]) for _ in range(G)]).astype(np.int32)
+    cand = np.empty((G, B, kin, 2), dtype=np.int32)
+    cand[..., 0] = vals.view(np.int32)
+    cand[..., 1] = idx
+
+    def run(c):
+        gv, gi, flag = L.merge_candidates(torch.from_numpy(np.ascontiguousarray(c)).to(cuda_device), shard, kout, truncated=True)
+        gv2, gi2 = L.merge_candidates(torch.from_numpy(np.ascontiguousarray(c)).to(cuda_device), shard, kout)
+        assert torch.equal(gv, gv2) and torch.equal(gi, gi2)    # the check does not change the result
+        return int(flag.item())
+
+    assert run(cand) == 1
+    ok = cand.copy()
+    ok[0, 2, :, 0] = (vals[0, 2] - 10.0).view(np.int32)       # back to an ordinary row: ~75 of 100 selected per shard
+    assert run(ok) == 0
 
 
 @pytest.mark.parametrize("G,B,kin,kout", [(8, 33, 32, 32), (4, 17, 65, 65), (8, 9, 128, 100), (2, 5, 7, 9), (8, 6, 224, 224),
