@@ -144,13 +144,16 @@ matryoshka_dense_operand_kernel(const float* __restrict__ z, int B, int H, const
 constexpr int kMatWarps = 4;
 
 // Sparse level decoder: warp per token row (persistent grid), one 32-bit code word = 16 features per
-// lane (D <= 512), per-level accumulators in registers. The level of a latent is warp-uniform, so
-// the accumulation is a uniform switch, not a predicated fan-out. Activity counts are kept in
-// registers over all rows of a warp and leave through a [warps, n_levels] partial array that a second
-// kernel sums: tens of thousands of atomics on n_levels addresses serialise in L2 (measured: 3.9 ms of
-// a 5.7 ms forward at B = 65536 before this change).
+// lane (D <= 512). The outputs are CUMULATIVE over the levels and every survivor list is sorted by column
+// (a sub-stream sweeps its tiles in ascending order), so the row is processed level by level with ONE
+// running accumulator: for level l every list is scanned from its cursor up to the level's last column,
+// then result[l] = bias + running sum is written. (The first version kept one accumulator set per level,
+// 64 + registers per thread: 143 registers, 12 warps per SM, issue slots 31 % busy.) The level test is
+// warp-uniform. Activity counts are kept in registers over all rows of a warp and leave through a
+// [warps, n_levels] partial array that a second kernel sums: tens of thousands of atomics on n_levels
+// addresses serialise in L2 (measured: 3.9 ms of a 5.7 ms forward at B = 65536 before this change).
 template <int NL>
-__global__ void __launch_bounds__(kMatWarps * 32)
+__global__ void __launch_bounds__(kMatWarps * 32, 6)
 decode_matryoshka_kernel(const uint2* __restrict__ cand, const int* __restrict__ cand_cnt, int nsub,
                          int cap, int B, const uint32_t* __restrict__ packed,
                          const float* __restrict__ scale, const int* __restrict__ level_start,
@@ -165,19 +168,14 @@ decode_matryoshka_kernel(const uint2* __restrict__ cand, const int* __restrict__
   const unsigned full = 0xffffffffu;
   const int words = D >> 4;                 // <= 32: lane `l` owns word l (features 16 l .. 16 l + 15)
   const bool has_word = lane < words;
-  int lstart[NL + 1];
-#pragma unroll
-  for (int l = 0; l <= NL; ++l) lstart[l] = (l <= n_levels) ? level_start[l] : 0x7fffffff;
   unsigned cnt[NL];
 #pragma unroll
   for (int l = 0; l < NL; ++l) cnt[l] = 0u;
 
   for (int row = blockIdx.x * kMatWarps + warp; row < B; row += gridDim.x * kMatWarps) {
-    float acc[NL][16];
+    float run[16];   // bias + sum over the active latents of the levels processed so far
 #pragma unroll
-    for (int l = 0; l < NL; ++l)
-#pragma unroll
-      for (int q = 0; q < 16; ++q) acc[l][q] = 0.f;
+    for (int q = 0; q < 16; ++q) run[q] = (bias && has_word) ? __ldg(bias + lane * 16 + q) : 0.f;
     float4 xr[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -185,77 +183,95 @@ decode_matryoshka_kernel(const uint2* __restrict__ cand, const int* __restrict__
       xr[c] = (exact && d < D) ? *reinterpret_cast<const float4*>(x_f32 + static_cast<size_t>(row) * D + d)
                                : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    // lane s keeps the length and the cursor of list s (nsub <= 32)
+    const int my_c = (lane < nsub) ? min(cand_cnt[static_cast<size_t>(row) * nsub + lane], cap) : 0;
+    int my_cur = 0;
     int n_act = 0;   // warp-uniform: active latents of this row (exported for the analysis consumers)
-    for (int s = 0; s < nsub; ++s) {
-      const size_t slot = static_cast<size_t>(row) * nsub + s;
-      const int c = min(cand_cnt[slot], cap);
-      const uint2* src = cand + slot * cap;
-      for (int base = 0; base < c; base += 32) {
-        const int e = base + lane;
-        const int my_col = (e < c) ? static_cast<int>(src[e].y) : -1;
-        const int m = min(32, c - base);
-        for (int j = 0; j < m; ++j) {
-          const int col = __shfl_sync(full, my_col, j);
-          if (col < 0 || col >= H) continue;
-          if (exact) {  // the sweep kept a rounding-error band below the threshold: decide in fp32
-            const float* wrow = w_f32 + static_cast<size_t>(col) * D;
-            float a0 = 0.f;
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-              const int d = cc * 128 + lane * 4;
-              if (d < D) {
-                const float4 u = __ldg(reinterpret_cast<const float4*>(wrow + d));
-                a0 = fmaf(xr[cc].x, u.x, a0); a0 = fmaf(xr[cc].y, u.y, a0);
-                a0 = fmaf(xr[cc].z, u.z, a0); a0 = fmaf(xr[cc].w, u.w, a0);
+    for (int l = 0; l < NL; ++l) {
+      if (l < n_levels) {
+        const int col_end = (l + 1 < n_levels) ? __ldg(level_start + l + 1) : 0x7fffffff;   // first column of the next level
+        for (int s = 0; s < nsub; ++s) {
+          const int c = __shfl_sync(full, my_c, s);
+          int cur = __shfl_sync(full, my_cur, s);
+          const uint2* src = cand + (static_cast<size_t>(row) * nsub + s) * cap;
+          bool level_done = false;
+          while (cur < c && !level_done) {
+            const int e = cur + lane;
+            const int my_col = (e < c) ? static_cast<int>(src[e].y) : 0x7fffffff;
+            // entries of this chunk that belong to the level: a prefix (the list is sorted by column)
+            const unsigned in_level = __ballot_sync(full, my_col < col_end);
+            const int m = __popc(in_level);             // in_level is a low-bit prefix mask
+            level_done = m < 32;
+            // two candidates per trip: their dictionary rows and scales are fetched together
+            for (int j = 0; j < m; j += 2) {
+              int col[2];
+              bool ok[2];
+              col[0] = __shfl_sync(full, my_col, j);
+              col[1] = __shfl_sync(full, my_col, min(j + 1, 31));
+              ok[0] = col[0] >= 0 && col[0] < H;
+              ok[1] = (j + 1 < m) && col[1] >= 0 && col[1] < H;
+              if (exact) {  // the sweep kept a rounding-error band below the threshold: decide in fp32
+                float a[2] = {0.f, 0.f};
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                  if (ok[t]) {   // warp-uniform
+                    const float* wrow = w_f32 + static_cast<size_t>(col[t]) * D;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                      const int d = cc * 128 + lane * 4;
+                      if (d < D) {
+                        const float4 u = __ldg(reinterpret_cast<const float4*>(wrow + d));
+                        a[t] = fmaf(xr[cc].x, u.x, a[t]); a[t] = fmaf(xr[cc].y, u.y, a[t]);
+                        a[t] = fmaf(xr[cc].z, u.z, a[t]); a[t] = fmaf(xr[cc].w, u.w, a[t]);
+                      }
+                    }
+                  }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                  a[0] += __shfl_xor_sync(full, a[0], o);
+                  a[1] += __shfl_xor_sync(full, a[1], o);
+                }
+#pragma unroll
+                for (int t = 0; t < 2; ++t)
+                  if (ok[t]) ok[t] = (a[t] + __ldg(b_enc + col[t]) >= thr_value);
+              }
+              float s2[2];
+              uint32_t bits[2];
+#pragma unroll
+              for (int t = 0; t < 2; ++t) {
+                s2[t] = ok[t] ? 2.f * __ldg(scale + col[t]) : 0.f;
+                bits[t] = (ok[t] && has_word) ? __ldg(packed + static_cast<size_t>(col[t]) * words + lane) : 0u;
+              }
+#pragma unroll
+              for (int t = 0; t < 2; ++t) {
+                if (ok[t]) {   // warp-uniform
+                  if (active_idx != nullptr) {
+                    if (lane == 0 && n_act < active_cap) active_idx[static_cast<size_t>(row) * active_cap + n_act] = col[t];
+                    ++n_act;
+                  }
+                  ++cnt[l];
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                  const float mag = ((bits[t] >> (2 * q)) & 1u) ? s2[t] : 0.f;
+                  run[q] += ((bits[t] >> (2 * q + 1)) & 1u) ? -mag : mag;
+                }
               }
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) a0 += __shfl_xor_sync(full, a0, o);
-            if (!(a0 + __ldg(b_enc + col) >= thr_value)) continue;
+            cur += m;
           }
-          if (active_idx != nullptr) {
-            if (lane == 0 && n_act < active_cap) active_idx[static_cast<size_t>(row) * active_cap + n_act] = col;
-            ++n_act;
-          }
-          int lvl = 0;
-#pragma unroll
-          for (int l = 1; l < NL; ++l) lvl += (col >= lstart[l]) ? 1 : 0;
-          const float s2 = 2.f * __ldg(scale + col);
-          const uint32_t bits = has_word ? __ldg(packed + static_cast<size_t>(col) * words + lane) : 0u;
-          float t[16];
-#pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const float mag = ((bits >> (2 * q)) & 1u) ? s2 : 0.f;
-            t[q] = ((bits >> (2 * q + 1)) & 1u) ? -mag : mag;
-          }
-#pragma unroll
-          for (int l = 0; l < NL; ++l) {
-            if (lvl == l) {   // warp-uniform
-              ++cnt[l];
-#pragma unroll
-              for (int q = 0; q < 16; ++q) acc[l][q] += t[q];
-            }
-          }
+          if (lane == s) my_cur = cur;
         }
-      }
-    }
-    if (active_idx != nullptr && lane == 0) active_cnt[row] = n_act;
-    // cumulative outputs: result[i] = bias + sum_{l <= i} acc[l]
-    if (has_word) {
-      float run[16];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) run[q] = bias ? __ldg(bias + lane * 16 + q) : 0.f;
-#pragma unroll
-      for (int l = 0; l < NL; ++l) {
-        if (l < n_levels) {
-#pragma unroll
-          for (int q = 0; q < 16; ++q) run[q] += acc[l][q];
+        if (has_word) {   // cumulative output of this level
           float4* dst = reinterpret_cast<float4*>(result + (static_cast<size_t>(l) * B + row) * D + lane * 16);
 #pragma unroll
           for (int q = 0; q < 4; ++q) dst[q] = make_float4(run[4 * q], run[4 * q + 1], run[4 * q + 2], run[4 * q + 3]);
         }
       }
     }
+    if (active_idx != nullptr && lane == 0) active_cnt[row] = n_act;
   }
   if (lane == 0) {
 #pragma unroll
@@ -340,7 +356,7 @@ const char* decode_matryoshka_launch(const void* cand, const int* cand_cnt, int 
   if (n_levels > 8) return "decode_matryoshka: at most 8 levels (n_bits <= 8)";
   if (D > 512 || (D % 16) != 0) return "decode_matryoshka: D must be a multiple of 16, <= 512";
   int blocks = (B + kMatWarps - 1) / kMatWarps;
-  if (blocks > num_sms * 8) blocks = num_sms * 8;
+  if (blocks > num_sms * 6) blocks = num_sms * 6;   // = resident blocks (launch bounds: 6 per SM)
   unsigned* partial = static_cast<unsigned*>(scratch);
   const uint2* c2 = reinterpret_cast<const uint2*>(cand);
 #define QSAE_MAT(NL) \
