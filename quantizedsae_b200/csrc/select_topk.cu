@@ -198,12 +198,13 @@ __device__ __forceinline__ void select_row_block(const SelectLaunch& p, int row,
   }
   __syncthreads();
 
-  if (ksort >= 2048) block_bitonic_desc_regs<8>(sel, ksort);
-  else block_bitonic_desc(sel, ksort);
+  // ---- sort (the gathered keys are no longer needed: their buffer is the scratch of the two-part sort)
+  __shared__ int s_pos[2];
+  const uint64_t* sorted = block_sort_selected(sel, out, ksort, keys, n_max, s_hist, s_ctl, s_pos);
 
   // ---- emit
   for (int j = threadIdx.x; j < p.k_out; j += THREADS) {
-    const uint64_t key = sel[j];
+    const uint64_t key = sorted[j];
     const bool valid = j < out;
     p.out_vals[static_cast<size_t>(row) * p.k_out + j] = valid ? sort_key_value(key) : 0.f;
     p.out_idx[static_cast<size_t>(row) * p.k_out + j] = valid ? static_cast<int32_t>(sort_key_col(key)) : -1;
@@ -216,7 +217,7 @@ __device__ __forceinline__ void select_row_block(const SelectLaunch& p, int row,
       // them over the exact k-th value
       const float worst_bf16 = key_to_float(s_worst_key);
       const float max_dev = key_to_float(s_dev_key);
-      const float kth = sort_key_value(sel[p.k_out - 1]);
+      const float kth = sort_key_value(sorted[p.k_out - 1]);
       if (!(worst_bf16 + 4.f * max_dev < kth)) flag = 1;
     }
     // an uncertified row is recomputed exactly when a rescue pass follows (it then clears the flag)

@@ -295,4 +295,53 @@ __device__ __forceinline__ void block_bitonic_desc_regs(uint64_t* sel, int ksort
   }
 }
 
+// Sort the `out` keys of sel[0, ksort) (ksort = next power of two >= out, the tail zero padded) descending and
+// return the buffer that holds the result. A bitonic network is oblivious to padding: k = 2097 would pay for
+// 4096 keys. When at least a quarter of the network would sort zeros and `scratch` is large enough, the keys are
+// split by a second radix select into the top ksort / 2 and the remainder (padded to ITS next power of two), the
+// two parts are sorted separately in scratch and already stand in order (2097 -> 2048 + 64: 2.4x less work).
+// hist: 256 ints, ctl: 4 ints, pos: 2 ints of shared memory. Ends with a block barrier.
+__device__ __forceinline__ const uint64_t* block_sort_selected(uint64_t* sel, int out, int ksort, uint64_t* scratch,
+                                                               int scratch_cap, int* hist, int* ctl, int* pos) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int p2 = ksort >> 1;
+  const int rest = out - p2;
+  if (ksort >= 2048 && rest > 0 && rest <= (ksort >> 2)) {
+    int r2 = 2;
+    while (r2 < rest) r2 <<= 1;
+    if (p2 + r2 <= scratch_cap) {
+      const uint64_t T1 = block_radix_select([&](int e) { return sel[e]; }, out, p2, hist, ctl);
+      if (threadIdx.x == 0) { pos[0] = 0; pos[1] = 0; }
+      __syncthreads();
+      for (int base = 0; base < out; base += blockDim.x) {
+        const int e = base + threadIdx.x;
+        const uint64_t key = (e < out) ? sel[e] : 0ull;
+        const bool hi = (e < out) && (key >= T1);
+        const bool lo = (e < out) && !hi;
+        const unsigned bh = __ballot_sync(full, hi), bl = __ballot_sync(full, lo);
+        int ph = 0, pl = 0;
+        if (lane == 0) {
+          if (bh) ph = atomicAdd(&pos[0], __popc(bh));
+          if (bl) pl = atomicAdd(&pos[1], __popc(bl));
+        }
+        ph = __shfl_sync(full, ph, 0) + __popc(bh & lt_mask);
+        pl = __shfl_sync(full, pl, 0) + __popc(bl & lt_mask);
+        if (hi && ph < p2) scratch[ph] = key;
+        if (lo && pl < r2) scratch[p2 + pl] = key;
+      }
+      for (int e = rest + threadIdx.x; e < r2; e += blockDim.x) scratch[p2 + e] = 0ull;
+      __syncthreads();
+      block_bitonic_desc_regs<8>(scratch, p2);
+      if (r2 >= 256) block_bitonic_desc_regs<8>(scratch + p2, r2);
+      else block_bitonic_desc(scratch + p2, r2);
+      return scratch;
+    }
+  }
+  if (ksort >= 2048) block_bitonic_desc_regs<8>(sel, ksort);
+  else block_bitonic_desc(sel, ksort);
+  return sel;
+}
+
 }  // namespace qsae
