@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--k", type=int, default=32, help="latents kept per row (model.k = k / 32768)")
     ap.add_argument("--cpu-batch", type=int, default=4096, help="rows per step of the CPU arm / cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--heavy-tail", action="store_true",
+                    help="SURVEY 8d heavy-tail variant of the inputs: 8 of the 512 dimensions scaled by 20")
     ap.add_argument("--variant", default="batch-sharded", choices=["batch-sharded", "dict-sharded"],
                     help="dict-sharded: BASELINE config 5, b_sae 512->2^20 with the dictionary split over the GPUs "
                          "(NCCL all-gather of top-k candidates + reduce-scatter of partial reconstructions)")
@@ -54,7 +56,8 @@ def parse():
 
 def workload_name(batch, k):
     return (f"b_sae input_dim=512 hidden_dim=32768 n_bits=4 gamma=4.0 k={k} forward, "
-            f"synthetic Pythia-70m-shaped activations, batch {batch} per GPU")
+            f"synthetic Pythia-70m-shaped activations{' (heavy-tail variant: 8 dims x 20)' if HEAVY_TAIL else ''}, "
+            f"batch {batch} per GPU")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -71,9 +74,15 @@ def make_weights(torch, device, seed=0):
     return We, be, logits.float().contiguous(), bd
 
 
+HEAVY_TAIL = False   # set from --heavy-tail
+
+
 def make_x(torch, device, batch, seed):
     g = torch.Generator(device=device).manual_seed(1000 + seed)
-    return torch.randn((batch, D), device=device, generator=g).bfloat16().float()
+    x = torch.randn((batch, D), device=device, generator=g)
+    if HEAVY_TAIL:       # a few outlier channels, like the residual stream of a transformer
+        x[:, torch.arange(8, device=device) * 61 + 5] *= 20.0
+    return x.bfloat16().float()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -411,7 +420,9 @@ def run_dict_sharded(args, rank, world, local_rank):
 
 
 def main():
+    global HEAVY_TAIL
     args = parse()
+    HEAVY_TAIL = bool(args.heavy_tail)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -424,7 +435,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", port, __file__, "--gpus", str(args.gpus),
                "--steps", str(args.steps), "--warmup", str(args.warmup), "--batch", str(args.batch), "--k", str(args.k),
-               "--variant", args.variant, "--hidden", str(args.hidden)]
+               "--variant", args.variant, "--hidden", str(args.hidden)] + (["--heavy-tail"] if args.heavy_tail else [])
         raise SystemExit(subprocess.call(cmd))
     if args.variant == "dict-sharded":
         run_dict_sharded(args, rank, world, local_rank)

@@ -194,18 +194,23 @@ class QuantizedMatryoshkaSAE(SparseAutoencoder):
         return {"latent_groups": groups, "reconstruction_levels": levels, "level_counts": counts,
                 "active_idx": a_idx, "active_cnt": a_cnt}
 
-    def forward(self, x):
-        x = require_cuda_input(x, self)
-        if self.dense_mode == "always":
-            return self._forward_dense(x)
+    def _forward_sparse(self, x):
+        """The sparse path without the host-side overflow check: -> (result [n_bits, B, D], counts, overflow [1]).
+        Callers that chain several forwards (rq_sae) read the flags once at the end instead of once per stage."""
         lin = self.encoder[0]
         packed, scale = self.decoder._packed()
         ls, _ = self.decoder._levels()
-        result, counts, overflow = _lib.matryoshka_forward(
+        return _lib.matryoshka_forward(
             x, self._w_bf16(), lin.bias.detach(), packed, scale, ls, self.n_bits,
             self.decoder.bias.detach() if self.allow_bias else None,
             w_f32=lin.weight.detach().contiguous() if self.exact else None,
             w_norm_max=self._w_norm_max() if self.exact else None)
+
+    def forward(self, x):
+        x = require_cuda_input(x, self)
+        if self.dense_mode == "always":
+            return self._forward_dense(x)
+        result, counts, overflow = self._forward_sparse(x)
         if self.dense_mode == "auto" and int(overflow.item()) != 0:
             return self._forward_dense(x)
         self.last_path = "sparse"

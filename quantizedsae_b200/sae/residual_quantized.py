@@ -10,6 +10,7 @@ construction; each one is the fused tcgen05 threshold encoder + sparse level dec
 """
 from __future__ import annotations
 
+import torch
 import torch.nn as nn
 
 from .. import _lib
@@ -41,7 +42,24 @@ class ResidualQuantizedSAE(SparseAutoencoder):
             s.exact = bool(value)
 
     def forward(self, x):
-        residual = require_cuda_input(x, self)
+        x = require_cuda_input(x, self)
+        if all(s.dense_mode == "auto" for s in self.saes):
+            # every stage on the sparse path, the overflow flags read once at the end (one host sync per forward
+            # instead of one per stage); any overflow -> the forward is redone stage by stage with the dense fallback
+            residual = x
+            groups, levels, flags = [], [], []
+            B = x.shape[0]
+            for sae in self.saes:
+                result, counts, overflow = sae._forward_sparse(residual)
+                groups.append(counts[-1].to(torch.float32) / float(max(B, 1)))
+                levels.append(result[-1])
+                flags.append(overflow)
+                residual = _lib.residual_update(residual, result[-1])
+            if int(torch.cat(flags).sum().item()) == 0:
+                for sae in self.saes:
+                    sae.last_path = "sparse"
+                return groups, levels
+        residual = x
         all_latent_groups, all_reconstruction_levels = [], []
         for sae in self.saes:
             latent_group, reconstructions = sae(residual)

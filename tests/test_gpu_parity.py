@@ -388,6 +388,24 @@ def test_prior_threshold_path_matches_oracle(cuda_device, k, exact):
     assert torch.equal(i0, idx) and torch.equal(v0, vals)
 
 
+@pytest.mark.parametrize("k,exact", [(32, False), (65, False), (32, True)])
+def test_heavy_tailed_activations(cuda_device, k, exact):
+    """SURVEY 8d config 1, heavy-tail variant: 8 of the 512 input dimensions scaled by 20 (outlier residual-stream
+    channels). The pre-activations of a row are then dominated by a few encoder columns -- a much heavier tail
+    than the Gaussian case; the sampled prior is distribution-free and the result must stay exact."""
+    B, H, D = 320, 32768, 512
+    x, W, b = _enc_case(B, H, D, 60 + k, bf16=not exact)
+    x[:, np.random.default_rng(1).choice(D, 8, replace=False)] *= 20.0
+    if not exact:
+        x = cases.round_bf16(x)
+    dx, dW, db = T(x, cuda_device), T(W, cuda_device), T(b, cuda_device)
+    wb = L.cast_bf16(dW)
+    vals, idx, flags = L.encode_topk(dx, wb, dW if exact else None, db, k, exact=exact, want_flags=True,
+                                     sample=L.prepare_sample(wb, db))
+    assert_topk_matches(vals.cpu().numpy(), idx.cpu().numpy(), O.encode_pre(x, W, b), k)
+    assert int((flags != 0).sum()) == 0
+
+
 def test_prior_failure_is_rescued_exactly(cuda_device):
     """Force the prior to fail: the sampled rows carry a huge bias that the real rows do not have,
     so every row's prior threshold is far above its true top-k and the count check must route
