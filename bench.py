@@ -89,17 +89,62 @@ def make_x(torch, device, batch, seed):
 # clocks sampler (nvidia-smi during the timed region)
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every 2 ms from a thread (a timed
+    region is only tens of milliseconds long), nvidia-smi -lms as the fallback when pynvml is unavailable."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         self.index, self.samples, self.proc = index, [], None
+        self.sm, self.reasons, self.sm_max = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.index])
+            except (ValueError, IndexError):
+                pass
+        return self.index
 
     def start(self):
         try:
+            import pynvml as N
+
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.sm_max = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": N.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": N.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": N.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": N.nvmlClocksThrottleReasonSwPowerCap}
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                        r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for name, bit in bits.items():
+                            if r & bit:
+                                self.reasons.add(name)
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+
+            self._nvml = N
+            self._thread = threading.Thread(target=poll, daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self._nvml = None
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-i", str(self._physical_index())], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -109,12 +154,16 @@ class ClockSampler:
             self.samples.append(line.strip())
 
     def stop(self):
+        if self._nvml is not None:
+            self._stop.set()
+            self._thread.join(timeout=1.0)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.sm_max,
+                    "samples": len(self.sm), "reasons": sorted(self.reasons), "source": "nvml, 2 ms polling"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for s in self.samples:
             p = [t.strip() for t in s.split(",")]
             if len(p) < 6:
@@ -123,11 +172,11 @@ class ClockSampler:
                 sm.append(float(p[0])); mx.append(float(p[1]))
             except ValueError:
                 continue
-            for n, v in zip(names, p[2:6]):
+            for n, v in zip(self.NAMES, p[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
 # ---------------------------------------------------------------------------------------------

@@ -22,6 +22,15 @@ with torch.device(dev):
 m.eval()
 m.exact = exact
 x = torch.randn((B, D), device=dev).bfloat16().float()
+# calibrate the encoder biases stage by stage so that ~0.1 % of a stage's latents fire (a trained model's regime;
+# at the default initialisation more than half of the latents are active and every stage takes the dense path)
+with torch.no_grad():
+    r = x[:4096]
+    for s in m.saes:
+        z = r @ s.encoder[0].weight.t()
+        s.encoder[0].bias.fill_(float(-3.1 * z.std()))
+        _, lv = s(r)
+        r = (r - lv[-1]) * 2
 with torch.no_grad():
     for _ in range(2):
         g, r = m(x)
