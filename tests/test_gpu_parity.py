@@ -253,6 +253,69 @@ def test_full_size_properties(cuda_device):
     assert torch.equal(i2, idx[:64]) and torch.equal(v2, vals[:64])
 
 
+def test_bench_size_properties(cuda_device):
+    """The bench workload itself (B = 65536 rows, H = 32768, D = 512, k = 32, qsae_bsae_forward): oracle on a row
+    sample, size-independent properties on everything."""
+    B, H, D, k = 65536, 32768, 512, 32
+    g = torch.Generator(device=cuda_device).manual_seed(11)
+    x = torch.randn((B, D), device=cuda_device, generator=g).bfloat16().float()
+    W = ((torch.rand((H, D), device=cuda_device, generator=g) * 2 - 1) * (6.0 / (H + D)) ** 0.5).bfloat16().float()
+    b = (0.01 * torch.randn(H, device=cuda_device, generator=g)).float()
+    packed = torch.randint(0, 256, (H, D // 2), dtype=torch.uint8, device=cuda_device, generator=g)
+    bd = torch.randn(D, device=cuda_device, generator=g)
+    wb = L.cast_bf16(W)
+    vals, idx, _, recon = L.bsae_forward(x, wb, None, b, k, packed, 4, 0.5, bd, sample=L.prepare_sample(wb, b))
+    assert bool((vals[:, :-1] >= vals[:, 1:]).all())                                   # sorted descending
+    assert int(idx.min()) >= 0 and int(idx.max()) < H
+    srt = torch.sort(idx, dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())                                     # distinct indices in every row
+    rows = np.r_[0:24, 30000:30024, B - 24:B]
+    xn, Wn, bn = x[rows].cpu().numpy(), W.cpu().numpy(), b.cpu().numpy()
+    assert_topk_matches(vals[rows].cpu().numpy(), idx[rows].cpu().numpy(), O.encode_pre(xn, Wn, bn), k)
+    ref = O.decode_rows(vals[rows].cpu().numpy(), idx[rows].cpu().numpy(),
+                        O.unpack_nibbles(packed.cpu().numpy()).astype(np.float32), 0.5, bd.cpu().numpy())
+    assert_recon_close(recon[rows].cpu().numpy(), ref)
+    # every 256th row against an independent CUDA-core fp32 evaluation: nothing larger than the k-th value was left out
+    sel = torch.arange(0, B, 256, device=cuda_device, dtype=torch.int32)
+    z = L.encode_dense(x, W, b, rows=sel)
+    kth = torch.sort(z, dim=1, descending=True).values[:, k - 1]
+    assert bool((kth <= vals[::256, -1] + 1e-5).all()) and bool((vals[::256, 0] - z.max(1).values).abs().max() <= 1e-5)
+
+
+def test_qsae_full_size_properties(cuda_device):
+    """q_sae at the config-4 shape (512 -> 32768, n_bits = 4, bias -0.543, B = 4096): exact level counts against the
+    oracle's activity over the whole batch, reconstructions against the oracle on a row sample, level structure."""
+    cfg = dict(D=512, H=32768, n_bits=4, abs_range=4.0, B=4096, enc_bias=-0.543, bf16=False, allow_bias=True, seed=92)
+    inp = cases.qsae_inputs(cfg)
+    m = Q.QuantizedMatryoshkaSAE(cfg["D"], cfg["H"], 32, cfg["abs_range"], cfg["n_bits"], True)
+    m.load_state_dict({"encoder.0.weight": torch.from_numpy(inp["We"]), "encoder.0.bias": torch.from_numpy(inp["be"]),
+                       "decoder.weight": torch.from_numpy(inp["W"]), "decoder.weight_mirror": torch.from_numpy(inp["Wm"]),
+                       "decoder.bias": torch.from_numpy(inp["bd"])}, strict=True)
+    m.to(cuda_device).eval()
+    with torch.no_grad():
+        r = m.forward_active(T(inp["x"], cuda_device))
+    assert m.last_path == "sparse"
+    z = O.encode_pre(inp["x"], inp["We"], inp["be"])
+    act = O.sigmoid_f32(z) > np.float32(0.5)
+    edges = np.cumsum([0] + O.matryoshka_level_sizes(cfg["H"], cfg["n_bits"]))
+    assert r["level_counts"].cpu().numpy().tolist() == [int(act[:, a:b].sum()) for a, b in zip(edges[:-1], edges[1:])]
+    assert np.array_equal(r["active_cnt"].cpu().numpy(), act.sum(1))                   # per-row activity, exact
+    ai = r["active_idx"].cpu().numpy()
+    for row in (0, 1777, 4095):
+        assert sorted(ai[row][ai[row] >= 0].tolist()) == np.nonzero(act[row])[0].tolist()
+    rows = np.r_[0:32, 4064:4096]
+    _, res, _ = O.qsae_forward(inp["x"][rows], inp["We"], inp["be"], inp["W"], inp["Wm"], inp["bd"], n_bits=cfg["n_bits"],
+                               abs_range=cfg["abs_range"], allow_bias=True)
+    for i in range(cfg["n_bits"]):
+        assert_recon_close(r["reconstruction_levels"][i][rows].cpu().numpy(), res[i])
+    # a level only adds vectors of norm 2^(n - l - 2) * quant_step per active latent (Appendix A.4): rows without an
+    # active latent in level l have identical consecutive outputs
+    lv = [t.cpu().numpy() for t in r["reconstruction_levels"]]
+    for l in range(1, cfg["n_bits"]):
+        quiet = ~act[:, edges[l]:edges[l + 1]].any(1)
+        assert np.array_equal(lv[l][quiet], lv[l - 1][quiet])
+
+
 # ------------------------------------------------------------------------------------------
 # modules vs the reference's own outputs
 # ------------------------------------------------------------------------------------------
