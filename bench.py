@@ -51,6 +51,8 @@ def parse():
                     help="dict-sharded: BASELINE config 5, b_sae 512->2^20 with the dictionary split over the GPUs "
                          "(NCCL all-gather of top-k candidates + reduce-scatter of partial reconstructions)")
     ap.add_argument("--hidden", type=int, default=2 ** 20, help="dictionary size of the dict-sharded variant")
+    ap.add_argument("--transport", default="nccl", choices=["nccl", "p2p"],
+                    help="dict-sharded variant: candidate / partial exchange through NCCL collectives or CUDA IPC peer memory")
     return ap.parse_args()
 
 
@@ -417,6 +419,7 @@ def run_dict_sharded(args, rank, world, local_rank):
         m.decoder.bias.copy_(torch.randn(D, device=device, generator=torch.Generator(device=device).manual_seed(7)))
     m.eval()
     m.exact = False
+    m.transport = args.transport
     m.k = k / Hh
     gx = torch.Generator(device=device).manual_seed(1000)     # the same x on every rank (replicated input)
     xs = [torch.randn((B, D), device=device, generator=gx).bfloat16().float() for _ in range(3)]
@@ -440,6 +443,8 @@ def run_dict_sharded(args, rank, world, local_rank):
             lat, rows, _ = m(xs[i % 3])
         ev1.record()
         barrier()
+    if m._peer is not None:
+        m._peer.check()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = L.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
@@ -458,7 +463,10 @@ def run_dict_sharded(args, rank, world, local_rank):
             "config": {"workload": f"b_sae input_dim=512 hidden_dim={Hh} n_bits=4 gamma=4.0 k={k} forward, batch {B} "
                                    f"replicated, dictionary split over {world} GPU(s)",
                        "l2": f"encoder shard {(Hh // world) * D * 2 / 1e6:.0f} MB bf16 per GPU streams from HBM every step (> 126 MB L2 when > 1); 3 rotating inputs",
-                       "parallelism": f"dictionary-sharded x{world}: NCCL all-gather of [B,k] candidates, reduce-scatter of [B,512] partials"},
+                       "parallelism": (f"dictionary-sharded x{world}: NCCL all-gather of [B,k] candidates, reduce-scatter of [B,512] partials"
+                                       if args.transport == "nccl" else
+                                       f"dictionary-sharded x{world}: candidates and [B,512] partials exchanged through CUDA IPC peer "
+                                       f"memory (flag-synchronised P2P loads inside the merge / reduce kernels)")},
             "roofline": {"bound": "tensor", "kernel": "encode_topk_kernel<8> over the local shard", "achieved": flops_per_gpu / (ms * 1e-3) / 1e12,
                          "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": flops_per_gpu / (ms * 1e-3) / 1e12 / peaks["tflops"],
                          "traffic": None, "note": "whole step time used (upper bound on kernel time): fraction is a lower bound",
@@ -484,7 +492,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", port, __file__, "--gpus", str(args.gpus),
                "--steps", str(args.steps), "--warmup", str(args.warmup), "--batch", str(args.batch), "--k", str(args.k),
-               "--variant", args.variant, "--hidden", str(args.hidden)] + (["--heavy-tail"] if args.heavy_tail else [])
+               "--variant", args.variant, "--hidden", str(args.hidden), "--transport", args.transport] + (["--heavy-tail"] if args.heavy_tail else [])
         raise SystemExit(subprocess.call(cmd))
     if args.variant == "dict-sharded":
         run_dict_sharded(args, rank, world, local_rank)

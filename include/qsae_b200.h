@@ -349,6 +349,29 @@ int qsae_merge_candidates(const void* cand_all, int n_shards, int B, int k_in, i
 
 /* qsae_decode_int4 / qsae_decode_int8 restricted to the latents [idx_begin, idx_begin + shard_latents)
  * held in `packed_shard` / `rows_shard` (global indices in idx; others are skipped). */
+/* ---- the same exchange over peer memory instead of NCCL (one process per GPU, NVLink / NVSwitch) ----------------
+ * Every rank owns one buffer (qsae_peer_alloc: cudaMalloc, zeroed) that its peers map through CUDA IPC
+ * (qsae_peer_export -> 64-byte handle, sent to the peers by the host side; qsae_peer_import / qsae_peer_close).
+ * A rank writes its candidate lists / partial reconstructions into ITS OWN buffer and then raises a sequence flag
+ * in every consumer's buffer (qsae_peer_signal: targets[g] = address of this rank's flag inside rank g's buffer);
+ * a consumer polls its own flags (qsae_peer_wait: flags[g] >= value for all g; bounded, ~2 s, then *timed_out = 1)
+ * and reads the data straight from peer memory inside the consuming kernel:
+ *   qsae_merge_candidates_peer: as qsae_merge_candidates, list s of row r at list_bases[s] + r * k_in entries
+ *   qsae_reduce_partials_peer:  out[r, :] = sum_g partial_g[row_begin + r, :] (fixed order, deterministic)
+ * list_bases / partial_bases / targets are DEVICE arrays of n_shards pointers. */
+int qsae_peer_alloc(size_t bytes, void** ptr);
+int qsae_peer_free(void* ptr);
+int qsae_peer_export(const void* ptr, unsigned char* handle64);
+int qsae_peer_import(const unsigned char* handle64, void** ptr);
+int qsae_peer_close(void* ptr);
+int qsae_peer_signal(void* const* targets, int n, unsigned value, void* stream);
+int qsae_peer_wait(const unsigned* flags, int n, unsigned value, int32_t* timed_out, void* stream);
+int qsae_merge_candidates_peer(const void* const* list_bases, int n_shards, int B, int k_in, int shard_latents, int k_out,
+                               float* out_vals, int32_t* out_idx, int32_t* incomplete, void* workspace,
+                               size_t workspace_bytes, void* stream);
+int qsae_reduce_partials_peer(const float* const* partial_bases, int n_shards, int row_begin, int rows, int D, float* out,
+                              void* stream);
+
 int qsae_decode_int4_range(const float* vals, const int32_t* idx, int B, int k, const uint8_t* packed_shard,
                            int shard_latents, int idx_begin, int D, float scale, const float* bias,
                            float* recon, void* stream);

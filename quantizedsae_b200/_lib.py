@@ -68,6 +68,15 @@ SYMBOLS = {
     "qsae_pack_candidates": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "qsae_merge_candidates_workspace_bytes": (_i, [_i, C.POINTER(_sz)]),
     "qsae_merge_candidates": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "qsae_peer_alloc": (_i, [_sz, C.POINTER(_vp)]),
+    "qsae_peer_free": (_i, [_vp]),
+    "qsae_peer_export": (_i, [_vp, C.c_char_p]),
+    "qsae_peer_import": (_i, [C.c_char_p, C.POINTER(_vp)]),
+    "qsae_peer_close": (_i, [_vp]),
+    "qsae_peer_signal": (_i, [_vp, _i, C.c_uint, _vp]),
+    "qsae_peer_wait": (_i, [_vp, _i, C.c_uint, _vp, _vp]),
+    "qsae_merge_candidates_peer": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "qsae_reduce_partials_peer": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "qsae_decode_int4_range": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
     "qsae_decode_int8_range": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
     "qsae_densify": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
@@ -532,11 +541,14 @@ def tsae_forward(x: torch.Tensor, w_parts, b_enc: torch.Tensor, t_bf16: torch.Te
     return h, recon
 
 
-def pack_candidates(vals: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
-    """(vals, idx) [B, k] -> [B, k, 2] int32 entries {float bits, index}: one all-gather operand."""
+def pack_candidates(vals: torch.Tensor, idx: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """(vals, idx) [B, k] -> [B, k, 2] int32 entries {float bits, index}: one all-gather operand
+    (or, with `out`, written straight into this rank's peer-exchange buffer)."""
     global launch_count
-    _need_cuda(vals, idx)
-    out = torch.empty(tuple(vals.shape) + (2,), dtype=torch.int32, device=vals.device)
+    _need_cuda(vals, idx, out)
+    if out is None:
+        out = torch.empty(tuple(vals.shape) + (2,), dtype=torch.int32, device=vals.device)
+    assert out.dtype == torch.int32 and out.numel() == 2 * vals.numel()
     check(load().qsae_pack_candidates(vals.data_ptr(), idx.data_ptr(), vals.numel(), out.data_ptr(), _stream()))
     launch_count += 1
     return out
@@ -564,12 +576,14 @@ def merge_candidates(cand_all: torch.Tensor, shard_latents: int, k_out: int, tru
     return (vals, idx, flag) if truncated else (vals, idx)
 
 
-def decode_range(vals, idx, dict_shard, shard_latents: int, idx_begin: int, D: int, scale: float, bias, n_bits: int):
+def decode_range(vals, idx, dict_shard, shard_latents: int, idx_begin: int, D: int, scale: float, bias, n_bits: int,
+                 out: torch.Tensor | None = None):
     """Partial reconstruction from the winners inside [idx_begin, idx_begin + shard_latents)."""
     global launch_count
-    _need_cuda(vals, idx, dict_shard, bias)
+    _need_cuda(vals, idx, dict_shard, bias, out)
     B, k = vals.shape
-    recon = torch.empty((B, D), dtype=torch.float32, device=vals.device)
+    recon = torch.empty((B, D), dtype=torch.float32, device=vals.device) if out is None else out
+    assert recon.dtype == torch.float32 and tuple(recon.shape) == (B, D)
     fn = load().qsae_decode_int4_range if n_bits <= 4 else load().qsae_decode_int8_range
     check(fn(vals.data_ptr(), idx.data_ptr(), B, k, dict_shard.data_ptr(), shard_latents, idx_begin, D, float(scale),
              _ptr(bias), recon.data_ptr(), _stream()))
@@ -621,5 +635,78 @@ def residual_update(residual: torch.Tensor, recon: torch.Tensor) -> torch.Tensor
     _need_cuda(residual, recon)
     out = torch.empty_like(residual)
     check(load().qsae_residual_update(residual.data_ptr(), recon.data_ptr(), residual.numel(), out.data_ptr(), _stream()))
+    launch_count += 1
+    return out
+
+
+# ---- peer-memory exchange (dictionary-sharded forward without NCCL on the data path) --------------------------------
+class _RawCudaBuffer:
+    """A cudaMalloc'ed / IPC-mapped region exposed to torch through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+def peer_alloc(nbytes: int, device) -> tuple:
+    """-> (ptr, uint8 tensor view, 64-byte IPC handle)"""
+    ptr = _vp()
+    check(load().qsae_peer_alloc(nbytes, C.byref(ptr)))
+    handle = C.create_string_buffer(64)
+    check(load().qsae_peer_export(ptr, handle))
+    view = torch.as_tensor(_RawCudaBuffer(ptr.value, nbytes), device=device)
+    return ptr.value, view, handle.raw
+
+
+def peer_import(handle: bytes) -> int:
+    ptr = _vp()
+    check(load().qsae_peer_import(C.create_string_buffer(handle, 64), C.byref(ptr)))
+    return ptr.value
+
+
+def peer_close(ptr: int) -> None:
+    check(load().qsae_peer_close(_vp(ptr)))
+
+
+def peer_free(ptr: int) -> None:
+    check(load().qsae_peer_free(_vp(ptr)))
+
+
+def peer_signal(targets: torch.Tensor, value: int) -> None:
+    """targets: device int64 [G] addresses of this rank's flag inside every rank's buffer."""
+    global launch_count
+    check(load().qsae_peer_signal(targets.data_ptr(), targets.numel(), value & 0xFFFFFFFF, _stream()))
+    launch_count += 1
+
+
+def peer_wait(flags_ptr: int, n: int, value: int, timed_out: torch.Tensor) -> None:
+    global launch_count
+    check(load().qsae_peer_wait(_vp(flags_ptr), n, value & 0xFFFFFFFF, timed_out.data_ptr(), _stream()))
+    launch_count += 1
+
+
+def merge_candidates_peer(list_bases: torch.Tensor, B: int, k_in: int, shard_latents: int, k_out: int,
+                          truncated: bool = False):
+    """list_bases: device int64 [G]; list s of row r at list_bases[s] + r * k_in 8-byte entries (peer memory)."""
+    global launch_count
+    dev = list_bases.device
+    vals = torch.empty((B, k_out), dtype=torch.float32, device=dev)
+    idx = torch.empty((B, k_out), dtype=torch.int32, device=dev)
+    flag = torch.zeros((1,), dtype=torch.int32, device=dev) if truncated else None
+    if B == 0:
+        return (vals, idx, flag) if truncated else (vals, idx)
+    n = _sz(0)
+    check(load().qsae_merge_candidates_workspace_bytes(B, C.byref(n)))
+    ws = _workspace(dev, int(n.value))
+    check(load().qsae_merge_candidates_peer(list_bases.data_ptr(), list_bases.numel(), B, k_in, shard_latents, k_out,
+                                            vals.data_ptr(), idx.data_ptr(), _ptr(flag), ws.data_ptr(), ws.numel(), _stream()))
+    launch_count += 2
+    return (vals, idx, flag) if truncated else (vals, idx)
+
+
+def reduce_partials_peer(partial_bases: torch.Tensor, row_begin: int, rows: int, D: int) -> torch.Tensor:
+    global launch_count
+    out = torch.empty((rows, D), dtype=torch.float32, device=partial_bases.device)
+    check(load().qsae_reduce_partials_peer(partial_bases.data_ptr(), partial_bases.numel(), row_begin, rows, D,
+                                           out.data_ptr(), _stream()))
     launch_count += 1
     return out

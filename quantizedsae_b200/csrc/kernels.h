@@ -90,6 +90,9 @@ struct SelectLaunch {
   // for some row, every entry of some list was selected -- entries that list's owner did not send could then
   // belong to the row's true top-k. Block-per-row kernel only; null = lists are complete, no check.
   int* incomplete;
+  // Lists that live in peer memory (dictionary shards, CUDA IPC): list s of row r starts at
+  // list_bases[s] + r * cap entries (device array of nsub pointers); null = the cand / stride layout above.
+  const void* const* list_bases;
 };
 
 // rescue.cu: exact per-row top-k for the rows listed by the merge kernel (persistent small grid,
@@ -194,6 +197,12 @@ const char* activation_counts_launch(const int32_t* idx, const float* vals, int 
 const char* coactivation_launch(const int32_t* idx, const float* vals, int B, int cap, int H, int32_t* cooc,
                                 cudaStream_t stream);
 const char* sq_error_launch(const float* a, const float* b, size_t n, double* out, cudaStream_t stream);
+
+// peer.cu: flag-based exchange over CUDA IPC peer memory (dictionary-sharded forward)
+const char* peer_signal_launch(unsigned* const* targets, int n, unsigned value, cudaStream_t stream);
+const char* peer_wait_launch(const unsigned* flags, int n, unsigned value, int* timed_out, cudaStream_t stream);
+const char* reduce_partials_peer_launch(const float* const* bases, int n, int row_begin, int rows, int D, float* out,
+                                        cudaStream_t stream);
 
 // encode_dense.cu
 const char* encode_dense_launch(const float* x, const int32_t* rows, int R, const float* w,

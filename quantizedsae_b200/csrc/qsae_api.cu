@@ -1086,11 +1086,15 @@ int qsae_merge_candidates_workspace_bytes(int B, size_t* bytes) {
   return QSAE_OK;
 }
 
-int qsae_merge_candidates(const void* cand_all, int n_shards, int B, int k_in, int shard_latents, int k_out,
-                          float* out_vals, int32_t* out_idx, int32_t* incomplete, void* workspace, size_t workspace_bytes,
-                          void* stream) {
+}  // extern "C"
+
+namespace {
+int merge_candidates_impl(const void* cand_all, const void* const* list_bases, int n_shards, int B, int k_in,
+                          int shard_latents, int k_out, float* out_vals, int32_t* out_idx, int32_t* incomplete,
+                          void* workspace, size_t workspace_bytes, void* stream) {
   if (B == 0) return QSAE_OK;
-  if (!cand_all || !out_vals || !out_idx || !workspace) return fail(QSAE_ERR_INVALID_ARGUMENT, "merge_candidates: null pointer");
+  if ((!cand_all && !list_bases) || !out_vals || !out_idx || !workspace)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "merge_candidates: null pointer");
   if (n_shards < 1 || n_shards > 32 || k_in < 1 || k_out < 1 || shard_latents < 1)
     return fail(QSAE_ERR_INVALID_ARGUMENT, "merge_candidates: need 1 <= n_shards <= 32, k_in, k_out >= 1");
   if (k_out > kMaxKLarge) return fail(QSAE_ERR_INVALID_ARGUMENT, "k=%d exceeds QSAE_MAX_K_LARGE=%d", k_out, kMaxKLarge);
@@ -1108,6 +1112,7 @@ int qsae_merge_candidates(const void* cand_all, int n_shards, int B, int k_in, i
   memset(&sl, 0, sizeof(sl));
   sl.B = B; sl.H = n_shards * shard_latents; sl.k_sel = k_out; sl.k_out = k_out; sl.nsub = n_shards; sl.cap = k_in;
   sl.cand = cand_all;                 // [n_shards][B][k_in] entries, every list full
+  sl.list_bases = list_bases;         // or one [B][k_in] list array per shard, in that shard's (peer) memory
   sl.row_stride = 1; sl.sub_stride = B; sl.sub_col_offset = shard_latents;
   sl.out_vals = out_vals; sl.out_idx = out_idx;
   // every row has exactly n_shards * k_in candidates: pick the tier that holds them
@@ -1121,6 +1126,84 @@ int qsae_merge_candidates(const void* cand_all, int n_shards, int B, int k_in, i
     return launch_status("select_topk kernel", select_topk_launch(sl, st));
   const int tier = n_cand <= 256 ? 8 : (n_cand <= 512 ? 16 : 32);
   return launch_status("select_small kernel", select_small_launch(sl, tier, nullptr, nullptr, num_sms(), counters + 1, ovf_rows, st));
+}
+}  // namespace
+
+extern "C" {
+
+int qsae_merge_candidates(const void* cand_all, int n_shards, int B, int k_in, int shard_latents, int k_out,
+                          float* out_vals, int32_t* out_idx, int32_t* incomplete, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  if (B > 0 && !cand_all) return fail(QSAE_ERR_INVALID_ARGUMENT, "merge_candidates: null pointer");
+  return merge_candidates_impl(cand_all, nullptr, n_shards, B, k_in, shard_latents, k_out, out_vals, out_idx, incomplete,
+                               workspace, workspace_bytes, stream);
+}
+
+int qsae_merge_candidates_peer(const void* const* list_bases, int n_shards, int B, int k_in, int shard_latents, int k_out,
+                               float* out_vals, int32_t* out_idx, int32_t* incomplete, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  if (B > 0 && !list_bases) return fail(QSAE_ERR_INVALID_ARGUMENT, "merge_candidates_peer: null pointer");
+  return merge_candidates_impl(nullptr, list_bases, n_shards, B, k_in, shard_latents, k_out, out_vals, out_idx, incomplete,
+                               workspace, workspace_bytes, stream);
+}
+
+// ---- peer buffers (cudaMalloc + CUDA IPC) and the flag protocol ---------------------------------------------------------
+int qsae_peer_alloc(size_t bytes, void** ptr) {
+  if (!ptr || bytes == 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "peer_alloc: bad argument");
+  cudaError_t e = cudaMalloc(ptr, bytes);
+  if (e == cudaSuccess) e = cudaMemset(*ptr, 0, bytes);
+  if (e != cudaSuccess) return fail(QSAE_ERR_CUDA, "peer_alloc: %s", cudaGetErrorString(e));
+  return QSAE_OK;
+}
+
+int qsae_peer_free(void* ptr) {
+  if (!ptr) return QSAE_OK;
+  cudaError_t e = cudaFree(ptr);
+  return e == cudaSuccess ? QSAE_OK : fail(QSAE_ERR_CUDA, "peer_free: %s", cudaGetErrorString(e));
+}
+
+int qsae_peer_export(const void* ptr, unsigned char* handle64) {
+  if (!ptr || !handle64) return fail(QSAE_ERR_INVALID_ARGUMENT, "peer_export: null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void*>(ptr));
+  if (e != cudaSuccess) return fail(QSAE_ERR_CUDA, "peer_export: %s", cudaGetErrorString(e));
+  memcpy(handle64, &h, 64);
+  return QSAE_OK;
+}
+
+int qsae_peer_import(const unsigned char* handle64, void** ptr) {
+  if (!handle64 || !ptr) return fail(QSAE_ERR_INVALID_ARGUMENT, "peer_import: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return fail(QSAE_ERR_CUDA, "peer_import: %s", cudaGetErrorString(e));
+  return QSAE_OK;
+}
+
+int qsae_peer_close(void* ptr) {
+  if (!ptr) return QSAE_OK;
+  cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  return e == cudaSuccess ? QSAE_OK : fail(QSAE_ERR_CUDA, "peer_close: %s", cudaGetErrorString(e));
+}
+
+int qsae_peer_signal(void* const* targets, int n, unsigned value, void* stream) {
+  if (!targets) return fail(QSAE_ERR_INVALID_ARGUMENT, "peer_signal: null pointer");
+  return launch_status("peer_signal", peer_signal_launch(reinterpret_cast<unsigned* const*>(targets), n, value, S(stream)));
+}
+
+int qsae_peer_wait(const unsigned* flags, int n, unsigned value, int32_t* timed_out, void* stream) {
+  if (!flags || !timed_out) return fail(QSAE_ERR_INVALID_ARGUMENT, "peer_wait: null pointer");
+  return launch_status("peer_wait", peer_wait_launch(flags, n, value, timed_out, S(stream)));
+}
+
+int qsae_reduce_partials_peer(const float* const* partial_bases, int n_shards, int row_begin, int rows, int D, float* out,
+                              void* stream) {
+  if (rows == 0) return QSAE_OK;
+  if (!partial_bases || !out || n_shards < 1 || rows < 0 || row_begin < 0 || D <= 0)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "reduce_partials_peer: bad argument");
+  return launch_status("reduce_partials_peer",
+                       reduce_partials_peer_launch(partial_bases, n_shards, row_begin, rows, D, out, S(stream)));
 }
 
 int qsae_decode_int4_range(const float* vals, const int32_t* idx, int B, int k, const uint8_t* packed_shard,

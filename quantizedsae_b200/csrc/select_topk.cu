@@ -25,6 +25,12 @@ __device__ __forceinline__ size_t list_slot(const SelectLaunch& p, int row, int 
 __device__ __forceinline__ int list_count(const SelectLaunch& p, size_t slot) {
   return p.cand_cnt ? min(p.cand_cnt[slot], p.cap) : p.cap;
 }
+// first entry of list (row, s): local layout, or the owner's buffer in peer memory
+__device__ __forceinline__ const uint2* list_ptr(const SelectLaunch& p, int row, int s) {
+  if (p.list_bases != nullptr)
+    return reinterpret_cast<const uint2*>(p.list_bases[s]) + static_cast<size_t>(row) * p.cap;
+  return reinterpret_cast<const uint2*>(p.cand) + list_slot(p, row, s) * p.cap;
+}
 
 __device__ __forceinline__ void atomic_min_float_key(unsigned* addr, float v) { atomicMin(addr, float_to_key(v)); }
 __device__ __forceinline__ void atomic_max_float_key(unsigned* addr, float v) { atomicMax(addr, float_to_key(v)); }
@@ -64,14 +70,13 @@ __device__ __forceinline__ void select_row_block(const SelectLaunch& p, int row,
   __syncthreads();
 
   // ---- gather survivors >= thr_row (order is irrelevant: the composite keys are unique)
-  const uint2* cand = reinterpret_cast<const uint2*>(p.cand);
   constexpr int BATCH = 8;
   for (int s = warp; s < p.nsub; s += nwarps) {
     const size_t slot = list_slot(p, row, s);
     const int c = list_count(p, slot);
     // a threshold-only sweep (no in-kernel cut) stops collecting when a list fills up
     if (lane == 0 && p.cand_cnt != nullptr && p.cand_cnt[slot] > p.cap - 32) s_ovf = 1;
-    const uint2* src = cand + slot * p.cap;
+    const uint2* src = list_ptr(p, row, s);
     const uint32_t col_add = static_cast<uint32_t>(s) * static_cast<uint32_t>(p.sub_col_offset);
     uint64_t lmin = ~0ull;
     for (int base = 0; base < c; base += 32 * BATCH) {
@@ -556,11 +561,10 @@ __device__ __forceinline__ void small_row(const SelectLaunch& p, int row, int ks
     return;
   }
   // ---- gather (every survivor already passed the row's threshold in the sweep)
-  const uint2* cand = reinterpret_cast<const uint2*>(p.cand);
   for (int s = 0; s < p.nsub; ++s) {
     const int c = __shfl_sync(full, my_c, s);
     const int off = __shfl_sync(full, incl, s) - c;
-    const uint2* src = cand + list_slot(p, row, s) * p.cap;
+    const uint2* src = list_ptr(p, row, s);
     const uint32_t col_add = static_cast<uint32_t>(s) * static_cast<uint32_t>(p.sub_col_offset);
 #pragma unroll 4
     for (int e = lane; e < c; e += 32) {

@@ -143,6 +143,78 @@ class CudaShardOps:
         return self._packed()[1] * w.numel()
 
 
+class PeerExchange:
+    """The two exchanges of the sharded forward over CUDA IPC peer memory (NVLink / NVSwitch) instead of NCCL.
+
+    Every rank owns one buffer, mapped by all peers:
+        [flags: 2 phases x G uint32][candidate lists: 2 slots x B x k x 8 B][partial rows: 2 slots x B x D x 4 B]
+    A rank writes its own lists / partial rows, raises its sequence flag in every consumer's buffer, and the
+    consumers read the data inside the merge / reduce kernels (P2P loads). Two slots: a rank can be one exchange
+    ahead of the slowest reader, never two (its next publish is ordered after a merge that needed every peer's
+    previous publish). Handles travel once, through the process group's object all-gather."""
+
+    FLAG_BYTES = 1024
+
+    def __init__(self, dist, group, rank: int, world: int, device, max_rows: int, max_k: int, D: int):
+        self.rank, self.world, self.device, self.D = rank, world, device, D
+        self.max_rows, self.max_k = max_rows, max_k
+        self.cand_slot = -(-(max_rows * max_k * 8) // 1024) * 1024
+        self.part_slot = -(-(max_rows * D * 4) // 1024) * 1024
+        self.cand_off = self.FLAG_BYTES
+        self.part_off = self.cand_off + 2 * self.cand_slot
+        nbytes = self.part_off + 2 * self.part_slot
+        self.ptr, self.buf, handle = _lib.peer_alloc(nbytes, device)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle, group=group)
+        self.peer_ptrs = [self.ptr if g == rank else _lib.peer_import(handles[g]) for g in range(world)]
+        i64 = dict(dtype=torch.int64, device=device)
+        self.cand_bases = [torch.tensor([p + self.cand_off + s * self.cand_slot for p in self.peer_ptrs], **i64) for s in (0, 1)]
+        self.part_bases = [torch.tensor([p + self.part_off + s * self.part_slot for p in self.peer_ptrs], **i64) for s in (0, 1)]
+        self.signal_targets = [torch.tensor([p + (ph * world + rank) * 4 for p in self.peer_ptrs], **i64) for ph in (0, 1)]
+        self.timed_out = torch.zeros((1,), dtype=torch.int32, device=device)
+        self.seq = [0, 0]          # exchanges done per phase (identical on every rank)
+        dist.barrier(group=group)  # every peer has mapped every buffer before the first signal is sent
+
+    def fits(self, rows: int, k: int, D: int) -> bool:
+        return rows <= self.max_rows and k <= self.max_k and D == self.D
+
+    def _exchange(self, phase: int) -> int:
+        """signal `my data of this exchange is in place`, wait for everybody's; -> slot that holds it"""
+        self.seq[phase] += 1
+        _lib.peer_signal(self.signal_targets[phase], self.seq[phase])
+        _lib.peer_wait(self.ptr + phase * self.world * 4, self.world, self.seq[phase], self.timed_out)
+        return (self.seq[phase] - 1) % 2
+
+    def publish_candidates(self, vals: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        """-> device int64 [G]: where the [B, k] lists of every shard start"""
+        B, k = vals.shape
+        slot = self.seq[0] % 2
+        a = self.cand_off + slot * self.cand_slot
+        _lib.pack_candidates(vals, idx, out=self.buf[a:a + B * k * 8].view(torch.int32).view(B, k, 2))
+        assert self._exchange(0) == slot
+        return self.cand_bases[slot]
+
+    def partial_view(self, B: int) -> torch.Tensor:
+        slot = self.seq[1] % 2
+        a = self.part_off + slot * self.part_slot
+        return self.buf[a:a + B * self.D * 4].view(torch.float32).view(B, self.D)
+
+    def reduce_rows(self, row_begin: int, rows: int) -> torch.Tensor:
+        slot = self._exchange(1)
+        return _lib.reduce_partials_peer(self.part_bases[slot], row_begin, rows, self.D)
+
+    def check(self) -> None:
+        if int(self.timed_out.item()) != 0:
+            raise RuntimeError("peer exchange: a flag wait timed out (a peer did not publish its data)")
+
+    def close(self) -> None:
+        for g, p in enumerate(self.peer_ptrs):
+            if g != self.rank:
+                _lib.peer_close(p)
+        _lib.peer_free(self.ptr)
+        self.peer_ptrs = []
+
+
 class DictionaryShardedBinarySAE(nn.Module):
     """Rank-local shard of BinarySAE(input_dim, hidden_dim, gamma, n_bits) (sae/binary.py:73).
 
@@ -179,6 +251,8 @@ class DictionaryShardedBinarySAE(nn.Module):
         self.polar_tol = 1e-6
         self.trim_min_k = 256                # k below this: every shard sends its full top-k (tiny anyway)
         self.last_exchange = None            # "truncated" / "full": which candidate exchange produced the last forward
+        self.transport = "nccl"              # "nccl" (torch.distributed collectives) | "p2p" (CUDA IPC peer memory)
+        self._peer = None
         self._pol_cache = None
         # ops=False defers the choice (tests install their own backend after construction)
         self.ops = CudaShardOps(self) if ops is None else (ops or None)
@@ -237,6 +311,8 @@ class DictionaryShardedBinarySAE(nn.Module):
         if k > self.hidden_dim:
             raise RuntimeError(f"selected index k out of range (k={k} > H={self.hidden_dim})")
         plan = self.plan
+        if self.transport == "p2p" and plan.world_size > 1:
+            return self._forward_p2p(x, k)
         k_loc, k_snd = plan.k_local(k), plan.k_send(k, self.trim_min_k)
         self.last_exchange = "full"
         vals = None
@@ -261,4 +337,57 @@ class DictionaryShardedBinarySAE(nn.Module):
                 rows = torch.cat([rows, rows.new_zeros((per - rows.shape[0], rows.shape[1]))], 0)
             rows = self._all_gather(rows).reshape(-1, rows.shape[1])[:B]
         latents = SparseLatents(vals, idx, (x.shape[0], self.hidden_dim))
+        return latents, rows, self.polarize_loss(x)
+
+    # ---- the same forward with both exchanges over peer memory --------------------------------------------------
+    def _peer_exchange(self, rows: int, k: int) -> PeerExchange:
+        if self._peer is None or not self._peer.fits(rows, k, self.input_dim):
+            if self._peer is not None:
+                torch.cuda.synchronize()
+                self._dist.barrier(group=self.group)      # nobody is still reading the old buffers
+                self._peer.close()
+            self._peer = PeerExchange(self._dist, self.group, self.plan.rank, self.plan.world_size, self.decoder.bias.device,
+                                      rows, k, self.input_dim)
+        return self._peer
+
+    def _forward_p2p(self, x: torch.Tensor, k: int):
+        plan = self.plan
+        ops = self.ops
+        B = x.shape[0]
+        k_loc, k_snd = plan.k_local(k), plan.k_send(k, self.trim_min_k)
+        px = self._peer_exchange(B, k_loc)
+        lin = self.encoder[0]
+        w32 = lin.weight.detach().contiguous()
+
+        def local_topk(kk):
+            v, i, _ = _lib.encode_topk(x, ops._w_bf16(), w32 if self.exact else None, lin.bias.detach(), kk, _lib.ACT_NONE,
+                                       self.exact, sample=ops._sample())
+            return v, i
+
+        self.last_exchange = "full"
+        vals = None
+        if k_snd < k_loc:
+            bases = px.publish_candidates(*local_topk(k_snd))
+            vals, idx, incomplete = _lib.merge_candidates_peer(bases, B, k_snd, plan.shard_latents, k, truncated=True)
+            if int(incomplete.item()) != 0:
+                vals = None
+            else:
+                self.last_exchange = "truncated"
+        if vals is None:
+            bases = px.publish_candidates(*local_topk(k_loc))
+            vals, idx = _lib.merge_candidates_peer(bases, B, k_loc, plan.shard_latents, k)
+        packed, _, gap = ops._packed()
+        if gap > self.polar_tol:
+            raise RuntimeError("dictionary-sharded b_sae serves the packed (polarised / hard) dictionary only; "
+                               f"max |sigmoid(w) - bit| = {gap:.3g} on this shard")
+        _lib.decode_range(vals, idx, packed, plan.shard_latents, plan.latent_begin, self.input_dim, self.quantization_step,
+                          self.decoder.bias.detach() if plan.rank == 0 else None, self.n_bits, out=px.partial_view(B))
+        a, b = plan.row_range(B)
+        rows = px.reduce_rows(a, b - a)
+        if self.gather_output:
+            per = plan.padded_batch(B) // plan.world_size
+            if rows.shape[0] != per:
+                rows = torch.cat([rows, rows.new_zeros((per - rows.shape[0], rows.shape[1]))], 0)
+            rows = self._all_gather(rows).reshape(-1, rows.shape[1])[:B]
+        latents = SparseLatents(vals, idx, (B, self.hidden_dim))
         return latents, rows, self.polarize_loss(x)

@@ -115,7 +115,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _nccl_worker(rank, world, port, out, D, H, B, kfrac):
+def _nccl_worker(rank, world, port, out, D, H, B, kfrac, transport="nccl"):
     import torch.distributed as dist
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -128,9 +128,13 @@ def _nccl_worker(rank, world, port, out, D, H, B, kfrac):
         m.load_state_dict(m.plan.shard_state_dict(full_state_dict(inp), cfg["n_bits"]), strict=True)
         m.to(dev).eval()
         m.k = kfrac
+        m.transport = transport
         with torch.no_grad():
-            lat, rows, pol = m(torch.from_numpy(inp["x"]).to(dev))
+            for _ in range(3 if transport == "p2p" else 1):     # p2p: several exchanges through the two buffer slots
+                lat, rows, pol = m(torch.from_numpy(inp["x"]).to(dev))
         torch.cuda.synchronize()
+        if transport == "p2p":
+            m._peer.check()                                     # no flag wait timed out
         out[rank] = (lat.values.cpu().numpy(), lat.indices.cpu().numpy(), rows.cpu().numpy(), float(pol),
                      m.plan.row_range(cfg["B"]), m.last_exchange)
     finally:
@@ -139,8 +143,11 @@ def _nccl_worker(rank, world, port, out, D, H, B, kfrac):
 
 # k = 32 of 32768 latents; and the reference default fraction 0.002 on 2^17 latents (k = 262 > QSAE_MAX_K:
 # block-level selection on every shard, radix-select merge of G * 262 candidates)
-@pytest.mark.parametrize("D,H,B,kfrac", [(512, 32768, 203, 2 ** -10), (128, 131072, 61, 0.002)])
-def test_dictionary_sharded_forward_under_nccl(cuda_device, D, H, B, kfrac):
+@pytest.mark.parametrize("D,H,B,kfrac,transport", [(512, 32768, 203, 2 ** -10, "nccl"), (128, 131072, 61, 0.002, "nccl"),
+                                                   (512, 32768, 203, 2 ** -10, "p2p"), (128, 131072, 61, 0.002, "p2p")])
+def test_dictionary_sharded_forward_under_nccl(cuda_device, D, H, B, kfrac, transport):
+    """transport "nccl": all-gather / reduce-scatter; "p2p": the same exchanges through CUDA IPC peer memory, read
+    inside the merge / reduce kernels (NCCL only carries the IPC handles once)."""
     world = min(torch.cuda.device_count(), 8)
     if world < 2:
         pytest.skip("needs >= 2 GPUs (gpurun --gpus N)")
@@ -150,7 +157,7 @@ def test_dictionary_sharded_forward_under_nccl(cuda_device, D, H, B, kfrac):
     port = _free_port()
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_nccl_worker, args=(world, port, out, D, H, B, kfrac), nprocs=world, join=True)
+        mp.spawn(_nccl_worker, args=(world, port, out, D, H, B, kfrac, transport), nprocs=world, join=True)
         res = {r: out[r] for r in range(world)}
     cfg, inp = sharded_case(D=D, H=H, B=B, seed=5)
     k = int(H * kfrac)
