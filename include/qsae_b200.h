@@ -215,13 +215,16 @@ int qsae_matryoshka_forward(const float* x_f32, const uint16_t* w_bf16,
 /* The same forward, additionally exporting each row's active latents for the analysis consumers
  * (_activation_mask of scripts/analysis/dynamic_analysis.py:30-73 without the dense [B, H] mask):
  * active_idx [B, active_cap] int32, unordered, empty slots = -1; active_cnt [B] = number of active latents of the
- * row (entries beyond active_cap are counted but not stored). NULL active_idx = plain forward. */
+ * row (entries beyond active_cap are counted but not stored). NULL active_idx = plain forward.
+ * residual_out [B, D] or NULL: (x - result[n_levels - 1]) * 2, the input of the next rq_sae stage
+ * (sae/residual_quantized.py:67), written by the level decoder from the reconstruction it still holds in
+ * registers instead of a separate pass (qsae_residual_update). Must not alias x_f32. */
 int qsae_matryoshka_forward_active(const float* x_f32, const uint16_t* w_bf16, const float* w_f32,
                                    const float* w_norm_max, const float* b_enc, const uint32_t* packed,
                                    const float* scale, const int* level_start, int n_levels, const float* dec_bias,
                                    int B, int H, int D, float* result, unsigned long long* level_count, int* overflow,
-                                   int32_t* active_idx, int active_cap, int32_t* active_cnt, void* workspace,
-                                   size_t workspace_bytes, void* stream);
+                                   int32_t* active_idx, int active_cap, int32_t* active_cnt, float* residual_out,
+                                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Analysis consumers over sparse active lists (scripts/analysis/dynamic_analysis.py:317-440).

@@ -46,7 +46,7 @@ SYMBOLS = {
     "qsae_matryoshka_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
     "qsae_matryoshka_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "qsae_matryoshka_forward_active": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp,
-                                            _vp, _i, _vp, _vp, _sz, _vp]),
+                                            _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "qsae_activation_counts": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "qsae_coactivation": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "qsae_sq_error_accumulate": (_i, [_vp, _vp, _sz, _vp, _vp]),
@@ -407,9 +407,10 @@ def decode_matryoshka_lists(lists, counts, cap, packed, scale, level_start, n_le
 
 
 def matryoshka_forward(x, w_bf16, b_enc, packed, scale, level_start, n_levels, dec_bias, w_f32=None, w_norm_max=None,
-                       active_cap: int = 0):
+                       active_cap: int = 0, want_residual: bool = False):
     """-> (result [n_levels, B, D] f32, level_count [n_levels] int64, overflow [1] int32)
-    active_cap > 0: additionally (active_idx [B, active_cap] int32 with -1 in empty slots, active_cnt [B] int32)."""
+    active_cap > 0: additionally (active_idx [B, active_cap] int32 with -1 in empty slots, active_cnt [B] int32).
+    want_residual: additionally (x - result[-1]) * 2 [B, D], the next rq_sae stage's input, as the last element."""
     global launch_count
     _need_cuda(x, w_bf16, b_enc, packed, scale, level_start, dec_bias)
     B, D = x.shape
@@ -419,9 +420,11 @@ def matryoshka_forward(x, w_bf16, b_enc, packed, scale, level_start, n_levels, d
     overflow = torch.empty((1,), dtype=torch.int32, device=x.device)
     a_idx = torch.empty((B, active_cap), dtype=torch.int32, device=x.device) if active_cap > 0 else None
     a_cnt = torch.zeros((B,), dtype=torch.int32, device=x.device) if active_cap > 0 else None
+    resid = torch.empty((B, D), dtype=torch.float32, device=x.device) if want_residual else None
     if B == 0:
         out = (result, counts.zero_(), overflow.zero_())
-        return out + (a_idx, a_cnt) if active_cap > 0 else out
+        out = out + (a_idx, a_cnt) if active_cap > 0 else out
+        return out + (resid,) if want_residual else out
     n = _sz(0)
     check(load().qsae_matryoshka_workspace_bytes(B, H, D, C.byref(n)))
     ws = _workspace(x.device, int(n.value))
@@ -429,9 +432,11 @@ def matryoshka_forward(x, w_bf16, b_enc, packed, scale, level_start, n_levels, d
                                                 b_enc.data_ptr(), packed.data_ptr(), scale.data_ptr(),
                                                 level_start.data_ptr(), n_levels, _ptr(dec_bias), B, H, D,
                                                 result.data_ptr(), counts.data_ptr(), overflow.data_ptr(),
-                                                _ptr(a_idx), active_cap, _ptr(a_cnt), ws.data_ptr(), ws.numel(), _stream()))
+                                                _ptr(a_idx), active_cap, _ptr(a_cnt), _ptr(resid), ws.data_ptr(), ws.numel(),
+                                                _stream()))
     launch_count += 4
-    return (result, counts, overflow, a_idx, a_cnt) if active_cap > 0 else (result, counts, overflow)
+    out = (result, counts, overflow, a_idx, a_cnt) if active_cap > 0 else (result, counts, overflow)
+    return out + (resid,) if want_residual else out
 
 
 def activation_counts(idx: torch.Tensor, vals: torch.Tensor | None, counts: torch.Tensor) -> None:

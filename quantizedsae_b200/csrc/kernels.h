@@ -177,7 +177,7 @@ const char* decode_matryoshka_launch(const void* cand, const int* cand_cnt, int 
                                      unsigned long long* level_count, const float* x_f32, const float* w_f32,
                                      const float* b_enc, float thr_value, int exact, void* scratch, int num_sms,
                                      cudaStream_t stream, int32_t* active_idx = nullptr, int active_cap = 0,
-                                     int* active_cnt = nullptr);
+                                     int* active_cnt = nullptr, const float* resid_in = nullptr, float* resid_out = nullptr);
 // scratch of decode_matryoshka_launch (per-warp activity counts before the final sum)
 size_t decode_matryoshka_scratch_bytes(int num_sms);
 // packed 2-bit codes [H, D/16] -> T^T as bf16 [D, H] with entries {-2, 0, +2} (B operand of the dense level GEMMs)

@@ -163,7 +163,8 @@ decode_matryoshka_kernel(const uint2* __restrict__ cand, const int* __restrict__
                          const float* __restrict__ x_f32, const float* __restrict__ w_f32,
                          const float* __restrict__ b_enc, float thr_value, int exact,
                          int32_t* __restrict__ active_idx /* [B, active_cap] or null */, int active_cap,
-                         int* __restrict__ active_cnt /* [B] */) {
+                         int* __restrict__ active_cnt /* [B] */,
+                         const float* __restrict__ resid_in /* [B, D] or null */, float* __restrict__ resid_out /* [B, D] */) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned full = 0xffffffffu;
   const int words = D >> 4;                 // <= 32: lane `l` owns word l (features 16 l .. 16 l + 15)
@@ -272,6 +273,18 @@ decode_matryoshka_kernel(const uint2* __restrict__ cand, const int* __restrict__
       }
     }
     if (active_idx != nullptr && lane == 0) active_cnt[row] = n_act;
+    // rq_sae: the next stage's input, (residual - reconstruction) * 2 (sae/residual_quantized.py:67), from the
+    // final reconstruction still in registers
+    if (resid_out != nullptr && has_word) {
+      const float4* rin = reinterpret_cast<const float4*>(resid_in + static_cast<size_t>(row) * D + lane * 16);
+      float4* rout = reinterpret_cast<float4*>(resid_out + static_cast<size_t>(row) * D + lane * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 r = rin[q];
+        rout[q] = make_float4((r.x - run[4 * q]) * 2.f, (r.y - run[4 * q + 1]) * 2.f, (r.z - run[4 * q + 2]) * 2.f,
+                              (r.w - run[4 * q + 3]) * 2.f);
+      }
+    }
   }
   if (lane == 0) {
 #pragma unroll
@@ -352,7 +365,8 @@ const char* decode_matryoshka_launch(const void* cand, const int* cand_cnt, int 
                                      int n_levels, int H, int D, const float* bias, float* result,
                                      unsigned long long* level_count, const float* x_f32, const float* w_f32,
                                      const float* b_enc, float thr_value, int exact, void* scratch, int num_sms,
-                                     cudaStream_t stream, int32_t* active_idx, int active_cap, int* active_cnt) {
+                                     cudaStream_t stream, int32_t* active_idx, int active_cap, int* active_cnt,
+                                     const float* resid_in, float* resid_out) {
   if (n_levels > 8) return "decode_matryoshka: at most 8 levels (n_bits <= 8)";
   if (D > 512 || (D % 16) != 0) return "decode_matryoshka: D must be a multiple of 16, <= 512";
   int blocks = (B + kMatWarps - 1) / kMatWarps;
@@ -361,7 +375,8 @@ const char* decode_matryoshka_launch(const void* cand, const int* cand_cnt, int 
   const uint2* c2 = reinterpret_cast<const uint2*>(cand);
 #define QSAE_MAT(NL) \
   decode_matryoshka_kernel<NL><<<blocks, kMatWarps * 32, 0, stream>>>(c2, cand_cnt, nsub, cap, B, packed, scale, level_start, \
-      n_levels, H, D, bias, result, partial, x_f32, w_f32, b_enc, thr_value, exact, active_idx, active_cap, active_cnt)
+      n_levels, H, D, bias, result, partial, x_f32, w_f32, b_enc, thr_value, exact, active_idx, active_cap, active_cnt, \
+      resid_in, resid_out)
   int nl;
   if (n_levels <= 1) { nl = 1; QSAE_MAT(1); }
   else if (n_levels <= 2) { nl = 2; QSAE_MAT(2); }

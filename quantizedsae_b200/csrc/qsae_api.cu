@@ -673,17 +673,19 @@ int qsae_matryoshka_forward(const float* x_f32, const uint16_t* w_bf16, const fl
                             int B, int H, int D, float* result, unsigned long long* level_count, int* overflow,
                             void* workspace, size_t workspace_bytes, void* stream) {
   return qsae_matryoshka_forward_active(x_f32, w_bf16, w_f32, w_norm_max, b_enc, packed, scale, level_start, n_levels,
-                                        dec_bias, B, H, D, result, level_count, overflow, nullptr, 0, nullptr, workspace,
-                                        workspace_bytes, stream);
+                                        dec_bias, B, H, D, result, level_count, overflow, nullptr, 0, nullptr, nullptr,
+                                        workspace, workspace_bytes, stream);
 }
 
 int qsae_matryoshka_forward_active(const float* x_f32, const uint16_t* w_bf16, const float* w_f32,
                                    const float* w_norm_max, const float* b_enc, const uint32_t* packed,
                                    const float* scale, const int* level_start, int n_levels, const float* dec_bias,
                                    int B, int H, int D, float* result, unsigned long long* level_count, int* overflow,
-                                   int32_t* active_idx, int active_cap, int32_t* active_cnt, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
+                                   int32_t* active_idx, int active_cap, int32_t* active_cnt, float* residual_out,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
   if (B == 0) return QSAE_OK;
+  if (residual_out != nullptr && (reinterpret_cast<uintptr_t>(residual_out) & 15) != 0)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_forward: residual_out must be 16-byte aligned");
   if (active_idx != nullptr && (active_cap < 1 || active_cnt == nullptr))
     return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_forward: active list export needs active_cap >= 1 and active_cnt");
   if (!x_f32 || !w_bf16 || !b_enc || !packed || !scale || !level_start || !result || !level_count || !overflow || !workspace)
@@ -724,7 +726,8 @@ int qsae_matryoshka_forward_active(const float* x_f32, const uint16_t* w_bf16, c
                                                                      scale, level_start, n_levels, H, D, dec_bias, result,
                                                                      level_count, x_f32, w_f32, b_enc, kActiveThreshold,
                                                                      exact, ws + mp.scratch_off, num_sms(), st, active_idx,
-                                                                     active_cap, active_cnt));
+                                                                     active_cap, active_cnt, residual_out ? x_f32 : nullptr,
+                                                                     residual_out));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -72,10 +72,23 @@ class QuantizedMatryoshkaDecoder(nn.Module):
         if not self.weight.is_cuda:
             raise RuntimeError("QuantizedMatryoshkaDecoder runs only on CUDA (no CPU fallback)")
         ls, lf = self._levels()
-        return self._prep.get(
-            "packed", param_key(self.weight, self.weight_mirror),
-            lambda: _lib.pack_matryoshka(self.weight.detach().contiguous(), self.weight_mirror.detach().contiguous(),
-                                         ls, lf))
+
+        def make():
+            packed, scale = _lib.pack_matryoshka(self.weight.detach().contiguous(), self.weight_mirror.detach().contiguous(),
+                                                 ls, lf)
+            # the reference warns on every forward when a row of S + S_mirror is all zero (:85-86); here once per
+            # weight version, when the dictionary is packed (scale = factor / (norm + 1e-8): norm < 1e-6 <=> scale > factor * 1e6 / 1.01)
+            starts = self._level_starts_host()
+            for i in range(self.n_bits):
+                sl = scale[starts[i]:starts[i + 1]]
+                if sl.numel():
+                    factor = float(lf[i])
+                    norms = factor / sl - 1e-8
+                    if bool((norms < 1e-6).any()):
+                        print(f"Warning: Very small norm detected at level {i}: min={float(norms.min().clamp_min(0.0)):.2e}")
+            return packed, scale
+
+        return self._prep.get("packed", param_key(self.weight, self.weight_mirror), make)
 
     def _t_bf16(self):
         """T^T [D, H] bf16 for the dense level GEMMs (cached per weight version)."""
@@ -194,9 +207,10 @@ class QuantizedMatryoshkaSAE(SparseAutoencoder):
         return {"latent_groups": groups, "reconstruction_levels": levels, "level_counts": counts,
                 "active_idx": a_idx, "active_cnt": a_cnt}
 
-    def _forward_sparse(self, x):
-        """The sparse path without the host-side overflow check: -> (result [n_bits, B, D], counts, overflow [1]).
-        Callers that chain several forwards (rq_sae) read the flags once at the end instead of once per stage."""
+    def _forward_sparse(self, x, want_residual: bool = False):
+        """The sparse path without the host-side overflow check: -> (result [n_bits, B, D], counts, overflow [1]
+        [, next residual (x - result[-1]) * 2]). Callers that chain several forwards (rq_sae) read the flags once at
+        the end instead of once per stage, and take the residual from the level decoder instead of a separate pass."""
         lin = self.encoder[0]
         packed, scale = self.decoder._packed()
         ls, _ = self.decoder._levels()
@@ -204,7 +218,7 @@ class QuantizedMatryoshkaSAE(SparseAutoencoder):
             x, self._w_bf16(), lin.bias.detach(), packed, scale, ls, self.n_bits,
             self.decoder.bias.detach() if self.allow_bias else None,
             w_f32=lin.weight.detach().contiguous() if self.exact else None,
-            w_norm_max=self._w_norm_max() if self.exact else None)
+            w_norm_max=self._w_norm_max() if self.exact else None, want_residual=want_residual)
 
     def forward(self, x):
         x = require_cuda_input(x, self)

@@ -50,11 +50,10 @@ class ResidualQuantizedSAE(SparseAutoencoder):
             groups, levels, flags = [], [], []
             B = x.shape[0]
             for sae in self.saes:
-                result, counts, overflow = sae._forward_sparse(residual)
+                result, counts, overflow, residual = sae._forward_sparse(residual, want_residual=True)
                 groups.append(counts[-1].to(torch.float32) / float(max(B, 1)))
                 levels.append(result[-1])
                 flags.append(overflow)
-                residual = _lib.residual_update(residual, result[-1])
             if int(torch.cat(flags).sum().item()) == 0:
                 for sae in self.saes:
                     sae.last_path = "sparse"
