@@ -849,7 +849,10 @@ const char* select_topk_list_launch(const SelectLaunch& p, const int* count, con
     if (e != cudaSuccess) return cudaGetErrorString(e);
     attr_set = true;
   }
-  select_topk_list_kernel<<<num_sms, kSelThreads, smem, stream>>>(p, n_max, ksort, count, rows);
+  // persistent grid, as many blocks as fit an SM's shared memory (at most 6); returns at once when the list is empty
+  int per_sm = static_cast<int>((200 * 1024) / (smem + 2048));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
+  select_topk_list_kernel<<<num_sms * per_sm, kSelThreads, smem, stream>>>(p, n_max, ksort, count, rows);
   return cuda_err(cudaGetLastError());
 }
 
