@@ -40,22 +40,29 @@ BSAE_CASES = {
     "bsae_polar_d512_h4096": dict(D=512, H=4096, n_bits=4, gamma=4.0, B=48, polar=True,  bf16=True,  seed=14),
     "bsae_soft_d512_h4096":  dict(D=512, H=4096, n_bits=4, gamma=1.5, B=24, polar=False, bf16=False, seed=15),
     "bsae_polar_d256_h8192_2b": dict(D=256, H=8192, n_bits=2, gamma=2.0, B=40, polar=True, bf16=True, seed=16),
+    # the headline shape itself (BASELINE config 1: 512 -> 32768, n_bits = 4, gamma = 4.0, reference-default k = 65);
+    # "big": the fixture stores a sha256 of the [H, D] integer dictionary instead of the array
+    "bsae_polar_d512_h32768": dict(D=512, H=32768, n_bits=4, gamma=4.0, B=16, polar=True, bf16=True, seed=17, big=True),
 }
 
 BASELINE_CASES = {
     "baseline_d64_h2048":  dict(D=64,  H=2048, B=32, bf16=False, seed=21),
     "baseline_d512_h4096": dict(D=512, H=4096, B=40, bf16=True,  seed=22),
+    "baseline_d512_h32768": dict(D=512, H=32768, B=16, bf16=True, seed=23),        # BASELINE config 2 shape
 }
 
 TSAE_CASES = {
     "tsae_d64_h2048":  dict(D=64,  H=2048, B=32, bf16=False, seed=31),
     "tsae_d512_h4096": dict(D=512, H=4096, B=24, bf16=True,  seed=32),
+    "tsae_d512_h32768": dict(D=512, H=32768, B=8, bf16=True, seed=33),             # BASELINE config 3 shape
 }
 
 QSAE_CASES = {
     "qsae_d64_h2048":  dict(D=64,  H=2048, n_bits=4, abs_range=4.0, B=32, enc_bias=-0.5, bf16=False, allow_bias=True,  seed=41),
     "qsae_d512_h4096": dict(D=512, H=4096, n_bits=4, abs_range=1.5, B=24, enc_bias=-0.543, bf16=True, allow_bias=True, seed=42),
     "qsae_d64_h1024_dense_nobias": dict(D=64, H=1024, n_bits=3, abs_range=4.0, B=16, enc_bias=0.0, bf16=False, allow_bias=False, seed=43),
+    # BASELINE config 4 shape (bias -0.543: mean L0 ~ 34)
+    "qsae_d512_h32768": dict(D=512, H=32768, n_bits=4, abs_range=4.0, B=16, enc_bias=-0.543, bf16=True, allow_bias=True, seed=44),
 }
 
 
@@ -153,6 +160,18 @@ def rqsae_state_dict(inp: dict, n_bits: int) -> dict:
         sd[f"saes.{i}.decoder.weight_mirror"] = inp[f"Wm{i}"]
         sd[f"saes.{i}.decoder.bias"] = inp[f"bd{i}"]
     return sd
+
+
+def int_weights_sha(int_w: np.ndarray) -> str:
+    """sha256 of the [H, D] integer dictionary as int8, row-major (big fixtures store this instead of the array)."""
+    return hashlib.sha256(np.ascontiguousarray(int_w, dtype=np.int8).tobytes()).hexdigest()
+
+
+def int_weights_match(got: np.ndarray, g) -> bool:
+    """got == the reference's quantized_int_weights() recorded in fixture g (array, or its sha256 for big cases)."""
+    if "int_weights" in g.files:
+        return bool(np.array_equal(got, g["int_weights"]))
+    return int_weights_sha(got) == str(g["int_weights_sha"])
 
 
 def checksum(arrays: dict) -> str:

@@ -45,10 +45,12 @@ def make_bsae(ref, name, cfg):
     vals, idx = cases.sparse_from_dense(_np(latent))
     k = int(cfg["H"] * m.k)
     assert vals.shape[1] == k, (vals.shape, k)
+    iw = _np(intw).astype(np.int8)
+    dictionary = dict(int_weights_sha=cases.int_weights_sha(iw)) if cfg.get("big") else dict(int_weights=iw)
     np.savez_compressed(
         OUT / f"{name}.npz", input_sha=cases.checksum(inp), k=k,
         latent_vals=vals, latent_idx=idx, recon=_np(recon), polarize=np.float64(pol.item()),
-        int_weights=_np(intw).astype(np.int8), soft_weights_row0=_np(softw)[:4].copy(),
+        soft_weights_row0=_np(softw)[:4].copy(), **dictionary,
         state_keys=np.array(sorted(m.state_dict().keys())),
         state_shapes=np.array([str(tuple(v.shape)) for _, v in sorted(m.state_dict().items())]),
     )
@@ -168,6 +170,14 @@ def main():
     if "--only-rqsae" in sys.argv:       # added after the first fixture set was committed
         for name, cfg in cases.RQSAE_CASES.items():
             make_rqsae(ref, name, cfg)
+        return
+    if "--only-headline-shapes" in sys.argv:   # the H = 32768 cases, added later still
+        make_bsae(ref, "bsae_polar_d512_h32768", cases.BSAE_CASES["bsae_polar_d512_h32768"])
+        make_baseline(ref, "baseline_d512_h32768", cases.BASELINE_CASES["baseline_d512_h32768"])
+        make_tsae(ref, "tsae_d512_h32768", cases.TSAE_CASES["tsae_d512_h32768"])
+        make_qsae(ref, "qsae_d512_h32768", cases.QSAE_CASES["qsae_d512_h32768"])
+        for p in sorted(OUT.glob("*h32768.npz")):
+            print(f"{p.name:40s} {p.stat().st_size/1024:8.1f} KiB")
         return
     for name, cfg in cases.RQSAE_CASES.items():
         make_rqsae(ref, name, cfg)

@@ -74,7 +74,7 @@ def test_pack_bitplanes_matches_reference_int_weights(cuda_device, golden_dir, n
     inp = cases.bsae_inputs(cfg)
     packed, pol, gap = L.pack_bitplanes(T(inp["logits"], cuda_device), cfg["D"], cfg["n_bits"])
     got = O.unpack_nibbles(packed.cpu().numpy()) if cfg["n_bits"] <= 4 else packed.cpu().numpy().view(np.int8)
-    assert np.array_equal(got, g["int_weights"])               # reference quantized_int_weights()
+    assert cases.int_weights_match(got, g)                     # reference quantized_int_weights()
     assert pol == pytest.approx(float(g["polarize"]), rel=1e-5, abs=1e-9)
     assert (gap == 0.0) == cfg["polar"]
     soft = L.dequant_soft(T(inp["logits"], cuda_device), cfg["D"], cfg["n_bits"]).cpu().numpy()
@@ -339,7 +339,7 @@ def test_bsae_module_matches_reference(cuda_device, golden_dir, name):
     assert float(pol) == pytest.approx(float(g["polarize"]), rel=1e-5, abs=1e-9)
     assert m.decoder.resolved_mode() == ("int" if cfg["polar"] else "soft")
     assert int(m.last_flags.sum()) == 0
-    assert np.array_equal(m.decoder.quantized_int_weights().cpu().numpy().astype(np.int8), g["int_weights"])
+    assert cases.int_weights_match(m.decoder.quantized_int_weights().cpu().numpy().astype(np.int8), g)
     # sparse return form carries the same information
     m.return_dense = False
     with torch.no_grad():
