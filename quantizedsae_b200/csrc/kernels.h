@@ -14,7 +14,8 @@ constexpr int kMaxSplits = 8;      // max CTAs sharing one row block along the l
 constexpr int kMaxK = 224;         // == QSAE_MAX_K: largest k of the warp-level selection paths
 constexpr int kMaxKLarge = 4096;   // == QSAE_MAX_K_LARGE: largest k of the block-level (radix select) paths
 constexpr size_t kSelectSmemBudget = 200 * 1024;   // shared memory of the block-per-row select kernels
-constexpr int kTopM = 16;          // register-resident top list of the sample pre-pass (mode 5)
+constexpr int kTopM = 64;          // values a thread keeps in the sample pre-pass (mode 5): top 2 of 32 column classes
+constexpr int kPriorMaxRank = 16;  // largest rank m of the prior threshold among a row's nsub * kTopM kept values
 
 struct EncodeLaunch {
   int B, H, D;
@@ -29,7 +30,7 @@ struct EncodeLaunch {
   const float* prior;   // mode 4: per-row threshold at prior[row * prior_stride]
   int prior_stride;
   int* overflow;        // mode 4 with k_sel <= 0 (threshold only): set to 1 when a buffer filled up
-  float* top_out;       // mode 5: [B][n_splits*2][kTopM] sorted largest values of each sub-stream
+  float* top_out;       // mode 5: [B][n_splits*2][kTopM] the two largest values of each column class, per sub-stream
   void* cand;           // [B][n_splits*2][cap] {float bits, int32 column}
   int* cand_cnt;        // [B][n_splits*2]
   float* cand_thr;      // [B][n_splits*2] inclusive lower bound of the row's k_sel-th largest value

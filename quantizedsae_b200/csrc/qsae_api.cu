@@ -67,10 +67,11 @@ void plan_stage(int B, int H, int k_sel, StageKind kind, bool allow_split_overri
     }
   }
   if (kind == kStageSamplePre && (B + kEncBM - 1) / kEncBM >= num_sms()) sp->n_splits = 1;  // enough row blocks
+  if (kind == kStageSamplePre && sp->n_splits > 4) sp->n_splits = 4;   // the prior kernel sorts at most 8 x kTopM values per row
   sp->tiles_per_split = (sp->n_tiles + sp->n_splits - 1) / sp->n_splits;
   sp->nsub = sp->n_splits * 2;
   if (kind == kStageSamplePre) {
-    sp->mode = 5;   // register-resident top list, no survivor buffers: cand region = the lists
+    sp->mode = 5;   // register-resident class top-2, no survivor buffers: cand region = the kept values
     sp->cap = 0;
     sp->cand_off = align_up(base, 256);
     sp->cnt_off = sp->thr_off = sp->cand_off;
@@ -132,7 +133,7 @@ int plan_encode(int B, int H, int D, int k, int exact, int n_sample, EncodePlan*
   if (n_sample >= 256 && H >= 8 * static_cast<long long>(n_sample)) {
     const char* ov = getenv("QSAE_ENCODE_PRIOR");  // "0" switches the prior off (tuning experiments)
     const int m = choose_prior_rank(k_sel, static_cast<double>(n_sample) / H);
-    if (!(ov && atoi(ov) == 0) && m <= kTopM && m <= n_sample) {
+    if (!(ov && atoi(ov) == 0) && m <= kPriorMaxRank && m <= n_sample) {
       pl->use_prior = true;
       pl->m = m;
     }

@@ -470,8 +470,8 @@ __device__ __forceinline__ int small_select(uint64_t* stage, int n, int k_sel, i
 
 // Bitonic sort (descending) of 32 * P composite keys held P per lane, element e = j * 32 + lane:
 // strides below 32 exchange through shuffles, larger strides are register moves.
-template <int P>
-__device__ __forceinline__ void warp_bitonic_desc(uint64_t (&k)[P], int lane) {
+template <int P, typename K>
+__device__ __forceinline__ void warp_bitonic_desc(K (&k)[P], int lane) {
   const unsigned full = 0xffffffffu;
 #pragma unroll
   for (int size = 2; size <= 32 * P; size <<= 1) {
@@ -483,7 +483,7 @@ __device__ __forceinline__ void warp_bitonic_desc(uint64_t (&k)[P], int lane) {
         for (int j = 0; j < P; ++j) {
           if ((j & js) == 0) {
             const bool desc = ((j * 32) & size) == 0;   // size >= 64 here: depends on j only
-            const uint64_t a = k[j], b = k[j | js];
+            const K a = k[j], b = k[j | js];
             const bool swap = (a < b) == desc;
             k[j] = swap ? b : a;
             k[j | js] = swap ? a : b;
@@ -494,8 +494,8 @@ __device__ __forceinline__ void warp_bitonic_desc(uint64_t (&k)[P], int lane) {
         for (int j = 0; j < P; ++j) {
           const bool desc = (((j * 32) | lane) & size) == 0;
           const bool lower = (lane & stride) == 0;
-          const uint64_t mine = k[j];
-          const uint64_t other = __shfl_xor_sync(full, mine, stride);
+          const K mine = k[j];
+          const K other = __shfl_xor_sync(full, mine, stride);
           const bool mine_big = mine > other;
           const bool take_max = (lower == desc);
           k[j] = (take_max == mine_big) ? mine : other;
@@ -658,38 +658,24 @@ select_small_kernel(SelectLaunch p, int ksort, const int* count, const int32_t* 
   }
 }
 
-// prior[row] = m-th largest of the row's n = nsub * kTopM pre-pass values (n <= 512, P = values
-// per lane). Each lane ranks its own values against everybody's by broadcast -- no dependent
-// chain: the m-th largest is the value with exactly m - 1 entries ahead of it in
-// (value desc, slot asc) order.
+// prior[row] = m-th largest of the row's n = nsub * kTopM pre-pass values (n <= 512, P = values per lane,
+// m <= 32): one warp per row sorts the ordered-integer images of the floats in registers (bitonic network,
+// shuffles below stride 32) and lane m - 1 holds the answer.
 template <int P>
 __global__ void __launch_bounds__(256)
 prior_from_top_kernel(const float* __restrict__ top, int B, int n, int m, float* __restrict__ prior) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= B) return;
-  const unsigned full = 0xffffffffu;
   const float* src = top + static_cast<size_t>(row) * n;
-  uint64_t key[P];
-  int rank[P];
+  uint32_t key[P];
 #pragma unroll
   for (int i = 0; i < P; ++i) {
     const int slot = lane + 32 * i;
-    key[i] = (slot < n) ? make_sort_key(src[slot], static_cast<uint32_t>(slot)) : 0ull;
-    rank[i] = 0;
+    key[i] = (slot < n) ? float_to_key(src[slot]) : 0u;   // padding sorts last
   }
-#pragma unroll
-  for (int i2 = 0; i2 < P; ++i2) {
-#pragma unroll 8
-    for (int l2 = 0; l2 < 32; ++l2) {
-      const uint64_t other = __shfl_sync(full, key[i2], l2);
-#pragma unroll
-      for (int i = 0; i < P; ++i) rank[i] += (other > key[i]) ? 1 : 0;
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < P; ++i)
-    if (key[i] != 0ull && rank[i] == m - 1) prior[row] = sort_key_value(key[i]);
+  warp_bitonic_desc<P>(key, lane);
+  if (lane == m - 1) prior[row] = key_to_float(key[0]);   // sorted position e = j * 32 + lane, m <= 32: j = 0
 }
 
 // Streaming survivors from a dense row, one warp per row, lanes over 32 consecutive columns.
