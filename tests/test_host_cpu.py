@@ -222,3 +222,29 @@ def test_inference_registry_mirrors_the_reference(tmp_path):
     torch.save({"state_dict": rq.state_dict()}, tmp_path / "rq.pth")     # wrapped checkpoints are unwrapped
     wr = I.load_sae("rq_sae", device="cpu", checkpoint_path=tmp_path / "rq.pth", input_dim=16, hidden_dim=64, n_bits=3)
     assert set(wr.decoder_dictionary()) >= {"level_0_weight", "level_2_effective_weight", "level_0_bias"}
+
+
+def test_analysis_has_no_cpu_path():
+    """quantizedsae_b200.analysis mirrors scripts/analysis/dynamic_analysis.py but runs on CUDA only."""
+    from quantizedsae_b200 import analysis as AN
+    from quantizedsae_b200.inference import framework as FW
+
+    for name in ("compute_reconstruction_error", "compute_reconstruction_error_by_level", "compute_l0_by_level",
+                 "compute_activation_stats", "analyze_dataset", "_activation_mask", "_hidden_dim"):
+        assert callable(getattr(AN, name))
+    m = Q.BinarySAE(64, 2048, 4.0, 4)
+    sae = FW.SAEWrapper(FW.SAE_REGISTRY["b_sae"], m, "cpu")
+    assert AN._hidden_dim(sae) == 2048
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        AN.compute_reconstruction_error(sae, [torch.zeros(4, 64)], device="cpu")
+
+
+def test_sharded_transport_defaults_and_k_send():
+    from quantizedsae_b200.sharded import DictionaryShardedBinarySAE, ShardPlan
+
+    m = DictionaryShardedBinarySAE(64, 4096, 4.0, 4, rank=0, world_size=1, ops=False)
+    assert m.transport == "nccl" and m._peer is None and m.trim_min_k == 256
+    p = ShardPlan(2 ** 20, 8, 5)
+    # never more than the shard's own top-k, never less than its fair share
+    for k in (32, 255, 256, 2097, 4096):
+        assert p.k_send(k) <= p.k_local(k) and p.k_send(k) >= min(p.k_local(k), -(-k // 8))
