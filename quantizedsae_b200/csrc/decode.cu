@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "decode_common.cuh"
 #include "kernels.h"
 
 namespace qsae {
@@ -18,19 +19,10 @@ namespace {
 
 constexpr int kDecWarps = 4;
 
-// NCH = number of 256-feature chunks a lane accumulates (D <= 256 * NCH)
-//
-// Exact integer accumulation. The kernel is bound by instruction issue, not by memory (the packed
-// dictionary is L2 resident), and int -> float conversion of every nibble was half of the issue slots.
-// Instead the row's k values are converted ONCE to fixed point, v_j = round(v_j * 2^S) with S chosen
-// from max_j |v_j| so that sum_j 15 |v_j| 2^S < 2^30, and every dictionary nibble contributes one
-// integer multiply-add: acc[d] += u'_jd * vfix_j with u' = w + 8 in [0, 15] (w ^ 8 on the two's
-// complement nibble). The bias of 8 leaves with one correction per row, acc[d] - 8 sum_j vfix_j, and a
-// single int -> float conversion per output feature follows. The sum is exact in integers (order
-// independent, deterministic); the only rounding is that of v_j to >= 18 fractional bits of max|v|.
-// WPL = 32-bit words (8 features each) per lane, read as one vector load: lane l owns the features
-// [8 WPL l, 8 WPL (l + 1)) -- D <= 256 WPL. FULL: D == 256 WPL exactly, no per-word guards.
-template <int WPL, bool FULL, bool RANGE>
+// decode_int4_kernel: one warp per token row around Int4RowDecoder (decode_common.cuh). WIDE (64-bit accumulators)
+// is chosen by the launcher for k > 128, where the 32-bit fixed-point scale would leave fewer than 18 fractional
+// bits of max |v|.
+template <int WPL, bool FULL, bool RANGE, bool WIDE>
 __global__ void __launch_bounds__(kDecWarps * 32)
 decode_int4_kernel(const float* __restrict__ vals, const int32_t* __restrict__ idx, int B, int k,
                    const uint32_t* __restrict__ packed, int H, int D, float scale,
@@ -40,7 +32,6 @@ decode_int4_kernel(const float* __restrict__ vals, const int32_t* __restrict__ i
   if (row >= B) return;
   const unsigned full = 0xffffffffu;
   const int words_per_row = D >> 3;
-  const int w0 = lane * WPL;                      // first word of this lane
   const float* vrow = vals + static_cast<size_t>(row) * k;
   const int32_t* irow = idx + static_cast<size_t>(row) * k;
 
@@ -58,83 +49,17 @@ decode_int4_kernel(const float* __restrict__ vals, const int32_t* __restrict__ i
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(full, amax, o));
   bad = __any_sync(full, bad);
-  int klog = 0;
-  while ((1 << klog) < k) ++klog;
-  const int e2 = max(static_cast<int>((__float_as_uint(amax) >> 23) & 0xFF) - 127, -100);  // amax < 2^(e2 + 1)
-  const int S = min(26 - klog - 1 - e2, 120);                                              // |v| 2^S < 2^(26 - klog)
-  const float to_fixed = __uint_as_float(static_cast<uint32_t>(S + 127) << 23);
-  const float from_fixed = __uint_as_float(static_cast<uint32_t>(127 - S) << 23);
 
-  int acc[WPL][8];
-#pragma unroll
-  for (int c = 0; c < WPL; ++c)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[c][j] = 0;
-  int vsum = 0;
-
+  Int4RowDecoder<WPL, FULL, WIDE> dec;
+  dec.begin(amax, bad, k);
   for (int base = 0; base < k; base += 32) {
     const int e = base + lane;
     int my_i = (e < k) ? irow[e] - idx_offset : -1;
-    const bool mine = my_i >= 0 && my_i < H;
-    // entries outside this dictionary contribute nothing: value 0, row 0
-    const int my_f = mine ? __float2int_rn(vrow[e] * to_fixed) : 0;
-    my_i = mine ? my_i : 0;
-    const int m = min(32, k - base);
-    // dictionary shards own ~1 / G of the winners: skip the rest (warp-uniform test; RANGE is a template
-    // flag because the test costs the plain decoder 10 % of its issue slots)
-    const unsigned owned = RANGE ? __ballot_sync(full, mine) : 0xffffffffu;
-#pragma unroll 4
-    for (int j = 0; j < m; ++j) {
-      if (RANGE && ((owned >> j) & 1u) == 0u) continue;
-      const int vf = __shfl_sync(full, my_f, j);
-      const int i = __shfl_sync(full, my_i, j);
-      vsum += vf;
-      const uint32_t* drow = packed + static_cast<size_t>(i) * words_per_row + w0;
-      uint32_t word[WPL];
-      if constexpr (FULL) {
-        if constexpr (WPL == 1) {
-          word[0] = __ldg(drow);
-        } else if constexpr (WPL == 2) {
-          const uint2 t = __ldg(reinterpret_cast<const uint2*>(drow));
-          word[0] = t.x; word[1] = t.y;
-        } else {
-          const uint4 t = __ldg(reinterpret_cast<const uint4*>(drow));
-          word[0] = t.x; word[1] = t.y; word[2] = t.z; word[3] = t.w;
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < WPL; ++c) word[c] = (w0 + c < words_per_row) ? __ldg(drow + c) : 0x88888888u;
-      }
-#pragma unroll
-      for (int c = 0; c < WPL; ++c) {
-        const uint32_t bits = word[c] ^ 0x88888888u;               // biased nibbles u' = w + 8
-        const uint32_t lo = bits & 0x0F0F0F0Fu;                     // features 0, 2, 4, 6 as bytes
-        const uint32_t hi = (bits >> 4) & 0x0F0F0F0Fu;              // features 1, 3, 5, 7
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          acc[c][2 * q] += static_cast<int>(__byte_perm(lo, 0u, 0x4440u + q)) * vf;
-          acc[c][2 * q + 1] += static_cast<int>(__byte_perm(hi, 0u, 0x4440u + q)) * vf;
-        }
-      }
-    }
+    if (my_i >= H) my_i = -1;
+    const float my_v = (my_i >= 0) ? vrow[e] : 0.f;
+    dec.template add_chunk<RANGE>(my_v, my_i, min(32, k - base), packed, words_per_row, lane);
   }
-  const int corr = 8 * vsum;
-  const float qnan = __uint_as_float(0x7FC00000u);
-#pragma unroll
-  for (int c = 0; c < WPL; ++c) {
-    const int d = (w0 + c) * 8;
-    if (FULL || d < D) {
-      float o[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float sum = static_cast<float>(acc[c][q] - corr) * from_fixed;
-        o[q] = bad ? qnan : (scale * sum + (bias ? __ldg(bias + d + q) : 0.f));
-      }
-      float4* dst = reinterpret_cast<float4*>(recon + static_cast<size_t>(row) * D + d);
-      dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-      dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-    }
-  }
+  dec.finish(scale, bias, recon + static_cast<size_t>(row) * D, D, lane);
 }
 
 // generic row decoder over float4-sized groups: T = float (4 per 16 B) or int8 (4 per 4 B)
@@ -227,15 +152,17 @@ const char* decode_int4_launch(const float* vals, const int32_t* idx, int B, int
   const int blocks = (B + kDecWarps - 1) / kDecWarps;
   const uint32_t* p32 = reinterpret_cast<const uint32_t*>(packed);
   const bool range = skip_unowned || idx_offset != 0;   // dictionary shards skip the winners other shards own
-#define QSAE_DEC4(WPL, FULL)                                                                                          \
-  do {                                                                                                                \
-    if (range)                                                                                                        \
-      decode_int4_kernel<WPL, FULL, true><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, p32, H, D, scale,   \
-                                                                                 bias, recon, idx_offset);            \
-    else                                                                                                              \
-      decode_int4_kernel<WPL, FULL, false><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, p32, H, D, scale,  \
-                                                                                  bias, recon, idx_offset);           \
+#define QSAE_DEC4K(WPL, FULL, RANGE, WIDE)                                                                             \
+  decode_int4_kernel<WPL, FULL, RANGE, WIDE><<<blocks, kDecWarps * 32, 0, stream>>>(vals, idx, B, k, p32, H, D, scale, \
+                                                                                    bias, recon, idx_offset)
+#define QSAE_DEC4(WPL, FULL)                                  \
+  do {                                                        \
+    if (range && wide) QSAE_DEC4K(WPL, FULL, true, true);     \
+    else if (range) QSAE_DEC4K(WPL, FULL, true, false);       \
+    else if (wide) QSAE_DEC4K(WPL, FULL, false, true);        \
+    else QSAE_DEC4K(WPL, FULL, false, false);                 \
   } while (0)
+  const bool wide = k > 128;   // 64-bit accumulators keep >= 30 fractional bits of max |v| for any k
   const bool aligned = (reinterpret_cast<uintptr_t>(packed) & 15) == 0;
   if (D == 256) QSAE_DEC4(1, true);
   else if (D == 512 && aligned) QSAE_DEC4(2, true);
@@ -244,6 +171,7 @@ const char* decode_int4_launch(const float* vals, const int32_t* idx, int B, int
   else if (D <= 512) QSAE_DEC4(2, false);
   else if (D <= 1024) QSAE_DEC4(4, false);
   else return "decode_int4: D must be <= 1024";
+#undef QSAE_DEC4K
 #undef QSAE_DEC4
   return cuda_err(cudaGetLastError());
 }

@@ -81,8 +81,10 @@ struct SelectLaunch {
   float* out_vals;        // [B, k_out]
   int32_t* out_idx;       // [B, k_out]
   int32_t* out_flags;     // [B] or null
-  int* rescue_count;      // prior mode: rows whose prior threshold failed the count check ...
+  int* rescue_count;      // rows that need the exact recomputation (failed count check, uncertified in exact mode) ...
   int32_t* rescue_rows;   // ... are appended here (capacity B) and their output left to the rescue kernel
+  int check_count;        // prior mode: the threshold is only probably valid, so a row with fewer than k_sel
+                          // survivors (or a list that filled up) is sent to the rescue list
   // Layout of the survivor lists: list (row, s) starts at entry (row * row_stride + s * sub_stride) * cap.
   // 0 / 0 = the fused encoder's layout [B][nsub][cap]. Gathered per-shard candidates are [nsub][B][cap].
   long long row_stride, sub_stride;
@@ -94,6 +96,14 @@ struct SelectLaunch {
   // Lists that live in peer memory (dictionary shards, CUDA IPC): list s of row r starts at
   // list_bases[s] + r * cap entries (device array of nsub pointers); null = the cand / stride layout above.
   const void* const* list_bases;
+  // Fused decode (prior path of qsae_bsae_forward): the warp / block that has just selected a row also decodes it,
+  // recon[row, :] = dec_scale * sum_j v_j * dict[i_j, :] + dec_bias (sae/binary.py:38). dec_kind 0 = off,
+  // 1 = packed int4 dictionary with D == 512 (one uint2 per lane), k_out <= 128.
+  int dec_kind;
+  const uint32_t* dec_packed;   // [H, D / 8] words
+  float dec_scale;
+  const float* dec_bias;        // [D] or null
+  float* dec_recon;             // [B, D]
 };
 
 // rescue.cu: exact per-row top-k for the rows listed by the merge kernel (persistent small grid,
@@ -131,6 +141,12 @@ const char* select_small_launch(const SelectLaunch& p, int tier, const int* coun
                                 int* ovf_count, int32_t* ovf_rows, cudaStream_t stream);
 const char* select_topk_list_launch(const SelectLaunch& p, const int* count, const int32_t* rows, int num_sms,
                                     cudaStream_t stream);
+// Tail of the prior path in ONE launch (persistent grid, returns at once when both lists are empty): rows the
+// warp-level merge could not hold (ovf_rows[0, *ovf_count): block-per-row radix select) and rows whose prior
+// failed the count check (r.rescue_rows[0, *r.rescue_count): exact recomputation); a row the block select wants
+// recomputed is recomputed by the same block. Every row handled here is also decoded when p.dec_kind != 0.
+const char* select_tail_launch(const SelectLaunch& p, const RescueLaunch& r, const int* ovf_count,
+                               const int32_t* ovf_rows, int num_sms, cudaStream_t stream);
 // prior[row] = m-th largest of the row's nsub * kTopM pre-pass values
 const char* prior_from_top_launch(const float* top, int B, int nsub, int m, float* prior, cudaStream_t stream);
 // survivors from a dense [R, H] matrix (one sub-stream per row, buffers of kDenseCap entries)

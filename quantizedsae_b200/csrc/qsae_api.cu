@@ -111,7 +111,7 @@ struct EncodePlan {
   int k_sel, m;
   bool use_prior;
   StagePlan main, pre;
-  size_t x_off, prior_off, counters_off, rescue_rows_off, ovf_rows_off, ovf2_rows_off, total;
+  size_t x_off, prior_off, counters_off, rescue_rows_off, ovf_rows_off, total;
 };
 
 int plan_encode(int B, int H, int D, int k, int exact, int n_sample, EncodePlan* pl) {
@@ -142,12 +142,11 @@ int plan_encode(int B, int H, int D, int k, int exact, int n_sample, EncodePlan*
   size_t off = align_up(static_cast<size_t>(B) * D * 2, 1024);
   plan_stage(B, H, k_sel, pl->use_prior ? kStagePriorMain : kStageClassBound, true, off, &pl->main);
   off = pl->main.end;
+  pl->counters_off = off; off += 256;
+  pl->rescue_rows_off = off; off = align_up(off + static_cast<size_t>(B) * 4, 256);
   if (pl->use_prior) {
     pl->prior_off = off; off = align_up(off + static_cast<size_t>(B) * 4, 256);
-    pl->counters_off = off; off += 256;
-    pl->rescue_rows_off = off; off = align_up(off + static_cast<size_t>(B) * 4, 256);
     pl->ovf_rows_off = off; off = align_up(off + static_cast<size_t>(B) * 4, 256);
-    pl->ovf2_rows_off = off; off = align_up(off + static_cast<size_t>(B) * 4, 256);
     plan_stage(B, n_sample, pl->m, kStageSamplePre, false, off, &pl->pre);
     off = pl->pre.end;
   }
@@ -334,7 +333,7 @@ int encode_topk_large(const float* x_f32, const uint16_t* w_bf16, const float* w
   sl.cand = el.cand; sl.cand_cnt = el.cand_cnt; sl.cand_thr = el.cand_thr;
   sl.x_f32 = x_f32; sl.w_f32 = w_f32; sl.bias = b_enc;
   sl.out_vals = out_vals; sl.out_idx = out_idx; sl.out_flags = out_flags;
-  sl.rescue_count = counters; sl.rescue_rows = rescue_rows;
+  sl.rescue_count = counters; sl.rescue_rows = rescue_rows; sl.check_count = 1;
   rc = launch_status("select_topk kernel", select_topk_launch(sl, st));
   if (rc != QSAE_OK) return rc;
   if (getenv("QSAE_DEBUG_LARGE")) {   // diagnostics: survivor statistics of this call (synchronises)
@@ -450,10 +449,20 @@ int qsae_prepare_encoder_sample(const uint16_t* w_bf16, const float* b_enc, int 
 }  // extern "C"
 
 namespace {
+// Decode that the merge kernels of the prior path may fuse (qsae_bsae_forward): packed int4 dictionary, D == 512.
+struct FusedDecode {
+  const uint32_t* packed;
+  float scale;
+  const float* bias;
+  float* recon;
+  bool done;   // out: the reconstruction was written by the merge / tail kernels
+};
+
 int encode_topk_impl(const float* x_f32, const uint16_t* w_bf16, const float* w_f32, const float* b_enc,
                      const uint16_t* w_sample, const float* b_sample, int n_sample,
                      int B, int H, int D, int k, int act, int exact, float* out_vals, int32_t* out_idx,
-                     int32_t* out_flags, void* workspace, size_t workspace_bytes, void* stream) {
+                     int32_t* out_flags, void* workspace, size_t workspace_bytes, void* stream,
+                     FusedDecode* fd = nullptr) {
   if (B == 0) return QSAE_OK;
   if (!x_f32 || !w_bf16 || !b_enc || !out_vals || !out_idx || !workspace)
     return fail(QSAE_ERR_INVALID_ARGUMENT, "encode_topk: null pointer");
@@ -480,6 +489,11 @@ int encode_topk_impl(const float* x_f32, const uint16_t* w_bf16, const float* w_
   rc = launch_status("cast x", cast_bf16_launch(x_f32, x_bf16, static_cast<size_t>(B) * D, st));
   if (rc != QSAE_OK) return rc;
 
+  int* counters = reinterpret_cast<int*>(ws + pl.counters_off);   // [0] rescue rows, [1] merge overflow rows
+  int32_t* rescue_rows = reinterpret_cast<int32_t*>(ws + pl.rescue_rows_off);
+  cudaError_t ce = cudaMemsetAsync(counters, 0, 4 * sizeof(int), st);
+  if (ce != cudaSuccess) return fail(QSAE_ERR_CUDA, "encode_topk: %s", cudaGetErrorString(ce));
+
   if (!pl.use_prior) {
     // ---- class-bound path: one sweep, block-per-row merge
     EncodeLaunch el;
@@ -496,17 +510,23 @@ int encode_topk_impl(const float* x_f32, const uint16_t* w_bf16, const float* w_
     sl.cand = el.cand; sl.cand_cnt = el.cand_cnt; sl.cand_thr = el.cand_thr;
     sl.x_f32 = x_f32; sl.w_f32 = w_f32; sl.bias = b_enc;
     sl.out_vals = out_vals; sl.out_idx = out_idx; sl.out_flags = out_flags;
-    return launch_status("select_topk kernel", select_topk_launch(sl, st));
+    if (exact) { sl.rescue_count = counters; sl.rescue_rows = rescue_rows; }   // uncertified rows only (the bound itself is exact)
+    rc = launch_status("select_topk kernel", select_topk_launch(sl, st));
+    if (rc != QSAE_OK || !exact) return rc;
+    // exact mode: a row whose fp32 re-scoring could not certify the selection is recomputed exactly, as on the
+    // prior path (round 1 left such rows flagged with their bf16-chosen candidates)
+    RescueLaunch rl;
+    memset(&rl, 0, sizeof(rl));
+    rl.B = B; rl.H = H; rl.D = D; rl.k_sel = pl.k_sel; rl.k_out = k; rl.act = act; rl.exact = exact;
+    rl.x_bf16 = x_bf16; rl.w_bf16 = w_bf16; rl.x_f32 = x_f32; rl.w_f32 = w_f32; rl.bias = b_enc;
+    rl.rescue_count = counters; rl.rescue_rows = rescue_rows;
+    rl.out_vals = out_vals; rl.out_idx = out_idx; rl.out_flags = out_flags;
+    return launch_status("rescue kernel", rescue_rows_launch(rl, num_sms(), st));
   }
 
   // ---- prior-threshold path
   float* prior = reinterpret_cast<float*>(ws + pl.prior_off);
-  int* counters = reinterpret_cast<int*>(ws + pl.counters_off);   // [0] rescue rows, [1] / [2] merge overflow rows (tier 1 / 2)
-  int32_t* rescue_rows = reinterpret_cast<int32_t*>(ws + pl.rescue_rows_off);
   int32_t* ovf_rows = reinterpret_cast<int32_t*>(ws + pl.ovf_rows_off);
-  int32_t* ovf2_rows = reinterpret_cast<int32_t*>(ws + pl.ovf2_rows_off);
-  cudaError_t ce = cudaMemsetAsync(counters, 0, 4 * sizeof(int), st);
-  if (ce != cudaSuccess) return fail(QSAE_ERR_CUDA, "encode_topk: %s", cudaGetErrorString(ce));
   // 1. pre-pass: the fused kernel over the sampled dictionary rows, top list kept in registers
   EncodeLaunch pe;
   fill_encode_launch(&pe, pl.pre, B, D, act, b_sample, ws);
@@ -532,26 +552,27 @@ int encode_topk_impl(const float* x_f32, const uint16_t* w_bf16, const float* w_
   sl.cand = el.cand; sl.cand_cnt = el.cand_cnt; sl.cand_thr = el.cand_thr;
   sl.x_f32 = x_f32; sl.w_f32 = w_f32; sl.bias = b_enc;
   sl.out_vals = out_vals; sl.out_idx = out_idx; sl.out_flags = out_flags;
-  sl.rescue_count = counters; sl.rescue_rows = rescue_rows;
-  //    tier 1: rows with <= 512 survivors (the expected count is ~32 m); tier 2: <= 1024; then block per row
+  sl.rescue_count = counters; sl.rescue_rows = rescue_rows; sl.check_count = 1;
+  // warp per row: up to 512 survivors in registers (the expected count is ~32 m); rows with more take a two-pass
+  // prefilter inside the same warp (round 1 had a second launch with 32 keys per lane for them: 25 us at B = 4096
+  // for ~4 % of the rows, more than the first tier). When the caller decodes with the packed int4 dictionary the
+  // warp that has just sorted a row also decodes it.
+  if (fd != nullptr && D == 512 && k <= 128 && (reinterpret_cast<uintptr_t>(fd->packed) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(fd->recon) & 15) == 0) {
+    sl.dec_kind = 1; sl.dec_packed = fd->packed; sl.dec_scale = fd->scale; sl.dec_bias = fd->bias; sl.dec_recon = fd->recon;
+    fd->done = true;
+  }
   rc = launch_status("select_small kernel", select_small_launch(sl, 16, nullptr, nullptr, num_sms(), counters + 1, ovf_rows, st));
   if (rc != QSAE_OK) return rc;
-  //  tier 2: rows with up to 1024 survivors, 32 keys per lane (3 % of the rows at k = 32, ~15 % at k = 65); the rest and
-  //  anything larger: block per row. (Measured: sending tier-1 overflow straight to the block kernel is slower,
-  //  2.586 vs 2.530 ms/step at k = 65.)
-  rc = launch_status("select_small kernel (tier 2)",
-                     select_small_launch(sl, 32, counters + 1, ovf_rows, num_sms(), counters + 2, ovf2_rows, st));
-  if (rc != QSAE_OK) return rc;
-  rc = launch_status("select_topk list kernel", select_topk_list_launch(sl, counters + 2, ovf2_rows, num_sms(), st));
-  if (rc != QSAE_OK) return rc;
-  // 4. rows whose prior failed the count check: exact recomputation
+  // tail, one launch: rows the warp merge could not hold (floods of equal values) through the block-per-row select,
+  // rows whose prior failed the count check through the exact recomputation; both decoded there when fused
   RescueLaunch rl;
   memset(&rl, 0, sizeof(rl));
   rl.B = B; rl.H = H; rl.D = D; rl.k_sel = pl.k_sel; rl.k_out = k; rl.act = act; rl.exact = exact;
   rl.x_bf16 = x_bf16; rl.w_bf16 = w_bf16; rl.x_f32 = x_f32; rl.w_f32 = w_f32; rl.bias = b_enc;
   rl.rescue_count = counters; rl.rescue_rows = rescue_rows;
   rl.out_vals = out_vals; rl.out_idx = out_idx; rl.out_flags = out_flags;
-  return launch_status("rescue kernel", rescue_rows_launch(rl, num_sms(), st));
+  return launch_status("select_tail kernel", select_tail_launch(sl, rl, counters + 1, ovf_rows, num_sms(), st));
 }
 }  // namespace
 
@@ -573,9 +594,11 @@ int qsae_bsae_forward(const float* x_f32, const uint16_t* w_bf16, const float* w
   if (B == 0) return QSAE_OK;
   if (!packed || !recon) return fail(QSAE_ERR_INVALID_ARGUMENT, "bsae_forward: null pointer");
   if (n_bits < 1 || n_bits > 8) return fail(QSAE_ERR_INVALID_ARGUMENT, "bsae_forward: 1 <= n_bits <= 8");
+  FusedDecode fd = {reinterpret_cast<const uint32_t*>(packed), qstep, dec_bias, recon, false};
   int rc = encode_topk_impl(x_f32, w_bf16, w_f32, b_enc, w_sample, b_sample, n_sample, B, H, D, k, QSAE_ACT_NONE, exact,
-                            out_vals, out_idx, out_flags, workspace, workspace_bytes, stream);
+                            out_vals, out_idx, out_flags, workspace, workspace_bytes, stream, n_bits <= 4 ? &fd : nullptr);
   if (rc != QSAE_OK) return rc;
+  if (fd.done) return QSAE_OK;
   if (n_bits <= 4) return qsae_decode_int4(out_vals, out_idx, B, k, packed, H, D, qstep, dec_bias, recon, stream);
   return qsae_decode_int8(out_vals, out_idx, B, k, reinterpret_cast<const int8_t*>(packed), H, D, qstep, dec_bias, recon,
                           stream);

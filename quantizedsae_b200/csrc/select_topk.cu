@@ -6,7 +6,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include "decode_common.cuh"
 #include "kernels.h"
+#include "rescue_common.cuh"
 #include "topk_common.cuh"
 
 namespace qsae {
@@ -39,10 +41,12 @@ __device__ __forceinline__ void atomic_max_float_key(unsigned* addr, float v) { 
 // filtered by the row-level bound), the block radix-selects the k_sel largest composite keys, all
 // warps re-score them in fp32 when asked to, then the block sorts and emits. Any k_sel that fits
 // shared memory: n_max gathered keys + ksort selected keys.
-template <int THREADS>
-__device__ __forceinline__ void select_row_block(const SelectLaunch& p, int row, int n_max, int ksort,
+// INLINE: the caller recomputes a failing row itself (tail kernel): nothing is appended to the rescue list and the
+// return value says whether the row needs the exact recomputation (uniform over the block).
+template <int THREADS, bool INLINE = false>
+__device__ __forceinline__ bool select_row_block(const SelectLaunch& p, int row, int n_max, int ksort,
                                                  uint8_t* sel_smem) {
-  __shared__ int s_n, s_out, s_ovf;
+  __shared__ int s_n, s_out, s_ovf, s_res;
   __shared__ unsigned long long s_listmin[32];   // smallest composite key of each list (incomplete-list check)
   __shared__ int s_hist[256];
   __shared__ int s_ctl[4];
@@ -116,12 +120,12 @@ __device__ __forceinline__ void select_row_block(const SelectLaunch& p, int row,
   // ---- prior mode: the threshold was only probably valid. Fewer than k_sel survivors means it
   //      was too high for this row, a full list that it was far too low: hand the row to the exact
   //      rescue kernel.
-  if (p.rescue_count != nullptr && (n < p.k_sel || s_ovf != 0)) {
+  if (p.check_count != 0 && (n < p.k_sel || s_ovf != 0)) {
     if (threadIdx.x == 0) {
-      p.rescue_rows[atomicAdd(p.rescue_count, 1)] = row;
+      if (!INLINE) p.rescue_rows[atomicAdd(p.rescue_count, 1)] = row;
       if (p.out_flags != nullptr) p.out_flags[row] = 2;
     }
-    return;
+    return true;
   }
 
   // ---- the k_sel largest composite keys -> sel[0, out)
@@ -226,9 +230,15 @@ __device__ __forceinline__ void select_row_block(const SelectLaunch& p, int row,
       if (!(worst_bf16 + 4.f * max_dev < kth)) flag = 1;
     }
     // an uncertified row is recomputed exactly when a rescue pass follows (it then clears the flag)
-    if (flag != 0 && p.rescue_count != nullptr) p.rescue_rows[atomicAdd(p.rescue_count, 1)] = row;
+    if (flag != 0 && p.rescue_count != nullptr && !INLINE) p.rescue_rows[atomicAdd(p.rescue_count, 1)] = row;
     if (p.out_flags != nullptr) p.out_flags[row] = flag;
+    s_res = (flag != 0 && p.rescue_count != nullptr) ? 1 : 0;
   }
+  if (INLINE) {
+    __syncthreads();
+    return s_res != 0;
+  }
+  return false;
 }
 
 template <int THREADS>
@@ -245,6 +255,64 @@ select_topk_list_kernel(SelectLaunch p, int n_max, int ksort, const int* count, 
   const int n = min(*count, p.B);
   for (int li = blockIdx.x; li < n; li += gridDim.x) {
     select_row_block<kSelThreads>(p, rows[li], n_max, ksort, sel_smem);
+    __syncthreads();
+  }
+}
+
+// Decode of one row by the calling warp from the (values, indices) this block has just written to global memory
+// (callers synchronise the block first).
+__device__ __forceinline__ void decode_row_from_outputs(const SelectLaunch& p, int row, int lane) {
+  const unsigned full = 0xffffffffu;
+  const int k = p.k_out;
+  const volatile float* vrow = p.out_vals + static_cast<size_t>(row) * k;
+  const volatile int32_t* irow = p.out_idx + static_cast<size_t>(row) * k;
+  float amax = 0.f;
+  bool bad = false;
+  for (int e = lane; e < k; e += 32) {
+    if (irow[e] >= 0) {
+      const float v = vrow[e];
+      bad |= !(fabsf(v) <= 3.0e38f);
+      amax = fmaxf(amax, fabsf(v));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(full, amax, o));
+  bad = __any_sync(full, bad);
+  Int4RowDecoder<2, true, false> dec;
+  dec.begin(amax, bad, k);
+  for (int base = 0; base < k; base += 32) {
+    const int e = base + lane;
+    const int my_i = (e < k) ? irow[e] : -1;
+    const float my_v = (my_i >= 0) ? vrow[e] : 0.f;
+    dec.template add_chunk<false>(my_v, my_i, min(32, k - base), p.dec_packed, 64, lane);
+  }
+  dec.finish(p.dec_scale, p.dec_bias, p.dec_recon + static_cast<size_t>(row) * 512, 512, lane);
+}
+
+// Tail of the prior path in one launch: see select_tail_launch in kernels.h.
+__global__ void __launch_bounds__(kSelThreads)
+select_tail_kernel(SelectLaunch p, RescueLaunch r, int n_max, int ksort, const int* ovf_count, const int32_t* ovf_rows) {
+  extern __shared__ __align__(16) uint8_t sel_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // rows listed by the merge kernel for the exact recomputation; this kernel appends nothing to that list
+  const int n_res = min(*r.rescue_count, p.B);
+  const int n_ovf = min(*ovf_count, p.B);
+  for (int li = blockIdx.x; li < n_ovf; li += gridDim.x) {
+    const int row = ovf_rows[li];
+    const bool redo = select_row_block<kSelThreads, true>(p, row, n_max, ksort, sel_smem);
+    __syncthreads();
+    if (redo) {
+      rescue_one_row(r, row);
+      __syncthreads();
+    }
+    if (p.dec_kind == 1 && warp == 0) decode_row_from_outputs(p, row, lane);
+    __syncthreads();
+  }
+  for (int li = blockIdx.x; li < n_res; li += gridDim.x) {
+    const int row = r.rescue_rows[li];
+    rescue_one_row(r, row);
+    __syncthreads();
+    if (p.dec_kind == 1 && warp == 0) decode_row_from_outputs(p, row, lane);
     __syncthreads();
   }
 }
@@ -533,6 +601,37 @@ __device__ __forceinline__ void sort_and_emit(const SelectLaunch& p, int row, co
       if (p.out_flags != nullptr) p.out_flags[row] = flag;
     }
   }
+  if (p.dec_kind == 1) {
+    // fused decode (sae/binary.py:38 restricted to the k winners), straight from the sorted registers. A row that
+    // was just listed for the exact recomputation is decoded again by the tail kernel.
+    const unsigned full = 0xffffffffu;
+    float amax = 0.f;
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const int e = j * 32 + lane;
+      if (e < p.k_out && e < out) {
+        const float v = sort_key_value(k[j]);
+        bad |= !(fabsf(v) <= 3.0e38f);
+        amax = fmaxf(amax, fabsf(v));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(full, amax, o));
+    bad = __any_sync(full, bad);
+    Int4RowDecoder<2, true, false> dec;
+    dec.begin(amax, bad, p.k_out);
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      if (j * 32 < p.k_out) {
+        const int e = j * 32 + lane;
+        const bool valid = e < p.k_out && e < out;
+        dec.template add_chunk<false>(valid ? sort_key_value(k[j]) : 0.f, valid ? static_cast<int>(sort_key_col(k[j])) : -1,
+                                      min(32, p.k_out - j * 32), p.dec_packed, 64, lane);
+      }
+    }
+    dec.finish(p.dec_scale, p.dec_bias, p.dec_recon + static_cast<size_t>(row) * 512, 512, lane);
+  }
 }
 
 // One row: gather -> select -> (re-score) -> sort -> emit. R = survivor keys per lane (capacity 32 * R).
@@ -548,34 +647,82 @@ __device__ __forceinline__ void small_row(const SelectLaunch& p, int row, int ks
     const int t = __shfl_up_sync(full, incl, o);
     if (lane >= o) incl += t;
   }
-  const int n = __shfl_sync(full, incl, 31);
-  if (n > 32 * R) {   // next tier
-    if (lane == 0) ovf_rows[atomicAdd(ovf_count, 1)] = row;
-    return;
-  }
-  if (p.rescue_count != nullptr && n < p.k_sel) {  // prior threshold too high for this row
+  const int n_all = __shfl_sync(full, incl, 31);
+  if (p.check_count != 0 && n_all < p.k_sel) {  // prior threshold too high for this row
     if (lane == 0) {
       p.rescue_rows[atomicAdd(p.rescue_count, 1)] = row;
       if (p.out_flags != nullptr) p.out_flags[row] = 2;
     }
     return;
   }
-  // ---- gather (every survivor already passed the row's threshold in the sweep)
-  for (int s = 0; s < p.nsub; ++s) {
-    const int c = __shfl_sync(full, my_c, s);
-    const int off = __shfl_sync(full, incl, s) - c;
-    const uint2* src = list_ptr(p, row, s);
-    const uint32_t col_add = static_cast<uint32_t>(s) * static_cast<uint32_t>(p.sub_col_offset);
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int n = n_all;
+  if (n_all <= 32 * R) {
+    // ---- gather (every survivor already passed the row's threshold in the sweep)
+    for (int s = 0; s < p.nsub; ++s) {
+      const int c = __shfl_sync(full, my_c, s);
+      const int off = __shfl_sync(full, incl, s) - c;
+      const uint2* src = list_ptr(p, row, s);
+      const uint32_t col_add = static_cast<uint32_t>(s) * static_cast<uint32_t>(p.sub_col_offset);
 #pragma unroll 4
-    for (int e = lane; e < c; e += 32) {
-      const uint2 t = src[e];
-      stage[off + e] = make_sort_key(__uint_as_float(t.x), t.y + col_add);
+      for (int e = lane; e < c; e += 32) {
+        const uint2 t = src[e];
+        stage[off + e] = make_sort_key(__uint_as_float(t.x), t.y + col_add);
+      }
     }
+    __syncwarp();
+  } else {
+    // ---- more survivors than the registers hold (a few per cent of the rows: the survivor count of a prior
+    //      threshold is negative-binomial). Two passes instead of a second kernel tier: the k_sel-th largest value
+    //      of the FIRST 32 R survivors is a lower bound of the row's k_sel-th largest, and only about
+    //      k_sel * n / (32 R) survivors reach it.
+    int filled = 0;
+    for (int s = 0; s < p.nsub && filled < 32 * R; ++s) {
+      const int c = min(__shfl_sync(full, my_c, s), 32 * R - filled);
+      const uint2* src = list_ptr(p, row, s);
+      const uint32_t col_add = static_cast<uint32_t>(s) * static_cast<uint32_t>(p.sub_col_offset);
+#pragma unroll 4
+      for (int e = lane; e < c; e += 32) {
+        const uint2 t = src[e];
+        stage[filled + e] = make_sort_key(__uint_as_float(t.x), t.y + col_add);
+      }
+      filled += c;
+    }
+    __syncwarp();
+    const int kept = small_select<R>(stage, 32 * R, p.k_sel, lane);
+    __syncwarp();
+    uint32_t tmin = 0xFFFFFFFFu;
+    for (int e = lane; e < kept; e += 32) tmin = min(tmin, static_cast<uint32_t>(stage[e] >> 32));
+    tmin = __reduce_min_sync(full, tmin);
+    __syncwarp();
+    int pos = 0;
+    for (int s = 0; s < p.nsub; ++s) {
+      const int c = __shfl_sync(full, my_c, s);
+      const uint2* src = list_ptr(p, row, s);
+      const uint32_t col_add = static_cast<uint32_t>(s) * static_cast<uint32_t>(p.sub_col_offset);
+#pragma unroll 2
+      for (int base = 0; base < c; base += 32) {
+        const int e = base + lane;
+        uint2 t = make_uint2(0u, 0u);
+        if (e < c) t = src[e];
+        const bool keep = (e < c) && (float_to_key(__uint_as_float(t.x)) >= tmin);
+        const unsigned b = __ballot_sync(full, keep);
+        const int at = pos + __popc(b & lt_mask);
+        if (keep && at < 32 * R) stage[at] = make_sort_key(__uint_as_float(t.x), t.y + col_add);
+        pos += __popc(b);
+      }
+    }
+    __syncwarp();
+    if (pos > 32 * R) {   // floods of equal values: block-per-row kernel
+      if (lane == 0) ovf_rows[atomicAdd(ovf_count, 1)] = row;
+      return;
+    }
+    n = pos;
   }
-  __syncwarp();
 
   const int k_sel = min(p.k_sel, n);
   const int out = small_select<R>(stage, n, k_sel, lane);
+  n = n_all;   // candidates were dropped iff the row had more than k_sel survivors in total
   uint64_t* sel = stage;
   for (int e = out + lane; e < ksort; e += 32) sel[e] = 0ull;
   __syncwarp();
@@ -839,6 +986,25 @@ const char* select_topk_list_launch(const SelectLaunch& p, const int* count, con
   int per_sm = static_cast<int>((200 * 1024) / (smem + 2048));
   per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
   select_topk_list_kernel<<<num_sms * per_sm, kSelThreads, smem, stream>>>(p, n_max, ksort, count, rows);
+  return cuda_err(cudaGetLastError());
+}
+
+const char* select_tail_launch(const SelectLaunch& p, const RescueLaunch& r, const int* ovf_count, const int32_t* ovf_rows,
+                               int num_sms, cudaStream_t stream) {
+  const int ksort = next_pow2(p.k_sel < 2 ? 2 : p.k_sel);
+  const int n_max = p.nsub * p.cap;
+  const size_t smem = static_cast<size_t>(n_max + ksort) * sizeof(uint64_t);
+  const size_t budget = 160 * 1024;   // next to ~31 KB of static shared memory (rescue_one_row + the block select)
+  if (smem > budget) return "select_tail: too many survivors per row for shared memory";
+  if (kResThreads != kSelThreads) return "select_tail: block size mismatch";
+  static bool attr_set = false;
+  if (smem > 16 * 1024 && !attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(select_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(budget));
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    attr_set = true;
+  }
+  select_tail_kernel<<<num_sms, kSelThreads, smem, stream>>>(p, r, n_max, ksort, ovf_count, ovf_rows);
   return cuda_err(cudaGetLastError());
 }
 

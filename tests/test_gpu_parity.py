@@ -485,9 +485,80 @@ def test_prior_failure_is_rescued_exactly(cuda_device):
         assert int((flags != 0).sum()) == 0          # rescued rows are exact by construction
 
 
+@pytest.mark.parametrize("k,exact,shift", [(32, False, 0.12), (65, False, 0.2), (32, True, 0.12), (100, False, 0.3)])
+def test_loose_prior_takes_the_two_pass_merge(cuda_device, k, exact, shift):
+    """A prior that is too LOW (sampled rows carry a negative bias): every row keeps far more than the 512 survivors
+    the merge warp holds in registers, so the whole batch goes through the in-warp two-pass prefilter (round 1: a
+    second kernel tier). The result must not depend on the prior at all."""
+    B, H, D = 300, 32768, 512
+    x, W, b = _enc_case(B, H, D, 900 + k, bf16=not exact)
+    dx, dW, db = T(x, cuda_device), T(W, cuda_device), T(b, cuda_device)
+    wb = L.cast_bf16(dW)
+    ws, bs = L.prepare_sample(wb, db)
+    v0, i0, _ = L.encode_topk(dx, wb, dW if exact else None, db, k, exact=exact, sample=(ws, bs))
+    vals, idx, flags = L.encode_topk(dx, wb, dW if exact else None, db, k, exact=exact, want_flags=True,
+                                     sample=(ws, bs - shift))
+    assert_topk_matches(vals.cpu().numpy(), idx.cpu().numpy(), O.encode_pre(x, W, b), k)
+    assert int((flags != 0).sum()) == 0
+    assert torch.equal(i0, idx) and torch.equal(v0, vals)
+    # and the fused decode of the same rows
+    packed = torch.randint(0, 256, (H, D // 2), dtype=torch.uint8, device=cuda_device)
+    bd = torch.randn(D, device=cuda_device)
+    v1, i1, _, r1 = L.bsae_forward(dx, wb, dW if exact else None, db, k, packed, 4, 0.5, bd, exact=exact,
+                                   sample=(ws, bs - shift))
+    assert torch.equal(i1, idx) and torch.equal(v1, vals)
+    assert torch.equal(r1, L.decode_int4(vals, idx, packed, H, D, 0.5, bd))
+
+
+def test_prior_path_relu_flood_goes_through_the_tail_kernel(cuda_device):
+    """ReLU with almost every pre-activation negative: the prior is 0, every list fills with equal zeros, the warp
+    merge cannot separate them (all tie with the k-th value) and hands the rows to the block-per-row select of the
+    tail kernel, which must apply the (value desc, index asc) rule exactly -- and decode the rows when fused."""
+    B, H, D, k = 150, 16384, 512, 32
+    x, W, b = _enc_case(B, H, D, 321)
+    b = (b - 5.0).astype(np.float32)
+    hot = np.random.default_rng(5).choice(H, 20, replace=False)
+    b[hot] += 10.0
+    dx, dW, db = T(x, cuda_device), T(W, cuda_device), T(b, cuda_device)
+    wb = L.cast_bf16(dW)
+    sample = L.prepare_sample(wb, db)
+    vals, idx, _ = L.encode_topk(dx, wb, None, db, k, act=L.ACT_RELU, sample=sample)
+    zr = np.maximum(O.encode_pre(x, W, b), 0).astype(np.float32)
+    rv, ri = O.topk_rows(zr, k)
+    assert (rv == 0).any(1).all(), "every row should end in a run of zeros"
+    assert np.array_equal(idx.cpu().numpy(), ri)
+    assert_vals_close(vals.cpu().numpy(), rv)
+
+
+def test_class_bound_exact_mode_rescues_uncertified_rows(cuda_device):
+    """H < 8192 has no sampled prior (class-bound sweep + block merge). Near-tied fp32 inputs that are not
+    bf16-representable can leave a row uncertified; round 1 returned such rows flagged with their bf16-chosen
+    candidates, now they are recomputed exactly: flags must be 0 and the indices exact."""
+    B, H, D, k = 96, 4096, 512, 32
+    rng = np.random.default_rng(77)
+    x = rng.standard_normal((B, D)).astype(np.float32)
+    W = cases.xavier_uniform(rng, H, D)
+    # clusters of nearly identical dictionary rows: their scores differ by ~1e-6 relative, far inside the bf16 band
+    base = rng.choice(H, 64, replace=False)
+    for j in base:
+        for t in range(1, 24):
+            W[(j + t * 37) % H] = W[j] * np.float32(1.0 + 3e-7 * t)
+    b = np.zeros(H, dtype=np.float32)
+    dx, dW, db = T(x, cuda_device), T(W, cuda_device), T(b, cuda_device)
+    vals, idx, flags = L.encode_topk(dx, L.cast_bf16(dW), dW, db, k, exact=True, want_flags=True)
+    assert int((flags != 0).sum()) == 0
+    z = O.encode_pre(x, W, b)
+    rv, _ = O.topk_rows(z, k)
+    gi = idx.cpu().numpy().astype(np.int64)
+    assert all(len(set(r.tolist())) == k for r in gi)
+    got = np.take_along_axis(z, gi, axis=1)           # the oracle's values at the selected columns, in our order
+    assert np.all(np.abs(got - rv) <= 2e-6 * np.maximum(1.0, np.abs(rv))), "selection differs beyond the planted near-ties"
+    assert_vals_close(vals.cpu().numpy(), got)
+
+
 @pytest.mark.parametrize("B,H,D,k,n_bits,exact", [
     (1000, 32768, 512, 32, 4, False), (700, 32768, 512, 65, 4, False), (300, 32768, 512, 32, 4, True),
-    (513, 16384, 512, 200, 4, False),      # rows spill into the tier-2 / block-level merge kernels
+    (513, 16384, 512, 200, 4, False),      # rows with more survivors than the merge warp holds (two-pass prefilter)
     (200, 16384, 256, 32, 4, False),
     (150, 8192, 512, 16, 8, False),        # int8 dictionary
     (90, 2048, 512, 8, 4, False),          # no sampled prior
