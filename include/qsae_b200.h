@@ -118,6 +118,21 @@ int qsae_prepare_encoder_sample(const uint16_t* w_bf16, const float* b_enc, int 
                                 uint16_t* w_sample /* [n_sample, D] */, float* b_sample /* [n_sample] */,
                                 void* stream);
 
+/* Measurement hook: per-stage events of the sampled-prior path of qsae_encode_topk / qsae_bsae_forward, recorded in
+ * stream order by the calling thread's next calls: [0] start, [1] prior ready (cast + sample pre-pass + prior),
+ * [2] sweep done, [3] merge (+ fused decode) done, [4] tail kernel done, [5] separate decode done (when not fused).
+ * events: n cudaEvent_t handles (n <= QSAE_N_STAGE_EVENTS; entries may be NULL); n = 0 switches it off. */
+#define QSAE_N_STAGE_EVENTS 6
+int qsae_set_stage_events(void* const* events, int n);
+
+/* Prior thresholds of the sampled path on their own (the first launch of qsae_encode_topk for small batches; exposed
+ * for tests and tuning): x -> bf16 (x_bf16 [B, D], out), contraction against the sampled rows on the tensor cores,
+ * prior[b] = m-th largest per-class maximum of row b's sampled pre-activations, a lower bound of the row's m-th
+ * largest sampled value. *ns_out = CTAs per 128-row block used (2 or 4); returns QSAE_ERR_INVALID_ARGUMENT when the
+ * shape has no such launch (large batches and widths other than 256 / 512 use the separate kernels). */
+int qsae_prior_prep(const float* x_f32, const uint16_t* w_sample, const float* b_sample, int n_sample, int B, int D,
+                    int act, int m, uint16_t* x_bf16, float* prior, int* ns_out, void* stream);
+
 /* Measurement hook: when both are non-NULL (cudaEvent_t), the calling thread's next
  * qsae_encode_topk calls record them on their stream immediately before / after the fused
  * encoder kernel, so a caller can time the dominant kernel alone. NULL, NULL switches it off. */

@@ -32,6 +32,8 @@ SYMBOLS = {
     "qsae_encode_topk_workspace_bytes": (_i, [_i, _i, _i, _i, _i, C.POINTER(_sz)]),
     "qsae_prepare_encoder_sample": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "qsae_set_encode_kernel_events": (_i, [_vp, _vp]),
+    "qsae_set_stage_events": (_i, [_vp, _i]),
+    "qsae_prior_prep": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, C.POINTER(_i), _vp]),
     "qsae_encode_topk": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "qsae_bsae_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp,
                                _sz, _vp]),
@@ -218,6 +220,21 @@ def prepare_sample(w_bf16: torch.Tensor, b_enc: torch.Tensor, n_sample: int | No
                                              bs.data_ptr(), _stream()))
     launch_count += 1
     return ws, bs
+
+
+def prior_prep(x: torch.Tensor, sample, m: int, act: int = ACT_NONE):
+    """The single-launch cast + sample pre-pass + prior of the small-batch path -> (x_bf16 [B,D], prior [B], ns)."""
+    global launch_count
+    w_s, b_s = sample
+    _need_cuda(x, w_s, b_s)
+    B, D = x.shape
+    xb = torch.empty((B, D), dtype=torch.bfloat16, device=x.device)
+    prior = torch.empty((B,), dtype=torch.float32, device=x.device)
+    ns = _i(0)
+    check(load().qsae_prior_prep(x.data_ptr(), w_s.data_ptr(), b_s.data_ptr(), w_s.shape[0], B, D, act, m,
+                                 xb.data_ptr(), prior.data_ptr(), C.byref(ns), _stream()))
+    launch_count += 1
+    return xb, prior, int(ns.value)
 
 
 _ws_cache: dict = {}

@@ -778,6 +778,284 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// prior_prep_kernel: cast + sample pre-pass + prior threshold in one launch (small batches; kernels.h PrepLaunch).
+//
+// Round 1 ran three launches before the sweep (cast 5 us, pre-pass 13.5 us, a sorting prior kernel 15 us at
+// B = 4096: a quarter of the step). Here one cluster of NS CTAs per 128-row block does all of it:
+//   * the eight epilogue warps read x in fp32, round it to bf16 and store it in the 128-byte-swizzled K-major
+//     layout the UMMA descriptors expect (the layout TMA would have produced); CTA 0 of the cluster also writes the
+//     row-major bf16 copy the sweep loads by TMA;
+//   * the CTA contracts the x tile against ITS tiles of the sampled dictionary rows (TMA ring -> tcgen05.mma ->
+//     TMEM, as in the sweep) and every epilogue thread keeps one running maximum per column class (column mod 32):
+//     one FMNMX per element;
+//   * the class maxima go to a padded shared-memory tile, the cluster synchronises, and CTA c computes the priors of
+//     rows [128 c / NS, 128 (c + 1) / NS): a warp reads the row's NS x 64 maxima from all CTAs (distributed shared
+//     memory) and bisects for the m-th largest.
+// The m-th largest class maximum is a lower bound of the m-th largest sampled value (distinct elements) and equals
+// it unless two of the row's top m fall into one of the 64 NS classes (17 % of the rows at m = 10, NS = 4: one rank
+// looser, ~3 % more survivors). The sweep's result never depends on it (count check + exact rescue).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPrepStages = 2;
+constexpr int kPrepPitch = 65;   // floats per row of the exchange tile: 2 x 32 class maxima + 1 (conflict-free both ways)
+
+struct PrepSmem { uint32_t a_off, b_off, exch_off, bar_off, tmem_ptr_off, total; };
+__host__ __device__ inline PrepSmem prep_smem_layout(int k_chunks) {
+  PrepSmem L;
+  L.a_off = 0;
+  L.b_off = k_chunks * kABytesPerChunk;
+  L.exch_off = L.b_off + kPrepStages * kBBytesPerStage;
+  L.bar_off = L.exch_off + ((BM * kPrepPitch * 4 + 15) / 16) * 16;
+  L.tmem_ptr_off = L.bar_off + 8 * (1 + 2 * kPrepStages + 4);
+  L.total = L.tmem_ptr_off + 16;
+  return L;
+}
+
+template <int K_CHUNKS, int NS>
+__global__ void __launch_bounds__(384, 1)
+prior_prep_kernel(const __grid_constant__ CUtensorMap tmap_w, PrepLaunch p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const PrepSmem L = prep_smem_layout(K_CHUNKS);
+  uint8_t* a_smem = smem + L.a_off;
+  uint8_t* b_smem = smem + L.b_off;
+  float* exch = reinterpret_cast<float*>(smem + L.exch_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* a_full = bars;
+  uint64_t* full = bars + 1;
+  uint64_t* empty = full + kPrepStages;
+  uint64_t* tmem_full = empty + kPrepStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L.tmem_ptr_off);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();            // == blockIdx.x: the cluster spans grid.x
+  const int m0 = blockIdx.y * BM;
+  const int n_tiles = (p.n_sample + BN - 1) / BN;
+  const int tiles_per_cta = (n_tiles + NS - 1) / NS;
+  const int tile_begin = static_cast<int>(rank) * tiles_per_cta;
+  const int n_my_tiles = max(0, min(n_tiles, tile_begin + tiles_per_cta) - tile_begin);
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0u) {
+      printf("qsae: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
+    mbar_init(a_full, 12);                              // one arrival per converting warp
+    for (int s = 0; s < kPrepStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
+    fence_mbar_init();
+    fence_proxy_async_smem();
+    if (p.zero_counters != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {
+      p.zero_counters[0] = 0; p.zero_counters[1] = 0; p.zero_counters[2] = 0; p.zero_counters[3] = 0;
+    }
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // ------------------------------------------------------------- x -> bf16 operand (all twelve warps)
+  // unit = 8 consecutive columns of one row = one 16-byte swizzle unit; consecutive threads take consecutive units,
+  // so a warp reads 1 KB of one fp32 row and writes 4 x 128 contiguous bytes of shared memory. 16 loads of 16 bytes
+  // in flight per thread (96 KB per SM): the copy is bound by latency x bytes in flight, not by bandwidth.
+  if (warp == 0 && lane == 0 && n_my_tiles > 0) {
+    // the first W stages travel while x is being converted
+    tma_prefetch_desc(&tmap_w);
+    for (int st0 = 0; st0 < kPrepStages && st0 < K_CHUNKS; ++st0) {
+      mbar_arrive_expect_tx(&full[st0], kBBytesPerStage);
+      tma_load_2d(b_smem + st0 * kBBytesPerStage, &tmap_w, &full[st0], st0 * BK, tile_begin * BN, kPolicyEvictLast);
+    }
+  }
+  {
+    constexpr int kUnitsPerRow = K_CHUNKS * 8;
+    constexpr int kUnits = BM * kUnitsPerRow;
+    const bool write_global = rank == 0u;
+    constexpr int BATCH = 8;
+#pragma unroll 1
+    for (int u0 = threadIdx.x; u0 < kUnits; u0 += 384 * BATCH) {
+      float4 lo[BATCH], hi[BATCH];
+#pragma unroll
+      for (int i = 0; i < BATCH; ++i) {
+        const int u = u0 + i * 384;
+        const int r = u / kUnitsPerRow, c8 = (u - r * kUnitsPerRow) * 8;
+        lo[i] = hi[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (u < kUnits && m0 + r < p.B && c8 < p.D) {
+          const float4* src = reinterpret_cast<const float4*>(p.x_f32 + static_cast<size_t>(m0 + r) * p.D + c8);
+          lo[i] = __ldg(src);
+          hi[i] = __ldg(src + 1);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < BATCH; ++i) {
+        const int u = u0 + i * 384;
+        if (u >= kUnits) continue;
+        const int r = u / kUnitsPerRow, cu = u - r * kUnitsPerRow;
+        const uint32_t w0 = pack_bf16x2(lo[i].x, lo[i].y), w1 = pack_bf16x2(lo[i].z, lo[i].w);
+        const uint32_t w2 = pack_bf16x2(hi[i].x, hi[i].y), w3 = pack_bf16x2(hi[i].z, hi[i].w);
+        const int kc = cu >> 3, j = cu & 7;
+        st_shared_v4(smem_u32(a_smem) + kc * kABytesPerChunk + r * 128 + ((j ^ (r & 7)) << 4), w0, w1, w2, w3);
+        if (write_global && m0 + r < p.B && cu * 8 < p.D)
+          *reinterpret_cast<uint4*>(p.x_bf16 + static_cast<size_t>(m0 + r) * p.D + cu * 8) = make_uint4(w0, w1, w2, w3);
+      }
+    }
+    fence_proxy_async_smem();     // generic-proxy stores -> visible to the tensor-core (async proxy) reads
+    __syncwarp();
+    if (lane == 0) mbar_arrive(a_full);
+  }
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer: my tiles of the sampled rows
+    if (lane == 0 && n_my_tiles > 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < n_my_tiles; ++t) {
+        const int n0 = (tile_begin + t) * BN;
+#pragma unroll 1
+        for (int kc = 0; kc < K_CHUNKS; ++kc) {
+          if (t > 0 || kc >= kPrepStages) {     // the first stages were issued before the conversion
+            mbar_wait(&empty[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&full[stage], kBBytesPerStage);
+            tma_load_2d(b_smem + stage * kBBytesPerStage, &tmap_w, &full[stage], kc * BK, n0, kPolicyEvictLast);
+          }
+          if (++stage == kPrepStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- MMA issuer
+    if (lane == 0 && n_my_tiles > 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
+      const uint64_t a_desc0 = umma_desc_kmajor_sw128(smem_u32(a_smem));
+      const uint64_t b_desc0 = umma_desc_kmajor_sw128(smem_u32(b_smem));
+      mbar_wait(a_full, 0);
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < n_my_tiles; ++t) {
+        const int acc = t & 1;
+        mbar_wait(&tmem_empty[acc], ((t >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+#pragma unroll 1
+        for (int kc = 0; kc < K_CHUNKS; ++kc) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((kc * kABytesPerChunk) >> 4);
+          const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((stage * kBBytesPerStage) >> 4);
+#pragma unroll
+          for (int ks = 0; ks < BK / UMMA_K; ++ks)
+            umma_f16_ss(d_tmem, a_desc + ks * 2, b_desc + ks * 2, idesc, (kc | ks) != 0 ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (kc == K_CHUNKS - 1) umma_commit(&tmem_full[acc]);
+          if (++stage == kPrepStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------- class maxima of my sample tiles
+    const int e = warp - 4;
+    const int quad = e & 3;       // TMEM lanes 32*quad .. +31 (hardware: warp_id % 4)
+    const int half = e >> 2;      // columns [half*128, half*128+128) of the tile
+    const int row_in_tile = quad * 32 + lane;
+    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    float top[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) top[j] = -INFINITY;
+    for (int t = 0; t < n_my_tiles; ++t) {
+      const int acc = t & 1;
+      mbar_wait(&tmem_full[acc], (t >> 1) & 1);
+      tc_fence_after();
+      const int n_tile = (tile_begin + t) * BN + half * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(lane_taddr + acc * BN + half * 128 + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n_tile + c * 32;
+        if (col0 + 32 <= p.n_sample) {
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(bias4 + j);
+            float v0 = __uint_as_float(r[4 * j + 0]) + b.x, v1 = __uint_as_float(r[4 * j + 1]) + b.y;
+            float v2 = __uint_as_float(r[4 * j + 2]) + b.z, v3 = __uint_as_float(r[4 * j + 3]) + b.w;
+            if (p.act == 1) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+            top[4 * j + 0] = fmaxf(top[4 * j + 0], v0);
+            top[4 * j + 1] = fmaxf(top[4 * j + 1], v1);
+            top[4 * j + 2] = fmaxf(top[4 * j + 2], v2);
+            top[4 * j + 3] = fmaxf(top[4 * j + 3], v3);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (col0 + j < p.n_sample) {
+              float v = __uint_as_float(r[j]) + __ldg(p.bias + col0 + j);
+              if (p.act == 1) v = fmaxf(v, 0.f);
+              top[j] = fmaxf(top[j], v);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+    // row-major padded tile: thread (row, half) writes 32 consecutive floats; lanes = rows, pitch 65 words
+#pragma unroll
+    for (int j = 0; j < 32; ++j) exch[row_in_tile * kPrepPitch + half * 32 + j] = top[j];
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // every CTA's class maxima are in place (release / acquire at cluster scope)
+
+  // ------------------------------------------------------------- priors of my share of the row block
+  {
+    constexpr int kRowsPerCta = BM / NS;
+    constexpr int NV = 2 * NS;                 // values per lane: NS CTAs x 2 column halves, class = lane
+    const unsigned fullmask = 0xffffffffu;
+    for (int rr = warp; rr < kRowsPerCta; rr += 12) {
+      const int r = static_cast<int>(rank) * kRowsPerCta + rr;
+      const int row = m0 + r;
+      if (row >= p.B) continue;               // warp-uniform
+      uint32_t key[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const uint32_t addr = smem_u32(exch + r * kPrepPitch + (i & 1) * 32 + lane);
+        key[i] = float_to_key(ld_dsmem_f32(addr, static_cast<uint32_t>(i >> 1)));
+      }
+      // m-th largest of the 32 NV keys: bisection from the first bit in which they differ
+      uint32_t a = 0xFFFFFFFFu, o = 0u;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) { a &= key[i]; o |= key[i]; }
+      a = __reduce_and_sync(fullmask, a);
+      o = __reduce_or_sync(fullmask, o);
+      uint32_t T = a;
+      const uint32_t diff = a ^ o;
+      if (diff != 0u) {
+        const int topbit = 31 - __clz(diff);
+        T = a & ~((2u << topbit) - 1u);
+#pragma unroll 1
+        for (int bit = topbit; bit >= 0; --bit) {
+          const uint32_t probe = T | (1u << bit);
+          int c = 0;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) c += (key[i] >= probe) ? 1 : 0;
+          c = __reduce_add_sync(fullmask, c);
+          if (c >= p.m) T = probe;
+        }
+      }
+      if (lane == 0) p.prior[row] = key_to_float(T);
+    }
+  }
+
+  cluster_sync_all();          // no CTA leaves while a peer may still read its class maxima
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -948,6 +1226,58 @@ const char* encode_dense_tc_launch(const uint16_t* x_bf16, const uint16_t* const
   BMaps bm;
   if (const char* err = make_b_maps(&bm, w_parts, n_parts, p)) return err;
   return launch_any<true>(tx, bm, p, stream);
+}
+
+
+namespace {
+template <int K_CHUNKS, int NS>
+cudaError_t launch_prep(const CUtensorMap& tw, const PrepLaunch& p, cudaStream_t stream) {
+  const PrepSmem L = prep_smem_layout(K_CHUNKS);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(prior_prep_kernel<K_CHUNKS, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(NS, (p.B + BM - 1) / BM);
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = L.total;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = NS;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, prior_prep_kernel<K_CHUNKS, NS>, tw, p);
+}
+}  // namespace
+
+int prior_prep_pick_ns(int B, int D, int n_sample, int m, int num_sms) {
+  if (const char* ov = getenv("QSAE_PRIOR_PREP")) {   // "0": always the separate cast / pre-pass / prior kernels
+    if (atoi(ov) == 0) return 0;
+  }
+  if (D != 512 && D != 256) return 0;                  // instantiated widths (the benchmark shapes)
+  if (n_sample < 512 || m < 1 || m > 32) return 0;
+  const int m_tiles = (B + BM - 1) / BM;
+  const int n_tiles = (n_sample + BN - 1) / BN;
+  if (4 * m_tiles <= num_sms - num_sms % 4 && n_tiles >= 4) return 4;
+  if (2 * m_tiles <= num_sms - num_sms % 2 && n_tiles >= 2) return 2;
+  return 0;
+}
+
+const char* prior_prep_launch(const uint16_t* w_sample, const PrepLaunch& p, cudaStream_t stream) {
+  CUtensorMap tw;
+  if (!make_tmap_bf16(&tw, w_sample, p.n_sample, p.D, BN)) return "cuTensorMapEncodeTiled(W sample) failed";
+  cudaError_t e;
+  if (p.D == 512 && p.ns == 4) e = launch_prep<8, 4>(tw, p, stream);
+  else if (p.D == 512 && p.ns == 2) e = launch_prep<8, 2>(tw, p, stream);
+  else if (p.D == 256 && p.ns == 4) e = launch_prep<4, 4>(tw, p, stream);
+  else if (p.D == 256 && p.ns == 2) e = launch_prep<4, 2>(tw, p, stream);
+  else return "prior_prep: unsupported shape";
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
 }  // namespace qsae

@@ -52,6 +52,24 @@ void encode_pick_mode(int k_sel, int* mode, int* cap);
 const char* encode_topk_launch(const uint16_t* x_bf16, const uint16_t* w_bf16, EncodeLaunch p,
                                cudaStream_t stream);
 
+// Prior of the sampled-threshold path in ONE launch for small batches (replaces cast + sample pre-pass + prior
+// kernel): clusters of `ns` CTAs per 128-row block convert x to bf16 (shared memory operand + the global copy the
+// sweep reads), contract it against their share of the sampled dictionary rows on the tensor cores, keep one running
+// maximum per (thread, column mod 32) class, exchange the maxima through distributed shared memory and write
+// prior[row] = m-th largest class maximum (a lower bound of the m-th largest sampled pre-activation).
+struct PrepLaunch {
+  int B, D, n_sample, act, m;
+  int ns;                  // CTAs per row block = cluster size: 2 or 4
+  const float* x_f32;      // [B, D]
+  uint16_t* x_bf16;        // [B, D] out
+  const float* bias;       // [n_sample] bias of the sampled rows
+  float* prior;            // [B] out
+  int* zero_counters;      // 4 ints cleared by the first block (saves the memset node), or null
+};
+// ns for this shape, 0 = use the separate kernels (large batches, narrow inputs)
+int prior_prep_pick_ns(int B, int D, int n_sample, int m, int num_sms);
+const char* prior_prep_launch(const uint16_t* w_sample, const PrepLaunch& p, cudaStream_t stream);
+
 // dense epilogue variant (t_sae): h = act(x W^T + b) as fp32 and/or bf16 hi (+ lo) [B, H], TMA stores
 // w_parts: 1..3 bf16 matrices [H, D] whose sum is W (hi, mid, lo of a split fp32 matrix): all are contracted
 // against x into the same accumulator. p.accum_mode selects plain / accumulating output (see EncodeLaunch).

@@ -271,6 +271,13 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// load one float from the shared memory of CTA `rank` of the cluster, at the offset of this CTA's `local_addr`
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(mapa_u32(local_addr, rank)) : "memory");
+  return v;
+}
+
 // ---------------------------------------------------------------- misc
 // monotone map float -> uint32 (larger float <=> larger key); -0.0 < +0.0, NaNs sort by payload
 __device__ __forceinline__ uint32_t float_to_key(float f) {

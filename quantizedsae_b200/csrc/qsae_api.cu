@@ -20,6 +20,12 @@ thread_local char g_err[512] = "";
 // optional CUDA events recorded immediately around the fused encoder kernel (bench.py roofline)
 thread_local cudaEvent_t g_enc_ev_start = nullptr;
 thread_local cudaEvent_t g_enc_ev_stop = nullptr;
+// optional per-stage events of qsae_encode_topk / qsae_bsae_forward (qsae_set_stage_events)
+thread_local cudaEvent_t g_stage_ev[QSAE_N_STAGE_EVENTS] = {nullptr};
+thread_local int g_stage_n = 0;
+inline void stage_mark(int i, cudaStream_t st) {
+  if (i < g_stage_n && g_stage_ev[i] != nullptr) cudaEventRecord(g_stage_ev[i], st);
+}
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -387,6 +393,13 @@ int qsae_set_encode_kernel_events(void* start_event, void* stop_event) {
   return QSAE_OK;
 }
 
+int qsae_set_stage_events(void* const* events, int n) {
+  if (n < 0 || n > QSAE_N_STAGE_EVENTS || (n > 0 && !events)) return fail(QSAE_ERR_INVALID_ARGUMENT, "set_stage_events: 0 <= n <= %d", QSAE_N_STAGE_EVENTS);
+  g_stage_n = n;
+  for (int i = 0; i < n; ++i) g_stage_ev[i] = reinterpret_cast<cudaEvent_t>(events[i]);
+  return QSAE_OK;
+}
+
 int qsae_cast_f32_to_bf16(const float* src, uint16_t* dst, size_t n, void* stream) {
   if (!src || !dst) return fail(QSAE_ERR_INVALID_ARGUMENT, "cast: null pointer");
   if (n == 0) return QSAE_OK;
@@ -486,13 +499,17 @@ int encode_topk_impl(const float* x_f32, const uint16_t* w_bf16, const float* w_
   int debug_mode = 0;
   if (const char* dm = getenv("QSAE_ENCODE_DEBUG_MODE")) debug_mode = atoi(dm);
 
-  rc = launch_status("cast x", cast_bf16_launch(x_f32, x_bf16, static_cast<size_t>(B) * D, st));
-  if (rc != QSAE_OK) return rc;
-
   int* counters = reinterpret_cast<int*>(ws + pl.counters_off);   // [0] rescue rows, [1] merge overflow rows
   int32_t* rescue_rows = reinterpret_cast<int32_t*>(ws + pl.rescue_rows_off);
-  cudaError_t ce = cudaMemsetAsync(counters, 0, 4 * sizeof(int), st);
-  if (ce != cudaSuccess) return fail(QSAE_ERR_CUDA, "encode_topk: %s", cudaGetErrorString(ce));
+  stage_mark(0, st);
+  // small batches on the prior path: cast, sample pre-pass, prior and the counter reset are ONE launch
+  const int prep_ns = (pl.use_prior && debug_mode == 0) ? prior_prep_pick_ns(B, D, n_sample, pl.m, num_sms()) : 0;
+  if (prep_ns == 0) {
+    rc = launch_status("cast x", cast_bf16_launch(x_f32, x_bf16, static_cast<size_t>(B) * D, st));
+    if (rc != QSAE_OK) return rc;
+    cudaError_t ce = cudaMemsetAsync(counters, 0, 4 * sizeof(int), st);
+    if (ce != cudaSuccess) return fail(QSAE_ERR_CUDA, "encode_topk: %s", cudaGetErrorString(ce));
+  }
 
   if (!pl.use_prior) {
     // ---- class-bound path: one sweep, block-per-row merge
@@ -527,14 +544,25 @@ int encode_topk_impl(const float* x_f32, const uint16_t* w_bf16, const float* w_
   // ---- prior-threshold path
   float* prior = reinterpret_cast<float*>(ws + pl.prior_off);
   int32_t* ovf_rows = reinterpret_cast<int32_t*>(ws + pl.ovf_rows_off);
-  // 1. pre-pass: the fused kernel over the sampled dictionary rows, top list kept in registers
-  EncodeLaunch pe;
-  fill_encode_launch(&pe, pl.pre, B, D, act, b_sample, ws);
-  pe.top_out = reinterpret_cast<float*>(ws + pl.pre.cand_off);
-  rc = launch_status("encode_topk kernel (sample pre-pass)", encode_topk_launch(x_bf16, w_sample, pe, st));
-  if (rc != QSAE_OK) return rc;
-  rc = launch_status("prior kernel", prior_from_top_launch(pe.top_out, B, pl.pre.nsub, pl.m, prior, st));
-  if (rc != QSAE_OK) return rc;
+  if (prep_ns > 0) {
+    // 1. cast + sample pre-pass + prior in one cluster launch (prior_prep_kernel)
+    PrepLaunch pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.B = B; pp.D = D; pp.n_sample = n_sample; pp.act = act; pp.m = pl.m; pp.ns = prep_ns;
+    pp.x_f32 = x_f32; pp.x_bf16 = x_bf16; pp.bias = b_sample; pp.prior = prior; pp.zero_counters = counters;
+    rc = launch_status("prior_prep kernel", prior_prep_launch(w_sample, pp, st));
+    if (rc != QSAE_OK) return rc;
+  } else {
+    // 1. pre-pass: the fused kernel over the sampled dictionary rows, top list kept in registers
+    EncodeLaunch pe;
+    fill_encode_launch(&pe, pl.pre, B, D, act, b_sample, ws);
+    pe.top_out = reinterpret_cast<float*>(ws + pl.pre.cand_off);
+    rc = launch_status("encode_topk kernel (sample pre-pass)", encode_topk_launch(x_bf16, w_sample, pe, st));
+    if (rc != QSAE_OK) return rc;
+    rc = launch_status("prior kernel", prior_from_top_launch(pe.top_out, B, pl.pre.nsub, pl.m, prior, st));
+    if (rc != QSAE_OK) return rc;
+  }
+  stage_mark(1, st);
   // 2. full sweep against the prior
   EncodeLaunch el;
   fill_encode_launch(&el, pl.main, B, D, act, b_enc, ws);
@@ -544,6 +572,7 @@ int encode_topk_impl(const float* x_f32, const uint16_t* w_bf16, const float* w_
   rc = launch_status("encode_topk kernel", encode_topk_launch(x_bf16, w_bf16, el, st));
   if (g_enc_ev_stop) cudaEventRecord(g_enc_ev_stop, st);
   if (rc != QSAE_OK) return rc;
+  stage_mark(2, st);
   // 3. merge (warp per row; rows with too many survivors go through the block kernel)
   SelectLaunch sl;
   memset(&sl, 0, sizeof(sl));
@@ -564,6 +593,7 @@ int encode_topk_impl(const float* x_f32, const uint16_t* w_bf16, const float* w_
   }
   rc = launch_status("select_small kernel", select_small_launch(sl, 16, nullptr, nullptr, num_sms(), counters + 1, ovf_rows, st));
   if (rc != QSAE_OK) return rc;
+  stage_mark(3, st);
   // tail, one launch: rows the warp merge could not hold (floods of equal values) through the block-per-row select,
   // rows whose prior failed the count check through the exact recomputation; both decoded there when fused
   RescueLaunch rl;
@@ -572,11 +602,27 @@ int encode_topk_impl(const float* x_f32, const uint16_t* w_bf16, const float* w_
   rl.x_bf16 = x_bf16; rl.w_bf16 = w_bf16; rl.x_f32 = x_f32; rl.w_f32 = w_f32; rl.bias = b_enc;
   rl.rescue_count = counters; rl.rescue_rows = rescue_rows;
   rl.out_vals = out_vals; rl.out_idx = out_idx; rl.out_flags = out_flags;
-  return launch_status("select_tail kernel", select_tail_launch(sl, rl, counters + 1, ovf_rows, num_sms(), st));
+  rc = launch_status("select_tail kernel", select_tail_launch(sl, rl, counters + 1, ovf_rows, num_sms(), st));
+  stage_mark(4, st);
+  return rc;
 }
 }  // namespace
 
 extern "C" {
+
+int qsae_prior_prep(const float* x_f32, const uint16_t* w_sample, const float* b_sample, int n_sample, int B, int D,
+                    int act, int m, uint16_t* x_bf16, float* prior, int* ns_out, void* stream) {
+  if (B == 0) return QSAE_OK;
+  if (!x_f32 || !w_sample || !b_sample || !x_bf16 || !prior) return fail(QSAE_ERR_INVALID_ARGUMENT, "prior_prep: null pointer");
+  const int ns = prior_prep_pick_ns(B, D, n_sample, m, num_sms());
+  if (ns_out) *ns_out = ns;
+  if (ns == 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "prior_prep: no single-launch variant for B=%d D=%d n_sample=%d m=%d", B, D, n_sample, m);
+  PrepLaunch pp;
+  memset(&pp, 0, sizeof(pp));
+  pp.B = B; pp.D = D; pp.n_sample = n_sample; pp.act = act; pp.m = m; pp.ns = ns;
+  pp.x_f32 = x_f32; pp.x_bf16 = x_bf16; pp.bias = b_sample; pp.prior = prior;
+  return launch_status("prior_prep kernel", prior_prep_launch(w_sample, pp, S(stream)));
+}
 
 int qsae_encode_topk(const float* x_f32, const uint16_t* w_bf16, const float* w_f32, const float* b_enc,
                      const uint16_t* w_sample, const float* b_sample, int n_sample,
@@ -599,9 +645,11 @@ int qsae_bsae_forward(const float* x_f32, const uint16_t* w_bf16, const float* w
                             out_vals, out_idx, out_flags, workspace, workspace_bytes, stream, n_bits <= 4 ? &fd : nullptr);
   if (rc != QSAE_OK) return rc;
   if (fd.done) return QSAE_OK;
-  if (n_bits <= 4) return qsae_decode_int4(out_vals, out_idx, B, k, packed, H, D, qstep, dec_bias, recon, stream);
-  return qsae_decode_int8(out_vals, out_idx, B, k, reinterpret_cast<const int8_t*>(packed), H, D, qstep, dec_bias, recon,
-                          stream);
+  if (n_bits <= 4) rc = qsae_decode_int4(out_vals, out_idx, B, k, packed, H, D, qstep, dec_bias, recon, stream);
+  else rc = qsae_decode_int8(out_vals, out_idx, B, k, reinterpret_cast<const int8_t*>(packed), H, D, qstep, dec_bias, recon,
+                             stream);
+  stage_mark(5, S(stream));
+  return rc;
 }
 
 int qsae_encode_dense_tc(const float* x_f32, const uint16_t* w_bf16, const float* b_enc, int B, int H, int D,

@@ -485,6 +485,57 @@ def test_prior_failure_is_rescued_exactly(cuda_device):
         assert int((flags != 0).sum()) == 0          # rescued rows are exact by construction
 
 
+@pytest.mark.parametrize("B,D,n_sample,m,act", [(300, 512, 1024, 10, 0), (4096, 512, 1024, 10, 0), (130, 256, 512, 7, 0),
+                                                (6000, 512, 1024, 12, 0), (200, 512, 2048, 9, 1), (77, 512, 1000, 5, 0)])
+def test_prior_prep_kernel_vs_numpy(cuda_device, B, D, n_sample, m, act):
+    """The single-launch cast + sample pre-pass + prior: x_bf16 must be the round-to-nearest bf16 of x (bit exact: it is
+    the sweep's operand) and prior[b] the m-th largest per-class maximum of row b's sampled pre-activations, classes =
+    (CTA of the cluster, column half of the 256-wide tile, column mod 32). Checks the hand-written 128-byte swizzle of
+    the x operand, the cluster exchange and the bisection."""
+    rng = np.random.default_rng(B + m)
+    x = rng.standard_normal((B, D)).astype(np.float32)
+    ws = cases.round_bf16(cases.xavier_uniform(rng, n_sample, D))
+    bs = (0.05 * rng.standard_normal(n_sample)).astype(np.float32)
+    dws = T(ws, cuda_device).bfloat16()
+    xb, prior, ns = L.prior_prep(T(x, cuda_device), (dws, T(bs, cuda_device)), m, act)
+    assert ns in (2, 4)
+    xr = cases.round_bf16(x)
+    assert np.array_equal(xb.float().cpu().numpy(), xr)
+    z = xr.astype(np.float64) @ ws.astype(np.float64).T + bs
+    if act:
+        z = np.maximum(z, 0.0)
+    n_tiles = (n_sample + 255) // 256
+    tiles_per_cta = (n_tiles + ns - 1) // ns
+    col = np.arange(n_sample)
+    cls = ((col // 256) // tiles_per_cta) * 64 + ((col % 256) // 128) * 32 + col % 32
+    cmax = np.full((B, ns * 64), -np.inf)
+    for c in range(ns * 64):
+        sel = cls == c
+        if sel.any():
+            cmax[:, c] = z[:, sel].max(1)
+    ref = -np.sort(-cmax, axis=1)[:, m - 1]
+    got = prior.cpu().numpy().astype(np.float64)
+    assert np.all(np.abs(got - ref) <= 2e-6 * np.maximum(1.0, np.abs(ref))), float(np.abs(got - ref).max())
+
+
+def test_prior_prep_path_is_bit_identical_to_the_separate_kernels(cuda_device, monkeypatch):
+    B, H, D, k = 700, 32768, 512, 32
+    x, W, b = _enc_case(B, H, D, 4242)
+    dx, dW, db = T(x, cuda_device), T(W, cuda_device), T(b, cuda_device)
+    wb = L.cast_bf16(dW)
+    sample = L.prepare_sample(wb, db)
+    packed = torch.randint(0, 256, (H, D // 2), dtype=torch.uint8, device=cuda_device)
+    bd = torch.randn(D, device=cuda_device)
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("QSAE_PRIOR_PREP", flag)
+        outs.append(L.bsae_forward(dx, wb, None, db, k, packed, 4, 0.5, bd, sample=sample))
+    for a, c in zip(outs[0], outs[1]):
+        if a is not None:
+            assert torch.equal(a, c)
+    assert_topk_matches(outs[0][0].cpu().numpy(), outs[0][1].cpu().numpy(), O.encode_pre(x, W, b), k)
+
+
 @pytest.mark.parametrize("k,exact,shift", [(32, False, 0.12), (65, False, 0.2), (32, True, 0.12), (100, False, 0.3)])
 def test_loose_prior_takes_the_two_pass_merge(cuda_device, k, exact, shift):
     """A prior that is too LOW (sampled rows carry a negative bias): every row keeps far more than the 512 survivors
