@@ -118,6 +118,14 @@ int qsae_prepare_encoder_sample(const uint16_t* w_bf16, const float* b_enc, int 
                                 uint16_t* w_sample /* [n_sample, D] */, float* b_sample /* [n_sample] */,
                                 void* stream);
 
+/* Kernels this library has launched in this process (all threads, monotonic): what bench.py reports as gpu_launches. */
+unsigned long long qsae_launch_count(void);
+
+/* Tuning / diagnostic switches (QSAE_ENCODE_SPLITS, QSAE_ENCODE_PRIOR, QSAE_ENCODE_CLUSTER, QSAE_ENCODE_RANGE,
+ * QSAE_PRIOR_PREP, QSAE_DECODE_PAIR, QSAE_DEBUG_*) are read from the environment once, on first use, never on a
+ * launch path. A process that changes them afterwards (tests, tuning runs) calls this to re-read them. */
+int qsae_reload_tuning(void);
+
 /* Measurement hook: per-stage events of the sampled-prior path of qsae_encode_topk / qsae_bsae_forward, recorded in
  * stream order by the calling thread's next calls: [0] start, [1] prior ready (cast + sample pre-pass + prior),
  * [2] sweep done, [3] merge (+ fused decode) done, [4] tail kernel done, [5] separate decode done (when not fused).

@@ -32,6 +32,8 @@ SYMBOLS = {
     "qsae_encode_topk_workspace_bytes": (_i, [_i, _i, _i, _i, _i, C.POINTER(_sz)]),
     "qsae_prepare_encoder_sample": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "qsae_set_encode_kernel_events": (_i, [_vp, _vp]),
+    "qsae_launch_count": (C.c_ulonglong, []),
+    "qsae_reload_tuning": (_i, []),
     "qsae_set_stage_events": (_i, [_vp, _i]),
     "qsae_prior_prep": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, C.POINTER(_i), _vp]),
     "qsae_encode_topk": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -95,7 +97,11 @@ class QsaeError(RuntimeError):
 
 
 _lib = None
-launch_count = 0  # kernels launched through this binding (bench.py reports it)
+
+
+def launch_count() -> int:
+    """Kernels libqsae_b200.so has launched in this process (counted in C: qsae_launch_count)."""
+    return int(load().qsae_launch_count())
 
 
 def load(build_if_missing: bool = True) -> C.CDLL:
@@ -149,18 +155,15 @@ def _need_cuda(*ts: torch.Tensor) -> None:
 # ------------------------------------------------------------------------------------------
 
 def cast_bf16(src: torch.Tensor) -> torch.Tensor:
-    global launch_count
     _need_cuda(src)
     assert src.dtype == torch.float32
     dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
     check(load().qsae_cast_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()))
-    launch_count += 1
     return dst
 
 
 def pack_bitplanes(logits: torch.Tensor, D: int, n_bits: int, want_stats: bool = True):
     """-> (packed uint8 [H, D/2] or int8-as-uint8 [H, D], polarize_loss float|None, max_gap float|None)."""
-    global launch_count
     _need_cuda(logits)
     H = logits.shape[0]
     assert logits.dtype == torch.float32 and logits.shape[1] == D * n_bits
@@ -168,7 +171,6 @@ def pack_bitplanes(logits: torch.Tensor, D: int, n_bits: int, want_stats: bool =
     packed = torch.empty((H, cols), dtype=torch.uint8, device=logits.device)
     stats = torch.zeros(2, dtype=torch.float64, device=logits.device) if want_stats else None
     check(load().qsae_pack_bitplanes(logits.data_ptr(), H, D, n_bits, packed.data_ptr(), _ptr(stats), _stream()))
-    launch_count += 1
     if not want_stats:
         return packed, None, None
     s = stats.cpu()
@@ -176,22 +178,18 @@ def pack_bitplanes(logits: torch.Tensor, D: int, n_bits: int, want_stats: bool =
 
 
 def dequant_soft(logits: torch.Tensor, D: int, n_bits: int) -> torch.Tensor:
-    global launch_count
     _need_cuda(logits)
     H = logits.shape[0]
     rows = torch.empty((H, D), dtype=torch.float32, device=logits.device)
     check(load().qsae_dequant_soft(logits.data_ptr(), H, D, n_bits, rows.data_ptr(), _stream()))
-    launch_count += 1
     return rows
 
 
 def transpose(src: torch.Tensor) -> torch.Tensor:
-    global launch_count
     _need_cuda(src)
     R, Cc = src.shape
     dst = torch.empty((Cc, R), dtype=torch.float32, device=src.device)
     check(load().qsae_transpose_f32(src.data_ptr(), R, Cc, dst.data_ptr(), _stream()))
-    launch_count += 1
     return dst
 
 
@@ -208,7 +206,6 @@ def default_sample_rows(H: int) -> int:
 
 def prepare_sample(w_bf16: torch.Tensor, b_enc: torch.Tensor, n_sample: int | None = None):
     """-> (w_sample [n,D] bf16, b_sample [n] f32) or None when the dictionary is too small."""
-    global launch_count
     _need_cuda(w_bf16, b_enc)
     H, D = w_bf16.shape
     n = default_sample_rows(H) if n_sample is None else n_sample
@@ -218,13 +215,11 @@ def prepare_sample(w_bf16: torch.Tensor, b_enc: torch.Tensor, n_sample: int | No
     bs = torch.empty((n,), dtype=torch.float32, device=w_bf16.device)
     check(load().qsae_prepare_encoder_sample(w_bf16.data_ptr(), b_enc.data_ptr(), H, D, n, ws.data_ptr(),
                                              bs.data_ptr(), _stream()))
-    launch_count += 1
     return ws, bs
 
 
 def prior_prep(x: torch.Tensor, sample, m: int, act: int = ACT_NONE):
     """The single-launch cast + sample pre-pass + prior of the small-batch path -> (x_bf16 [B,D], prior [B], ns)."""
-    global launch_count
     w_s, b_s = sample
     _need_cuda(x, w_s, b_s)
     B, D = x.shape
@@ -233,7 +228,6 @@ def prior_prep(x: torch.Tensor, sample, m: int, act: int = ACT_NONE):
     ns = _i(0)
     check(load().qsae_prior_prep(x.data_ptr(), w_s.data_ptr(), b_s.data_ptr(), w_s.shape[0], B, D, act, m,
                                  xb.data_ptr(), prior.data_ptr(), C.byref(ns), _stream()))
-    launch_count += 1
     return xb, prior, int(ns.value)
 
 
@@ -258,7 +252,6 @@ def _workspace(device, nbytes: int) -> torch.Tensor:
 def encode_topk(x: torch.Tensor, w_bf16: torch.Tensor, w_f32: torch.Tensor | None, b_enc: torch.Tensor,
                 k: int, act: int = ACT_NONE, exact: bool = False, want_flags: bool = False, sample=None):
     """-> (vals [B,k] f32, idx [B,k] i32, flags [B] i32 | None)"""
-    global launch_count
     _need_cuda(x, w_bf16, w_f32, b_enc)
     B, D = x.shape
     H = w_bf16.shape[0]
@@ -275,7 +268,6 @@ def encode_topk(x: torch.Tensor, w_bf16: torch.Tensor, w_f32: torch.Tensor | Non
     check(load().qsae_encode_topk(x.data_ptr(), w_bf16.data_ptr(), _ptr(w_f32), b_enc.data_ptr(), _ptr(w_s),
                                   _ptr(b_s), n_s, B, H, D, k, act, 1 if exact else 0, vals.data_ptr(),
                                   idx.data_ptr(), _ptr(flags), ws.data_ptr(), ws.numel(), _stream()))
-    launch_count += 3 if n_s == 0 else 8
     return vals, idx, flags
 
 
@@ -283,7 +275,6 @@ def bsae_forward(x: torch.Tensor, w_bf16: torch.Tensor, w_f32: torch.Tensor | No
                  packed: torch.Tensor, n_bits: int, qstep: float, dec_bias: torch.Tensor | None, exact: bool = False,
                  want_flags: bool = False, sample=None):
     """BinarySAE.forward on device buffers -> (vals [B,k], idx [B,k], flags | None, recon [B,D])."""
-    global launch_count
     _need_cuda(x, w_bf16, w_f32, b_enc, packed, dec_bias)
     B, D = x.shape
     H = w_bf16.shape[0]
@@ -301,13 +292,11 @@ def bsae_forward(x: torch.Tensor, w_bf16: torch.Tensor, w_f32: torch.Tensor | No
                                    n_s, B, H, D, k, 1 if exact else 0, packed.data_ptr(), n_bits, float(qstep),
                                    _ptr(dec_bias), vals.data_ptr(), idx.data_ptr(), _ptr(flags), recon.data_ptr(),
                                    ws.data_ptr(), ws.numel(), _stream()))
-    launch_count += 4 if n_s == 0 else 10
     return vals, idx, flags, recon
 
 
 def encode_dense_tc(x: torch.Tensor, w_bf16: torch.Tensor, b_enc: torch.Tensor, act: int = ACT_NONE) -> torch.Tensor:
     """Diagnostic: dense z [B,H] straight from the tcgen05 encoder kernel."""
-    global launch_count
     _need_cuda(x, w_bf16, b_enc)
     B, D = x.shape
     H = w_bf16.shape[0]
@@ -315,25 +304,21 @@ def encode_dense_tc(x: torch.Tensor, w_bf16: torch.Tensor, b_enc: torch.Tensor, 
     ws = _workspace(x.device, encode_topk_workspace_bytes(B, H, D, 1))
     check(load().qsae_encode_dense_tc(x.data_ptr(), w_bf16.data_ptr(), b_enc.data_ptr(), B, H, D, act,
                                       z.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
-    launch_count += 2
     return z
 
 
 def encode_dense(x: torch.Tensor, w_f32: torch.Tensor, b_enc: torch.Tensor | None, act: int = ACT_NONE,
                  rows: torch.Tensor | None = None) -> torch.Tensor:
-    global launch_count
     _need_cuda(x, w_f32, b_enc, rows)
     R = x.shape[0] if rows is None else rows.numel()
     H, D = w_f32.shape
     z = torch.empty((R, H), dtype=torch.float32, device=x.device)
     check(load().qsae_encode_dense_f32(x.data_ptr(), _ptr(rows), R, w_f32.data_ptr(), _ptr(b_enc), H, D, act,
                                        z.data_ptr(), _stream()))
-    launch_count += 1
     return z
 
 
 def topk_dense(z: torch.Tensor, k: int):
-    global launch_count
     _need_cuda(z)
     R, H = z.shape
     vals = torch.empty((R, k), dtype=torch.float32, device=z.device)
@@ -345,18 +330,15 @@ def topk_dense(z: torch.Tensor, k: int):
     ws = _workspace(z.device, int(n.value))
     check(load().qsae_topk_dense(z.data_ptr(), R, H, k, vals.data_ptr(), idx.data_ptr(), ws.data_ptr(),
                                  ws.numel(), _stream()))
-    launch_count += 2
     return vals, idx
 
 
 def _decode(fn_name: str, vals, idx, dict_t, H, D, scale, bias):
-    global launch_count
     _need_cuda(vals, idx, dict_t, bias)
     B, k = vals.shape
     recon = torch.empty((B, D), dtype=torch.float32, device=vals.device)
     check(getattr(load(), fn_name)(vals.data_ptr(), idx.data_ptr(), B, k, dict_t.data_ptr(), H, D, float(scale),
                                    _ptr(bias), recon.data_ptr(), _stream()))
-    launch_count += 1
     return recon
 
 
@@ -373,19 +355,16 @@ def decode_rows_f32(vals, idx, rows, H, D, scale, bias):
 
 
 def densify(vals: torch.Tensor, idx: torch.Tensor, H: int) -> torch.Tensor:
-    global launch_count
     _need_cuda(vals, idx)
     B, k = vals.shape
     dense = torch.empty((B, H), dtype=torch.float32, device=vals.device)
     check(load().qsae_densify(vals.data_ptr(), idx.data_ptr(), B, k, H, dense.data_ptr(), _stream()))
-    launch_count += 1
     return dense
 
 
 def pack_matryoshka(weight: torch.Tensor, weight_mirror: torch.Tensor, level_start: torch.Tensor,
                     level_factor: torch.Tensor):
     """-> (packed [H, D/16] int32 (2-bit codes), scale [H] f32)"""
-    global launch_count
     _need_cuda(weight, weight_mirror, level_start, level_factor)
     H, D = weight.shape
     packed = torch.empty((H, D // 16), dtype=torch.int32, device=weight.device)
@@ -393,21 +372,17 @@ def pack_matryoshka(weight: torch.Tensor, weight_mirror: torch.Tensor, level_sta
     check(load().qsae_pack_matryoshka(weight.data_ptr(), weight_mirror.data_ptr(), H, D, level_start.data_ptr(),
                                       level_factor.data_ptr(), level_factor.numel(), packed.data_ptr(),
                                       scale.data_ptr(), _stream()))
-    launch_count += 1
     return packed, scale
 
 
 def max_row_norm(w_f32: torch.Tensor) -> torch.Tensor:
-    global launch_count
     _need_cuda(w_f32)
     out = torch.zeros(1, dtype=torch.float32, device=w_f32.device)
     check(load().qsae_max_row_norm(w_f32.data_ptr(), w_f32.shape[0], w_f32.shape[1], out.data_ptr(), _stream()))
-    launch_count += 1
     return out
 
 
 def decode_matryoshka_lists(lists, counts, cap, packed, scale, level_start, n_levels, H, D, dec_bias):
-    global launch_count
     _need_cuda(lists, counts, packed, scale, level_start, dec_bias)
     B = counts.shape[0]
     result = torch.empty((n_levels, B, D), dtype=torch.float32, device=lists.device)
@@ -419,7 +394,6 @@ def decode_matryoshka_lists(lists, counts, cap, packed, scale, level_start, n_le
                                               scale.data_ptr(), level_start.data_ptr(), n_levels, H, D, _ptr(dec_bias),
                                               result.data_ptr(), level_count.data_ptr(), ws.data_ptr(), ws.numel(),
                                               _stream()))
-    launch_count += 2
     return result, level_count
 
 
@@ -428,7 +402,6 @@ def matryoshka_forward(x, w_bf16, b_enc, packed, scale, level_start, n_levels, d
     """-> (result [n_levels, B, D] f32, level_count [n_levels] int64, overflow [1] int32)
     active_cap > 0: additionally (active_idx [B, active_cap] int32 with -1 in empty slots, active_cnt [B] int32).
     want_residual: additionally (x - result[-1]) * 2 [B, D], the next rq_sae stage's input, as the last element."""
-    global launch_count
     _need_cuda(x, w_bf16, b_enc, packed, scale, level_start, dec_bias)
     B, D = x.shape
     H = w_bf16.shape[0]
@@ -451,67 +424,55 @@ def matryoshka_forward(x, w_bf16, b_enc, packed, scale, level_start, n_levels, d
                                                 result.data_ptr(), counts.data_ptr(), overflow.data_ptr(),
                                                 _ptr(a_idx), active_cap, _ptr(a_cnt), _ptr(resid), ws.data_ptr(), ws.numel(),
                                                 _stream()))
-    launch_count += 4
     out = (result, counts, overflow, a_idx, a_cnt) if active_cap > 0 else (result, counts, overflow)
     return out + (resid,) if want_residual else out
 
 
 def activation_counts(idx: torch.Tensor, vals: torch.Tensor | None, counts: torch.Tensor) -> None:
     """counts [H] int64 += rows in which each latent is active (idx [B, cap] int32, -1 = empty; vals: active iff > 0)."""
-    global launch_count
     _need_cuda(idx, vals, counts)
     assert idx.dtype == torch.int32 and counts.dtype == torch.int64 and idx.dim() == 2
     B, cap = idx.shape
     check(load().qsae_activation_counts(idx.data_ptr(), _ptr(vals), B, cap, counts.numel(), counts.data_ptr(), _stream()))
-    launch_count += 1
 
 
 def coactivation(idx: torch.Tensor, vals: torch.Tensor | None, cooc: torch.Tensor) -> None:
     """cooc [H, H] int32 += A^T A of the boolean activity described by the lists."""
-    global launch_count
     _need_cuda(idx, vals, cooc)
     assert idx.dtype == torch.int32 and cooc.dtype == torch.int32 and cooc.dim() == 2 and cooc.shape[0] == cooc.shape[1]
     B, cap = idx.shape
     check(load().qsae_coactivation(idx.data_ptr(), _ptr(vals), B, cap, cooc.shape[0], cooc.data_ptr(), _stream()))
-    launch_count += 1
 
 
 def sq_error_accumulate(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> None:
     """out (device float64 scalar) += sum (a - b)^2."""
-    global launch_count
     _need_cuda(a, b, out)
     assert a.dtype == torch.float32 and b.dtype == torch.float32 and out.dtype == torch.float64 and a.numel() == b.numel()
     check(load().qsae_sq_error_accumulate(a.data_ptr(), b.data_ptr(), a.numel(), out.data_ptr(), _stream()))
-    launch_count += 1
 
 
 def pack_ternary(w: torch.Tensor, threshold: float = 0.5, want_bf16: bool = True, want_rows: bool = False):
     """decoder.weight [D, H] -> (T bf16 [D, H] | None, T int8 rows [H, D] | None), T = sign(w) * (|w| >= thr)."""
-    global launch_count
     _need_cuda(w)
     D, H = w.shape
     assert w.dtype == torch.float32
     t_bf16 = torch.empty((D, H), dtype=torch.bfloat16, device=w.device) if want_bf16 else None
     t_rows = torch.empty((H, D), dtype=torch.int8, device=w.device) if want_rows else None
     check(load().qsae_pack_ternary(w.data_ptr(), D, H, float(threshold), _ptr(t_bf16), _ptr(t_rows), _stream()))
-    launch_count += 1
     return t_bf16, t_rows
 
 
 def split_bf16(src: torch.Tensor, want_lo: bool = True):
-    global launch_count
     _need_cuda(src)
     assert src.dtype == torch.float32
     hi = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
     lo = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device) if want_lo else None
     check(load().qsae_split_bf16(src.data_ptr(), hi.data_ptr(), _ptr(lo), src.numel(), _stream()))
-    launch_count += 1
     return hi, lo
 
 
 def decode_dense(a_hi: torch.Tensor, a_lo: torch.Tensor | None, b_t: torch.Tensor, bias: torch.Tensor | None = None):
     """out [B, N] = (a_hi (+ a_lo)) [B, K] @ b_t [N, K]^T (+ bias); bf16 operands, fp32 result."""
-    global launch_count
     _need_cuda(a_hi, a_lo, b_t, bias)
     B, K = a_hi.shape
     N = b_t.shape[0]
@@ -524,26 +485,22 @@ def decode_dense(a_hi: torch.Tensor, a_lo: torch.Tensor | None, b_t: torch.Tenso
     ws = _workspace(a_hi.device, int(n.value))
     check(load().qsae_decode_dense(a_hi.data_ptr(), _ptr(a_lo), b_t.data_ptr(), B, K, N, _ptr(bias), out.data_ptr(),
                                    ws.data_ptr(), ws.numel(), _stream()))
-    launch_count += 2
     return out
 
 
 def split_bf16x3(src: torch.Tensor):
     """-> (hi, mid, lo) bf16 tensors with hi + mid + lo == src exactly."""
-    global launch_count
     _need_cuda(src)
     assert src.dtype == torch.float32
     parts = tuple(torch.empty(src.shape, dtype=torch.bfloat16, device=src.device) for _ in range(3))
     check(load().qsae_split_bf16x3(src.data_ptr(), parts[0].data_ptr(), parts[1].data_ptr(), parts[2].data_ptr(),
                                    src.numel(), _stream()))
-    launch_count += 1
     return parts
 
 
 def tsae_forward(x: torch.Tensor, w_parts, b_enc: torch.Tensor, t_bf16: torch.Tensor, exact: bool):
     """w_parts: (bf16(W),) for the fast mode or split_bf16x3(W) for the exact mode.
     -> (h [B, H] f32 dense ReLU latents, recon [B, D] f32)"""
-    global launch_count
     w_hi = w_parts[0]
     w_mid, w_lo = (w_parts[1], w_parts[2]) if exact else (None, None)
     _need_cuda(x, w_hi, w_mid, w_lo, b_enc, t_bf16)
@@ -559,20 +516,17 @@ def tsae_forward(x: torch.Tensor, w_parts, b_enc: torch.Tensor, t_bf16: torch.Te
     check(load().qsae_tsae_forward(x.data_ptr(), w_hi.data_ptr(), _ptr(w_mid), _ptr(w_lo), b_enc.data_ptr(),
                                    t_bf16.data_ptr(), B, H, D, 1 if exact else 0, h.data_ptr(), recon.data_ptr(),
                                    ws.data_ptr(), ws.numel(), _stream()))
-    launch_count += 6 if exact else 4
     return h, recon
 
 
 def pack_candidates(vals: torch.Tensor, idx: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     """(vals, idx) [B, k] -> [B, k, 2] int32 entries {float bits, index}: one all-gather operand
     (or, with `out`, written straight into this rank's peer-exchange buffer)."""
-    global launch_count
     _need_cuda(vals, idx, out)
     if out is None:
         out = torch.empty(tuple(vals.shape) + (2,), dtype=torch.int32, device=vals.device)
     assert out.dtype == torch.int32 and out.numel() == 2 * vals.numel()
     check(load().qsae_pack_candidates(vals.data_ptr(), idx.data_ptr(), vals.numel(), out.data_ptr(), _stream()))
-    launch_count += 1
     return out
 
 
@@ -580,7 +534,6 @@ def merge_candidates(cand_all: torch.Tensor, shard_latents: int, k_out: int, tru
     """cand_all [G, B, k_in, 2] int32 (gathered pack_candidates outputs) -> global (vals, idx) [B, k_out].
     truncated=True (the shards sent fewer candidates than they hold): -> (vals, idx, incomplete [1] int32);
     incomplete != 0 means some shard's list was used up and the exchange must be repeated with full lists."""
-    global launch_count
     _need_cuda(cand_all)
     G, B, k_in, two = cand_all.shape
     assert two == 2 and cand_all.dtype == torch.int32
@@ -594,14 +547,12 @@ def merge_candidates(cand_all: torch.Tensor, shard_latents: int, k_out: int, tru
     ws = _workspace(cand_all.device, int(n.value))
     check(load().qsae_merge_candidates(cand_all.data_ptr(), G, B, k_in, shard_latents, k_out, vals.data_ptr(),
                                        idx.data_ptr(), _ptr(flag), ws.data_ptr(), ws.numel(), _stream()))
-    launch_count += 2
     return (vals, idx, flag) if truncated else (vals, idx)
 
 
 def decode_range(vals, idx, dict_shard, shard_latents: int, idx_begin: int, D: int, scale: float, bias, n_bits: int,
                  out: torch.Tensor | None = None):
     """Partial reconstruction from the winners inside [idx_begin, idx_begin + shard_latents)."""
-    global launch_count
     _need_cuda(vals, idx, dict_shard, bias, out)
     B, k = vals.shape
     recon = torch.empty((B, D), dtype=torch.float32, device=vals.device) if out is None else out
@@ -609,25 +560,21 @@ def decode_range(vals, idx, dict_shard, shard_latents: int, idx_begin: int, D: i
     fn = load().qsae_decode_int4_range if n_bits <= 4 else load().qsae_decode_int8_range
     check(fn(vals.data_ptr(), idx.data_ptr(), B, k, dict_shard.data_ptr(), shard_latents, idx_begin, D, float(scale),
              _ptr(bias), recon.data_ptr(), _stream()))
-    launch_count += 1
     return recon
 
 
 def unpack_matryoshka_t(packed: torch.Tensor, D: int) -> torch.Tensor:
     """packed 2-bit codes [H, D/16] -> T^T bf16 [D, H] (entries -2, 0, +2)."""
-    global launch_count
     _need_cuda(packed)
     H = packed.shape[0]
     t = torch.empty((D, H), dtype=torch.bfloat16, device=packed.device)
     check(load().qsae_unpack_matryoshka_t(packed.data_ptr(), H, D, t.data_ptr(), _stream()))
-    launch_count += 1
     return t
 
 
 def matryoshka_forward_dense(x, w_parts, b_enc, t_bf16, scale, level_start_dev, level_start_host, dec_bias):
     """Dense q_sae forward -> (result [n_levels, B, D] f32, level_count [n_levels] int64).
     w_parts: (bf16(W),) or split_bf16x3(W) for fp32-accurate activity decisions."""
-    global launch_count
     w_hi = w_parts[0]
     w_mid, w_lo = (w_parts[1], w_parts[2]) if len(w_parts) == 3 else (None, None)
     _need_cuda(x, w_hi, w_mid, w_lo, b_enc, t_bf16, scale, level_start_dev, dec_bias)
@@ -647,17 +594,14 @@ def matryoshka_forward_dense(x, w_parts, b_enc, t_bf16, scale, level_start_dev, 
                                                scale.data_ptr(), level_start_dev.data_ptr(), starts, n_levels,
                                                _ptr(dec_bias), B, H, D, result.data_ptr(), counts.data_ptr(),
                                                ws.data_ptr(), ws.numel(), _stream()))
-    launch_count += 3 + 2 * n_levels
     return result, counts
 
 
 def residual_update(residual: torch.Tensor, recon: torch.Tensor) -> torch.Tensor:
     """(residual - recon) * 2 (sae/residual_quantized.py:67)."""
-    global launch_count
     _need_cuda(residual, recon)
     out = torch.empty_like(residual)
     check(load().qsae_residual_update(residual.data_ptr(), recon.data_ptr(), residual.numel(), out.data_ptr(), _stream()))
-    launch_count += 1
     return out
 
 
@@ -672,7 +616,8 @@ class _RawCudaBuffer:
 def peer_alloc(nbytes: int, device) -> tuple:
     """-> (ptr, uint8 tensor view, 64-byte IPC handle)"""
     ptr = _vp()
-    check(load().qsae_peer_alloc(nbytes, C.byref(ptr)))
+    with torch.cuda.device(device):       # cudaMalloc allocates on the current device
+        check(load().qsae_peer_alloc(nbytes, C.byref(ptr)))
     handle = C.create_string_buffer(64)
     check(load().qsae_peer_export(ptr, handle))
     view = torch.as_tensor(_RawCudaBuffer(ptr.value, nbytes), device=device)
@@ -695,21 +640,16 @@ def peer_free(ptr: int) -> None:
 
 def peer_signal(targets: torch.Tensor, value: int) -> None:
     """targets: device int64 [G] addresses of this rank's flag inside every rank's buffer."""
-    global launch_count
     check(load().qsae_peer_signal(targets.data_ptr(), targets.numel(), value & 0xFFFFFFFF, _stream()))
-    launch_count += 1
 
 
 def peer_wait(flags_ptr: int, n: int, value: int, timed_out: torch.Tensor) -> None:
-    global launch_count
     check(load().qsae_peer_wait(_vp(flags_ptr), n, value & 0xFFFFFFFF, timed_out.data_ptr(), _stream()))
-    launch_count += 1
 
 
 def merge_candidates_peer(list_bases: torch.Tensor, B: int, k_in: int, shard_latents: int, k_out: int,
                           truncated: bool = False):
     """list_bases: device int64 [G]; list s of row r at list_bases[s] + r * k_in 8-byte entries (peer memory)."""
-    global launch_count
     dev = list_bases.device
     vals = torch.empty((B, k_out), dtype=torch.float32, device=dev)
     idx = torch.empty((B, k_out), dtype=torch.int32, device=dev)
@@ -721,14 +661,11 @@ def merge_candidates_peer(list_bases: torch.Tensor, B: int, k_in: int, shard_lat
     ws = _workspace(dev, int(n.value))
     check(load().qsae_merge_candidates_peer(list_bases.data_ptr(), list_bases.numel(), B, k_in, shard_latents, k_out,
                                             vals.data_ptr(), idx.data_ptr(), _ptr(flag), ws.data_ptr(), ws.numel(), _stream()))
-    launch_count += 2
     return (vals, idx, flag) if truncated else (vals, idx)
 
 
 def reduce_partials_peer(partial_bases: torch.Tensor, row_begin: int, rows: int, D: int) -> torch.Tensor:
-    global launch_count
     out = torch.empty((rows, D), dtype=torch.float32, device=partial_bases.device)
     check(load().qsae_reduce_partials_peer(partial_bases.data_ptr(), partial_bases.numel(), row_begin, rows, D,
                                            out.data_ptr(), _stream()))
-    launch_count += 1
     return out

@@ -305,7 +305,7 @@ const char* dense_decode_launch(const uint16_t* a_hi, const uint16_t* a_lo, int 
   if (!make_tmap(&ta1, a_lo ? a_lo : a_hi, B, K, lda, BM)) return "cuTensorMapEncodeTiled(A lo) failed";
   // CTA pairs need two row blocks; QSAE_DECODE_PAIR=0/1 overrides (tests and tuning experiments)
   bool pair = B > BM;
-  if (const char* m = getenv("QSAE_DECODE_PAIR")) pair = pair && atoi(m) != 0;
+  if (tuning().decode_pair >= 0) pair = pair && tuning().decode_pair != 0;
   if (!make_tmap(&tb, b_t, N, K, ldb, pair ? BN / 2 : BN)) return "cuTensorMapEncodeTiled(B) failed";
   DecodeLaunch p;
   p.B = B; p.K = K; p.N = N;
@@ -322,6 +322,7 @@ const char* dense_decode_launch(const uint16_t* a_hi, const uint16_t* a_lo, int 
   size_t g = (n / 4 + 255) / 256;
   if (g > 148 * 8) g = 148 * 8;
   if (g < 1) g = 1;
+  count_launches(1);
   reduce_partials_kernel<<<static_cast<int>(g), 256, 0, stream>>>(p.partial, splits, n, bias, prev, N, out);
   return cuda_err(cudaGetLastError());
 }

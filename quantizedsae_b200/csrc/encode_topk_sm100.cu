@@ -60,8 +60,9 @@ __host__ __device__ constexpr int epi_warps(bool dense) { return 8; }
 __host__ __device__ constexpr int cta_threads(bool dense) { return 128 + epi_warps(dense) * 32; }
 constexpr int kTmemCols = 512;                  // 2 accumulators x 256 columns
 
+constexpr int kMaxPieces = 4;   // pieces of one CTA's range (a range is shorter than a row block: at most 2; see PieceIter)
 struct SmemLayout {
-  uint32_t a_off, b_off, staging_off, bias_off, share_off, bar_off, tmem_ptr_off, total;
+  uint32_t a_off, b_off, staging_off, bias_off, share_off, bar_off, tmem_ptr_off, piece_off, total;
 };
 // pair (cta_group::2): a CTA keeps only its half of every W stage (16 KiB), which pays for deeper rings
 __host__ __device__ constexpr int ring_stages(bool dense, bool pair) {
@@ -77,8 +78,9 @@ __host__ __device__ inline SmemLayout smem_layout(int k_chunks, bool dense, bool
   L.bias_off = L.staging_off + (dense ? epi_warps(true) * dense_stage_bytes(pair) : 0);
   L.share_off = L.bias_off + 2 * BN * 4;         // partner thresholds, 2 x 128 x bf16
   L.bar_off = L.share_off + 2 * BM * 2;
-  L.tmem_ptr_off = L.bar_off + 8 * (1 + 2 * stages + 8);
-  L.total = L.tmem_ptr_off + 16;
+  L.tmem_ptr_off = L.bar_off + 8 * (1 + 2 * stages + 9);
+  L.piece_off = L.tmem_ptr_off + 16;
+  L.total = L.piece_off + 16 + kMaxPieces * 32;
   return L;
 }
 
@@ -167,10 +169,16 @@ __device__ __forceinline__ float pick32(const float (&v)[32], int j) {
 // MODE 4: fixed prior threshold per row (p.prior), no class bookkeeping
 // MODE 5: no survivor buffers at all: every thread keeps the two largest values of each of the 32 column
 //         classes of its sub-stream in registers and writes these kTopM = 64 values to p.top_out (sample pre-pass)
+// One PIECE of a CTA's work: n_my_tiles tiles starting at tile_begin against the x rows [m0, m0 + 128). A CTA of
+// the (split, row block) grid has one piece; a CTA of the range schedule (see Piece below) up to three, and calls
+// this once per piece: all selection state is per piece. tt0 = tiles this CTA has processed before the piece (the
+// accumulator / barrier phases run on across pieces); sub_base + half = the piece's sub-stream among the row's
+// p.nsub survivor lists; zero_from >= 0: this is the last piece of its row block and the lists from zero_from on
+// are unused for these rows (their counts are cleared for the merge).
 template <int MODE>
 __device__ __forceinline__ void epilogue_loop(const EncodeLaunch& p, int n_my_tiles, int tile_begin,
-                                              int split, int m0, int e, int lane, uint32_t tmem_base,
-                                              const float* bias_smem, uint16_t* share,
+                                              int sub_base, int m0, int tt0, int zero_from, int e, int lane,
+                                              uint32_t tmem_base, const float* bias_smem, uint16_t* share,
                                               uint64_t* tmem_full, uint64_t* tmem_empty,
                                               uint64_t* bias_full, uint64_t* pair_empty) {
   const unsigned full = 0xffffffffu;
@@ -180,8 +188,8 @@ __device__ __forceinline__ void epilogue_loop(const EncodeLaunch& p, int n_my_ti
   const int row = m0 + row_in_tile;
   const bool row_ok = row < p.B;
   const bool live = row_ok && p.debug_mode == 0;
-  const int nsub = p.n_splits * 2;
-  const int sub = split * 2 + half;
+  const int nsub = p.nsub;
+  const int sub = sub_base + half;
   const int cap = p.cap;
   const size_t slot = static_cast<size_t>(row_ok ? row : 0) * nsub + sub;
   uint2* buf = reinterpret_cast<uint2*>(p.cand) + slot * cap;
@@ -214,8 +222,8 @@ __device__ __forceinline__ void epilogue_loop(const EncodeLaunch& p, int n_my_ti
   for (int j = 0; j < (kTop2 ? 32 : 1); ++j) top2[j] = init;
 
   for (int t = 0; t < n_my_tiles; ++t) {
-    const int acc = t & 1;
-    const uint32_t ph = (t >> 1) & 1;
+    const int acc = (tt0 + t) & 1;
+    const uint32_t ph = ((tt0 + t) >> 1) & 1;
     mbar_wait(&tmem_full[acc], ph);
     mbar_wait(&bias_full[acc], ph);
     tc_fence_after();
@@ -336,8 +344,56 @@ __device__ __forceinline__ void epilogue_loop(const EncodeLaunch& p, int n_my_ti
   } else if (row_ok) {
     p.cand_cnt[slot] = cnt;
     p.cand_thr[slot] = live ? valid_bound : -INFINITY;
+    if (zero_from >= 0 && half == 0) {
+      for (int s2 = zero_from; s2 < nsub; ++s2) {
+        p.cand_cnt[static_cast<size_t>(row) * nsub + s2] = 0;
+        p.cand_thr[static_cast<size_t>(row) * nsub + s2] = -INFINITY;
+      }
+    }
   }
 }
+
+// ---- range schedule --------------------------------------------------------------------------------------
+// Small batches do not fill the machine with (split, row block) CTAs: B = 4096 gives 32 row blocks x 4 splits = 128
+// CTAs on 148 SMs. With p.range_g > 0 the grid is range_g CTAs (one per SM) and the U = row_blocks x n_tiles tile
+// units, in row-block-major order, are cut into range_g contiguous ranges of (almost) equal length: CTA g sweeps
+// units [g U / G, (g + 1) U / G). A range that crosses a row-block boundary is processed in pieces, the x tile
+// being reloaded in between (the producer waits for the MMAs that still read the old one); every piece is a
+// sub-stream pair of its row block, numbered by the CTA's position among the CTAs that touch the block.
+struct Piece {
+  int rb, tile0, n, sub_base, zero_from;
+};
+__host__ __device__ inline long long range_start(long long g, long long U, long long G) { return g * U / G; }
+// the CTA whose range contains unit u: the largest g with g U / G <= u
+__host__ __device__ inline int range_owner(long long u, long long U, long long G) {
+  return static_cast<int>(((u + 1) * G - 1) / U);
+}
+struct PieceIter {
+  long long u, u_end, U, G;
+  int n_tiles, g;
+  bool legacy, done;
+  Piece legacy_piece;
+  __device__ bool next(Piece& pc) {
+    if (legacy) {
+      if (done) return false;
+      done = true;
+      pc = legacy_piece;
+      return pc.n > 0;
+    }
+    if (u >= u_end) return false;
+    const int rb = static_cast<int>(u / n_tiles);
+    const int t0 = static_cast<int>(u - static_cast<long long>(rb) * n_tiles);
+    const long long left = u_end - u;
+    const int n = static_cast<int>(left < n_tiles - t0 ? left : n_tiles - t0);
+    const long long first_u = static_cast<long long>(rb) * n_tiles;
+    const int g_first = range_owner(first_u, U, G);
+    pc.rb = rb; pc.tile0 = t0; pc.n = n;
+    pc.sub_base = 2 * (g - g_first);
+    pc.zero_from = (t0 + n == n_tiles) ? pc.sub_base + 2 : -1;
+    u += n;
+    return true;
+  }
+};
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -369,7 +425,7 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
 // WIDE: 36-word fp32 staging rows (32 columns at a time); otherwise the fp32 tile goes through the
 // 20-word bf16 layout in two 16-column halves (the single-CTA variant has no shared memory to spare).
 template <bool WIDE>
-__device__ __forceinline__ void epilogue_dense(const EncodeLaunch& p, int n_my_tiles, int tile_begin, int m0, int e,
+__device__ __forceinline__ void epilogue_dense(const EncodeLaunch& p, int n_my_tiles, int tile_begin, int m0, int tt0, int e,
                                                int lane, uint32_t tmem_base, const float* bias_smem, uint8_t* staging,
                                                uint64_t* tmem_full, uint64_t* tmem_empty, uint64_t* bias_full,
                                                uint64_t* pair_empty) {
@@ -387,8 +443,8 @@ __device__ __forceinline__ void epilogue_dense(const EncodeLaunch& p, int n_my_t
   const int h_row = lane >> 2, h_col = (lane & 3) * 8;
 
   for (int t = 0; t < n_my_tiles; ++t) {
-    const int acc = t & 1;
-    const uint32_t ph = (t >> 1) & 1;
+    const int acc = (tt0 + t) & 1;
+    const uint32_t ph = ((tt0 + t) >> 1) & 1;
     mbar_wait(&tmem_full[acc], ph);
     mbar_wait(&bias_full[acc], ph);
     tc_fence_after();
@@ -589,26 +645,57 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* bias_full = tmem_empty + 2;
   uint64_t* pair_empty = bias_full + 2;     // leader only: both CTAs' epilogues released accumulator a
+  uint64_t* a_empty = pair_empty + 2;       // every MMA of the finished piece has completed (the x tile may be replaced)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L.tmem_ptr_off);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // range schedule (single-CTA variant only): one CTA per SM sweeps a contiguous range of tile units
+  const bool ranged = (CL == 0) && p.range_g > 0;
   // cluster variants pair two row blocks along grid.x (CTA pairs must be adjacent in x)
-  const int split = (CL != 0) ? blockIdx.y : blockIdx.x;
-  const int m0 = ((CL != 0) ? blockIdx.x : blockIdx.y) * BM;
-  const int tile_begin = split * p.tiles_per_split;
-  const int tile_end = min(p.n_tiles, tile_begin + p.tiles_per_split);
-  const int n_my_tiles = max(0, tile_end - tile_begin);
+  const int split = ranged ? 0 : ((CL != 0) ? blockIdx.y : blockIdx.x);
+  const int m0_grid = ranged ? 0 : ((CL != 0) ? blockIdx.x : blockIdx.y) * BM;
   const uint32_t cta_rank = (CL != 0) ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0u;
   const int k_iters = (p.k_parts > 1 ? p.k_parts : 1) * K_CHUNKS;
-
+  // the CTA's pieces, computed once by thread 0 (64-bit divisions) and read from shared memory by every role
+  int* piece_n = reinterpret_cast<int*>(smem + L.piece_off);
+  Piece* piece_tab = reinterpret_cast<Piece*>(smem + L.piece_off + 16);
+  if (threadIdx.x == 0) {
+    PieceIter it;
+    it.legacy = !ranged;
+    it.done = false;
+    it.n_tiles = p.n_tiles;
+    it.g = blockIdx.x;
+    it.U = static_cast<long long>((p.B + BM - 1) / BM) * p.n_tiles;
+    it.G = ranged ? p.range_g : 1;
+    it.u = ranged ? range_start(blockIdx.x, it.U, it.G) : 0;
+    it.u_end = ranged ? range_start(blockIdx.x + 1, it.U, it.G) : 0;
+    const int tile_begin = split * p.tiles_per_split;
+    const int tile_end = min(p.n_tiles, tile_begin + p.tiles_per_split);
+    it.legacy_piece.rb = m0_grid / BM;
+    it.legacy_piece.tile0 = tile_begin;
+    it.legacy_piece.n = max(0, tile_end - tile_begin);
+    it.legacy_piece.sub_base = split * 2;
+    it.legacy_piece.zero_from = -1;
+    int n = 0;
+    Piece pc;
+    while (it.next(pc)) {
+      if (n == kMaxPieces) {
+        printf("qsae: more than %d pieces in one CTA's tile range\n", kMaxPieces);
+        __trap();
+      }
+      piece_tab[n++] = pc;
+    }
+    *piece_n = n;
+  }
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0u) {
       printf("qsae: dynamic shared memory is not 1024-byte aligned\n");
       __trap();
     }
     mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], MCAST ? 2 : 1);   // multicast: both CTAs' MMAs must have released the stage
@@ -635,136 +722,163 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
 
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer
-    if (lane == 0 && n_my_tiles > 0) {
+    if (lane == 0) {
       tma_prefetch_desc(&tmap_x);
       tma_prefetch_desc(&tmap_b0);
-      if constexpr (PAIR) {
-        // both x tiles and both halves of every W stage are credited to the leader's barriers
-        const uint32_t a_full_leader = mapa_u32(smem_u32(a_full), 0);
-        if (leader) mbar_arrive_expect_tx(a_full, 2 * K_CHUNKS * kABytesPerChunk);
-#pragma unroll
-        for (int kc = 0; kc < K_CHUNKS; ++kc)
-          tma_load_2d_pair(a_smem + kc * kABytesPerChunk, &tmap_x, a_full_leader, kc * BK, m0, kPolicyEvictFirst);
-      } else {
-        mbar_arrive_expect_tx(a_full, K_CHUNKS * kABytesPerChunk);
-#pragma unroll
-        for (int kc = 0; kc < K_CHUNKS; ++kc)
-          tma_load_2d(a_smem + kc * kABytesPerChunk, &tmap_x, a_full, kc * BK, m0, kPolicyEvictFirst);
-      }
+      const int n_pieces = *piece_n;
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = 0; t < n_my_tiles; ++t) {
-        const int n0 = (tile_begin + t) * BN;
-        // p.k_parts B operands (bf16 parts of W) are contracted against the same resident x tile
+      for (int pi = 0; pi < n_pieces; ++pi) {
+        const Piece pc = piece_tab[pi];
+        const int m0 = pc.rb * BM;
+        // a new x tile may only land once every MMA that reads the previous one has completed
+        if (pi > 0) mbar_wait(a_empty, static_cast<uint32_t>(pi - 1) & 1u);
+        if constexpr (PAIR) {
+          // both x tiles and both halves of every W stage are credited to the leader's barriers
+          const uint32_t a_full_leader = mapa_u32(smem_u32(a_full), 0);
+          if (leader) mbar_arrive_expect_tx(a_full, 2 * K_CHUNKS * kABytesPerChunk);
+#pragma unroll
+          for (int kc = 0; kc < K_CHUNKS; ++kc)
+            tma_load_2d_pair(a_smem + kc * kABytesPerChunk, &tmap_x, a_full_leader, kc * BK, m0, kPolicyEvictFirst);
+        } else {
+          mbar_arrive_expect_tx(a_full, K_CHUNKS * kABytesPerChunk);
+#pragma unroll
+          for (int kc = 0; kc < K_CHUNKS; ++kc)
+            tma_load_2d(a_smem + kc * kABytesPerChunk, &tmap_x, a_full, kc * BK, m0, kPolicyEvictFirst);
+        }
+        for (int t = 0; t < pc.n; ++t) {
+          const int n0 = (pc.tile0 + t) * BN;
+          // p.k_parts B operands (bf16 parts of W) are contracted against the same resident x tile
 #pragma unroll 1
-        for (int it = 0; it < k_iters; ++it) {
-          const int part = it / K_CHUNKS, kc = it - part * K_CHUNKS;
-          const CUtensorMap* tb = part == 0 ? &tmap_b0 : (part == 1 ? &tmap_b1 : &tmap_b2);
-          mbar_wait(&empty[stage], phase ^ 1u);
-          if constexpr (PAIR) {
-            if (leader) mbar_arrive_expect_tx(&full[stage], kBBytesPerStage);   // 16 KiB from each CTA
-            tma_load_2d_pair(b_smem + stage * kStageBytes, tb, mapa_u32(smem_u32(&full[stage]), 0), kc * BK,
-                             n0 + static_cast<int>(cta_rank) * (BN / 2), kPolicyEvictLast);
-          } else if constexpr (MCAST) {
-            mbar_arrive_expect_tx(&full[stage], kBBytesPerStage);
-            // my half of the stage lands in both CTAs; the other half arrives from the peer
-            tma_load_2d_mcast(b_smem + stage * kBBytesPerStage + cta_rank * (kBBytesPerStage / 2), tb,
-                              &full[stage], kc * BK, n0 + static_cast<int>(cta_rank) * (BN / 2), 0x3, kPolicyEvictLast);
-          } else {
-            mbar_arrive_expect_tx(&full[stage], kBBytesPerStage);
-            tma_load_2d(b_smem + stage * kBBytesPerStage, tb, &full[stage], kc * BK, n0, kPolicyEvictLast);
+          for (int it2 = 0; it2 < k_iters; ++it2) {
+            const int part = it2 / K_CHUNKS, kc = it2 - part * K_CHUNKS;
+            const CUtensorMap* tb = part == 0 ? &tmap_b0 : (part == 1 ? &tmap_b1 : &tmap_b2);
+            mbar_wait(&empty[stage], phase ^ 1u);
+            if constexpr (PAIR) {
+              if (leader) mbar_arrive_expect_tx(&full[stage], kBBytesPerStage);   // 16 KiB from each CTA
+              tma_load_2d_pair(b_smem + stage * kStageBytes, tb, mapa_u32(smem_u32(&full[stage]), 0), kc * BK,
+                               n0 + static_cast<int>(cta_rank) * (BN / 2), kPolicyEvictLast);
+            } else if constexpr (MCAST) {
+              mbar_arrive_expect_tx(&full[stage], kBBytesPerStage);
+              // my half of the stage lands in both CTAs; the other half arrives from the peer
+              tma_load_2d_mcast(b_smem + stage * kBBytesPerStage + cta_rank * (kBBytesPerStage / 2), tb,
+                                &full[stage], kc * BK, n0 + static_cast<int>(cta_rank) * (BN / 2), 0x3, kPolicyEvictLast);
+            } else {
+              mbar_arrive_expect_tx(&full[stage], kBBytesPerStage);
+              tma_load_2d(b_smem + stage * kBBytesPerStage, tb, &full[stage], kc * BK, n0, kPolicyEvictLast);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------- MMA issuer (pair: the leader only)
-    if (lane == 0 && n_my_tiles > 0 && (!PAIR || leader)) {
+    if (lane == 0 && (!PAIR || leader)) {
       constexpr uint32_t idesc = umma_idesc_bf16_f32(PAIR ? 2 * BM : BM, BN);
       const uint64_t a_desc0 = umma_desc_kmajor_sw128(smem_u32(a_smem));
       const uint64_t b_desc0 = umma_desc_kmajor_sw128(smem_u32(b_smem));
-      mbar_wait(a_full, 0);
+      const int n_pieces = *piece_n;
+      int tt = 0;
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = 0; t < n_my_tiles; ++t) {
-        const int acc = t & 1;
-        mbar_wait(PAIR ? &pair_empty[acc] : &tmem_empty[acc], ((t >> 1) & 1) ^ 1u);
+      for (int pi = 0; pi < n_pieces; ++pi) {
+        const Piece pc = piece_tab[pi];
+        mbar_wait(a_full, static_cast<uint32_t>(pi) & 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-#pragma unroll 1
-        for (int it = 0; it < k_iters; ++it) {
-          const int kc = it % K_CHUNKS;      // every part of W meets the same x chunks
-          mbar_wait(&full[stage], phase);
+        for (int t = 0; t < pc.n; ++t, ++tt) {
+          const int acc = tt & 1;
+          mbar_wait(PAIR ? &pair_empty[acc] : &tmem_empty[acc], ((tt >> 1) & 1) ^ 1u);
           tc_fence_after();
-          const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((kc * kABytesPerChunk) >> 4);
-          const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((stage * kStageBytes) >> 4);
+          const uint32_t d_tmem = tmem_base + acc * BN;
+#pragma unroll 1
+          for (int it2 = 0; it2 < k_iters; ++it2) {
+            const int kc = it2 % K_CHUNKS;      // every part of W meets the same x chunks
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((kc * kABytesPerChunk) >> 4);
+            const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((stage * kStageBytes) >> 4);
 #pragma unroll
-          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-            // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the
-            // (address >> 4) field of the descriptor
-            if constexpr (PAIR) umma_f16_ss_pair(d_tmem, a_desc + ks * 2, b_desc + ks * 2, idesc, (it | ks) != 0 ? 1u : 0u);
-            else umma_f16_ss(d_tmem, a_desc + ks * 2, b_desc + ks * 2, idesc, (it | ks) != 0 ? 1u : 0u);
+            for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+              // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the
+              // (address >> 4) field of the descriptor
+              if constexpr (PAIR) umma_f16_ss_pair(d_tmem, a_desc + ks * 2, b_desc + ks * 2, idesc, (it2 | ks) != 0 ? 1u : 0u);
+              else umma_f16_ss(d_tmem, a_desc + ks * 2, b_desc + ks * 2, idesc, (it2 | ks) != 0 ? 1u : 0u);
+            }
+            if constexpr (PAIR) {
+              umma_commit_pair(&empty[stage], 0x3);
+              if (it2 == k_iters - 1) umma_commit_pair(&tmem_full[acc], 0x3);
+            } else {
+              if constexpr (MCAST) umma_commit_mcast(&empty[stage], 0x3);
+              else umma_commit(&empty[stage]);
+              if (it2 == k_iters - 1) umma_commit(&tmem_full[acc]);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
-          if constexpr (PAIR) {
-            umma_commit_pair(&empty[stage], 0x3);
-            if (it == k_iters - 1) umma_commit_pair(&tmem_full[acc], 0x3);
-          } else {
-            if constexpr (MCAST) umma_commit_mcast(&empty[stage], 0x3);
-            else umma_commit(&empty[stage]);
-            if (it == k_iters - 1) umma_commit(&tmem_full[acc]);
-          }
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
+        if constexpr (CL == 0) umma_commit(a_empty);   // the piece's MMAs no longer read the x tile once this fires
       }
     }
   } else if (warp == 3) {
     // ------------------------------------------------------------- bias tile loader
-    for (int t = 0; t < n_my_tiles; ++t) {
-      const int acc = t & 1;
-      mbar_wait(&tmem_empty[acc], ((t >> 1) & 1) ^ 1u);
-      const int n0 = (tile_begin + t) * BN;
+    const int n_pieces = *piece_n;
+    int tt = 0;
+    for (int pi = 0; pi < n_pieces; ++pi) {
+      const Piece pc = piece_tab[pi];
+      for (int t = 0; t < pc.n; ++t, ++tt) {
+        const int acc = tt & 1;
+        mbar_wait(&tmem_empty[acc], ((tt >> 1) & 1) ^ 1u);
+        const int n0 = (pc.tile0 + t) * BN;
 #pragma unroll
-      for (int i = 0; i < BN / 32; ++i) {
-        const int c = i * 32 + lane;
-        bias_smem[acc * BN + c] = (p.bias != nullptr && n0 + c < p.H) ? __ldg(p.bias + n0 + c) : 0.f;
+        for (int i = 0; i < BN / 32; ++i) {
+          const int c = i * 32 + lane;
+          bias_smem[acc * BN + c] = (p.bias != nullptr && n0 + c < p.H) ? __ldg(p.bias + n0 + c) : 0.f;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bias_full[acc]);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bias_full[acc]);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------- epilogue / selection
     const int e = warp - 4;
     uint64_t* pe = PAIR ? pair_empty : nullptr;
-    if constexpr (DENSE) {
-      epilogue_dense<PAIR>(p, n_my_tiles, tile_begin, m0, e, lane, tmem_base, bias_smem, smem + L.staging_off,
+    const int n_pieces = *piece_n;
+    int tt0 = 0;
+#pragma unroll 1
+    for (int pi = 0; pi < n_pieces; ++pi) {
+      const Piece pc = piece_tab[pi];
+      const int m0 = pc.rb * BM;
+      if constexpr (DENSE) {
+        epilogue_dense<PAIR>(p, pc.n, pc.tile0, m0, tt0, e, lane, tmem_base, bias_smem, smem + L.staging_off,
+                             tmem_full, tmem_empty, bias_full, pe);
+      } else
+      switch (p.mode) {
+        case 1:
+          epilogue_loop<1>(p, pc.n, pc.tile0, pc.sub_base, m0, tt0, pc.zero_from, e, lane, tmem_base, bias_smem, share,
                            tmem_full, tmem_empty, bias_full, pe);
-    } else
-    switch (p.mode) {
-      case 1:
-        epilogue_loop<1>(p, n_my_tiles, tile_begin, split, m0, e, lane, tmem_base, bias_smem, share,
-                         tmem_full, tmem_empty, bias_full, pe);
-        break;
-      case 2:
-        epilogue_loop<2>(p, n_my_tiles, tile_begin, split, m0, e, lane, tmem_base, bias_smem, share,
-                         tmem_full, tmem_empty, bias_full, pe);
-        break;
-      case 3:
-        epilogue_loop<3>(p, n_my_tiles, tile_begin, split, m0, e, lane, tmem_base, bias_smem, share,
-                         tmem_full, tmem_empty, bias_full, pe);
-        break;
-      case 4:
-        epilogue_loop<4>(p, n_my_tiles, tile_begin, split, m0, e, lane, tmem_base, bias_smem, share,
-                         tmem_full, tmem_empty, bias_full, pe);
-        break;
-      case 5:
-        epilogue_loop<5>(p, n_my_tiles, tile_begin, split, m0, e, lane, tmem_base, bias_smem, share,
-                         tmem_full, tmem_empty, bias_full, pe);
-        break;
-      default:
-        epilogue_loop<0>(p, n_my_tiles, tile_begin, split, m0, e, lane, tmem_base, bias_smem, share,
-                         tmem_full, tmem_empty, bias_full, pe);
-        break;
+          break;
+        case 2:
+          epilogue_loop<2>(p, pc.n, pc.tile0, pc.sub_base, m0, tt0, pc.zero_from, e, lane, tmem_base, bias_smem, share,
+                           tmem_full, tmem_empty, bias_full, pe);
+          break;
+        case 3:
+          epilogue_loop<3>(p, pc.n, pc.tile0, pc.sub_base, m0, tt0, pc.zero_from, e, lane, tmem_base, bias_smem, share,
+                           tmem_full, tmem_empty, bias_full, pe);
+          break;
+        case 4:
+          epilogue_loop<4>(p, pc.n, pc.tile0, pc.sub_base, m0, tt0, pc.zero_from, e, lane, tmem_base, bias_smem, share,
+                           tmem_full, tmem_empty, bias_full, pe);
+          break;
+        case 5:
+          epilogue_loop<5>(p, pc.n, pc.tile0, pc.sub_base, m0, tt0, pc.zero_from, e, lane, tmem_base, bias_smem, share,
+                           tmem_full, tmem_empty, bias_full, pe);
+          break;
+        default:
+          epilogue_loop<0>(p, pc.n, pc.tile0, pc.sub_base, m0, tt0, pc.zero_from, e, lane, tmem_base, bias_smem, share,
+                           tmem_full, tmem_empty, bias_full, pe);
+          break;
+      }
+      tt0 += pc.n;
     }
   }
 
@@ -1106,6 +1220,7 @@ cudaError_t launch_k(const CUtensorMap& tx, const BMaps& b, const EncodeLaunch& 
     attr_set = true;
   }
   dim3 grid(p.n_splits, (p.B + BM - 1) / BM);
+  if (CL == 0 && p.range_g > 0) grid = dim3(p.range_g, 1);
   if constexpr (CL != 0) {
     // whole clusters along x; the padding CTA sweeps zero rows and writes nothing
     grid = dim3(((p.B + BM - 1) / BM + 1) / 2 * 2, p.n_splits);
@@ -1153,7 +1268,7 @@ const char* launch_any(const CUtensorMap& tx, const BMaps& b, const EncodeLaunch
 // Cluster variant of a launch: 0 single CTA, 1 multicast pair, 2 cta_group::2 pair. Pairs need two row
 // blocks. QSAE_ENCODE_CLUSTER overrides the default (tests and tuning experiments).
 int pick_cluster(const EncodeLaunch& p, int dflt) {
-  if (const char* m = getenv("QSAE_ENCODE_CLUSTER")) dflt = atoi(m);
+  if (tuning().encode_cluster >= 0) dflt = tuning().encode_cluster;
   if (dflt < 0 || dflt > 2 || p.D <= 448 || p.B <= BM) return 0;
   return dflt;
 }
@@ -1175,6 +1290,30 @@ int encode_pick_splits(int B, int H, int num_sms) {
     if (eff > best * 1.03) { best = eff; best_s = s; }
   }
   return best_s;
+}
+
+int encode_pick_range(int B, int H, int num_sms, int* nsub) {
+  *nsub = 0;
+  if (tuning().encode_range == 0 || B >= 16384) return 0;   // large batches: the multicast pairs take over
+  const long long m_tiles = (B + BM - 1) / BM;
+  const long long n_tiles = (H + BN - 1) / BN;
+  const long long U = m_tiles * n_tiles;
+  const int s = encode_pick_splits(B, H, num_sms);
+  const long long units = m_tiles * s;
+  const long long waves = (units + num_sms - 1) / num_sms;
+  const long long tps = (n_tiles + s - 1) / s;
+  const double eff = (static_cast<double>(units) / (waves * num_sms)) *
+                     (static_cast<double>(n_tiles) / (static_cast<double>(tps) * s));
+  if (eff >= 0.95 || U < 2ll * num_sms) return 0;
+  const long long G = num_sms;
+  int max_pieces = 1;
+  for (long long rb = 0; rb < m_tiles; ++rb) {
+    const int pieces = range_owner(rb * n_tiles + n_tiles - 1, U, G) - range_owner(rb * n_tiles, U, G) + 1;
+    if (pieces > max_pieces) max_pieces = pieces;
+  }
+  if (2 * max_pieces > 32) return 0;   // the warp-level merge reads at most 32 lists per row
+  *nsub = 2 * max_pieces;
+  return static_cast<int>(G);
 }
 
 void encode_pick_mode(int k_sel, int* mode, int* cap) {
@@ -1202,7 +1341,7 @@ const char* encode_topk_launch(const uint16_t* x_bf16, const uint16_t* w_bf16, E
   p.dense_flags = 0;
   p.k_parts = 1;
   p.accum_mode = 0;
-  p.cluster = pick_cluster(p, p.B >= 16384 ? 1 : 0);
+  p.cluster = p.range_g > 0 ? 0 : pick_cluster(p, p.B >= 16384 ? 1 : 0);
   BMaps bm;
   if (const char* err = make_b_maps(&bm, &w_bf16, 1, p)) return err;
   return launch_any<false>(tx, bm, p, stream);
@@ -1221,7 +1360,7 @@ const char* encode_dense_tc_launch(const uint16_t* x_bf16, const uint16_t* const
   p.k_parts = n_parts;
   p.dense_flags = (out_f32 ? 1 : 0) | (out_hi ? 2 : 0) | (out_lo ? 4 : 0);
   if (p.dense_flags == 0) return "dense encoder: no output requested";
-  if (const char* m = getenv("QSAE_DENSE_FLAGS_MASK")) p.dense_flags &= atoi(m);  // timing experiments only
+  if (tuning().dense_flags_mask >= 0) p.dense_flags &= tuning().dense_flags_mask;  // timing experiments only
   p.cluster = pick_cluster(p, kDefaultClusterDense);
   BMaps bm;
   if (const char* err = make_b_maps(&bm, w_parts, n_parts, p)) return err;
@@ -1256,9 +1395,7 @@ cudaError_t launch_prep(const CUtensorMap& tw, const PrepLaunch& p, cudaStream_t
 }  // namespace
 
 int prior_prep_pick_ns(int B, int D, int n_sample, int m, int num_sms) {
-  if (const char* ov = getenv("QSAE_PRIOR_PREP")) {   // "0": always the separate cast / pre-pass / prior kernels
-    if (atoi(ov) == 0) return 0;
-  }
+  if (tuning().prior_prep == 0) return 0;   // always the separate cast / pre-pass / prior kernels
   if (D != 512 && D != 256) return 0;                  // instantiated widths (the benchmark shapes)
   if (n_sample < 512 || m < 1 || m > 32) return 0;
   const int m_tiles = (B + BM - 1) / BM;

@@ -17,10 +17,33 @@ constexpr size_t kSelectSmemBudget = 200 * 1024;   // shared memory of the block
 constexpr int kTopM = 64;          // values a thread keeps in the sample pre-pass (mode 5): top 2 of 32 column classes
 constexpr int kPriorMaxRank = 16;  // largest rank m of the prior threshold among a row's nsub * kTopM kept values
 
+// Tuning / diagnostic switches, read ONCE from the environment (never on a launch path); qsae_reload_tuning()
+// re-reads them (tests and tuning experiments that change the environment of a live process).
+struct Tuning {
+  int encode_splits;      // QSAE_ENCODE_SPLITS: latent-axis splits of the sweep (0 = automatic)
+  int encode_prior;       // QSAE_ENCODE_PRIOR: 0 switches the sampled prior off
+  int encode_debug_mode;  // QSAE_ENCODE_DEBUG_MODE: timing experiments (EncodeLaunch::debug_mode)
+  int encode_cluster;     // QSAE_ENCODE_CLUSTER: 0 / 1 / 2 forces the cluster variant (-1 = automatic)
+  int encode_range;       // QSAE_ENCODE_RANGE: 0 keeps the (split, row block) grid at small batches
+  int prior_prep;         // QSAE_PRIOR_PREP: 0 keeps the separate cast / pre-pass / prior kernels
+  int dense_flags_mask;   // QSAE_DENSE_FLAGS_MASK: masks dense epilogue outputs (-1 = off; timing experiments)
+  int decode_pair;        // QSAE_DECODE_PAIR: 0 / 1 forces the decoder GEMM variant (-1 = automatic)
+  int peer_timeout_ms;    // QSAE_PEER_TIMEOUT_MS: bound of a peer-memory flag wait (default 20000)
+  int debug_large;        // QSAE_DEBUG_LARGE: survivor statistics of the large-k path on stderr (synchronises)
+  int debug_pipeline;     // QSAE_DEBUG_PIPELINE: per-chunk event timeline of the host-buffer pipeline on stderr
+};
+const Tuning& tuning();
+void reload_tuning();
+// kernels launched by this library in this process (qsae_launch_count): the C-ABI wrappers count one per *_launch
+// call, launchers that start further kernels add them here
+void count_launches(int n);
+
 struct EncodeLaunch {
   int B, H, D;
   int k_sel;            // survivors that must be retained per row (k, or k + rescore margin)
   int n_splits;         // grid.x
+  int nsub;             // survivor lists per row: 2 n_splits, or the range schedule's 2 x max pieces per row block
+  int range_g;          // > 0: range schedule (encode_topk_sm100.cu) with this many CTAs instead of the (split, row block) grid
   int tiles_per_split;  // in units of kEncBN latents
   int n_tiles;          // ceil(H / kEncBN)
   int act;              // 0 none, 1 relu
@@ -48,6 +71,8 @@ struct EncodeLaunch {
 
 // encode_topk_sm100.cu
 int encode_pick_splits(int B, int H, int num_sms);
+// range schedule for this shape: CTAs to launch (0 = keep the (split, row block) grid) and lists per row
+int encode_pick_range(int B, int H, int num_sms, int* nsub);
 void encode_pick_mode(int k_sel, int* mode, int* cap);
 const char* encode_topk_launch(const uint16_t* x_bf16, const uint16_t* w_bf16, EncodeLaunch p,
                                cudaStream_t stream);

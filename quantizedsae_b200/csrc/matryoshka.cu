@@ -339,6 +339,7 @@ const char* matryoshka_dense_operand_launch(const float* z, int B, int H, const 
                                                                            a_hi, a_lo, partial);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cudaGetErrorString(e);
+  count_launches(1);
   sum_level_counts_kernel<<<1, 256, 0, stream>>>(partial, static_cast<int>(g), 32, n_levels, level_count);
   return cuda_err(cudaGetLastError());
 }
@@ -385,6 +386,7 @@ const char* decode_matryoshka_launch(const void* cand, const int* cand_cnt, int 
 #undef QSAE_MAT
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cudaGetErrorString(e);
+  count_launches(1);
   sum_level_counts_kernel<<<1, 256, 0, stream>>>(partial, blocks * kMatWarps, nl, n_levels, level_count);
   return cuda_err(cudaGetLastError());
 }

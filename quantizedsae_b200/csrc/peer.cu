@@ -5,8 +5,9 @@
 // over NVLink, fused with the selection) and the final kernel sums the peers' partial rows it owns.
 // Synchronisation: per (phase, producer) sequence flags living in the consumer's buffer, written remotely by a
 // one-block signal kernel after the producing kernel (stream order), polled by a one-block wait kernel before the
-// consuming kernel. The wait is bounded (about two seconds): on timeout it raises a device flag and returns, so a
-// lost peer can never hang the GPU.
+// consuming kernel. The wait is bounded (QSAE_PEER_TIMEOUT_MS, default 20 s): on timeout it raises a device flag and
+// returns, so a lost peer can never hang the GPU; the host side (sharded.PeerExchange) reads the flag after every
+// forward and raises.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -24,14 +25,15 @@ __global__ void peer_signal_kernel(unsigned* const* __restrict__ targets, int n,
   __threadfence_system();
 }
 
-__global__ void peer_wait_kernel(const unsigned* __restrict__ flags, int n, unsigned value, int* __restrict__ timed_out) {
+__global__ void peer_wait_kernel(const unsigned* __restrict__ flags, int n, unsigned value, int* __restrict__ timed_out,
+                                 long long timeout_cycles) {
   const int g = threadIdx.x;
   if (g >= n) return;
   const volatile unsigned* f = flags + g;
   const long long t0 = clock64();
   // flags only grow (sequence numbers); signed difference tolerates wrap-around
   while (static_cast<int>(*f - value) < 0) {
-    if (clock64() - t0 > 4000000000ll) {   // ~2 s at 2 GHz
+    if (clock64() - t0 > timeout_cycles) {
       atomicExch(timed_out, 1);
       break;
     }
@@ -67,7 +69,8 @@ const char* peer_signal_launch(unsigned* const* targets, int n, unsigned value, 
 
 const char* peer_wait_launch(const unsigned* flags, int n, unsigned value, int* timed_out, cudaStream_t stream) {
   if (n < 1 || n > 32) return "peer_wait: 1 <= n <= 32";
-  peer_wait_kernel<<<1, 32, 0, stream>>>(flags, n, value, timed_out);
+  const long long cycles = static_cast<long long>(tuning().peer_timeout_ms > 0 ? tuning().peer_timeout_ms : 20000) * 2000000ll;   // ~2 GHz
+  peer_wait_kernel<<<1, 32, 0, stream>>>(flags, n, value, timed_out, cycles);
   return cuda_err(cudaGetLastError());
 }
 

@@ -7,12 +7,46 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <new>
 
 #include "../../include/qsae_b200.h"
 #include "kernels.h"
 
 using namespace qsae;
+
+namespace qsae {
+namespace {
+std::atomic<unsigned long long> g_launches{0};
+Tuning g_tuning;
+bool g_tuning_loaded = false;
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+}  // namespace
+void reload_tuning() {
+  Tuning t;
+  t.encode_splits = env_int("QSAE_ENCODE_SPLITS", 0);
+  t.encode_prior = env_int("QSAE_ENCODE_PRIOR", 1);
+  t.encode_debug_mode = env_int("QSAE_ENCODE_DEBUG_MODE", 0);
+  t.encode_cluster = env_int("QSAE_ENCODE_CLUSTER", -1);
+  t.encode_range = env_int("QSAE_ENCODE_RANGE", 1);
+  t.prior_prep = env_int("QSAE_PRIOR_PREP", 1);
+  t.dense_flags_mask = env_int("QSAE_DENSE_FLAGS_MASK", -1);
+  t.decode_pair = env_int("QSAE_DECODE_PAIR", -1);
+  t.peer_timeout_ms = env_int("QSAE_PEER_TIMEOUT_MS", 20000);
+  t.debug_large = getenv("QSAE_DEBUG_LARGE") != nullptr;
+  t.debug_pipeline = getenv("QSAE_DEBUG_PIPELINE") != nullptr;
+  g_tuning = t;
+  g_tuning_loaded = true;
+}
+void count_launches(int n) { g_launches.fetch_add(static_cast<unsigned long long>(n), std::memory_order_relaxed); }
+const Tuning& tuning() {
+  if (!g_tuning_loaded) reload_tuning();
+  return g_tuning;
+}
+}  // namespace qsae
 
 namespace {
 
@@ -35,7 +69,10 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 int launch_status(const char* what, const char* err) {
-  if (err == nullptr) return QSAE_OK;
+  if (err == nullptr) {
+    count_launches(1);
+    return QSAE_OK;
+  }
   return fail(QSAE_ERR_CUDA, "%s: %s", what, err);
 }
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -55,7 +92,7 @@ int num_sms() {
 
 // One fused-kernel + merge stage over a dictionary of H rows.
 struct StagePlan {
-  int H, k_sel, n_splits, nsub, n_tiles, tiles_per_split, mode, cap;
+  int H, k_sel, n_splits, nsub, n_tiles, tiles_per_split, mode, cap, range_g;
   size_t cand_off, cnt_off, thr_off, end;
 };
 
@@ -64,13 +101,12 @@ enum StageKind { kStageClassBound = 0, kStagePriorMain = 1, kStageSamplePre = 2 
 void plan_stage(int B, int H, int k_sel, StageKind kind, bool allow_split_override, size_t base, StagePlan* sp) {
   sp->H = H;
   sp->k_sel = k_sel;
+  sp->range_g = 0;
   sp->n_tiles = (H + kEncBN - 1) / kEncBN;
   sp->n_splits = encode_pick_splits(B, H, num_sms());
   if (allow_split_override) {
-    if (const char* ov = getenv("QSAE_ENCODE_SPLITS")) {  // tuning experiments only
-      const int s = atoi(ov);
-      if (s >= 1 && s <= kMaxSplits && s <= sp->n_tiles) sp->n_splits = s;
-    }
+    const int s = tuning().encode_splits;   // tuning experiments only
+    if (s >= 1 && s <= kMaxSplits && s <= sp->n_tiles) sp->n_splits = s;
   }
   if (kind == kStageSamplePre && (B + kEncBM - 1) / kEncBM >= num_sms()) sp->n_splits = 1;  // enough row blocks
   if (kind == kStageSamplePre && sp->n_splits > 4) sp->n_splits = 4;   // the prior kernel sorts at most 8 x kTopM values per row
@@ -87,6 +123,16 @@ void plan_stage(int B, int H, int k_sel, StageKind kind, bool allow_split_overri
   if (kind == kStagePriorMain) {
     sp->mode = 4;
     sp->cap = 512;
+    // small batches: one CTA per SM over contiguous tile ranges instead of the (split, row block) grid; a list then
+    // covers ~1 / nsub of a row's latents (a few dozen survivors), so 256 entries are plenty (a full list is cut
+    // exactly in the kernel, as always)
+    int range_nsub = 0;
+    const int g = (k_sel > 0 && allow_split_override && tuning().encode_splits == 0) ? encode_pick_range(B, H, num_sms(), &range_nsub) : 0;
+    if (g > 0) {
+      sp->range_g = g;
+      sp->nsub = range_nsub;
+      sp->cap = 256;
+    }
   } else {
     encode_pick_mode(k_sel, &sp->mode, &sp->cap);
     if (sp->tiles_per_split * (kEncBN / 2) <= 448) sp->cap = 512;  // a sub-stream this short cannot fill more
@@ -137,9 +183,8 @@ int plan_encode(int B, int H, int D, int k, int exact, int n_sample, EncodePlan*
   pl->use_prior = false;
   pl->m = 0;
   if (n_sample >= 256 && H >= 8 * static_cast<long long>(n_sample)) {
-    const char* ov = getenv("QSAE_ENCODE_PRIOR");  // "0" switches the prior off (tuning experiments)
     const int m = choose_prior_rank(k_sel, static_cast<double>(n_sample) / H);
-    if (!(ov && atoi(ov) == 0) && m <= kPriorMaxRank && m <= n_sample) {
+    if (tuning().encode_prior != 0 && m <= kPriorMaxRank && m <= n_sample) {
       pl->use_prior = true;
       pl->m = m;
     }
@@ -165,6 +210,7 @@ void fill_encode_launch(EncodeLaunch* el, const StagePlan& sp, int B, int D, int
   memset(el, 0, sizeof(*el));
   el->B = B; el->H = sp.H; el->D = D; el->k_sel = sp.k_sel;
   el->n_splits = sp.n_splits; el->tiles_per_split = sp.tiles_per_split; el->n_tiles = sp.n_tiles;
+  el->nsub = sp.nsub; el->range_g = sp.range_g;
   el->act = act; el->mode = sp.mode; el->cap = sp.cap; el->bias = bias;
   el->cand = ws + sp.cand_off;
   el->cand_cnt = reinterpret_cast<int*>(ws + sp.cnt_off);
@@ -342,7 +388,7 @@ int encode_topk_large(const float* x_f32, const uint16_t* w_bf16, const float* w
   sl.rescue_count = counters; sl.rescue_rows = rescue_rows; sl.check_count = 1;
   rc = launch_status("select_topk kernel", select_topk_launch(sl, st));
   if (rc != QSAE_OK) return rc;
-  if (getenv("QSAE_DEBUG_LARGE")) {   // diagnostics: survivor statistics of this call (synchronises)
+  if (tuning().debug_large) {   // diagnostics: survivor statistics of this call (synchronises)
     cudaStreamSynchronize(st);
     int h_counters[4];
     cudaMemcpy(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost);
@@ -390,6 +436,13 @@ int qsae_check_device(void) {
 int qsae_set_encode_kernel_events(void* start_event, void* stop_event) {
   g_enc_ev_start = reinterpret_cast<cudaEvent_t>(start_event);
   g_enc_ev_stop = reinterpret_cast<cudaEvent_t>(stop_event);
+  return QSAE_OK;
+}
+
+unsigned long long qsae_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int qsae_reload_tuning(void) {
+  reload_tuning();
   return QSAE_OK;
 }
 
@@ -496,8 +549,7 @@ int encode_topk_impl(const float* x_f32, const uint16_t* w_bf16, const float* w_
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   uint16_t* x_bf16 = reinterpret_cast<uint16_t*>(ws + pl.x_off);
   cudaStream_t st = S(stream);
-  int debug_mode = 0;
-  if (const char* dm = getenv("QSAE_ENCODE_DEBUG_MODE")) debug_mode = atoi(dm);
+  const int debug_mode = tuning().encode_debug_mode;
 
   int* counters = reinterpret_cast<int*>(ws + pl.counters_off);   // [0] rescue rows, [1] merge overflow rows
   int32_t* rescue_rows = reinterpret_cast<int32_t*>(ws + pl.rescue_rows_off);
@@ -1228,7 +1280,7 @@ int qsae_merge_candidates_peer(const void* const* list_bases, int n_shards, int 
 // ---- peer buffers (cudaMalloc + CUDA IPC) and the flag protocol ---------------------------------------------------------
 int qsae_peer_alloc(size_t bytes, void** ptr) {
   if (!ptr || bytes == 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "peer_alloc: bad argument");
-  cudaError_t e = cudaMalloc(ptr, bytes);
+  cudaError_t e = cudaMalloc(ptr, bytes);   // on the CURRENT device: callers select it first (sharded.PeerExchange does)
   if (e == cudaSuccess) e = cudaMemset(*ptr, 0, bytes);
   if (e != cudaSuccess) return fail(QSAE_ERR_CUDA, "peer_alloc: %s", cudaGetErrorString(e));
   return QSAE_OK;
@@ -1407,7 +1459,7 @@ int qsae_bsae_forward_host(qsae_bsae_plan* p, const float* x_host, int B, float*
   // (2048 rows, doubling) to start the output stream early, the rest are as large as the plan allows because
   // the kernels are more efficient on large batches (the compute leg must stay ahead of the copy-out leg).
   int next_rows = p->chunk < 2048 ? p->chunk : 2048;
-  const bool trace = getenv("QSAE_DEBUG_PIPELINE") != nullptr;   // diagnostics: per-chunk event timeline on stderr
+  const bool trace = tuning().debug_pipeline != 0;   // diagnostics: per-chunk event timeline on stderr
   constexpr int kTraceMax = 64;
   cudaEvent_t tev[kTraceMax][4];
   int trows[kTraceMax];

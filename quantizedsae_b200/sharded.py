@@ -151,7 +151,14 @@ class PeerExchange:
     A rank writes its own lists / partial rows, raises its sequence flag in every consumer's buffer, and the
     consumers read the data inside the merge / reduce kernels (P2P loads). Two slots: a rank can be one exchange
     ahead of the slowest reader, never two (its next publish is ordered after a merge that needed every peer's
-    previous publish). Handles travel once, through the process group's object all-gather."""
+    previous publish). Handles travel once, through the process group's object all-gather.
+
+    Failure mode (the NCCL transport has none of its own: its watchdog owns that): a flag wait is bounded
+    (QSAE_PEER_TIMEOUT_MS, default 20 s) and raises a device flag on expiry instead of hanging the GPU. The flag is
+    copied to pinned host memory after every forward (asynchronously) and examined at the start of the next one and
+    wherever the forward synchronises anyway: `check()` raises RuntimeError and marks the exchange broken, and the
+    module drops it (results of the forward that timed out are invalid and the sequence numbers of the ranks no longer
+    agree, so the exchange is rebuilt -- collectively -- on the next forward)."""
 
     FLAG_BYTES = 1024
 
@@ -172,6 +179,10 @@ class PeerExchange:
         self.part_bases = [torch.tensor([p + self.part_off + s * self.part_slot for p in self.peer_ptrs], **i64) for s in (0, 1)]
         self.signal_targets = [torch.tensor([p + (ph * world + rank) * 4 for p in self.peer_ptrs], **i64) for ph in (0, 1)]
         self.timed_out = torch.zeros((1,), dtype=torch.int32, device=device)
+        self._host_flag = torch.zeros((1,), dtype=torch.int32).pin_memory()
+        self._flag_event = None
+        self.broken = False
+        self._dist, self._group = dist, group
         self.seq = [0, 0]          # exchanges done per phase (identical on every rank)
         dist.barrier(group=group)  # every peer has mapped every buffer before the first signal is sent
 
@@ -203,16 +214,40 @@ class PeerExchange:
         slot = self._exchange(1)
         return _lib.reduce_partials_peer(self.part_bases[slot], row_begin, rows, self.D)
 
-    def check(self) -> None:
-        if int(self.timed_out.item()) != 0:
-            raise RuntimeError("peer exchange: a flag wait timed out (a peer did not publish its data)")
+    def _raise(self):
+        self.broken = True
+        raise RuntimeError("peer exchange: a flag wait timed out (a peer did not publish its data within "
+                           "QSAE_PEER_TIMEOUT_MS); the results of that forward are invalid")
 
-    def close(self) -> None:
+    def check(self) -> None:
+        """Synchronous check (one tiny device -> host read)."""
+        if int(self.timed_out.item()) != 0:
+            self._raise()
+
+    def note_forward_done(self) -> None:
+        """Queue an asynchronous copy of the timeout flag behind the forward that was just enqueued."""
+        self._host_flag.copy_(self.timed_out, non_blocking=True)
+        self._flag_event = torch.cuda.Event()
+        self._flag_event.record()
+
+    def check_previous(self) -> None:
+        """No host synchronisation: looks at the flag copy of the previous forward if it has landed."""
+        if self._flag_event is not None and self._flag_event.query():
+            self._flag_event = None
+            if int(self._host_flag[0]) != 0:
+                self._raise()
+
+    def close(self, collective: bool = True) -> None:
+        """Unmap the peers' buffers, wait until every peer has unmapped ours (freeing memory that a peer still has
+        mapped is undefined behaviour), then free. collective=False skips the barrier (teardown after a failure,
+        when the peers may be gone)."""
         for g, p in enumerate(self.peer_ptrs):
             if g != self.rank:
                 _lib.peer_close(p)
-        _lib.peer_free(self.ptr)
         self.peer_ptrs = []
+        if collective:
+            self._dist.barrier(group=self._group)
+        _lib.peer_free(self.ptr)
 
 
 class DictionaryShardedBinarySAE(nn.Module):
@@ -251,6 +286,7 @@ class DictionaryShardedBinarySAE(nn.Module):
         self.polar_tol = 1e-6
         self.trim_min_k = 256                # k below this: every shard sends its full top-k (tiny anyway)
         self.last_exchange = None            # "truncated" / "full": which candidate exchange produced the last forward
+        self.last_k_send = None              # candidates per shard and row of the last (successful) exchange round
         self.transport = "nccl"              # "nccl" (torch.distributed collectives) | "p2p" (CUDA IPC peer memory)
         self._peer = None
         self._pol_cache = None
@@ -324,6 +360,7 @@ class DictionaryShardedBinarySAE(nn.Module):
                 vals = None                                                   # some shard ran out of candidates
             else:
                 self.last_exchange = "truncated"
+        self.last_k_send = k_snd if vals is not None else k_loc
         if vals is None:
             cand = self.ops.local_candidates(x, k_loc)                        # [B, k_loc, 2]
             cand_all = self._all_gather(cand)                                 # [G, B, k_loc, 2]
@@ -340,7 +377,16 @@ class DictionaryShardedBinarySAE(nn.Module):
         return latents, rows, self.polarize_loss(x)
 
     # ---- the same forward with both exchanges over peer memory --------------------------------------------------
+    def local_candidates(self, x: torch.Tensor) -> torch.Tensor:
+        """The rank-local stage alone (fused encoder sweep + top-k over this shard, candidates of the first exchange
+        round): what bench.py times to split a step into local compute and exchange + merge + decode."""
+        k = self.top_k()
+        return self.ops.local_candidates(x.contiguous().float(), self.plan.k_send(k, self.trim_min_k))
+
     def _peer_exchange(self, rows: int, k: int) -> PeerExchange:
+        if self._peer is not None and self._peer.broken:
+            self._peer.close(collective=False)
+            self._peer = None
         if self._peer is None or not self._peer.fits(rows, k, self.input_dim):
             if self._peer is not None:
                 torch.cuda.synchronize()
@@ -356,6 +402,7 @@ class DictionaryShardedBinarySAE(nn.Module):
         B = x.shape[0]
         k_loc, k_snd = plan.k_local(k), plan.k_send(k, self.trim_min_k)
         px = self._peer_exchange(B, k_loc)
+        px.check_previous()                    # a flag wait of the previous forward timed out: raise before going on
         lin = self.encoder[0]
         w32 = lin.weight.detach().contiguous()
 
@@ -373,6 +420,8 @@ class DictionaryShardedBinarySAE(nn.Module):
                 vals = None
             else:
                 self.last_exchange = "truncated"
+            px.check()                         # the forward has synchronised anyway: a stale merge must not be used
+        self.last_k_send = k_snd if vals is not None else k_loc
         if vals is None:
             bases = px.publish_candidates(*local_topk(k_loc))
             vals, idx = _lib.merge_candidates_peer(bases, B, k_loc, plan.shard_latents, k)
@@ -389,5 +438,6 @@ class DictionaryShardedBinarySAE(nn.Module):
             if rows.shape[0] != per:
                 rows = torch.cat([rows, rows.new_zeros((per - rows.shape[0], rows.shape[1]))], 0)
             rows = self._all_gather(rows).reshape(-1, rows.shape[1])[:B]
+        px.note_forward_done()
         latents = SparseLatents(vals, idx, (B, self.hidden_dim))
         return latents, rows, self.polarize_loss(x)

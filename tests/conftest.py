@@ -27,3 +27,27 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+@pytest.fixture
+def tuning():
+    """Set QSAE_* tuning switches for one test: tuning(NAME, value) sets the variable and makes the library
+    re-read its switches (they are cached, never read on a launch path); everything is restored afterwards."""
+    from quantizedsae_b200 import _lib as L
+
+    saved = {}
+
+    def set_(name, value):
+        if name not in saved:
+            saved[name] = os.environ.get(name)
+        os.environ[name] = str(value)
+        L.check(L.load().qsae_reload_tuning())
+
+    yield set_
+    for name, old in saved.items():
+        if old is None:
+            os.environ.pop(name, None)
+        else:
+            os.environ[name] = old
+    if saved:
+        L.check(L.load().qsae_reload_tuning())

@@ -43,14 +43,14 @@ def test_analysis_matches_reference(cuda_device, golden_dir, name):
     sae = build_wrapper(kind, cfg, inp, cuda_device)
     loader = [torch.from_numpy(b) for b in AC.batches(inp["x"])]
     tok = torch.from_numpy(g["token_ids"])
-    launches0 = L.launch_count
+    launches0 = L.launch_count()
     st = AN.compute_activation_stats(sae, loader, token_ids=tok, tokens_per_context=AC.TOKENS_PER_CONTEXT, device="cuda")
     res = {"mse": AN.compute_reconstruction_error(sae, loader, device="cuda"),
            "mse_by_level": AN.compute_reconstruction_error_by_level(sae, loader, device="cuda").numpy(),
            "l0_by_level": AN.compute_l0_by_level(sae, loader, device="cuda").numpy(),
            "activation_counts": st["activation_counts"].numpy(), "coactivation": st["coactivation"].numpy(),
            "tokens_per_feature": st["tokens_per_feature"]}
-    assert L.launch_count > launches0
+    assert L.launch_count() > launches0
     AC.check_against_golden(res, g, cfg["H"], mse_rtol=2e-5)
     # the reference-shaped dense mask, and the one-pass variant
     mask = torch.cat([AN._activation_mask(sae, b) for b in loader]).numpy()

@@ -429,7 +429,7 @@ def test_host_pipeline_entry(cuda_device):
 
 
 def test_native_library_was_used(cuda_device):
-    assert L._lib is not None and L.launch_count > 0
+    assert L._lib is not None and L.launch_count() > 0
 
 
 # ------------------------------------------------------------------------------------------
@@ -518,7 +518,32 @@ def test_prior_prep_kernel_vs_numpy(cuda_device, B, D, n_sample, m, act):
     assert np.all(np.abs(got - ref) <= 2e-6 * np.maximum(1.0, np.abs(ref))), float(np.abs(got - ref).max())
 
 
-def test_prior_prep_path_is_bit_identical_to_the_separate_kernels(cuda_device, monkeypatch):
+@pytest.mark.parametrize("B,H,D,k,exact", [(4096, 32768, 512, 32, False), (1000, 32768, 512, 65, False), (2048, 16384, 512, 32, True),
+                                           (333, 32768, 512, 32, False), (700, 16384, 256, 100, False)])
+def test_range_schedule_is_bit_identical_to_the_grid_schedule(cuda_device, tuning, B, H, D, k, exact):
+    """Small batches sweep with one CTA per SM over contiguous tile ranges (pieces of up to three row blocks per CTA,
+    x tile reloaded in between, per-piece survivor lists); the (split, row block) grid must give the same bits, and
+    both must match the oracle."""
+    x, W, b = _enc_case(B, H, D, 31 + B, bf16=not exact)
+    dx, dW, db = T(x, cuda_device), T(W, cuda_device), T(b, cuda_device)
+    wb = L.cast_bf16(dW)
+    sample = L.prepare_sample(wb, db)
+    packed = torch.randint(0, 256, (H, D // 2), dtype=torch.uint8, device=cuda_device)
+    bd = torch.randn(D, device=cuda_device)
+    outs = []
+    for flag in ("1", "0"):
+        tuning("QSAE_ENCODE_RANGE", flag)
+        outs.append(L.bsae_forward(dx, wb, dW if exact else None, db, k, packed, 4, 0.5, bd, exact=exact, want_flags=True,
+                                   sample=sample))
+    for a, c in zip(outs[0], outs[1]):
+        assert torch.equal(a, c)
+    rows = np.random.default_rng(0).choice(B, min(B, 256), replace=False)
+    z = O.encode_pre(x[rows], W, b)
+    assert_topk_matches(outs[0][0].cpu().numpy()[rows], outs[0][1].cpu().numpy()[rows], z, k)
+    assert int((outs[0][2] != 0).sum()) == 0
+
+
+def test_prior_prep_path_is_bit_identical_to_the_separate_kernels(cuda_device, tuning):
     B, H, D, k = 700, 32768, 512, 32
     x, W, b = _enc_case(B, H, D, 4242)
     dx, dW, db = T(x, cuda_device), T(W, cuda_device), T(b, cuda_device)
@@ -528,7 +553,7 @@ def test_prior_prep_path_is_bit_identical_to_the_separate_kernels(cuda_device, m
     bd = torch.randn(D, device=cuda_device)
     outs = []
     for flag in ("1", "0"):
-        monkeypatch.setenv("QSAE_PRIOR_PREP", flag)
+        tuning("QSAE_PRIOR_PREP", flag)
         outs.append(L.bsae_forward(dx, wb, None, db, k, packed, 4, 0.5, bd, sample=sample))
     for a, c in zip(outs[0], outs[1]):
         if a is not None:
@@ -992,7 +1017,7 @@ def test_qsae_untrained_model_falls_back_to_dense(cuda_device):
 
 
 @pytest.mark.parametrize("mcast", ["1", "2"])
-def test_cluster_variants_are_bit_identical(cuda_device, monkeypatch, mcast):
+def test_cluster_variants_are_bit_identical(cuda_device, tuning, mcast):
     """The cluster-of-two variants of the encoder -- 1: TMA multicast of the W stages, 2: cta_group::2
     MMA pairs -- with the sparse and the dense epilogue must give the same bits as the single-CTA
     variant; odd numbers of row blocks exercise the padding CTA."""
@@ -1000,13 +1025,13 @@ def test_cluster_variants_are_bit_identical(cuda_device, monkeypatch, mcast):
     x, W, b = _enc_case(B, H, D, 55)
     dx, dW, db = T(x, cuda_device), T(W, cuda_device), T(b, cuda_device)
     wb = L.cast_bf16(dW)
-    monkeypatch.setenv("QSAE_ENCODE_CLUSTER", mcast)
+    tuning("QSAE_ENCODE_CLUSTER", mcast)
     vals, idx, _ = L.encode_topk(dx, wb, None, db, k, sample=L.prepare_sample(wb, db))
     assert_topk_matches(vals.cpu().numpy(), idx.cpu().numpy(), O.encode_pre(x, W, b), k)
     wd = (0.4824 * np.random.default_rng(1).standard_normal((D, H))).astype(np.float32)
     t_bf16, _ = L.pack_ternary(T(wd, cuda_device))
     h, recon = L.tsae_forward(dx, (wb,), db, t_bf16, exact=False)
-    monkeypatch.setenv("QSAE_ENCODE_CLUSTER", "0")
+    tuning("QSAE_ENCODE_CLUSTER", "0")
     v0, i0, _ = L.encode_topk(dx, wb, None, db, k, sample=L.prepare_sample(wb, db))
     h0, r0 = L.tsae_forward(dx, (wb,), db, t_bf16, exact=False)
     assert torch.equal(vals, v0) and torch.equal(idx, i0) and torch.equal(h, h0) and torch.equal(recon, r0)
@@ -1059,16 +1084,16 @@ def test_inference_wrapper_on_gpu(cuda_device, golden_dir, tmp_path):
 
 
 @pytest.mark.parametrize("B,K,N", [(300, 4096, 512), (129, 1000, 64), (1024, 8192, 384)])
-def test_decoder_gemm_pair_variant_is_bit_identical(cuda_device, monkeypatch, B, K, N):
+def test_decoder_gemm_pair_variant_is_bit_identical(cuda_device, tuning, B, K, N):
     """cta_group::2 pairs (default for more than one row block) against the single-CTA kernel."""
     rng = np.random.default_rng(B)
     a = np.maximum(rng.standard_normal((B, K)), 0).astype(np.float32)
     t = O.ternarize((0.4824 * rng.standard_normal((N, K))).astype(np.float32))
     hi, lo = L.split_bf16(T(a, cuda_device))
     tb = T(t.astype(np.float32), cuda_device).bfloat16().contiguous()
-    monkeypatch.setenv("QSAE_DECODE_PAIR", "1")
+    tuning("QSAE_DECODE_PAIR", "1")
     one, two = L.decode_dense(hi, None, tb), L.decode_dense(hi, lo, tb)
-    monkeypatch.setenv("QSAE_DECODE_PAIR", "0")
+    tuning("QSAE_DECODE_PAIR", "0")
     assert torch.equal(one, L.decode_dense(hi, None, tb)) and torch.equal(two, L.decode_dense(hi, lo, tb))
     assert_recon_close(two.cpu().numpy(), (a.astype(np.float64) @ t.T.astype(np.float64)).astype(np.float32))
 
