@@ -21,6 +21,17 @@
 
 namespace qsae {
 
+// 8-byte asynchronous copy global -> shared (LDGSTS): the gather of a whole batch of dictionary rows is issued
+// before any of it is consumed
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 template <int WPL, bool FULL, bool WIDE = false>
 struct Int4RowDecoder {
   using acc_t = typename std::conditional<WIDE, long long, int>::type;
@@ -100,6 +111,46 @@ struct Int4RowDecoder {
     }
   }
 
+  // The same accumulation from dictionary rows that were staged in shared memory first (all of a batch's gathers
+  // in flight at once instead of four at a time): row e of the batch at rows + e * 32 * WPL words; lane `first + e`
+  // holds the batch's entry e (my_v; mine == false: the entry contributes nothing and its staged row is ignored).
+  __device__ __forceinline__ void add_staged(float my_v, bool mine, int first, int m, const uint32_t* rows, int lane) {
+    const unsigned full = 0xffffffffu;
+    const int my_f = mine ? __float2int_rn(my_v * to_fixed) : 0;
+#pragma unroll 4
+    for (int e = 0; e < m; ++e) {
+      const int vf = __shfl_sync(full, my_f, first + e);
+      vsum += vf;
+      uint32_t word[WPL];
+      const uint32_t* r = rows + (e * 32 + lane) * WPL;
+      if constexpr (WPL == 1) {
+        word[0] = r[0];
+      } else if constexpr (WPL == 2) {
+        const uint2 t = *reinterpret_cast<const uint2*>(r);
+        word[0] = t.x; word[1] = t.y;
+      } else {
+        const uint4 t = *reinterpret_cast<const uint4*>(r);
+        word[0] = t.x; word[1] = t.y; word[2] = t.z; word[3] = t.w;
+      }
+#pragma unroll
+      for (int c = 0; c < WPL; ++c) {
+        const uint32_t bits = word[c] ^ 0x88888888u;
+        const uint32_t lo = bits & 0x0F0F0F0Fu;
+        const uint32_t hi = (bits >> 4) & 0x0F0F0F0Fu;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if constexpr (WIDE) {
+            acc[c][2 * q] += static_cast<long long>(static_cast<int>(__byte_perm(lo, 0u, 0x4440u + q))) * vf;
+            acc[c][2 * q + 1] += static_cast<long long>(static_cast<int>(__byte_perm(hi, 0u, 0x4440u + q))) * vf;
+          } else {
+            acc[c][2 * q] += static_cast<int>(__byte_perm(lo, 0u, 0x4440u + q)) * vf;
+            acc[c][2 * q + 1] += static_cast<int>(__byte_perm(hi, 0u, 0x4440u + q)) * vf;
+          }
+        }
+      }
+    }
+  }
+
   __device__ __forceinline__ void finish(float scale, const float* __restrict__ bias, float* __restrict__ recon_row,
                                          int D, int lane) const {
     const acc_t corr = 8 * vsum;
@@ -109,11 +160,20 @@ struct Int4RowDecoder {
     for (int c = 0; c < WPL; ++c) {
       const int d = (w0 + c) * 8;
       if (FULL || d < D) {
-        float o[8];
+        float o[8], bv[8];
+        if (bias != nullptr) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + d));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + d + 4));
+          bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
+          bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) bv[q] = 0.f;
+        }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float sum = static_cast<float>(acc[c][q] - corr) * from_fixed;
-          o[q] = bad ? qnan : (scale * sum + (bias ? __ldg(bias + d + q) : 0.f));
+          o[q] = bad ? qnan : (scale * sum + bv[q]);
         }
         float4* dst = reinterpret_cast<float4*>(recon_row + d);
         dst[0] = make_float4(o[0], o[1], o[2], o[3]);

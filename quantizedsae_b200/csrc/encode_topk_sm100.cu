@@ -920,7 +920,7 @@ __host__ __device__ inline PrepSmem prep_smem_layout(int k_chunks) {
   L.b_off = k_chunks * kABytesPerChunk;
   L.exch_off = L.b_off + kPrepStages * kBBytesPerStage;
   L.bar_off = L.exch_off + ((BM * kPrepPitch * 4 + 15) / 16) * 16;
-  L.tmem_ptr_off = L.bar_off + 8 * (1 + 2 * kPrepStages + 4);
+  L.tmem_ptr_off = L.bar_off + 8 * (k_chunks + 2 * kPrepStages + 4);
   L.total = L.tmem_ptr_off + 16;
   return L;
 }
@@ -934,8 +934,8 @@ prior_prep_kernel(const __grid_constant__ CUtensorMap tmap_w, PrepLaunch p) {
   uint8_t* b_smem = smem + L.b_off;
   float* exch = reinterpret_cast<float*>(smem + L.exch_off);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
-  uint64_t* a_full = bars;
-  uint64_t* full = bars + 1;
+  uint64_t* a_full = bars;                            // one per 64-column chunk of x: the MMAs start on chunk 0
+  uint64_t* full = bars + K_CHUNKS;                   // while the later chunks are still being converted
   uint64_t* empty = full + kPrepStages;
   uint64_t* tmem_full = empty + kPrepStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -955,7 +955,7 @@ prior_prep_kernel(const __grid_constant__ CUtensorMap tmap_w, PrepLaunch p) {
       printf("qsae: dynamic shared memory is not 1024-byte aligned\n");
       __trap();
     }
-    mbar_init(a_full, 12);                              // one arrival per converting warp
+    for (int kc = 0; kc < K_CHUNKS; ++kc) mbar_init(&a_full[kc], 12);   // one arrival per converting warp
     for (int s = 0; s < kPrepStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
     fence_mbar_init();
@@ -983,17 +983,21 @@ prior_prep_kernel(const __grid_constant__ CUtensorMap tmap_w, PrepLaunch p) {
     }
   }
   {
-    constexpr int kUnitsPerRow = K_CHUNKS * 8;
-    constexpr int kUnits = BM * kUnitsPerRow;
+    // chunk-major order: unit u = (chunk u / 1024, row (u % 1024) / 8, 16-byte unit u % 8), so that the first chunks
+    // of the operand are complete (and their barrier arrives) while the later ones are still in flight
+    constexpr int kUnitsPerChunk = BM * 8;
+    constexpr int kUnits = K_CHUNKS * kUnitsPerChunk;
     const bool write_global = rank == 0u;
     constexpr int BATCH = 8;
+    constexpr int kPerIter = 384 * BATCH;              // 3 chunks per iteration
+    static_assert(kPerIter % kUnitsPerChunk == 0, "an iteration must cover whole chunks");
 #pragma unroll 1
-    for (int u0 = threadIdx.x; u0 < kUnits; u0 += 384 * BATCH) {
+    for (int u0 = threadIdx.x; u0 < kUnits; u0 += kPerIter) {
       float4 lo[BATCH], hi[BATCH];
 #pragma unroll
       for (int i = 0; i < BATCH; ++i) {
         const int u = u0 + i * 384;
-        const int r = u / kUnitsPerRow, c8 = (u - r * kUnitsPerRow) * 8;
+        const int kc = u / kUnitsPerChunk, r = (u % kUnitsPerChunk) >> 3, c8 = kc * BK + (u & 7) * 8;
         lo[i] = hi[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (u < kUnits && m0 + r < p.B && c8 < p.D) {
           const float4* src = reinterpret_cast<const float4*>(p.x_f32 + static_cast<size_t>(m0 + r) * p.D + c8);
@@ -1005,18 +1009,22 @@ prior_prep_kernel(const __grid_constant__ CUtensorMap tmap_w, PrepLaunch p) {
       for (int i = 0; i < BATCH; ++i) {
         const int u = u0 + i * 384;
         if (u >= kUnits) continue;
-        const int r = u / kUnitsPerRow, cu = u - r * kUnitsPerRow;
+        const int kc = u / kUnitsPerChunk, r = (u % kUnitsPerChunk) >> 3, j = u & 7;
         const uint32_t w0 = pack_bf16x2(lo[i].x, lo[i].y), w1 = pack_bf16x2(lo[i].z, lo[i].w);
         const uint32_t w2 = pack_bf16x2(hi[i].x, hi[i].y), w3 = pack_bf16x2(hi[i].z, hi[i].w);
-        const int kc = cu >> 3, j = cu & 7;
         st_shared_v4(smem_u32(a_smem) + kc * kABytesPerChunk + r * 128 + ((j ^ (r & 7)) << 4), w0, w1, w2, w3);
-        if (write_global && m0 + r < p.B && cu * 8 < p.D)
-          *reinterpret_cast<uint4*>(p.x_bf16 + static_cast<size_t>(m0 + r) * p.D + cu * 8) = make_uint4(w0, w1, w2, w3);
+        const int c8 = kc * BK + j * 8;
+        if (write_global && m0 + r < p.B && c8 < p.D)
+          *reinterpret_cast<uint4*>(p.x_bf16 + static_cast<size_t>(m0 + r) * p.D + c8) = make_uint4(w0, w1, w2, w3);
+      }
+      fence_proxy_async_smem();     // generic-proxy stores -> visible to the tensor-core (async proxy) reads
+      __syncwarp();
+      if (lane == 0) {
+        const int c_begin = (u0 - static_cast<int>(threadIdx.x)) / kUnitsPerChunk;
+        const int c_end = min(K_CHUNKS, c_begin + kPerIter / kUnitsPerChunk);
+        for (int kc = c_begin; kc < c_end; ++kc) mbar_arrive(&a_full[kc]);
       }
     }
-    fence_proxy_async_smem();     // generic-proxy stores -> visible to the tensor-core (async proxy) reads
-    __syncwarp();
-    if (lane == 0) mbar_arrive(a_full);
   }
 
   if (warp == 0) {
@@ -1043,8 +1051,6 @@ prior_prep_kernel(const __grid_constant__ CUtensorMap tmap_w, PrepLaunch p) {
       constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
       const uint64_t a_desc0 = umma_desc_kmajor_sw128(smem_u32(a_smem));
       const uint64_t b_desc0 = umma_desc_kmajor_sw128(smem_u32(b_smem));
-      mbar_wait(a_full, 0);
-      tc_fence_after();
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < n_my_tiles; ++t) {
@@ -1054,6 +1060,7 @@ prior_prep_kernel(const __grid_constant__ CUtensorMap tmap_w, PrepLaunch p) {
         const uint32_t d_tmem = tmem_base + acc * BN;
 #pragma unroll 1
         for (int kc = 0; kc < K_CHUNKS; ++kc) {
+          if (t == 0) mbar_wait(&a_full[kc], 0);     // this chunk of the x operand has been converted
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((kc * kABytesPerChunk) >> 4);
@@ -1140,26 +1147,17 @@ prior_prep_kernel(const __grid_constant__ CUtensorMap tmap_w, PrepLaunch p) {
         const uint32_t addr = smem_u32(exch + r * kPrepPitch + (i & 1) * 32 + lane);
         key[i] = float_to_key(ld_dsmem_f32(addr, static_cast<uint32_t>(i >> 1)));
       }
-      // m-th largest of the 32 NV keys: bisection from the first bit in which they differ
-      uint32_t a = 0xFFFFFFFFu, o = 0u;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) { a &= key[i]; o |= key[i]; }
-      a = __reduce_and_sync(fullmask, a);
-      o = __reduce_or_sync(fullmask, o);
-      uint32_t T = a;
-      const uint32_t diff = a ^ o;
-      if (diff != 0u) {
-        const int topbit = 31 - __clz(diff);
-        T = a & ~((2u << topbit) - 1u);
+      // m-th largest of the 32 NV keys: m rounds of "take the maximum, retire every key equal to it". Equal keys
+      // retire together, so with ties the result is at most the true m-th largest: still a valid lower bound.
+      uint32_t T = 0u;
 #pragma unroll 1
-        for (int bit = topbit; bit >= 0; --bit) {
-          const uint32_t probe = T | (1u << bit);
-          int c = 0;
+      for (int round = 0; round < p.m; ++round) {
+        uint32_t mx = key[0];
 #pragma unroll
-          for (int i = 0; i < NV; ++i) c += (key[i] >= probe) ? 1 : 0;
-          c = __reduce_add_sync(fullmask, c);
-          if (c >= p.m) T = probe;
-        }
+        for (int i = 1; i < NV; ++i) mx = max(mx, key[i]);
+        T = __reduce_max_sync(fullmask, mx);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) key[i] = (key[i] == T) ? 0u : key[i];
       }
       if (lane == 0) p.prior[row] = key_to_float(T);
     }

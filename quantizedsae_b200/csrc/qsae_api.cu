@@ -639,7 +639,7 @@ int encode_topk_impl(const float* x_f32, const uint16_t* w_bf16, const float* w_
   // for ~4 % of the rows, more than the first tier). When the caller decodes with the packed int4 dictionary the
   // warp that has just sorted a row also decodes it.
   if (fd != nullptr && D == 512 && k <= 128 && (reinterpret_cast<uintptr_t>(fd->packed) & 15) == 0 &&
-      (reinterpret_cast<uintptr_t>(fd->recon) & 15) == 0) {
+      ((reinterpret_cast<uintptr_t>(fd->recon) | reinterpret_cast<uintptr_t>(fd->bias)) & 15) == 0) {
     sl.dec_kind = 1; sl.dec_packed = fd->packed; sl.dec_scale = fd->scale; sl.dec_bias = fd->bias; sl.dec_recon = fd->recon;
     fd->done = true;
   }
@@ -1184,6 +1184,8 @@ int qsae_decode_int4(const float* vals, const int32_t* idx, int B, int k, const 
                      int D, float scale, const float* bias, float* recon, void* stream) {
   int rc = check_decode("decode_int4", vals, idx, packed, recon, B, k, H, D, 8);
   if (rc != QSAE_OK || B == 0) return rc;
+  if ((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(recon)) & 15)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "decode_int4: bias and recon must be 16-byte aligned");
   return launch_status("decode_int4", decode_int4_launch(vals, idx, B, k, packed, H, D, scale, bias, recon, 0, S(stream)));
 }
 
@@ -1341,6 +1343,8 @@ int qsae_decode_int4_range(const float* vals, const int32_t* idx, int B, int k, 
                            void* stream) {
   int rc = check_decode("decode_int4_range", vals, idx, packed_shard, recon, B, k, shard_latents, D, 8);
   if (rc != QSAE_OK || B == 0) return rc;
+  if ((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(recon)) & 15)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "decode_int4_range: bias and recon must be 16-byte aligned");
   return launch_status("decode_int4", decode_int4_launch(vals, idx, B, k, packed_shard, shard_latents, D, scale, bias, recon,
                                                          idx_begin, S(stream), true));
 }

@@ -574,8 +574,9 @@ __device__ __forceinline__ void warp_bitonic_desc(K (&k)[P], int lane) {
 }
 
 template <int P>
-__device__ __forceinline__ void sort_and_emit(const SelectLaunch& p, int row, const uint64_t* sel, int out, int n,
+__device__ __forceinline__ void sort_and_emit(const SelectLaunch& p, int row, uint64_t* stage, int stage_rows, int out, int n,
                                               int k_sel, float worst_bf16, float max_dev, int lane) {
+  const uint64_t* sel = stage;
   uint64_t k[P];
 #pragma unroll
   for (int j = 0; j < P; ++j) k[j] = sel[j * 32 + lane];
@@ -621,6 +622,9 @@ __device__ __forceinline__ void sort_and_emit(const SelectLaunch& p, int row, co
     bad = __any_sync(full, bad);
     Int4RowDecoder<2, true, false> dec;
     dec.begin(amax, bad, p.k_out);
+    // (Staging the gathered rows through the warp's shared-memory area with cp.async, a whole batch in flight at
+    // once, was measured and is slower: 41.5 vs 38.9 us for the stage at B = 4096 -- LDGSTS issues at 8 cycles per
+    // instruction and the kernel is not bound by the latency of these L2-resident rows.)
 #pragma unroll
     for (int j = 0; j < P; ++j) {
       if (j * 32 < p.k_out) {
@@ -658,14 +662,34 @@ __device__ __forceinline__ void small_row(const SelectLaunch& p, int row, int ks
   const unsigned lt_mask = (1u << lane) - 1u;
   int n = n_all;
   if (n_all <= 32 * R) {
-    // ---- gather (every survivor already passed the row's threshold in the sweep)
+    // ---- gather (every survivor already passed the row's threshold in the sweep). Lists are short (a few dozen
+    //      entries): the first 32 entries of four lists are loaded before any is stored, so a row costs
+    //      nsub / 4 dependent L2 round trips instead of nsub; longer lists finish in a second loop.
+    for (int s0 = 0; s0 < p.nsub; s0 += 4) {
+      uint2 t[4];
+      int cs[4], offs[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int s = min(s0 + q, p.nsub - 1);
+        cs[q] = (s0 + q < p.nsub) ? __shfl_sync(full, my_c, s) : 0;
+        offs[q] = __shfl_sync(full, incl, s) - __shfl_sync(full, my_c, s);
+        t[q] = make_uint2(0u, 0u);
+        if (lane < cs[q]) t[q] = list_ptr(p, row, s)[lane];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t col_add = static_cast<uint32_t>(s0 + q) * static_cast<uint32_t>(p.sub_col_offset);
+        if (lane < cs[q]) stage[offs[q] + lane] = make_sort_key(__uint_as_float(t[q].x), t[q].y + col_add);
+      }
+    }
     for (int s = 0; s < p.nsub; ++s) {
       const int c = __shfl_sync(full, my_c, s);
+      if (c <= 32) continue;
       const int off = __shfl_sync(full, incl, s) - c;
       const uint2* src = list_ptr(p, row, s);
       const uint32_t col_add = static_cast<uint32_t>(s) * static_cast<uint32_t>(p.sub_col_offset);
 #pragma unroll 4
-      for (int e = lane; e < c; e += 32) {
+      for (int e = 32 + lane; e < c; e += 32) {
         const uint2 t = src[e];
         stage[off + e] = make_sort_key(__uint_as_float(t.x), t.y + col_add);
       }
@@ -780,10 +804,11 @@ __device__ __forceinline__ void small_row(const SelectLaunch& p, int row, int ks
   }
 
   // ---- sort in registers and emit (value desc, column asc)
-  if (ksort <= 32) sort_and_emit<1>(p, row, sel, out, n, k_sel, worst_bf16, max_dev, lane);
-  else if (ksort <= 64) sort_and_emit<2>(p, row, sel, out, n, k_sel, worst_bf16, max_dev, lane);
-  else if (ksort <= 128) sort_and_emit<4>(p, row, sel, out, n, k_sel, worst_bf16, max_dev, lane);
-  else sort_and_emit<8>(p, row, sel, out, n, k_sel, worst_bf16, max_dev, lane);
+  constexpr int kStageRows = R;   // 256-byte dictionary rows that fit the warp's 32 R x 8-byte staging area
+  if (ksort <= 32) sort_and_emit<1>(p, row, sel, kStageRows, out, n, k_sel, worst_bf16, max_dev, lane);
+  else if (ksort <= 64) sort_and_emit<2>(p, row, sel, kStageRows, out, n, k_sel, worst_bf16, max_dev, lane);
+  else if (ksort <= 128) sort_and_emit<4>(p, row, sel, kStageRows, out, n, k_sel, worst_bf16, max_dev, lane);
+  else sort_and_emit<8>(p, row, sel, kStageRows, out, n, k_sel, worst_bf16, max_dev, lane);
   __syncwarp();
 }
 
