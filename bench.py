@@ -345,10 +345,12 @@ class Timer:
 
         gs = []
         per_step = 0
+        pool = torch.cuda.graph_pool_handle()
+        cap = torch.cuda.Stream()          # one capture stream: the library's per-(device, stream) workspace is shared
         for i in range(n):
             g = torch.cuda.CUDAGraph()
             c0 = L.launch_count()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, pool=pool, stream=cap):
                 out = fn(i)
             per_step = L.launch_count() - c0
             gs.append((g, out))
@@ -475,7 +477,7 @@ def e2e_bsae(args, T, world, device, B, k, We, be, bd, xs):
     del logits2
     try:
         depth = 4   # steps in flight: step i + 1's H2D copy overlaps step i's kernels and step i - 1's D2H copy
-        hx = [x.cpu().pin_memory() for x in xs[:depth]]
+        hx = [xs[j % len(xs)].cpu().pin_memory() for j in range(depth)]
         hv = [torch.empty((B, k), dtype=torch.float32).pin_memory() for _ in range(depth)]
         hi = [torch.empty((B, k), dtype=torch.int32).pin_memory() for _ in range(depth)]
         hr = [torch.empty((B, D), dtype=torch.float32).pin_memory() for _ in range(depth)]
@@ -526,6 +528,34 @@ def e2e_bsae(args, T, world, device, B, k, We, be, bd, xs):
             res["ms_per_step"] = pipe_s / n * 1e3
             res["api"] = (f"qsae_bsae_submit_host / qsae_bsae_wait_host: {depth} steps in flight (pinned host x in; values, indices, "
                           f"reconstruction to pinned host); every step's H2D and D2H copies are inside the timed region")
+            # opt-in narrow host formats: bf16 x in (exact here: x is bf16-representable), bf16 reconstruction out
+            L.check(lib.qsae_bsae_plan_set_io(plan, 1, 1))
+            hxb = [h.bfloat16().pin_memory() for h in hx]
+            hrb = [torch.empty((B, D), dtype=torch.bfloat16).pin_memory() for _ in range(depth)]
+
+            def submit16(i):
+                j = i % depth
+                wait(j)
+                t = C.c_int(0)
+                L.check(lib.qsae_bsae_submit_host(plan, hxb[j].data_ptr(), B, hv[j].data_ptr(), hi[j].data_ptr(),
+                                                  hrb[j].data_ptr(), C.byref(t)))
+                tickets[j] = t.value
+
+            for i in range(depth):
+                submit16(i)
+            for j in range(depth):
+                wait(j)
+            T.barrier()
+            t0 = time.perf_counter()
+            for i in range(n):
+                submit16(i)
+            for j in range(depth):
+                wait(j)
+            s16 = T.max_over_ranks(time.perf_counter() - t0)
+            res["bf16_io"] = {"value": world * B * n / s16, "ms_per_step": s16 / n * 1e3, "h2d_bytes_per_step": B * D * 2,
+                              "d2h_bytes_per_step": B * k * 8 + B * D * 2,
+                              "note": "qsae_bsae_plan_set_io(x bf16, recon bf16): opt-in, halves the PCIe bytes of x and of the reconstruction"}
+            L.check(lib.qsae_bsae_plan_set_io(plan, 0, 0))
         else:
             res["value"] = res["synchronous"]["value"]
             res["ms_per_step"] = res["synchronous"]["ms_per_step"]
@@ -670,6 +700,10 @@ def bench_qsae(args, T, rank, world, device, peaks, steps, warmup):
     with torch.no_grad():
         m.encoder[0].weight.copy_(m.encoder[0].weight.bfloat16().float())
         m.encoder[0].bias.fill_(-0.543)          # mean total L0 ~ 33.6
+        for w in (m.decoder.weight, m.decoder.weight_mirror):
+            # sigmoid(w) >= 0.5 in fp32 depends on the expf implementation for |w| < ~1e-7 (edge (a)):
+            # keep the synthetic decoder logits away from that band so the in-run oracle check is meaningful
+            w.copy_(torch.where(w.abs() < 1e-6, torch.full_like(w, 1e-6), w))
     m.eval()
     m.exact = False
     for B in (4096, 65536):
@@ -682,7 +716,7 @@ def bench_qsae(args, T, rank, world, device, peaks, steps, warmup):
                      "mean_l0": float(sum(float(g) for g in groups))}
             if B == 4096:
                 rows = np.arange(0, B, B // 16)[:16]
-                lg, res = O.qsae_forward(xs[0][rows].cpu().numpy(), m.encoder[0].weight.detach().cpu().numpy(),
+                lg, res, _act = O.qsae_forward(xs[0][rows].cpu().numpy(), m.encoder[0].weight.detach().cpu().numpy(),
                                          m.encoder[0].bias.detach().cpu().numpy(), m.decoder.weight.detach().cpu().numpy(),
                                          m.decoder.weight_mirror.detach().cpu().numpy(), m.decoder.bias.detach().cpu().numpy(),
                                          n_bits=4, abs_range=4.0)
@@ -723,8 +757,7 @@ def bench_soft_decode(args, T, device, peaks, B=4096, k=65):
     g = torch.Generator(device=device).manual_seed(11)
     rows = torch.randn((H, D), device=device, generator=g)
     vals = torch.randn((B, k), device=device, generator=g)
-    idx = torch.stack([torch.randperm(H, device=device, generator=g)[:k] for _ in range(64)]).to(torch.int32)
-    idx = idx.repeat(B // 64, 1).contiguous()
+    idx = torch.randint(0, H, (B, k), device=device, generator=g, dtype=torch.int32)   # every row its own k dictionary rows
     bd = torch.randn(D, device=device, generator=g)
     ms = T.time(lambda i: L.decode_rows_f32(vals, idx, rows, H, D, 0.5, bd), 20, 3)
     nbytes = B * (k * (D * 4 + 8) + D * 4)

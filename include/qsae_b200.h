@@ -225,7 +225,9 @@ int qsae_matryoshka_workspace_bytes(int B, int H, int D, size_t* bytes);
  * result[i, b, :] = bias + sum_{h active, level(h) <= i} scale[h] * T[h, :]     (cumulative, :121-129)
  * level_count[i]  = number of active latents of level i over the batch (latent_group[i] * B).
  * *overflow is set to 1 when a row had more active latents than the sparse path holds
- * (1024 per sub-stream); the result is then incomplete and the caller must use a dense path. */
+ * (1024 per sub-stream); active latents were then dropped and the caller must use a dense path. So that the flag
+ * may be read lazily (no host synchronisation per forward), every output of such a call -- result, and the residual
+ * of qsae_matryoshka_forward_active -- is NaN: a wrong reconstruction can never be used unnoticed. */
 int qsae_matryoshka_forward(const float* x_f32, const uint16_t* w_bf16,
                             const float* w_f32 /* [H,D] or NULL: exact fp32 activity decisions */,
                             const float* w_norm_max /* device scalar from qsae_max_row_norm; exact only */,
@@ -425,6 +427,22 @@ void qsae_bsae_plan_destroy(qsae_bsae_plan* plan);
 /* x_host [B,D] float32 (pinned for full overlap); outputs: vals/idx [B,k], recon [B,D] on host */
 int qsae_bsae_forward_host(qsae_bsae_plan* plan, const float* x_host, int B, float* vals_host,
                            int32_t* idx_host, float* recon_host);
+
+/* The same forward as a stream of batches: submit enqueues the H2D copies, kernels and D2H copies of one batch and
+ * returns at once with a ticket; wait blocks until that batch's outputs are in host memory. Several batches may be
+ * in flight (up to QSAE_MAX_PENDING tickets; submit fails with QSAE_ERR_INVALID_ARGUMENT when all are taken), so the
+ * copy-in of batch i + 1 overlaps the kernels of batch i and the copy-out of batch i - 1. Host buffers must stay
+ * valid (and should be pinned) until the ticket has been waited for. Tickets complete in submission order. */
+#define QSAE_MAX_PENDING 8
+int qsae_bsae_submit_host(qsae_bsae_plan* plan, const void* x_host, int B, float* vals_host, int32_t* idx_host,
+                          void* recon_host, int* ticket);
+int qsae_bsae_wait_host(qsae_bsae_plan* plan, int ticket);
+
+/* Host-side formats of the plan's calls (both entry points), to cut PCIe bytes when the caller can accept it:
+ * x_is_bf16 != 0: x_host holds bfloat16 (2 bytes per element; exact for bf16-representable activations);
+ * recon_mode 0: float32 reconstruction (default), 1: bfloat16 (rounded to nearest), 2: none (recon_host ignored).
+ * Values / indices are always float32 / int32. */
+int qsae_bsae_plan_set_io(qsae_bsae_plan* plan, int x_is_bf16, int recon_mode);
 
 #ifdef __cplusplus
 }

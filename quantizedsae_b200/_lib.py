@@ -87,6 +87,9 @@ SYMBOLS = {
     "qsae_bsae_plan_create": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _i, C.POINTER(_vp)]),
     "qsae_bsae_plan_destroy": (None, [_vp]),
     "qsae_bsae_forward_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "qsae_bsae_submit_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp, C.POINTER(_i)]),
+    "qsae_bsae_wait_host": (_i, [_vp, _i]),
+    "qsae_bsae_plan_set_io": (_i, [_vp, _i, _i]),
 }
 
 

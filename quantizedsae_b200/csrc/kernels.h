@@ -198,6 +198,8 @@ const char* dense_candidates_launch(const float* z, int R, int H, int k, void* c
 
 // pack.cu
 const char* cast_bf16_launch(const float* src, uint16_t* dst, size_t n, cudaStream_t stream);
+// bf16 -> float32 (exact)
+const char* upcast_bf16_launch(const uint16_t* src, float* dst, size_t n, cudaStream_t stream);
 const char* pack_bitplanes_launch(const float* logits, int H, int D, int n_bits, uint8_t* packed,
                                   double* stats, cudaStream_t stream);
 const char* dequant_soft_launch(const float* logits, int H, int D, int n_bits, float* rows,
@@ -237,7 +239,8 @@ const char* decode_matryoshka_launch(const void* cand, const int* cand_cnt, int 
                                      unsigned long long* level_count, const float* x_f32, const float* w_f32,
                                      const float* b_enc, float thr_value, int exact, void* scratch, int num_sms,
                                      cudaStream_t stream, int32_t* active_idx = nullptr, int active_cap = 0,
-                                     int* active_cnt = nullptr, const float* resid_in = nullptr, float* resid_out = nullptr);
+                                     int* active_cnt = nullptr, const float* resid_in = nullptr, float* resid_out = nullptr,
+                                     const int* poison_flag = nullptr);
 // scratch of decode_matryoshka_launch (per-warp activity counts before the final sum)
 size_t decode_matryoshka_scratch_bytes(int num_sms);
 // packed 2-bit codes [H, D/16] -> T^T as bf16 [D, H] with entries {-2, 0, +2} (B operand of the dense level GEMMs)

@@ -164,9 +164,13 @@ decode_matryoshka_kernel(const uint2* __restrict__ cand, const int* __restrict__
                          const float* __restrict__ b_enc, float thr_value, int exact,
                          int32_t* __restrict__ active_idx /* [B, active_cap] or null */, int active_cap,
                          int* __restrict__ active_cnt /* [B] */,
-                         const float* __restrict__ resid_in /* [B, D] or null */, float* __restrict__ resid_out /* [B, D] */) {
+                         const float* __restrict__ resid_in /* [B, D] or null */, float* __restrict__ resid_out /* [B, D] */,
+                         const int* __restrict__ poison_flag /* != 0: the sweep overflowed a survivor list */) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned full = 0xffffffffu;
+  // A sweep whose survivor lists overflowed has dropped active latents: every output of this call becomes NaN, so a
+  // caller that reads the overflow flag lazily (no host synchronisation per forward) can never use a wrong result
+  const float poison = (poison_flag != nullptr && *poison_flag != 0) ? __uint_as_float(0x7FC00000u) : 0.f;
   const int words = D >> 4;                 // <= 32: lane `l` owns word l (features 16 l .. 16 l + 15)
   const bool has_word = lane < words;
   unsigned cnt[NL];
@@ -268,7 +272,8 @@ decode_matryoshka_kernel(const uint2* __restrict__ cand, const int* __restrict__
         if (has_word) {   // cumulative output of this level
           float4* dst = reinterpret_cast<float4*>(result + (static_cast<size_t>(l) * B + row) * D + lane * 16);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) dst[q] = make_float4(run[4 * q], run[4 * q + 1], run[4 * q + 2], run[4 * q + 3]);
+          for (int q = 0; q < 4; ++q)
+            dst[q] = make_float4(run[4 * q] + poison, run[4 * q + 1] + poison, run[4 * q + 2] + poison, run[4 * q + 3] + poison);
         }
       }
     }
@@ -281,8 +286,8 @@ decode_matryoshka_kernel(const uint2* __restrict__ cand, const int* __restrict__
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 r = rin[q];
-        rout[q] = make_float4((r.x - run[4 * q]) * 2.f, (r.y - run[4 * q + 1]) * 2.f, (r.z - run[4 * q + 2]) * 2.f,
-                              (r.w - run[4 * q + 3]) * 2.f);
+        rout[q] = make_float4((r.x - run[4 * q]) * 2.f + poison, (r.y - run[4 * q + 1]) * 2.f + poison,
+                              (r.z - run[4 * q + 2]) * 2.f + poison, (r.w - run[4 * q + 3]) * 2.f + poison);
       }
     }
   }
@@ -367,7 +372,7 @@ const char* decode_matryoshka_launch(const void* cand, const int* cand_cnt, int 
                                      unsigned long long* level_count, const float* x_f32, const float* w_f32,
                                      const float* b_enc, float thr_value, int exact, void* scratch, int num_sms,
                                      cudaStream_t stream, int32_t* active_idx, int active_cap, int* active_cnt,
-                                     const float* resid_in, float* resid_out) {
+                                     const float* resid_in, float* resid_out, const int* poison_flag) {
   if (n_levels > 8) return "decode_matryoshka: at most 8 levels (n_bits <= 8)";
   if (D > 512 || (D % 16) != 0) return "decode_matryoshka: D must be a multiple of 16, <= 512";
   int blocks = (B + kMatWarps - 1) / kMatWarps;
@@ -377,7 +382,7 @@ const char* decode_matryoshka_launch(const void* cand, const int* cand_cnt, int 
 #define QSAE_MAT(NL) \
   decode_matryoshka_kernel<NL><<<blocks, kMatWarps * 32, 0, stream>>>(c2, cand_cnt, nsub, cap, B, packed, scale, level_start, \
       n_levels, H, D, bias, result, partial, x_f32, w_f32, b_enc, thr_value, exact, active_idx, active_cap, active_cnt, \
-      resid_in, resid_out)
+      resid_in, resid_out, poison_flag)
   int nl;
   if (n_levels <= 1) { nl = 1; QSAE_MAT(1); }
   else if (n_levels <= 2) { nl = 2; QSAE_MAT(2); }

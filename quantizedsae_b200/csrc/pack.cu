@@ -33,6 +33,18 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, uint16_t* __rest
   }
 }
 
+__global__ void upcast_bf16_kernel(const uint16_t* __restrict__ src, float* __restrict__ dst, size_t n) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t n4 = n / 4;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const uint2 v = reinterpret_cast<const uint2*>(src)[i];
+    reinterpret_cast<float4*>(dst)[i] = make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xFFFF0000u),
+                                                    __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xFFFF0000u));
+  }
+  for (size_t i = n4 * 4 + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = __uint_as_float(static_cast<uint32_t>(src[i]) << 16);
+}
+
 // One thread per output feature (h, d): reads its n_bits logits, emits the integer.
 // Threads of a warp read consecutive features, i.e. a contiguous 32*n_bits*4-byte span.
 template <bool kNibble>
@@ -247,6 +259,11 @@ int grid_for(size_t n, int block, int cap = 148 * 16) {
 
 const char* cast_bf16_launch(const float* src, uint16_t* dst, size_t n, cudaStream_t stream) {
   cast_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, stream>>>(src, dst, n);
+  return cuda_err(cudaGetLastError());
+}
+
+const char* upcast_bf16_launch(const uint16_t* src, float* dst, size_t n, cudaStream_t stream) {
+  upcast_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, stream>>>(src, dst, n);
   return cuda_err(cudaGetLastError());
 }
 

@@ -854,7 +854,7 @@ int qsae_matryoshka_forward_active(const float* x_f32, const uint16_t* w_bf16, c
                                                                      level_count, x_f32, w_f32, b_enc, kActiveThreshold,
                                                                      exact, ws + mp.scratch_off, num_sms(), st, active_idx,
                                                                      active_cap, active_cnt, residual_out ? x_f32 : nullptr,
-                                                                     residual_out));
+                                                                     residual_out, overflow));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1378,16 +1378,25 @@ struct qsae_bsae_plan {
   uint16_t* w_sample;
   float* b_sample;
   int n_sample;
+  int x_is_bf16, recon_mode;      // host formats (qsae_bsae_plan_set_io)
+  int next_slot;                  // chunks go round the slots across calls
   static constexpr int kSlots = 4;
   struct Slot {
     cudaStream_t stream;
     float* x;
+    uint16_t* x16;                // bf16 host input lands here and is widened on the device
     void* ws;
     size_t ws_bytes;
     float* vals;
     int32_t* idx;
     float* recon;
+    uint16_t* recon16;            // bf16 host output
   } slot[kSlots];
+  struct Pending {
+    bool active;
+    bool used[kSlots];
+    cudaEvent_t done[kSlots];     // recorded on a slot's stream after the call's last operation there
+  } pending[QSAE_MAX_PENDING];
 };
 
 void qsae_bsae_plan_destroy(qsae_bsae_plan* p) {
@@ -1395,8 +1404,11 @@ void qsae_bsae_plan_destroy(qsae_bsae_plan* p) {
   for (int s = 0; s < qsae_bsae_plan::kSlots; ++s) {
     auto& sl = p->slot[s];
     if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
-    cudaFree(sl.x); cudaFree(sl.ws); cudaFree(sl.vals); cudaFree(sl.idx); cudaFree(sl.recon);
+    cudaFree(sl.x); cudaFree(sl.x16); cudaFree(sl.ws); cudaFree(sl.vals); cudaFree(sl.idx); cudaFree(sl.recon); cudaFree(sl.recon16);
   }
+  for (int t = 0; t < QSAE_MAX_PENDING; ++t)
+    for (int s = 0; s < qsae_bsae_plan::kSlots; ++s)
+      if (p->pending[t].done[s]) cudaEventDestroy(p->pending[t].done[s]);
   cudaFree(p->w_bf16);
   cudaFree(p->packed);
   cudaFree(p->w_sample);
@@ -1431,11 +1443,16 @@ int qsae_bsae_plan_create(const float* w_enc, const float* b_enc, const float* l
     sl.ws_bytes = ws_bytes;
     e = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&sl.x, static_cast<size_t>(max_chunk_rows) * D * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&sl.x16, static_cast<size_t>(max_chunk_rows) * D * 2);
     if (e == cudaSuccess) e = cudaMalloc(&sl.ws, ws_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&sl.vals, static_cast<size_t>(max_chunk_rows) * k * 4);
     if (e == cudaSuccess) e = cudaMalloc(&sl.idx, static_cast<size_t>(max_chunk_rows) * k * 4);
     if (e == cudaSuccess) e = cudaMalloc(&sl.recon, static_cast<size_t>(max_chunk_rows) * D * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&sl.recon16, static_cast<size_t>(max_chunk_rows) * D * 2);
   }
+  for (int t = 0; t < QSAE_MAX_PENDING && e == cudaSuccess; ++t)
+    for (int s = 0; s < qsae_bsae_plan::kSlots && e == cudaSuccess; ++s)
+      e = cudaEventCreateWithFlags(&p->pending[t].done[s], cudaEventDisableTiming);
   if (e != cudaSuccess) {
     qsae_bsae_plan_destroy(p);
     return fail(QSAE_ERR_CUDA, "plan_create: %s", cudaGetErrorString(e));
@@ -1452,33 +1469,55 @@ int qsae_bsae_plan_create(const float* w_enc, const float* b_enc, const float* l
   return QSAE_OK;
 }
 
-int qsae_bsae_forward_host(qsae_bsae_plan* p, const float* x_host, int B, float* vals_host,
-                           int32_t* idx_host, float* recon_host) {
-  if (!p || !x_host || !vals_host || !idx_host || !recon_host || B < 0)
-    return fail(QSAE_ERR_INVALID_ARGUMENT, "forward_host: bad argument");
+int qsae_bsae_plan_set_io(qsae_bsae_plan* p, int x_is_bf16, int recon_mode) {
+  if (!p || recon_mode < 0 || recon_mode > 2) return fail(QSAE_ERR_INVALID_ARGUMENT, "plan_set_io: bad argument");
+  for (int t = 0; t < QSAE_MAX_PENDING; ++t)
+    if (p->pending[t].active) return fail(QSAE_ERR_INVALID_ARGUMENT, "plan_set_io: batches are still in flight");
+  p->x_is_bf16 = x_is_bf16 != 0;
+  p->recon_mode = recon_mode;
+  return QSAE_OK;
+}
+
+}  // extern "C"
+
+namespace {
+// Enqueue one batch on the plan's slot streams. ramp: the synchronous call starts with small chunks so that the
+// copy-out leg begins early; a stream of batches overlaps across calls instead and uses full chunks.
+int enqueue_batch(qsae_bsae_plan* p, const void* x_host, int B, float* vals_host, int32_t* idx_host, void* recon_host,
+                  bool ramp, bool* used) {
   int rc = QSAE_OK;
   int c = 0;
-  // Chunk schedule: the device -> host copy of the results is the longest leg (B * (8 k + 4 D) bytes over PCIe), and
-  // it cannot start before the first chunk has been copied in and computed. So the first chunks are small
-  // (2048 rows, doubling) to start the output stream early, the rest are as large as the plan allows because
+  // Chunk schedule of the synchronous call: the device -> host copy of the results is the longest leg (B * (8 k + 4 D)
+  // bytes over PCIe), and it cannot start before the first chunk has been copied in and computed. So the first chunks
+  // are small (2048 rows, doubling) to start the output stream early, the rest are as large as the plan allows because
   // the kernels are more efficient on large batches (the compute leg must stay ahead of the copy-out leg).
-  int next_rows = p->chunk < 2048 ? p->chunk : 2048;
-  const bool trace = tuning().debug_pipeline != 0;   // diagnostics: per-chunk event timeline on stderr
+  int next_rows = (!ramp || p->chunk < 2048) ? p->chunk : 2048;
+  const bool trace = ramp && tuning().debug_pipeline != 0;   // diagnostics: per-chunk event timeline on stderr
   constexpr int kTraceMax = 64;
   cudaEvent_t tev[kTraceMax][4];
   int trows[kTraceMax];
   if (trace) {
     for (int i = 0; i < kTraceMax; ++i) for (int j = 0; j < 4; ++j) cudaEventCreate(&tev[i][j]);
   }
+  const size_t x_elem = p->x_is_bf16 ? 2 : 4;
   for (int r0 = 0, rows = 0; r0 < B && rc == QSAE_OK; r0 += rows, ++c) {
-    auto& sl = p->slot[c % qsae_bsae_plan::kSlots];
+    const int si = p->next_slot;
+    p->next_slot = (p->next_slot + 1) % qsae_bsae_plan::kSlots;
+    auto& sl = p->slot[si];
+    used[si] = true;
     rows = (B - r0 < next_rows) ? (B - r0) : next_rows;
     next_rows = (next_rows * 2 < p->chunk) ? next_rows * 2 : p->chunk;
     if (trace && c < kTraceMax) { trows[c] = rows; cudaEventRecord(tev[c][0], sl.stream); }
     cudaStream_t st = sl.stream;  // stream order protects the slot's buffers from its previous use
-    cudaError_t e = cudaMemcpyAsync(sl.x, x_host + static_cast<size_t>(r0) * p->D,
-                                    static_cast<size_t>(rows) * p->D * 4, cudaMemcpyHostToDevice, st);
+    const size_t n_x = static_cast<size_t>(rows) * p->D;
+    cudaError_t e = cudaMemcpyAsync(p->x_is_bf16 ? static_cast<void*>(sl.x16) : static_cast<void*>(sl.x),
+                                    static_cast<const uint8_t*>(x_host) + static_cast<size_t>(r0) * p->D * x_elem, n_x * x_elem,
+                                    cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) { rc = fail(QSAE_ERR_CUDA, "forward_host H2D: %s", cudaGetErrorString(e)); break; }
+    if (p->x_is_bf16) {
+      rc = launch_status("upcast x", upcast_bf16_launch(sl.x16, sl.x, n_x, st));
+      if (rc != QSAE_OK) break;
+    }
     if (trace && c < kTraceMax) cudaEventRecord(tev[c][1], st);
     rc = qsae_bsae_forward(sl.x, p->w_bf16, p->w_f32, p->b_enc, p->w_sample, p->b_sample, p->n_sample, rows, p->H, p->D,
                            p->k, 0, p->packed, p->n_bits, p->qstep, p->dec_bias, sl.vals, sl.idx, nullptr, sl.recon, sl.ws,
@@ -1490,17 +1529,20 @@ int qsae_bsae_forward_host(qsae_bsae_plan* p, const float* x_host, int B, float*
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(idx_host + static_cast<size_t>(r0) * p->k, sl.idx, static_cast<size_t>(rows) * p->k * 4,
                           cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess)
-      e = cudaMemcpyAsync(recon_host + static_cast<size_t>(r0) * p->D, sl.recon, static_cast<size_t>(rows) * p->D * 4,
+    if (e == cudaSuccess && p->recon_mode == 0)
+      e = cudaMemcpyAsync(static_cast<float*>(recon_host) + static_cast<size_t>(r0) * p->D, sl.recon, n_x * 4,
                           cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && p->recon_mode == 1) {
+      rc = launch_status("cast recon", cast_bf16_launch(sl.recon, sl.recon16, n_x, st));
+      if (rc != QSAE_OK) break;
+      e = cudaMemcpyAsync(static_cast<uint16_t*>(recon_host) + static_cast<size_t>(r0) * p->D, sl.recon16, n_x * 2,
+                          cudaMemcpyDeviceToHost, st);
+    }
     if (e != cudaSuccess) rc = fail(QSAE_ERR_CUDA, "forward_host D2H: %s", cudaGetErrorString(e));
     if (trace && c < kTraceMax) cudaEventRecord(tev[c][3], st);
   }
-  for (int s = 0; s < qsae_bsae_plan::kSlots; ++s) {
-    cudaError_t e = cudaStreamSynchronize(p->slot[s].stream);
-    if (e != cudaSuccess && rc == QSAE_OK) rc = fail(QSAE_ERR_CUDA, "forward_host sync: %s", cudaGetErrorString(e));
-  }
   if (trace) {
+    for (int s = 0; s < qsae_bsae_plan::kSlots; ++s) cudaStreamSynchronize(p->slot[s].stream);
     const int nc = c < kTraceMax ? c : kTraceMax;
     for (int i = 0; i < nc && rc == QSAE_OK; ++i) {
       float t[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1510,6 +1552,57 @@ int qsae_bsae_forward_host(qsae_bsae_plan* p, const float* x_host, int B, float*
     }
     for (int i = 0; i < kTraceMax; ++i) for (int j = 0; j < 4; ++j) cudaEventDestroy(tev[i][j]);
   }
+  return rc;
+}
+}  // namespace
+
+extern "C" {
+
+int qsae_bsae_forward_host(qsae_bsae_plan* p, const float* x_host, int B, float* vals_host,
+                           int32_t* idx_host, float* recon_host) {
+  if (!p || !x_host || !vals_host || !idx_host || (!recon_host && p && p->recon_mode != 2) || B < 0)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "forward_host: bad argument");
+  bool used[qsae_bsae_plan::kSlots] = {false, false, false, false};
+  int rc = enqueue_batch(p, x_host, B, vals_host, idx_host, recon_host, true, used);
+  for (int s = 0; s < qsae_bsae_plan::kSlots; ++s) {
+    cudaError_t e = cudaStreamSynchronize(p->slot[s].stream);
+    if (e != cudaSuccess && rc == QSAE_OK) rc = fail(QSAE_ERR_CUDA, "forward_host sync: %s", cudaGetErrorString(e));
+  }
+  return rc;
+}
+
+int qsae_bsae_submit_host(qsae_bsae_plan* p, const void* x_host, int B, float* vals_host, int32_t* idx_host,
+                          void* recon_host, int* ticket) {
+  if (!p || !x_host || !vals_host || !idx_host || (!recon_host && p && p->recon_mode != 2) || B < 0 || !ticket)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "submit_host: bad argument");
+  int t = -1;
+  for (int i = 0; i < QSAE_MAX_PENDING; ++i)
+    if (!p->pending[i].active) { t = i; break; }
+  if (t < 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "submit_host: %d batches already in flight; wait for one first", QSAE_MAX_PENDING);
+  auto& pd = p->pending[t];
+  for (int s = 0; s < qsae_bsae_plan::kSlots; ++s) pd.used[s] = false;
+  int rc = enqueue_batch(p, x_host, B, vals_host, idx_host, recon_host, false, pd.used);
+  for (int s = 0; s < qsae_bsae_plan::kSlots; ++s) {
+    if (!pd.used[s]) continue;
+    cudaError_t e = cudaEventRecord(pd.done[s], p->slot[s].stream);
+    if (e != cudaSuccess && rc == QSAE_OK) rc = fail(QSAE_ERR_CUDA, "submit_host: %s", cudaGetErrorString(e));
+  }
+  pd.active = true;   // also after an error: the caller waits (and thereby drains) what was enqueued
+  *ticket = t;
+  return rc;
+}
+
+int qsae_bsae_wait_host(qsae_bsae_plan* p, int ticket) {
+  if (!p || ticket < 0 || ticket >= QSAE_MAX_PENDING || !p->pending[ticket].active)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "wait_host: unknown ticket %d", ticket);
+  auto& pd = p->pending[ticket];
+  int rc = QSAE_OK;
+  for (int s = 0; s < qsae_bsae_plan::kSlots; ++s) {
+    if (!pd.used[s]) continue;
+    cudaError_t e = cudaEventSynchronize(pd.done[s]);
+    if (e != cudaSuccess && rc == QSAE_OK) rc = fail(QSAE_ERR_CUDA, "wait_host: %s", cudaGetErrorString(e));
+  }
+  pd.active = false;
   return rc;
 }
 

@@ -10,9 +10,17 @@ packed {-2,0,+2} rows per level, emitting the cumulative reconstructions in one 
 When a row has more active latents than the survivor lists hold (1024 per sub-stream, e.g. an
 untrained model with ~50 % activity) the forward is redone on the dense path: dense pre-activations,
 A = active * scale as bf16 hi + lo and one tcgen05 GEMM per level (qsae_matryoshka_forward_dense).
-`dense_mode`: "auto" (default: sparse first, dense on overflow), "always", "never" (raise on overflow).
+`dense_mode`: "auto" (default), "always", "never" (sparse only; raise on overflow, one host sync per forward).
+"auto" costs NO host synchronisation in the steady state (the reference itself syncs once per level, :85): the first
+forward of a weight version checks the overflow flag synchronously and records the regime (sparse / dense);
+afterwards a dense-regime model goes straight to the dense path, and a sparse-regime model reads the flag lazily --
+it is copied to pinned host memory behind the forward and examined at the start of the next one. Should a later
+batch overflow after all, its outputs are NaN (the kernel poisons them: never a silently wrong reconstruction), a
+warning is issued at the next forward and the module switches to the dense regime. `overflowed()` checks now.
 """
 from __future__ import annotations
+
+import warnings
 
 import torch
 import torch.nn as nn
@@ -144,6 +152,9 @@ class QuantizedMatryoshkaSAE(SparseAutoencoder):
         self.exact = True                    # decide activity from an fp32 re-scoring (any fp32 weights)
         self.dense_mode = "auto"             # "auto" | "always" | "never"
         self.last_path = None                # "sparse" / "dense": which path produced the last forward
+        self.last_overflow = None            # device flag of the last sparse forward (1: lists overflowed, outputs NaN)
+        self._regime = None                  # (weight key, "sparse" | "dense"): decided by the first forward of a weight version
+        self._pending = None                 # (pinned host flag, event) of the last unchecked sparse forward
         self._prep = PreparedCache()
 
     def _w_bf16(self):
@@ -220,12 +231,56 @@ class QuantizedMatryoshkaSAE(SparseAutoencoder):
             w_f32=lin.weight.detach().contiguous() if self.exact else None,
             w_norm_max=self._w_norm_max() if self.exact else None, want_residual=want_residual)
 
+    def _weights_key(self):
+        lin = self.encoder[0]
+        return param_key(lin.weight, lin.bias, self.decoder.weight, self.decoder.weight_mirror)
+
+    def _take_pending(self, block: bool) -> bool:
+        """-> True when the last unchecked sparse forward overflowed (block=False: only if its flag copy has landed)."""
+        if self._pending is None:
+            return False
+        host, ev = self._pending
+        if not block and not ev.query():
+            return False
+        ev.synchronize()
+        self._pending = None
+        return int(host[0]) != 0
+
+    def overflowed(self) -> bool:
+        """Synchronous check of the last sparse forward: True = its survivor lists overflowed and its outputs are NaN."""
+        if self.last_overflow is None:
+            return False
+        return int(self.last_overflow.item()) != 0
+
     def forward(self, x):
         x = require_cuda_input(x, self)
         if self.dense_mode == "always":
             return self._forward_dense(x)
-        result, counts, overflow = self._forward_sparse(x)
-        if self.dense_mode == "auto" and int(overflow.item()) != 0:
+        key = self._weights_key()
+        regime = self._regime[1] if (self._regime is not None and self._regime[0] == key) else None
+        capturing = torch.cuda.is_current_stream_capturing()
+        if self.dense_mode == "auto" and not capturing and self._take_pending(block=False):
+            warnings.warn("q_sae: the previous forward overflowed the sparse survivor lists (its outputs were NaN); "
+                          "switching this weight version to the dense path")
+            self._regime = (key, "dense")
+            regime = "dense"
+        if self.dense_mode == "auto" and regime == "dense":
             return self._forward_dense(x)
+        result, counts, overflow = self._forward_sparse(x)
+        self.last_overflow = overflow
+        if self.dense_mode == "never" or (regime is None and not capturing):
+            # synchronous: "never" must raise now; the first forward of a weight version decides the regime
+            if int(overflow.item()) != 0:
+                if self.dense_mode == "never":
+                    return self.decoder._finish(result, counts, overflow, x.shape[0])     # raises
+                self._regime = (key, "dense")
+                return self._forward_dense(x)
+            self._regime = (key, "sparse")
+        elif not capturing:
+            host = torch.empty((1,), dtype=torch.int32).pin_memory() if self._pending is None else self._pending[0]
+            host.copy_(overflow, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._pending = (host, ev)
         self.last_path = "sparse"
-        return self.decoder._finish(result, counts, overflow, x.shape[0])
+        return self.decoder._finish(result, counts, None, x.shape[0])

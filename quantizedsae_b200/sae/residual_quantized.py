@@ -41,11 +41,29 @@ class ResidualQuantizedSAE(SparseAutoencoder):
         for s in self.saes:
             s.exact = bool(value)
 
+    def _weights_key(self):
+        return tuple(s._weights_key() for s in self.saes)
+
     def forward(self, x):
         x = require_cuda_input(x, self)
-        if all(s.dense_mode == "auto" for s in self.saes):
-            # every stage on the sparse path, the overflow flags read once at the end (one host sync per forward
-            # instead of one per stage); any overflow -> the forward is redone stage by stage with the dense fallback
+        key = self._weights_key()
+        regime = self._regime[1] if (getattr(self, "_regime", None) is not None and self._regime[0] == key) else None
+        capturing = torch.cuda.is_current_stream_capturing()
+        pending = getattr(self, "_pending", None)
+        if pending is not None and not capturing and pending[1].query():
+            self._pending = None
+            if int(pending[0][0]) != 0:
+                import warnings
+
+                warnings.warn("rq_sae: the previous forward overflowed a stage's sparse survivor lists (its outputs were NaN); "
+                              "switching this weight version to the stage-by-stage path with the dense fallback")
+                self._regime = (key, "dense")
+                regime = "dense"
+        if all(s.dense_mode == "auto" for s in self.saes) and regime != "dense":
+            # every stage on the sparse path; no host synchronisation in the steady state: the first forward of a
+            # weight version reads the stages' overflow flags (one sync) and records the regime, later forwards copy
+            # the flags to pinned memory behind the forward and look at them at the start of the next one (an overflowing
+            # stage poisons its outputs and the residual it hands on with NaN, so nothing wrong is ever returned quietly)
             residual = x
             groups, levels, flags = [], [], []
             B = x.shape[0]
@@ -54,7 +72,19 @@ class ResidualQuantizedSAE(SparseAutoencoder):
                 groups.append(counts[-1].to(torch.float32) / float(max(B, 1)))
                 levels.append(result[-1])
                 flags.append(overflow)
-            if int(torch.cat(flags).sum().item()) == 0:
+            any_flag = torch.cat(flags).sum().to(torch.int32).reshape(1)
+            self.last_overflow = any_flag
+            ok = True
+            if regime is None and not capturing:
+                ok = int(any_flag.item()) == 0
+                self._regime = (key, "sparse" if ok else "dense")
+            elif not capturing:
+                host = torch.empty((1,), dtype=torch.int32).pin_memory() if pending is None else pending[0]
+                host.copy_(any_flag, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                self._pending = (host, ev)
+            if ok:
                 for sae in self.saes:
                     sae.last_path = "sparse"
                 return groups, levels
