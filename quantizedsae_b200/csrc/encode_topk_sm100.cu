@@ -961,7 +961,7 @@ prior_prep_kernel(const __grid_constant__ CUtensorMap tmap_w, PrepLaunch p) {
     fence_mbar_init();
     fence_proxy_async_smem();
     if (p.zero_counters != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {
-      p.zero_counters[0] = 0; p.zero_counters[1] = 0; p.zero_counters[2] = 0; p.zero_counters[3] = 0;
+      for (int i = 0; i < kPriorCounters; ++i) p.zero_counters[i] = 0;
     }
   }
   if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr);

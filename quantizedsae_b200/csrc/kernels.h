@@ -15,7 +15,9 @@ constexpr int kMaxK = 224;         // == QSAE_MAX_K: largest k of the warp-level
 constexpr int kMaxKLarge = 4096;   // == QSAE_MAX_K_LARGE: largest k of the block-level (radix select) paths
 constexpr size_t kSelectSmemBudget = 200 * 1024;   // shared memory of the block-per-row select kernels
 constexpr int kTopM = 64;          // values a thread keeps in the sample pre-pass (mode 5): top 2 of 32 column classes
-constexpr int kPriorMaxRank = 16;  // largest rank m of the prior threshold among a row's nsub * kTopM kept values
+constexpr int kPriorMaxRank = 16;
+constexpr int kRescueSlots = 8;    // rows the tail kernel recomputes with the whole grid at a time (scratch: one dense row each)
+constexpr int kPriorCounters = 4 + kRescueSlots;   // ints zeroed per call: [0] rescue rows, [1] block-select rows, [4..] slot tickets  // largest rank m of the prior threshold among a row's nsub * kTopM kept values
 
 // Tuning / diagnostic switches, read ONCE from the environment (never on a launch path); qsae_reload_tuning()
 // re-reads them (tests and tuning experiments that change the environment of a live process).
@@ -89,7 +91,7 @@ struct PrepLaunch {
   uint16_t* x_bf16;        // [B, D] out
   const float* bias;       // [n_sample] bias of the sampled rows
   float* prior;            // [B] out
-  int* zero_counters;      // 4 ints cleared by the first block (saves the memset node), or null
+  int* zero_counters;      // kPriorCounters ints cleared by the first block (saves the memset node), or null
 };
 // ns for this shape, 0 = use the separate kernels (large batches, narrow inputs)
 int prior_prep_pick_ns(int B, int D, int n_sample, int m, int num_sms);
@@ -163,6 +165,11 @@ struct RescueLaunch {
   float* out_vals;
   int32_t* out_idx;
   int32_t* out_flags;      // may be null
+  // tail kernel only: the first kRescueSlots listed rows are recomputed by the WHOLE grid (every block scores its
+  // slice of the dictionary into z_scratch[slot][H], the last block to finish selects): one row costs tens of
+  // microseconds instead of milliseconds on a single block. null: every row block-per-row (rescue_one_row).
+  float* z_scratch;        // [kRescueSlots, H]
+  int* slot_done;          // [kRescueSlots] tickets, zero on entry
 };
 const char* rescue_rows_launch(const RescueLaunch& p, int num_sms, cudaStream_t stream);
 

@@ -163,7 +163,7 @@ struct EncodePlan {
   int k_sel, m;
   bool use_prior;
   StagePlan main, pre;
-  size_t x_off, prior_off, counters_off, rescue_rows_off, ovf_rows_off, total;
+  size_t x_off, prior_off, counters_off, rescue_rows_off, ovf_rows_off, rescue_z_off, total;
 };
 
 int plan_encode(int B, int H, int D, int k, int exact, int n_sample, EncodePlan* pl) {
@@ -198,6 +198,7 @@ int plan_encode(int B, int H, int D, int k, int exact, int n_sample, EncodePlan*
   if (pl->use_prior) {
     pl->prior_off = off; off = align_up(off + static_cast<size_t>(B) * 4, 256);
     pl->ovf_rows_off = off; off = align_up(off + static_cast<size_t>(B) * 4, 256);
+    pl->rescue_z_off = off; off = align_up(off + static_cast<size_t>(kRescueSlots) * H * 4, 256);
     plan_stage(B, n_sample, pl->m, kStageSamplePre, false, off, &pl->pre);
     off = pl->pre.end;
   }
@@ -559,7 +560,7 @@ int encode_topk_impl(const float* x_f32, const uint16_t* w_bf16, const float* w_
   if (prep_ns == 0) {
     rc = launch_status("cast x", cast_bf16_launch(x_f32, x_bf16, static_cast<size_t>(B) * D, st));
     if (rc != QSAE_OK) return rc;
-    cudaError_t ce = cudaMemsetAsync(counters, 0, 4 * sizeof(int), st);
+    cudaError_t ce = cudaMemsetAsync(counters, 0, kPriorCounters * sizeof(int), st);
     if (ce != cudaSuccess) return fail(QSAE_ERR_CUDA, "encode_topk: %s", cudaGetErrorString(ce));
   }
 
@@ -654,8 +655,21 @@ int encode_topk_impl(const float* x_f32, const uint16_t* w_bf16, const float* w_
   rl.x_bf16 = x_bf16; rl.w_bf16 = w_bf16; rl.x_f32 = x_f32; rl.w_f32 = w_f32; rl.bias = b_enc;
   rl.rescue_count = counters; rl.rescue_rows = rescue_rows;
   rl.out_vals = out_vals; rl.out_idx = out_idx; rl.out_flags = out_flags;
+  rl.z_scratch = reinterpret_cast<float*>(ws + pl.rescue_z_off); rl.slot_done = counters + 4;
   rc = launch_status("select_tail kernel", select_tail_launch(sl, rl, counters + 1, ovf_rows, num_sms(), st));
   stage_mark(4, st);
+  if (tuning().debug_large) {   // diagnostics (synchronises): rows that took the tail kernel
+    cudaStreamSynchronize(st);
+    int h[4] = {0, 0, 0, 0};
+    cudaMemcpy(h, counters, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[qsae prior path] B=%d k_sel=%d m=%d nsub=%d cap=%d: %d rows recomputed exactly, %d rows through the block select\n",
+            B, pl.k_sel, pl.m, pl.main.nsub, pl.main.cap, h[0], h[1]);
+    if (h[0] > 0 && h[0] <= 8) {
+      int32_t rr[8];
+      cudaMemcpy(rr, rescue_rows, h[0] * sizeof(int32_t), cudaMemcpyDeviceToHost);
+      for (int i = 0; i < h[0]; ++i) fprintf(stderr, "  rescued row %d\n", rr[i]);
+    }
+  }
   return rc;
 }
 }  // namespace

@@ -259,6 +259,51 @@ select_topk_list_kernel(SelectLaunch p, int n_max, int ksort, const int* count, 
   }
 }
 
+// Top-k of one dense row z[0, H) (any k): radix select on the composite keys built on the fly, then
+// sort in shared memory. Leaves the ordered keys in sel[0, ksort) (zero padded); returns their count.
+template <int THREADS, bool BYPASS_L1 = false>
+__device__ __forceinline__ int dense_row_topk(const float* zptr, int H, int k, int ksort, uint64_t* sel, int* hist,
+                                              int* ctl, int* s_out) {
+  // BYPASS_L1: the row was written by other blocks of this launch (L1 is not coherent across SMs)
+  auto z = [&](int e) { return BYPASS_L1 ? __ldcg(zptr + e) : zptr[e]; };
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  if (threadIdx.x == 0) *s_out = 0;
+  const uint64_t T = block_radix_select([&](int e) { return make_sort_key(z(e), static_cast<uint32_t>(e)); }, H, k,
+                                        hist, ctl);
+  __syncthreads();
+  for (int base = 0; base < H; base += THREADS) {
+    const int e = base + threadIdx.x;
+    const uint64_t key = (e < H) ? make_sort_key(z(e), static_cast<uint32_t>(e)) : 0ull;
+    const bool keep = (e < H) && (key >= T);
+    const unsigned b = __ballot_sync(full, keep);
+    if (b != 0u) {
+      int pos = 0;
+      if (lane == 0) pos = atomicAdd(s_out, __popc(b));
+      pos = __shfl_sync(full, pos, 0) + __popc(b & lt_mask);
+      if (keep && pos < ksort) sel[pos] = key;
+    }
+  }
+  __syncthreads();
+  const int out = min(*s_out, ksort);
+  for (int e = out + threadIdx.x; e < ksort; e += THREADS) sel[e] = 0ull;
+  __syncthreads();
+  if (ksort >= 2048) block_bitonic_desc_regs<8>(sel, ksort);
+  else block_bitonic_desc(sel, ksort);
+  return out;
+}
+
+__device__ __forceinline__ void emit_sorted(const uint64_t* sel, int out, int row, int k_out, float* out_vals,
+                                            int32_t* out_idx) {
+  for (int j = threadIdx.x; j < k_out; j += blockDim.x) {
+    const uint64_t key = sel[j];
+    const bool valid = j < out;
+    out_vals[static_cast<size_t>(row) * k_out + j] = valid ? sort_key_value(key) : 0.f;
+    out_idx[static_cast<size_t>(row) * k_out + j] = valid ? static_cast<int32_t>(sort_key_col(key)) : -1;
+  }
+}
+
 // Decode of one row by the calling warp from the (values, indices) this block has just written to global memory
 // (callers synchronise the block first).
 __device__ __forceinline__ void decode_row_from_outputs(const SelectLaunch& p, int row, int lane) {
@@ -308,55 +353,95 @@ select_tail_kernel(SelectLaunch p, RescueLaunch r, int n_max, int ksort, const i
     if (p.dec_kind == 1 && warp == 0) decode_row_from_outputs(p, row, lane);
     __syncthreads();
   }
-  for (int li = blockIdx.x; li < n_res; li += gridDim.x) {
+  // ---- rows whose prior failed the count check. The first kRescueSlots of them are recomputed by the whole grid:
+  //      every block scores its slice of the dictionary for the row (CUDA cores, the arithmetic of rescue_one_row,
+  //      four latents in flight per warp) into a dense scratch row, and the block that finishes last selects, emits
+  //      and decodes. (A single block per row, as for the remaining rows below, takes milliseconds per row: its
+  //      33 MB dictionary sweep is bound by the latency of one load chain per warp.)
+  const int n_fast = (r.z_scratch != nullptr) ? min(n_res, kRescueSlots) : 0;
+  if (n_fast > 0) {
+    __shared__ float4 xs[128];
+    __shared__ int s_last;
+    const unsigned full = 0xffffffffu;
+    const int D = r.D, H = r.H;
+    const int per = (H + gridDim.x - 1) / gridDim.x;
+    const int h0 = blockIdx.x * per, h1 = min(H, h0 + per);
+    uint64_t* sel = reinterpret_cast<uint64_t*>(sel_smem);
+    int* hist = reinterpret_cast<int*>(sel_smem + static_cast<size_t>(ksort) * 8);    // 256 + 4 + 1 ints behind the sort buffer
+    for (int li = 0; li < n_fast; ++li) {
+      const int row = r.rescue_rows[li];
+      float* z = r.z_scratch + static_cast<size_t>(li) * H;
+      __syncthreads();
+      for (int q = threadIdx.x; q < 128; q += kSelThreads) {
+        const int d = q * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (d < D) {
+          if (r.exact) v = *reinterpret_cast<const float4*>(r.x_f32 + static_cast<size_t>(row) * D + d);
+          else v = bf16x4_to_float4(*reinterpret_cast<const uint2*>(r.x_bf16 + static_cast<size_t>(row) * D + d));
+        }
+        xs[q] = v;
+      }
+      __syncthreads();
+      float4 xr[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) xr[c] = xs[c * 32 + lane];
+      for (int hb = h0 + warp * 4; hb < h1; hb += (kSelThreads / 32) * 4) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float4 w[4][4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int h = min(hb + t, h1 - 1);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int d = c * 128 + lane * 4;
+            w[t][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (d < D) {
+              if (r.exact) w[t][c] = __ldg(reinterpret_cast<const float4*>(r.w_f32 + static_cast<size_t>(h) * D + d));
+              else w[t][c] = bf16x4_to_float4(__ldg(reinterpret_cast<const uint2*>(r.w_bf16 + static_cast<size_t>(h) * D + d)));
+            }
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            acc[t] = fmaf(xr[c].x, w[t][c].x, acc[t]); acc[t] = fmaf(xr[c].y, w[t][c].y, acc[t]);
+            acc[t] = fmaf(xr[c].z, w[t][c].z, acc[t]); acc[t] = fmaf(xr[c].w, w[t][c].w, acc[t]);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) acc[t] += __shfl_xor_sync(full, acc[t], o);
+        }
+        if (lane < 4 && hb + lane < h1) {
+          float sc = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]) + __ldg(r.bias + hb + lane);
+          if (r.act == 1) sc = fmaxf(sc, 0.f);
+          z[hb + lane] = sc;
+        }
+      }
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) s_last = (atomicAdd(&r.slot_done[li], 1) == static_cast<int>(gridDim.x) - 1) ? 1 : 0;
+      __syncthreads();
+      if (s_last) {   // block-uniform: every other block's slice is visible (their fence precedes their ticket)
+        __threadfence();
+        const int ksort_out = ksort;
+        const int out = dense_row_topk<kSelThreads, true>(z, H, r.k_out, ksort_out, sel, hist, hist + 256, hist + 260);
+        emit_sorted(sel, out, row, r.k_out, r.out_vals, r.out_idx);
+        if (r.out_flags != nullptr && threadIdx.x == 0) r.out_flags[row] = 0;  // exact by construction
+        __syncthreads();
+        if (p.dec_kind == 1 && warp == 0) decode_row_from_outputs(p, row, lane);
+      }
+    }
+    __syncthreads();
+  }
+  for (int li = n_fast + blockIdx.x; li < n_res; li += gridDim.x) {
     const int row = r.rescue_rows[li];
     rescue_one_row(r, row);
     __syncthreads();
     if (p.dec_kind == 1 && warp == 0) decode_row_from_outputs(p, row, lane);
     __syncthreads();
-  }
-}
-
-// Top-k of one dense row z[0, H) (any k): radix select on the composite keys built on the fly, then
-// sort in shared memory. Leaves the ordered keys in sel[0, ksort) (zero padded); returns their count.
-template <int THREADS>
-__device__ __forceinline__ int dense_row_topk(const float* z, int H, int k, int ksort, uint64_t* sel, int* hist,
-                                              int* ctl, int* s_out) {
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  if (threadIdx.x == 0) *s_out = 0;
-  const uint64_t T = block_radix_select([&](int e) { return make_sort_key(z[e], static_cast<uint32_t>(e)); }, H, k,
-                                        hist, ctl);
-  __syncthreads();
-  for (int base = 0; base < H; base += THREADS) {
-    const int e = base + threadIdx.x;
-    const uint64_t key = (e < H) ? make_sort_key(z[e], static_cast<uint32_t>(e)) : 0ull;
-    const bool keep = (e < H) && (key >= T);
-    const unsigned b = __ballot_sync(full, keep);
-    if (b != 0u) {
-      int pos = 0;
-      if (lane == 0) pos = atomicAdd(s_out, __popc(b));
-      pos = __shfl_sync(full, pos, 0) + __popc(b & lt_mask);
-      if (keep && pos < ksort) sel[pos] = key;
-    }
-  }
-  __syncthreads();
-  const int out = min(*s_out, ksort);
-  for (int e = out + threadIdx.x; e < ksort; e += THREADS) sel[e] = 0ull;
-  __syncthreads();
-  if (ksort >= 2048) block_bitonic_desc_regs<8>(sel, ksort);
-  else block_bitonic_desc(sel, ksort);
-  return out;
-}
-
-__device__ __forceinline__ void emit_sorted(const uint64_t* sel, int out, int row, int k_out, float* out_vals,
-                                            int32_t* out_idx) {
-  for (int j = threadIdx.x; j < k_out; j += blockDim.x) {
-    const uint64_t key = sel[j];
-    const bool valid = j < out;
-    out_vals[static_cast<size_t>(row) * k_out + j] = valid ? sort_key_value(key) : 0.f;
-    out_idx[static_cast<size_t>(row) * k_out + j] = valid ? static_cast<int32_t>(sort_key_col(key)) : -1;
   }
 }
 
