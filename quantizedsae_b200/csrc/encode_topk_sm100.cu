@@ -1359,7 +1359,7 @@ const char* encode_dense_tc_launch(const uint16_t* x_bf16, const uint16_t* const
   p.dense_flags = (out_f32 ? 1 : 0) | (out_hi ? 2 : 0) | (out_lo ? 4 : 0);
   if (p.dense_flags == 0) return "dense encoder: no output requested";
   if (tuning().dense_flags_mask >= 0) p.dense_flags &= tuning().dense_flags_mask;  // timing experiments only
-  p.cluster = pick_cluster(p, kDefaultClusterDense);
+  p.cluster = p.range_g > 0 ? 0 : pick_cluster(p, kDefaultClusterDense);
   BMaps bm;
   if (const char* err = make_b_maps(&bm, w_parts, n_parts, p)) return err;
   return launch_any<true>(tx, bm, p, stream);

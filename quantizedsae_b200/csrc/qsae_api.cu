@@ -33,6 +33,7 @@ void reload_tuning() {
   t.encode_cluster = env_int("QSAE_ENCODE_CLUSTER", -1);
   t.encode_range = env_int("QSAE_ENCODE_RANGE", 1);
   t.prior_prep = env_int("QSAE_PRIOR_PREP", 1);
+  t.dense_range = env_int("QSAE_DENSE_RANGE", 0);
   t.dense_flags_mask = env_int("QSAE_DENSE_FLAGS_MASK", -1);
   t.decode_pair = env_int("QSAE_DECODE_PAIR", -1);
   t.peer_timeout_ms = env_int("QSAE_PEER_TIMEOUT_MS", 20000);
@@ -98,7 +99,8 @@ struct StagePlan {
 
 enum StageKind { kStageClassBound = 0, kStagePriorMain = 1, kStageSamplePre = 2 };
 
-void plan_stage(int B, int H, int k_sel, StageKind kind, bool allow_split_override, size_t base, StagePlan* sp) {
+void plan_stage(int B, int H, int k_sel, StageKind kind, bool allow_split_override, size_t base, StagePlan* sp,
+                bool allow_range = false) {
   sp->H = H;
   sp->k_sel = k_sel;
   sp->range_g = 0;
@@ -127,7 +129,7 @@ void plan_stage(int B, int H, int k_sel, StageKind kind, bool allow_split_overri
     // covers ~1 / nsub of a row's latents (a few dozen survivors), so 256 entries are plenty (a full list is cut
     // exactly in the kernel, as always)
     int range_nsub = 0;
-    const int g = (k_sel > 0 && allow_split_override && tuning().encode_splits == 0) ? encode_pick_range(B, H, num_sms(), &range_nsub) : 0;
+    const int g = (allow_range && tuning().encode_splits == 0) ? encode_pick_range(B, H, num_sms(), &range_nsub) : 0;
     if (g > 0) {
       sp->range_g = g;
       sp->nsub = range_nsub;
@@ -191,7 +193,7 @@ int plan_encode(int B, int H, int D, int k, int exact, int n_sample, EncodePlan*
   }
   pl->x_off = 0;
   size_t off = align_up(static_cast<size_t>(B) * D * 2, 1024);
-  plan_stage(B, H, k_sel, pl->use_prior ? kStagePriorMain : kStageClassBound, true, off, &pl->main);
+  plan_stage(B, H, k_sel, pl->use_prior ? kStagePriorMain : kStageClassBound, true, off, &pl->main, true);
   off = pl->main.end;
   pl->counters_off = off; off += 256;
   pl->rescue_rows_off = off; off = align_up(off + static_cast<size_t>(B) * 4, 256);
@@ -758,8 +760,9 @@ int plan_matryoshka(int B, int H, int D, MatPlan* mp) {
     return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka: D must be a multiple of 16 in [16, 512], got %d", D);
   mp->x_off = 0;
   mp->prior_off = align_up(static_cast<size_t>(B) * D * 2, 1024);
-  plan_stage(B, H, 0, kStagePriorMain, false, mp->prior_off + align_up(static_cast<size_t>(B) * 4, 256), &mp->st);
-  mp->st.cap = kCandCapMax;  // every active latent is kept: largest buffers
+  plan_stage(B, H, 0, kStagePriorMain, false, mp->prior_off + align_up(static_cast<size_t>(B) * 4, 256), &mp->st, true);
+  // every active latent is kept: largest buffers. Range schedule: more, shorter lists per row (the same capacity per row)
+  mp->st.cap = mp->st.range_g > 0 ? kCandCapMax / 2 : kCandCapMax;
   mp->st.cnt_off = mp->st.cand_off + static_cast<size_t>(B) * mp->st.nsub * mp->st.cap * 8;
   mp->st.thr_off = mp->st.cnt_off + static_cast<size_t>(B) * mp->st.nsub * 4;
   mp->st.end = align_up(mp->st.thr_off + static_cast<size_t>(B) * mp->st.nsub * 4, 256);
@@ -961,6 +964,10 @@ int dense_encode_tc(const float* x_f32, const uint16_t* w_hi, const uint16_t* w_
   el.n_tiles = (H + kEncBN - 1) / kEncBN;
   el.n_splits = encode_pick_splits(B, H, num_sms());
   el.tiles_per_split = (el.n_tiles + el.n_splits - 1) / el.n_splits;
+  if (tuning().dense_range != 0) {   // one CTA per SM over contiguous tile ranges (single-CTA variant) instead of CTA pairs
+    int unused = 0;
+    el.range_g = encode_pick_range(B, H, num_sms(), &unused);
+  }
   const size_t xn = static_cast<size_t>(B) * D;
   const size_t xstride = align_up(xn * 2, 1024);
   uint16_t* xh = reinterpret_cast<uint16_t*>(x_parts);
