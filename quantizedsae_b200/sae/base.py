@@ -4,6 +4,13 @@ weight-preparation cache shared by the B200 modules.
 Prepared (packed / bf16 / transposed) copies of parameters are device-resident and keyed on the
 parameters' identity, storage pointer and in-place version counter, so `load_state_dict`,
 `.to(device)`, optimizer steps and `param.data = ...` all invalidate them.
+
+Limitation: an in-place edit made THROUGH `.data` (`w.data.mul_(m)`, `w.data.copy_(v)`; the reference's own
+`STEWeights.init_mask` / `update_mask` do `self.weight.data *= mask`) changes none of the three -- `.data` is a
+detached alias with its own version counter -- so the prepared copies would go stale silently. After such an edit
+call `module.invalidate()` (every module of this package has it; it also reaches the sub-modules' caches).
+Tensors created under `torch.inference_mode()` have no version counter: for them the key is identity + storage
+pointer only, and `invalidate()` is the way to announce any in-place change.
 """
 from __future__ import annotations
 
@@ -11,9 +18,31 @@ import torch
 import torch.nn as nn
 
 
+def _version(t: torch.Tensor) -> int:
+    try:
+        return t._version
+    except RuntimeError:          # inference tensors do not track a version counter
+        return -1
+
+
 def param_key(*tensors: torch.Tensor | None) -> tuple:
-    return tuple(None if t is None else (id(t), t.data_ptr(), t._version, tuple(t.shape), str(t.device))
+    return tuple(None if t is None else (id(t), t.data_ptr(), _version(t), tuple(t.shape), str(t.device))
                  for t in tensors)
+
+
+def invalidate_prepared(module: nn.Module) -> None:
+    """Drop every prepared (packed / bf16 / transposed / sampled) copy held by `module` and its sub-modules; the next
+    forward rebuilds them from the current parameter values."""
+    for m in module.modules():
+        prep = getattr(m, "_prep", None)
+        if isinstance(prep, PreparedCache):
+            prep.clear()
+        for name in ("_regime", "_pending", "_pol_cache"):
+            if hasattr(m, name):
+                setattr(m, name, None)
+        ops = getattr(m, "ops", None)
+        if ops is not None and isinstance(getattr(ops, "_prep", None), PreparedCache):
+            ops._prep.clear()
 
 
 class PreparedCache:
@@ -57,6 +86,12 @@ class SparseAutoencoder(nn.Module):
         self.hidden_dim = hidden_dim
         self.encoder = None
         self.decoder = None
+
+    def invalidate(self) -> None:
+        """Forget the prepared copies of the weights (see the module docstring: needed after `.data` edits)."""
+        invalidate_prepared(self)
+
+    refresh = invalidate
 
     def encode(self, x):
         if self.encoder is None:

@@ -12,7 +12,7 @@ import torch.nn as nn
 
 from .. import _lib
 from ..sparse import SparseLatents
-from .base import PreparedCache, param_key, require_cuda_input
+from .base import PreparedCache, invalidate_prepared, param_key, require_cuda_input
 
 
 class BaselineSparseAutoencoder(nn.Module):
@@ -28,6 +28,13 @@ class BaselineSparseAutoencoder(nn.Module):
         self.last_flags = None
         self._prep = PreparedCache()
 
+
+    def invalidate(self) -> None:
+        """Forget the prepared copies of the weights (needed after in-place edits through `.data`, which bump no version
+        counter; see sae/base.py)."""
+        invalidate_prepared(self)
+
+    refresh = invalidate
     def _w_bf16(self):
         w = self.encoder[0].weight
         return self._prep.get("w_bf16", param_key(w), lambda: _lib.cast_bf16(w.detach().contiguous()))

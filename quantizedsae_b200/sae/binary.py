@@ -26,7 +26,7 @@ import torch.nn as nn
 
 from .. import _lib
 from ..sparse import SparseLatents
-from .base import PreparedCache, SparseAutoencoder, param_key, require_cuda_input
+from .base import PreparedCache, invalidate_prepared, SparseAutoencoder, param_key, require_cuda_input
 
 
 class binary_decoder(nn.Module):
@@ -47,6 +47,13 @@ class binary_decoder(nn.Module):
         self._prep = PreparedCache()
 
     # ---- cached device-side dictionaries -------------------------------------------------
+
+    def invalidate(self) -> None:
+        """Forget the prepared copies of the weights (needed after in-place edits through `.data`, which bump no version
+        counter; see sae/base.py)."""
+        invalidate_prepared(self)
+
+    refresh = invalidate
     def _packed(self):
         """(packed dictionary, polarize_loss, max |p - bit|) for the current logits."""
         if not self.weight.is_cuda:

@@ -26,7 +26,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from .base import PreparedCache, SparseAutoencoder, param_key, require_cuda_input
+from .base import PreparedCache, invalidate_prepared, SparseAutoencoder, param_key, require_cuda_input
 
 
 def nested_sizes(in_features: int, n_bits: int) -> list:
@@ -63,6 +63,13 @@ class QuantizedMatryoshkaDecoder(nn.Module):
         self._prep = PreparedCache()
 
     # ---- prepared dictionary ---------------------------------------------------------------
+
+    def invalidate(self) -> None:
+        """Forget the prepared copies of the weights (needed after in-place edits through `.data`, which bump no version
+        counter; see sae/base.py)."""
+        invalidate_prepared(self)
+
+    refresh = invalidate
     def _levels(self):
         dev = self.weight.device
 

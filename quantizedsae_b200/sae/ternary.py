@@ -27,7 +27,7 @@ import torch.nn as nn
 
 from .. import _lib
 from ..sparse import SparseLatents
-from .base import PreparedCache, param_key, require_cuda_input
+from .base import PreparedCache, invalidate_prepared, param_key, require_cuda_input
 
 
 class STEWeights(nn.Module):
@@ -42,6 +42,13 @@ class STEWeights(nn.Module):
         self.exact = True
         self._prep = PreparedCache()
 
+
+    def invalidate(self) -> None:
+        """Forget the prepared copies of the weights (needed after in-place edits through `.data`, which bump no version
+        counter; see sae/base.py)."""
+        invalidate_prepared(self)
+
+    refresh = invalidate
     def _ternary(self):
         """(T bf16 [D, H], T int8 rows [H, D]) for the current weights."""
         if not self.weight.is_cuda:
@@ -79,6 +86,13 @@ class TernarySparseAutoencoder(nn.Module):
         self.exact = True
         self._prep = PreparedCache()
 
+
+    def invalidate(self) -> None:
+        """Forget the prepared copies of the weights (needed after in-place edits through `.data`, which bump no version
+        counter; see sae/base.py)."""
+        invalidate_prepared(self)
+
+    refresh = invalidate
     def _w_bf16(self):
         w = self.encoder[0].weight
         return self._prep.get("w_bf16", param_key(w), lambda: _lib.cast_bf16(w.detach().contiguous()))

@@ -29,7 +29,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .sae.base import PreparedCache, param_key
+from .sae.base import PreparedCache, invalidate_prepared, param_key
 from .sparse import SparseLatents
 
 
@@ -303,6 +303,10 @@ class DictionaryShardedBinarySAE(nn.Module):
 
     def top_k(self) -> int:
         return int(self.hidden_dim * self.k)          # over the FULL dictionary, as sae/binary.py:94
+
+    def invalidate(self) -> None:
+        """Forget the prepared copies of this shard's weights (needed after in-place edits through `.data`)."""
+        invalidate_prepared(self)
 
     # ---- collectives (world size 1 degenerates to local views) -------------------------------
     def _all_gather(self, t: torch.Tensor) -> torch.Tensor:

@@ -491,6 +491,27 @@ def test_host_pipeline_submit_wait_and_bf16_io(cuda_device):
         lib.qsae_bsae_plan_destroy(plan)
 
 
+def test_data_edits_need_invalidate(cuda_device):
+    """In-place edits through `.data` (the reference's STEWeights.init_mask / update_mask do `weight.data *= mask`)
+    bump no version counter: the prepared dictionary stays until invalidate() -- the documented contract."""
+    D, H, B = 64, 2048, 32
+    torch.manual_seed(1)
+    with torch.device(cuda_device):
+        m = Q.TernarySparseAutoencoder(D, H)
+    with torch.no_grad():
+        m.decoder.weight.copy_(0.6 * torch.randn(D, H, device=cuda_device))
+    m.eval()
+    x = torch.randn(B, D, device=cuda_device)
+    with torch.no_grad():
+        _, r0 = m(x)
+        m.decoder.weight.data.mul_(0.0)            # every ternary weight becomes 0
+        _, r1 = m(x)
+        assert torch.equal(r0, r1)                 # stale prepared copy (documented)
+        m.invalidate()
+        _, r2 = m(x)
+    assert float(r2.abs().max()) == 0.0
+
+
 def test_native_library_was_used(cuda_device):
     assert L._lib is not None and L.launch_count() > 0
 

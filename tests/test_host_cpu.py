@@ -248,3 +248,29 @@ def test_sharded_transport_defaults_and_k_send():
     # never more than the shard's own top-k, never less than its fair share
     for k in (32, 255, 256, 2097, 4096):
         assert p.k_send(k) <= p.k_local(k) and p.k_send(k) >= min(p.k_local(k), -(-k // 8))
+
+
+def test_param_key_handles_inference_tensors_and_invalidate_exists():
+    """`_version` raises for tensors created under inference_mode; every module offers invalidate() for
+    in-place edits made through `.data` (which bump no version counter)."""
+    import torch
+
+    import quantizedsae_b200 as Q
+    from quantizedsae_b200.sae.base import PreparedCache, param_key
+
+    with torch.inference_mode():
+        w = torch.zeros(4)
+    assert param_key(w)[0][2] == -1
+    v = torch.zeros(4)
+    k0 = param_key(v)
+    v.add_(1)
+    assert param_key(v) != k0                  # ordinary in-place edits are seen ...
+    k1 = param_key(v)
+    v.data.mul_(2)
+    assert param_key(v) == k1                  # ... edits through .data are not: invalidate() is the contract
+    for m in (Q.BinarySAE(16, 64, 4.0, 4), Q.BaselineSparseAutoencoder(16, 64), Q.TernarySparseAutoencoder(16, 64),
+              Q.QuantizedMatryoshkaSAE(16, 64, 4, n_bits=2), Q.ResidualQuantizedSAE(16, 64, 4, n_bits=2)):
+        m._prep = getattr(m, "_prep", PreparedCache())
+        m._prep.get("x", (1,), lambda: 1)
+        m.invalidate()
+        assert m._prep._slots == {}
