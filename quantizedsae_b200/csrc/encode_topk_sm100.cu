@@ -208,7 +208,7 @@ __device__ __forceinline__ void epilogue_loop(const EncodeLaunch& p, int n_my_ti
     // prior threshold: the m-th largest pre-activation of a sample of this row's latents
     // (itself one of the row's values). Tight, but only probably <= the k-th largest: the merge
     // kernel verifies it by counting survivors and sends the rare failing row to the rescue path.
-    thr = fmaxf(thr, __ldg(p.prior + static_cast<size_t>(row) * p.prior_stride));
+    thr = fmaxf(thr, p.prior != nullptr ? __ldg(p.prior + static_cast<size_t>(row) * p.prior_stride) : p.prior_const);
     valid_bound = thr;
   }
   constexpr bool kClasses = (MODE >= 1 && MODE <= 3);

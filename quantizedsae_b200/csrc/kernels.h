@@ -53,8 +53,9 @@ struct EncodeLaunch {
   int mode;             // epilogue bound: 0 bisection only, 1/2/3 class maxima, 4 prior (see .cu)
   int cap;              // entries per survivor buffer
   const float* bias;    // [H]
-  const float* prior;   // mode 4: per-row threshold at prior[row * prior_stride]
+  const float* prior;   // mode 4: per-row threshold at prior[row * prior_stride]; null: prior_const for every row
   int prior_stride;
+  float prior_const;
   int* overflow;        // mode 4 with k_sel <= 0 (threshold only): set to 1 when a buffer filled up
   float* top_out;       // mode 5: [B][n_splits*2][kTopM] the two largest values of each column class, per sub-stream
   void* cand;           // [B][n_splits*2][cap] {float bits, int32 column}

@@ -159,7 +159,7 @@ decode_matryoshka_kernel(const uint2* __restrict__ cand, const int* __restrict__
                          const float* __restrict__ scale, const int* __restrict__ level_start,
                          int n_levels, int H, int D, const float* __restrict__ bias,
                          float* __restrict__ result /* [n_levels, B, D] */,
-                         unsigned* __restrict__ count_partial /* [gridDim.x * kMatWarps, NL] */,
+                         unsigned long long* __restrict__ level_count /* [n_levels], += */,
                          const float* __restrict__ x_f32, const float* __restrict__ w_f32,
                          const float* __restrict__ b_enc, float thr_value, int exact,
                          int32_t* __restrict__ active_idx /* [B, active_cap] or null */, int active_cap,
@@ -291,9 +291,20 @@ decode_matryoshka_kernel(const uint2* __restrict__ cand, const int* __restrict__
       }
     }
   }
+  // activity counts: the block's warps add up in shared memory, then one 64-bit atomic per level and block (a few
+  // thousand integer atomics on n_levels addresses per launch; the sum is exact, so the order does not matter).
+  // Round 1 summed a [warps, n_levels] partial array in a second, single-block kernel: 12.7 us at any batch size.
+  __shared__ unsigned s_cnt[kMatWarps][NL];
   if (lane == 0) {
 #pragma unroll
-    for (int l = 0; l < NL; ++l) count_partial[(static_cast<size_t>(blockIdx.x) * kMatWarps + warp) * NL + l] = cnt[l];
+    for (int l = 0; l < NL; ++l) s_cnt[warp][l] = cnt[l];
+  }
+  __syncthreads();
+  if (threadIdx.x < NL && threadIdx.x < n_levels) {
+    unsigned long long t = 0ull;
+#pragma unroll
+    for (int w = 0; w < kMatWarps; ++w) t += s_cnt[w][threadIdx.x];
+    if (t != 0ull) atomicAdd(level_count + threadIdx.x, t);
   }
 }
 
@@ -377,22 +388,17 @@ const char* decode_matryoshka_launch(const void* cand, const int* cand_cnt, int 
   if (D > 512 || (D % 16) != 0) return "decode_matryoshka: D must be a multiple of 16, <= 512";
   int blocks = (B + kMatWarps - 1) / kMatWarps;
   if (blocks > num_sms * 6) blocks = num_sms * 6;   // = resident blocks (launch bounds: 6 per SM)
-  unsigned* partial = static_cast<unsigned*>(scratch);
+  (void)scratch;   // round 1: per-warp partial counts for a second kernel; the counts now leave through atomics
   const uint2* c2 = reinterpret_cast<const uint2*>(cand);
 #define QSAE_MAT(NL) \
   decode_matryoshka_kernel<NL><<<blocks, kMatWarps * 32, 0, stream>>>(c2, cand_cnt, nsub, cap, B, packed, scale, level_start, \
-      n_levels, H, D, bias, result, partial, x_f32, w_f32, b_enc, thr_value, exact, active_idx, active_cap, active_cnt, \
+      n_levels, H, D, bias, result, level_count, x_f32, w_f32, b_enc, thr_value, exact, active_idx, active_cap, active_cnt, \
       resid_in, resid_out, poison_flag)
-  int nl;
-  if (n_levels <= 1) { nl = 1; QSAE_MAT(1); }
-  else if (n_levels <= 2) { nl = 2; QSAE_MAT(2); }
-  else if (n_levels <= 4) { nl = 4; QSAE_MAT(4); }
-  else { nl = 8; QSAE_MAT(8); }
+  if (n_levels <= 1) QSAE_MAT(1);
+  else if (n_levels <= 2) QSAE_MAT(2);
+  else if (n_levels <= 4) QSAE_MAT(4);
+  else QSAE_MAT(8);
 #undef QSAE_MAT
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return cudaGetErrorString(e);
-  count_launches(1);
-  sum_level_counts_kernel<<<1, 256, 0, stream>>>(partial, blocks * kMatWarps, nl, n_levels, level_count);
   return cuda_err(cudaGetLastError());
 }
 

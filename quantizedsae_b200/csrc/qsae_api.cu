@@ -848,7 +848,6 @@ int qsae_matryoshka_forward_active(const float* x_f32, const uint16_t* w_bf16, c
   cudaStream_t st = S(stream);
   cudaError_t ce = cudaMemsetAsync(level_count, 0, static_cast<size_t>(n_levels) * sizeof(unsigned long long), st);
   if (ce == cudaSuccess) ce = cudaMemsetAsync(overflow, 0, sizeof(int), st);
-  if (ce == cudaSuccess && !exact) ce = cudaMemcpyAsync(thr, &kActiveThreshold, sizeof(float), cudaMemcpyHostToDevice, st);
   if (ce != cudaSuccess) return fail(QSAE_ERR_CUDA, "matryoshka_forward: %s", cudaGetErrorString(ce));
   if (exact) {
     rc = launch_status("row_threshold", row_threshold_launch(x_f32, B, D, w_norm_max, kActiveThreshold, thr, st));
@@ -858,7 +857,7 @@ int qsae_matryoshka_forward_active(const float* x_f32, const uint16_t* w_bf16, c
   if (rc != QSAE_OK) return rc;
   EncodeLaunch el;
   fill_encode_launch(&el, mp.st, B, D, QSAE_ACT_NONE, b_enc, ws);
-  el.prior = thr; el.prior_stride = exact ? 1 : 0;   // per-row band, or one constant threshold
+  el.prior = exact ? thr : nullptr; el.prior_stride = 1; el.prior_const = kActiveThreshold;   // per-row band, or one constant threshold (by value)
   el.overflow = overflow;
   rc = launch_status("encode kernel (threshold)", encode_topk_launch(x_bf16, w_bf16, el, st));
   if (rc != QSAE_OK) return rc;

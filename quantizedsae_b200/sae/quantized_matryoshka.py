@@ -120,7 +120,7 @@ class QuantizedMatryoshkaDecoder(nn.Module):
         if overflow is not None and int(overflow.item()) != 0:
             raise RuntimeError("q_sae: a row has more active latents than the sparse decoder holds "
                                "(1024 per sub-stream) and dense_mode is 'never'")
-        groups = counts.to(torch.float32) / float(max(B, 1))
+        groups = torch.true_divide(counts, float(max(B, 1))).to(torch.float32)   # int64 / float -> float32 in one kernel
         return [groups[i] for i in range(self.n_bits)], [result[i] for i in range(self.n_bits)]
 
     def forward(self, latent):
