@@ -611,6 +611,38 @@ __device__ __forceinline__ void epilogue_dense(const EncodeLaunch& p, int n_my_t
   }
 }
 
+// one piece of the epilogue role: dense epilogue, or the selection mode of this launch
+template <bool DENSE, bool PAIR>
+__device__ __forceinline__ void run_epilogue_piece(const EncodeLaunch& p, int n, int tile0, int sub_base, int m0, int tt0,
+                                                   int zero_from, int e, int lane, uint32_t tmem_base, const float* bias_smem,
+                                                   uint16_t* share, uint8_t* staging, uint64_t* tmem_full, uint64_t* tmem_empty,
+                                                   uint64_t* bias_full, uint64_t* pe) {
+  if constexpr (DENSE) {
+    epilogue_dense<PAIR>(p, n, tile0, m0, tt0, e, lane, tmem_base, bias_smem, staging, tmem_full, tmem_empty, bias_full, pe);
+  } else {
+    switch (p.mode) {
+      case 1:
+        epilogue_loop<1>(p, n, tile0, sub_base, m0, tt0, zero_from, e, lane, tmem_base, bias_smem, share, tmem_full, tmem_empty, bias_full, pe);
+        break;
+      case 2:
+        epilogue_loop<2>(p, n, tile0, sub_base, m0, tt0, zero_from, e, lane, tmem_base, bias_smem, share, tmem_full, tmem_empty, bias_full, pe);
+        break;
+      case 3:
+        epilogue_loop<3>(p, n, tile0, sub_base, m0, tt0, zero_from, e, lane, tmem_base, bias_smem, share, tmem_full, tmem_empty, bias_full, pe);
+        break;
+      case 4:
+        epilogue_loop<4>(p, n, tile0, sub_base, m0, tt0, zero_from, e, lane, tmem_base, bias_smem, share, tmem_full, tmem_empty, bias_full, pe);
+        break;
+      case 5:
+        epilogue_loop<5>(p, n, tile0, sub_base, m0, tt0, zero_from, e, lane, tmem_base, bias_smem, share, tmem_full, tmem_empty, bias_full, pe);
+        break;
+      default:
+        epilogue_loop<0>(p, n, tile0, sub_base, m0, tt0, zero_from, e, lane, tmem_base, bias_smem, share, tmem_full, tmem_empty, bias_full, pe);
+        break;
+    }
+  }
+}
+
 // CL = 0: one CTA per 128 rows.
 // CL = 1 (multicast): clusters of two CTAs along the row-block axis sweep the same W tiles in
 //   lockstep; each CTA fetches half of every 256 x 64 stage (128 latents) and TMA-multicasts it into
@@ -842,43 +874,23 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
     // ------------------------------------------------------------- epilogue / selection
     const int e = warp - 4;
     uint64_t* pe = PAIR ? pair_empty : nullptr;
-    const int n_pieces = *piece_n;
-    int tt0 = 0;
+    if constexpr (CL != 0) {
+      // cluster variants never run the range schedule: one piece, its constants known at compile time (keeps the
+      // epilogue's register allocation where it was before pieces existed: the B = 65536 sweep lost 7 % otherwise)
+      const int tile_begin = split * p.tiles_per_split;
+      const int n = max(0, min(p.n_tiles, tile_begin + p.tiles_per_split) - tile_begin);
+      if (n > 0) run_epilogue_piece<DENSE, PAIR>(p, n, tile_begin, split * 2, m0_grid, 0, -1, e, lane, tmem_base, bias_smem, share, smem + L.staging_off,
+                                                 tmem_full, tmem_empty, bias_full, pe);
+    } else {
+      const int n_pieces = *piece_n;
+      int tt0 = 0;
 #pragma unroll 1
-    for (int pi = 0; pi < n_pieces; ++pi) {
-      const Piece pc = piece_tab[pi];
-      const int m0 = pc.rb * BM;
-      if constexpr (DENSE) {
-        epilogue_dense<PAIR>(p, pc.n, pc.tile0, m0, tt0, e, lane, tmem_base, bias_smem, smem + L.staging_off,
-                             tmem_full, tmem_empty, bias_full, pe);
-      } else
-      switch (p.mode) {
-        case 1:
-          epilogue_loop<1>(p, pc.n, pc.tile0, pc.sub_base, m0, tt0, pc.zero_from, e, lane, tmem_base, bias_smem, share,
-                           tmem_full, tmem_empty, bias_full, pe);
-          break;
-        case 2:
-          epilogue_loop<2>(p, pc.n, pc.tile0, pc.sub_base, m0, tt0, pc.zero_from, e, lane, tmem_base, bias_smem, share,
-                           tmem_full, tmem_empty, bias_full, pe);
-          break;
-        case 3:
-          epilogue_loop<3>(p, pc.n, pc.tile0, pc.sub_base, m0, tt0, pc.zero_from, e, lane, tmem_base, bias_smem, share,
-                           tmem_full, tmem_empty, bias_full, pe);
-          break;
-        case 4:
-          epilogue_loop<4>(p, pc.n, pc.tile0, pc.sub_base, m0, tt0, pc.zero_from, e, lane, tmem_base, bias_smem, share,
-                           tmem_full, tmem_empty, bias_full, pe);
-          break;
-        case 5:
-          epilogue_loop<5>(p, pc.n, pc.tile0, pc.sub_base, m0, tt0, pc.zero_from, e, lane, tmem_base, bias_smem, share,
-                           tmem_full, tmem_empty, bias_full, pe);
-          break;
-        default:
-          epilogue_loop<0>(p, pc.n, pc.tile0, pc.sub_base, m0, tt0, pc.zero_from, e, lane, tmem_base, bias_smem, share,
-                           tmem_full, tmem_empty, bias_full, pe);
-          break;
+      for (int pi = 0; pi < n_pieces; ++pi) {
+        const Piece pc = piece_tab[pi];
+        run_epilogue_piece<DENSE, PAIR>(p, pc.n, pc.tile0, pc.sub_base, pc.rb * BM, tt0, pc.zero_from, e, lane, tmem_base, bias_smem, share,
+                                        smem + L.staging_off, tmem_full, tmem_empty, bias_full, pe);
+        tt0 += pc.n;
       }
-      tt0 += pc.n;
     }
   }
 
