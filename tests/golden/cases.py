@@ -196,3 +196,27 @@ def sparse_from_dense(latent: np.ndarray):
         vals[b, : len(j)] = v[o]
         idx[b, : len(j)] = j[o]
     return vals, idx
+
+
+# training-side fixtures: case name -> loss weight used by tests/golden/make_golden_train.py
+TRAIN_BSAE = {"bsae_soft_d64_h2048": 0.3, "bsae_soft_d32_h1024_8b": 0.05, "bsae_soft_d512_h4096": 1.0}   # polarize_lambda
+TRAIN_QSAE = {"qsae_d64_h2048": 1e-3, "qsae_d64_h1024_dense_nobias": 1e-3, "qsae_d512_h4096": 1e-3}      # sparsity_lambda
+
+RIGL_CASES = {
+    "rigl_d64_h2048": dict(D=64, H=2048, B=32, seed=61, sparsity=0.7, f_decay=0.3),
+    "rigl_d32_h1024_ties": dict(D=32, H=1024, B=16, seed=62, sparsity=0.5, f_decay=0.1, quantise=True),
+}
+
+
+def rigl_inputs(cfg):
+    rng = np.random.default_rng(cfg["seed"])
+    D, H, B = cfg["D"], cfg["H"], cfg["B"]
+    w = (0.4824 * rng.standard_normal((D, H))).astype(F32)
+    if cfg.get("quantise"):
+        # |w| on a 1/64 grid: many equal magnitudes, so the drop threshold removes whole tie groups (ternary.py:67-69)
+        w = (np.round(w * 64) / 64).astype(F32)
+    act = np.maximum(rng.standard_normal((B, H)), 0).astype(F32) + F32(1e-3)   # no exact-zero column means
+    grad = rng.standard_normal((B, D)).astype(F32)
+    return dict(w=w, act=act, grad=grad)
+
+
