@@ -444,6 +444,65 @@ int qsae_bsae_wait_host(qsae_bsae_plan* plan, int ticket);
  * Values / indices are always float32 / int32. */
 int qsae_bsae_plan_set_io(qsae_bsae_plan* plan, int x_is_bf16, int recon_mode);
 
+/* ---------------------------------------------------------------------------------------
+ * Training-side pieces adjacent to the forward. The reference gets them from eager autograd over
+ * dense [B, H] latents; these work on the sparse forward quantities. Gradient outputs ACCUMULATE (+=) unless stated,
+ * like torch's .grad. Sums that join by atomics agree with a serial sum to fp32 rounding (order not fixed).
+ * ------------------------------------------------------------------------------------- */
+
+/* dst[idx[b,j], :] += scale * coef[b,j] * src[b, :]; dst_col[idx[b,j]] += scale * coef[b,j] (dst_col may be NULL).
+ * coef NULL = 1. idx [B,k] int32, entries < 0 or >= H are skipped. The sparse outer product of
+ *   d loss / d int_w   = q * sparse_latent^T @ grad_recon      (backward of sae/binary.py:38)
+ *   d loss / d W_enc   = grad_z^T @ x, d loss / d b_enc        (backward of the encoder Linear under the top-k mask, :92-99) */
+int qsae_rows_scatter_add(const float* coef, const int32_t* idx, const float* src /* [B,D] */, int B, int k, int D, int H,
+                          float scale, float* dst /* [H,D] */, float* dst_col /* [H] or NULL */, void* stream);
+/* out[b,j] = scale * <g[b,:], rows[idx[b,j], :]> (written, not accumulated; 0 for skipped entries):
+ *   d loss / d latent at the k kept positions = q * grad_recon @ int_w^T restricted to the mask (sae/binary.py:38,99) */
+int qsae_rows_gather_dot(const float* g /* [B,D] */, const float* rows /* [H,D] */, const int32_t* idx, int B, int k, int D,
+                         int H, float scale, float* out /* [B,k] */, void* stream);
+/* out[c] += scale * sum_r src[r,c]: bias gradients; with scale = 1/R the batch means of STEWeights.update_mask
+ * (sae/ternary.py:74-75) */
+int qsae_column_sum(const float* src, int R, int C, float scale, float* out /* [C] */, void* stream);
+/* Chain rule through the sigmoid bits + gradient of polarize_loss (sae/binary.py:26-43):
+ *   grad_logits[h, d n + i] (=|+=) (G[h,d] c_i + gp 2^i (1 - 2p) / (H D n)) p (1 - p),  p = sigmoid(logit), c = [1,2,..,-2^(n-1)]
+ * G [H,D] = d loss / d int_w (NULL = polarize term only); gp_dev: device scalar holding the upstream gradient of
+ * polarize_loss (polarize_lambda under the reference trainer, training/trainer.py:150), NULL = use gp_host.
+ * accumulate 0: overwrite, 1: += */
+int qsae_bsae_logit_grad(const float* logits, const float* G, int H, int D, int n_bits, const float* gp_dev, float gp_host,
+                         int accumulate, float* grad_logits /* [H, D*n_bits] */, void* stream);
+
+/* STE backward of QuantizedMatryoshkaDecoder.forward wrt weight / weight_mirror (sae/quantized_matryoshka.py:94-121,
+ * joint_gradient = False) and apply_secant_grad (:145-190), over the active lists exported by
+ * qsae_matryoshka_forward_active.
+ * step 1 (scatter): M[h,:] += grad_levels[level(h)][b,:] for every active (b,h); z2[h] += 1      (M, z2 caller-zeroed)
+ * step 2 (finish):  grad_w[h,d]  += (alpha[h] M[h,d] - sec[h] Bsign(w[h,d])) s'(w[h,d]), same for the mirror, with
+ *                   sec[h] = c m z2[h] alpha[h]^2 (c = 1/B/D; m = n_bits - level if joint_bits = n_bits > 0, else 1);
+ *                   M NULL = secant term only (apply_secant_grad), z2 NULL = STE term only (loss.backward()). */
+int qsae_matryoshka_backward_scatter(const int32_t* active_idx, int B, int cap, int H, int D,
+                                     const float* const* grad_levels /* host array of n_levels device pointers [B,D] */,
+                                     const int* level_start /* host, n_levels + 1 */, int n_levels, float* M /* [H,D] */,
+                                     int32_t* z2 /* [H] */, void* stream);
+int qsae_matryoshka_backward_finish(const float* w, const float* w_mirror, const float* M, const int32_t* z2,
+                                    const float* alpha /* [H] scale_vector */, const int* level_start /* host */,
+                                    int n_levels, int H, int D, float c, int joint_bits, float* grad_w, float* grad_w_mirror,
+                                    void* stream);
+
+/* RigL mask maintenance of STEWeights (sae/ternary.py:27-90); weight, mask [D,H] float32 (mask holds 0 / 1), both
+ * updated in place; exact order statistics by a three-pass radix select on the device, no host synchronisation.
+ * Ties at a cut that torch.topk leaves unspecified are resolved by the lowest flat index.
+ * qsae_rigl_init_mask:   the n_inactive smallest |w| -> mask 0; weight *= mask                          (:27-39)
+ * qsae_rigl_update_mask: drop every active |w| <= the n_drop-th smallest active |w|; grow the n_grow largest
+ *                        |d_mean[d]| |a_mean[h]| among inactive positions; weight *= mask                (:54-87)
+ *                        a_mean [H] / d_mean [D] = batch means of input_activations / output_grad (NULL: no grow step)
+ * qsae_mul_inplace:      a *= b (mask_grad, :89-90) */
+int qsae_rigl_workspace_bytes(size_t* bytes);
+int qsae_rigl_init_mask(float* weight, float* mask, int D, int H, unsigned long long n_inactive, void* workspace,
+                        size_t workspace_bytes, void* stream);
+int qsae_rigl_update_mask(float* weight, float* mask, const float* a_mean, const float* d_mean, int D, int H,
+                          unsigned long long n_drop, unsigned long long n_grow, void* workspace, size_t workspace_bytes,
+                          void* stream);
+int qsae_mul_inplace(float* a, const float* b, size_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,6 +90,16 @@ SYMBOLS = {
     "qsae_bsae_submit_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp, C.POINTER(_i)]),
     "qsae_bsae_wait_host": (_i, [_vp, _i]),
     "qsae_bsae_plan_set_io": (_i, [_vp, _i, _i]),
+    "qsae_rows_scatter_add": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "qsae_rows_gather_dot": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
+    "qsae_column_sum": (_i, [_vp, _i, _i, _f, _vp, _vp]),
+    "qsae_bsae_logit_grad": (_i, [_vp, _vp, _i, _i, _i, _vp, _f, _i, _vp, _vp]),
+    "qsae_matryoshka_backward_scatter": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_i), _i, _vp, _vp, _vp]),
+    "qsae_matryoshka_backward_finish": (_i, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_i), _i, _i, _i, _f, _i, _vp, _vp, _vp]),
+    "qsae_rigl_workspace_bytes": (_i, [C.POINTER(_sz)]),
+    "qsae_rigl_init_mask": (_i, [_vp, _vp, _i, _i, C.c_ulonglong, _vp, _sz, _vp]),
+    "qsae_rigl_update_mask": (_i, [_vp, _vp, _vp, _vp, _i, _i, C.c_ulonglong, C.c_ulonglong, _vp, _sz, _vp]),
+    "qsae_mul_inplace": (_i, [_vp, _vp, _sz, _vp]),
 }
 
 
@@ -452,6 +462,128 @@ def sq_error_accumulate(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> 
     _need_cuda(a, b, out)
     assert a.dtype == torch.float32 and b.dtype == torch.float32 and out.dtype == torch.float64 and a.numel() == b.numel()
     check(load().qsae_sq_error_accumulate(a.data_ptr(), b.data_ptr(), a.numel(), out.data_ptr(), _stream()))
+
+
+# ---- training-side pieces adjacent to the forward (csrc/train.cu) ----------------
+
+def _f32c(*ts):
+    for t in ts:
+        if t is not None:
+            assert t.dtype == torch.float32 and t.is_contiguous(), "float32 contiguous tensors expected"
+
+
+def rows_scatter_add(coef, idx: torch.Tensor, src: torch.Tensor, dst: torch.Tensor, scale: float = 1.0, dst_col=None) -> None:
+    """dst[idx[b,j], :] += scale * coef[b,j] * src[b, :] (coef None = 1); dst_col[idx[b,j]] += scale * coef[b,j]."""
+    _need_cuda(coef, idx, src, dst, dst_col)
+    _f32c(coef, src, dst, dst_col)
+    assert idx.dtype == torch.int32 and idx.is_contiguous() and idx.dim() == 2 and src.dim() == 2 and dst.dim() == 2
+    B, k = idx.shape
+    assert src.shape[0] == B and src.shape[1] == dst.shape[1] and (coef is None or tuple(coef.shape) == (B, k))
+    check(load().qsae_rows_scatter_add(_ptr(coef), idx.data_ptr(), src.data_ptr(), B, k, src.shape[1], dst.shape[0], float(scale),
+                                       dst.data_ptr(), _ptr(dst_col), _stream()))
+
+
+def rows_gather_dot(g: torch.Tensor, rows: torch.Tensor, idx: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """out[b,j] = scale * <g[b,:], rows[idx[b,j], :]>."""
+    _need_cuda(g, rows, idx)
+    _f32c(g, rows)
+    assert idx.dtype == torch.int32 and idx.is_contiguous() and idx.dim() == 2 and g.shape[1] == rows.shape[1]
+    B, k = idx.shape
+    out = torch.zeros((B, k), dtype=torch.float32, device=g.device)
+    check(load().qsae_rows_gather_dot(g.data_ptr(), rows.data_ptr(), idx.data_ptr(), B, k, g.shape[1], rows.shape[0], float(scale),
+                                      out.data_ptr(), _stream()))
+    return out
+
+
+def column_sum(src: torch.Tensor, scale: float = 1.0, out: torch.Tensor | None = None) -> torch.Tensor:
+    """out[c] += scale * sum_r src[r, c] (out None: a fresh zero vector)."""
+    _need_cuda(src, out)
+    _f32c(src, out)
+    R, Cn = src.shape
+    if out is None:
+        out = torch.zeros(Cn, dtype=torch.float32, device=src.device)
+    check(load().qsae_column_sum(src.data_ptr(), R, Cn, float(scale), out.data_ptr(), _stream()))
+    return out
+
+
+def bsae_logit_grad(logits: torch.Tensor, G: torch.Tensor | None, D: int, n_bits: int, grad_polarize, grad: torch.Tensor,
+                    accumulate: bool) -> None:
+    """grad_logits (=|+=) (G c_i + gp 2^i (1 - 2p) / N) p (1 - p); grad_polarize: python float or 0-d device tensor."""
+    _need_cuda(logits, G, grad)
+    _f32c(logits, G, grad)
+    H = logits.shape[0]
+    assert logits.shape[1] == D * n_bits and grad.shape == logits.shape
+    gp_dev, gp_host = None, 0.0
+    if isinstance(grad_polarize, torch.Tensor):
+        _need_cuda(grad_polarize)
+        assert grad_polarize.dtype == torch.float32 and grad_polarize.numel() == 1
+        gp_dev = grad_polarize
+    else:
+        gp_host = float(grad_polarize)
+    check(load().qsae_bsae_logit_grad(logits.data_ptr(), _ptr(G), H, D, n_bits, _ptr(gp_dev), gp_host, int(accumulate),
+                                      grad.data_ptr(), _stream()))
+
+
+def _level_array(level_start_host):
+    n = len(level_start_host) - 1
+    return n, (C.c_int * (n + 1))(*[int(v) for v in level_start_host])
+
+
+def matryoshka_backward_scatter(active_idx: torch.Tensor, grad_levels, level_start_host, M: torch.Tensor, z2: torch.Tensor) -> None:
+    """M[h,:] += grad_levels[level(h)][b,:] for every active (b,h); z2[h] += 1."""
+    _need_cuda(active_idx, M, z2, *grad_levels)
+    _f32c(M, *grad_levels)
+    assert active_idx.dtype == torch.int32 and active_idx.is_contiguous() and z2.dtype == torch.int32
+    B, cap = active_idx.shape
+    H, D = M.shape
+    n, ls = _level_array(level_start_host)
+    assert len(grad_levels) == n and all(tuple(g.shape) == (B, D) for g in grad_levels)
+    ptrs = (_vp * n)(*[g.data_ptr() for g in grad_levels])
+    check(load().qsae_matryoshka_backward_scatter(active_idx.data_ptr(), B, cap, H, D, ptrs, ls, n, M.data_ptr(), z2.data_ptr(),
+                                                  _stream()))
+
+
+def matryoshka_backward_finish(w, w_mirror, M, z2, alpha, level_start_host, c: float, joint_bits: int, grad_w, grad_w_mirror) -> None:
+    """grad_w += (alpha M - sec Bsign(w)) s'(w), same for the mirror (M None: secant only; z2 None: STE only)."""
+    _need_cuda(w, w_mirror, M, z2, alpha, grad_w, grad_w_mirror)
+    _f32c(w, w_mirror, M, alpha, grad_w, grad_w_mirror)
+    H, D = w.shape
+    n, ls = _level_array(level_start_host)
+    check(load().qsae_matryoshka_backward_finish(w.data_ptr(), w_mirror.data_ptr(), _ptr(M), _ptr(z2), alpha.data_ptr(), ls, n, H, D,
+                                                 float(c), int(joint_bits), grad_w.data_ptr(), grad_w_mirror.data_ptr(), _stream()))
+
+
+def _rigl_ws(device) -> torch.Tensor:
+    n = _sz(0)
+    check(load().qsae_rigl_workspace_bytes(C.byref(n)))
+    return _workspace(device, int(n.value))
+
+
+def rigl_init_mask(weight: torch.Tensor, mask: torch.Tensor, n_inactive: int) -> None:
+    """In place: the n_inactive smallest |w| -> mask 0; weight *= mask (sae/ternary.py:27-39)."""
+    _need_cuda(weight, mask)
+    _f32c(weight, mask)
+    D, H = weight.shape
+    ws = _rigl_ws(weight.device)
+    check(load().qsae_rigl_init_mask(weight.data_ptr(), mask.data_ptr(), D, H, int(n_inactive), ws.data_ptr(), ws.numel(), _stream()))
+
+
+def rigl_update_mask(weight: torch.Tensor, mask: torch.Tensor, a_mean, d_mean, n_drop: int, n_grow: int) -> None:
+    """In place RigL drop / grow step (sae/ternary.py:54-87)."""
+    _need_cuda(weight, mask, a_mean, d_mean)
+    _f32c(weight, mask, a_mean, d_mean)
+    D, H = weight.shape
+    assert a_mean is None or (a_mean.numel() == H and d_mean.numel() == D)
+    ws = _rigl_ws(weight.device)
+    check(load().qsae_rigl_update_mask(weight.data_ptr(), mask.data_ptr(), _ptr(a_mean), _ptr(d_mean), D, H, int(n_drop), int(n_grow),
+                                       ws.data_ptr(), ws.numel(), _stream()))
+
+
+def mul_inplace(a: torch.Tensor, b: torch.Tensor) -> None:
+    _need_cuda(a, b)
+    _f32c(a, b)
+    assert a.numel() == b.numel()
+    check(load().qsae_mul_inplace(a.data_ptr(), b.data_ptr(), a.numel(), _stream()))
 
 
 def pack_ternary(w: torch.Tensor, threshold: float = 0.5, want_bf16: bool = True, want_rows: bool = False):

@@ -270,6 +270,27 @@ const char* coactivation_launch(const int32_t* idx, const float* vals, int B, in
                                 cudaStream_t stream);
 const char* sq_error_launch(const float* a, const float* b, size_t n, double* out, cudaStream_t stream);
 
+// train.cu: training-side kernels adjacent to the forward
+const char* rows_scatter_add_launch(const float* coef, const int32_t* idx, const float* src, int B, int k, int D, int H,
+                                    float scale, float* dst, float* dst_col, cudaStream_t stream);
+const char* rows_gather_dot_launch(const float* g, const float* rows, const int32_t* idx, int B, int k, int D, int H,
+                                   float scale, float* out, cudaStream_t stream);
+const char* column_sum_launch(const float* src, int R, int C, float scale, float* out, cudaStream_t stream);
+const char* bsae_logit_grad_launch(const float* logits, const float* G, int H, int D, int n_bits, const float* gp_dev,
+                                   float gp_host, int accumulate, float* grad, cudaStream_t stream);
+const char* matryoshka_scatter_launch(const int32_t* idx, int B, int cap, int H, int D, const float* const* g_levels,
+                                      const int* level_start, int n_levels, float* M, int32_t* z2, cudaStream_t stream);
+const char* matryoshka_grad_finish_launch(const float* W, const float* Wm, const float* M, const int32_t* z2,
+                                          const float* alpha, const int* level_start, int n_levels, int H, int D, float c,
+                                          int joint_bits, float* gW, float* gWm, cudaStream_t stream);
+size_t rigl_workspace_bytes(int sms);
+const char* rigl_init_mask_launch(float* weight, float* mask, int D, int H, unsigned long long n_inactive, void* ws, int sms,
+                                  cudaStream_t stream);
+const char* rigl_update_mask_launch(float* weight, float* mask, const float* amean, const float* dmean, int D, int H,
+                                    unsigned long long n_drop, unsigned long long n_grow, void* ws, int sms,
+                                    cudaStream_t stream);
+const char* mul_inplace_launch(float* a, const float* b, size_t n, cudaStream_t stream);
+
 // peer.cu: flag-based exchange over CUDA IPC peer memory (dictionary-sharded forward)
 const char* peer_signal_launch(unsigned* const* targets, int n, unsigned value, cudaStream_t stream);
 const char* peer_wait_launch(const unsigned* flags, int n, unsigned value, int* timed_out, cudaStream_t stream);

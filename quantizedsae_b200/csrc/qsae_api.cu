@@ -899,6 +899,117 @@ int qsae_sq_error_accumulate(const float* a, const float* b, size_t n, double* o
 }
 
 // ---------------------------------------------------------------------------------------------
+// training-side pieces adjacent to the forward (train.cu)
+// ---------------------------------------------------------------------------------------------
+int qsae_rows_scatter_add(const float* coef, const int32_t* idx, const float* src, int B, int k, int D, int H, float scale,
+                          float* dst, float* dst_col, void* stream) {
+  if (B < 0 || k < 0 || D <= 0 || H <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "rows_scatter_add: bad shape");
+  if (B == 0 || k == 0) return QSAE_OK;
+  if (!idx || !src || !dst) return fail(QSAE_ERR_INVALID_ARGUMENT, "rows_scatter_add: null pointer");
+  if ((D % 4) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) != 0)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "rows_scatter_add: src / dst must be 16-byte aligned");
+  return launch_status("rows_scatter_add", rows_scatter_add_launch(coef, idx, src, B, k, D, H, scale, dst, dst_col, S(stream)));
+}
+
+int qsae_rows_gather_dot(const float* g, const float* rows, const int32_t* idx, int B, int k, int D, int H, float scale,
+                         float* out, void* stream) {
+  if (B < 0 || k < 0 || D <= 0 || H <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "rows_gather_dot: bad shape");
+  if (B == 0 || k == 0) return QSAE_OK;
+  if (!g || !rows || !idx || !out) return fail(QSAE_ERR_INVALID_ARGUMENT, "rows_gather_dot: null pointer");
+  if ((D % 4) == 0 && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(rows)) & 15) != 0)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "rows_gather_dot: g / rows must be 16-byte aligned");
+  return launch_status("rows_gather_dot", rows_gather_dot_launch(g, rows, idx, B, k, D, H, scale, out, S(stream)));
+}
+
+int qsae_column_sum(const float* src, int R, int C, float scale, float* out, void* stream) {
+  if (R < 0 || C < 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "column_sum: bad shape");
+  if (R == 0 || C == 0) return QSAE_OK;
+  if (!src || !out) return fail(QSAE_ERR_INVALID_ARGUMENT, "column_sum: null pointer");
+  return launch_status("column_sum", column_sum_launch(src, R, C, scale, out, S(stream)));
+}
+
+int qsae_bsae_logit_grad(const float* logits, const float* G, int H, int D, int n_bits, const float* gp_dev, float gp_host,
+                         int accumulate, float* grad_logits, void* stream) {
+  if (H <= 0 || D <= 0 || n_bits < 1 || n_bits > 16) return fail(QSAE_ERR_INVALID_ARGUMENT, "bsae_logit_grad: bad shape");
+  if (!logits || !grad_logits) return fail(QSAE_ERR_INVALID_ARGUMENT, "bsae_logit_grad: null pointer");
+  return launch_status("bsae_logit_grad",
+                       bsae_logit_grad_launch(logits, G, H, D, n_bits, gp_dev, gp_host, accumulate, grad_logits, S(stream)));
+}
+
+static int check_levels(const char* who, const int* level_start, int n_levels, int H) {
+  if (!level_start || n_levels < 1 || n_levels > 8) return fail(QSAE_ERR_INVALID_ARGUMENT, "%s: 1..8 levels", who);
+  if (level_start[0] != 0 || level_start[n_levels] != H) return fail(QSAE_ERR_INVALID_ARGUMENT, "%s: level_start must span [0, H]", who);
+  for (int i = 0; i < n_levels; ++i)
+    if (level_start[i + 1] < level_start[i]) return fail(QSAE_ERR_INVALID_ARGUMENT, "%s: level_start must be non-decreasing", who);
+  return QSAE_OK;
+}
+
+int qsae_matryoshka_backward_scatter(const int32_t* active_idx, int B, int cap, int H, int D, const float* const* grad_levels,
+                                     const int* level_start, int n_levels, float* M, int32_t* z2, void* stream) {
+  if (B < 0 || cap < 0 || H <= 0 || D <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_backward_scatter: bad shape");
+  int rc = check_levels("matryoshka_backward_scatter", level_start, n_levels, H);
+  if (rc != QSAE_OK) return rc;
+  if (B == 0 || cap == 0) return QSAE_OK;
+  if (!active_idx || !grad_levels || !M || !z2) return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_backward_scatter: null pointer");
+  for (int i = 0; i < n_levels; ++i)
+    if (!grad_levels[i] || ((D % 4) == 0 && (reinterpret_cast<uintptr_t>(grad_levels[i]) & 15) != 0))
+      return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_backward_scatter: grad_levels[%d] null or not 16-byte aligned", i);
+  return launch_status("matryoshka_backward_scatter",
+                       matryoshka_scatter_launch(active_idx, B, cap, H, D, grad_levels, level_start, n_levels, M, z2, S(stream)));
+}
+
+int qsae_matryoshka_backward_finish(const float* w, const float* w_mirror, const float* M, const int32_t* z2, const float* alpha,
+                                    const int* level_start, int n_levels, int H, int D, float c, int joint_bits, float* grad_w,
+                                    float* grad_w_mirror, void* stream) {
+  if (H <= 0 || D <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_backward_finish: bad shape");
+  int rc = check_levels("matryoshka_backward_finish", level_start, n_levels, H);
+  if (rc != QSAE_OK) return rc;
+  if (!w || !w_mirror || !alpha || !grad_w || !grad_w_mirror || (!M && !z2))
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka_backward_finish: null pointer");
+  return launch_status("matryoshka_backward_finish",
+                       matryoshka_grad_finish_launch(w, w_mirror, M, z2, alpha, level_start, n_levels, H, D, c, joint_bits,
+                                                     grad_w, grad_w_mirror, S(stream)));
+}
+
+int qsae_rigl_workspace_bytes(size_t* bytes) {
+  if (!bytes) return fail(QSAE_ERR_INVALID_ARGUMENT, "workspace query: null pointer");
+  *bytes = align_up(rigl_workspace_bytes(num_sms()), 256);
+  return QSAE_OK;
+}
+
+static int check_rigl(const char* who, const float* weight, const float* mask, int D, int H, void* ws, size_t ws_bytes) {
+  if (D <= 0 || H <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "%s: bad shape", who);
+  if (static_cast<unsigned long long>(D) * static_cast<unsigned long long>(H) >= 0xffffffffull)
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "%s: D * H must be below 2^32", who);
+  if (!weight || !mask || !ws) return fail(QSAE_ERR_INVALID_ARGUMENT, "%s: null pointer", who);
+  if (ws_bytes < align_up(rigl_workspace_bytes(num_sms()), 256)) return fail(QSAE_ERR_WORKSPACE_TOO_SMALL, "%s: workspace too small", who);
+  return QSAE_OK;
+}
+
+int qsae_rigl_init_mask(float* weight, float* mask, int D, int H, unsigned long long n_inactive, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  int rc = check_rigl("rigl_init_mask", weight, mask, D, H, workspace, workspace_bytes);
+  if (rc != QSAE_OK) return rc;
+  const char* e = rigl_init_mask_launch(weight, mask, D, H, n_inactive, workspace, num_sms(), S(stream));
+  return e ? fail(QSAE_ERR_CUDA, "rigl_init_mask: %s", e) : QSAE_OK;
+}
+
+int qsae_rigl_update_mask(float* weight, float* mask, const float* a_mean, const float* d_mean, int D, int H,
+                          unsigned long long n_drop, unsigned long long n_grow, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  int rc = check_rigl("rigl_update_mask", weight, mask, D, H, workspace, workspace_bytes);
+  if (rc != QSAE_OK) return rc;
+  const char* e = rigl_update_mask_launch(weight, mask, a_mean, d_mean, D, H, n_drop, n_grow, workspace, num_sms(), S(stream));
+  return e ? fail(QSAE_ERR_CUDA, "rigl_update_mask: %s", e) : QSAE_OK;
+}
+
+int qsae_mul_inplace(float* a, const float* b, size_t n, void* stream) {
+  if (n == 0) return QSAE_OK;
+  if (!a || !b) return fail(QSAE_ERR_INVALID_ARGUMENT, "mul_inplace: null pointer");
+  return launch_status("mul_inplace", mul_inplace_launch(a, b, n, S(stream)));
+}
+
+// ---------------------------------------------------------------------------------------------
 // t_sae
 // ---------------------------------------------------------------------------------------------
 int qsae_split_bf16(const float* src, uint16_t* hi, uint16_t* lo, size_t n, void* stream) {

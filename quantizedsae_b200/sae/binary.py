@@ -150,6 +150,7 @@ class BinarySAE(SparseAutoencoder):
         self.return_dense = True             # reference returns a dense [B,H] latent
         self.exact = True                    # fp32 re-scoring of the tensor-core candidates
         self.last_flags = None               # rows whose selection was not certified (exact mode)
+        self.autograd = False                # True: forward attaches the sparse backward (quantizedsae_b200/training.py)
         self._prep = PreparedCache()
 
     def _w_bf16(self):
@@ -181,6 +182,10 @@ class BinarySAE(SparseAutoencoder):
         return SparseLatents(vals, idx, (x.shape[0], self.hidden_dim))
 
     def forward(self, x):
+        if self.autograd and torch.is_grad_enabled():
+            # training (training/trainer.py:143-151): soft-bit forward with the sparse backward attached
+            from .. import training
+            return training.bsae_forward(self, x)
         if self.decoder.resolved_mode() == "int":
             # packed dictionary: encoder + top-k + sparse decode behind one C-ABI call (qsae_bsae_forward)
             x = require_cuda_input(x, self)

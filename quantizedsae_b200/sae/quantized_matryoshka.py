@@ -123,6 +123,19 @@ class QuantizedMatryoshkaDecoder(nn.Module):
         groups = torch.true_divide(counts, float(max(B, 1))).to(torch.float32)   # int64 / float -> float32 in one kernel
         return [groups[i] for i in range(self.n_bits)], [result[i] for i in range(self.n_bits)]
 
+    # ---- training-side (quantizedsae_b200/training.py) --------------------------
+    def ste_backward(self, active_idx, grad_levels, batch_size=None):
+        """Accumulate the STE gradients of weight / weight_mirror / bias for upstream gradients
+        grad_levels[i] = d loss / d result[i] (what loss.backward() leaves there in the reference, :94-124);
+        active_idx [B, cap] from QuantizedMatryoshkaSAE.forward_active. Returns z2 (:137)."""
+        from .. import training
+        return training.qsae_ste_backward(self, active_idx, grad_levels, batch_size)
+
+    def apply_secant_grad(self):
+        """(:145-190) secant correction of weight.grad / weight_mirror.grad from the last ste_backward's context."""
+        from .. import training
+        training.qsae_apply_secant_grad(self)
+
     def forward(self, latent):
         """Reference signature: dense latent [B, H] (sigmoid outputs) -> (latent_group, result)."""
         if not latent.is_cuda:

@@ -57,6 +57,19 @@ class STEWeights(nn.Module):
                               lambda: _lib.pack_ternary(self.weight.detach().contiguous(), self.threshold,
                                                         want_bf16=True, want_rows=True))
 
+    # ---- RigL mask maintenance (sae/ternary.py:27-90; csrc/train.cu) ---------------------------
+    def init_mask(self, sparsity):
+        from .. import training
+        training.rigl_init_mask(self, sparsity)
+
+    def update_mask(self, f_decay, sparsity_rate=0.7):
+        from .. import training
+        training.rigl_update_mask(self, f_decay, sparsity_rate)
+
+    def mask_grad(self):
+        from .. import training
+        training.rigl_mask_grad(self)
+
     def hard_weights(self) -> torch.Tensor:
         """sign(W) * (|W| >= threshold) as float32 [D, H] (sae/ternary.py:46-49)."""
         return self._ternary()[0].float()

@@ -274,3 +274,34 @@ def test_param_key_handles_inference_tensors_and_invalidate_exists():
         m._prep.get("x", (1,), lambda: 1)
         m.invalidate()
         assert m._prep._slots == {}
+
+
+def test_training_side_has_no_cpu_path_and_validates_arguments():
+    """SURVEY 8f-4 entry points: host-side validation of the C ABI and the no-CPU-fallback rule of the module API."""
+    import ctypes as C
+
+    lib = _lib.load()
+    n = C.c_size_t(0)
+    assert lib.qsae_rigl_workspace_bytes(C.byref(n)) == 0 and n.value >= 8192
+    assert lib.qsae_rigl_workspace_bytes(None) == -1
+    assert lib.qsae_rows_scatter_add(None, None, None, 4, 4, 0, 16, 1.0, None, None, None) == -1          # D <= 0
+    assert lib.qsae_rows_scatter_add(None, None, None, 4, 4, 8, 16, 1.0, None, None, None) == -1          # null pointers
+    assert lib.qsae_rows_scatter_add(None, None, None, 0, 4, 8, 16, 1.0, None, None, None) == 0           # empty batch
+    assert lib.qsae_bsae_logit_grad(None, None, 4, 4, 40, None, 0.0, 0, None, None) == -1                 # n_bits range
+    starts = (C.c_int * 3)(0, 5, 9)
+    assert lib.qsae_matryoshka_backward_finish(None, None, None, None, None, starts, 2, 10, 4, 0.0, 0, None, None, None) == -1
+    assert b"span [0, H]" in lib.qsae_last_error()
+    assert lib.qsae_rigl_init_mask(None, None, 70000, 70000, 1, None, 0, None) == -1                      # D * H >= 2^32
+    assert b"2^32" in lib.qsae_last_error()
+    ste = Q.STEWeights(64, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ste.init_mask(0.5)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ste.update_mask(0.3)
+    m = Q.BinarySAE(8, 256, 4.0, 4)
+    m.autograd = True
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(2, 8))
+    dec = Q.QuantizedMatryoshkaDecoder(64, 8, n_bits=4)
+    with pytest.raises(RuntimeError, match="no training context"):
+        dec.apply_secant_grad()
