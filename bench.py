@@ -54,6 +54,10 @@ def parse():
     ap.add_argument("--no-graph", action="store_true",
                     help="launch the kernels directly instead of replaying the step from CUDA graphs (default: graphs for "
                          "batches up to 16384 rows, where launch gaps are a visible share of the step)")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="batches in flight: consecutive steps alternate between this many CUDA streams, so the small kernels "
+                         "around one batch's sweep (prior, merge + decode, tail) overlap the neighbouring batches' (1 = one "
+                         "stream, every step strictly after the previous one; reported beside the headline either way)")
     ap.add_argument("--quick", action="store_true", help="config 1 only: skip the attached configs")
     ap.add_argument("--heavy-tail", action="store_true",
                     help="SURVEY 8d heavy-tail variant of the inputs: 8 of the 512 dimensions scaled by 20")
@@ -321,40 +325,90 @@ class Timer:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t[0])
 
-    def time(self, fn, steps, warmup):
-        """fn(i) enqueues step i. -> ms per step: CUDA events on the launching stream, barrier + synchronize on both
-        sides, max over ranks."""
+    def streams(self, n, always=False):
+        """The timer's worker streams (created once: the library keeps one workspace per stream)."""
+        if n <= 1 and not always:
+            return []
+        pool = self.__dict__.setdefault("_workers", [])
+        while len(pool) < n:
+            pool.append(self.torch.cuda.Stream(device=self.device))
+        return pool[:n]
+
+    def on_streams(self, fn, streams):
+        """fn(i) issued on streams[i % S] (S batches in flight); no streams: fn itself."""
+        if not streams:
+            return fn
         torch = self.torch
+
+        def run(i):
+            with torch.cuda.stream(streams[i % len(streams)]):
+                return fn(i)
+        return run
+
+    def fork(self, streams):
+        """Event on the current stream that every worker stream waits for (start of a timed region)."""
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record()
+        for st in streams:
+            st.wait_event(e)
+        return e
+
+    def join(self, streams):
+        """The current stream waits for everything issued on the worker streams; -> event behind it."""
+        cur = self.torch.cuda.current_stream()
+        for st in streams:
+            ev = self.torch.cuda.Event()
+            ev.record(st)
+            cur.wait_event(ev)
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def time(self, fn, steps, warmup, streams=()):
+        """fn(i) enqueues step i (on its own stream when `streams` are in use: see on_streams / graphs). -> ms per step:
+        CUDA events on the launching stream around the fork / join of the worker streams, barrier + synchronize on both
+        sides, max over ranks."""
         for i in range(warmup):
             fn(i)
+        self.join(streams)
         self.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0 = self.fork(streams)
         for i in range(steps):
             fn(i)
-        e1.record()
+        e1 = self.join(streams)
         self.barrier()
         return self.max_over_ranks(e0.elapsed_time(e1)) / steps
 
-    def graphs(self, fn, n):
+    def graphs(self, fn, n, n_streams=1):
         """One CUDA graph per rotating input: fn(i) captured for i in [0, n) (ctypes launches go to torch's current
-        stream; workspaces are allocated by the warm-up that must precede this, outputs live in the graphs' pool).
-        -> (replay(i), launches per step counted by the library during capture)"""
+        stream; outputs and the library's per-(device, stream) workspaces live in the graphs' pool). With n_streams > 1
+        graph i is captured on, and always replayed on, stream i % n_streams (n is trimmed to a multiple of it), so
+        consecutive steps are in flight together on different streams.
+        -> (replay(i), launches per step counted by the library during capture, graphs, worker streams)"""
         torch = self.torch
         from quantizedsae_b200 import _lib as L
 
         gs = []
         per_step = 0
         pool = torch.cuda.graph_pool_handle()
-        cap = torch.cuda.Stream()          # one capture stream: the library's per-(device, stream) workspace is shared
+        S = max(1, n_streams)
+        caps = self.streams(S, always=True)
+        n = max(S, n - n % S)
         for i in range(n):
             g = torch.cuda.CUDAGraph()
             c0 = L.launch_count()
-            with torch.cuda.graph(g, pool=pool, stream=cap):
+            with torch.cuda.graph(g, pool=pool, stream=caps[i % S]):
                 out = fn(i)
             per_step = L.launch_count() - c0
             gs.append((g, out))
-        return (lambda i: gs[i % n][0].replay()), per_step, gs
+        if S == 1:
+            return (lambda i: gs[i % n][0].replay()), per_step, gs, []
+
+        def replay(i):
+            j = i % n
+            with torch.cuda.stream(caps[j % S]):
+                gs[j][0].replay()
+        return replay, per_step, gs, caps
 
 
 def oracle_rows_check(O, np, x_rows, We, be, k, vals, idx):
@@ -405,35 +459,56 @@ def bench_bsae(args, T, rank, world, device, B, k, steps, warmup, want_e2e=True,
     parity = oracle_rows_check(O, np, xs[0][rows].cpu().numpy(), We.cpu().numpy(), be.cpu().numpy(), k,
                                v[rows].cpu().numpy(), ix[rows].cpu().numpy())
 
-    # ---- headline: device-resident steps, graph replay for small batches
+    # ---- headline: device-resident steps, graph replay for small batches, args.streams batches in flight
     use_graph = graph and not args.no_graph and B <= 16384
+    S = max(1, args.streams)
     launches_per_step = None
     sampler = ClockSampler(device.index)
     if use_graph:
-        replay, launches_per_step, keep = T.graphs(step, n_in)
-        run = replay
+        run, launches_per_step, keep, streams = T.graphs(step, n_in, S)
     else:
-        run = step
+        streams = T.streams(S)
+        run = T.on_streams(step, streams)
     for i in range(warmup):
         run(i)
+    T.join(streams)
     T.barrier()
     if rank == 0:
         sampler.start()
     c0 = L.launch_count()
     T.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0 = T.fork(streams)
     for i in range(steps):
         run(i)
-    e1.record()
+    e1 = T.join(streams)
     T.barrier()
     elapsed_ms = T.max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
     launches = launches_per_step * steps if use_graph else L.launch_count() - c0
     ms = elapsed_ms / steps
     out = {"value": world * B / (ms * 1e-3), "ms_per_step": ms, "elapsed_ms": elapsed_ms, "clocks": clocks, "gpu_launches": int(launches),
-           "launch": ("CUDA graph replay, one graph per rotating input" if use_graph else "direct launches"),
-           "parity_checked": parity, "n_inputs": n_in, "batch": B, "k": k}
+           "launch": ("CUDA graph replay, one graph per rotating input" if use_graph else "direct launches") +
+                     (f"; {S} batches in flight: consecutive steps alternate between {S} streams, every step's kernels are inside "
+                      f"the timed region (fork / join events on the timing stream)" if S > 1 else "; one stream"),
+           "parity_checked": parity, "n_inputs": n_in, "batch": B, "k": k, "streams": S}
+    if S > 1:
+        # the pipelined steps produce the same bits as a lone step, and the strictly serial number is reported beside it
+        if use_graph:
+            torch.cuda.synchronize()
+            same = all(torch.equal(a, b) for a, b in zip((v, ix, rec), keep[0][1]))
+            one, _, keep1, _ = T.graphs(step, n_in, 1)
+        else:
+            with torch.cuda.stream(streams[0]):
+                o2 = step(0)
+            torch.cuda.synchronize()
+            same = all(torch.equal(a, b) for a, b in zip((v, ix, rec), o2))
+            one = step
+        ms1 = T.time(one, steps, warmup)
+        out["pipelined_results_identical"] = bool(same)
+        out["single_stream"] = {"value": world * B / (ms1 * 1e-3), "unit": UNIT, "ms_per_step": ms1,
+                                "note": "the same steps on one stream: each batch's first kernel starts after the previous batch's last"}
+        if use_graph:
+            del keep1
 
     # ---- the same step launched directly (no graph), and in exact mode
     if use_graph:
@@ -620,8 +695,10 @@ def bench_baseline(args, T, rank, world, device, peaks, steps, warmup, B=65536):
     m.return_dense, m.exact = False, False
     n_in = n_rotating(B)
     xs = [make_x(torch, device, B, 50 + s + 100 * rank) for s in range(n_in)]
+    streams = T.streams(args.streams)
     with torch.no_grad():
-        ms = T.time(lambda i: m(xs[i % n_in]), steps, max(3, warmup))
+        ms1 = T.time(lambda i: m(xs[i % n_in]), steps, max(3, warmup))
+        ms = T.time(T.on_streams(lambda i: m(xs[i % n_in]), streams), steps, max(3, warmup), streams) if streams else ms1
         lat, recon = m(xs[0])
         rows = np.arange(0, B, B // 32)[:32]
         parity = oracle_rows_check(O, np, xs[0][rows].cpu().numpy(), m.encoder[0].weight.detach().cpu().numpy(),
@@ -638,6 +715,7 @@ def bench_baseline(args, T, rank, world, device, peaks, steps, warmup, B=65536):
             "roofline": {"bound": "tensor", "achieved": tf, "unit": "TFLOP/s", "frac_burst": tf / peaks["burst"],
                          "frac_sustained": tf / peaks["sustained"], "algorithmic_flops_per_step": flops,
                          "note": "whole forward (encoder sweep + merge + fp32 row-gather decode) against the encoder's 2 B D H flops"},
+            "launch": f"direct launches, {max(1, args.streams)} batches in flight on as many streams", "single_stream_ms": ms1,
             "exact_mode": {"value": world * B / (ems * 1e-3), "ms_per_step": ems},
             "e2e": e2e, "parity_checked": parity, "latents_out": "sparse (values, indices); dense [B,H] not written"}
 
@@ -666,10 +744,15 @@ def bench_tsae(args, T, rank, world, device, peaks, steps, warmup, B=4096):
         ms = T.time(lambda i: m(xs[i % n_in]), steps, max(3, warmup))
         if B <= 16384 and not args.no_graph:
             n_g = min(n_in, 4)        # every graph keeps its own dense h [B, H] (0.5 GB at B = 4096): 4 inputs rotate = 34 MB of x + 2 GB of h > L2
-            replay, _, keep = T.graphs(lambda i: m(xs[i % n_g]), n_g)
+            replay, _, keep, _ = T.graphs(lambda i: m(xs[i % n_g]), n_g)
             ms_direct, ms = ms, T.time(replay, steps, max(3, warmup))
             launch = f"CUDA graph replay of model(x), {n_g} graphs rotating (direct launches: {ms_direct:.4f} ms)"
             del keep
+            if args.streams > 1:
+                replay, _, keep, streams = T.graphs(lambda i: m(xs[i % n_g]), n_g, args.streams)
+                ms_one, ms = ms, T.time(replay, steps, max(3, warmup), streams)
+                launch += f"; {args.streams} batches in flight on as many streams (one stream: {ms_one:.4f} ms)"
+                del keep
         h, recon = m(xs[0])
         rows = np.arange(0, B, B // 16)[:16]
         We, be = m.encoder[0].weight.detach().cpu().numpy(), m.encoder[0].bias.detach().cpu().numpy()
@@ -723,13 +806,26 @@ def bench_qsae(args, T, rank, world, device, peaks, steps, warmup):
                      "mean_l0": float(sum(float(g) for g in groups)), "launch": "direct launches"}
             if B <= 16384 and not args.no_graph and m.last_path == "sparse":
                 # steady state has no host synchronisation (regime known, overflow flag lazy): the forward is capturable
-                replay, _, keep = T.graphs(lambda i: m(xs[i % n_in]), n_in)
+                replay, _, keep, _ = T.graphs(lambda i: m(xs[i % n_in]), n_in)
                 gms = T.time(replay, steps, max(3, warmup))
                 entry["direct_launch_ms"] = ms
                 entry.update({"value": world * B / (gms * 1e-3), "ms_per_step": gms,
                               "launch": "CUDA graph replay of model(x), one graph per rotating input"})
                 ms = gms
                 del keep
+                if args.streams > 1:
+                    replay, _, keep, streams = T.graphs(lambda i: m(xs[i % n_in]), n_in, args.streams)
+                    gms = T.time(replay, steps, max(3, warmup), streams)
+                    entry.update({"value": world * B / (gms * 1e-3), "ms_per_step": gms, "single_stream_ms": ms,
+                                  "launch": entry["launch"] + f"; {args.streams} batches in flight on as many streams"})
+                    ms = gms
+                    del keep
+            elif args.streams > 1 and m.last_path == "sparse":
+                streams = T.streams(args.streams)
+                pms = T.time(T.on_streams(lambda i: m(xs[i % n_in]), streams), steps, max(3, warmup), streams)
+                entry.update({"value": world * B / (pms * 1e-3), "ms_per_step": pms, "single_stream_ms": ms,
+                              "launch": f"direct launches, {args.streams} batches in flight on as many streams"})
+                ms = pms
             if B == 4096:
                 rows = np.arange(0, B, B // 16)[:16]
                 lg, res, _act = O.qsae_forward(xs[0][rows].cpu().numpy(), m.encoder[0].weight.detach().cpu().numpy(),
@@ -782,6 +878,65 @@ def bench_soft_decode(args, T, device, peaks, B=4096, k=65):
             "ms": ms, "algorithmic_bytes_per_token": k * (D * 4 + 8) + D * 4,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
                          "note": "algorithmic bytes; the 67 MB dictionary is largely L2-resident, so values above the HBM peak are L2 hits"}}
+
+
+def bench_training_side(args, T, device, peaks, B=4096):
+    """the training-side kernels at the config-1 shape (soft logits, reference-default k = 65): one b_sae
+    trainer step (forward + loss + backward through the sparse autograd node, training/trainer.py:143-151), its
+    HBM-bound logit-gradient pass, and one RigL update_mask over the [512, 32768] ternary decoder."""
+    import torch
+
+    import quantizedsae_b200 as Q
+    from quantizedsae_b200 import _lib as L
+
+    g = torch.Generator(device=device).manual_seed(21)
+    m = Q.BinarySAE(D, H, 4.0, 4).to(device)
+    with torch.no_grad():
+        m.decoder.weight.copy_(torch.randn((H, D * 4), device=device, generator=g) * 1.5)
+    m.autograd, m.return_dense, m.exact = True, False, True
+    xs = [torch.randn((B, D), device=device, generator=g) for _ in range(4)]
+
+    def step(i):
+        x = xs[i % len(xs)]
+        m.zero_grad(set_to_none=True)
+        _, recon, pol = m(x)
+        (0.5 * torch.nn.functional.mse_loss(recon, x) + 0.1 * pol).backward()
+
+    step_ms = T.time(step, 10, 3)
+    logits = m.decoder.weight.detach()
+    G = torch.randn((H, D), device=device, generator=g)
+    grad = torch.empty_like(logits)
+    lg_ms = T.time(lambda i: L.bsae_logit_grad(logits, G, D, 4, 0.1, grad, False), 20, 3)
+    lg_bytes = H * D * 4 * (4 + 1 + 4)            # logits in, G in, gradient out
+    k = 65
+    vals = torch.randn((B, k), device=device, generator=g)
+    idx = torch.randint(0, H, (B, k), device=device, generator=g, dtype=torch.int32)
+    gr = torch.randn((B, D), device=device, generator=g)
+    dst = torch.zeros((H, D), device=device)
+    sc_ms = T.time(lambda i: L.rows_scatter_add(vals, idx, gr, dst, 0.5), 20, 3)
+    sc_bytes = B * k * D * 4                      # one 16-byte reduction per 4 gradient entries
+    w = torch.randn((D, H), device=device, generator=g) * 0.4824
+    mask = torch.ones_like(w)
+    L.rigl_init_mask(w, mask, int(0.7 * w.numel()))
+    a_mean = torch.rand(H, device=device, generator=g) + 1e-3
+    d_mean = torch.randn(D, device=device, generator=g)
+    n = int(0.1 * 0.3 * w.numel())
+    rg_ms = T.time(lambda i: L.rigl_update_mask(w, mask, a_mean, d_mean, n, n), 10, 3)
+    rg_bytes = w.numel() * 4 * (6 * 2 + 2 + 2 + 4)   # 6 histogram passes + drop apply + tie count over (w, mask); apply reads both, writes both
+    hbm = peaks["hbm_gbs"]
+
+    def rl(nbytes, ms, note):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        return {"ms": ms, "algorithmic_bytes": nbytes, "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s",
+                                                                      "frac": gbs / hbm, "note": note}}
+
+    return {"workload": f"training-side kernels (SURVEY 8f-4) at 512->32768 n_bits=4, soft logits, k={k}, B={B}",
+            "bsae_trainer_step": {"ms": step_ms, "tokens_per_s": B / (step_ms * 1e-3),
+                                  "what": "forward (exact encoder + top-k, soft-row decode, pack for polarize_loss) + 0.5 mse + 0.1 polarize "
+                                          "+ backward to all four parameter gradients"},
+            "bsae_logit_grad_kernel": rl(lg_bytes, lg_ms, "streams logits + d/d int_w in, gradient out: 604 MB"),
+            "rows_scatter_add_kernel": rl(sc_bytes, sc_ms, "atomic traffic B k D 4 bytes into a 67 MB matrix (L2-resident)"),
+            "rigl_update_mask": rl(rg_bytes, rg_ms, "17 launches: two 3-pass radix selects over 16.7 M entries + apply passes")}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -914,6 +1069,9 @@ def run_b200(args, rank, world, local_rank):
             extra["4_q_sae"] = bench_qsae(args, T, rank, world, device, peaks, max(5, steps // 2), 3)
             torch.cuda.empty_cache()
             extra["soft_bit_decode"] = bench_soft_decode(args, T, device, peaks)
+            torch.cuda.empty_cache()
+            extra["f4_training_side"] = bench_training_side(args, T, device, peaks)
+            torch.cuda.empty_cache()
             if world > 1:
                 extra["5_dict_sharded"] = bench_dict_sharded(args, T, rank, world, device, peaks, max(5, steps // 2), 3)
             out["configs"] = extra

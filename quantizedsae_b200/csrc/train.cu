@@ -129,42 +129,65 @@ column_sum_kernel(const float* __restrict__ src, int R, int C, float scale, floa
 // rows because D n_bits % 4 == 0 on this path; the launcher falls back to VEC = 1 otherwise).
 // gp: device scalar (upstream gradient of polarize_loss, e.g. polarize_lambda) or NULL = gp_host.
 // ---------------------------------------------------------------------------------------------
+// blockIdx.x / threadIdx.x pick the group of VEC consecutive logits of a row, blockIdx.y strides over the rows: bit
+// index, bit weight and dictionary column are per-thread constants. The logistic uses the fast exponential /
+// reciprocal (relative error ~1e-6: a gradient, not a thresholded bit -- the packing kernels keep the exact form).
 template <int VEC>
 __global__ void __launch_bounds__(256)
 bsae_logit_grad_kernel(const float* __restrict__ logits, const float* __restrict__ G, int H, int D, int n_bits,
                        const float* __restrict__ gp_dev, float gp_host, int accumulate, float* __restrict__ grad) {
-  const size_t cols = static_cast<size_t>(D) * n_bits;
-  const size_t total = static_cast<size_t>(H) * cols / VEC;
+  const int cols = D * n_bits;
+  const int groups = cols / VEC;
+  const int cg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cg >= groups) return;
   const float gp = (gp_dev != nullptr ? *gp_dev : gp_host) / static_cast<float>(static_cast<double>(H) * cols);
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
-    const size_t first = e * VEC;
-    const size_t h = first / cols;
-    const int col0 = static_cast<int>(first - h * cols);
-    float w[VEC], o[VEC];
-    if (VEC == 4) {
-      const float4 v = reinterpret_cast<const float4*>(logits)[e];
-      w[0] = v.x; w[1 % VEC] = v.y; w[2 % VEC] = v.z; w[3 % VEC] = v.w;
-    } else {
-      w[0] = logits[first];
+  int dcol[VEC];
+  float ci[VEC], gpw[VEC];
+#pragma unroll
+  for (int u = 0; u < VEC; ++u) {
+    const int col = cg * VEC + u;
+    dcol[u] = col / n_bits;
+    const int i = col - dcol[u] * n_bits;
+    const float pw = static_cast<float>(1u << i);
+    ci[u] = (i == n_bits - 1) ? -pw : pw;
+    gpw[u] = gp * pw;
+  }
+  constexpr int R = 2;                                // rows in flight per thread
+  for (int h0 = blockIdx.y; h0 < H; h0 += R * gridDim.y) {
+    float w[R][VEC], up0[R][VEC], old[R][VEC];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int h = h0 + r * gridDim.y;
+      if (h >= H) continue;
+      const size_t e = static_cast<size_t>(h) * groups + cg;
+      if (VEC == 4) {
+        const float4 v = reinterpret_cast<const float4*>(logits)[e];
+        w[r][0] = v.x; w[r][1 % VEC] = v.y; w[r][2 % VEC] = v.z; w[r][3 % VEC] = v.w;
+        if (accumulate) {
+          const float4 o = reinterpret_cast<const float4*>(grad)[e];
+          old[r][0] = o.x; old[r][1 % VEC] = o.y; old[r][2 % VEC] = o.z; old[r][3 % VEC] = o.w;
+        }
+      } else {
+        w[r][0] = logits[e];
+        if (accumulate) old[r][0] = grad[e];
+      }
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) up0[r][u] = G != nullptr ? G[static_cast<size_t>(h) * D + dcol[u]] : 0.f;
     }
 #pragma unroll
-    for (int u = 0; u < VEC; ++u) {
-      const int col = col0 + u;
-      const int d = col / n_bits, i = col - d * n_bits;
-      const float p = logistic(w[u]);
-      const float pw = static_cast<float>(1u << i);
-      const float ci = (i == n_bits - 1) ? -pw : pw;
-      const float up = (G != nullptr ? G[h * D + d] * ci : 0.f) + gp * pw * (1.f - 2.f * p);
-      o[u] = up * p * (1.f - p);
-    }
-    if (VEC == 4) {
-      float4* gp4 = reinterpret_cast<float4*>(grad) + e;
-      float4 r = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
-      if (accumulate) { const float4 old = *gp4; r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w; }
-      *gp4 = r;
-    } else {
-      grad[first] = accumulate ? grad[first] + o[0] : o[0];
+    for (int r = 0; r < R; ++r) {
+      const int h = h0 + r * gridDim.y;
+      if (h >= H) continue;
+      const size_t e = static_cast<size_t>(h) * groups + cg;
+      float o[VEC];
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) {
+        const float p = __frcp_rn(1.0f + __expf(-w[r][u]));
+        o[u] = (up0[r][u] * ci[u] + gpw[u] * (1.f - 2.f * p)) * (p * (1.f - p));
+        if (accumulate) o[u] += old[r][u];
+      }
+      if (VEC == 4) reinterpret_cast<float4*>(grad)[e] = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
+      else grad[e] = o[0];
     }
   }
 }
@@ -287,6 +310,9 @@ __device__ __forceinline__ bool select_key(const SelectSrc& s, size_t i, unsigne
   return true;
 }
 
+// The first pass sees a few exponent bins only (all |w| of a layer share their leading bits): lanes that hit the same
+// bin are merged with __match_any_sync and one lane adds the group's count. Four independent elements per thread and
+// trip keep enough loads in flight to stream at HBM rate.
 template <int MODE>
 __global__ void __launch_bounds__(256)
 select_hist_kernel(SelectSrc s, int shift, int bits, SelectState* st) {
@@ -295,10 +321,24 @@ select_hist_kernel(SelectSrc s, int shift, int bits, SelectState* st) {
   __syncthreads();
   const unsigned int prefix = st->prefix, pmask = st->prefix_mask;
   const unsigned int dmask = (1u << bits) - 1u;
+  const int lane = threadIdx.x & 31;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < s.n; i += stride) {
-    unsigned int key;
-    if (select_key<MODE>(s, i, &key) && (key & pmask) == prefix) atomicAdd(&h[(key >> shift) & dmask], 1u);
+  const size_t first = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (size_t base = first - lane; base < s.n; base += 4 * stride) {      // warp-uniform trip count
+    unsigned int bin[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t i = base + lane + u * stride;
+      unsigned int key;
+      bin[u] = 0xffffffffu;
+      if (i < s.n && select_key<MODE>(s, i, &key) && (key & pmask) == prefix) bin[u] = (key >> shift) & dmask;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (__ballot_sync(0xffffffffu, bin[u] != 0xffffffffu) == 0u) continue;
+      const unsigned int peers = __match_any_sync(0xffffffffu, bin[u]);
+      if (bin[u] != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&h[bin[u]], static_cast<unsigned int>(__popc(peers)));
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < kSelBins; i += blockDim.x)
@@ -310,31 +350,67 @@ __global__ void select_init_kernel(SelectState* st, unsigned long long k) {
   for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) st->hist[i] = 0;
 }
 
-// one thread: the bin that holds rank k, then clear the histogram for the next pass
-__global__ void select_pick_kernel(int shift, int bits, SelectState* st) {
-  __shared__ unsigned int chosen;
-  __shared__ unsigned long long before;
-  if (threadIdx.x == 0) {
-    unsigned long long cum = 0, k = st->k;
-    const int nb = 1 << bits;
-    int b = 0;
-    for (; b < nb; ++b) {
-      const unsigned long long c = st->hist[b];
-      if (cum + c >= k) break;
-      cum += c;
-    }
-    if (b == nb) {           // fewer than k candidates: everything is selected
-      b = nb - 1;
-      st->k = ~0ull;
-    } else if (st->k != ~0ull) {
-      st->k = k - cum;
-    }
-    chosen = static_cast<unsigned int>(b);
-    before = cum;
-    st->prefix |= chosen << shift;
-    st->prefix_mask |= ((1u << bits) - 1u) << shift;
+// Exclusive prefix sums of 2048 counters held 8 per thread by a block of 256 threads (64-bit: 2^32 elements may tie).
+__device__ __forceinline__ unsigned long long block_exclusive_scan_256(unsigned long long local, unsigned long long* total) {
+  __shared__ unsigned long long warp_tot[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned long long incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  unsigned long long base = 0, all = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    if (w < wid) base += warp_tot[w];
+    all += warp_tot[w];
   }
   __syncthreads();
+  *total = all;
+  return base + incl - local;
+}
+
+// the bin that holds rank k (block of 256 threads, 8 bins each), then clear the histogram for the next pass
+__global__ void __launch_bounds__(256) select_pick_kernel(int shift, int bits, SelectState* st) {
+  const int nb = 1 << bits;
+  unsigned int c[8];
+  unsigned long long local = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int b = threadIdx.x * 8 + j;
+    c[j] = b < nb ? st->hist[b] : 0u;
+    local += c[j];
+  }
+  const unsigned long long k = st->k;
+  unsigned long long total;
+  unsigned long long cum = block_exclusive_scan_256(local, &total);
+  __syncthreads();                                   // everybody has read st->k and the histogram
+  if (k != ~0ull && total < k) {                     // fewer than k candidates: everything is selected
+    if (threadIdx.x == 0) {
+      st->k = ~0ull;
+      st->prefix |= static_cast<unsigned int>(nb - 1) << shift;
+      st->prefix_mask |= ((1u << bits) - 1u) << shift;
+    }
+  } else if (k == ~0ull) {
+    if (threadIdx.x == 0) {
+      st->prefix |= static_cast<unsigned int>(nb - 1) << shift;
+      st->prefix_mask |= ((1u << bits) - 1u) << shift;
+    }
+  } else if (cum < k && k <= cum + local) {          // exactly one thread owns rank k
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (cum + c[j] >= k) {
+        st->k = k - cum;
+        st->prefix |= static_cast<unsigned int>(threadIdx.x * 8 + j) << shift;
+        st->prefix_mask |= ((1u << bits) - 1u) << shift;
+        break;
+      }
+      cum += c[j];
+    }
+  }
   for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) st->hist[i] = 0;
 }
 
@@ -368,15 +444,25 @@ select_tie_count_kernel(SelectSrc s, size_t per_block, const SelectState* st, un
   if (threadIdx.x == 0) tie_count[blockIdx.x] = total;
 }
 
-__global__ void select_tie_scan_kernel(unsigned int* tie_count, int nblocks) {
-  if (threadIdx.x == 0) {
-    unsigned long long run = 0;
-    for (int b = 0; b < nblocks; ++b) {
-      const unsigned int c = tie_count[b];
-      tie_count[b] = run > 0xffffffffull ? 0xffffffffu : static_cast<unsigned int>(run);
-      run += c;
-    }
+// exclusive prefix of the per-block tie counts (at most 2048 blocks), total in [nblocks]
+__global__ void __launch_bounds__(256) select_tie_scan_kernel(unsigned int* tie_count, int nblocks) {
+  unsigned int c[8];
+  unsigned long long local = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int b = threadIdx.x * 8 + j;
+    c[j] = b < nblocks ? tie_count[b] : 0u;
+    local += c[j];
   }
+  unsigned long long total;
+  unsigned long long run = block_exclusive_scan_256(local, &total);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int b = threadIdx.x * 8 + j;
+    if (b < nblocks) tie_count[b] = run > 0xffffffffull ? 0xffffffffu : static_cast<unsigned int>(run);
+    run += c[j];
+  }
+  if (threadIdx.x == 0) tie_count[nblocks] = total > 0xffffffffull ? 0xffffffffu : static_cast<unsigned int>(total);
 }
 
 // selected -> new_value in mask (init_mask: 0, grow: 1); then weight *= mask over the whole range (:39, :86-87)
@@ -393,6 +479,16 @@ select_apply_kernel(SelectSrc s, size_t per_block, const SelectState* st, const 
   const unsigned long long take = st->k;
   const size_t lo = static_cast<size_t>(blockIdx.x) * per_block;
   const size_t hi = lo + per_block < s.n ? lo + per_block : s.n;
+  if (tie_base[blockIdx.x + 1] == tie_base[blockIdx.x]) {
+    // no element of this range sits exactly on the threshold (the usual case): plain elementwise pass
+    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      unsigned int key = 0;
+      float m = mask[i];
+      if (select_key<MODE>(s, i, &key) && key < T) { m = new_value; mask[i] = m; }
+      if (weight != nullptr && m == 0.f) weight[i] = 0.f * weight[i];
+    }
+    return;
+  }
   for (size_t base = lo; base < hi; base += blockDim.x) {
     const size_t i = base + threadIdx.x;
     unsigned int key = 0;
@@ -453,7 +549,7 @@ const char* run_tie_apply(const SelectSrc& s, const SelectState* st, unsigned in
   per = (per + 255) / 256 * 256;
   const int nb = static_cast<int>((s.n + per - 1) / per);
   select_tie_count_kernel<MODE><<<nb, 256, 0, stream>>>(s, per, st, tie_scratch);
-  select_tie_scan_kernel<<<1, 32, 0, stream>>>(tie_scratch, nb);
+  select_tie_scan_kernel<<<1, 256, 0, stream>>>(tie_scratch, nb);
   select_apply_kernel<MODE><<<nb, 256, 0, stream>>>(s, per, st, tie_scratch, new_value, mask, weight);
   count_launches(3);
   return cuda_err(cudaGetLastError());
@@ -501,10 +597,15 @@ const char* bsae_logit_grad_launch(const float* logits, const float* G, int H, i
   const size_t n = static_cast<size_t>(H) * cols;
   if (n == 0) return nullptr;
   const bool vec = (cols & 3) == 0 && ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(grad)) & 15) == 0;
+  const size_t groups = vec ? cols / 4 : cols;
+  const int gx = static_cast<int>((groups + 255) / 256);
+  int gy = (148 * 16 + gx - 1) / gx;             // ~16 blocks per SM; every block walks H / gy rows
+  if (gy > H) gy = H;
+  if (gy > 65535) gy = 65535;
   if (vec)
-    bsae_logit_grad_kernel<4><<<grid_for(n / 4, 256, 148 * 16), 256, 0, stream>>>(logits, G, H, D, n_bits, gp_dev, gp_host, accumulate, grad);
+    bsae_logit_grad_kernel<4><<<dim3(gx, gy), 256, 0, stream>>>(logits, G, H, D, n_bits, gp_dev, gp_host, accumulate, grad);
   else
-    bsae_logit_grad_kernel<1><<<grid_for(n, 256, 148 * 16), 256, 0, stream>>>(logits, G, H, D, n_bits, gp_dev, gp_host, accumulate, grad);
+    bsae_logit_grad_kernel<1><<<dim3(gx, gy), 256, 0, stream>>>(logits, G, H, D, n_bits, gp_dev, gp_host, accumulate, grad);
   return cuda_err(cudaGetLastError());
 }
 
@@ -538,7 +639,7 @@ const char* matryoshka_grad_finish_launch(const float* W, const float* Wm, const
 }
 
 size_t rigl_workspace_bytes(int sms) {
-  return 1024 + sizeof(SelectState) + static_cast<size_t>(sms) * 8 * sizeof(unsigned int);
+  return 1024 + sizeof(SelectState) + (static_cast<size_t>(sms) * 8 + 2) * sizeof(unsigned int);
 }
 
 const char* rigl_init_mask_launch(float* weight, float* mask, int D, int H, unsigned long long n_inactive, void* ws, int sms,

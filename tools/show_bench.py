@@ -28,6 +28,8 @@ def walk(name, c, ind=2):
               (f", parity {c['parity_checked']}" if 'parity_checked' in c else "") + (f", comm {c['comm_ms']*1e3:.0f} us" if 'comm_ms' in c else ""))
     elif "ms" in c and "roofline" in c:
         print(" " * ind + f"{name}: {c['ms']*1e3:.1f} us, {c['roofline']['achieved']:.0f} {c['roofline']['unit']} frac {c['roofline']['frac']:.2f}")
+    elif "ms" in c and "tokens_per_s" in c:
+        print(" " * ind + f"{name}: {c['ms']*1e3:.1f} us, {c['tokens_per_s']/1e6:.2f} M tokens/s")
     for k, v in c.items():
         if isinstance(v, dict) and k not in ("roofline", "exact_mode", "e2e", "clocks"):
             walk(k, v, ind + 2)
