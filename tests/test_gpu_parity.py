@@ -1244,3 +1244,41 @@ def test_exact_dense_encoder_split_passes(cuda_device, B, H, D):
     # tighter: the split passes are as good as an fp32 matmul (products exact, fp32 accumulation)
     assert np.max(np.abs(got - h64)) <= 4e-6 * max(1.0, np.max(np.abs(h64)))
     assert_recon_close(recon.cpu().numpy(), (h64 @ O.ternarize(wd).T.astype(np.float64)).astype(np.float32))
+
+
+def test_stream_pipeline_matches_serial_forwards(cuda_device):
+    """Two batches in flight on two streams (quantizedsae_b200/pipeline.py) give the bits of the serial loop."""
+    from quantizedsae_b200.pipeline import StreamPipeline
+
+    cfg = cases.BSAE_CASES["bsae_polar_d512_h4096"]
+    inp = cases.bsae_inputs(cfg)
+    m = Q.BinarySAE(cfg["D"], cfg["H"], cfg["gamma"], cfg["n_bits"]).to(cuda_device)
+    m.load_state_dict({"encoder.0.weight": T(inp["We"], cuda_device), "encoder.0.bias": T(inp["be"], cuda_device),
+                       "decoder.weight": T(inp["logits"], cuda_device), "decoder.bias": T(inp["bd"], cuda_device)}, strict=True)
+    m.return_dense = False
+    rng = np.random.default_rng(3)
+    batches = [T(cases.round_bf16(rng.standard_normal((300 + 17 * i, cfg["D"])).astype(np.float32)), cuda_device) for i in range(7)]
+    pipe = StreamPipeline(m, n_streams=2)
+    got = list(pipe.map(batches))                      # the first batch also builds the prepared weights
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        want = [m(b) for b in batches]
+    torch.cuda.synchronize()
+    assert len(got) == len(want)
+    for (gl, gr, gp), (wl, wr, wp) in zip(got, want):
+        assert torch.equal(gl.indices, wl.indices) and torch.equal(gl.values, wl.values)
+        assert torch.equal(gr, wr) and float(gp) == float(wp)
+    # a q_sae model through the same pipeline, three streams
+    qc = cases.QSAE_CASES["qsae_d512_h4096"]
+    qi = cases.qsae_inputs(qc)
+    q = Q.QuantizedMatryoshkaSAE(qc["D"], qc["H"], 32, qc["abs_range"], qc["n_bits"], qc["allow_bias"]).to(cuda_device)
+    q.load_state_dict({"encoder.0.weight": T(qi["We"], cuda_device), "encoder.0.bias": T(qi["be"], cuda_device),
+                       "decoder.weight": T(qi["W"], cuda_device), "decoder.weight_mirror": T(qi["Wm"], cuda_device),
+                       "decoder.bias": T(qi["bd"], cuda_device)}, strict=True)
+    qb = [T(cases.round_bf16(rng.standard_normal((200, qc["D"])).astype(np.float32)), cuda_device) for _ in range(5)]
+    got = list(StreamPipeline(q, n_streams=3).map(qb))
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        want = [q(b) for b in qb]
+    for (gg, gl), (wg, wl) in zip(got, want):
+        assert all(torch.equal(a, b) for a, b in zip(gl, wl)) and all(float(a) == float(b) for a, b in zip(gg, wg))
