@@ -267,6 +267,13 @@ int qsae_coactivation(const int32_t* idx, const float* vals, int B, int cap, int
                       void* stream);
 int qsae_sq_error_accumulate(const float* a, const float* b, size_t n, double* out /* device scalar */, void* stream);
 
+/* Dense [B, H] latents (what the reference hands to its decoders: sae/binary.py:24, sae/quantized_matryoshka.py:47)
+ * -> sparse per-row lists, ascending latent order. mode 0: entries != 0; mode 1: entries > thr (q_sae activity, :99).
+ * Any of idx [B, cap] (-1 padded), vals [B, cap] (0 padded), pairs [B, cap, 2] (the list format of
+ * qsae_decode_matryoshka_lists) may be NULL; cnt [B] counts every hit, stored or not (cap = 0: count only). */
+int qsae_compact_dense(const float* dense, int B, int H, int mode, float thr, int cap, int32_t* idx, float* vals,
+                       int32_t* pairs, int32_t* cnt, void* stream);
+
 /* Dense path of the same forward, for any activity level (the sparse path reports *overflow when a row
  * has more active latents than its survivor lists hold -- e.g. an untrained model, ~50 % active):
  * dense pre-activations, A = (sigmoid(z) > 0.5) * scale as bf16 hi + lo, and one tcgen05 GEMM per level

@@ -54,6 +54,7 @@ SYMBOLS = {
     "qsae_activation_counts": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "qsae_coactivation": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "qsae_sq_error_accumulate": (_i, [_vp, _vp, _sz, _vp, _vp]),
+    "qsae_compact_dense": (_i, [_vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "qsae_max_row_norm": (_i, [_vp, _i, _i, _vp, _vp]),
     "qsae_residual_update": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "qsae_unpack_matryoshka_t": (_i, [_vp, _i, _i, _vp, _vp]),
@@ -584,6 +585,25 @@ def mul_inplace(a: torch.Tensor, b: torch.Tensor) -> None:
     _f32c(a, b)
     assert a.numel() == b.numel()
     check(load().qsae_mul_inplace(a.data_ptr(), b.data_ptr(), a.numel(), _stream()))
+
+
+def compact_dense(dense: torch.Tensor, mode: int, thr: float = 0.0, want_vals: bool = False, want_pairs: bool = False):
+    """Dense [B, H] -> (idx [B, cap] int32 (-1 padded, ascending) | pairs [B, cap, 2], vals [B, cap] | None, cnt [B] int32).
+    mode 0: entries != 0, mode 1: entries > thr. Two launches (count, then fill) with one host read of the largest
+    count between them: the output shape depends on the data."""
+    _need_cuda(dense)
+    assert dense.dtype == torch.float32 and dense.is_contiguous() and dense.dim() == 2
+    B, H = dense.shape
+    cnt = torch.zeros((B,), dtype=torch.int32, device=dense.device)
+    lib = load()
+    check(lib.qsae_compact_dense(dense.data_ptr(), B, H, mode, float(thr), 0, None, None, None, cnt.data_ptr(), _stream()))
+    cap = max(1, int(cnt.max().item())) if B else 1
+    idx = None if want_pairs else torch.empty((B, cap), dtype=torch.int32, device=dense.device)
+    pairs = torch.empty((B, cap, 2), dtype=torch.int32, device=dense.device) if want_pairs else None
+    vals = torch.empty((B, cap), dtype=torch.float32, device=dense.device) if want_vals else None
+    check(lib.qsae_compact_dense(dense.data_ptr(), B, H, mode, float(thr), cap, _ptr(idx), _ptr(vals), _ptr(pairs), cnt.data_ptr(),
+                                 _stream()))
+    return (pairs if want_pairs else idx), vals, cnt
 
 
 def pack_ternary(w: torch.Tensor, threshold: float = 0.5, want_bf16: bool = True, want_rows: bool = False):

@@ -95,7 +95,89 @@ sq_error_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t
   if (threadIdx.x == 0) atomicAdd(out, s[0]);
 }
 
+
+// Dense [B, H] latents -> per-row lists of the entries with (mode 0) v != 0 or (mode 1) v > thr, in ascending latent
+// order: idx [B, cap] (-1 padded) and / or vals [B, cap] (0 padded) and / or pairs [B, cap, 2] (second component = latent,
+// the format of qsae_decode_matryoshka_lists); cnt [B] counts every hit, stored or not. The entry the reference-shaped
+// decoders take when a caller hands them the dense matrix (sae/binary.py:24, sae/quantized_matryoshka.py:47,99).
+__global__ void __launch_bounds__(256)
+compact_dense_kernel(const float* __restrict__ dense, int B, int H, int mode, float thr, int cap, int32_t* __restrict__ idx,
+                     float* __restrict__ vals, int32_t* __restrict__ pairs, int32_t* __restrict__ cnt) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const bool vec = (H & 3) == 0 && (reinterpret_cast<uintptr_t>(dense) & 15) == 0;
+  for (int row = warp; row < B; row += nwarps) {
+    const float* r = dense + static_cast<size_t>(row) * H;
+    int n = 0;
+    const int step = vec ? 128 : 32;
+    for (int base = 0; base < H; base += step) {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      int first, nv;
+      if (vec) {
+        first = base + lane * 4;
+        nv = first < H ? 4 : 0;
+        if (nv) {
+          const float4 q = *reinterpret_cast<const float4*>(r + first);
+          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        }
+      } else {
+        first = base + lane;
+        nv = first < H ? 1 : 0;
+        if (nv) v[0] = r[first];
+      }
+      bool hit[4];
+      int mine = 0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        hit[c] = c < nv && (mode == 0 ? v[c] != 0.f : v[c] > thr);
+        mine += hit[c] ? 1 : 0;
+      }
+      // exclusive prefix of the per-lane hit counts (ascending latent order = lane-major, then component)
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      int pos = n + incl - mine;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (hit[c]) {
+          if (pos < cap) {
+            const size_t o = static_cast<size_t>(row) * cap + pos;
+            if (idx) idx[o] = first + c;
+            if (vals) vals[o] = v[c];
+            if (pairs) { pairs[2 * o] = 0; pairs[2 * o + 1] = first + c; }
+          }
+          ++pos;
+        }
+      }
+      n += total;
+    }
+    (void)lt;
+    for (int e = min(n, cap) + lane; e < cap; e += 32) {       // padding
+      const size_t o = static_cast<size_t>(row) * cap + e;
+      if (idx) idx[o] = -1;
+      if (vals) vals[o] = 0.f;
+      if (pairs) { pairs[2 * o] = 0; pairs[2 * o + 1] = 0; }
+    }
+    if (lane == 0) cnt[row] = n;
+  }
+}
+
 }  // namespace
+
+const char* compact_dense_launch(const float* dense, int B, int H, int mode, float thr, int cap, int32_t* idx, float* vals,
+                                 int32_t* pairs, int32_t* cnt, cudaStream_t stream) {
+  if (B == 0) return nullptr;
+  int blocks = (B + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  compact_dense_kernel<<<blocks, 256, 0, stream>>>(dense, B, H, mode, thr, cap, idx, vals, pairs, cnt);
+  return cuda_err(cudaGetLastError());
+}
 
 const char* activation_counts_launch(const int32_t* idx, const float* vals, int B, int cap, int H,
                                      unsigned long long* counts, cudaStream_t stream) {

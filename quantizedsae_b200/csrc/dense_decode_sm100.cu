@@ -17,6 +17,7 @@
 
 #include "kernels.h"
 #include "ptx_sm100.cuh"
+#include "tmap_cache.cuh"
 
 namespace qsae {
 
@@ -229,13 +230,20 @@ bool make_tmap(CUtensorMap* map, const void* base, int rows, int cols, int ld, i
       return false;
     enc = reinterpret_cast<EncodeTiledFn>(ptr);
   }
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};   // row pitch in bytes (a K sub-range keeps the full pitch)
-  cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  const TmapKey key{base, static_cast<unsigned long long>(rows), static_cast<unsigned long long>(cols),
+                    static_cast<unsigned long long>(ld) * 2, static_cast<unsigned int>(BK), static_cast<unsigned int>(box_rows),
+                    static_cast<int>(CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), static_cast<int>(CU_TENSOR_MAP_SWIZZLE_128B),
+                    tmap_current_device()};
+  EncodeTiledFn fn = enc;
+  return tmap_cache().get(key, map, [&](CUtensorMap* m) {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};   // row pitch in bytes (a K sub-range keeps the full pitch)
+    cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  });
 }
 
 template <int N_TILES, bool PAIR>

@@ -31,9 +31,15 @@
 
 #include "kernels.h"
 #include "ptx_sm100.cuh"
+#include "tmap_cache.cuh"
 #include "topk_common.cuh"
 
 namespace qsae {
+
+TmapCache& tmap_cache() {
+  static TmapCache cache;
+  return cache;
+}
 
 namespace {
 
@@ -1203,13 +1209,17 @@ bool make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, c
                   int box_cols, int box_rows, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return false;
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * elem_bytes};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, dtype, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
+  const TmapKey key{base, static_cast<unsigned long long>(rows), static_cast<unsigned long long>(cols),
+                    static_cast<unsigned long long>(cols) * elem_bytes, static_cast<unsigned int>(box_cols),
+                    static_cast<unsigned int>(box_rows), static_cast<int>(dtype), static_cast<int>(swizzle), tmap_current_device()};
+  return tmap_cache().get(key, map, [&](CUtensorMap* m) {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * elem_bytes};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(m, dtype, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  });
 }
 // bf16 operand tile: {64 x box_rows} box, 128-byte swizzle
 bool make_tmap_bf16(CUtensorMap* map, const void* base, int rows, int cols, int box_rows) {

@@ -269,6 +269,8 @@ const char* activation_counts_launch(const int32_t* idx, const float* vals, int 
 const char* coactivation_launch(const int32_t* idx, const float* vals, int B, int cap, int H, int32_t* cooc,
                                 cudaStream_t stream);
 const char* sq_error_launch(const float* a, const float* b, size_t n, double* out, cudaStream_t stream);
+const char* compact_dense_launch(const float* dense, int B, int H, int mode, float thr, int cap, int32_t* idx, float* vals,
+                                 int32_t* pairs, int32_t* cnt, cudaStream_t stream);
 
 // train.cu: training-side kernels adjacent to the forward
 const char* rows_scatter_add_launch(const float* coef, const int32_t* idx, const float* src, int B, int k, int D, int H,

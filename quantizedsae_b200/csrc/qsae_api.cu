@@ -898,6 +898,14 @@ int qsae_sq_error_accumulate(const float* a, const float* b, size_t n, double* o
   return launch_status("sq_error", sq_error_launch(a, b, n, out, S(stream)));
 }
 
+int qsae_compact_dense(const float* dense, int B, int H, int mode, float thr, int cap, int32_t* idx, float* vals, int32_t* pairs,
+                       int32_t* cnt, void* stream) {
+  if (B < 0 || H <= 0 || cap < 0 || (mode != 0 && mode != 1)) return fail(QSAE_ERR_INVALID_ARGUMENT, "compact_dense: bad arguments");
+  if (B == 0) return QSAE_OK;
+  if (!dense || !cnt) return fail(QSAE_ERR_INVALID_ARGUMENT, "compact_dense: null pointer");
+  return launch_status("compact_dense", compact_dense_launch(dense, B, H, mode, thr, cap, idx, vals, pairs, cnt, S(stream)));
+}
+
 // ---------------------------------------------------------------------------------------------
 // training-side pieces adjacent to the forward (train.cu)
 // ---------------------------------------------------------------------------------------------

@@ -120,18 +120,14 @@ class binary_decoder(nn.Module):
 
 
 def sparsify_dense(latent: torch.Tensor) -> SparseLatents:
-    """Dense [B, H] latent (as the reference passes to its decoder) -> SparseLatents, keeping the
-    non-zeros of each row. Uses the dense top-k kernel on |latent| to locate them."""
+    """Dense [B, H] latent (as the reference passes to its decoder, sae/binary.py:24) -> SparseLatents holding the
+    non-zeros of each row in ascending latent order (qsae_compact_dense: one counting and one filling launch)."""
     if not latent.is_cuda:
         raise RuntimeError("binary_decoder.forward needs CUDA tensors (no CPU fallback)")
     latent = latent.contiguous().float()
-    nnz = int((latent != 0).sum(1).max().item()) if latent.numel() else 0
-    k = max(1, nnz)
-    if k > _lib.QSAE_MAX_K_LARGE:
-        raise RuntimeError(f"dense latent with {nnz} non-zeros per row exceeds QSAE_MAX_K_LARGE={_lib.QSAE_MAX_K_LARGE}")
-    _, idx = _lib.topk_dense(latent.abs(), k)
-    vals = torch.gather(latent, 1, idx.long())
-    idx = torch.where(vals != 0, idx, torch.full_like(idx, -1))
+    idx, vals, cnt = _lib.compact_dense(latent, 0, want_vals=True)
+    if idx.shape[1] > _lib.QSAE_MAX_K_LARGE:
+        raise RuntimeError(f"dense latent with {idx.shape[1]} non-zeros per row exceeds QSAE_MAX_K_LARGE={_lib.QSAE_MAX_K_LARGE}")
     return SparseLatents(vals, idx, tuple(latent.shape))
 
 

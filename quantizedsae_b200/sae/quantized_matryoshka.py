@@ -140,13 +140,10 @@ class QuantizedMatryoshkaDecoder(nn.Module):
         """Reference signature: dense latent [B, H] (sigmoid outputs) -> (latent_group, result)."""
         if not latent.is_cuda:
             raise RuntimeError("QuantizedMatryoshkaDecoder runs only on CUDA (no CPU fallback)")
-        active = latent > 0.5                                           # (:99)
-        B, H = active.shape
-        cnt = active.sum(1).to(torch.int32)
-        cap = max(1, int(cnt.max().item()))
-        order = torch.argsort(active.to(torch.uint8), dim=1, descending=True, stable=True)[:, :cap]
-        lists = torch.zeros((B, cap, 2), dtype=torch.int32, device=latent.device)
-        lists[:, :, 1] = order.to(torch.int32)
+        B, H = latent.shape
+        # active = latent > 0.5 (:99), compacted into per-row lists by qsae_compact_dense
+        lists, _, cnt = _lib.compact_dense(latent.contiguous().float(), 1, 0.5, want_pairs=True)
+        cap = lists.shape[1]
         packed, scale = self._packed()
         ls, _ = self._levels()
         result, counts = _lib.decode_matryoshka_lists(lists, cnt.contiguous(), cap, packed, scale, ls, self.n_bits,

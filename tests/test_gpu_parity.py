@@ -1282,3 +1282,25 @@ def test_stream_pipeline_matches_serial_forwards(cuda_device):
         want = [q(b) for b in qb]
     for (gg, gl), (wg, wl) in zip(got, want):
         assert all(torch.equal(a, b) for a, b in zip(gl, wl)) and all(float(a) == float(b) for a, b in zip(gg, wg))
+
+
+@pytest.mark.parametrize("B,H", [(1, 5), (7, 130), (33, 2048), (5, 4099)])
+def test_compact_dense_vs_numpy(cuda_device, B, H):
+    rng = np.random.default_rng(B * 31 + H)
+    a = rng.standard_normal((B, H)).astype(np.float32)
+    a[rng.random((B, H)) < 0.9] = 0.0
+    a[0, :] = 0.0                                                # an empty row
+    idx, vals, cnt = L.compact_dense(T(a, cuda_device), 0, want_vals=True)
+    idx, vals, cnt = idx.cpu().numpy(), vals.cpu().numpy(), cnt.cpu().numpy()
+    assert np.array_equal(cnt, (a != 0).sum(1))
+    assert idx.shape[1] == max(1, cnt.max())
+    for b in range(B):
+        nz = np.nonzero(a[b])[0]
+        assert np.array_equal(idx[b, :len(nz)], nz) and np.all(idx[b, len(nz):] == -1)
+        assert np.array_equal(vals[b, :len(nz)], a[b, nz]) and np.all(vals[b, len(nz):] == 0)
+    pairs, _, cnt2 = L.compact_dense(T(a, cuda_device), 1, 0.5, want_pairs=True)
+    pairs, cnt2 = pairs.cpu().numpy(), cnt2.cpu().numpy()
+    assert np.array_equal(cnt2, (a > 0.5).sum(1))
+    for b in range(B):
+        hit = np.nonzero(a[b] > 0.5)[0]
+        assert np.array_equal(pairs[b, :len(hit), 1], hit)
