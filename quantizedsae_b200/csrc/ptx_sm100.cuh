@@ -43,13 +43,17 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster. Default semantics (release at CTA
+// scope), NOT .release.cluster: the only users signal "this warp has drained its TMEM accumulator" (ordered by
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync), and a cluster-scope release makes the warp wait until every
+// global store it has issued is acknowledged by L2 -- ncu showed 14 % of the dense encoder's stall samples on that
+// membar (profiles/r2s2_*): the epilogue's 192 KB of stores per tile were serialised with the next tile.
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
       "}\n" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");
