@@ -310,10 +310,37 @@ __device__ __forceinline__ bool select_key(const SelectSrc& s, size_t i, unsigne
   return true;
 }
 
+// Four consecutive elements [4 g, 4 g + 4) with 16-byte loads (the launcher guarantees n % 4 == 0, H % 4 == 0 and
+// 16-byte aligned arrays, so the four share their row d of the score matrix). -> 4-bit mask of valid elements.
+template <int MODE>
+__device__ __forceinline__ unsigned int select_keys4(const SelectSrc& s, size_t g, unsigned int (&key)[4]) {
+  unsigned int valid = 0u;
+  if (MODE == kSelAbsActive || MODE == kSelAbsAll) {
+    const float4 w = reinterpret_cast<const float4*>(s.w)[g];
+    key[0] = __float_as_uint(fabsf(w.x)); key[1] = __float_as_uint(fabsf(w.y));
+    key[2] = __float_as_uint(fabsf(w.z)); key[3] = __float_as_uint(fabsf(w.w));
+    if (MODE == kSelAbsAll) return 0xfu;
+    const float4 m = reinterpret_cast<const float4*>(s.mask)[g];
+    valid = (m.x != 0.f ? 1u : 0u) | (m.y != 0.f ? 2u : 0u) | (m.z != 0.f ? 4u : 0u) | (m.w != 0.f ? 8u : 0u);
+    return valid;
+  }
+  const float4 m = reinterpret_cast<const float4*>(s.mask)[g];
+  valid = (m.x == 0.f ? 1u : 0u) | (m.y == 0.f ? 2u : 0u) | (m.z == 0.f ? 4u : 0u) | (m.w == 0.f ? 8u : 0u);
+  if (valid == 0u) return 0u;
+  const unsigned int first = static_cast<unsigned int>(g) * 4u;          // n < 2^32 (checked by the C ABI)
+  const unsigned int d = first / static_cast<unsigned int>(s.H);
+  const unsigned int h = first - d * static_cast<unsigned int>(s.H);
+  const float dm = fabsf(s.dmean[d]);
+  const float4 a = *reinterpret_cast<const float4*>(s.amean + h);
+  key[0] = ~__float_as_uint(dm * fabsf(a.x)); key[1] = ~__float_as_uint(dm * fabsf(a.y));
+  key[2] = ~__float_as_uint(dm * fabsf(a.z)); key[3] = ~__float_as_uint(dm * fabsf(a.w));
+  return valid;
+}
+
 // The first pass sees a few exponent bins only (all |w| of a layer share their leading bits): lanes that hit the same
 // bin are merged with __match_any_sync and one lane adds the group's count. Four independent elements per thread and
 // trip keep enough loads in flight to stream at HBM rate.
-template <int MODE>
+template <int MODE, bool VEC>
 __global__ void __launch_bounds__(256)
 select_hist_kernel(SelectSrc s, int shift, int bits, SelectState* st) {
   __shared__ unsigned int h[kSelBins];
@@ -322,22 +349,34 @@ select_hist_kernel(SelectSrc s, int shift, int bits, SelectState* st) {
   const unsigned int prefix = st->prefix, pmask = st->prefix_mask;
   const unsigned int dmask = (1u << bits) - 1u;
   const int lane = threadIdx.x & 31;
+  constexpr int E = VEC ? 4 : 1;            // elements per group
+  constexpr int U = VEC ? 2 : 4;            // groups in flight per thread and trip
+  const size_t ng = s.n / E;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   const size_t first = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  for (size_t base = first - lane; base < s.n; base += 4 * stride) {      // warp-uniform trip count
-    unsigned int bin[4];
+  for (size_t base = first - lane; base < ng; base += U * stride) {      // warp-uniform trip count
+    unsigned int bin[U][E];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const size_t i = base + lane + u * stride;
-      unsigned int key;
-      bin[u] = 0xffffffffu;
-      if (i < s.n && select_key<MODE>(s, i, &key) && (key & pmask) == prefix) bin[u] = (key >> shift) & dmask;
+    for (int u = 0; u < U; ++u) {
+      const size_t g = base + lane + u * stride;
+      unsigned int key[4] = {0u, 0u, 0u, 0u};
+      unsigned int valid = 0u;
+      if (g < ng) {
+        if (VEC) valid = select_keys4<MODE>(s, g, key);
+        else valid = select_key<MODE>(s, g, &key[0]) ? 1u : 0u;
+      }
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+        bin[u][e] = (((valid >> e) & 1u) && (key[e] & pmask) == prefix) ? ((key[e] >> shift) & dmask) : 0xffffffffu;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (__ballot_sync(0xffffffffu, bin[u] != 0xffffffffu) == 0u) continue;
-      const unsigned int peers = __match_any_sync(0xffffffffu, bin[u]);
-      if (bin[u] != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&h[bin[u]], static_cast<unsigned int>(__popc(peers)));
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        if (__ballot_sync(0xffffffffu, bin[u][e] != 0xffffffffu) == 0u) continue;
+        const unsigned int peers = __match_any_sync(0xffffffffu, bin[u][e]);
+        if (bin[u][e] != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&h[bin[u][e]], static_cast<unsigned int>(__popc(peers)));
+      }
     }
   }
   __syncthreads();
@@ -416,28 +455,51 @@ __global__ void __launch_bounds__(256) select_pick_kernel(int shift, int bits, S
 
 // drop (:68-69): active &= !(|w| <= threshold) -- every tie at the threshold goes
 __global__ void __launch_bounds__(256)
-rigl_drop_apply_kernel(const float* __restrict__ w, float* __restrict__ mask, size_t n, const SelectState* st) {
+rigl_drop_apply_kernel(const float* __restrict__ w, float* __restrict__ mask, size_t n, int vec, const SelectState* st) {
   const unsigned int thr = st->prefix;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (vec) {
+    for (size_t g = tid; g < n / 4; g += stride) {
+      const float4 ww = reinterpret_cast<const float4*>(w)[g];
+      float4 m = reinterpret_cast<float4*>(mask)[g];
+      bool ch = false;
+      if (m.x != 0.f && __float_as_uint(fabsf(ww.x)) <= thr) { m.x = 0.f; ch = true; }
+      if (m.y != 0.f && __float_as_uint(fabsf(ww.y)) <= thr) { m.y = 0.f; ch = true; }
+      if (m.z != 0.f && __float_as_uint(fabsf(ww.z)) <= thr) { m.z = 0.f; ch = true; }
+      if (m.w != 0.f && __float_as_uint(fabsf(ww.w)) <= thr) { m.w = 0.f; ch = true; }
+      if (ch) reinterpret_cast<float4*>(mask)[g] = m;
+    }
+    return;
+  }
+  for (size_t i = tid; i < n; i += stride)
     if (mask[i] != 0.f && __float_as_uint(fabsf(w[i])) <= thr) mask[i] = 0.f;
 }
 
 // Tie-ranked apply: elements with key < T are selected, of those == T the first st->k by flat index.
 // Every block owns a contiguous range; ties are counted per block, scanned by one block, ranked inside the range.
-template <int MODE>
+template <int MODE, bool VEC>
 __global__ void __launch_bounds__(256)
 select_tie_count_kernel(SelectSrc s, size_t per_block, const SelectState* st, unsigned int* tie_count) {
   __shared__ unsigned int total;
   if (threadIdx.x == 0) total = 0;
   __syncthreads();
   const unsigned int T = st->prefix;
-  const size_t lo = static_cast<size_t>(blockIdx.x) * per_block;
+  const size_t lo = static_cast<size_t>(blockIdx.x) * per_block;          // per_block is a multiple of 256 (and of 4)
   const size_t hi = lo + per_block < s.n ? lo + per_block : s.n;
   unsigned int c = 0;
-  for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    unsigned int key;
-    if (select_key<MODE>(s, i, &key) && key == T) ++c;
+  if (VEC) {
+    for (size_t g = lo / 4 + threadIdx.x; g < hi / 4; g += blockDim.x) {
+      unsigned int key[4];
+      const unsigned int valid = select_keys4<MODE>(s, g, key);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) c += (((valid >> e) & 1u) && key[e] == T) ? 1u : 0u;
+    }
+  } else {
+    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      unsigned int key;
+      if (select_key<MODE>(s, i, &key) && key == T) ++c;
+    }
   }
   if (c) atomicAdd(&total, c);
   __syncthreads();
@@ -466,7 +528,7 @@ __global__ void __launch_bounds__(256) select_tie_scan_kernel(unsigned int* tie_
 }
 
 // selected -> new_value in mask (init_mask: 0, grow: 1); then weight *= mask over the whole range (:39, :86-87)
-template <int MODE>
+template <int MODE, bool VEC>
 __global__ void __launch_bounds__(256)
 select_apply_kernel(SelectSrc s, size_t per_block, const SelectState* st, const unsigned int* tie_base,
                     float new_value, float* __restrict__ mask, float* __restrict__ weight) {
@@ -479,6 +541,31 @@ select_apply_kernel(SelectSrc s, size_t per_block, const SelectState* st, const 
   const unsigned long long take = st->k;
   const size_t lo = static_cast<size_t>(blockIdx.x) * per_block;
   const size_t hi = lo + per_block < s.n ? lo + per_block : s.n;
+  if (VEC && tie_base[blockIdx.x + 1] == tie_base[blockIdx.x]) {
+    // no element of this range sits exactly on the threshold (the usual case): plain elementwise pass, 16-byte accesses
+    for (size_t g = lo / 4 + threadIdx.x; g < hi / 4; g += blockDim.x) {
+      unsigned int key[4];
+      const unsigned int valid = select_keys4<MODE>(s, g, key);
+      float4 m = reinterpret_cast<float4*>(mask)[g];
+      float* mm = reinterpret_cast<float*>(&m);
+      bool ch = false, any_zero = false;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (((valid >> e) & 1u) && key[e] < T) { mm[e] = new_value; ch = true; }
+        any_zero |= mm[e] == 0.f;
+      }
+      if (ch) reinterpret_cast<float4*>(mask)[g] = m;
+      if (weight != nullptr && any_zero) {
+        float4 w = reinterpret_cast<float4*>(weight)[g];
+        if (m.x == 0.f) w.x = 0.f * w.x;
+        if (m.y == 0.f) w.y = 0.f * w.y;
+        if (m.z == 0.f) w.z = 0.f * w.z;
+        if (m.w == 0.f) w.w = 0.f * w.w;
+        reinterpret_cast<float4*>(weight)[g] = w;
+      }
+    }
+    return;
+  }
   if (tie_base[blockIdx.x + 1] == tie_base[blockIdx.x]) {
     // no element of this range sits exactly on the threshold (the usual case): plain elementwise pass
     for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
@@ -529,13 +616,20 @@ int grid_for(size_t work_items, int threads, int max_blocks) {
   return static_cast<int>(g);
 }
 
+// 16-byte accesses over groups of four consecutive elements are possible
+bool select_vec_ok(const SelectSrc& s) {
+  auto al = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return (s.n & 3) == 0 && (s.H & 3) == 0 && al(s.w) && al(s.mask) && al(s.amean);
+}
+
 template <int MODE>
 const char* run_select(const SelectSrc& s, unsigned long long k, SelectState* st, int sms, cudaStream_t stream) {
   select_init_kernel<<<1, 256, 0, stream>>>(st, k);
   const int grid = grid_for(s.n, 256 * 8, sms * 8);
   const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
   for (int p = 0; p < 3; ++p) {
-    select_hist_kernel<MODE><<<grid, 256, 0, stream>>>(s, shifts[p], bits[p], st);
+    if (select_vec_ok(s)) select_hist_kernel<MODE, true><<<grid, 256, 0, stream>>>(s, shifts[p], bits[p], st);
+    else select_hist_kernel<MODE, false><<<grid, 256, 0, stream>>>(s, shifts[p], bits[p], st);
     select_pick_kernel<<<1, 256, 0, stream>>>(shifts[p], bits[p], st);
   }
   count_launches(7);
@@ -548,9 +642,11 @@ const char* run_tie_apply(const SelectSrc& s, const SelectState* st, unsigned in
   size_t per = (s.n + nblocks - 1) / nblocks;
   per = (per + 255) / 256 * 256;
   const int nb = static_cast<int>((s.n + per - 1) / per);
-  select_tie_count_kernel<MODE><<<nb, 256, 0, stream>>>(s, per, st, tie_scratch);
+  if (select_vec_ok(s)) select_tie_count_kernel<MODE, true><<<nb, 256, 0, stream>>>(s, per, st, tie_scratch);
+  else select_tie_count_kernel<MODE, false><<<nb, 256, 0, stream>>>(s, per, st, tie_scratch);
   select_tie_scan_kernel<<<1, 256, 0, stream>>>(tie_scratch, nb);
-  select_apply_kernel<MODE><<<nb, 256, 0, stream>>>(s, per, st, tie_scratch, new_value, mask, weight);
+  if (select_vec_ok(s)) select_apply_kernel<MODE, true><<<nb, 256, 0, stream>>>(s, per, st, tie_scratch, new_value, mask, weight);
+  else select_apply_kernel<MODE, false><<<nb, 256, 0, stream>>>(s, per, st, tie_scratch, new_value, mask, weight);
   count_launches(3);
   return cuda_err(cudaGetLastError());
 }
@@ -662,7 +758,7 @@ const char* rigl_update_mask_launch(float* weight, float* mask, const float* ame
   if (n_drop > 0) {
     const char* e = run_select<kSelAbsActive>(s, n_drop, st, sms, stream);
     if (e) return e;
-    rigl_drop_apply_kernel<<<grid_for(s.n, 256 * 4, sms * 8), 256, 0, stream>>>(weight, mask, s.n, st);
+    rigl_drop_apply_kernel<<<grid_for(s.n, 256 * 4, sms * 8), 256, 0, stream>>>(weight, mask, s.n, select_vec_ok(s) ? 1 : 0, st);
     count_launches(1);
   }
   if (n_grow > 0 && amean != nullptr && dmean != nullptr) {

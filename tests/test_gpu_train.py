@@ -380,3 +380,21 @@ def test_rigl_full_size_against_oracle(cuda_device):
     assert np.array_equal(mt.cpu().numpy(), m1)
     assert np.array_equal(wt.cpu().numpy(), w1)
     assert int(m1.sum()) == int(m0.sum())              # drop n, grow n (no ties in continuous data)
+
+
+@pytest.mark.parametrize("D,H", [(3, 37), (5, 64), (16, 250)])
+def test_rigl_odd_shapes_against_oracle(cuda_device, D, H):
+    """Shapes that take the scalar (H % 4 != 0) and the 16-byte paths of the selection kernels."""
+    rng = np.random.default_rng(D * H)
+    w = rng.standard_normal((D, H)).astype(np.float32)
+    m0, w0 = TO.rigl_init_mask(w, 0.6)
+    wt, mt = T(w, cuda_device), torch.ones((D, H), device=cuda_device)
+    L.rigl_init_mask(wt, mt, int(w.size * 0.6))
+    assert np.array_equal(mt.cpu().numpy(), m0) and np.array_equal(wt.cpu().numpy(), w0)
+    a = (rng.random(H) + 0.01).astype(np.float32)
+    d = rng.standard_normal(D).astype(np.float32)
+    f_decay = 0.25
+    n = int(f_decay * (1 - 0.7) * w.size)
+    L.rigl_update_mask(wt, mt, T(a, cuda_device), T(d, cuda_device), n, n)
+    m1, w1 = TO.rigl_update_mask(w0, m0, a[None, :], d[None, :], f_decay, 0.7)
+    assert np.array_equal(mt.cpu().numpy(), m1) and np.array_equal(wt.cpu().numpy(), w1)
