@@ -883,6 +883,56 @@ def bench_soft_decode(args, T, device, peaks, B=4096, k=65):
                          "note": "algorithmic bytes; the 67 MB dictionary is largely L2-resident, so values above the HBM peak are L2 hits"}}
 
 
+def bench_bsae_soft(args, T, rank, world, device, peaks, steps, warmup, B=4096):
+    """The reference's literal b_sae forward semantics: soft bits sigmoid(w) on NON-polarised logits,
+    reference-default k = 65, through the nn.Module API (decode_mode 'auto' resolves to the fp32 soft dictionary)."""
+    import numpy as np
+    import torch
+
+    import quantizedsae_b200 as Q
+    from oracle import qsae_oracle as O
+
+    torch.manual_seed(0)
+    with torch.device(device):
+        m = Q.BinarySAE(D, H, GAMMA, N_BITS)
+    g = torch.Generator(device=device).manual_seed(31)
+    with torch.no_grad():
+        m.encoder[0].weight.copy_(m.encoder[0].weight.bfloat16().float())
+        m.decoder.weight.copy_(torch.randn(m.decoder.weight.shape, device=device, generator=g) * 1.5)
+        m.decoder.bias.copy_(torch.randn(D, device=device, generator=g))
+    m.eval()
+    m.return_dense = False
+    n_in = n_rotating(B)
+    xs = [make_x(torch, device, B, 40 + s + 100 * rank) for s in range(n_in)]
+    out = {}
+    with torch.no_grad():
+        for exact in (False, True):
+            m.exact = exact
+            m(xs[0])
+            assert m.decoder.resolved_mode() == "soft"
+            ms1 = T.time(lambda i: m(xs[i % n_in]), steps, max(3, warmup))
+            streams = T.streams(args.streams)
+            ms = T.time(T.on_streams(lambda i: m(xs[i % n_in]), streams), steps, max(3, warmup), streams) if streams else ms1
+            out["exact" if exact else "fast"] = {"value": world * B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "single_stream_ms": ms1}
+        m.exact = False
+        lat, recon, pol = m(xs[0])
+        rows = np.arange(0, B, B // 16)[:16]
+        k = lat.indices.shape[1]
+        rv, ri, rr, rp = O.bsae_forward(xs[0][rows].cpu().numpy(), m.encoder[0].weight.detach().cpu().numpy(),
+                                        m.encoder[0].bias.detach().cpu().numpy(), m.decoder.weight.detach().cpu().numpy(),
+                                        m.decoder.bias.detach().cpu().numpy(), n_bits=N_BITS, gamma=GAMMA, k=k, mode="soft")
+        rms = float(np.sqrt(np.mean(rr.astype(np.float64) ** 2))) + 1e-30
+        parity = bool(np.array_equal(lat.indices[rows].cpu().numpy(), ri) and
+                      np.allclose(recon[rows].cpu().numpy(), rr, rtol=1e-4, atol=1e-4 * rms) and abs(float(pol) / rp - 1) < 1e-5)
+    tf = 2.0 * B * H * D / (out["fast"]["ms_per_step"] * 1e-3) / 1e12
+    return {"workload": f"b_sae 512->32768 n_bits=4 forward with SOFT bits (non-polarised logits, fp32 soft dictionary 67 MB), "
+                        f"reference-default k={k}, batch {B}, nn.Module API", "value": out["fast"]["value"], "unit": UNIT,
+            "ms_per_step": out["fast"]["ms_per_step"], "single_stream_ms": out["fast"]["single_stream_ms"], "batch": B,
+            "exact_mode": out["exact"], "parity_checked": parity,
+            "roofline": {"bound": "tensor", "achieved": tf, "unit": "TFLOP/s", "frac_burst": tf / peaks["burst"],
+                         "frac_sustained": tf / peaks["sustained"]}}
+
+
 def bench_training_side(args, T, device, peaks, B=4096):
     """the training-side kernels at the config-1 shape (soft logits, reference-default k = 65): one b_sae
     trainer step (forward + loss + backward through the sparse autograd node, training/trainer.py:143-151), its
@@ -1075,6 +1125,7 @@ def run_b200(args, rank, world, local_rank):
             extra["4_q_sae"] = bench_qsae(args, T, rank, world, device, peaks, max(5, steps // 2), 3)
             torch.cuda.empty_cache()
             extra["soft_bit_decode"] = bench_soft_decode(args, T, device, peaks)
+            extra["1_soft_bits_b4096_k65"] = bench_bsae_soft(args, T, rank, world, device, peaks, max(5, steps // 2), 3)
             torch.cuda.empty_cache()
             extra["f4_training_side"] = bench_training_side(args, T, device, peaks)
             torch.cuda.empty_cache()
