@@ -995,6 +995,53 @@ def bench_training_side(args, T, device, peaks, B=4096):
 # ---------------------------------------------------------------------------------------------
 # config 5: b_sae 512 -> 2^20, dictionary split over the ranks (strong scaling)
 # ---------------------------------------------------------------------------------------------
+def dict_sharded_parity(m, x, latents, rows, rank, world, dist, k, n_rows=8):
+    """In-run oracle check of the dictionary-sharded forward (config 5): for a few rows of rank 0's row block every rank
+    scores ITS shard with the numpy oracle (fp32 pre-activations, local top-k, hard int4 rows of the winners it owns),
+    rank 0 merges the candidates (value desc, global index asc), sums the partial reconstructions and compares with what
+    the CUDA path returned. -> bool on rank 0 (None elsewhere)."""
+    import numpy as np
+
+    from oracle import qsae_oracle as O
+
+    plan = m.plan
+    R = list(range(0, min(n_rows, rows.shape[0])))                    # rank 0 owns the first rows of the batch
+    xr = x[R].cpu().numpy()
+    lin = m.encoder[0]
+    z = O.encode_pre(xr, lin.weight.detach().cpu().numpy(), lin.bias.detach().cpu().numpy())
+    lv, li = O.topk_rows(z, min(k, z.shape[1]))
+    a, b = plan.latent_range()
+    gi = latents.indices[R].cpu().numpy().astype(np.int64)            # the CUDA path's global winners (same on all ranks)
+    gv = latents.values[R].cpu().numpy()
+    mine = (gi >= a) & (gi < b)
+    loc = np.where(mine, gi - a, 0)
+    need = np.unique(loc[mine])
+    logit_rows = m.decoder.weight.detach()[need.tolist() if len(need) else [0]].cpu().numpy()
+    iw = np.zeros((b - a, m.input_dim), dtype=np.float32)
+    if len(need):
+        iw[need] = O.dequant_hard(logit_rows, m.n_bits).astype(np.float32)
+    q = m.decoder.quantization_step if hasattr(m.decoder, "quantization_step") else m.quantization_step
+    partial = O.decode_rows(np.where(mine, gv, np.float32(0)), loc, iw, q, None).astype(np.float64)
+    payload = (lv, li.astype(np.int64) + a, partial)
+    gathered = [None] * world
+    if world > 1:
+        dist.all_gather_object(gathered, payload)
+    else:
+        gathered = [payload]
+    if rank != 0:
+        return None
+    v = np.concatenate([g[0] for g in gathered], axis=1)
+    i = np.concatenate([g[1] for g in gathered], axis=1)
+    order = np.lexsort((i, -v.astype(np.float64)), axis=1)[:, :k]
+    ri = np.take_along_axis(i, order, 1)
+    rv = np.take_along_axis(v, order, 1)
+    ok = bool(np.array_equal(gi, ri) and np.all(np.abs(gv - rv) <= 1e-5 * np.maximum(1.0, np.abs(rv))))
+    recon = sum(g[2] for g in gathered) + m.decoder.bias.detach().cpu().numpy().astype(np.float64)
+    got = rows[R].cpu().numpy()
+    rms = float(np.sqrt(np.mean(recon ** 2))) + 1e-30
+    return ok and bool(np.allclose(got, recon, rtol=1e-4, atol=1e-4 * rms))
+
+
 def bench_dict_sharded(args, T, rank, world, device, peaks, steps, warmup, ks=(32, 2097), B=4096):
     import torch
 
@@ -1030,12 +1077,20 @@ def bench_dict_sharded(args, T, rank, world, device, peaks, steps, warmup, ks=(3
                 local_ms = T.time(lambda i: m.local_candidates(xs[i % 3]), max(3, steps // 2), 2) if hasattr(m, "local_candidates") else None
             if getattr(m, "_peer", None) is not None:
                 m._peer.check()
+            parity = None
+            if k <= 64:      # oracle spot check of this transport (the k = 2097 variant shares every kernel but the large-k select, covered by the tests)
+                with torch.no_grad():
+                    lat, rws, _ = m(xs[0])
+                torch.cuda.synchronize()
+                parity = dict_sharded_parity(m, xs[0], lat, rws, rank, world, dist, k)
             tf = flops_per_gpu / (ms * 1e-3) / 1e12
             k_send = getattr(m, "last_k_send", None)
             entry = {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "k": k, "transport": transport,
                      "roofline": {"bound": "tensor", "achieved": tf, "unit": "TFLOP/s", "frac_burst": tf / peaks["burst"],
                                   "frac_sustained": tf / peaks["sustained"],
                                   "note": "per-GPU sweep flops over the WHOLE step time (exchange + merge + decode included): lower bound of the kernel's fraction"}}
+            if parity is not None:
+                entry["parity_checked"] = parity
             if local_ms is not None:
                 entry["local_ms"] = local_ms
                 entry["comm_ms"] = max(0.0, ms - local_ms)
