@@ -666,7 +666,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
                    const __grid_constant__ CUtensorMap tmap_b1,
                    const __grid_constant__ CUtensorMap tmap_b2, EncodeLaunch p) {
   constexpr bool MCAST = CL == 1;
-  constexpr bool PAIR = CL == 2;
+  constexpr bool PAIR = CL >= 2;            // CL = 3: cta_group::2 pairs ON the range schedule (sparse sweeps, small batches)
   constexpr int kStages = ring_stages(DENSE, PAIR);
   constexpr int kStageBytes = stage_bytes(PAIR);
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -689,7 +689,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   // range schedule (single-CTA variant only): one CTA per SM sweeps a contiguous range of tile units
-  const bool ranged = (CL == 0) && p.range_g > 0;
+  const bool ranged = (CL == 0 || CL == 3) && p.range_g > 0;
   // cluster variants pair two row blocks along grid.x (CTA pairs must be adjacent in x)
   const int split = ranged ? 0 : ((CL != 0) ? blockIdx.y : blockIdx.x);
   const int m0_grid = ranged ? 0 : ((CL != 0) ? blockIdx.x : blockIdx.y) * BM;
@@ -704,11 +704,12 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
     it.legacy = !ranged;
     it.done = false;
     it.n_tiles = p.n_tiles;
-    it.g = blockIdx.x;
-    it.U = static_cast<long long>((p.B + BM - 1) / BM) * p.n_tiles;
+    // pair variant: the units are (pair of row blocks, tile); both CTAs of a pair walk the same range
+    it.g = (CL == 3) ? blockIdx.x / 2 : blockIdx.x;
+    it.U = static_cast<long long>(((p.B + BM - 1) / BM) / (CL == 3 ? 2 : 1)) * p.n_tiles;
     it.G = ranged ? p.range_g : 1;
-    it.u = ranged ? range_start(blockIdx.x, it.U, it.G) : 0;
-    it.u_end = ranged ? range_start(blockIdx.x + 1, it.U, it.G) : 0;
+    it.u = ranged ? range_start(it.g, it.U, it.G) : 0;
+    it.u_end = ranged ? range_start(it.g + 1, it.U, it.G) : 0;
     const int tile_begin = split * p.tiles_per_split;
     const int tile_end = min(p.n_tiles, tile_begin + p.tiles_per_split);
     it.legacy_piece.rb = m0_grid / BM;
@@ -723,6 +724,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
         printf("qsae: more than %d pieces in one CTA's tile range\n", kMaxPieces);
         __trap();
       }
+      if (CL == 3) pc.rb = 2 * pc.rb + static_cast<int>(cta_rank);   // my row block of the pair
       piece_tab[n++] = pc;
     }
     *piece_n = n;
@@ -855,6 +857,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
           }
         }
         if constexpr (CL == 0) umma_commit(a_empty);   // the piece's MMAs no longer read the x tile once this fires
+        if constexpr (CL == 3) umma_commit_pair(a_empty, 0x3);   // ... in either CTA of the pair
       }
     }
   } else if (warp == 3) {
@@ -880,8 +883,8 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
     // ------------------------------------------------------------- epilogue / selection
     const int e = warp - 4;
     uint64_t* pe = PAIR ? pair_empty : nullptr;
-    if constexpr (CL != 0) {
-      // cluster variants never run the range schedule: one piece, its constants known at compile time (keeps the
+    if constexpr (CL == 1 || CL == 2) {
+      // these cluster variants never run the range schedule: one piece, its constants known at compile time (keeps the
       // epilogue's register allocation where it was before pieces existed: the B = 65536 sweep lost 7 % otherwise)
       const int tile_begin = split * p.tiles_per_split;
       const int n = max(0, min(p.n_tiles, tile_begin + p.tiles_per_split) - tile_begin);
@@ -1231,7 +1234,7 @@ struct BMaps { CUtensorMap m[3]; };   // the (up to three) bf16 parts of W, boxe
 
 template <int K_CHUNKS, bool DENSE, int CL>
 cudaError_t launch_k(const CUtensorMap& tx, const BMaps& b, const EncodeLaunch& p, cudaStream_t stream) {
-  const SmemLayout L = smem_layout(K_CHUNKS, DENSE, CL == 2);
+  const SmemLayout L = smem_layout(K_CHUNKS, DENSE, CL >= 2);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(encode_topk_kernel<K_CHUNKS, DENSE, CL>,
@@ -1244,6 +1247,7 @@ cudaError_t launch_k(const CUtensorMap& tx, const BMaps& b, const EncodeLaunch& 
   if constexpr (CL != 0) {
     // whole clusters along x; the padding CTA sweeps zero rows and writes nothing
     grid = dim3(((p.B + BM - 1) / BM + 1) / 2 * 2, p.n_splits);
+    if (CL == 3) grid = dim3(2 * p.range_g, 1);   // range_g pairs, one CTA per SM
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(cta_threads(DENSE));
@@ -1266,6 +1270,7 @@ cudaError_t launch_k(const CUtensorMap& tx, const BMaps& b, const EncodeLaunch& 
 template <bool DENSE>
 const char* launch_any(const CUtensorMap& tx, const BMaps& b, const EncodeLaunch& p, cudaStream_t stream) {
   const int kc = (p.D + BK - 1) / BK;
+  if (p.cluster == 3 && kc != 8) return "the pair range schedule exists for D > 448 only";
   cudaError_t e;
   switch (kc) {
     case 1: e = launch_k<1, DENSE, 0>(tx, b, p, stream); break;
@@ -1276,7 +1281,10 @@ const char* launch_any(const CUtensorMap& tx, const BMaps& b, const EncodeLaunch
     case 6: e = launch_k<6, DENSE, 0>(tx, b, p, stream); break;
     case 7: e = launch_k<7, DENSE, 0>(tx, b, p, stream); break;
     case 8:   // the headline width: the cluster variants exist here
-      if (p.cluster == 2) e = launch_k<8, DENSE, 2>(tx, b, p, stream);
+      if (p.cluster == 3) {
+        if constexpr (DENSE) return "the pair range schedule has no dense epilogue";
+        else e = launch_k<8, false, 3>(tx, b, p, stream);
+      } else if (p.cluster == 2) e = launch_k<8, DENSE, 2>(tx, b, p, stream);
       else if (p.cluster == 1) e = launch_k<8, DENSE, 1>(tx, b, p, stream);
       else e = launch_k<8, DENSE, 0>(tx, b, p, stream);
       break;
@@ -1312,8 +1320,9 @@ int encode_pick_splits(int B, int H, int num_sms) {
   return best_s;
 }
 
-int encode_pick_range(int B, int H, int num_sms, int* nsub) {
+int encode_pick_range(int B, int H, int num_sms, int* nsub, int* pair) {
   *nsub = 0;
+  if (pair) *pair = 0;
   if (tuning().encode_range == 0 || B >= 16384) return 0;   // large batches: the multicast pairs take over
   const long long m_tiles = (B + BM - 1) / BM;
   const long long n_tiles = (H + BN - 1) / BN;
@@ -1325,14 +1334,22 @@ int encode_pick_range(int B, int H, int num_sms, int* nsub) {
   const double eff = (static_cast<double>(units) / (waves * num_sms)) *
                      (static_cast<double>(n_tiles) / (static_cast<double>(tps) * s));
   if (eff >= 0.95 || U < 2ll * num_sms) return 0;
-  const long long G = num_sms;
+  // cta_group::2 pairs on the range schedule: the units are (pair of row blocks, tile), one pair per two SMs. Halves the
+  // W bytes every SM pulls from L2 (the single-CTA sweep runs at the L2 slice limit: 3.5 us per tile against 3.1 us
+  // for the pair). Needs whole pairs of full row blocks.
+  const bool use_pair = pair != nullptr && tuning().encode_range_pair != 0 && (B % (2 * BM)) == 0 && (num_sms % 2) == 0 &&
+                        (H % BN) == 0 && U / 2 >= num_sms;
+  const long long G = use_pair ? num_sms / 2 : num_sms;
+  const long long rbs = use_pair ? m_tiles / 2 : m_tiles;
+  const long long Ur = rbs * n_tiles;
   int max_pieces = 1;
-  for (long long rb = 0; rb < m_tiles; ++rb) {
-    const int pieces = range_owner(rb * n_tiles + n_tiles - 1, U, G) - range_owner(rb * n_tiles, U, G) + 1;
+  for (long long rb = 0; rb < rbs; ++rb) {
+    const int pieces = range_owner(rb * n_tiles + n_tiles - 1, Ur, G) - range_owner(rb * n_tiles, Ur, G) + 1;
     if (pieces > max_pieces) max_pieces = pieces;
   }
   if (2 * max_pieces > 32) return 0;   // the warp-level merge reads at most 32 lists per row
   *nsub = 2 * max_pieces;
+  if (pair) *pair = use_pair ? 1 : 0;
   return static_cast<int>(G);
 }
 
@@ -1361,7 +1378,7 @@ const char* encode_topk_launch(const uint16_t* x_bf16, const uint16_t* w_bf16, E
   p.dense_flags = 0;
   p.k_parts = 1;
   p.accum_mode = 0;
-  p.cluster = p.range_g > 0 ? 0 : pick_cluster(p, p.B >= 16384 ? 1 : 0);
+  p.cluster = p.range_g > 0 ? (p.range_pair ? 3 : 0) : pick_cluster(p, p.B >= 16384 ? 1 : 0);
   BMaps bm;
   if (const char* err = make_b_maps(&bm, &w_bf16, 1, p)) return err;
   return launch_any<false>(tx, bm, p, stream);

@@ -27,6 +27,7 @@ struct Tuning {
   int encode_debug_mode;  // QSAE_ENCODE_DEBUG_MODE: timing experiments (EncodeLaunch::debug_mode)
   int encode_cluster;     // QSAE_ENCODE_CLUSTER: 0 / 1 / 2 forces the cluster variant (-1 = automatic)
   int encode_range;       // QSAE_ENCODE_RANGE: 0 keeps the (split, row block) grid at small batches
+  int encode_range_pair;  // QSAE_ENCODE_RANGE_PAIR: 1 = cta_group::2 pairs on the range schedule (sparse sweeps)
   int prior_prep;         // QSAE_PRIOR_PREP: 0 keeps the separate cast / pre-pass / prior kernels
   int dense_range;        // QSAE_DENSE_RANGE: 1 = dense epilogue (t_sae) on the range schedule instead of CTA pairs (experiment)
   int dense_flags_mask;   // QSAE_DENSE_FLAGS_MASK: masks dense epilogue outputs (-1 = off; timing experiments)
@@ -46,7 +47,8 @@ struct EncodeLaunch {
   int k_sel;            // survivors that must be retained per row (k, or k + rescore margin)
   int n_splits;         // grid.x
   int nsub;             // survivor lists per row: 2 n_splits, or the range schedule's 2 x max pieces per row block
-  int range_g;          // > 0: range schedule (encode_topk_sm100.cu) with this many CTAs instead of the (split, row block) grid
+  int range_g;          // > 0: range schedule (encode_topk_sm100.cu) with this many CTAs (or CTA pairs) instead of the (split, row block) grid
+  int range_pair;       // range schedule over cta_group::2 pairs (range_g pairs, 2 range_g CTAs)
   int tiles_per_split;  // in units of kEncBN latents
   int n_tiles;          // ceil(H / kEncBN)
   int act;              // 0 none, 1 relu
@@ -76,7 +78,7 @@ struct EncodeLaunch {
 // encode_topk_sm100.cu
 int encode_pick_splits(int B, int H, int num_sms);
 // range schedule for this shape: CTAs to launch (0 = keep the (split, row block) grid) and lists per row
-int encode_pick_range(int B, int H, int num_sms, int* nsub);
+int encode_pick_range(int B, int H, int num_sms, int* nsub, int* pair = nullptr);
 void encode_pick_mode(int k_sel, int* mode, int* cap);
 const char* encode_topk_launch(const uint16_t* x_bf16, const uint16_t* w_bf16, EncodeLaunch p,
                                cudaStream_t stream);

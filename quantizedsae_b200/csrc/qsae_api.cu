@@ -32,6 +32,7 @@ void reload_tuning() {
   t.encode_debug_mode = env_int("QSAE_ENCODE_DEBUG_MODE", 0);
   t.encode_cluster = env_int("QSAE_ENCODE_CLUSTER", -1);
   t.encode_range = env_int("QSAE_ENCODE_RANGE", 1);
+  t.encode_range_pair = env_int("QSAE_ENCODE_RANGE_PAIR", 1);
   t.prior_prep = env_int("QSAE_PRIOR_PREP", 1);
   t.dense_range = env_int("QSAE_DENSE_RANGE", 0);
   t.dense_flags_mask = env_int("QSAE_DENSE_FLAGS_MASK", -1);
@@ -93,17 +94,19 @@ int num_sms() {
 
 // One fused-kernel + merge stage over a dictionary of H rows.
 struct StagePlan {
-  int H, k_sel, n_splits, nsub, n_tiles, tiles_per_split, mode, cap, range_g;
+  int H, k_sel, n_splits, nsub, n_tiles, tiles_per_split, mode, cap, range_g, range_pair;
   size_t cand_off, cnt_off, thr_off, end;
 };
 
 enum StageKind { kStageClassBound = 0, kStagePriorMain = 1, kStageSamplePre = 2 };
 
+// D: width of the contraction when the caller allows the range schedule (the pair variant exists for D = 512 only)
 void plan_stage(int B, int H, int k_sel, StageKind kind, bool allow_split_override, size_t base, StagePlan* sp,
-                bool allow_range = false) {
+                bool allow_range = false, int D = 0) {
   sp->H = H;
   sp->k_sel = k_sel;
   sp->range_g = 0;
+  sp->range_pair = 0;
   sp->n_tiles = (H + kEncBN - 1) / kEncBN;
   sp->n_splits = encode_pick_splits(B, H, num_sms());
   if (allow_split_override) {
@@ -128,10 +131,12 @@ void plan_stage(int B, int H, int k_sel, StageKind kind, bool allow_split_overri
     // small batches: one CTA per SM over contiguous tile ranges instead of the (split, row block) grid; a list then
     // covers ~1 / nsub of a row's latents (a few dozen survivors), so 256 entries are plenty (a full list is cut
     // exactly in the kernel, as always)
-    int range_nsub = 0;
-    const int g = (allow_range && tuning().encode_splits == 0) ? encode_pick_range(B, H, num_sms(), &range_nsub) : 0;
+    int range_nsub = 0, range_pair = 0;
+    const int g = (allow_range && tuning().encode_splits == 0)
+                      ? encode_pick_range(B, H, num_sms(), &range_nsub, D > 448 ? &range_pair : nullptr) : 0;
     if (g > 0) {
       sp->range_g = g;
+      sp->range_pair = range_pair;
       sp->nsub = range_nsub;
       sp->cap = 256;
     }
@@ -193,7 +198,7 @@ int plan_encode(int B, int H, int D, int k, int exact, int n_sample, EncodePlan*
   }
   pl->x_off = 0;
   size_t off = align_up(static_cast<size_t>(B) * D * 2, 1024);
-  plan_stage(B, H, k_sel, pl->use_prior ? kStagePriorMain : kStageClassBound, true, off, &pl->main, true);
+  plan_stage(B, H, k_sel, pl->use_prior ? kStagePriorMain : kStageClassBound, true, off, &pl->main, true, D);
   off = pl->main.end;
   pl->counters_off = off; off += 256;
   pl->rescue_rows_off = off; off = align_up(off + static_cast<size_t>(B) * 4, 256);
@@ -213,7 +218,7 @@ void fill_encode_launch(EncodeLaunch* el, const StagePlan& sp, int B, int D, int
   memset(el, 0, sizeof(*el));
   el->B = B; el->H = sp.H; el->D = D; el->k_sel = sp.k_sel;
   el->n_splits = sp.n_splits; el->tiles_per_split = sp.tiles_per_split; el->n_tiles = sp.n_tiles;
-  el->nsub = sp.nsub; el->range_g = sp.range_g;
+  el->nsub = sp.nsub; el->range_g = sp.range_g; el->range_pair = sp.range_pair;
   el->act = act; el->mode = sp.mode; el->cap = sp.cap; el->bias = bias;
   el->cand = ws + sp.cand_off;
   el->cand_cnt = reinterpret_cast<int*>(ws + sp.cnt_off);
@@ -760,7 +765,7 @@ int plan_matryoshka(int B, int H, int D, MatPlan* mp) {
     return fail(QSAE_ERR_INVALID_ARGUMENT, "matryoshka: D must be a multiple of 16 in [16, 512], got %d", D);
   mp->x_off = 0;
   mp->prior_off = align_up(static_cast<size_t>(B) * D * 2, 1024);
-  plan_stage(B, H, 0, kStagePriorMain, false, mp->prior_off + align_up(static_cast<size_t>(B) * 4, 256), &mp->st, true);
+  plan_stage(B, H, 0, kStagePriorMain, false, mp->prior_off + align_up(static_cast<size_t>(B) * 4, 256), &mp->st, true, D);
   // every active latent is kept: largest buffers. Range schedule: more, shorter lists per row (the same capacity per row)
   mp->st.cap = mp->st.range_g > 0 ? kCandCapMax / 2 : kCandCapMax;
   mp->st.cnt_off = mp->st.cand_off + static_cast<size_t>(B) * mp->st.nsub * mp->st.cap * 8;

@@ -627,6 +627,28 @@ def test_range_schedule_is_bit_identical_to_the_grid_schedule(cuda_device, tunin
     assert int((outs[0][2] != 0).sum()) == 0
 
 
+@pytest.mark.parametrize("B,H,D,k,exact", [(4096, 32768, 512, 32, False), (1536, 32768, 512, 65, True), (2048, 16384, 512, 32, False)])
+def test_pair_range_schedule_is_bit_identical_to_the_single_cta_range_schedule(cuda_device, tuning, B, H, D, k, exact):
+    """Batches of whole row-block pairs run the range schedule over cta_group::2 pairs (units = (pair of row blocks, tile),
+    74 pairs on 148 SMs, x tiles of both CTAs reloaded between pieces): same bits as the single-CTA range schedule."""
+    x, W, b = _enc_case(B, H, D, 77 + B, bf16=not exact)
+    dx, dW, db = T(x, cuda_device), T(W, cuda_device), T(b, cuda_device)
+    wb = L.cast_bf16(dW)
+    sample = L.prepare_sample(wb, db)
+    packed = torch.randint(0, 256, (H, D // 2), dtype=torch.uint8, device=cuda_device)
+    bd = torch.randn(D, device=cuda_device)
+    outs = []
+    for flag in ("1", "0"):
+        tuning("QSAE_ENCODE_RANGE_PAIR", flag)
+        outs.append(L.bsae_forward(dx, wb, dW if exact else None, db, k, packed, 4, 0.5, bd, exact=exact, want_flags=True,
+                                   sample=sample))
+    for a, c in zip(outs[0], outs[1]):
+        assert torch.equal(a, c)
+    rows = np.random.default_rng(1).choice(B, 128, replace=False)
+    z = O.encode_pre(x[rows], W, b)
+    assert_topk_matches(outs[0][0].cpu().numpy()[rows], outs[0][1].cpu().numpy()[rows], z, k)
+
+
 def test_prior_prep_path_is_bit_identical_to_the_separate_kernels(cuda_device, tuning):
     B, H, D, k = 700, 32768, 512, 32
     x, W, b = _enc_case(B, H, D, 4242)
