@@ -1147,7 +1147,7 @@ def run_b200(args, rank, world, local_rank):
                        "parallelism": f"batch-sharded x{world}, replicated weights, no collective",
                        "parity_checked": r["parity_checked"], "numa": numa},
             "roofline": roofline_block(peaks, flops, r["kernel_ms"], flops, r["ms_per_step"], r["elapsed_ms"], r["clocks"],
-                                       "encode_topk_kernel<8,0,0> (range schedule, one CTA per SM)" if B < 16384 else "encode_topk_kernel<8,0,1>",
+                                       "encode_topk_kernel<8,0,3> (range schedule over cta_group::2 pairs, one CTA per SM)" if B < 16384 else "encode_topk_kernel<8,0,1>",
                                        "encode_topk_kernel_dram_bytes_per_launch_b4096" if B == 4096 else "encode_topk_kernel_dram_bytes_per_launch"),
             "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "clocks": r["clocks"],
             "exact_mode": r["exact_mode"],
