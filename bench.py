@@ -1099,6 +1099,17 @@ def bench_dict_sharded(args, T, rank, world, device, peaks, steps, warmup, ks=(3
                 entry["k_send"] = k_send
                 entry["nvlink_bytes_per_step_per_gpu"] = B * k_send * 8 * (world - 1) + (B // max(world, 1)) * D * 4 * (world - 1)
             out[f"{transport}_k{k}"] = entry
+            if k > 224:
+                # the same step with the winners returned as a set (ordered_latents = False): the sort of 2097 winners per
+                # row is most of the large-k selection's instructions and the reference only uses the set (sae/binary.py:96-99)
+                m.ordered_latents = False
+                with torch.no_grad():
+                    ums = T.time(lambda i: m(xs[i % 3]), steps, max(3, warmup))
+                m.ordered_latents = True
+                if getattr(m, "_peer", None) is not None:
+                    m._peer.check()
+                out[f"{transport}_k{k}_unordered"] = {"value": B / (ums * 1e-3), "unit": UNIT, "ms_per_step": ums, "k": k,
+                                                      "transport": transport, "note": "SparseLatents hold each row's k winners as a set"}
     return out
 
 

@@ -126,6 +126,13 @@ unsigned long long qsae_launch_count(void);
  * launch path. A process that changes them afterwards (tests, tuning runs) calls this to re-read them. */
 int qsae_reload_tuning(void);
 
+/* Large selections (k > QSAE_MAX_K through qsae_encode_topk, and qsae_merge_candidates[_peer]) spend most of their
+ * instructions sorting the winners into (value desc, index asc) order. The reference only ever uses the winners as a set
+ * (mask / scatter into the dense latent, sae/binary.py:96-99; the decoder sums them): with on != 0 the calling thread's
+ * subsequent fast-mode (exact = 0) large selections emit the same k winners in no particular order. Exact mode and
+ * the warp-level paths (k <= QSAE_MAX_K) always sort. Thread-local; off by default. */
+int qsae_set_unordered_topk(int on);
+
 /* Measurement hook: per-stage events of the sampled-prior path of qsae_encode_topk / qsae_bsae_forward, recorded in
  * stream order by the calling thread's next calls: [0] start, [1] prior ready (cast + sample pre-pass + prior),
  * [2] sweep done, [3] merge (+ fused decode) done, [4] tail kernel done, [5] separate decode done (when not fused).

@@ -35,6 +35,7 @@ SYMBOLS = {
     "qsae_launch_count": (C.c_ulonglong, []),
     "qsae_reload_tuning": (_i, []),
     "qsae_set_stage_events": (_i, [_vp, _i]),
+    "qsae_set_unordered_topk": (_i, [_i]),
     "qsae_prior_prep": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, C.POINTER(_i), _vp]),
     "qsae_encode_topk": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "qsae_bsae_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp,
@@ -146,6 +147,24 @@ def check(status: int) -> None:
         if status == -5:
             raise RuntimeError(msg)  # torch.topk raises RuntimeError for k > H as well
         raise QsaeError(status, msg)
+
+
+class unordered_topk:
+    """Context manager: large fast-mode selections (k > QSAE_MAX_K, candidate merges) inside the block return their
+    winners as a set, in no particular order (qsae_set_unordered_topk)."""
+
+    def __init__(self, on: bool = True):
+        self.on = bool(on)
+
+    def __enter__(self):
+        if self.on:
+            check(load().qsae_set_unordered_topk(1))
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            check(load().qsae_set_unordered_topk(0))
+        return False
 
 
 def _stream() -> int:

@@ -138,6 +138,7 @@ struct SelectLaunch {
   // 0 / 0 = the fused encoder's layout [B][nsub][cap]. Gathered per-shard candidates are [nsub][B][cap].
   long long row_stride, sub_stride;
   int sub_col_offset;     // column of an entry of list s is stored_col + s * sub_col_offset (dictionary shards)
+  int unsorted;           // block-level select (k > 224), fast mode: emit the k winners as a set, in no particular order
   // Truncated candidate lists (dictionary shards send fewer than k candidates each): *incomplete is set to 1 when,
   // for some row, every entry of some list was selected -- entries that list's owner did not send could then
   // belong to the row's true top-k. Block-per-row kernel only; null = lists are complete, no check.

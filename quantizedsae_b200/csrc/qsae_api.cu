@@ -59,6 +59,8 @@ thread_local cudaEvent_t g_enc_ev_stop = nullptr;
 // optional per-stage events of qsae_encode_topk / qsae_bsae_forward (qsae_set_stage_events)
 thread_local cudaEvent_t g_stage_ev[QSAE_N_STAGE_EVENTS] = {nullptr};
 thread_local int g_stage_n = 0;
+// qsae_set_unordered_topk: block-level selections (k > QSAE_MAX_K, candidate merges) emit unordered winner sets
+thread_local int g_unordered_topk = 0;
 inline void stage_mark(int i, cudaStream_t st) {
   if (i < g_stage_n && g_stage_ev[i] != nullptr) cudaEventRecord(g_stage_ev[i], st);
 }
@@ -394,6 +396,7 @@ int encode_topk_large(const float* x_f32, const uint16_t* w_bf16, const float* w
   sl.x_f32 = x_f32; sl.w_f32 = w_f32; sl.bias = b_enc;
   sl.out_vals = out_vals; sl.out_idx = out_idx; sl.out_flags = out_flags;
   sl.rescue_count = counters; sl.rescue_rows = rescue_rows; sl.check_count = 1;
+  sl.unsorted = g_unordered_topk;
   rc = launch_status("select_topk kernel", select_topk_launch(sl, st));
   if (rc != QSAE_OK) return rc;
   if (tuning().debug_large) {   // diagnostics: survivor statistics of this call (synchronises)
@@ -451,6 +454,11 @@ unsigned long long qsae_launch_count(void) { return g_launches.load(std::memory_
 
 int qsae_reload_tuning(void) {
   reload_tuning();
+  return QSAE_OK;
+}
+
+int qsae_set_unordered_topk(int on) {
+  g_unordered_topk = on != 0 ? 1 : 0;
   return QSAE_OK;
 }
 
@@ -1391,6 +1399,7 @@ int merge_candidates_impl(const void* cand_all, const void* const* list_bases, i
   sl.list_bases = list_bases;         // or one [B][k_in] list array per shard, in that shard's (peer) memory
   sl.row_stride = 1; sl.sub_stride = B; sl.sub_col_offset = shard_latents;
   sl.out_vals = out_vals; sl.out_idx = out_idx;
+  sl.unsorted = g_unordered_topk;
   // every row has exactly n_shards * k_in candidates: pick the tier that holds them
   const long long n_cand = static_cast<long long>(n_shards) * k_in;
   if (incomplete != nullptr) {   // truncated lists (k_in < the shards' full candidate count): completeness check

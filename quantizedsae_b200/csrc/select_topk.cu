@@ -209,7 +209,9 @@ __device__ __forceinline__ bool select_row_block(const SelectLaunch& p, int row,
 
   // ---- sort (the gathered keys are no longer needed: their buffer is the scratch of the two-part sort)
   __shared__ int s_pos[2];
-  const uint64_t* sorted = block_sort_selected(sel, out, ksort, keys, n_max, s_hist, s_ctl, s_pos);
+  // (fast mode, on request: the winners as a set -- the decoders and the dense latent do not depend on the order)
+  const uint64_t* sorted = (p.unsorted != 0 && !p.exact) ? sel
+                                                         : block_sort_selected(sel, out, ksort, keys, n_max, s_hist, s_ctl, s_pos);
 
   // ---- emit
   for (int j = threadIdx.x; j < p.k_out; j += THREADS) {

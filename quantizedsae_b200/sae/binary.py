@@ -147,6 +147,7 @@ class BinarySAE(SparseAutoencoder):
         self.exact = True                    # fp32 re-scoring of the tensor-core candidates
         self.last_flags = None               # rows whose selection was not certified (exact mode)
         self.autograd = False                # True: forward attaches the sparse backward (quantizedsae_b200/training.py)
+        self.ordered_latents = True          # False (fast mode, k > QSAE_MAX_K): sparse latents as unordered winner sets
         self._prep = PreparedCache()
 
     def _w_bf16(self):
@@ -178,6 +179,12 @@ class BinarySAE(SparseAutoencoder):
         return SparseLatents(vals, idx, (x.shape[0], self.hidden_dim))
 
     def forward(self, x):
+        if not self.ordered_latents and not self.exact:
+            with _lib.unordered_topk():
+                return self._forward(x)
+        return self._forward(x)
+
+    def _forward(self, x):
         if self.autograd and torch.is_grad_enabled():
             # training (training/trainer.py:143-151): soft-bit forward with the sparse backward attached
             from .. import training

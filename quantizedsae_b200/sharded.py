@@ -288,6 +288,10 @@ class DictionaryShardedBinarySAE(nn.Module):
         self.last_exchange = None            # "truncated" / "full": which candidate exchange produced the last forward
         self.last_k_send = None              # candidates per shard and row of the last (successful) exchange round
         self.transport = "nccl"              # "nccl" (torch.distributed collectives) | "p2p" (CUDA IPC peer memory)
+        # False: the returned SparseLatents hold the k winners of each row as a SET (no value order). The reference only
+        # uses them as a set (mask / scatter, sae/binary.py:96-99); sorting 2097 winners per row is most of the large-k
+        # selection's instructions. Fast mode (exact = False) only; exact mode always sorts.
+        self.ordered_latents = True
         self._peer = None
         self._pol_cache = None
         # ops=False defers the choice (tests install their own backend after construction)
@@ -350,6 +354,13 @@ class DictionaryShardedBinarySAE(nn.Module):
         k = self.top_k()
         if k > self.hidden_dim:
             raise RuntimeError(f"selected index k out of range (k={k} > H={self.hidden_dim})")
+        plan = self.plan
+        if not self.ordered_latents and not self.exact and isinstance(self.ops, CudaShardOps):
+            with _lib.unordered_topk():
+                return self._forward_impl(x, k)
+        return self._forward_impl(x, k)
+
+    def _forward_impl(self, x: torch.Tensor, k: int):
         plan = self.plan
         if self.transport == "p2p" and plan.world_size > 1:
             return self._forward_p2p(x, k)
