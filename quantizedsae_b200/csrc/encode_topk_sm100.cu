@@ -448,6 +448,15 @@ __device__ __forceinline__ void epilogue_dense(const EncodeLaunch& p, int n_my_t
   const int f_row = lane >> 3, f_col = (lane & 7) * 4;
   const int h_row = lane >> 2, h_col = (lane & 3) * 8;
 
+  // act == 2: activity counts of the current level, flushed (one atomic per warp) when the level changes
+  unsigned n_act = 0u;
+  int cur_lvl = 0;
+  auto flush_level_count = [&]() {
+    const unsigned tot = __reduce_add_sync(0xffffffffu, n_act);
+    if (lane == 0 && tot != 0u) atomicAdd(p.step_level_count + cur_lvl, static_cast<unsigned long long>(tot));
+    n_act = 0u;
+  };
+
   for (int t = 0; t < n_my_tiles; ++t) {
     const int acc = (tt0 + t) & 1;
     const uint32_t ph = ((tt0 + t) >> 1) & 1;
@@ -456,6 +465,14 @@ __device__ __forceinline__ void epilogue_dense(const EncodeLaunch& p, int n_my_t
     tc_fence_after();
     const int n_tile = (tile_begin + t) * BN + cgrp * kColsPerWarp;
     const float4* bias4 = reinterpret_cast<const float4*>(bias_smem + acc * BN + cgrp * kColsPerWarp);
+    if (p.act == 2) {   // the warp's 128 columns of a tile lie in one level (boundaries are multiples of 128)
+      int lvl = 0;
+      while (lvl + 1 < p.step_n_levels && n_tile >= __ldg(p.step_level_start + lvl + 1)) ++lvl;
+      if (lvl != cur_lvl) {
+        flush_level_count();
+        cur_lvl = lvl;
+      }
+    }
 #pragma unroll 1
     for (int c = 0; c < kColsPerWarp / 32; ++c) {
       uint32_t r[32];
@@ -475,6 +492,23 @@ __device__ __forceinline__ void epilogue_dense(const EncodeLaunch& p, int n_my_t
         for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]), 0.f));
       }
       if (!warp_live || col0 >= p.H) continue;  // warp-uniform
+      if (p.act == 2) {
+        // q_sae dense path: r = active ? scale[col] : 0 (the A operand of the level GEMMs; hi / lo leave below)
+        const float4* sc4 = reinterpret_cast<const float4*>(p.step_scale + col0);
+        unsigned n = 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 s = __ldg(sc4 + j);
+          const bool a0 = __uint_as_float(r[4 * j + 0]) >= p.step_thr, a1 = __uint_as_float(r[4 * j + 1]) >= p.step_thr;
+          const bool a2 = __uint_as_float(r[4 * j + 2]) >= p.step_thr, a3 = __uint_as_float(r[4 * j + 3]) >= p.step_thr;
+          n += (a0 ? 1u : 0u) + (a1 ? 1u : 0u) + (a2 ? 1u : 0u) + (a3 ? 1u : 0u);
+          r[4 * j + 0] = a0 ? __float_as_uint(s.x) : 0u;
+          r[4 * j + 1] = a1 ? __float_as_uint(s.y) : 0u;
+          r[4 * j + 2] = a2 ? __float_as_uint(s.z) : 0u;
+          r[4 * j + 3] = a3 ? __float_as_uint(s.w) : 0u;
+        }
+        if (row0 + lane < p.B) n_act += n;
+      }
       if (p.accum_mode != 0) {
         // Split-operand passes (exact fp32 encoder): r holds this pass's raw partial products (the
         // launcher passes no bias for these passes; the final pass adds p.accum_bias here).
@@ -615,6 +649,7 @@ __device__ __forceinline__ void epilogue_dense(const EncodeLaunch& p, int n_my_t
       if (pair_empty != nullptr) mbar_arrive_cluster(&pair_empty[acc], 0);
     }
   }
+  if (p.act == 2) flush_level_count();
 }
 
 // one piece of the epilogue role: dense epilogue, or the selection mode of this launch
@@ -911,6 +946,180 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
     if constexpr (PAIR) tmem_dealloc_pair<kTmemCols>(tmem_base);
     else tmem_dealloc<kTmemCols>(tmem_base);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// encode_dense_split_kernel: the fp32-accurate dense encoder (exact mode of t_sae / of the q_sae dense path) in ONE
+// launch. x = xh + xm + xl and W = wh + wm + wl (bf16 parts, both sums exact); the six partial products above 2^-24
+// are contracted into the SAME TMEM accumulator, smallest first:
+//     xl wh, xm wm, xh wl, xm wh, xh wm, xh wh        (K = 6 D in effect)
+// so the dense fp32 output is written once (the three-pass form read-modify-wrote it twice: 2.1 ms of a 2.3 ms
+// forward at B = 4096). No x tile is resident: every ring stage carries one 128 x 64 chunk of an x part next to
+// the CTA's half (128 latents) of the matching W chunk, the cta_group::2 pair executes M = 256 MMAs (CL = 2 of the
+// kernel above), and the epilogue is the same dense epilogue (accum_mode 0: bias + activation, fp32 / hi / lo).
+// The MMAs of a tile take six times as long as its drain, so the stores hide behind the tensor pipe here.
+constexpr int kSplitStages = 5;
+constexpr int kSplitStageBytes = kABytesPerChunk + kBBytesPerStage / 2;   // 32 KiB: x chunk | my half of the W chunk
+__host__ __device__ inline SmemLayout split_smem_layout() {
+  SmemLayout L;
+  L.a_off = 0;
+  L.b_off = 0;
+  L.staging_off = kSplitStages * kSplitStageBytes;
+  L.bias_off = L.staging_off + epi_warps(true) * dense_stage_bytes(true);
+  L.share_off = L.bias_off + 2 * BN * 4;
+  L.bar_off = L.share_off;
+  L.tmem_ptr_off = L.bar_off + 8 * (2 * kSplitStages + 8);
+  L.piece_off = L.tmem_ptr_off + 16;
+  L.total = L.piece_off;
+  return L;
+}
+
+__global__ void __launch_bounds__(cta_threads(true), 1)
+encode_dense_split_kernel(const __grid_constant__ CUtensorMap tmap_xh, const __grid_constant__ CUtensorMap tmap_xm,
+                          const __grid_constant__ CUtensorMap tmap_xl, const __grid_constant__ CUtensorMap tmap_wh,
+                          const __grid_constant__ CUtensorMap tmap_wm, const __grid_constant__ CUtensorMap tmap_wl,
+                          EncodeLaunch p, int k_chunks) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const SmemLayout L = split_smem_layout();
+  uint8_t* ring = smem;
+  float* bias_smem = reinterpret_cast<float*>(smem + L.bias_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* full = bars;
+  uint64_t* empty = full + kSplitStages;
+  uint64_t* tmem_full = empty + kSplitStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* bias_full = tmem_empty + 2;
+  uint64_t* pair_empty = bias_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L.tmem_ptr_off);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0u;
+  // Range schedule: the units are (pair of row blocks, tile) in row-block-major order; pair g of the gridDim.x / 2
+  // pairs sweeps the contiguous units [u0, u1). Nothing is resident per row block, so a range may cross row blocks
+  // freely and every pair gets the same number of units (+-1).
+  const int n_tiles = p.n_tiles;
+  const long long U = static_cast<long long>(((p.B + BM - 1) / BM + 1) / 2) * n_tiles;
+  const long long G = gridDim.x / 2;
+  const long long u0 = range_start(blockIdx.x / 2, U, G);
+  const int n_my = static_cast<int>(range_start(blockIdx.x / 2 + 1, U, G) - u0);
+  const int rbp0 = static_cast<int>(u0 / n_tiles);
+  const int tile0 = static_cast<int>(u0 - static_cast<long long>(rbp0) * n_tiles);
+  const int k_iters = 6 * k_chunks;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0u) {
+      printf("qsae: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
+    for (int s = 0; s < kSplitStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], epi_warps(true));
+      mbar_init(&bias_full[a], 1);
+      mbar_init(&pair_empty[a], 2 * epi_warps(true));
+    }
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 2) tmem_alloc_pair<kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_xh);
+      tma_prefetch_desc(&tmap_wh);
+      int stage = 0;
+      uint32_t phase = 0;
+      int rbp = rbp0, tile = tile0;
+      for (int t = 0; t < n_my; ++t) {
+        const int m0 = (2 * rbp + static_cast<int>(cta_rank)) * BM;
+        const int n0 = tile * BN + static_cast<int>(cta_rank) * (BN / 2);
+#pragma unroll 1
+        for (int it = 0; it < k_iters; ++it) {
+          const int prod = it / k_chunks, kc = it - prod * k_chunks;
+          // product order (smallest first): xl wh, xm wm, xh wl, xm wh, xh wm, xh wh
+          const CUtensorMap* tx = (prod == 0) ? &tmap_xl : ((prod == 1 || prod == 3) ? &tmap_xm : &tmap_xh);
+          const CUtensorMap* tw = (prod == 2) ? &tmap_wl : ((prod == 1 || prod == 4) ? &tmap_wm : &tmap_wh);
+          mbar_wait(&empty[stage], phase ^ 1u);
+          const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), 0);
+          if (leader) mbar_arrive_expect_tx(&full[stage], 2 * kSplitStageBytes);   // 32 KiB from each CTA
+          uint8_t* dst = ring + stage * kSplitStageBytes;
+          tma_load_2d_pair(dst, tx, full_leader, kc * BK, m0, kPolicyEvictLast);
+          tma_load_2d_pair(dst + kABytesPerChunk, tw, full_leader, kc * BK, n0, kPolicyEvictLast);
+          if (++stage == kSplitStages) { stage = 0; phase ^= 1u; }
+        }
+        if (++tile == n_tiles) { tile = 0; ++rbp; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(2 * BM, BN);
+      const uint64_t a_desc0 = umma_desc_kmajor_sw128(smem_u32(ring));
+      const uint64_t b_desc0 = umma_desc_kmajor_sw128(smem_u32(ring + kABytesPerChunk));
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < n_my; ++t) {
+        const int acc = t & 1;
+        mbar_wait(&pair_empty[acc], ((t >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+#pragma unroll 1
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t so = static_cast<uint64_t>((stage * kSplitStageBytes) >> 4);
+#pragma unroll
+          for (int ks = 0; ks < BK / UMMA_K; ++ks)
+            umma_f16_ss_pair(d_tmem, a_desc0 + so + ks * 2, b_desc0 + so + ks * 2, idesc, (it | ks) != 0 ? 1u : 0u);
+          umma_commit_pair(&empty[stage], 0x3);
+          if (it == k_iters - 1) umma_commit_pair(&tmem_full[acc], 0x3);
+          if (++stage == kSplitStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    int tile = tile0;
+    for (int t = 0; t < n_my; ++t) {
+      const int acc = t & 1;
+      mbar_wait(&tmem_empty[acc], ((t >> 1) & 1) ^ 1u);
+      const int n0 = tile * BN;
+#pragma unroll
+      for (int i = 0; i < BN / 32; ++i) {
+        const int c = i * 32 + lane;
+        bias_smem[acc * BN + c] = (p.bias != nullptr && n0 + c < p.H) ? __ldg(p.bias + n0 + c) : 0.f;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bias_full[acc]);
+      if (++tile == n_tiles) tile = 0;
+    }
+  } else if (warp >= 4) {
+    // one call of the dense epilogue per row-block pair the range touches
+    int rbp = rbp0, tile = tile0, done = 0;
+#pragma unroll 1
+    while (done < n_my) {
+      const int n = min(n_my - done, n_tiles - tile);
+      epilogue_dense<true>(p, n, tile, (2 * rbp + static_cast<int>(cta_rank)) * BM, done, warp - 4, lane, tmem_base, bias_smem,
+                           smem + L.staging_off, tmem_full, tmem_empty, bias_full, pair_empty);
+      done += n;
+      tile = 0;
+      ++rbp;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc_pair<kTmemCols>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1391,6 +1600,8 @@ const char* encode_dense_tc_launch(const uint16_t* x_bf16, const uint16_t* const
   if ((reinterpret_cast<uintptr_t>(out_f32) | reinterpret_cast<uintptr_t>(out_hi) | reinterpret_cast<uintptr_t>(out_lo)) & 15)
     return "dense tensor-core encoder: outputs must be 16-byte aligned";
   if (p.accum_mode != 0 && !out_f32) return "dense encoder: accumulating passes need the fp32 output";
+  if (p.act == 2 && (p.accum_mode != 0 || !p.step_scale || !p.step_level_start || !p.step_level_count || (p.H % 128) != 0))
+    return "dense encoder: the step-operand epilogue needs scale / levels / counts, H % 128 == 0 and a plain pass";
   CUtensorMap tx;
   if (!make_tmap_bf16(&tx, x_bf16, p.B, p.D, BM)) return "cuTensorMapEncodeTiled(x) failed";
   p.out_f32 = out_f32; p.out_hi = out_hi; p.out_lo = out_lo;
@@ -1402,6 +1613,54 @@ const char* encode_dense_tc_launch(const uint16_t* x_bf16, const uint16_t* const
   BMaps bm;
   if (const char* err = make_b_maps(&bm, w_parts, n_parts, p)) return err;
   return launch_any<true>(tx, bm, p, stream);
+}
+
+const char* encode_dense_split_launch(const uint16_t* const* x_parts, const uint16_t* const* w_parts, EncodeLaunch p,
+                                      float* out_f32, uint16_t* out_hi, uint16_t* out_lo, int num_sms, cudaStream_t stream) {
+  if ((p.H % 8) != 0) return "dense tensor-core encoder needs H % 8 == 0";
+  if ((reinterpret_cast<uintptr_t>(out_f32) | reinterpret_cast<uintptr_t>(out_hi) | reinterpret_cast<uintptr_t>(out_lo)) & 15)
+    return "dense tensor-core encoder: outputs must be 16-byte aligned";
+  if (p.act == 2 && (!p.step_scale || !p.step_level_start || !p.step_level_count || (p.H % 128) != 0))
+    return "dense encoder: the step-operand epilogue needs scale / levels / counts and H % 128 == 0";
+  p.out_f32 = out_f32; p.out_hi = out_hi; p.out_lo = out_lo;
+  p.k_parts = 3;
+  p.accum_mode = 0;
+  p.range_g = 0;
+  p.cluster = 2;
+  p.dense_flags = (out_f32 ? 1 : 0) | (out_hi ? 2 : 0) | (out_lo ? 4 : 0);
+  if (p.dense_flags == 0) return "dense encoder: no output requested";
+  if (tuning().dense_flags_mask >= 0) p.dense_flags &= tuning().dense_flags_mask;  // timing experiments only
+  CUtensorMap tx[3], tw[3];
+  for (int i = 0; i < 3; ++i) {
+    if (!make_tmap_bf16(&tx[i], x_parts[i], p.B, p.D, BM)) return "cuTensorMapEncodeTiled(x part) failed";
+    if (!make_tmap_bf16(&tw[i], w_parts[i], p.H, p.D, BN / 2)) return "cuTensorMapEncodeTiled(W part) failed";
+  }
+  const SmemLayout L = split_smem_layout();
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(encode_dense_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  // range schedule over CTA pairs: one pair per two SMs, or one per unit when there are fewer units than that
+  const long long units = static_cast<long long>(((p.B + BM - 1) / BM + 1) / 2) * p.n_tiles;
+  int n_pairs = num_sms / 2;
+  if (units < n_pairs) n_pairs = static_cast<int>(units);
+  cfg.gridDim = dim3(2 * n_pairs, 1);
+  cfg.blockDim = dim3(cta_threads(true));
+  cfg.dynamicSmemBytes = L.total;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const int k_chunks = (p.D + BK - 1) / BK;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, encode_dense_split_kernel, tx[0], tx[1], tx[2], tw[0], tw[1], tw[2], p, k_chunks);
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
 

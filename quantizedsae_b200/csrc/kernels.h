@@ -31,6 +31,8 @@ struct Tuning {
   int prior_prep;         // QSAE_PRIOR_PREP: 0 keeps the separate cast / pre-pass / prior kernels
   int dense_range;        // QSAE_DENSE_RANGE: 1 = dense epilogue (t_sae) on the range schedule instead of CTA pairs (experiment)
   int dense_flags_mask;   // QSAE_DENSE_FLAGS_MASK: masks dense epilogue outputs (-1 = off; timing experiments)
+  int dense_step_fused;   // QSAE_DENSE_STEP_FUSED: 0 = q_sae dense path writes fp32 pre-activations and runs the separate operand kernel
+  int dense_split_fused;  // QSAE_DENSE_SPLIT_FUSED: 0 = exact dense encoder as three accumulating passes instead of the one-launch kernel
   int decode_pair;        // QSAE_DECODE_PAIR: 0 / 1 forces the decoder GEMM variant (-1 = automatic)
   int peer_timeout_ms;    // QSAE_PEER_TIMEOUT_MS: bound of a peer-memory flag wait (default 20000)
   int debug_large;        // QSAE_DEBUG_LARGE: survivor statistics of the large-k path on stderr (synchronises)
@@ -51,7 +53,7 @@ struct EncodeLaunch {
   int range_pair;       // range schedule over cta_group::2 pairs (range_g pairs, 2 range_g CTAs)
   int tiles_per_split;  // in units of kEncBN latents
   int n_tiles;          // ceil(H / kEncBN)
-  int act;              // 0 none, 1 relu
+  int act;              // 0 none, 1 relu; dense epilogue only: 2 = step operand, out = (z >= step_thr) ? step_scale[col] : 0
   int mode;             // epilogue bound: 0 bisection only, 1/2/3 class maxima, 4 prior (see .cu)
   int cap;              // entries per survivor buffer
   const float* bias;    // [H]
@@ -71,6 +73,12 @@ struct EncodeLaunch {
   float* out_f32;       // dense epilogue: [B, H] row-major outputs (set by the launcher)
   uint16_t* out_hi;
   uint16_t* out_lo;
+  // act == 2 (q_sae dense path: the A operand of the level GEMMs written straight from the encoder epilogue)
+  float step_thr;
+  const float* step_scale;            // [H]
+  const int* step_level_start;        // [step_n_levels + 1] device, multiples of 128
+  int step_n_levels;
+  unsigned long long* step_level_count;   // [step_n_levels] += active (row, latent) pairs per level
   int debug_mode;       // 0 normal; timing experiments: 1 no survivors, 2 no TMEM drain
   float* debug_z;       // optional dense [B, H] dump of the accumulator (+bias, act); diagnostics only
 };
@@ -106,6 +114,11 @@ const char* prior_prep_launch(const uint16_t* w_sample, const PrepLaunch& p, cud
 // against x into the same accumulator. p.accum_mode selects plain / accumulating output (see EncodeLaunch).
 const char* encode_dense_tc_launch(const uint16_t* x_bf16, const uint16_t* const* w_parts, int n_parts, EncodeLaunch p,
                                    float* out_f32, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t stream);
+// the same fp32-accurate product (x and W as three bf16 parts each, six partial products) in ONE launch: both operands
+// stream through the ring, every product lands in the same TMEM accumulator, the output is written once
+// (p.bias / p.act applied; p.n_tiles as for encode_dense_tc_launch; a range schedule over num_sms / 2 CTA pairs)
+const char* encode_dense_split_launch(const uint16_t* const* x_parts, const uint16_t* const* w_parts, EncodeLaunch p,
+                                      float* out_f32, uint16_t* out_hi, uint16_t* out_lo, int num_sms, cudaStream_t stream);
 // src -> three bf16 parts with hi + mid + lo == src exactly (24 mantissa bits); mid / lo may be null
 const char* split_bf16x3_launch(const float* src, uint16_t* hi, uint16_t* mid, uint16_t* lo, size_t n, cudaStream_t stream);
 

@@ -113,28 +113,61 @@ __global__ void unpack_matryoshka_t_kernel(const uint32_t* __restrict__ packed, 
   }
 }
 
-// a[b, h] = (z[b, h] >= thr) ? scale[h] : 0, as bf16 hi + lo (hi + lo = scale to 2^-17); per-level activity counts
+// a[b, h] = (z[b, h] >= thr) ? scale[h] : 0, as bf16 hi + lo (hi + lo = scale to 2^-17); per-level activity counts.
+// HBM-streaming (4 B read, 4 B written per element): 8 consecutive latents per thread through 16-byte accesses; a
+// group of 8 lies inside one level (level boundaries are multiples of 8), its count is added once per warp when
+// the warp's groups share the level (the usual case), else per lane.
 __global__ void __launch_bounds__(256)
 matryoshka_dense_operand_kernel(const float* __restrict__ z, int B, int H, const float* __restrict__ scale, float thr,
                                 const int* __restrict__ level_start, int n_levels, uint16_t* __restrict__ a_hi,
                                 uint16_t* __restrict__ a_lo, unsigned* __restrict__ count_partial /* [gridDim.x, 32] */) {
   __shared__ unsigned s_cnt[32];
+  __shared__ int s_start[33];
   if (threadIdx.x < 32) s_cnt[threadIdx.x] = 0u;
+  if (threadIdx.x <= n_levels) s_start[threadIdx.x] = level_start[threadIdx.x];
   __syncthreads();
-  const size_t total = static_cast<size_t>(B) * H;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned h8 = static_cast<unsigned>(H >> 3);
+  const size_t groups = static_cast<size_t>(B) * h8;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
-    const int h = static_cast<int>(e % H);
-    const bool active = z[e] >= thr;
-    const float a = active ? scale[h] : 0.f;
-    const __nv_bfloat16 hi = __float2bfloat16_rn(a);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(a - __bfloat162float(hi));
-    a_hi[e] = *reinterpret_cast<const uint16_t*>(&hi);
-    a_lo[e] = *reinterpret_cast<const uint16_t*>(&lo);
-    if (active) {
-      int lvl = 0;
-      while (lvl + 1 < n_levels && h >= level_start[lvl + 1]) ++lvl;
-      atomicAdd(&s_cnt[lvl], 1u);
+  const size_t first = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // whole warps iterate together (the tail lanes of the last iteration carry an empty group)
+  for (size_t g0 = first - lane; g0 < groups; g0 += stride) {
+    const size_t g = g0 + lane;
+    const bool live = g < groups;
+    int lvl = -1;
+    unsigned n_act = 0u;
+    if (live) {
+      const int h = static_cast<int>(g % h8) << 3;
+      const float4 z0 = __ldcs(reinterpret_cast<const float4*>(z + g * 8));
+      const float4 z1 = __ldcs(reinterpret_cast<const float4*>(z + g * 8) + 1);
+      const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + h));
+      const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + h) + 1);
+      const float zv[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+      const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool a0 = zv[2 * i] >= thr, a1 = zv[2 * i + 1] >= thr;
+        n_act += (a0 ? 1u : 0u) + (a1 ? 1u : 0u);
+        const float v0 = a0 ? sv[2 * i] : 0.f, v1 = a1 ? sv[2 * i + 1] : 0.f;
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
+        const __nv_bfloat162 ll = __floats2bfloat162_rn(v0 - __bfloat162float(hh.x), v1 - __bfloat162float(hh.y));
+        hi[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        lo[i] = *reinterpret_cast<const uint32_t*>(&ll);
+      }
+      *reinterpret_cast<uint4*>(a_hi + g * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(a_lo + g * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      lvl = 0;
+      while (lvl + 1 < n_levels && h >= s_start[lvl + 1]) ++lvl;
+    }
+    const int lvl0 = __shfl_sync(full, lvl, 0);
+    if (__all_sync(full, lvl == lvl0)) {
+      const unsigned tot = __reduce_add_sync(full, n_act);
+      if (lane == 0 && tot != 0u) atomicAdd(&s_cnt[lvl0], tot);
+    } else if (n_act != 0u) {
+      atomicAdd(&s_cnt[lvl], n_act);
     }
   }
   __syncthreads();
@@ -308,23 +341,21 @@ decode_matryoshka_kernel(const uint2* __restrict__ cand, const int* __restrict__
   }
 }
 
-// level_count[l] += sum over the partial rows (one block; fixed order)
+// level_count[l] += sum over the partial rows (one block per level; fixed order)
 __global__ void __launch_bounds__(256)
 sum_level_counts_kernel(const unsigned* __restrict__ partial, int n_rows, int stride, int n_levels,
                         unsigned long long* __restrict__ level_count) {
   __shared__ unsigned long long s[256];
-  for (int l = 0; l < n_levels; ++l) {
-    unsigned long long a = 0ull;
-    for (int r = threadIdx.x; r < n_rows; r += blockDim.x) a += partial[static_cast<size_t>(r) * stride + l];
-    s[threadIdx.x] = a;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) level_count[l] += s[0];
+  const int l = blockIdx.x;
+  unsigned long long a = 0ull;
+  for (int r = threadIdx.x; r < n_rows; r += blockDim.x) a += partial[static_cast<size_t>(r) * stride + l];
+  s[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
     __syncthreads();
   }
+  if (threadIdx.x == 0) level_count[l] += s[0];
 }
 
 }  // namespace
@@ -348,7 +379,9 @@ size_t matryoshka_dense_operand_scratch_bytes() { return static_cast<size_t>(148
 const char* matryoshka_dense_operand_launch(const float* z, int B, int H, const float* scale, float thr,
                                             const int* level_start, int n_levels, uint16_t* a_hi, uint16_t* a_lo,
                                             unsigned long long* level_count, void* scratch, cudaStream_t stream) {
-  size_t g = (static_cast<size_t>(B) * H + 255) / 256;
+  if ((H % 8) != 0) return "matryoshka_dense_operand: H must be a multiple of 8";
+  if (n_levels > 32) return "matryoshka_dense_operand: at most 32 levels";
+  size_t g = (static_cast<size_t>(B) * (H / 8) + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
   unsigned* partial = static_cast<unsigned*>(scratch);
   matryoshka_dense_operand_kernel<<<static_cast<int>(g), 256, 0, stream>>>(z, B, H, scale, thr, level_start, n_levels,
@@ -356,7 +389,7 @@ const char* matryoshka_dense_operand_launch(const float* z, int B, int H, const 
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cudaGetErrorString(e);
   count_launches(1);
-  sum_level_counts_kernel<<<1, 256, 0, stream>>>(partial, static_cast<int>(g), 32, n_levels, level_count);
+  sum_level_counts_kernel<<<n_levels, 256, 0, stream>>>(partial, static_cast<int>(g), 32, n_levels, level_count);
   return cuda_err(cudaGetLastError());
 }
 

@@ -36,6 +36,8 @@ void reload_tuning() {
   t.prior_prep = env_int("QSAE_PRIOR_PREP", 1);
   t.dense_range = env_int("QSAE_DENSE_RANGE", 0);
   t.dense_flags_mask = env_int("QSAE_DENSE_FLAGS_MASK", -1);
+  t.dense_split_fused = env_int("QSAE_DENSE_SPLIT_FUSED", 1);
+  t.dense_step_fused = env_int("QSAE_DENSE_STEP_FUSED", 1);
   t.decode_pair = env_int("QSAE_DECODE_PAIR", -1);
   t.peer_timeout_ms = env_int("QSAE_PEER_TIMEOUT_MS", 20000);
   t.debug_large = getenv("QSAE_DEBUG_LARGE") != nullptr;
@@ -1080,18 +1082,27 @@ namespace {
 // Dense pre-activations (+ activation) on the tensor cores.
 //   w_mid == w_lo == nullptr: one pass over bf16(x) and w_hi (fast mode).
 //   otherwise: fp32-accurate product through 8 + 8 + 8-bit operand splits, x = xh + xm + xl and
-//   W = wh + wm + wl (both exact), keeping the six partial products above 2^-24:
+//   W = wh + wm + wl (both exact), keeping the six partial products above 2^-24 -- by default in ONE launch
+//   (encode_dense_split_kernel: both operands streamed, one accumulator, outputs written once); with
+//   QSAE_DENSE_SPLIT_FUSED=0 as the three accumulating passes of the first version:
 //     pass 1: xh * (wh + wm + wl) -> out      pass 2: out += xm * (wh + wm)
 //     pass 3: out = act(out + xl * wh + bias), bf16 hi (+ lo) of the result written alongside.
 //   Each pass is one launch of the dense encoder kernel (the x tile is resident in shared memory, the W
 //   parts stream through the ring into the same TMEM accumulator).
 // x_parts: workspace for the bf16 part(s) of x, 3 * align_up(B * D * 2, 1024) bytes in split mode.
+// step: act == 2 only (EncodeLaunch::step_*): the q_sae dense path's A operand written by the epilogue.
+struct StepOperand { float thr; const float* scale; const int* level_start; int n_levels; unsigned long long* level_count; };
 int dense_encode_tc(const float* x_f32, const uint16_t* w_hi, const uint16_t* w_mid, const uint16_t* w_lo,
                     const float* b_enc, int B, int H, int D, int act, uint8_t* x_parts, float* out_f32, uint16_t* out_hi,
-                    uint16_t* out_lo, cudaStream_t st) {
+                    uint16_t* out_lo, cudaStream_t st, const StepOperand* step = nullptr) {
   EncodeLaunch el;
   memset(&el, 0, sizeof(el));
   el.B = B; el.H = H; el.D = D; el.act = act; el.bias = b_enc;
+  if (act == 2) {
+    if (!step) return fail(QSAE_ERR_INVALID_ARGUMENT, "dense encoder: step operand without its description");
+    el.step_thr = step->thr; el.step_scale = step->scale; el.step_level_start = step->level_start;
+    el.step_n_levels = step->n_levels; el.step_level_count = step->level_count;
+  }
   el.n_tiles = (H + kEncBN - 1) / kEncBN;
   el.n_splits = encode_pick_splits(B, H, num_sms());
   el.tiles_per_split = (el.n_tiles + el.n_splits - 1) / el.n_splits;
@@ -1115,6 +1126,17 @@ int dense_encode_tc(const float* x_f32, const uint16_t* w_hi, const uint16_t* w_
   uint16_t* xl = reinterpret_cast<uint16_t*>(x_parts + 2 * xstride);
   int rc = launch_status("split x", split_bf16x3_launch(x_f32, xh, xm, xl, xn, st));
   if (rc != QSAE_OK) return rc;
+  if (act == 2 && !(tuning().dense_split_fused != 0 && tuning().dense_range == 0))
+    return fail(QSAE_ERR_INVALID_ARGUMENT, "dense encoder: the step operand needs the one-launch split kernel");
+  if (tuning().dense_split_fused != 0 && tuning().dense_range == 0) {
+    // one launch: all six partial products into one TMEM accumulator, outputs written once
+    const uint16_t* xp[3] = {xh, xm, xl};
+    const uint16_t* wp[3] = {w_hi, w_mid, w_lo};
+    if (g_enc_ev_start) cudaEventRecord(g_enc_ev_start, st);
+    rc = launch_status("encode kernel (dense, split operands)", encode_dense_split_launch(xp, wp, el, out_f32, out_hi, out_lo, num_sms(), st));
+    if (g_enc_ev_stop) cudaEventRecord(g_enc_ev_stop, st);
+    return rc;
+  }
   el.bias = nullptr;            // the kernel's bias loader treats a null bias as zeros; the final pass adds b_enc
   el.accum_bias = b_enc;
   const uint16_t* p1[3] = {w_hi, w_mid, w_lo};
@@ -1256,15 +1278,26 @@ int qsae_matryoshka_forward_dense(const float* x_f32, const uint16_t* w_hi, cons
   cudaStream_t st = S(stream);
   cudaError_t ce = cudaMemsetAsync(level_count, 0, static_cast<size_t>(n_levels) * sizeof(unsigned long long), st);
   if (ce != cudaSuccess) return fail(QSAE_ERR_CUDA, "matryoshka_forward_dense: %s", cudaGetErrorString(ce));
-  // 1. dense pre-activations on the tensor cores: one bf16 pass, or the fp32-accurate split passes when
+  // 1. dense pre-activations on the tensor cores: one bf16 pass, or the fp32-accurate split product when
   //    the mid / lo parts of W are given (exact activity decisions for any fp32 operands)
-  rc = dense_encode_tc(x_f32, w_hi, w_mid, w_lo, b_enc, B, H, D, QSAE_ACT_NONE, ws + mp.x_off, z, nullptr, nullptr, st);
-  if (rc != QSAE_OK) return rc;
-  // 2. A = active * scale, split into bf16 hi / lo; activity counts per level
-  rc = launch_status("matryoshka_dense_operand",
-                     matryoshka_dense_operand_launch(z, B, H, scale, kActiveThreshold, level_start_dev, n_levels, a_hi, a_lo,
-                                                     level_count, ws + mp.cnt_off, st));
-  if (rc != QSAE_OK) return rc;
+  // 2. A = active * scale, split into bf16 hi / lo; activity counts per level -- written by the encoder's
+  //    epilogue itself when the level boundaries are multiples of 128 (the fp32 pre-activations never reach
+  //    HBM: 1.07 GB of traffic and two launches less at B = 4096, H = 32768), else by a streaming kernel
+  bool fuse_step = tuning().dense_step_fused != 0 && tuning().dense_range == 0 &&
+                   ((w_mid == nullptr || w_lo == nullptr) || tuning().dense_split_fused != 0);
+  for (int i = 0; i <= n_levels; ++i) fuse_step = fuse_step && (level_start_host[i] % 128) == 0;
+  if (fuse_step) {
+    const StepOperand so = {kActiveThreshold, scale, level_start_dev, n_levels, level_count};
+    rc = dense_encode_tc(x_f32, w_hi, w_mid, w_lo, b_enc, B, H, D, 2, ws + mp.x_off, nullptr, a_hi, a_lo, st, &so);
+    if (rc != QSAE_OK) return rc;
+  } else {
+    rc = dense_encode_tc(x_f32, w_hi, w_mid, w_lo, b_enc, B, H, D, QSAE_ACT_NONE, ws + mp.x_off, z, nullptr, nullptr, st);
+    if (rc != QSAE_OK) return rc;
+    rc = launch_status("matryoshka_dense_operand",
+                       matryoshka_dense_operand_launch(z, B, H, scale, kActiveThreshold, level_start_dev, n_levels, a_hi, a_lo,
+                                                       level_count, ws + mp.cnt_off, st));
+    if (rc != QSAE_OK) return rc;
+  }
   // 3. one GEMM per level over its K range, outputs accumulated level by level (:121-129)
   const size_t bd = static_cast<size_t>(B) * D;
   for (int i = 0; i < n_levels; ++i) {

@@ -1122,6 +1122,57 @@ def test_qsae_untrained_model_falls_back_to_dense(cuda_device):
         m(T(inp["x"], cuda_device))
 
 
+@pytest.mark.parametrize("exact", [False, True])
+@pytest.mark.parametrize("B,H", [(160, 32768), (700, 4096), (40, 1024)])
+def test_qsae_dense_operand_from_the_encoder_epilogue(cuda_device, tuning, B, H, exact):
+    """The dense path's A operand (active * scale as bf16 hi / lo) and the per-level activity counts written by the
+    encoder epilogue itself (act = 2) against the first form: fp32 pre-activations to HBM + the streaming operand kernel.
+    Same activity decisions, same operand bits: identical outputs. exact: the one-launch split-operand encoder."""
+    cfg = dict(D=512, H=H, n_bits=4, abs_range=4.0, B=B, enc_bias=0.0, bf16=not exact, allow_bias=True, seed=B + H)
+    inp = cases.qsae_inputs(cfg)
+    m = Q.QuantizedMatryoshkaSAE(cfg["D"], H, 32, cfg["abs_range"], cfg["n_bits"], True)
+    m.load_state_dict({"encoder.0.weight": torch.from_numpy(inp["We"]), "encoder.0.bias": torch.from_numpy(inp["be"]),
+                       "decoder.weight": torch.from_numpy(inp["W"]), "decoder.weight_mirror": torch.from_numpy(inp["Wm"]),
+                       "decoder.bias": torch.from_numpy(inp["bd"])}, strict=True)
+    m.to(cuda_device).eval()
+    m.dense_mode, m.exact = "always", exact
+    x = T(inp["x"], cuda_device)
+    with torch.no_grad():
+        g1, r1 = m(x)
+        tuning("QSAE_DENSE_STEP_FUSED", "0")
+        g0, r0 = m(x)
+    assert [float(v) for v in g1] == [float(v) for v in g0]
+    assert all(torch.equal(a, b) for a, b in zip(r1, r0))
+    rg, rr, _ = O.qsae_forward(inp["x"], inp["We"], inp["be"], inp["W"], inp["Wm"], inp["bd"], n_bits=4, abs_range=4.0,
+                               allow_bias=True)
+    # fast mode: a pre-activation within fp32 accumulation noise of the threshold may fall on either side (a handful of
+    # the B * H decisions); exact mode decides every one like the fp32 reference
+    np.testing.assert_allclose(np.array([float(v) for v in g1]), rg, rtol=1e-6 if exact else 2e-5, atol=1e-6)
+    for i in range(4):
+        assert_recon_close(r1[i].cpu().numpy(), rr[i])
+
+
+@pytest.mark.parametrize("B,H,D", [(300, 8192, 512), (130, 1000, 72), (1024, 32768, 512)])
+def test_exact_dense_encoder_one_launch_vs_three_passes(cuda_device, tuning, B, H, D):
+    """encode_dense_split_kernel (all six partial products of the 3 x 3 bf16 split in one TMEM accumulator, both operands
+    streamed, range schedule over CTA pairs) against the three accumulating passes of the first version: both within
+    4e-6 of the fp64 product, and within 2e-6 * max|h| of each other (they differ in the fp32 accumulation order only)."""
+    x, W, b = _enc_case(B, H, D, seed=B + D + 1, bf16=False)
+    rng = np.random.default_rng(10)
+    wd = (0.4824 * rng.standard_normal((D, H))).astype(np.float32)
+    parts = L.split_bf16x3(T(W, cuda_device))
+    t_bf16, _ = L.pack_ternary(T(wd, cuda_device))
+    h1, r1 = L.tsae_forward(T(x, cuda_device), parts, T(b, cuda_device), t_bf16, exact=True)
+    tuning("QSAE_DENSE_SPLIT_FUSED", "0")
+    h3, r3 = L.tsae_forward(T(x, cuda_device), parts, T(b, cuda_device), t_bf16, exact=True)
+    h64 = np.maximum(x.astype(np.float64) @ W.astype(np.float64).T + b, 0)
+    scale = max(1.0, float(np.max(np.abs(h64))))
+    for h in (h1, h3):
+        assert np.max(np.abs(h.cpu().numpy() - h64)) <= 4e-6 * scale
+    assert float((h1 - h3).abs().max()) <= 2e-6 * scale
+    assert_recon_close(r1.cpu().numpy(), r3.cpu().numpy())
+
+
 def test_qsae_lazy_overflow_regime(cuda_device):
     """dense_mode = "auto" synchronises only on the first forward of a weight version. Sparse regime, then a batch whose
     activity overflows the survivor lists: that forward's outputs are NaN (never a silently wrong reconstruction), the
