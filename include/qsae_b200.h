@@ -118,6 +118,11 @@ int qsae_prepare_encoder_sample(const uint16_t* w_bf16, const float* b_enc, int 
                                 uint16_t* w_sample /* [n_sample, D] */, float* b_sample /* [n_sample] */,
                                 void* stream);
 
+/* Rows of the stratified encoder sample the sampled-prior path works best with for a dictionary of H latents
+ * (0: the dictionary is too small to sample; the class-bound path is used). H / QSAE_SAMPLE_DIV rounded up to whole
+ * 256-row tiles. What qsae_bsae_plan_create and the Python modules pass to qsae_prepare_encoder_sample. */
+int qsae_default_sample_rows(int H);
+
 /* Kernels this library has launched in this process (all threads, monotonic): what bench.py reports as gpu_launches. */
 unsigned long long qsae_launch_count(void);
 

@@ -34,6 +34,7 @@ SYMBOLS = {
     "qsae_set_encode_kernel_events": (_i, [_vp, _vp]),
     "qsae_launch_count": (C.c_ulonglong, []),
     "qsae_reload_tuning": (_i, []),
+    "qsae_default_sample_rows": (_i, [_i]),
     "qsae_set_stage_events": (_i, [_vp, _i]),
     "qsae_set_unordered_topk": (_i, [_i]),
     "qsae_prior_prep": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, C.POINTER(_i), _vp]),
@@ -234,7 +235,7 @@ def encode_topk_workspace_bytes(B: int, H: int, D: int, k: int, n_sample: int = 
 
 def default_sample_rows(H: int) -> int:
     """Rows of the sampled dictionary used for the prior threshold (0 = do not sample)."""
-    return ((H // 32 + 255) // 256) * 256 if H >= 8192 else 0
+    return int(load().qsae_default_sample_rows(int(H)))
 
 
 def prepare_sample(w_bf16: torch.Tensor, b_enc: torch.Tensor, n_sample: int | None = None):

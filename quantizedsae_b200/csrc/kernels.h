@@ -15,7 +15,7 @@ constexpr int kMaxK = 224;         // == QSAE_MAX_K: largest k of the warp-level
 constexpr int kMaxKLarge = 4096;   // == QSAE_MAX_K_LARGE: largest k of the block-level (radix select) paths
 constexpr size_t kSelectSmemBudget = 200 * 1024;   // shared memory of the block-per-row select kernels
 constexpr int kTopM = 64;          // values a thread keeps in the sample pre-pass (mode 5): top 2 of 32 column classes
-constexpr int kPriorMaxRank = 16;
+constexpr int kPriorMaxRank = 32;
 constexpr int kRescueSlots = 8;    // rows the tail kernel recomputes with the whole grid at a time (scratch: one dense row each)
 constexpr int kPriorCounters = 4 + kRescueSlots;   // ints zeroed per call: [0] rescue rows, [1] block-select rows, [4..] slot tickets  // largest rank m of the prior threshold among a row's nsub * kTopM kept values
 
@@ -28,6 +28,7 @@ struct Tuning {
   int encode_cluster;     // QSAE_ENCODE_CLUSTER: 0 / 1 / 2 forces the cluster variant (-1 = automatic)
   int encode_range;       // QSAE_ENCODE_RANGE: 0 keeps the (split, row block) grid at small batches
   int encode_range_pair;  // QSAE_ENCODE_RANGE_PAIR: 1 = cta_group::2 pairs on the range schedule (sparse sweeps)
+  int sample_div;         // QSAE_SAMPLE_DIV: the sampled prior works on H / sample_div of the latents
   int prior_prep;         // QSAE_PRIOR_PREP: 0 keeps the separate cast / pre-pass / prior kernels
   int dense_range;        // QSAE_DENSE_RANGE: 1 = dense epilogue (t_sae) on the range schedule instead of CTA pairs (experiment)
   int dense_flags_mask;   // QSAE_DENSE_FLAGS_MASK: masks dense epilogue outputs (-1 = off; timing experiments)

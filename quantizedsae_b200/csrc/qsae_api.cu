@@ -34,6 +34,8 @@ void reload_tuning() {
   t.encode_range = env_int("QSAE_ENCODE_RANGE", 1);
   t.encode_range_pair = env_int("QSAE_ENCODE_RANGE_PAIR", 1);
   t.prior_prep = env_int("QSAE_PRIOR_PREP", 1);
+  t.sample_div = env_int("QSAE_SAMPLE_DIV", 16);
+  if (t.sample_div < 8) t.sample_div = 8;   // the plan samples only when H >= 8 n_sample
   t.dense_range = env_int("QSAE_DENSE_RANGE", 0);
   t.dense_flags_mask = env_int("QSAE_DENSE_FLAGS_MASK", -1);
   t.dense_split_fused = env_int("QSAE_DENSE_SPLIT_FUSED", 1);
@@ -453,6 +455,11 @@ int qsae_set_encode_kernel_events(void* start_event, void* stop_event) {
 }
 
 unsigned long long qsae_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int qsae_default_sample_rows(int H) {
+  if (H < 8192) return 0;
+  return ((H / tuning().sample_div + 255) / 256) * 256;
+}
 
 int qsae_reload_tuning(void) {
   reload_tuning();
@@ -1609,7 +1616,7 @@ int qsae_bsae_plan_create(const float* w_enc, const float* b_enc, const float* l
   if (max_chunk_rows <= 0) return fail(QSAE_ERR_INVALID_ARGUMENT, "plan_create: max_chunk_rows must be positive");
   if (n_bits < 1 || n_bits > 8) return fail(QSAE_ERR_INVALID_ARGUMENT, "plan_create: 1 <= n_bits <= 8");
   size_t ws_bytes = 0;
-  const int n_sample = (H >= 8192) ? ((H / 32 + 255) / 256) * 256 : 0;
+  const int n_sample = qsae_default_sample_rows(H);
   int rc = qsae_encode_topk_workspace_bytes(max_chunk_rows, H, D, k, n_sample, &ws_bytes);
   if (rc != QSAE_OK) return rc;
   qsae_bsae_plan* p = new (std::nothrow) qsae_bsae_plan();
