@@ -113,7 +113,7 @@ int qsae_encode_topk_workspace_bytes(int B, int H, int D, int k, int n_sample, s
 
 /* Gather a stratified pseudo-random sample of n_sample dictionary rows (and their biases) for
  * the prior-threshold pre-pass of qsae_encode_topk. One-time, per weight version.
- * Recommended: n_sample = H / 32 rounded up to a multiple of 256, for H >= 8192. */
+ * Recommended: n_sample = qsae_default_sample_rows(H) (H / 16 rounded up to a multiple of 256, for H >= 8192). */
 int qsae_prepare_encoder_sample(const uint16_t* w_bf16, const float* b_enc, int H, int D, int n_sample,
                                 uint16_t* w_sample /* [n_sample, D] */, float* b_sample /* [n_sample] */,
                                 void* stream);
@@ -127,7 +127,8 @@ int qsae_default_sample_rows(int H);
 unsigned long long qsae_launch_count(void);
 
 /* Tuning / diagnostic switches (QSAE_ENCODE_SPLITS, QSAE_ENCODE_PRIOR, QSAE_ENCODE_CLUSTER, QSAE_ENCODE_RANGE,
- * QSAE_PRIOR_PREP, QSAE_DECODE_PAIR, QSAE_DEBUG_*) are read from the environment once, on first use, never on a
+ * QSAE_PRIOR_PREP, QSAE_SAMPLE_DIV, QSAE_DENSE_SPLIT_FUSED, QSAE_DENSE_STEP_FUSED, QSAE_DECODE_PAIR, QSAE_DEBUG_*) are
+ * read from the environment once, on first use, never on a
  * launch path. A process that changes them afterwards (tests, tuning runs) calls this to re-read them. */
 int qsae_reload_tuning(void);
 
@@ -353,9 +354,10 @@ int qsae_decode_dense(const uint16_t* a_hi /* [B, K] */, const uint16_t* a_lo /*
  *            order when x and W are bf16-representable), written as fp32 (h_out) and bf16 by TMA stores
  *            from the GEMM epilogue; recon from one pass over bf16(h) (relative error <= 2^-9 per term).
  * exact = 1: any fp32 operands. x and W are split exactly into three bf16 parts each and the six partial
- *            products above 2^-24 are accumulated on the tensor cores in three launches of the dense
- *            encoder (xh (wh + wm + wl); += xm (wh + wm); act(+ xl wh + b)); recon from two accumulating
- *            passes over the hi/lo split of h (2^-17 per term).
+ *            products above 2^-24 are accumulated on the tensor cores in ONE launch (both operands streamed,
+ *            all six products into the same TMEM accumulator, smallest first; QSAE_DENSE_SPLIT_FUSED=0: the
+ *            three accumulating launches of the first version); recon from two accumulating passes over the
+ *            hi/lo split of h (2^-17 per term).
  * H % 8 == 0, D % 8 == 0, 8 <= D <= 512. */
 int qsae_tsae_workspace_bytes(int B, int H, int D, int exact, size_t* bytes);
 int qsae_tsae_forward(const float* x_f32, const uint16_t* w_hi /* [H, D]: bf16(W) */,
