@@ -1140,7 +1140,7 @@ encode_dense_split_kernel(const __grid_constant__ CUtensorMap tmap_xh, const __g
 // it unless two of the row's top m fall into one of the 64 NS classes (17 % of the rows at m = 10, NS = 4: one rank
 // looser, ~3 % more survivors). The sweep's result never depends on it (count check + exact rescue).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kPrepStages = 2;
+constexpr int kPrepStages = 3;   // the exchange tile aliases the x operand (dead once the MMAs are done), which pays for the third stage
 constexpr int kPrepPitch = 65;   // floats per row of the exchange tile: 2 x 32 class maxima + 1 (conflict-free both ways)
 
 struct PrepSmem { uint32_t a_off, b_off, exch_off, bar_off, tmem_ptr_off, total; };
@@ -1148,8 +1148,12 @@ __host__ __device__ inline PrepSmem prep_smem_layout(int k_chunks) {
   PrepSmem L;
   L.a_off = 0;
   L.b_off = k_chunks * kABytesPerChunk;
-  L.exch_off = L.b_off + kPrepStages * kBBytesPerStage;
-  L.bar_off = L.exch_off + ((BM * kPrepPitch * 4 + 15) / 16) * 16;
+  // class maxima over the x operand when it is large enough (k_chunks >= 3: 48 KB >= 33 KB), else behind the ring
+  const uint32_t exch_bytes = ((BM * kPrepPitch * 4 + 15) / 16) * 16;
+  const uint32_t ring_end = L.b_off + kPrepStages * kBBytesPerStage;
+  const bool alias = static_cast<uint32_t>(k_chunks) * kABytesPerChunk >= exch_bytes;
+  L.exch_off = alias ? L.a_off : ring_end;
+  L.bar_off = alias ? ring_end : ring_end + exch_bytes;
   L.tmem_ptr_off = L.bar_off + 8 * (k_chunks + 2 * kPrepStages + 4);
   L.total = L.tmem_ptr_off + 16;
   return L;
@@ -1256,6 +1260,10 @@ prior_prep_kernel(const __grid_constant__ CUtensorMap tmap_w, PrepLaunch p) {
       }
     }
   }
+
+  // The class maxima are written over the x operand. A CTA with tiles writes them after its last accumulator is
+  // complete (every MMA has read the operand); a CTA without tiles must see all twelve warps' conversion stores first.
+  if (n_my_tiles == 0) __syncthreads();
 
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer: my tiles of the sampled rows
