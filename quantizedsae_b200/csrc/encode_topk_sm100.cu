@@ -978,7 +978,7 @@ __global__ void __launch_bounds__(cta_threads(true), 1)
 encode_dense_split_kernel(const __grid_constant__ CUtensorMap tmap_xh, const __grid_constant__ CUtensorMap tmap_xm,
                           const __grid_constant__ CUtensorMap tmap_xl, const __grid_constant__ CUtensorMap tmap_wh,
                           const __grid_constant__ CUtensorMap tmap_wm, const __grid_constant__ CUtensorMap tmap_wl,
-                          EncodeLaunch p, int k_chunks) {
+                          EncodeLaunch p, int k_chunks, int n_prod) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const SmemLayout L = split_smem_layout();
   uint8_t* ring = smem;
@@ -1006,7 +1006,10 @@ encode_dense_split_kernel(const __grid_constant__ CUtensorMap tmap_xh, const __g
   const int n_my = static_cast<int>(range_start(blockIdx.x / 2 + 1, U, G) - u0);
   const int rbp0 = static_cast<int>(u0 / n_tiles);
   const int tile0 = static_cast<int>(u0 - static_cast<long long>(rbp0) * n_tiles);
-  const int k_iters = 6 * k_chunks;
+  // n_prod = 6: the split-operand product; n_prod = 1: only xh wh (the fast mode's single bf16 product on this
+  // kernel's schedule: all 148 SMs at any batch, nothing resident)
+  const int k_iters = n_prod * k_chunks;
+  const int prod0 = 6 - n_prod;
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0u) {
@@ -1045,7 +1048,7 @@ encode_dense_split_kernel(const __grid_constant__ CUtensorMap tmap_xh, const __g
         const int n0 = tile * BN + static_cast<int>(cta_rank) * (BN / 2);
 #pragma unroll 1
         for (int it = 0; it < k_iters; ++it) {
-          const int prod = it / k_chunks, kc = it - prod * k_chunks;
+          const int pi = it / k_chunks, kc = it - pi * k_chunks, prod = prod0 + pi;
           // product order (smallest first): xl wh, xm wm, xh wl, xm wh, xh wm, xh wh
           const CUtensorMap* tx = (prod == 0) ? &tmap_xl : ((prod == 1 || prod == 3) ? &tmap_xm : &tmap_xh);
           const CUtensorMap* tw = (prod == 2) ? &tmap_wl : ((prod == 1 || prod == 4) ? &tmap_wm : &tmap_wh);
@@ -1498,10 +1501,8 @@ const char* launch_any(const CUtensorMap& tx, const BMaps& b, const EncodeLaunch
     case 6: e = launch_k<6, DENSE, 0>(tx, b, p, stream); break;
     case 7: e = launch_k<7, DENSE, 0>(tx, b, p, stream); break;
     case 8:   // the headline width: the cluster variants exist here
-      if (p.cluster == 3) {
-        if constexpr (DENSE) return "the pair range schedule has no dense epilogue";
-        else e = launch_k<8, false, 3>(tx, b, p, stream);
-      } else if (p.cluster == 2) e = launch_k<8, DENSE, 2>(tx, b, p, stream);
+      if (p.cluster == 3) e = launch_k<8, DENSE, 3>(tx, b, p, stream);
+      else if (p.cluster == 2) e = launch_k<8, DENSE, 2>(tx, b, p, stream);
       else if (p.cluster == 1) e = launch_k<8, DENSE, 1>(tx, b, p, stream);
       else e = launch_k<8, DENSE, 0>(tx, b, p, stream);
       break;
@@ -1617,21 +1618,22 @@ const char* encode_dense_tc_launch(const uint16_t* x_bf16, const uint16_t* const
   p.dense_flags = (out_f32 ? 1 : 0) | (out_hi ? 2 : 0) | (out_lo ? 4 : 0);
   if (p.dense_flags == 0) return "dense encoder: no output requested";
   if (tuning().dense_flags_mask >= 0) p.dense_flags &= tuning().dense_flags_mask;  // timing experiments only
-  p.cluster = p.range_g > 0 ? 0 : pick_cluster(p, kDefaultClusterDense);
+  p.cluster = p.range_g > 0 ? (p.range_pair ? 3 : 0) : pick_cluster(p, kDefaultClusterDense);
   BMaps bm;
   if (const char* err = make_b_maps(&bm, w_parts, n_parts, p)) return err;
   return launch_any<true>(tx, bm, p, stream);
 }
 
-const char* encode_dense_split_launch(const uint16_t* const* x_parts, const uint16_t* const* w_parts, EncodeLaunch p,
+const char* encode_dense_split_launch(const uint16_t* const* x_parts, const uint16_t* const* w_parts, int n_parts, EncodeLaunch p,
                                       float* out_f32, uint16_t* out_hi, uint16_t* out_lo, int num_sms, cudaStream_t stream) {
+  if (n_parts != 1 && n_parts != 3) return "dense tensor-core encoder (streamed operands): 1 or 3 parts per operand";
   if ((p.H % 8) != 0) return "dense tensor-core encoder needs H % 8 == 0";
   if ((reinterpret_cast<uintptr_t>(out_f32) | reinterpret_cast<uintptr_t>(out_hi) | reinterpret_cast<uintptr_t>(out_lo)) & 15)
     return "dense tensor-core encoder: outputs must be 16-byte aligned";
   if (p.act == 2 && (!p.step_scale || !p.step_level_start || !p.step_level_count || (p.H % 128) != 0))
     return "dense encoder: the step-operand epilogue needs scale / levels / counts and H % 128 == 0";
   p.out_f32 = out_f32; p.out_hi = out_hi; p.out_lo = out_lo;
-  p.k_parts = 3;
+  p.k_parts = n_parts;
   p.accum_mode = 0;
   p.range_g = 0;
   p.cluster = 2;
@@ -1640,8 +1642,9 @@ const char* encode_dense_split_launch(const uint16_t* const* x_parts, const uint
   if (tuning().dense_flags_mask >= 0) p.dense_flags &= tuning().dense_flags_mask;  // timing experiments only
   CUtensorMap tx[3], tw[3];
   for (int i = 0; i < 3; ++i) {
-    if (!make_tmap_bf16(&tx[i], x_parts[i], p.B, p.D, BM)) return "cuTensorMapEncodeTiled(x part) failed";
-    if (!make_tmap_bf16(&tw[i], w_parts[i], p.H, p.D, BN / 2)) return "cuTensorMapEncodeTiled(W part) failed";
+    const int j = i < n_parts ? i : 0;
+    if (!make_tmap_bf16(&tx[i], x_parts[j], p.B, p.D, BM)) return "cuTensorMapEncodeTiled(x part) failed";
+    if (!make_tmap_bf16(&tw[i], w_parts[j], p.H, p.D, BN / 2)) return "cuTensorMapEncodeTiled(W part) failed";
   }
   const SmemLayout L = split_smem_layout();
   static bool attr_set = false;
@@ -1667,7 +1670,8 @@ const char* encode_dense_split_launch(const uint16_t* const* x_parts, const uint
   cfg.attrs = at;
   cfg.numAttrs = 1;
   const int k_chunks = (p.D + BK - 1) / BK;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, encode_dense_split_kernel, tx[0], tx[1], tx[2], tw[0], tw[1], tw[2], p, k_chunks);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, encode_dense_split_kernel, tx[0], tx[1], tx[2], tw[0], tw[1], tw[2], p, k_chunks,
+                                     n_parts == 3 ? 6 : 1);
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 

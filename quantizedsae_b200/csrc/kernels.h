@@ -33,6 +33,7 @@ struct Tuning {
   int dense_range;        // QSAE_DENSE_RANGE: 1 = dense epilogue (t_sae) on the range schedule instead of CTA pairs (experiment)
   int dense_flags_mask;   // QSAE_DENSE_FLAGS_MASK: masks dense epilogue outputs (-1 = off; timing experiments)
   int dense_step_fused;   // QSAE_DENSE_STEP_FUSED: 0 = q_sae dense path writes fp32 pre-activations and runs the separate operand kernel
+  int dense_fast_streamed;  // QSAE_DENSE_FAST_STREAMED: 1 = fast-mode dense encoder on the streamed-operand kernel (range schedule over CTA pairs)
   int dense_split_fused;  // QSAE_DENSE_SPLIT_FUSED: 0 = exact dense encoder as three accumulating passes instead of the one-launch kernel
   int decode_pair;        // QSAE_DECODE_PAIR: 0 / 1 forces the decoder GEMM variant (-1 = automatic)
   int peer_timeout_ms;    // QSAE_PEER_TIMEOUT_MS: bound of a peer-memory flag wait (default 20000)
@@ -118,7 +119,8 @@ const char* encode_dense_tc_launch(const uint16_t* x_bf16, const uint16_t* const
 // the same fp32-accurate product (x and W as three bf16 parts each, six partial products) in ONE launch: both operands
 // stream through the ring, every product lands in the same TMEM accumulator, the output is written once
 // (p.bias / p.act applied; p.n_tiles as for encode_dense_tc_launch; a range schedule over num_sms / 2 CTA pairs)
-const char* encode_dense_split_launch(const uint16_t* const* x_parts, const uint16_t* const* w_parts, EncodeLaunch p,
+// n_parts = 1: only the bf16 product x_parts[0] w_parts[0] (fast mode) on the same schedule
+const char* encode_dense_split_launch(const uint16_t* const* x_parts, const uint16_t* const* w_parts, int n_parts, EncodeLaunch p,
                                       float* out_f32, uint16_t* out_hi, uint16_t* out_lo, int num_sms, cudaStream_t stream);
 // src -> three bf16 parts with hi + mid + lo == src exactly (24 mantissa bits); mid / lo may be null
 const char* split_bf16x3_launch(const float* src, uint16_t* hi, uint16_t* mid, uint16_t* lo, size_t n, cudaStream_t stream);

@@ -39,6 +39,7 @@ void reload_tuning() {
   t.dense_range = env_int("QSAE_DENSE_RANGE", 0);
   t.dense_flags_mask = env_int("QSAE_DENSE_FLAGS_MASK", -1);
   t.dense_split_fused = env_int("QSAE_DENSE_SPLIT_FUSED", 1);
+  t.dense_fast_streamed = env_int("QSAE_DENSE_FAST_STREAMED", 0);
   t.dense_step_fused = env_int("QSAE_DENSE_STEP_FUSED", 1);
   t.decode_pair = env_int("QSAE_DECODE_PAIR", -1);
   t.peer_timeout_ms = env_int("QSAE_PEER_TIMEOUT_MS", 20000);
@@ -1113,9 +1114,13 @@ int dense_encode_tc(const float* x_f32, const uint16_t* w_hi, const uint16_t* w_
   el.n_tiles = (H + kEncBN - 1) / kEncBN;
   el.n_splits = encode_pick_splits(B, H, num_sms());
   el.tiles_per_split = (el.n_tiles + el.n_splits - 1) / el.n_splits;
-  if (tuning().dense_range != 0) {   // one CTA per SM over contiguous tile ranges (single-CTA variant) instead of CTA pairs
+  if (tuning().dense_range == 1) {   // one CTA per SM over contiguous tile ranges (single-CTA variant) instead of CTA pairs
     int unused = 0;
     el.range_g = encode_pick_range(B, H, num_sms(), &unused);
+  } else if (tuning().dense_range == 2 && D > 448) {   // cta_group::2 pairs ON the range schedule (all SMs at small batches)
+    int unused = 0, pair = 0;
+    const int g = encode_pick_range(B, H, num_sms(), &unused, &pair);
+    if (g > 0 && pair) { el.range_g = g; el.range_pair = 1; }
   }
   const size_t xn = static_cast<size_t>(B) * D;
   const size_t xstride = align_up(xn * 2, 1024);
@@ -1125,6 +1130,11 @@ int dense_encode_tc(const float* x_f32, const uint16_t* w_hi, const uint16_t* w_
     if (rc != QSAE_OK) return rc;
     const uint16_t* parts[1] = {w_hi};
     if (g_enc_ev_start) cudaEventRecord(g_enc_ev_start, st);
+    if (tuning().dense_fast_streamed != 0 && tuning().dense_range != 1) {
+      const uint16_t* xp[1] = {xh};
+      rc = launch_status("encode kernel (dense, streamed operands)",
+                         encode_dense_split_launch(xp, parts, 1, el, out_f32, out_hi, out_lo, num_sms(), st));
+    } else
     rc = launch_status("encode kernel (dense)", encode_dense_tc_launch(xh, parts, 1, el, out_f32, out_hi, out_lo, st));
     if (g_enc_ev_stop) cudaEventRecord(g_enc_ev_stop, st);
     return rc;
@@ -1133,14 +1143,14 @@ int dense_encode_tc(const float* x_f32, const uint16_t* w_hi, const uint16_t* w_
   uint16_t* xl = reinterpret_cast<uint16_t*>(x_parts + 2 * xstride);
   int rc = launch_status("split x", split_bf16x3_launch(x_f32, xh, xm, xl, xn, st));
   if (rc != QSAE_OK) return rc;
-  if (act == 2 && !(tuning().dense_split_fused != 0 && tuning().dense_range == 0))
+  if (act == 2 && !(tuning().dense_split_fused != 0 && tuning().dense_range != 1))
     return fail(QSAE_ERR_INVALID_ARGUMENT, "dense encoder: the step operand needs the one-launch split kernel");
-  if (tuning().dense_split_fused != 0 && tuning().dense_range == 0) {
+  if (tuning().dense_split_fused != 0 && tuning().dense_range != 1) {
     // one launch: all six partial products into one TMEM accumulator, outputs written once
     const uint16_t* xp[3] = {xh, xm, xl};
     const uint16_t* wp[3] = {w_hi, w_mid, w_lo};
     if (g_enc_ev_start) cudaEventRecord(g_enc_ev_start, st);
-    rc = launch_status("encode kernel (dense, split operands)", encode_dense_split_launch(xp, wp, el, out_f32, out_hi, out_lo, num_sms(), st));
+    rc = launch_status("encode kernel (dense, split operands)", encode_dense_split_launch(xp, wp, 3, el, out_f32, out_hi, out_lo, num_sms(), st));
     if (g_enc_ev_stop) cudaEventRecord(g_enc_ev_stop, st);
     return rc;
   }
@@ -1290,7 +1300,7 @@ int qsae_matryoshka_forward_dense(const float* x_f32, const uint16_t* w_hi, cons
   // 2. A = active * scale, split into bf16 hi / lo; activity counts per level -- written by the encoder's
   //    epilogue itself when the level boundaries are multiples of 128 (the fp32 pre-activations never reach
   //    HBM: 1.07 GB of traffic and two launches less at B = 4096, H = 32768), else by a streaming kernel
-  bool fuse_step = tuning().dense_step_fused != 0 && tuning().dense_range == 0 &&
+  bool fuse_step = tuning().dense_step_fused != 0 && tuning().dense_range != 1 &&
                    ((w_mid == nullptr || w_lo == nullptr) || tuning().dense_split_fused != 0);
   for (int i = 0; i <= n_levels; ++i) fuse_step = fuse_step && (level_start_host[i] % 128) == 0;
   if (fuse_step) {
