@@ -660,14 +660,45 @@ __device__ __forceinline__ void warp_bitonic_desc(K (&k)[P], int lane) {
   }
 }
 
-template <int P>
+// TAIL: 32 P + 1 keys (k_sel = 65, the reference's default k at H = 32768, would otherwise pay for the 128-key
+// network: 28 compare-exchange steps over four keys per lane instead of 21 over two). The smallest key is moved out
+// first -- it is the last element of the order whatever the rest looks like -- and the other 32 P are sorted.
+template <int P, bool TAIL = false>
 __device__ __forceinline__ void sort_and_emit(const SelectLaunch& p, int row, uint64_t* stage, int stage_rows, int out, int n,
                                               int k_sel, float worst_bf16, float max_dev, int lane) {
+  const unsigned full = 0xffffffffu;
   const uint64_t* sel = stage;
   uint64_t k[P];
 #pragma unroll
   for (int j = 0; j < P; ++j) k[j] = sel[j * 32 + lane];
+  uint64_t tail = 0ull;
+  if constexpr (TAIL) {
+    tail = sel[32 * P];                      // zero when the row has at most 32 P entries
+    uint64_t mn = k[0];
+#pragma unroll
+    for (int j = 1; j < P; ++j) mn = (k[j] < mn) ? k[j] : mn;
+    const uint32_t hmin = __reduce_min_sync(full, static_cast<uint32_t>(mn >> 32));
+    const uint32_t lmin = __reduce_min_sync(full, static_cast<uint32_t>(mn >> 32) == hmin ? static_cast<uint32_t>(mn) : 0xFFFFFFFFu);
+    const uint64_t wmin = (static_cast<uint64_t>(hmin) << 32) | lmin;
+    if (wmin < tail) {                       // warp-uniform; the keys of a full row are distinct (distinct columns)
+#pragma unroll
+      for (int j = 0; j < P; ++j) k[j] = (k[j] == wmin) ? tail : k[j];
+      tail = wmin;
+    }
+  }
   warp_bitonic_desc<P>(k, lane);
+  auto finish_row = [&](uint64_t kth_key) {  // by the thread that holds output position k_out - 1
+    int flag = 0;
+    if (p.exact && n > k_sel && p.k_out <= out) {
+      // every dropped candidate scored <= worst_bf16 on the tensor cores; certified when even 4x the
+      // largest observed rounding deviation cannot lift one of them over the exact k-th value
+      const float kth = sort_key_value(kth_key);
+      if (!(worst_bf16 + 4.f * max_dev < kth)) flag = 1;
+    }
+    // an uncertified row is recomputed exactly when a rescue pass follows (it then clears the flag)
+    if (flag != 0 && p.rescue_count != nullptr) p.rescue_rows[atomicAdd(p.rescue_count, 1)] = row;
+    if (p.out_flags != nullptr) p.out_flags[row] = flag;
+  };
 #pragma unroll
   for (int j = 0; j < P; ++j) {
     const int e = j * 32 + lane;
@@ -676,23 +707,18 @@ __device__ __forceinline__ void sort_and_emit(const SelectLaunch& p, int row, ui
       p.out_vals[static_cast<size_t>(row) * p.k_out + e] = valid ? sort_key_value(k[j]) : 0.f;
       p.out_idx[static_cast<size_t>(row) * p.k_out + e] = valid ? static_cast<int32_t>(sort_key_col(k[j])) : -1;
     }
-    if (e == p.k_out - 1) {
-      int flag = 0;
-      if (p.exact && n > k_sel && p.k_out <= out) {
-        // every dropped candidate scored <= worst_bf16 on the tensor cores; certified when even 4x the
-        // largest observed rounding deviation cannot lift one of them over the exact k-th value
-        const float kth = sort_key_value(k[j]);
-        if (!(worst_bf16 + 4.f * max_dev < kth)) flag = 1;
-      }
-      // an uncertified row is recomputed exactly when a rescue pass follows (it then clears the flag)
-      if (flag != 0 && p.rescue_count != nullptr) p.rescue_rows[atomicAdd(p.rescue_count, 1)] = row;
-      if (p.out_flags != nullptr) p.out_flags[row] = flag;
-    }
+    if (e == p.k_out - 1) finish_row(k[j]);
+  }
+  const bool tail_out = TAIL && 32 * P < p.k_out;    // the tail is output position 32 P
+  const bool tail_valid = tail_out && 32 * P < out;
+  if (tail_out && lane == 0) {
+    p.out_vals[static_cast<size_t>(row) * p.k_out + 32 * P] = tail_valid ? sort_key_value(tail) : 0.f;
+    p.out_idx[static_cast<size_t>(row) * p.k_out + 32 * P] = tail_valid ? static_cast<int32_t>(sort_key_col(tail)) : -1;
+    if (32 * P == p.k_out - 1) finish_row(tail);
   }
   if (p.dec_kind == 1) {
     // fused decode (sae/binary.py:38 restricted to the k winners), straight from the sorted registers. A row that
     // was just listed for the exact recomputation is decoded again by the tail kernel.
-    const unsigned full = 0xffffffffu;
     float amax = 0.f;
     bool bad = false;
 #pragma unroll
@@ -703,6 +729,11 @@ __device__ __forceinline__ void sort_and_emit(const SelectLaunch& p, int row, ui
         bad |= !(fabsf(v) <= 3.0e38f);
         amax = fmaxf(amax, fabsf(v));
       }
+    }
+    if (tail_valid) {
+      const float v = sort_key_value(tail);
+      bad |= !(fabsf(v) <= 3.0e38f);
+      amax = fmaxf(amax, fabsf(v));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(full, amax, o));
@@ -720,6 +751,11 @@ __device__ __forceinline__ void sort_and_emit(const SelectLaunch& p, int row, ui
         dec.template add_chunk<false>(valid ? sort_key_value(k[j]) : 0.f, valid ? static_cast<int>(sort_key_col(k[j])) : -1,
                                       min(32, p.k_out - j * 32), p.dec_packed, 64, lane);
       }
+    }
+    if (tail_out) {
+      const bool valid = tail_valid && lane == 0;
+      dec.template add_chunk<false>(valid ? sort_key_value(tail) : 0.f, valid ? static_cast<int>(sort_key_col(tail)) : -1, 1,
+                                    p.dec_packed, 64, lane);
     }
     dec.finish(p.dec_scale, p.dec_bias, p.dec_recon + static_cast<size_t>(row) * 512, 512, lane);
   }
@@ -894,6 +930,7 @@ __device__ __forceinline__ void small_row(const SelectLaunch& p, int row, int ks
   constexpr int kStageRows = R;   // 256-byte dictionary rows that fit the warp's 32 R x 8-byte staging area
   if (ksort <= 32) sort_and_emit<1>(p, row, sel, kStageRows, out, n, k_sel, worst_bf16, max_dev, lane);
   else if (ksort <= 64) sort_and_emit<2>(p, row, sel, kStageRows, out, n, k_sel, worst_bf16, max_dev, lane);
+  else if (p.k_sel == 65) sort_and_emit<2, true>(p, row, sel, kStageRows, out, n, k_sel, worst_bf16, max_dev, lane);
   else if (ksort <= 128) sort_and_emit<4>(p, row, sel, kStageRows, out, n, k_sel, worst_bf16, max_dev, lane);
   else sort_and_emit<8>(p, row, sel, kStageRows, out, n, k_sel, worst_bf16, max_dev, lane);
   __syncwarp();
