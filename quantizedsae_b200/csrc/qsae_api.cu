@@ -34,6 +34,7 @@ void reload_tuning() {
   t.encode_range = env_int("QSAE_ENCODE_RANGE", 1);
   t.encode_range_pair = env_int("QSAE_ENCODE_RANGE_PAIR", 1);
   t.prior_prep = env_int("QSAE_PRIOR_PREP", 1);
+  t.merge_tier = env_int("QSAE_MERGE_TIER", 0);
   t.sample_div = env_int("QSAE_SAMPLE_DIV", 16);
   if (t.sample_div < 8) t.sample_div = 8;   // the plan samples only when H >= 8 n_sample
   t.dense_range = env_int("QSAE_DENSE_RANGE", 0);
@@ -669,7 +670,19 @@ int encode_topk_impl(const float* x_f32, const uint16_t* w_bf16, const float* w_
     sl.dec_kind = 1; sl.dec_packed = fd->packed; sl.dec_scale = fd->scale; sl.dec_bias = fd->bias; sl.dec_recon = fd->recon;
     fd->done = true;
   }
-  rc = launch_status("select_small kernel", select_small_launch(sl, 16, nullptr, nullptr, num_sms(), counters + 1, ovf_rows, st));
+  // keys per lane: the survivors of the prior threshold are negative-binomial, m / r on average with a spread of
+  // sqrt(m) / r (r = n_sample / H). Large batches (many waves of merge warps, issue-bound) take the smallest tier
+  // that holds mean + 3 sigma: 12 keys per lane at k = 32 (267 vs 285 us at B = 65536); one wave of warps
+  // (B <= 8192) is latency-bound and faster with 16 (28.7 vs 34.8 us at B = 4096).
+  int tier = 16;
+  if (tuning().merge_tier > 0) tier = tuning().merge_tier;
+  else if (n_sample > 0 && pl.m > 0 && B > 8192) {
+    const double inv_r = static_cast<double>(H) / n_sample;
+    const double need = (pl.m + 3.0 * sqrt(static_cast<double>(pl.m))) * inv_r;
+    tier = need <= 256.0 ? 8 : (need <= 384.0 ? 12 : 16);
+  }
+  if (32 * tier < pl.k_sel) tier = 16;
+  rc = launch_status("select_small kernel", select_small_launch(sl, tier, nullptr, nullptr, num_sms(), counters + 1, ovf_rows, st));
   if (rc != QSAE_OK) return rc;
   stage_mark(3, st);
   // tail, one launch: rows the warp merge could not hold (floods of equal values) through the block-per-row select,

@@ -1110,9 +1110,10 @@ const char* select_small_launch(const SelectLaunch& p, int tier, const int* coun
   const int blocks = rows ? num_sms * 4 : (p.B + kSmallWarps - 1) / kSmallWarps;
   switch (tier) {
     case 8: select_small_kernel<8><<<blocks, kSmallWarps * 32, 0, stream>>>(p, ksort, count, rows, ovf_count, ovf_rows); break;
+    case 12: select_small_kernel<12><<<blocks, kSmallWarps * 32, 0, stream>>>(p, ksort, count, rows, ovf_count, ovf_rows); break;
     case 16: select_small_kernel<16><<<blocks, kSmallWarps * 32, 0, stream>>>(p, ksort, count, rows, ovf_count, ovf_rows); break;
     case 32: select_small_kernel<32><<<blocks, kSmallWarps * 32, 0, stream>>>(p, ksort, count, rows, ovf_count, ovf_rows); break;
-    default: return "select_small: tier must be 8, 16 or 32 keys per lane";
+    default: return "select_small: tier must be 8, 12, 16 or 32 keys per lane";
   }
   return cuda_err(cudaGetLastError());
 }
