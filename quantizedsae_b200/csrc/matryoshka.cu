@@ -185,8 +185,8 @@ constexpr int kMatWarps = 4;
 // warp-uniform. Activity counts are kept in registers over all rows of a warp and leave through a
 // [warps, n_levels] partial array that a second kernel sums: tens of thousands of atomics on n_levels
 // addresses serialise in L2 (measured: 3.9 ms of a 5.7 ms forward at B = 65536 before this change).
-template <int NL>
-__global__ void __launch_bounds__(kMatWarps * 32, 6)
+template <int NL, int BPS = 6>
+__global__ void __launch_bounds__(kMatWarps * 32, BPS)
 decode_matryoshka_kernel(const uint2* __restrict__ cand, const int* __restrict__ cand_cnt, int nsub,
                          int cap, int B, const uint32_t* __restrict__ packed,
                          const float* __restrict__ scale, const int* __restrict__ level_start,
@@ -419,18 +419,31 @@ const char* decode_matryoshka_launch(const void* cand, const int* cand_cnt, int 
                                      const float* resid_in, float* resid_out, const int* poison_flag) {
   if (n_levels > 8) return "decode_matryoshka: at most 8 levels (n_bits <= 8)";
   if (D > 512 || (D % 16) != 0) return "decode_matryoshka: D must be a multiple of 16, <= 512";
+  // Resident blocks per SM (launch bounds). Six (80 registers) is the fastest steady state; a batch whose rows fit one
+  // wave of 7 or 8 blocks per SM but not of 6 (B = 4096 on 148 SMs: 27.7 rows per SM against 24 warps) would run two
+  // half-empty waves of a latency-bound kernel, so it takes the smallest occupancy that holds every row at once.
+  int bps = 6;
+  if (tuning().mat_bps >= 6 && tuning().mat_bps <= 8) bps = tuning().mat_bps;
+  else if (tuning().mat_bps == 0) {
+    const long long rows_per_wave6 = static_cast<long long>(num_sms) * 6 * kMatWarps;
+    if (B > rows_per_wave6 && B <= static_cast<long long>(num_sms) * 7 * kMatWarps) bps = 7;
+    else if (B > rows_per_wave6 && B <= static_cast<long long>(num_sms) * 8 * kMatWarps) bps = 8;
+  }
   int blocks = (B + kMatWarps - 1) / kMatWarps;
-  if (blocks > num_sms * 6) blocks = num_sms * 6;   // = resident blocks (launch bounds: 6 per SM)
+  if (blocks > num_sms * bps) blocks = num_sms * bps;   // = resident blocks
   (void)scratch;   // round 1: per-warp partial counts for a second kernel; the counts now leave through atomics
   const uint2* c2 = reinterpret_cast<const uint2*>(cand);
-#define QSAE_MAT(NL) \
-  decode_matryoshka_kernel<NL><<<blocks, kMatWarps * 32, 0, stream>>>(c2, cand_cnt, nsub, cap, B, packed, scale, level_start, \
+#define QSAE_MAT_B(NL, BPS) \
+  decode_matryoshka_kernel<NL, BPS><<<blocks, kMatWarps * 32, 0, stream>>>(c2, cand_cnt, nsub, cap, B, packed, scale, level_start, \
       n_levels, H, D, bias, result, level_count, x_f32, w_f32, b_enc, thr_value, exact, active_idx, active_cap, active_cnt, \
       resid_in, resid_out, poison_flag)
+#define QSAE_MAT(NL) \
+  do { if (bps == 8) QSAE_MAT_B(NL, 8); else if (bps == 7) QSAE_MAT_B(NL, 7); else QSAE_MAT_B(NL, 6); } while (0)
   if (n_levels <= 1) QSAE_MAT(1);
   else if (n_levels <= 2) QSAE_MAT(2);
   else if (n_levels <= 4) QSAE_MAT(4);
   else QSAE_MAT(8);
+#undef QSAE_MAT_B
 #undef QSAE_MAT
   return cuda_err(cudaGetLastError());
 }

@@ -34,6 +34,7 @@ void reload_tuning() {
   t.encode_range = env_int("QSAE_ENCODE_RANGE", 1);
   t.encode_range_pair = env_int("QSAE_ENCODE_RANGE_PAIR", 1);
   t.prior_prep = env_int("QSAE_PRIOR_PREP", 1);
+  t.mat_bps = env_int("QSAE_MAT_BPS", 0);
   t.merge_tier = env_int("QSAE_MERGE_TIER", 0);
   t.sample_div = env_int("QSAE_SAMPLE_DIV", 16);
   if (t.sample_div < 8) t.sample_div = 8;   // the plan samples only when H >= 8 n_sample
