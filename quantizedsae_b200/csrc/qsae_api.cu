@@ -1148,8 +1148,9 @@ int dense_encode_tc(const float* x_f32, const uint16_t* w_hi, const uint16_t* w_
       const uint16_t* xp[1] = {xh};
       rc = launch_status("encode kernel (dense, streamed operands)",
                          encode_dense_split_launch(xp, parts, 1, el, out_f32, out_hi, out_lo, num_sms(), st));
-    } else
-    rc = launch_status("encode kernel (dense)", encode_dense_tc_launch(xh, parts, 1, el, out_f32, out_hi, out_lo, st));
+    } else {
+      rc = launch_status("encode kernel (dense)", encode_dense_tc_launch(xh, parts, 1, el, out_f32, out_hi, out_lo, st));
+    }
     if (g_enc_ev_stop) cudaEventRecord(g_enc_ev_stop, st);
     return rc;
   }
