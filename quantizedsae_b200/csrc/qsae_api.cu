@@ -200,7 +200,10 @@ int plan_encode(int B, int H, int D, int k, int exact, int n_sample, EncodePlan*
   pl->m = 0;
   if (n_sample >= 256 && H >= 8 * static_cast<long long>(n_sample)) {
     const int m = choose_prior_rank(k_sel, static_cast<double>(n_sample) / H);
-    if (tuning().encode_prior != 0 && m <= kPriorMaxRank && m <= n_sample) {
+    // the warp merge holds 512 survivors per row in registers; the prior pays while mean + sigma of the survivor
+    // count (m / r, sqrt(m) / r) stays inside (k_sel <= 128 at r = 1 / 16), above that the class-bound modes take over
+    const bool fits = (m + sqrt(static_cast<double>(m))) * (static_cast<double>(H) / n_sample) <= 512.0;
+    if (tuning().encode_prior != 0 && m <= kPriorMaxRank && m <= n_sample && fits) {
       pl->use_prior = true;
       pl->m = m;
     }

@@ -535,6 +535,25 @@ def test_prior_threshold_path_matches_oracle(cuda_device, k, exact):
     assert torch.equal(i0, idx) and torch.equal(v0, vals)
 
 
+@pytest.mark.parametrize("k,exact", [(65, False), (65, True), (100, False)])
+def test_prior_ranks_above_16_on_the_separate_prior_kernels(cuda_device, k, exact):
+    """B = 9600 rows is past the single-launch prior kernel (2 x 75 row blocks > 148 SMs): cast, sample pre-pass (top-2 per
+    column class) and the sorting prior kernel run as separate launches. With the H / 16 sample the prior ranks are
+    18 (k_sel = 65), 20 (k_sel = 81, exact) and 23 (k_sel = 100): above the old limit of 16. Same result as without the
+    sample, and the oracle's indices on a strided subset of the rows."""
+    B, H, D = 9600, 32768, 512
+    x, W, b = _enc_case(B, H, D, 80 + k, bf16=not exact)
+    dx, dW, db = T(x, cuda_device), T(W, cuda_device), T(b, cuda_device)
+    wb = L.cast_bf16(dW)
+    sample = L.prepare_sample(wb, db)
+    vals, idx, flags = L.encode_topk(dx, wb, dW if exact else None, db, k, exact=exact, want_flags=True, sample=sample)
+    assert int((flags != 0).sum()) == 0
+    v0, i0, _ = L.encode_topk(dx, wb, dW if exact else None, db, k, exact=exact)
+    assert torch.equal(i0, idx) and torch.equal(v0, vals)
+    rows = np.arange(0, B, 25)
+    assert_topk_matches(vals[rows].cpu().numpy(), idx[rows].cpu().numpy(), O.encode_pre(x[rows], W, b), k)
+
+
 @pytest.mark.parametrize("k,exact", [(32, False), (65, False), (32, True)])
 def test_heavy_tailed_activations(cuda_device, k, exact):
     """SURVEY 8d config 1, heavy-tail variant: 8 of the 512 input dimensions scaled by 20 (outlier residual-stream
