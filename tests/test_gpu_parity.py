@@ -1322,7 +1322,7 @@ def test_decoder_gemm_pair_variant_is_bit_identical(cuda_device, tuning, B, K, N
     assert_recon_close(two.cpu().numpy(), (a.astype(np.float64) @ t.T.astype(np.float64)).astype(np.float32))
 
 
-@pytest.mark.parametrize("B,H,D", [(24, 4096, 512), (300, 8192, 512), (130, 1000, 72), (512, 32768, 512)])
+@pytest.mark.parametrize("B,H,D", [(24, 4096, 512), (300, 8192, 512), (130, 1000, 72), (512, 32768, 512), (1, 304, 8), (129, 264, 16), (257, 8, 8)])
 def test_exact_dense_encoder_split_passes(cuda_device, B, H, D):
     """fp32-accurate dense encoder on the tensor cores (3 x 3 bf16 operand split, three accumulating
     launches; single-CTA variant for small shapes, cta_group::2 pairs for D = 512 and B > 128):
