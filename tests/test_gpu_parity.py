@@ -1143,7 +1143,7 @@ def test_qsae_untrained_model_falls_back_to_dense(cuda_device):
 
 
 @pytest.mark.parametrize("exact", [False, True])
-@pytest.mark.parametrize("B,H", [(160, 32768), (700, 4096), (40, 1024)])
+@pytest.mark.parametrize("B,H", [(160, 32768), (700, 4096), (40, 1024), (90, 832)])
 def test_qsae_dense_operand_from_the_encoder_epilogue(cuda_device, tuning, B, H, exact):
     """The dense path's A operand (active * scale as bf16 hi / lo) and the per-level activity counts written by the
     encoder epilogue itself (act = 2) against the first form: fp32 pre-activations to HBM + the streaming operand kernel.
