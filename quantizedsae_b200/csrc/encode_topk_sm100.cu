@@ -66,7 +66,8 @@ __host__ __device__ constexpr int epi_warps(bool dense) { return 8; }
 __host__ __device__ constexpr int cta_threads(bool dense) { return 128 + epi_warps(dense) * 32; }
 constexpr int kTmemCols = 512;                  // 2 accumulators x 256 columns
 
-constexpr int kMaxPieces = 4;   // pieces of one CTA's range (a range is shorter than a row block: at most 2; see PieceIter)
+constexpr int kMaxPieces = 8;   // pieces of one CTA's range: 2 when a range is shorter than a row block (full sweeps), up to
+                                // ceil(range / tiles per row block) + 1 for short sweeps (the sample pre-pass); checked by encode_pick_range
 struct SmemLayout {
   uint32_t a_off, b_off, staging_off, bias_off, share_off, bar_off, tmem_ptr_off, piece_off, total;
 };
@@ -346,6 +347,14 @@ __device__ __forceinline__ void epilogue_loop(const EncodeLaunch& p, int n_my_ti
 #pragma unroll
       for (int i = 0; i < kTopM / 4; ++i)
         dst[i] = make_float4(tm[4 * i], tm[4 * i + 1], tm[4 * i + 2], tm[4 * i + 3]);
+      if (zero_from >= 0 && half == 0) {   // range schedule: the row block's unused lists hold no values
+        const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        for (int s2 = zero_from; s2 < nsub; ++s2) {
+          float4* z = reinterpret_cast<float4*>(p.top_out + (static_cast<size_t>(row) * nsub + s2) * kTopM);
+#pragma unroll
+          for (int i = 0; i < kTopM / 4; ++i) z[i] = ninf;
+        }
+      }
     }
   } else if (row_ok) {
     p.cand_cnt[slot] = cnt;
@@ -1538,10 +1547,10 @@ int encode_pick_splits(int B, int H, int num_sms) {
   return best_s;
 }
 
-int encode_pick_range(int B, int H, int num_sms, int* nsub, int* pair) {
+int encode_pick_range(int B, int H, int num_sms, int* nsub, int* pair, bool any_batch) {
   *nsub = 0;
   if (pair) *pair = 0;
-  if (tuning().encode_range == 0 || B >= 16384) return 0;   // large batches: the multicast pairs take over
+  if (tuning().encode_range == 0 || (B >= 16384 && !any_batch)) return 0;   // large batches: the multicast pairs take over
   const long long m_tiles = (B + BM - 1) / BM;
   const long long n_tiles = (H + BN - 1) / BN;
   const long long U = m_tiles * n_tiles;
@@ -1551,7 +1560,7 @@ int encode_pick_range(int B, int H, int num_sms, int* nsub, int* pair) {
   const long long tps = (n_tiles + s - 1) / s;
   const double eff = (static_cast<double>(units) / (waves * num_sms)) *
                      (static_cast<double>(n_tiles) / (static_cast<double>(tps) * s));
-  if (eff >= 0.95 || U < 2ll * num_sms) return 0;
+  if ((eff >= 0.95 && !any_batch) || U < 2ll * num_sms) return 0;
   // cta_group::2 pairs on the range schedule: the units are (pair of row blocks, tile), one pair per two SMs. Halves the
   // W bytes every SM pulls from L2 (the single-CTA sweep runs at the L2 slice limit: 3.5 us per tile against 3.1 us
   // for the pair). Needs whole pairs of full row blocks.
@@ -1566,6 +1575,8 @@ int encode_pick_range(int B, int H, int num_sms, int* nsub, int* pair) {
     if (pieces > max_pieces) max_pieces = pieces;
   }
   if (2 * max_pieces > 32) return 0;   // the warp-level merge reads at most 32 lists per row
+  const long long range_len = (Ur + G - 1) / G;
+  if ((range_len + n_tiles - 1) / n_tiles + 1 > kMaxPieces) return 0;   // pieces of one CTA's range (its piece table)
   *nsub = 2 * max_pieces;
   if (pair) *pair = use_pair ? 1 : 0;
   return static_cast<int>(G);

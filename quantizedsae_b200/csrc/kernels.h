@@ -29,6 +29,7 @@ struct Tuning {
   int encode_range;       // QSAE_ENCODE_RANGE: 0 keeps the (split, row block) grid at small batches
   int encode_range_pair;  // QSAE_ENCODE_RANGE_PAIR: 1 = cta_group::2 pairs on the range schedule (sparse sweeps)
   int mat_bps;            // QSAE_MAT_BPS: 6 / 7 / 8 forces the resident blocks per SM of the q_sae level decoder (0 = automatic, -1 = always 6)
+  int prepass_range;      // QSAE_PREPASS_RANGE: 1 = sample pre-pass of large batches on the pair range schedule (experiment; no gain measured)
   int merge_tier;         // QSAE_MERGE_TIER: 8 / 12 / 16 forces the keys per lane of the warp merge (0 = from the expected survivor count)
   int sample_div;         // QSAE_SAMPLE_DIV: the sampled prior works on H / sample_div of the latents
   int prior_prep;         // QSAE_PRIOR_PREP: 0 keeps the separate cast / pre-pass / prior kernels
@@ -90,7 +91,9 @@ struct EncodeLaunch {
 // encode_topk_sm100.cu
 int encode_pick_splits(int B, int H, int num_sms);
 // range schedule for this shape: CTAs to launch (0 = keep the (split, row block) grid) and lists per row
-int encode_pick_range(int B, int H, int num_sms, int* nsub, int* pair = nullptr);
+// any_batch: also for B >= 16384 (short sweeps such as the sample pre-pass, where a (split, row block) CTA has only a
+// few tiles to amortise its x tile over)
+int encode_pick_range(int B, int H, int num_sms, int* nsub, int* pair = nullptr, bool any_batch = false);
 void encode_pick_mode(int k_sel, int* mode, int* cap);
 const char* encode_topk_launch(const uint16_t* x_bf16, const uint16_t* w_bf16, EncodeLaunch p,
                                cudaStream_t stream);

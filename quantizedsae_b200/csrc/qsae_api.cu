@@ -35,6 +35,7 @@ void reload_tuning() {
   t.encode_range_pair = env_int("QSAE_ENCODE_RANGE_PAIR", 1);
   t.prior_prep = env_int("QSAE_PRIOR_PREP", 1);
   t.mat_bps = env_int("QSAE_MAT_BPS", 0);
+  t.prepass_range = env_int("QSAE_PREPASS_RANGE", 0);
   t.merge_tier = env_int("QSAE_MERGE_TIER", 0);
   t.sample_div = env_int("QSAE_SAMPLE_DIV", 16);
   if (t.sample_div < 8) t.sample_div = 8;   // the plan samples only when H >= 8 n_sample
@@ -129,6 +130,20 @@ void plan_stage(int B, int H, int k_sel, StageKind kind, bool allow_split_overri
   if (kind == kStageSamplePre) {
     sp->mode = 5;   // register-resident class top-2, no survivor buffers: cand region = the kept values
     sp->cap = 0;
+    // Large batches: a (1 split, row block) CTA sweeps only the sample's few tiles (8 at H = 32768) per x tile and 512
+    // CTAs make 3.46 waves on 148 SMs. Experiment (QSAE_PREPASS_RANGE=1, off by default): CTA pairs on the range
+    // schedule sweep ~28 contiguous units each on every SM; a row block is then shared by at most two pairs (4 lists of
+    // kTopM values per row). Measured at B = 65536: pre-pass 139 -> 124 us (each of a range's 3-4 x-tile reloads drains
+    // the MMA pipeline) but the prior kernel reads twice the values (+15 us): no gain.
+    if (allow_range && tuning().prepass_range != 0 && sp->n_splits == 1 && (B + kEncBM - 1) / kEncBM >= num_sms() && D > 448) {
+      int range_nsub = 0, range_pair = 0;
+      const int g = encode_pick_range(B, H, num_sms(), &range_nsub, &range_pair, true);
+      if (g > 0 && range_pair && range_nsub <= 8) {
+        sp->range_g = g;
+        sp->range_pair = 1;
+        sp->nsub = range_nsub;
+      }
+    }
     sp->cand_off = align_up(base, 256);
     sp->cnt_off = sp->thr_off = sp->cand_off;
     sp->end = align_up(sp->cand_off + static_cast<size_t>(B) * sp->nsub * kTopM * 4, 256);
@@ -218,7 +233,7 @@ int plan_encode(int B, int H, int D, int k, int exact, int n_sample, EncodePlan*
     pl->prior_off = off; off = align_up(off + static_cast<size_t>(B) * 4, 256);
     pl->ovf_rows_off = off; off = align_up(off + static_cast<size_t>(B) * 4, 256);
     pl->rescue_z_off = off; off = align_up(off + static_cast<size_t>(kRescueSlots) * H * 4, 256);
-    plan_stage(B, n_sample, pl->m, kStageSamplePre, false, off, &pl->pre);
+    plan_stage(B, n_sample, pl->m, kStageSamplePre, false, off, &pl->pre, true, D);
     off = pl->pre.end;
   }
   pl->total = off;

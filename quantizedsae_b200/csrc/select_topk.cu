@@ -970,8 +970,20 @@ prior_from_top_kernel(const float* __restrict__ top, int B, int n, int m, float*
     const int slot = lane + 32 * i;
     key[i] = (slot < n) ? float_to_key(src[slot]) : 0u;   // padding sorts last
   }
-  warp_bitonic_desc<P>(key, lane);
-  if (lane == m - 1) prior[row] = key_to_float(key[0]);   // sorted position e = j * 32 + lane, m <= 32: j = 0
+  // m-th largest by m rounds of "take the maximum, retire every key equal to it" (m <= 32 rounds of ~3 P instructions
+  // instead of a bitonic network over 32 P keys). Equal keys retire together, so with ties the result is at most the
+  // true m-th largest: still a valid lower bound (the sweep's result never depends on it).
+  uint32_t T = 0u;
+#pragma unroll 1
+  for (int round = 0; round < m; ++round) {
+    uint32_t mx = key[0];
+#pragma unroll
+    for (int i = 1; i < P; ++i) mx = max(mx, key[i]);
+    T = __reduce_max_sync(0xffffffffu, mx);
+#pragma unroll
+    for (int i = 0; i < P; ++i) key[i] = (key[i] == T) ? 0u : key[i];
+  }
+  if (lane == 0) prior[row] = key_to_float(T);
 }
 
 // Streaming survivors from a dense row, one warp per row, lanes over 32 consecutive columns.
