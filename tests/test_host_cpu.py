@@ -29,6 +29,31 @@ def test_library_exports_every_declared_symbol():
     assert lib.qsae_abi_version() == 1
 
 
+def test_default_sample_rows_and_its_tuning_switch(monkeypatch):
+    """Rows of the stratified encoder sample (host logic of the sampled-prior path, no device call): H / 16 in whole
+    256-row tiles for dictionaries of at least 8192 latents, none below; QSAE_SAMPLE_DIV is read once and re-read by
+    qsae_reload_tuning; the workspace query accepts the recommended size."""
+    import ctypes as C
+
+    lib = _lib.load()
+    monkeypatch.delenv("QSAE_SAMPLE_DIV", raising=False)
+    assert lib.qsae_reload_tuning() == 0
+    assert [_lib.default_sample_rows(h) for h in (1024, 8191, 8192, 32768, 2 ** 17, 2 ** 20)] == [0, 0, 512, 2048, 8192, 65536]
+    assert _lib.default_sample_rows(40000) == 2560        # 2500 rounded up to whole tiles
+    monkeypatch.setenv("QSAE_SAMPLE_DIV", "32")
+    assert _lib.default_sample_rows(32768) == 2048        # cached until reloaded
+    assert lib.qsae_reload_tuning() == 0
+    assert _lib.default_sample_rows(32768) == 1024
+    monkeypatch.setenv("QSAE_SAMPLE_DIV", "2")             # clamped: the plan samples only when H >= 8 n_sample
+    assert lib.qsae_reload_tuning() == 0
+    assert _lib.default_sample_rows(32768) == 4096
+    monkeypatch.delenv("QSAE_SAMPLE_DIV")
+    assert lib.qsae_reload_tuning() == 0
+    n = C.c_size_t(0)
+    assert lib.qsae_encode_topk_workspace_bytes(4096, 32768, 512, 32, _lib.default_sample_rows(32768), C.byref(n)) == 0
+    assert n.value > 0
+
+
 def test_sass_is_blackwell_native():
     """tcgen05 / TMA / TMEM loads must be present in the built library (no GPU needed)."""
     import shutil
