@@ -33,7 +33,7 @@ struct Tuning {
   int merge_tier;         // QSAE_MERGE_TIER: 8 / 12 / 16 forces the keys per lane of the warp merge (0 = from the expected survivor count)
   int sample_div;         // QSAE_SAMPLE_DIV: the sampled prior works on H / sample_div of the latents
   int prior_prep;         // QSAE_PRIOR_PREP: 0 keeps the separate cast / pre-pass / prior kernels
-  int dense_range;        // QSAE_DENSE_RANGE: 1 = dense epilogue (t_sae) on the range schedule instead of CTA pairs (experiment)
+  int dense_range;        // QSAE_DENSE_RANGE: dense epilogue (t_sae) on the range schedule: 1 = single CTAs, 2 = cta_group::2 pairs (experiments; both slower)
   int dense_flags_mask;   // QSAE_DENSE_FLAGS_MASK: masks dense epilogue outputs (-1 = off; timing experiments)
   int dense_step_fused;   // QSAE_DENSE_STEP_FUSED: 0 = q_sae dense path writes fp32 pre-activations and runs the separate operand kernel
   int dense_fast_streamed;  // QSAE_DENSE_FAST_STREAMED: 1 = fast-mode dense encoder on the streamed-operand kernel (range schedule over CTA pairs)
