@@ -967,7 +967,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
 // the CTA's half (128 latents) of the matching W chunk, the cta_group::2 pair executes M = 256 MMAs (CL = 2 of the
 // kernel above), and the epilogue is the same dense epilogue (accum_mode 0: bias + activation, fp32 / hi / lo).
 // The MMAs of a tile take six times as long as its drain, so the stores hide behind the tensor pipe here.
-constexpr int kSplitStages = 5;
+constexpr int kSplitStages = 6;
 constexpr int kSplitStageBytes = kABytesPerChunk + kBBytesPerStage / 2;   // 32 KiB: x chunk | my half of the W chunk
 __host__ __device__ inline SmemLayout split_smem_layout() {
   SmemLayout L;
