@@ -279,8 +279,10 @@ def run_reference(args, rank):
         "warmup": warmup, "ms_per_step": mean_s * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.cpu_batch, args.k), "cpu_rows_per_step": args.cpu_batch,
-                   "note": "every step is one full forward of the configs[0] batch (4096 rows), the same rows per step as the "
-                           "B200 arm; value = mean over the timed steps, cpu_baseline carries median and best"},
+                   "note": (f"every step is one full forward of {args.cpu_batch} rows"
+                            + (" (the configs[0] batch, the same rows per step as the B200 arm)" if args.cpu_batch == 4096 else
+                               " (a bounded sample: the B200 arm's step has 4096 rows; the metric is a per-token rate)")
+                            + "; value = mean over the timed steps, cpu_baseline carries median and best")},
         "cpu_baseline": dict(cb, value=rate),
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)

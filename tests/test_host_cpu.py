@@ -54,6 +54,25 @@ def test_default_sample_rows_and_its_tuning_switch(monkeypatch):
     assert n.value > 0
 
 
+def test_bench_reference_arm_line_on_cpu():
+    """`bench.py --impl reference` needs no GPU: it times the op-for-op CPU port of the reference forward and prints the
+    contract's JSON line (same metric / unit as the B200 arm, impl = reference, cpu_baseline and a zero-copy e2e block)."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--cpu-batch", "32"], capture_output=True, text=True, timeout=600, cwd=str(ROOT))
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "tokens/s" and line["higher_is_better"] is True
+    assert line["metric"] == "b_sae 512->32768 4-bit fwd tokens/s" and line["value"] > 0 and line["steps"] == 1
+    assert line["config"]["cpu_rows_per_step"] == 32 and "32 rows" in line["config"]["note"]
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "32 rows" in cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
 def test_sass_is_blackwell_native():
     """tcgen05 / TMA / TMEM loads must be present in the built library (no GPU needed)."""
     import shutil
