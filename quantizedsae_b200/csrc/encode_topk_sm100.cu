@@ -967,7 +967,11 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tmap_x,
 // the CTA's half (128 latents) of the matching W chunk, the cta_group::2 pair executes M = 256 MMAs (CL = 2 of the
 // kernel above), and the epilogue is the same dense epilogue (accum_mode 0: bias + activation, fp32 / hi / lo).
 // The MMAs of a tile take six times as long as its drain, so the stores hide behind the tensor pipe here.
+// Six 32 KiB stages next to the 32 KiB store staging area: 231.6 KB, all the shared memory a CTA can have (five stages:
+// 620 us at B = 4096, H = 32768; six: 595 us -- this kernel is bound by the tensor pipe, and ring depth shows).
 constexpr int kSplitStages = 6;
+static_assert(kSplitStages * (kABytesPerChunk + kBBytesPerStage / 2) + 8 * 4096 + 2 * kEncBN * 4 + 8 * (2 * kSplitStages + 8) + 16
+                  <= 227 * 1024, "encode_dense_split_kernel: shared memory budget");
 constexpr int kSplitStageBytes = kABytesPerChunk + kBBytesPerStage / 2;   // 32 KiB: x chunk | my half of the W chunk
 __host__ __device__ inline SmemLayout split_smem_layout() {
   SmemLayout L;
